@@ -1,0 +1,442 @@
+"""Circuit description: the information circom's compiler hands to a code producer.
+
+The Rust compiler cannot run in this environment, so circuits are authored in a
+small Python DSL that plays the role of `compiler/` up to the point where the
+reference calls a code producer (compiler/src/circuit_design/circuit.rs:596
+`Circuit::produce_c`): a list of *template instances* (one per distinct
+template + parameters, like `TemplateCodeInfo`, circuit_design/template.rs:12-31),
+each with
+
+  * its own signals numbered outputs, inputs, intermediates
+    (constraint_generation/src/execution_data/executed_template.rs:442-552),
+  * its sub-components in creation order (CreateCmpBucket),
+  * a straight-line body of field operations over own signals, sub-component
+    signals, constants and temporaries (Compute / Load / Store buckets with all
+    compile-time-bounded loops unrolled), and
+  * its R1CS constraints  A*B - C = 0  (circom_algebra/src/algebra.rs:113-145).
+
+`CircuitDesc.save()` writes the binary ".cb2c" description that the CUDA
+back end (circom_b200/csrc/flatten.cpp) lowers to the flat, levelised
+instruction tape, and that oracle/ consumes independently.
+"""
+from __future__ import annotations
+
+import struct
+from typing import Callable, Dict, List, Optional, Sequence, Tuple, Union
+
+PRIMES = {
+    "bn128": 21888242871839275222246405745257275088548364400416034343698204186575808495617,
+    "bls12381": 52435875175126190479447740508185965837690552500527637822603658699938581184513,
+}
+PRIME_IDS = {"bn128": 0, "bls12381": 1}
+
+# OperatorType (compiler/src/intermediate_representation/compute_bucket.rs:7-34) + moves
+OPS = {
+    "NOP": 0, "MUL": 1, "DIV": 2, "ADD": 3, "SUB": 4, "POW": 5, "IDIV": 6, "MOD": 7,
+    "SHL": 8, "SHR": 9, "LEQ": 10, "GEQ": 11, "LT": 12, "GT": 13, "EQ": 14, "NEQ": 15,
+    "LOR": 16, "LAND": 17, "LNOT": 18, "BOR": 19, "BAND": 20, "BXOR": 21, "BNOT": 22,
+    "NEG": 23, "COPY": 24, "SELECT": 25, "ASSERT": 26, "ASSERT_EQ": 27,
+}
+OP_NAMES = {v: k for k, v in OPS.items()}
+
+# reference kinds
+K_NONE, K_OWN, K_SUB, K_CONST, K_TMP, K_ONE = 0, 1, 2, 3, 4, 5
+Ref = Tuple[int, int, int]  # (kind, sub, idx)
+NONE_REF: Ref = (K_NONE, 0, 0)
+ONE_REF: Ref = (K_ONE, 0, 0)
+
+
+def pack_ref(r: Ref) -> int:
+    return (r[0] << 56) | (r[1] << 32) | r[2]
+
+
+class Expr:
+    """A value inside a template body: where it lives (`ref`) plus, when it is at
+    most quadratic in the signals, its symbolic form (the role of
+    circom_algebra::ArithmeticExpression, algebra.rs:9)."""
+
+    __slots__ = ("t", "ref", "lin", "quad", "const")
+
+    def __init__(self, t: "Template", ref: Ref, lin=None, quad=None, const=None):
+        self.t = t
+        self.ref = ref
+        self.lin = lin      # dict key->coeff ; key = Ref of a signal or ONE_REF
+        self.quad = quad    # (A, B, C) dicts
+        self.const = const  # int if compile-time constant
+
+    # -- coercion -------------------------------------------------------------
+    def _co(self, o) -> "Expr":
+        return o if isinstance(o, Expr) else self.t.const(o)
+
+    # -- arithmetic -----------------------------------------------------------
+    def __add__(self, o): return self.t._add(self, self._co(o))
+    def __radd__(self, o): return self.t._add(self._co(o), self)
+    def __sub__(self, o): return self.t._sub(self, self._co(o))
+    def __rsub__(self, o): return self.t._sub(self._co(o), self)
+    def __mul__(self, o): return self.t._mul(self, self._co(o))
+    def __rmul__(self, o): return self.t._mul(self._co(o), self)
+    def __neg__(self): return self.t._neg(self)
+    def __truediv__(self, o): return self.t._bin("DIV", self, self._co(o))
+    def __floordiv__(self, o): return self.t._bin("IDIV", self, self._co(o))
+    def __mod__(self, o): return self.t._bin("MOD", self, self._co(o))
+    def __pow__(self, o): return self.t._bin("POW", self, self._co(o))
+    def __lshift__(self, o): return self.t._bin("SHL", self, self._co(o))
+    def __rshift__(self, o): return self.t._bin("SHR", self, self._co(o))
+    def __and__(self, o): return self.t._bin("BAND", self, self._co(o))
+    def __or__(self, o): return self.t._bin("BOR", self, self._co(o))
+    def __xor__(self, o): return self.t._bin("BXOR", self, self._co(o))
+    def __invert__(self): return self.t._un("BNOT", self)
+    # comparisons are explicit methods (python's == must stay identity)
+    def lt(self, o): return self.t._bin("LT", self, self._co(o))
+    def gt(self, o): return self.t._bin("GT", self, self._co(o))
+    def leq(self, o): return self.t._bin("LEQ", self, self._co(o))
+    def geq(self, o): return self.t._bin("GEQ", self, self._co(o))
+    def eq(self, o): return self.t._bin("EQ", self, self._co(o))
+    def neq(self, o): return self.t._bin("NEQ", self, self._co(o))
+    def land(self, o): return self.t._bin("LAND", self, self._co(o))
+    def lor(self, o): return self.t._bin("LOR", self, self._co(o))
+    def lnot(self): return self.t._un("LNOT", self)
+
+
+def _lin_add(a: dict, b: dict, q: int, sign: int = 1) -> dict:
+    r = dict(a)
+    for k, v in b.items():
+        nv = (r.get(k, 0) + sign * v) % q
+        if nv:
+            r[k] = nv
+        else:
+            r.pop(k, None)
+    return r
+
+
+def _lin_scale(a: dict, c: int, q: int) -> dict:
+    c %= q
+    if c == 0:
+        return {}
+    return {k: (v * c) % q for k, v in a.items()}
+
+
+class Sub:
+    """Handle on a sub-component inside a template body."""
+
+    def __init__(self, parent: "Template", index: int, tmpl: "Template", name: str):
+        self.parent, self.index, self.tmpl, self.name = parent, index, tmpl, name
+
+    def sig(self, name: str, i: Optional[int] = None):
+        off, size, cat = self.tmpl.sig_info[name]
+        if i is None and size == 1 and not self.tmpl.sig_is_array[name]:
+            return self._mk(name, 0)
+        if i is None:
+            return [self._mk(name, j) for j in range(size)]
+        return self._mk(name, i)
+
+    def _mk(self, name: str, j: int) -> Expr:
+        ref = (K_SUB, self.index, ("name", name, j))  # resolved at finalize
+        return Expr(self.parent, ref, lin={ref: 1})
+
+    def __getitem__(self, key):
+        if isinstance(key, tuple):
+            return self.sig(key[0], key[1])
+        return self.sig(key)
+
+
+class Template:
+    """One template instance (template name + concrete parameters)."""
+
+    def __init__(self, desc: "CircuitDesc", name: str):
+        self.desc = desc
+        self.q = desc.q
+        self.name = name
+        self.sigs: Dict[str, list] = {"out": [], "in": [], "inter": []}  # (name, size)
+        self.sig_info: Dict[str, Tuple[int, int, str]] = {}
+        self.sig_is_array: Dict[str, bool] = {}
+        self.subs: List[Sub] = []
+        self.n_tmp = 0
+        self.ops: List[Tuple[int, Ref, Ref, Ref, Ref]] = []
+        self.constraints: List[Tuple[dict, dict, dict]] = []
+        self.finalized = False
+        self.id = -1
+
+    # -- declarations -----------------------------------------------------------
+    def _decl(self, cat: str, name: str, size: Optional[int]):
+        assert not self.finalized and name not in self.sig_info
+        n = 1 if size is None else size
+        self.sigs[cat].append((name, n))
+        self.sig_info[name] = (-1, n, cat)
+        self.sig_is_array[name] = size is not None
+        mk = lambda j: Expr(self, (K_OWN, 0, ("name", name, j)), lin={(K_OWN, 0, ("name", name, j)): 1})
+        return mk(0) if size is None else [mk(j) for j in range(n)]
+
+    def output(self, name, size=None): return self._decl("out", name, size)
+    def input(self, name, size=None): return self._decl("in", name, size)
+    def signal(self, name, size=None): return self._decl("inter", name, size)
+
+    def component(self, name: str, tmpl: "Template") -> Sub:
+        assert tmpl.finalized, "instantiate finished templates only"
+        s = Sub(self, len(self.subs), tmpl, name)
+        self.subs.append(s)
+        return s
+
+    # -- values -------------------------------------------------------------------
+    def const(self, v: int) -> Expr:
+        v = int(v) % self.q
+        cid = self.desc.const_id(v)
+        return Expr(self, (K_CONST, 0, cid), lin=({ONE_REF: v} if v else {}), const=v)
+
+    def _tmp(self) -> Ref:
+        self.n_tmp += 1
+        return (K_TMP, 0, self.n_tmp - 1)
+
+    def _emit(self, op: str, a: Expr, b: Optional[Expr] = None, c: Optional[Expr] = None) -> Ref:
+        dst = self._tmp()
+        self.ops.append((OPS[op], dst, a.ref, b.ref if b is not None else NONE_REF,
+                         c.ref if c is not None else NONE_REF))
+        return dst
+
+    def _fold(self, op: str, a: Expr, b: Optional[Expr]) -> Optional[Expr]:
+        if a.const is not None and (b is None or b.const is not None):
+            from . import fieldpy
+            v = fieldpy.apply(self.q, OPS[op], a.const, b.const if b is not None else 0)
+            return self.const(v)
+        return None
+
+    def _add(self, a: Expr, b: Expr) -> Expr:
+        f = self._fold("ADD", a, b)
+        if f: return f
+        r = Expr(self, self._emit("ADD", a, b))
+        if a.lin is not None and b.lin is not None:
+            r.lin = _lin_add(a.lin, b.lin, self.q)
+        elif a.quad is not None and b.lin is not None:
+            r.quad = (a.quad[0], a.quad[1], _lin_add(a.quad[2], b.lin, self.q))
+        elif b.quad is not None and a.lin is not None:
+            r.quad = (b.quad[0], b.quad[1], _lin_add(b.quad[2], a.lin, self.q))
+        return r
+
+    def _sub(self, a: Expr, b: Expr) -> Expr:
+        f = self._fold("SUB", a, b)
+        if f: return f
+        r = Expr(self, self._emit("SUB", a, b))
+        if a.lin is not None and b.lin is not None:
+            r.lin = _lin_add(a.lin, b.lin, self.q, -1)
+        elif a.quad is not None and b.lin is not None:
+            r.quad = (a.quad[0], a.quad[1], _lin_add(a.quad[2], b.lin, self.q, -1))
+        elif b.quad is not None and a.lin is not None:
+            nA = _lin_scale(b.quad[0], self.q - 1, self.q)
+            r.quad = (nA, b.quad[1], _lin_add(a.lin, b.quad[2], self.q, -1))
+        return r
+
+    def _mul(self, a: Expr, b: Expr) -> Expr:
+        f = self._fold("MUL", a, b)
+        if f: return f
+        r = Expr(self, self._emit("MUL", a, b))
+        if a.const is not None or b.const is not None:
+            c, x = (a, b) if a.const is not None else (b, a)
+            if x.lin is not None:
+                r.lin = _lin_scale(x.lin, c.const, self.q)
+            elif x.quad is not None:
+                r.quad = (_lin_scale(x.quad[0], c.const, self.q), x.quad[1],
+                          _lin_scale(x.quad[2], c.const, self.q))
+        elif a.lin is not None and b.lin is not None:
+            r.quad = (a.lin, b.lin, {})
+        return r
+
+    def _neg(self, a: Expr) -> Expr:
+        f = self._fold("NEG", a, None)
+        if f: return f
+        r = Expr(self, self._emit("NEG", a))
+        if a.lin is not None:
+            r.lin = _lin_scale(a.lin, self.q - 1, self.q)
+        elif a.quad is not None:
+            r.quad = (_lin_scale(a.quad[0], self.q - 1, self.q), a.quad[1],
+                      _lin_scale(a.quad[2], self.q - 1, self.q))
+        return r
+
+    def _bin(self, op: str, a: Expr, b: Expr) -> Expr:
+        f = self._fold(op, a, b)
+        if f: return f
+        return Expr(self, self._emit(op, a, b))
+
+    def _un(self, op: str, a: Expr) -> Expr:
+        f = self._fold(op, a, None)
+        if f: return f
+        return Expr(self, self._emit(op, a))
+
+    def select(self, cond: Expr, a, b) -> Expr:
+        """`cond ? a : b` (BranchBucket on Fr_isTrue, branch_bucket.rs:100-122); both arms
+        are evaluated, so they must be total (inv(0)=0 is)."""
+        a = a if isinstance(a, Expr) else self.const(a)
+        b = b if isinstance(b, Expr) else self.const(b)
+        return Expr(self, self._emit("SELECT", a, b, cond))
+
+    # -- statements -------------------------------------------------------------------
+    def assign(self, dst: Expr, src) -> None:
+        """`dst <-- src` (StoreBucket, store_bucket.rs:607-646)."""
+        src = src if isinstance(src, Expr) else self.const(src)
+        assert dst.ref[0] in (K_OWN, K_SUB)
+        self.ops.append((OPS["COPY"], dst.ref, src.ref, NONE_REF, NONE_REF))
+
+    def constrain(self, lhs, rhs, emit_assert: bool = True) -> None:
+        """`lhs === rhs`: records the R1CS constraint and (sanity_check >= 1,
+        assert_bucket.rs:70-88) the run-time equality assert."""
+        lhs = lhs if isinstance(lhs, Expr) else self.const(lhs)
+        rhs = rhs if isinstance(rhs, Expr) else self.const(rhs)
+        self._record_constraint(lhs, rhs)
+        if emit_assert:
+            self.ops.append((OPS["ASSERT_EQ"], NONE_REF, lhs.ref, rhs.ref, NONE_REF))
+
+    def _record_constraint(self, lhs: Expr, rhs: Expr) -> None:
+        q = self.q
+        # lhs - rhs == 0  as  A*B - C == 0
+        if lhs.quad is not None and rhs.lin is not None:
+            A, B, C = lhs.quad[0], lhs.quad[1], _lin_add(rhs.lin, lhs.quad[2], q, -1)
+        elif rhs.quad is not None and lhs.lin is not None:
+            A, B, C = rhs.quad[0], rhs.quad[1], _lin_add(lhs.lin, rhs.quad[2], q, -1)
+        elif lhs.lin is not None and rhs.lin is not None:
+            A, B, C = {}, {}, _lin_add(rhs.lin, lhs.lin, q, -1)
+        else:
+            raise ValueError("non quadratic constraint in template %s" % self.name)
+        self.constraints.append((A, B, C))
+
+    def assign_constrained(self, dst: Expr, src) -> None:
+        """`dst <== src`  =  `dst <-- src; dst === src`.  The assert of a freshly stored
+        value is vacuous and is not emitted as a tape op."""
+        src = src if isinstance(src, Expr) else self.const(src)
+        self.assign(dst, src)
+        self._record_constraint(dst, src)
+
+    # -- finalisation -------------------------------------------------------------------
+    def finalize(self) -> "Template":
+        assert not self.finalized
+        off = 0
+        for cat in ("out", "in", "inter"):
+            for name, n in self.sigs[cat]:
+                self.sig_info[name] = (off, n, cat)
+                off += n
+        self.n_out = sum(n for _, n in self.sigs["out"])
+        self.n_in = sum(n for _, n in self.sigs["in"])
+        self.n_inter = sum(n for _, n in self.sigs["inter"])
+        self.n_own = off
+
+        def res(r: Ref) -> Ref:
+            if r[0] == K_OWN and isinstance(r[2], tuple):
+                _, name, j = r[2]
+                o, n, _c = self.sig_info[name]
+                assert 0 <= j < n
+                return (K_OWN, 0, o + j)
+            if r[0] == K_SUB and isinstance(r[2], tuple):
+                _, name, j = r[2]
+                o, n, _c = self.subs[r[1]].tmpl.sig_info[name]
+                assert 0 <= j < n
+                return (K_SUB, r[1], o + j)
+            return r
+
+        self.ops = [(op, res(d), res(a), res(b), res(c)) for op, d, a, b, c in self.ops]
+        self.constraints = [tuple({res(k): v for k, v in lc.items()} for lc in con)
+                            for con in self.constraints]
+        self.total_signals = self.n_own + sum(s.tmpl.total_signals for s in self.subs)
+        self.total_components = 1 + sum(s.tmpl.total_components for s in self.subs)
+        self.finalized = True
+        self.id = len(self.desc.templates)
+        self.desc.templates.append(self)
+        return self
+
+
+class CircuitDesc:
+    def __init__(self, prime: str = "bn128"):
+        self.prime = prime
+        self.q = PRIMES[prime]
+        self.templates: List[Template] = []
+        self.consts: List[int] = []
+        self._cid: Dict[int, int] = {}
+        self._cache: Dict[tuple, Template] = {}
+        self.main: Optional[Template] = None
+        self.name = "circuit"
+
+    def const_id(self, v: int) -> int:
+        v %= self.q
+        i = self._cid.get(v)
+        if i is None:
+            i = len(self.consts)
+            self.consts.append(v)
+            self._cid[v] = i
+        return i
+
+    def template(self, name: str, params: tuple, build: Callable[["Template"], None]) -> Template:
+        """Get-or-build the instance of template `name` for concrete `params`."""
+        key = (name, params)
+        t = self._cache.get(key)
+        if t is None:
+            label = name if not params else "%s_%s" % (name, "_".join(str(p) for p in params))
+            t = Template(self, "".join(ch if ch.isalnum() else "_" for ch in label))
+            build(t)
+            t.finalize()
+            self._cache[key] = t
+        return t
+
+    def set_main(self, t: Template, name: Optional[str] = None) -> "CircuitDesc":
+        self.main = t
+        self.name = name or t.name
+        return self
+
+    # -- sizes ---------------------------------------------------------------------------
+    @property
+    def total_signals(self) -> int:
+        return 1 + self.main.total_signals
+
+    def main_inputs(self) -> List[Tuple[str, int, int]]:
+        """(name, global signal id of first element, size) for the main inputs, in signal order
+        (the content of InputHashMap, c_code_generator.rs:575-603)."""
+        out = []
+        for name, n in self.main.sigs["in"]:
+            off, _, _ = self.main.sig_info[name]
+            out.append((name, 1 + off, n))
+        return out
+
+    def main_outputs(self) -> List[Tuple[str, int, int]]:
+        out = []
+        for name, n in self.main.sigs["out"]:
+            off, _, _ = self.main.sig_info[name]
+            out.append((name, 1 + off, n))
+        return out
+
+    # -- serialisation -------------------------------------------------------------------
+    def to_bytes(self) -> bytes:
+        import numpy as np
+        assert self.main is not None
+        # constraint coefficients go through the constant table as well
+        blobs = []
+        for t in self.templates:
+            nb = t.name.encode()
+            nb += b"\0" * ((-len(nb)) % 4)
+            cons_words = []
+            nterms = 0
+            for con in t.constraints:
+                for lc in con:
+                    cons_words.append(len(lc))
+                    for k in sorted(lc.keys(), key=pack_ref):
+                        cons_words.append(pack_ref(k))
+                        cons_words.append(self.const_id(lc[k]))
+                        nterms += 1
+            hdr = struct.pack("<I", len(t.name.encode())) + nb
+            hdr += struct.pack("<8I", t.n_out, t.n_in, t.n_inter, len(t.subs), t.n_tmp, len(t.ops),
+                               len(t.constraints), nterms)
+            subs = np.array([s.tmpl.id for s in t.subs], dtype="<u4").tobytes()
+            ops = np.array([[op, pack_ref(d), pack_ref(a), pack_ref(b), pack_ref(c)]
+                            for op, d, a, b, c in t.ops], dtype="<u8").reshape(-1, 5).tobytes()
+            cons = np.array(cons_words, dtype="<u8").tobytes()
+            blobs.append(hdr + subs + ops + cons)
+        names = b""
+        ins = self.main_inputs()
+        for name, gid, n in ins:
+            nb = name.encode()
+            names += struct.pack("<I", len(nb)) + nb + b"\0" * ((-len(nb)) % 4)
+            names += struct.pack("<II", gid, n)
+        head = b"CB2C" + struct.pack("<7I", 1, PRIME_IDS[self.prime], len(self.consts), len(self.templates),
+                                     self.main.id, len(ins), 0)
+        consts = b"".join(int(c).to_bytes(32, "little") for c in self.consts)
+        return head + consts + b"".join(blobs) + names
+
+    def save(self, path: str) -> str:
+        with open(path, "wb") as f:
+            f.write(self.to_bytes())
+        return path

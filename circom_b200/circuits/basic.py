@@ -1,0 +1,115 @@
+"""Small circuits: the only ones whose circom source is in the reference tree.
+
+  Multiplier2   mkdocs/docs/getting-started/writing-circuits.md:17-28
+  IsZero        mkdocs/docs/circom-language/basic-operators.md:133-147
+  Num2Bits      mkdocs/docs/circom-language/basic-operators.md:151-170
+  MultiplierN / AndN   mkdocs/docs/more-circuits/more-basic-circuits.md
+plus `AllOps`, a synthetic template that exercises every OperatorType once
+(compiler/src/intermediate_representation/compute_bucket.rs:7-34).
+"""
+from __future__ import annotations
+
+from ..circuit import CircuitDesc, Template
+
+
+def multiplier2(d: CircuitDesc) -> Template:
+    def build(t: Template):
+        a = t.input("a")
+        b = t.input("b")
+        c = t.output("c")
+        t.assign_constrained(c, a * b)
+    return d.template("Multiplier2", (), build)
+
+
+def is_zero(d: CircuitDesc) -> Template:
+    def build(t: Template):
+        i = t.input("in")
+        out = t.output("out")
+        inv = t.signal("inv")
+        # inv <-- in!=0 ? 1/in : 0   (both arms evaluated; 1/0 == 0 in the runtime)
+        t.assign(inv, t.select(i.neq(0), t.const(1) / i, 0))
+        t.assign_constrained(out, -i * inv + 1)
+        t.constrain(i * out, 0)
+    return d.template("IsZero", (), build)
+
+
+def num2bits(d: CircuitDesc, n: int) -> Template:
+    def build(t: Template):
+        i = t.input("in")
+        out = t.output("out", n)
+        lc1 = t.const(0)
+        e2 = 1
+        for k in range(n):
+            t.assign(out[k], (i >> k) & 1)
+            t.constrain(out[k] * (out[k] - 1), 0)
+            lc1 = lc1 + out[k] * e2
+            e2 = e2 + e2
+        t.constrain(lc1, i)
+    return d.template("Num2Bits", (n,), build)
+
+
+def bits2num(d: CircuitDesc, n: int) -> Template:
+    def build(t: Template):
+        i = t.input("in", n)
+        out = t.output("out")
+        lc1 = t.const(0)
+        e2 = 1
+        for k in range(n):
+            lc1 = lc1 + i[k] * e2
+            e2 = e2 + e2
+        t.assign_constrained(out, lc1)
+    return d.template("Bits2Num", (n,), build)
+
+
+def less_than(d: CircuitDesc, n: int) -> Template:
+    """circomlib-style LessThan(n): Num2Bits(n+1) of in[0] + 2^n - in[1]."""
+    n2b = num2bits(d, n + 1)
+
+    def build(t: Template):
+        i = t.input("in", 2)
+        out = t.output("out")
+        c = t.component("n2b", n2b)
+        t.assign_constrained(c["in"], i[0] + (1 << n) - i[1])
+        t.assign_constrained(out, 1 - c["out", n])
+    return d.template("LessThan", (n,), build)
+
+
+def multiplier_n(d: CircuitDesc, n: int) -> Template:
+    m2 = multiplier2(d)
+
+    def build(t: Template):
+        i = t.input("in", n)
+        out = t.output("out")
+        comps = [t.component("comp[%d]" % k, m2) for k in range(n - 1)]
+        t.assign_constrained(comps[0]["a"], i[0])
+        t.assign_constrained(comps[0]["b"], i[1])
+        for k in range(n - 2):
+            t.assign_constrained(comps[k + 1]["a"], comps[k]["c"])
+            t.assign_constrained(comps[k + 1]["b"], i[k + 2])
+        t.assign_constrained(out, comps[n - 2]["c"])
+    return d.template("MultiplierN", (n,), build)
+
+
+def all_ops(d: CircuitDesc) -> Template:
+    """One use of every runtime operator; outputs are `<--` hints so that no constraint
+    restricts the input domain (division by zero in `\\` and `%` is guarded)."""
+    iz = is_zero(d)
+
+    def build(t: Template):
+        a = t.input("a")
+        b = t.input("b")
+        outs = t.output("o", 27)
+        vals = [
+            a * b, a / b, a + b, a - b, a ** (b & 15),
+            a // t.select(b.eq(0), 1, b), a % t.select(b.eq(0), 1, b),
+            a << (b & 255), a >> (b & 255), a << b, a >> b,
+            a.leq(b), a.geq(b), a.lt(b), a.gt(b), a.eq(b), a.neq(b),
+            a.lor(b), a.land(b), a.lnot(), a | b, a & b, a ^ b, ~a, -a,
+        ]
+        for k, v in enumerate(vals):
+            t.assign(outs[k], v)
+        z = t.component("iz", iz)
+        t.assign_constrained(z["in"], a - b)
+        t.assign_constrained(outs[25], z["out"])
+        t.assign_constrained(outs[26], a * b + a)
+    return d.template("AllOps", (), build)

@@ -1,0 +1,725 @@
+// C ABI (include/circom_b200.h) over the lowering (flatten.cpp), the formats (formats.cpp) and the
+// sm_100a kernels (kernels.cuh).  There is no CPU execution path: every compute entry point
+// returns CW_ENODEV when no CUDA device is present.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/circom_b200.h"
+#include "kernels.cuh"
+#include "tape.h"
+
+using namespace cw;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CU(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(CW_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                 \
+    } while (0)
+
+FrParams make_dev_params(const FieldParams &F) {
+    FrParams p;
+    memset(&p, 0, sizeof(p));
+    auto split = [](u32 *dst, const U256 &v) {
+        for (int i = 0; i < 4; ++i) {
+            dst[2 * i] = (u32)v.v[i];
+            dst[2 * i + 1] = (u32)(v.v[i] >> 32);
+        }
+    };
+    split(p.q, F.q);
+    split(p.half, F.half);
+    split(p.r1, F.r1);
+    split(p.r2, F.r2);
+    U256 two = u256_from_u64(2), qm2;
+    u256_sub(qm2, F.q, two);
+    split(p.qm2, qm2);
+    p.np32 = F.np32;
+    p.qbits = F.qbits;
+    p.top_mask = (F.qbits - 224 >= 32) ? 0xFFFFFFFFu : ((1u << (F.qbits - 224)) - 1u);
+    return p;
+}
+
+std::mutex g_dev_mutex;
+std::map<int, bool> g_dev_ready;
+
+int ensure_device(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(CW_ENODEV, "no CUDA device available (circom_b200 has no CPU execution path)");
+    }
+    if (device < 0 || device >= n) return fail(CW_EINVAL, "bad device index");
+    CU(cudaSetDevice(device));
+    std::lock_guard<std::mutex> lk(g_dev_mutex);
+    if (!g_dev_ready[device]) {
+        FrParams h[2] = {make_dev_params(make_field(0)), make_dev_params(make_field(1))};
+        CU(cudaMemcpyToSymbol(c_fr, h, sizeof(h)));
+        g_dev_ready[device] = true;
+    }
+    return CW_OK;
+}
+
+struct DevTape {
+    uint4 *ops = nullptr;
+    u32 *level_start = nullptr;
+    uint4 *consts = nullptr;
+    u32 *witness_slot = nullptr;
+};
+struct DevR1cs {
+    unsigned long long *row_ptr = nullptr;
+    u32 *col = nullptr, *coef = nullptr;
+    uint4 *dictM = nullptr;
+    unsigned char *kind = nullptr;
+};
+
+template <class T>
+int upload(T **dst, const void *src, size_t bytes) {
+    CU(cudaMalloc((void **)dst, bytes ? bytes : 16));
+    if (bytes) CU(cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    return CW_OK;
+}
+
+int env_int(const char *name, int dflt) {
+    const char *s = getenv(name);
+    return s && *s ? atoi(s) : dflt;
+}
+
+}  // namespace
+
+struct cw_circuit {
+    Tape tape;
+    mutable std::mutex mu;
+    mutable std::map<int, DevTape> dev;
+};
+
+struct cw_r1cs {
+    R1csData data;
+    FieldParams F;
+    std::mutex mu;
+    std::map<int, DevR1cs> dev;
+};
+
+struct cw_batch {
+    const cw_circuit *c = nullptr;
+    int device = 0;
+    u32 batch = 0, batch_padded = 0, bt_log2 = 0, threads = 256;
+    cudaStream_t stream = nullptr;
+    uint4 *slots = nullptr, *inputs_d = nullptr, *witness_d = nullptr;
+    u32 *first_assert_d = nullptr;
+    int *err_d = nullptr;
+    DevTape dt;
+    std::vector<uint64_t> host_inputs;  // [batch][n_inputs][4]
+    std::vector<uint8_t> assigned;      // [batch][n_inputs]
+    std::vector<u32> remaining;         // [batch]
+    bool host_inputs_dirty = false;
+    bool inputs_on_device = false;
+    bool ran = false;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+};
+
+static int get_dev_tape(const cw_circuit *c, int device, DevTape &out) {
+    std::lock_guard<std::mutex> lk(c->mu);
+    auto it = c->dev.find(device);
+    if (it != c->dev.end()) {
+        out = it->second;
+        return CW_OK;
+    }
+    const Tape &t = c->tape;
+    DevTape d;
+    int rc;
+    if ((rc = upload(&d.ops, t.ops.data(), t.ops.size() * 4))) return rc;
+    if ((rc = upload(&d.level_start, t.level_start.data(), t.level_start.size() * 4))) return rc;
+    if ((rc = upload(&d.consts, t.consts.data(), t.consts.size() * 32))) return rc;
+    if ((rc = upload(&d.witness_slot, t.witness_slot.data(), t.witness_slot.size() * 4))) return rc;
+    c->dev[device] = d;
+    out = d;
+    return CW_OK;
+}
+
+extern "C" {
+
+int cw_version(void) { return 100; }
+const char *cw_last_error(void) { return g_err.c_str(); }
+int cw_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int cw_circuit_load_mem(const void *data, size_t len, uint32_t flags, cw_circuit **out) {
+    if (!data || !out) return fail(CW_EINVAL, "null argument");
+    cw_circuit *c = new cw_circuit();
+    try {
+        lower_circuit((const uint8_t *)data, len, flags, c->tape);
+    } catch (const std::exception &e) {
+        delete c;
+        return fail(CW_EFORMAT, e.what());
+    }
+    *out = c;
+    return CW_OK;
+}
+
+int cw_circuit_load(const char *path, uint32_t flags, cw_circuit **out) {
+    if (!path || !out) return fail(CW_EINVAL, "null argument");
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(CW_EIO, std::string("cannot open ") + path);
+    fseek(f, 0, SEEK_END);
+    long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<uint8_t> buf(sz);
+    size_t rd = sz ? fread(buf.data(), 1, sz, f) : 0;
+    fclose(f);
+    if ((long)rd != sz) return fail(CW_EIO, "short read");
+    return cw_circuit_load_mem(buf.data(), buf.size(), flags, out);
+}
+
+void cw_circuit_destroy(cw_circuit *c) {
+    if (!c) return;
+    for (auto &kv : c->dev) {
+        cudaSetDevice(kv.first);
+        cudaFree(kv.second.ops);
+        cudaFree(kv.second.level_start);
+        cudaFree(kv.second.consts);
+        cudaFree(kv.second.witness_slot);
+    }
+    delete c;
+}
+
+int cw_circuit_stats(const cw_circuit *c, cw_stats *o) {
+    if (!c || !o) return fail(CW_EINVAL, "null argument");
+    const Tape &t = c->tape;
+    memset(o, 0, sizeof(*o));
+    o->n_signals = t.n_signals;
+    o->n_witness = t.n_witness;
+    o->n_inputs = t.n_inputs;
+    o->n_outputs = t.n_outputs;
+    o->n_components = t.n_components;
+    o->n_constants = t.consts.size();
+    o->n_ir_ops = t.n_ir_ops;
+    o->n_tape_ops = t.n_tape_ops();
+    o->n_slots = t.n_slots;
+    o->n_levels = t.n_levels();
+    o->n_constraints = t.r1cs.n_constraints;
+    o->n_nnz = t.r1cs.col.size();
+    o->n_mul_ops = t.n_mul_ops;
+    o->n_conv_ops = t.n_conv_ops;
+    o->max_level_width = t.max_level_width;
+    return CW_OK;
+}
+
+int cw_circuit_prime(const cw_circuit *c, int *prime_id, uint64_t q[4]) {
+    if (!c) return fail(CW_EINVAL, "null argument");
+    if (prime_id) *prime_id = c->tape.F.prime_id;
+    if (q) memcpy(q, c->tape.F.q.v, 32);
+    return CW_OK;
+}
+
+uint32_t cw_get_main_input_signal_start(const cw_circuit *c) { return (uint32_t)c->tape.n_outputs + 1; }
+uint32_t cw_get_main_input_signal_no(const cw_circuit *c) { return (uint32_t)c->tape.n_inputs; }
+uint32_t cw_get_total_signal_no(const cw_circuit *c) { return (uint32_t)c->tape.n_signals; }
+uint32_t cw_get_number_of_components(const cw_circuit *c) { return (uint32_t)c->tape.n_components; }
+uint32_t cw_get_size_of_input_hashmap(const cw_circuit *c) { return (uint32_t)c->tape.hashmap.size(); }
+uint32_t cw_get_size_of_witness(const cw_circuit *c) { return (uint32_t)c->tape.n_witness; }
+uint32_t cw_get_size_of_constants(const cw_circuit *c) { return (uint32_t)c->tape.consts.size(); }
+
+uint64_t cw_fnv1a(const char *name) { return fnv1a(name, strlen(name)); }
+
+// getInputSignalHashPosition (calcwit.cpp:51-69)
+static int hash_pos(const Tape &t, uint64_t h, size_t *pos) {
+    size_t n = t.hashmap.size();
+    size_t p = (size_t)(h % n);
+    if (t.hashmap[p].hash != h || t.hashmap[p].signalid == 0) {
+        size_t ini = p;
+        p = (p + 1) % n;
+        while (p != ini) {
+            if (t.hashmap[p].hash == h && t.hashmap[p].signalid != 0) {
+                *pos = p;
+                return CW_OK;
+            }
+            if (t.hashmap[p].signalid == 0) return fail(CW_ENOTFOUND, "Signal not found");
+            p = (p + 1) % n;
+        }
+        return fail(CW_ENOTFOUND, "Signals not found");
+    }
+    *pos = p;
+    return CW_OK;
+}
+
+int cw_get_input_signal_size(const cw_circuit *c, uint64_t h, uint64_t *size) {
+    size_t p;
+    int rc = hash_pos(c->tape, h, &p);
+    if (rc) return rc;
+    *size = c->tape.hashmap[p].signalsize;
+    return CW_OK;
+}
+int cw_get_input_signal_id(const cw_circuit *c, uint64_t h, uint64_t *id) {
+    size_t p;
+    int rc = hash_pos(c->tape, h, &p);
+    if (rc) return rc;
+    *id = c->tape.hashmap[p].signalid;
+    return CW_OK;
+}
+
+int cw_circuit_tape(const cw_circuit *c, uint32_t *ops, uint32_t *level_start, uint32_t *witness_slot) {
+    const Tape &t = c->tape;
+    if (ops) memcpy(ops, t.ops.data(), t.ops.size() * 4);
+    if (level_start) memcpy(level_start, t.level_start.data(), t.level_start.size() * 4);
+    if (witness_slot) memcpy(witness_slot, t.witness_slot.data(), t.witness_slot.size() * 4);
+    return CW_OK;
+}
+
+int cw_circuit_write_dat(const cw_circuit *c, const char *path) {
+    try {
+        write_dat(c->tape, path);
+    } catch (const std::exception &e) {
+        return fail(CW_EIO, e.what());
+    }
+    return CW_OK;
+}
+
+// ---- batch ------------------------------------------------------------------------------------
+int cw_batch_create(const cw_circuit *c, uint32_t batch, int device, cw_batch **out) {
+    if (!c || !out || batch == 0) return fail(CW_EINVAL, "bad argument");
+    if (c->tape.flags & CW_FLAG_HOST_ONLY) return fail(CW_ESTATE, "circuit was loaded with CW_FLAG_HOST_ONLY");
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    const Tape &t = c->tape;
+    cw_batch *b = new cw_batch();
+    b->c = c;
+    b->device = device;
+    b->batch = batch;
+    // tile size: keep at least ~4 CTAs per SM in flight before widening tiles for coalescing
+    int bt = env_int("CW_BT_LOG2", -1);
+    if (bt < 0) {
+        bt = 0;
+        while (bt < 5 && (batch >> (bt + 1)) >= 148u * 4u) ++bt;
+    }
+    if (bt > 5) bt = 5;
+    b->bt_log2 = (u32)bt;
+    u32 btn = 1u << bt;
+    b->batch_padded = (batch + btn - 1) / btn * btn;
+    int th = env_int("CW_THREADS", 0);
+    if (th <= 0) {
+        // enough threads for a typical level: average width x tile, clamped to [64, 512]
+        uint64_t avg = t.n_levels() ? (t.n_tape_ops() / t.n_levels() + 1) * btn : 64;
+        th = 64;
+        while (th < 512 && (uint64_t)th < avg) th <<= 1;
+    }
+    th = (th + 31) / 32 * 32;
+    if (th > 1024) th = 1024;
+    b->threads = (u32)th;
+    size_t slot_bytes = (size_t)b->batch_padded * t.n_slots * 32;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    size_t need = slot_bytes + (size_t)batch * (t.n_witness + t.n_inputs) * 32 + (64u << 20);
+    if (need > free_b) {
+        delete b;
+        return fail(CW_ECUDA, "batch needs " + std::to_string(need >> 20) + " MiB of device memory, " +
+                                  std::to_string(free_b >> 20) + " MiB free");
+    }
+    if ((rc = get_dev_tape(c, device, b->dt))) { delete b; return rc; }
+    CU(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    CU(cudaMalloc((void **)&b->slots, slot_bytes));
+    CU(cudaMalloc((void **)&b->inputs_d, std::max<size_t>((size_t)batch * t.n_inputs * 32, 32)));
+    CU(cudaMalloc((void **)&b->witness_d, (size_t)batch * t.n_witness * 32));
+    CU(cudaMalloc((void **)&b->first_assert_d, (size_t)batch * 4));
+    CU(cudaMalloc((void **)&b->err_d, (size_t)batch * 4));
+    for (auto &e : b->ev) CU(cudaEventCreate(&e));
+    b->host_inputs.assign((size_t)batch * t.n_inputs * 4, 0);
+    b->assigned.assign((size_t)batch * t.n_inputs, 0);
+    b->remaining.assign(batch, (u32)t.n_inputs);
+    *out = b;
+    return CW_OK;
+}
+
+void cw_batch_destroy(cw_batch *b) {
+    if (!b) return;
+    cudaSetDevice(b->device);
+    cudaFree(b->slots);
+    cudaFree(b->inputs_d);
+    cudaFree(b->witness_d);
+    cudaFree(b->first_assert_d);
+    cudaFree(b->err_d);
+    for (auto &e : b->ev)
+        if (e) cudaEventDestroy(e);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+}
+
+int cw_batch_set_input(cw_batch *b, uint32_t inst, uint64_t h, uint32_t idx, const uint64_t limbs[4]) {
+    if (!b || inst >= b->batch) return fail(CW_EINVAL, "bad instance");
+    const Tape &t = b->c->tape;
+    if (b->remaining[inst] == 0) return fail(CW_ESTATE, "No more signals to be assigned");
+    size_t p;
+    int rc = hash_pos(t, h, &p);
+    if (rc) return rc;
+    if (idx >= t.hashmap[p].signalsize) return fail(CW_EINVAL, "Input signal array access exceeds the size");
+    uint64_t si = t.hashmap[p].signalid + idx;
+    uint64_t k = si - (t.n_outputs + 1);
+    if (b->assigned[(size_t)inst * t.n_inputs + k]) return fail(CW_ESTATE, "Signal assigned twice: " + std::to_string(si));
+    U256 v;
+    memcpy(v.v, limbs, 32);
+    if (!(v < t.F.q)) return fail(CW_EINVAL, "input value not reduced modulo the field prime");
+    memcpy(&b->host_inputs[((size_t)inst * t.n_inputs + k) * 4], limbs, 32);
+    b->assigned[(size_t)inst * t.n_inputs + k] = 1;
+    b->remaining[inst]--;
+    b->host_inputs_dirty = true;
+    return CW_OK;
+}
+
+int cw_batch_remaining_inputs(const cw_batch *b, uint32_t inst, uint32_t *rem) {
+    if (!b || inst >= b->batch) return fail(CW_EINVAL, "bad instance");
+    *rem = b->remaining[inst];
+    return CW_OK;
+}
+
+int cw_batch_set_inputs(cw_batch *b, const uint64_t *inputs, int is_device_ptr) {
+    if (!b || !inputs) return fail(CW_EINVAL, "null argument");
+    const Tape &t = b->c->tape;
+    CU(cudaSetDevice(b->device));
+    size_t bytes = (size_t)b->batch * t.n_inputs * 32;
+    CU(cudaMemcpyAsync(b->inputs_d, inputs, bytes, is_device_ptr ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                       b->stream));
+    std::fill(b->remaining.begin(), b->remaining.end(), 0u);
+    b->host_inputs_dirty = false;
+    b->inputs_on_device = true;
+    return CW_OK;
+}
+
+int cw_batch_run(cw_batch *b) {
+    if (!b) return fail(CW_EINVAL, "null argument");
+    const Tape &t = b->c->tape;
+    CU(cudaSetDevice(b->device));
+    if (b->host_inputs_dirty || !b->inputs_on_device) {
+        for (u32 i = 0; i < b->batch; ++i)
+            if (b->remaining[i])
+                return fail(CW_ESTATE, "Not all inputs have been set. Only " +
+                                           std::to_string(t.n_inputs - b->remaining[i]) + " out of " +
+                                           std::to_string(t.n_inputs) + " (instance " + std::to_string(i) + ")");
+        CU(cudaMemcpyAsync(b->inputs_d, b->host_inputs.data(), b->host_inputs.size() * 8, cudaMemcpyHostToDevice,
+                           b->stream));
+        b->host_inputs_dirty = false;
+        b->inputs_on_device = true;
+    }
+    TapeDev tp;
+    tp.ops = b->dt.ops;
+    tp.level_start = b->dt.level_start;
+    tp.consts = b->dt.consts;
+    tp.n_levels = (u32)t.n_levels();
+    tp.n_slots = t.n_slots;
+    tp.n_pre = t.n_pre;
+    tp.n_inputs = (u32)t.n_inputs;
+    CU(cudaMemsetAsync(b->first_assert_d, 0xFF, (size_t)b->batch * 4, b->stream));
+    CU(cudaMemsetAsync(b->err_d, 0, (size_t)b->batch * 4, b->stream));
+    CU(cudaEventRecord(b->ev[0], b->stream));
+    {
+        size_t total = (size_t)b->batch_padded * (t.n_inputs + 1);
+        u32 grid = (u32)std::min<size_t>((total + 255) / 256, 148 * 8);
+        stage_inputs_kernel<<<grid, 256, 0, b->stream>>>(tp, b->inputs_d, b->slots, b->batch, b->batch_padded, b->bt_log2);
+    }
+    u32 tiles = b->batch_padded >> b->bt_log2;
+    if (tp.n_levels) {
+        if (t.F.prime_id == 0)
+            tape_exec_kernel<0><<<tiles, b->threads, 0, b->stream>>>(tp, b->slots, b->bt_log2, b->first_assert_d, b->err_d, b->batch);
+        else
+            tape_exec_kernel<1><<<tiles, b->threads, 0, b->stream>>>(tp, b->slots, b->bt_log2, b->first_assert_d, b->err_d, b->batch);
+    }
+    CU(cudaEventRecord(b->ev[1], b->stream));
+    {
+        size_t total = (size_t)tiles * t.n_witness << b->bt_log2;
+        u32 grid = (u32)std::min<size_t>((total + 255) / 256, 148 * 16);
+        if (t.F.prime_id == 0)
+            witness_gather_kernel<0><<<grid, 256, 0, b->stream>>>(b->slots, b->dt.witness_slot, b->witness_d, t.n_slots, (u32)t.n_witness, b->batch, b->bt_log2);
+        else
+            witness_gather_kernel<1><<<grid, 256, 0, b->stream>>>(b->slots, b->dt.witness_slot, b->witness_d, t.n_slots, (u32)t.n_witness, b->batch, b->bt_log2);
+    }
+    CU(cudaEventRecord(b->ev[2], b->stream));
+    CU(cudaGetLastError());
+    b->ran = true;
+    return CW_OK;
+}
+
+int cw_batch_sync(cw_batch *b) {
+    if (!b) return fail(CW_EINVAL, "null argument");
+    CU(cudaSetDevice(b->device));
+    CU(cudaStreamSynchronize(b->stream));
+    return CW_OK;
+}
+
+int cw_batch_status(cw_batch *b, int32_t *status) {
+    if (!b || !status) return fail(CW_EINVAL, "null argument");
+    if (!b->ran) return fail(CW_ESTATE, "batch has not been run");
+    CU(cudaSetDevice(b->device));
+    std::vector<u32> fa(b->batch);
+    std::vector<int> er(b->batch);
+    CU(cudaMemcpyAsync(fa.data(), b->first_assert_d, (size_t)b->batch * 4, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(er.data(), b->err_d, (size_t)b->batch * 4, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    for (u32 i = 0; i < b->batch; ++i) {
+        if (er[i]) status[i] = -1;  // division by zero: the reference process aborts inside GMP
+        else status[i] = fa[i] == 0xFFFFFFFFu ? 0 : (int32_t)(fa[i] + 1);
+    }
+    return CW_OK;
+}
+
+int cw_batch_get_witness(cw_batch *b, uint64_t *out) {
+    if (!b || !out) return fail(CW_EINVAL, "null argument");
+    if (!b->ran) return fail(CW_ESTATE, "batch has not been run");
+    CU(cudaSetDevice(b->device));
+    CU(cudaMemcpyAsync(out, b->witness_d, (size_t)b->batch * b->c->tape.n_witness * 32, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    return CW_OK;
+}
+
+int cw_batch_witness_device(cw_batch *b, const uint64_t **dptr) {
+    if (!b || !dptr) return fail(CW_EINVAL, "null argument");
+    *dptr = (const uint64_t *)b->witness_d;
+    return CW_OK;
+}
+
+void *cw_batch_stream(cw_batch *b) { return b ? (void *)b->stream : nullptr; }
+
+int cw_batch_last_ms(cw_batch *b, float *exec_ms, float *gather_ms) {
+    if (!b || !b->ran) return fail(CW_ESTATE, "batch has not been run");
+    CU(cudaSetDevice(b->device));
+    CU(cudaEventSynchronize(b->ev[2]));
+    if (exec_ms) CU(cudaEventElapsedTime(exec_ms, b->ev[0], b->ev[1]));
+    if (gather_ms) CU(cudaEventElapsedTime(gather_ms, b->ev[1], b->ev[2]));
+    return CW_OK;
+}
+
+int cw_batch_wtns_bytes(cw_batch *b, uint32_t inst, uint8_t *out, size_t cap, size_t *len) {
+    if (!b || inst >= b->batch) return fail(CW_EINVAL, "bad instance");
+    if (!b->ran) return fail(CW_ESTATE, "batch has not been run");
+    const Tape &t = b->c->tape;
+    size_t need = 76 + 32 * (size_t)t.n_witness;
+    if (len) *len = need;
+    if (!out) return CW_OK;
+    if (cap < need) return fail(CW_EINVAL, "buffer too small");
+    CU(cudaSetDevice(b->device));
+    std::vector<uint64_t> w((size_t)t.n_witness * 4);
+    CU(cudaMemcpyAsync(w.data(), b->witness_d + (size_t)inst * t.n_witness * 2, (size_t)t.n_witness * 32,
+                       cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    std::vector<uint8_t> bytes = wtns_bytes(t.F, w.data(), t.n_witness);
+    memcpy(out, bytes.data(), need);
+    return CW_OK;
+}
+
+int cw_batch_write_wtns(cw_batch *b, uint32_t inst, const char *path) {
+    size_t need = 0;
+    int rc = cw_batch_wtns_bytes(b, inst, nullptr, 0, &need);
+    if (rc) return rc;
+    std::vector<uint8_t> buf(need);
+    if ((rc = cw_batch_wtns_bytes(b, inst, buf.data(), need, &need))) return rc;
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(CW_EIO, std::string("cannot open ") + path);
+    size_t wr = fwrite(buf.data(), 1, need, f);
+    fclose(f);
+    return wr == need ? CW_OK : fail(CW_EIO, "short write");
+}
+
+// ---- R1CS -------------------------------------------------------------------------------------
+int cw_r1cs_from_circuit(const cw_circuit *c, cw_r1cs **out) {
+    if (!c || !out) return fail(CW_EINVAL, "null argument");
+    cw_r1cs *r = new cw_r1cs();
+    r->data = c->tape.r1cs;
+    r->F = c->tape.F;
+    *out = r;
+    return CW_OK;
+}
+int cw_r1cs_load(const char *path, cw_r1cs **out) {
+    if (!path || !out) return fail(CW_EINVAL, "null argument");
+    cw_r1cs *r = new cw_r1cs();
+    try {
+        read_r1cs(path, r->data);
+    } catch (const std::exception &e) {
+        delete r;
+        return fail(CW_EFORMAT, e.what());
+    }
+    r->F = make_field(r->data.prime_id);
+    *out = r;
+    return CW_OK;
+}
+int cw_r1cs_write(const cw_r1cs *r, const char *path, uint32_t n_pub_out, uint32_t n_pub_in, uint32_t n_prv_in) {
+    if (!r || !path) return fail(CW_EINVAL, "null argument");
+    try {
+        R1csData d = r->data;
+        d.n_pub_out = n_pub_out;
+        d.n_pub_in = n_pub_in;
+        d.n_prv_in = n_prv_in;
+        write_r1cs(d, r->F, path);
+    } catch (const std::exception &e) {
+        return fail(CW_EIO, e.what());
+    }
+    return CW_OK;
+}
+int cw_r1cs_info(const cw_r1cs *r, uint64_t *n_wires, uint64_t *n_constraints, uint64_t *nnz, int *prime_id) {
+    if (!r) return fail(CW_EINVAL, "null argument");
+    if (n_wires) *n_wires = r->data.n_wires;
+    if (n_constraints) *n_constraints = r->data.n_constraints;
+    if (nnz) *nnz = r->data.col.size();
+    if (prime_id) *prime_id = r->data.prime_id;
+    return CW_OK;
+}
+void cw_r1cs_destroy(cw_r1cs *r) {
+    if (!r) return;
+    for (auto &kv : r->dev) {
+        cudaSetDevice(kv.first);
+        cudaFree(kv.second.row_ptr);
+        cudaFree(kv.second.col);
+        cudaFree(kv.second.coef);
+        cudaFree(kv.second.dictM);
+        cudaFree(kv.second.kind);
+    }
+    delete r;
+}
+
+int cw_r1cs_check(cw_r1cs *r, const uint64_t *witness, int is_device_ptr, uint32_t batch, int device,
+                  int64_t *first_bad, float *kernel_ms) {
+    if (!r || !witness || !first_bad || batch == 0) return fail(CW_EINVAL, "bad argument");
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    DevR1cs d;
+    {
+        std::lock_guard<std::mutex> lk(r->mu);
+        auto it = r->dev.find(device);
+        if (it == r->dev.end()) {
+            const R1csData &R = r->data;
+            std::vector<U256> dm(R.dict.size());
+            std::vector<unsigned char> kind(R.dict.size());
+            U256 one = u256_from_u64(1), m1;
+            u256_sub(m1, r->F.q, one);
+            for (size_t i = 0; i < R.dict.size(); ++i) {
+                dm[i] = r->F.to_mont(R.dict[i]);
+                kind[i] = R.dict[i] == one ? 1 : (R.dict[i] == m1 ? 2 : 0);
+            }
+            if ((rc = upload(&d.row_ptr, R.row_ptr.data(), R.row_ptr.size() * 8))) return rc;
+            if ((rc = upload(&d.col, R.col.data(), R.col.size() * 4))) return rc;
+            if ((rc = upload(&d.coef, R.coef.data(), R.coef.size() * 4))) return rc;
+            if ((rc = upload(&d.dictM, dm.data(), dm.size() * 32))) return rc;
+            if ((rc = upload(&d.kind, kind.data(), kind.size()))) return rc;
+            r->dev[device] = d;
+        } else d = it->second;
+    }
+    const R1csData &R = r->data;
+    const uint4 *w_d = (const uint4 *)witness;
+    uint4 *tmp = nullptr;
+    if (!is_device_ptr) {
+        CU(cudaMalloc((void **)&tmp, (size_t)batch * R.n_wires * 32));
+        CU(cudaMemcpy(tmp, witness, (size_t)batch * R.n_wires * 32, cudaMemcpyHostToDevice));
+        w_d = tmp;
+    }
+    unsigned long long *fb_d = nullptr;
+    CU(cudaMalloc((void **)&fb_d, (size_t)batch * 8));
+    CU(cudaMemset(fb_d, 0xFF, (size_t)batch * 8));
+    R1csDev rd;
+    rd.row_ptr = d.row_ptr;
+    rd.col = d.col;
+    rd.coef = d.coef;
+    rd.dictM = d.dictM;
+    rd.kind = d.kind;
+    rd.n_constraints = (u32)R.n_constraints;
+    rd.n_wires = (u32)R.n_wires;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    dim3 grid((u32)std::min<uint64_t>((R.n_constraints + 255) / 256, 148 * 8), std::min<u32>(batch, 65535u));
+    if (grid.x == 0) grid.x = 1;
+    CU(cudaEventRecord(e0));
+    if (R.prime_id == 0) r1cs_check_kernel<0><<<grid, 256>>>(rd, w_d, batch, fb_d);
+    else r1cs_check_kernel<1><<<grid, 256>>>(rd, w_d, batch, fb_d);
+    CU(cudaEventRecord(e1));
+    CU(cudaGetLastError());
+    std::vector<unsigned long long> fb(batch);
+    CU(cudaMemcpy(fb.data(), fb_d, (size_t)batch * 8, cudaMemcpyDeviceToHost));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    if (kernel_ms) *kernel_ms = ms;
+    for (u32 i = 0; i < batch; ++i) first_bad[i] = fb[i] == ~0ull ? -1 : (int64_t)fb[i];
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(fb_d);
+    if (tmp) cudaFree(tmp);
+    return CW_OK;
+}
+
+// ---- field batch ops ---------------------------------------------------------------------------
+int cw_fr_batch_op(int prime_id, int op, const uint64_t *a, const uint64_t *b, const uint64_t *c, uint64_t *r,
+                   size_t n, int device) {
+    if (!a || !r || prime_id < 0 || prime_id > 1) return fail(CW_EINVAL, "bad argument");
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    uint4 *A = nullptr, *B = nullptr, *C = nullptr, *Rr = nullptr;
+    int *err = nullptr;
+    if ((rc = upload(&A, a, n * 32))) return rc;
+    if (b && (rc = upload(&B, b, n * 32))) return rc;
+    if (c && (rc = upload(&C, c, n * 32))) return rc;
+    CU(cudaMalloc((void **)&Rr, n * 32 + 32));
+    CU(cudaMalloc((void **)&err, 4));
+    CU(cudaMemset(err, 0, 4));
+    u32 grid = (u32)std::min<size_t>((n + 127) / 128, 148 * 16);
+    if (!grid) grid = 1;
+    if (prime_id == 0) fr_batch_op_kernel<0><<<grid, 128>>>(op, A, B, C, Rr, n, err);
+    else fr_batch_op_kernel<1><<<grid, 128>>>(op, A, B, C, Rr, n, err);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(r, Rr, n * 32, cudaMemcpyDeviceToHost));
+    int herr = 0;
+    CU(cudaMemcpy(&herr, err, 4, cudaMemcpyDeviceToHost));
+    cudaFree(A);
+    cudaFree(B);
+    cudaFree(C);
+    cudaFree(Rr);
+    cudaFree(err);
+    return herr ? fail(CW_EINVAL, "division by zero in batch op") : CW_OK;
+}
+
+int cw_fr_mul_bench(int prime_id, size_t n, int iters, int device, float *ms) {
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    std::vector<uint64_t> h(n * 4);
+    uint64_t s = 0x9E3779B97F4A7C15ull;
+    for (auto &x : h) {
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+        x = s;
+    }
+    for (size_t i = 0; i < n; ++i) h[4 * i + 3] &= 0x0FFFFFFFFFFFFFFFull;
+    uint4 *d = nullptr;
+    if ((rc = upload(&d, h.data(), n * 32))) return rc;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    u32 grid = (u32)((n + 255) / 256);
+    for (int rep = 0; rep < 2; ++rep) {
+        CU(cudaEventRecord(e0));
+        if (prime_id == 0) fr_mul_bench_kernel<0><<<grid, 256>>>(d, n, iters);
+        else fr_mul_bench_kernel<1><<<grid, 256>>>(d, n, iters);
+        CU(cudaEventRecord(e1));
+        CU(cudaEventSynchronize(e1));
+    }
+    CU(cudaEventElapsedTime(ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    return CW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,576 @@
+// Lowering: circuit description (.cb2c) -> flat, levelised instruction tape.
+//
+// This is the job a `cuda_elements` code producer does in place of
+// Circuit::produce_c (compiler/src/circuit_design/circuit.rs:596-612): instead of
+// printing one C++ function per template instance, the component tree is
+// instantiated once and its field operations are emitted as a single SSA tape.
+//
+//   1. symbolic execution in the reference's run order: a sub-component body is
+//      expanded when its last input is stored (store_bucket.rs:660-734,
+//      template.rs:274-278), so the emission order is a valid schedule;
+//   2. moves are removed by aliasing (Fr_copy of store_bucket.rs:607-646 becomes
+//      slot renaming);
+//   3. static representation inference: each value lives in canonical or
+//      Montgomery form, decided here, replacing the reference's run-time
+//      tri-state dispatch (generic/fr.cpp:416-533); a Montgomery product of a
+//      Montgomery and a canonical operand is canonical for free, exactly the
+//      mixed case of Fr_mul (generic/fr.cpp:449-465); conversions are cached;
+//   4. dead values are dropped, ops are levelised (wavefronts), sorted by
+//      (level, opcode) and slots renumbered so that the destination of tape
+//      op i is slot n_pre + i.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <unordered_map>
+
+#include "../../include/circom_b200.h"
+#include "tape.h"
+
+namespace cw {
+
+uint64_t fnv1a(const char *s, size_t n) {  // calcwit.cpp:17-24
+    uint64_t h = 0xCBF29CE484222325ULL;
+    for (size_t i = 0; i < n; ++i) {
+        h ^= (uint64_t)(int64_t)(signed char)s[i];  // `u64(c)` of a (signed) char
+        h *= 0x100000001B3ULL;
+    }
+    return h;
+}
+
+namespace {
+
+enum { K_NONE = 0, K_OWN = 1, K_SUB = 2, K_CONST = 3, K_TMP = 4, K_ONE = 5 };
+enum Form { FC = 0, FM = 1 };
+
+struct IrOp {
+    uint32_t op;
+    uint64_t d, a, b, c;
+};
+struct Term {
+    uint64_t ref;
+    uint32_t cid;
+};
+struct Tmpl {
+    std::string name;
+    uint32_t n_out, n_in, n_inter, n_tmp, n_own;
+    std::vector<uint32_t> subs;
+    std::vector<IrOp> ops;
+    std::vector<uint32_t> lc_len;  // 3 per constraint
+    std::vector<Term> terms;
+    uint64_t total_signals = 0, total_components = 0;
+};
+
+inline int rk(uint64_t r) { return (int)(r >> 56); }
+inline uint32_t rsub(uint64_t r) { return (uint32_t)((r >> 32) & 0xFFFFFF); }
+inline uint32_t ridx(uint64_t r) { return (uint32_t)r; }
+
+struct Reader {
+    const uint8_t *p, *end;
+    template <class T>
+    T get() {
+        if (p + sizeof(T) > end) throw std::runtime_error("cb2c: truncated");
+        T v;
+        memcpy(&v, p, sizeof(T));
+        p += sizeof(T);
+        return v;
+    }
+    const uint8_t *bytes(size_t n) {
+        if (p + n > end) throw std::runtime_error("cb2c: truncated");
+        const uint8_t *r = p;
+        p += n;
+        return r;
+    }
+    std::string str() {
+        uint32_t n = get<uint32_t>();
+        const uint8_t *b = bytes((n + 3) & ~3u);
+        return std::string((const char *)b, n);
+    }
+};
+
+struct Val {
+    uint32_t slot[2] = {NO_SLOT, NO_SLOT};  // provisional slot holding the canonical / Montgomery image
+    int32_t cid = -1;                       // IR constant id if this value is a compile-time constant
+};
+
+struct Lowerer {
+    Tape &T;
+    const FieldParams &F;
+    uint32_t flags;
+    std::vector<Tmpl> tm;
+    std::vector<U256> ir_consts;
+    std::vector<Val> vals;
+    std::vector<int32_t> sig_vid;
+    // provisional tape
+    std::vector<uint32_t> pops;  // 4 words per op
+    std::vector<uint32_t> plevel;
+    std::vector<uint32_t> slot_level;  // per provisional slot
+    // constant table (raw patterns)
+    std::vector<U256> consts;
+    std::unordered_map<std::string, uint32_t> const_index;
+    uint32_t n_pre = 0;
+    uint64_t n_ir_ops = 0, n_conv = 0, n_asserts = 0;
+    int32_t vid_one = -1;
+
+    Lowerer(Tape &t, uint32_t fl) : T(t), F(t.F), flags(fl) {}
+
+    uint32_t raw_const(const U256 &v) {
+        std::string key((const char *)v.v, 32);
+        auto it = const_index.find(key);
+        if (it != const_index.end()) return it->second;
+        uint32_t i = (uint32_t)consts.size();
+        consts.push_back(v);
+        const_index.emplace(std::move(key), i);
+        return i;
+    }
+    uint32_t const_operand(int32_t cid, Form f) {
+        const U256 &v = ir_consts[cid];
+        return OPERAND_CONST | raw_const(f == FM ? F.to_mont(v) : v);
+    }
+    uint32_t operand_level(uint32_t o) const { return (o & OPERAND_CONST) || o == NO_SLOT ? 0 : slot_level[o]; }
+
+    uint32_t emit(uint32_t opcode, uint32_t a, uint32_t b = NO_SLOT, uint32_t c = NO_SLOT, bool c_is_imm = false) {
+        uint32_t slot = n_pre + (uint32_t)(pops.size() / 4);
+        pops.push_back(opcode);
+        pops.push_back(a);
+        pops.push_back(b);
+        pops.push_back(c);
+        uint32_t l = std::max(operand_level(a), operand_level(b));
+        if (!c_is_imm) l = std::max(l, operand_level(c));
+        slot_level.push_back(l + 1);
+        return slot;
+    }
+    int32_t new_val(uint32_t slot, Form f) {
+        Val v;
+        v.slot[f] = slot;
+        vals.push_back(v);
+        return (int32_t)vals.size() - 1;
+    }
+    bool has(int32_t vid, Form f) const { return vals[vid].cid >= 0 || vals[vid].slot[f] != NO_SLOT; }
+    bool is_const(int32_t vid) const { return vals[vid].cid >= 0; }
+    // operand holding `vid` in form `f`, converting (once) if necessary
+    uint32_t need(int32_t vid, Form f) {
+        Val &v = vals[vid];
+        if (v.cid >= 0) return const_operand(v.cid, f);
+        if (v.slot[f] != NO_SLOT) return v.slot[f];
+        uint32_t src = v.slot[1 - f];
+        if (src == NO_SLOT) throw std::runtime_error("lowering: value without representation");
+        // to Montgomery: MontMul(x, R^2) = x*R ; to canonical: MontMul(xR, 1) = x
+        U256 k = (f == FM) ? F.r2 : u256_from_u64(1);
+        uint32_t s = emit(CW_OP_MUL, src, OPERAND_CONST | raw_const(k));
+        ++n_conv;
+        vals[vid].slot[f] = s;
+        return s;
+    }
+    Form any_form(int32_t vid) const {
+        const Val &v = vals[vid];
+        if (v.cid >= 0) return FC;
+        return v.slot[FM] != NO_SLOT ? FM : FC;
+    }
+    // common form for an operation that needs both operands in the same representation
+    Form common_form(int32_t x, int32_t y) const {
+        bool xc = is_const(x), yc = is_const(y);
+        if (xc && yc) return FC;
+        if (xc) return any_form(y);
+        if (yc) return any_form(x);
+        if (has(x, FM) && has(y, FM)) return FM;
+        if (has(x, FC) && has(y, FC)) return FC;
+        return FM;
+    }
+
+    int32_t lower_op(uint32_t op, int32_t a, int32_t b, int32_t c) {
+        switch (op) {
+            case CW_OP_ADD:
+            case CW_OP_SUB: {
+                Form f = common_form(a, b);
+                return new_val(emit(op, need(a, f), need(b, f)), f);
+            }
+            case CW_OP_NEG: {
+                Form f = any_form(a);
+                return new_val(emit(op, need(a, f)), f);
+            }
+            case CW_OP_MUL: {
+                if (is_const(a) || is_const(b)) {
+                    int32_t k = is_const(a) ? a : b, x = is_const(a) ? b : a;
+                    if (is_const(x)) return new_val(emit(op, need(k, FM), need(x, FC)), FC);
+                    Form f = any_form(x);
+                    return new_val(emit(op, need(x, f), need(k, FM)), f);
+                }
+                if (has(a, FM) && has(b, FM)) return new_val(emit(op, need(a, FM), need(b, FM)), FM);
+                if (has(a, FM)) return new_val(emit(op, need(a, FM), need(b, FC)), FC);
+                if (has(b, FM)) return new_val(emit(op, need(a, FC), need(b, FM)), FC);
+                return new_val(emit(op, need(a, FM), need(b, FC)), FC);  // converts a once
+            }
+            case CW_OP_DIV: {
+                uint32_t inv = emit(CW_OP_INV, need(b, FM));
+                int32_t iv = new_val(inv, FM);
+                Form f = is_const(a) ? FC : any_form(a);
+                return new_val(emit(CW_OP_MUL, need(a, f), need(iv, FM)), f);
+            }
+            case CW_OP_POW:
+                return new_val(emit(op, need(a, FM), need(b, FC)), FM);
+            case CW_OP_IDIV: case CW_OP_MOD: case CW_OP_SHL: case CW_OP_SHR:
+            case CW_OP_BOR: case CW_OP_BAND: case CW_OP_BXOR:
+            case CW_OP_LEQ: case CW_OP_GEQ: case CW_OP_LT: case CW_OP_GT:
+                return new_val(emit(op, need(a, FC), need(b, FC)), FC);
+            case CW_OP_BNOT:
+                return new_val(emit(op, need(a, FC)), FC);
+            case CW_OP_EQ:
+            case CW_OP_NEQ: {
+                Form f = common_form(a, b);
+                return new_val(emit(op, need(a, f), need(b, f)), FC);
+            }
+            case CW_OP_LOR:
+            case CW_OP_LAND:
+                return new_val(emit(op, need(a, any_form(a)), need(b, any_form(b))), FC);
+            case CW_OP_LNOT:
+                return new_val(emit(op, need(a, any_form(a))), FC);
+            case CW_OP_SELECT: {
+                Form f = common_form(a, b);
+                return new_val(emit(op, need(a, f), need(b, f), need(c, any_form(c))), f);
+            }
+            default:
+                throw std::runtime_error("lowering: unsupported opcode " + std::to_string(op));
+        }
+    }
+
+    // ---- symbolic execution of the component tree -------------------------------------------
+    struct Comp {
+        uint32_t tid;
+        uint64_t start;
+        uint32_t counter;
+        bool ran = false;
+    };
+
+    void run(Comp &c) {
+        const Tmpl &t = tm[c.tid];
+        c.ran = true;
+        std::vector<int32_t> tmp(t.n_tmp, -1);
+        std::vector<Comp> subs(t.subs.size());
+        uint64_t off = c.start + t.n_own;
+        for (size_t i = 0; i < t.subs.size(); ++i) {
+            const Tmpl &st = tm[t.subs[i]];
+            subs[i].tid = t.subs[i];
+            subs[i].start = off;
+            subs[i].counter = st.n_in;
+            off += st.total_signals;
+            if (st.n_in == 0) run(subs[i]);
+        }
+        auto load = [&](uint64_t r) -> int32_t {
+            int32_t v = -1;
+            switch (rk(r)) {
+                case K_OWN: v = sig_vid[c.start + ridx(r)]; break;
+                case K_SUB: v = sig_vid[subs[rsub(r)].start + ridx(r)]; break;
+                case K_CONST: v = (int32_t)ridx(r); break;  // vids [0, n_consts) are the constants
+                case K_TMP: v = tmp[ridx(r)]; break;
+                case K_ONE: v = vid_one; break;
+                default: return -1;
+            }
+            if (v < 0) throw std::runtime_error("lowering: read of unassigned value in template " + t.name);
+            return v;
+        };
+        for (const IrOp &o : t.ops) {
+            ++n_ir_ops;
+            if (o.op == CW_OP_ASSERT_EQ || o.op == CW_OP_ASSERT) {
+                uint32_t id = (uint32_t)n_asserts++;
+                if (flags & CW_FLAG_NO_ASSERTS) continue;
+                if (o.op == CW_OP_ASSERT_EQ) {
+                    int32_t a = load(o.a), b = load(o.b);
+                    Form f = common_form(a, b);
+                    emit(CW_OP_ASSERT_EQ, need(a, f), need(b, f), id, true);
+                } else {
+                    int32_t a = load(o.a);
+                    emit(CW_OP_ASSERT, need(a, any_form(a)), NO_SLOT, id, true);
+                }
+                continue;
+            }
+            int32_t v;
+            if (o.op == CW_OP_COPY) {
+                v = load(o.a);  // a move is an alias
+            } else {
+                int32_t a = load(o.a), b = rk(o.b) ? load(o.b) : -1, cc = rk(o.c) ? load(o.c) : -1;
+                v = lower_op(o.op, a, b, cc);
+            }
+            switch (rk(o.d)) {
+                case K_TMP: tmp[ridx(o.d)] = v; break;
+                case K_OWN: {
+                    uint64_t g = c.start + ridx(o.d);
+                    if (sig_vid[g] >= 0) throw std::runtime_error("lowering: signal assigned twice in " + t.name);
+                    sig_vid[g] = v;
+                    break;
+                }
+                case K_SUB: {
+                    Comp &sc = subs[rsub(o.d)];
+                    const Tmpl &st = tm[sc.tid];
+                    uint64_t g = sc.start + ridx(o.d);
+                    if (sig_vid[g] >= 0) throw std::runtime_error("lowering: signal assigned twice in " + t.name);
+                    sig_vid[g] = v;
+                    uint32_t li = ridx(o.d);
+                    if (li >= st.n_out && li < st.n_out + st.n_in) {
+                        if (--sc.counter == 0) run(sc);
+                    }
+                    break;
+                }
+                default: throw std::runtime_error("lowering: bad destination");
+            }
+        }
+        for (Comp &sc : subs)
+            if (!sc.ran) throw std::runtime_error("lowering: sub-component of " + t.name + " never received all its inputs");
+    }
+
+    void collect_constraints(uint32_t tid, uint64_t start) {
+        const Tmpl &t = tm[tid];
+        std::vector<uint64_t> offs(t.subs.size());
+        uint64_t off = start + t.n_own;
+        for (size_t i = 0; i < t.subs.size(); ++i) {
+            offs[i] = off;
+            off += tm[t.subs[i]].total_signals;
+        }
+        R1csData &R = T.r1cs;
+        size_t ti = 0;
+        std::vector<std::pair<uint32_t, uint32_t>> row;
+        for (size_t k = 0; k < t.lc_len.size(); ++k) {
+            row.clear();
+            for (uint32_t j = 0; j < t.lc_len[k]; ++j, ++ti) {
+                const Term &tr = t.terms[ti];
+                uint64_t g;
+                switch (rk(tr.ref)) {
+                    case K_OWN: g = start + ridx(tr.ref); break;
+                    case K_SUB: g = offs[rsub(tr.ref)] + ridx(tr.ref); break;
+                    case K_ONE: g = 0; break;
+                    default: throw std::runtime_error("cb2c: bad constraint reference");
+                }
+                row.emplace_back((uint32_t)g, tr.cid);
+            }
+            std::sort(row.begin(), row.end());  // wire ids ascending (r1cs_writer.rs:59-60)
+            for (auto &e : row) {
+                R.col.push_back(e.first);
+                R.coef.push_back(e.second);
+            }
+            R.row_ptr.push_back(R.col.size());
+        }
+        for (size_t i = 0; i < t.subs.size(); ++i) collect_constraints(t.subs[i], offs[i]);
+    }
+
+    void parse(const uint8_t *data, size_t len) {
+        Reader r{data, data + len};
+        if (memcmp(r.bytes(4), "CB2C", 4)) throw std::runtime_error("cb2c: bad magic");
+        uint32_t version = r.get<uint32_t>();
+        if (version != 1) throw std::runtime_error("cb2c: unsupported version");
+        uint32_t prime = r.get<uint32_t>(), n_consts = r.get<uint32_t>(), n_tm = r.get<uint32_t>();
+        main_tid = r.get<uint32_t>();
+        uint32_t n_names = r.get<uint32_t>();
+        r.get<uint32_t>();
+        if (prime > 1) throw std::runtime_error("cb2c: unknown prime");
+        T.F = make_field((int)prime);
+        ir_consts.resize(n_consts);
+        for (auto &c : ir_consts) {
+            memcpy(c.v, r.bytes(32), 32);
+            if (!(c < T.F.q)) throw std::runtime_error("cb2c: constant not reduced");
+        }
+        tm.resize(n_tm);
+        for (uint32_t i = 0; i < n_tm; ++i) {
+            Tmpl &t = tm[i];
+            t.name = r.str();
+            t.n_out = r.get<uint32_t>();
+            t.n_in = r.get<uint32_t>();
+            t.n_inter = r.get<uint32_t>();
+            uint32_t n_sub = r.get<uint32_t>();
+            t.n_tmp = r.get<uint32_t>();
+            uint32_t n_ops = r.get<uint32_t>(), n_cons = r.get<uint32_t>(), n_terms = r.get<uint32_t>();
+            t.n_own = t.n_out + t.n_in + t.n_inter;
+            t.subs.resize(n_sub);
+            for (auto &s : t.subs) {
+                s = r.get<uint32_t>();
+                if (s >= i) throw std::runtime_error("cb2c: sub-component template must precede its user");
+            }
+            t.ops.resize(n_ops);
+            for (auto &o : t.ops) {
+                o.op = (uint32_t)r.get<uint64_t>();
+                o.d = r.get<uint64_t>();
+                o.a = r.get<uint64_t>();
+                o.b = r.get<uint64_t>();
+                o.c = r.get<uint64_t>();
+            }
+            t.lc_len.reserve(n_cons * 3);
+            t.terms.reserve(n_terms);
+            for (uint32_t k = 0; k < n_cons * 3; ++k) {
+                uint32_t n = (uint32_t)r.get<uint64_t>();
+                t.lc_len.push_back(n);
+                for (uint32_t j = 0; j < n; ++j) {
+                    Term tr;
+                    tr.ref = r.get<uint64_t>();
+                    tr.cid = (uint32_t)r.get<uint64_t>();
+                    if (tr.cid >= n_consts) throw std::runtime_error("cb2c: bad coefficient id");
+                    t.terms.push_back(tr);
+                }
+            }
+            t.total_signals = t.n_own;
+            t.total_components = 1;
+            for (auto s : t.subs) {
+                t.total_signals += tm[s].total_signals;
+                t.total_components += tm[s].total_components;
+            }
+        }
+        if (main_tid >= n_tm) throw std::runtime_error("cb2c: bad main template");
+        for (uint32_t i = 0; i < n_names; ++i) {
+            InputInfo in;
+            in.name = r.str();
+            in.signal_id = r.get<uint32_t>();
+            in.size = r.get<uint32_t>();
+            in.hash = fnv1a(in.name.data(), in.name.size());
+            T.inputs.push_back(in);
+        }
+    }
+    uint32_t main_tid = 0;
+
+    void lower() {
+        const Tmpl &M = tm[main_tid];
+        uint64_t S = 1 + M.total_signals;
+        if (S >= 0x7FFFFFFFull) throw std::runtime_error("circuit too large");
+        T.n_signals = S;
+        T.n_inputs = M.n_in;
+        T.n_outputs = M.n_out;
+        T.n_components = M.total_components;
+        n_pre = 1 + M.n_in;
+        // constants are vids [0, n_consts)
+        vals.resize(ir_consts.size());
+        for (size_t i = 0; i < ir_consts.size(); ++i) vals[i].cid = (int32_t)i;
+        sig_vid.assign(S, -1);
+        slot_level.assign(n_pre, 0);
+        vid_one = new_val(0, FC);  // slot 0: the constant-one signal (calcwit.cpp:34)
+        sig_vid[0] = vid_one;
+        for (uint32_t i = 0; i < M.n_in; ++i) sig_vid[1 + M.n_out + i] = new_val(1 + i, FC);
+        Comp mc;
+        mc.tid = main_tid;
+        mc.start = 1;
+        mc.counter = 0;
+        run(mc);
+
+        // witness = every signal, in signal order (O0-style witness list, dag/src/witness_producer.rs:3-19)
+        uint64_t W = S;
+        T.n_witness = W;
+        std::vector<uint32_t> wslot(W);
+        size_t n_prov = pops.size() / 4;
+        std::vector<uint8_t> live(n_pre + n_prov, 0);
+        for (uint64_t i = 0; i < W; ++i) {
+            int32_t v = sig_vid[i];
+            if (v < 0) throw std::runtime_error("lowering: signal " + std::to_string(i) + " is never assigned");
+            if (vals[v].cid >= 0) {
+                // a signal that is a compile-time constant: materialise it once
+                uint32_t s = emit(CW_OP_COPY, const_operand(vals[v].cid, FC));
+                vals[v].cid = -1;
+                vals[v].slot[FC] = s;
+                live.push_back(0);
+                ++n_prov;
+            }
+            if (vals[v].slot[FC] != NO_SLOT) wslot[i] = vals[v].slot[FC];
+            else wslot[i] = vals[v].slot[FM] | WSLOT_MONT;
+            live[wslot[i] & ~WSLOT_MONT] = 1;
+        }
+        // dead-value elimination (reverse sweep; provisional order is topological)
+        for (size_t i = n_prov; i-- > 0;) {
+            uint32_t *o = &pops[i * 4];
+            bool is_assert = o[0] == CW_OP_ASSERT || o[0] == CW_OP_ASSERT_EQ;
+            if (!is_assert && !live[n_pre + i]) continue;
+            live[n_pre + i] = 1;
+            for (int k = 1; k <= 3; ++k) {
+                if (k == 3 && is_assert) break;
+                if (o[k] != NO_SLOT && !(o[k] & OPERAND_CONST)) live[o[k]] = 1;
+            }
+        }
+        // counting sort by (level, opcode)
+        uint32_t max_level = 0;
+        size_t n_live = 0;
+        for (size_t i = 0; i < n_prov; ++i)
+            if (live[n_pre + i]) {
+                ++n_live;
+                max_level = std::max(max_level, slot_level[n_pre + i]);
+            }
+        std::vector<uint32_t> order;
+        order.reserve(n_live);
+        for (size_t i = 0; i < n_prov; ++i)
+            if (live[n_pre + i]) order.push_back((uint32_t)i);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+            uint32_t lx = slot_level[n_pre + x], ly = slot_level[n_pre + y];
+            if (lx != ly) return lx < ly;
+            return pops[x * 4] < pops[y * 4];
+        });
+        std::vector<uint32_t> remap(n_pre + n_prov, NO_SLOT);
+        for (uint32_t i = 0; i < n_pre; ++i) remap[i] = i;
+        for (size_t r = 0; r < order.size(); ++r) remap[n_pre + order[r]] = n_pre + (uint32_t)r;
+        T.ops.resize(n_live * 4);
+        T.level_start.assign(max_level + 1, 0);
+        T.n_mul_ops = 0;
+        for (size_t r = 0; r < order.size(); ++r) {
+            const uint32_t *o = &pops[(size_t)order[r] * 4];
+            uint32_t *d = &T.ops[r * 4];
+            bool is_assert = o[0] == CW_OP_ASSERT || o[0] == CW_OP_ASSERT_EQ;
+            d[0] = o[0];
+            for (int k = 1; k <= 3; ++k) {
+                if (k == 3 && is_assert) d[k] = o[k];          // immediate: IR assert number
+                else if (o[k] == NO_SLOT) d[k] = OPERAND_CONST;  // unused operand: constant 0 (never read for its value)
+                else if (o[k] & OPERAND_CONST) d[k] = o[k];
+                else d[k] = remap[o[k]];
+            }
+            if (o[0] == CW_OP_MUL) ++T.n_mul_ops;
+            T.level_start[slot_level[n_pre + order[r]]]++;  // count per level (levels start at 1)
+        }
+        // prefix sums: level_start[l-1] = first op of level l
+        {
+            std::vector<uint32_t> ls(max_level + 1, 0);
+            uint32_t acc = 0;
+            uint64_t widest = 0;
+            for (uint32_t l = 1; l <= max_level; ++l) {
+                ls[l - 1] = acc;
+                widest = std::max<uint64_t>(widest, T.level_start[l]);
+                acc += T.level_start[l];
+            }
+            ls[max_level] = acc;
+            T.level_start.swap(ls);
+            T.max_level_width = widest;
+        }
+        T.witness_slot.resize(W);
+        for (uint64_t i = 0; i < W; ++i) T.witness_slot[i] = remap[wslot[i] & ~WSLOT_MONT] | (wslot[i] & WSLOT_MONT);
+        T.consts = consts;
+        if (T.consts.empty()) T.consts.push_back(u256_from_u64(0));
+        T.n_pre = n_pre;
+        T.n_slots = n_pre + (uint32_t)n_live;
+        T.n_ir_ops = n_ir_ops;
+        T.n_conv_ops = n_conv;
+        T.n_asserts = n_asserts;
+        T.flags = flags;
+
+        // input hash map, laid out as the reference's .dat (c_code_generator.rs:575-603)
+        uint64_t hs = 256;
+        while (hs < T.inputs.size()) hs <<= 1;  // get_input_hash_map_entry_size (c_elements/mod.rs:167-169)
+        T.hashmap.assign(hs, HashEntry{0, 0, 0});
+        for (const InputInfo &in : T.inputs) {
+            uint64_t p = in.hash % hs;
+            while (T.hashmap[p].signalid != 0) p = (p + 1) % hs;
+            T.hashmap[p] = HashEntry{in.hash, in.signal_id, in.size};
+        }
+
+        // R1CS in witness numbering (identity map here)
+        R1csData &R = T.r1cs;
+        R.prime_id = F.prime_id;
+        R.n_wires = W;
+        R.row_ptr.push_back(0);
+        R.dict = ir_consts;
+        collect_constraints(main_tid, 1);
+        R.n_constraints = (R.row_ptr.size() - 1) / 3;
+        R.n_pub_out = (uint32_t)M.n_out;
+        R.n_pub_in = 0;
+        R.n_prv_in = (uint32_t)M.n_in;
+    }
+};
+
+}  // namespace
+
+void lower_circuit(const uint8_t *data, size_t len, uint32_t flags, Tape &out) {
+    Lowerer L(out, flags);
+    L.parse(data, len);
+    L.lower();
+}
+
+}  // namespace cw

@@ -1,0 +1,424 @@
+// Device field library: 256-bit prime-field arithmetic on 8 x u32 limbs for BN254 / BLS12-381 Fr.
+//
+// GPU counterpart of the reference's Fr_* runtime (c_elements/<prime>/fr.asm,
+// c_elements/generic/fr.cpp); value semantics are those of SURVEY.md Appendix C.
+// Everything here is `__host__ __device__` plain C++ so that tests/ can compile the very
+// same source for the CPU and check it against the oracle without a GPU; the PTX fast
+// path of the Montgomery product is selected only under __CUDA_ARCH__.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define CW_HD __host__ __device__ __forceinline__
+#else
+#define CW_HD inline
+#endif
+
+namespace cw {
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+struct FrParams {
+    u32 q[8];     // modulus
+    u32 half[8];  // q >> 1  (generic/fr.cpp:9)
+    u32 r1[8];    // 2^256 mod q : Montgomery image of 1
+    u32 r2[8];    // 2^512 mod q
+    u32 qm2[8];   // q - 2 (Fermat exponent)
+    u32 np32;     // -q^-1 mod 2^32
+    u32 qbits;    // 254 / 255
+    u32 top_mask; // lboMask on limb 7 (generic/fr.cpp:16)
+    u32 pad;
+};
+
+// ---- raw 256-bit helpers -----------------------------------------------------------------------
+CW_HD u32 u256_add(u32 *r, const u32 *a, const u32 *b) {  // returns carry
+    u64 c = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        c += (u64)a[i] + b[i];
+        r[i] = (u32)c;
+        c >>= 32;
+    }
+    return (u32)c;
+}
+CW_HD u32 u256_sub(u32 *r, const u32 *a, const u32 *b) {  // returns borrow
+    u32 br = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        u64 t = (u64)a[i] - b[i] - br;
+        r[i] = (u32)t;
+        br = (u32)(t >> 63);
+    }
+    return br;
+}
+CW_HD bool u256_geq(const u32 *a, const u32 *b) {  // a >= b
+    u32 t[8];
+    return u256_sub(t, a, b) == 0;
+}
+CW_HD bool u256_gt(const u32 *a, const u32 *b) { return !u256_geq(b, a); }
+CW_HD bool u256_is_zero(const u32 *a) {
+    u32 o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o |= a[i];
+    return o == 0;
+}
+CW_HD bool u256_eq(const u32 *a, const u32 *b) {
+    u32 o = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o |= a[i] ^ b[i];
+    return o == 0;
+}
+CW_HD void u256_set(u32 *r, const u32 *a) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = a[i];
+}
+CW_HD void u256_set_u32(u32 *r, u32 v) {
+    r[0] = v;
+#pragma unroll
+    for (int i = 1; i < 8; ++i) r[i] = 0;
+}
+// r = r >= q ? r - q : r
+CW_HD void fr_cond_sub(u32 *r, const FrParams &P) {
+    u32 t[8];
+    u32 br = u256_sub(t, r, P.q);
+    if (!br) u256_set(r, t);
+}
+
+// ---- add / sub / neg (generic/fr.cpp:19-86) ----------------------------------------------------
+CW_HD void fr_add(u32 *r, const u32 *a, const u32 *b, const FrParams &P) {
+    u32 s[8], t[8];
+    u32 c = u256_add(s, a, b);
+    u32 br = u256_sub(t, s, P.q);
+    bool use_t = c || !br;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = use_t ? t[i] : s[i];
+}
+CW_HD void fr_sub(u32 *r, const u32 *a, const u32 *b, const FrParams &P) {
+    u32 s[8], t[8];
+    u32 br = u256_sub(s, a, b);
+    u256_add(t, s, P.q);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = br ? t[i] : s[i];
+}
+CW_HD void fr_neg(u32 *r, const u32 *a, const FrParams &P) {
+    u32 t[8];
+    u256_sub(t, P.q, a);
+    bool z = u256_is_zero(a);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = z ? 0u : t[i];
+}
+
+// ---- Montgomery product a*b*2^-256 mod q, CIOS (generic/fr.cpp:110-164; bn128/fr.asm:365-531) --
+CW_HD void fr_mont_mul_c(u32 *r, const u32 *a, const u32 *b, const FrParams &P) {
+    u32 t[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        u64 c = 0;
+        u32 bi = b[i];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            c += (u64)a[j] * bi + t[j];
+            t[j] = (u32)c;
+            c >>= 32;
+        }
+        c += t[8];
+        t[8] = (u32)c;
+        u32 t9 = (u32)(c >> 32);
+        u32 m = t[0] * P.np32;
+        c = (u64)m * P.q[0] + t[0];
+        c >>= 32;
+#pragma unroll
+        for (int j = 1; j < 8; ++j) {
+            c += (u64)m * P.q[j] + t[j];
+            t[j - 1] = (u32)c;
+            c >>= 32;
+        }
+        c += t[8];
+        t[7] = (u32)c;
+        t[8] = t9 + (u32)(c >> 32);
+    }
+    // both moduli are < 2^255, so the CIOS result is < 2q < 2^256 and t[8] == 0
+    u32 d[8];
+    u32 br = u256_sub(d, t, P.q);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = br ? t[i] : d[i];
+}
+
+#if defined(__CUDA_ARCH__)
+// PTX carry-chain version: operand-scanning CIOS with mad.lo.cc / madc.hi.cc chains on
+// the integer (IMAD) pipe; even/odd columns are accumulated separately so that each chain
+// is a pure carry chain (no 64-bit adds).  Same result as fr_mont_mul_c.
+__device__ __forceinline__ void fr_mont_mul_ptx(u32 *r, const u32 *a, const u32 *b, const FrParams &P);
+#endif
+
+CW_HD void fr_mont_mul(u32 *r, const u32 *a, const u32 *b, const FrParams &P) {
+    fr_mont_mul_c(r, a, b, P);
+}
+
+CW_HD void fr_to_mont(u32 *r, const u32 *a, const FrParams &P) { fr_mont_mul(r, a, P.r2, P); }
+CW_HD void fr_from_mont(u32 *r, const u32 *a, const FrParams &P) {
+    u32 one[8];
+    u256_set_u32(one, 1);
+    fr_mont_mul(r, a, one, P);
+}
+
+// ---- exponentiation in the Montgomery domain: base = xR, exponent canonical -> x^e R -------------
+// Fr_pow (generic/fr.cpp:2877-2893) / Fr_inv via Fermat (x^(q-2); 0 -> 0 like the pinned
+// behaviour of mpz_invert's ignored failure, generic/fr.cpp:2895-2906).
+CW_HD void fr_pow_mont(u32 *r, const u32 *base, const u32 *e_in, const FrParams &P) {
+    // left-to-right square-and-multiply; the exponent is consumed by shifting a register copy so
+    // that no array is indexed dynamically (dynamic indexing would push it to local memory)
+    u32 acc[8], e[8];
+    u256_set(acc, P.r1);
+    u256_set(e, e_in);
+    bool started = false;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int i = 0; i < 256; ++i) {
+        u32 bit = e[7] >> 31;
+#pragma unroll
+        for (int j = 7; j > 0; --j) e[j] = (e[j] << 1) | (e[j - 1] >> 31);
+        e[0] <<= 1;
+        if (started) {
+            u32 t[8];
+            fr_mont_mul(t, acc, acc, P);
+            u256_set(acc, t);
+        }
+        if (bit) {
+            if (started) {
+                u32 t[8];
+                fr_mont_mul(t, acc, base, P);
+                u256_set(acc, t);
+            } else {
+                u256_set(acc, base);
+                started = true;
+            }
+        }
+    }
+    u256_set(r, acc);
+}
+CW_HD void fr_inv_mont(u32 *r, const u32 *a, const FrParams &P) { fr_pow_mont(r, a, P.qm2, P); }
+
+// ---- shifts on the canonical integer (generic/fr.cpp:329-364,1995-2027,2157-2307) ----------------
+// barrel shifters with static register indices only
+CW_HD void u256_shl(u32 *r, const u32 *a, u32 k) {  // 0 <= k < 256, result mod 2^256
+    u32 t[8];
+    u256_set(t, a);
+    if (k & 128) {
+#pragma unroll
+        for (int i = 7; i >= 0; --i) t[i] = i >= 4 ? t[i - 4] : 0;
+    }
+    if (k & 64) {
+#pragma unroll
+        for (int i = 7; i >= 0; --i) t[i] = i >= 2 ? t[i - 2] : 0;
+    }
+    if (k & 32) {
+#pragma unroll
+        for (int i = 7; i >= 0; --i) t[i] = i >= 1 ? t[i - 1] : 0;
+    }
+    u32 s = k & 31;
+    if (s) {
+#pragma unroll
+        for (int i = 7; i > 0; --i) t[i] = (t[i] << s) | (t[i - 1] >> (32 - s));
+        t[0] <<= s;
+    }
+    u256_set(r, t);
+}
+CW_HD void u256_shr(u32 *r, const u32 *a, u32 k) {
+    u32 t[8];
+    u256_set(t, a);
+    if (k & 128) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = i + 4 < 8 ? t[i + 4] : 0;
+    }
+    if (k & 64) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = i + 2 < 8 ? t[i + 2] : 0;
+    }
+    if (k & 32) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] = i + 1 < 8 ? t[i + 1] : 0;
+    }
+    u32 s = k & 31;
+    if (s) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) t[i] = (t[i] >> s) | (t[i + 1] << (32 - s));
+        t[7] >>= s;
+    }
+    u256_set(r, t);
+}
+CW_HD void fr_mask_wrap(u32 *r, const FrParams &P) {  // top-limb mask then one conditional subtraction
+    r[7] &= P.top_mask;
+    fr_cond_sub(r, P);
+}
+// decode the shift amount: returns 0 = plain by k, 1 = opposite direction by k, 2 = result is zero
+CW_HD int fr_shift_kind(const u32 *b, u32 &k, const FrParams &P) {
+    u32 hi = b[1] | b[2] | b[3] | b[4] | b[5] | b[6] | b[7];
+    if (!hi && b[0] < P.qbits) { k = b[0]; return 0; }
+    u32 nb[8];
+    u256_sub(nb, P.q, b);  // "negative" amount -j is stored as q-j
+    hi = nb[1] | nb[2] | nb[3] | nb[4] | nb[5] | nb[6] | nb[7];
+    if (!hi && nb[0] < P.qbits) { k = nb[0]; return 1; }
+    k = 0;
+    return 2;
+}
+CW_HD void fr_shl(u32 *r, const u32 *a, const u32 *b, const FrParams &P) {
+    u32 k;
+    int kind = fr_shift_kind(b, k, P);
+    if (kind == 0) { u256_shl(r, a, k); fr_mask_wrap(r, P); }
+    else if (kind == 1) u256_shr(r, a, k);
+    else u256_set_u32(r, 0);
+}
+CW_HD void fr_shr(u32 *r, const u32 *a, const u32 *b, const FrParams &P) {
+    u32 k;
+    int kind = fr_shift_kind(b, k, P);
+    if (kind == 0) u256_shr(r, a, k);
+    else if (kind == 1) { u256_shl(r, a, k); fr_mask_wrap(r, P); }
+    else u256_set_u32(r, 0);
+}
+
+// ---- comparisons on val(x) = x > half ? x - q : x (generic/fr.cpp:1184-1218,1294-1363) ----------
+CW_HD bool fr_lt(const u32 *a, const u32 *b, const FrParams &P) {
+    bool an = u256_gt(a, P.half), bn = u256_gt(b, P.half);
+    if (an != bn) return an;
+    return u256_gt(b, a);
+}
+
+// ---- integer division of canonical values (Fr_idiv / Fr_mod, generic/fr.cpp:2835-2875) ----------
+// returns false on division by zero (the reference process aborts inside GMP)
+CW_HD u32 u256_clz(const u32 *a) {  // leading zero bits, 256 for zero
+    u32 n = 0;
+    bool done = false;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) {
+        if (!done) {
+            if (a[i]) {
+                u32 x = a[i], c = 0;
+                while (!(x & 0x80000000u)) { x <<= 1; ++c; }
+                n += c;
+                done = true;
+            } else n += 32;
+        }
+    }
+    return n;
+}
+CW_HD bool u256_divmod(u32 *quo, u32 *rem, const u32 *a, const u32 *b) {
+    if (u256_is_zero(b)) {
+        u256_set_u32(quo, 0);
+        u256_set_u32(rem, 0);
+        return false;
+    }
+    // power-of-two divisor: shift / mask
+    u32 lzb = u256_clz(b);
+    {
+        u32 single[8], one[8];
+        u256_set_u32(one, 1);
+        u256_shl(single, one, 255 - lzb);
+        if (u256_eq(single, b)) {
+            u32 bit = 255 - lzb;
+            u256_shr(quo, a, bit);
+            u32 t[8];
+            u256_shl(t, quo, bit);
+            u256_sub(rem, a, t);
+            return true;
+        }
+    }
+    // restoring division, one bit per step; the numerator is consumed from a shifting register copy
+    u32 lza = u256_clz(a);
+    u32 n[8], q[8], r[8];
+    if (lza == 256) {
+        u256_set_u32(quo, 0);
+        u256_set_u32(rem, 0);
+        return true;
+    }
+    u256_shl(n, a, lza);
+    u256_set_u32(q, 0);
+    u256_set_u32(r, 0);
+    int steps = 256 - (int)lza;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int i = 0; i < steps; ++i) {
+        u32 carry = n[7] >> 31;
+#pragma unroll
+        for (int j = 7; j > 0; --j) n[j] = (n[j] << 1) | (n[j - 1] >> 31);
+        n[0] <<= 1;
+#pragma unroll
+        for (int j = 7; j > 0; --j) r[j] = (r[j] << 1) | (r[j - 1] >> 31);
+        r[0] = (r[0] << 1) | carry;  // r < b < 2^255 before the shift: no overflow
+        u32 t[8];
+        u32 br = u256_sub(t, r, b);
+#pragma unroll
+        for (int j = 7; j > 0; --j) q[j] = (q[j] << 1) | (q[j - 1] >> 31);
+        q[0] <<= 1;
+        if (!br) {
+            u256_set(r, t);
+            q[0] |= 1;
+        }
+    }
+    u256_set(quo, q);
+    u256_set(rem, r);
+    return true;
+}
+
+// ---- one tape instruction ----------------------------------------------------------------------
+// Opcodes are cw_op (include/circom_b200.h).  Operands arrive in the representation the lowering
+// chose (flatten.cpp); `err` is set to 1 on division by zero.  Returns true if r holds a result.
+enum {
+    OP_MUL = 1, OP_ADD = 3, OP_SUB = 4, OP_POW = 5, OP_IDIV = 6, OP_MOD = 7, OP_SHL = 8, OP_SHR = 9,
+    OP_LEQ = 10, OP_GEQ = 11, OP_LT = 12, OP_GT = 13, OP_EQ = 14, OP_NEQ = 15, OP_LOR = 16, OP_LAND = 17,
+    OP_LNOT = 18, OP_BOR = 19, OP_BAND = 20, OP_BXOR = 21, OP_BNOT = 22, OP_NEG = 23, OP_COPY = 24,
+    OP_SELECT = 25, OP_ASSERT = 26, OP_ASSERT_EQ = 27, OP_INV = 28
+};
+
+CW_HD void fr_exec(u32 opcode, u32 *r, const u32 *a, const u32 *b, const FrParams &P, int &err) {
+    switch (opcode) {
+        case OP_MUL: fr_mont_mul(r, a, b, P); break;
+        case OP_ADD: fr_add(r, a, b, P); break;
+        case OP_SUB: fr_sub(r, a, b, P); break;
+        case OP_NEG: fr_neg(r, a, P); break;
+        case OP_INV: fr_inv_mont(r, a, P); break;
+        case OP_POW: fr_pow_mont(r, a, b, P); break;
+        case OP_IDIV: { u32 rem[8]; if (!u256_divmod(r, rem, a, b)) err = 1; break; }
+        case OP_MOD: { u32 quo[8]; if (!u256_divmod(quo, r, a, b)) err = 1; break; }
+        case OP_SHL: fr_shl(r, a, b, P); break;
+        case OP_SHR: fr_shr(r, a, b, P); break;
+        case OP_LT: u256_set_u32(r, fr_lt(a, b, P)); break;
+        case OP_GT: u256_set_u32(r, fr_lt(b, a, P)); break;
+        case OP_LEQ: u256_set_u32(r, !fr_lt(b, a, P)); break;
+        case OP_GEQ: u256_set_u32(r, !fr_lt(a, b, P)); break;
+        case OP_EQ: u256_set_u32(r, u256_eq(a, b)); break;
+        case OP_NEQ: u256_set_u32(r, !u256_eq(a, b)); break;
+        case OP_LOR: u256_set_u32(r, !u256_is_zero(a) || !u256_is_zero(b)); break;
+        case OP_LAND: u256_set_u32(r, !u256_is_zero(a) && !u256_is_zero(b)); break;
+        case OP_LNOT: u256_set_u32(r, u256_is_zero(a)); break;
+        case OP_BOR:
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] = a[i] | b[i];
+            fr_mask_wrap(r, P);
+            break;
+        case OP_BAND:
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] = a[i] & b[i];
+            fr_mask_wrap(r, P);
+            break;
+        case OP_BXOR:
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] = a[i] ^ b[i];
+            fr_mask_wrap(r, P);
+            break;
+        case OP_BNOT:
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] = ~a[i];
+            fr_mask_wrap(r, P);
+            break;
+        case OP_COPY: u256_set(r, a); break;
+        default: u256_set_u32(r, 0); break;
+    }
+}
+
+}  // namespace cw

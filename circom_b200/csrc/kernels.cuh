@@ -1,0 +1,278 @@
+// sm_100a kernels: tape execution, input staging, witness gather, R1CS check, field batch ops.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fr_device.cuh"
+
+namespace cw {
+
+// Per-prime parameters live in constant memory so that modulus limbs are read as c[bank][imm]
+// instruction operands (no registers, no loads).
+__constant__ FrParams c_fr[2];
+
+// ---- value-slot storage ---------------------------------------------------------------------
+// One instance tile holds BT = 1 << bt_log2 instances.  A slot (256-bit value) of a tile is two
+// 16-byte halves, each stored for the BT instances contiguously:
+//     uint4 index = (tile * n_slots + slot) * 2 * BT + half * BT + instance_in_tile
+// so a (warp of) thread(s) working on BT instances of one op issues 128-bit loads over
+// BT*16 contiguous bytes per half; with BT = 1 this is the plain 32-byte element (one DRAM sector).
+__device__ __forceinline__ void load_slot(u32 *v, const uint4 *__restrict__ tile_base, u32 slot, u32 bt_log2,
+                                          u32 inst) {
+    size_t i = ((size_t)slot << (bt_log2 + 1)) + inst;
+    uint4 lo = tile_base[i];
+    uint4 hi = tile_base[i + ((size_t)1 << bt_log2)];
+    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+    v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+}
+__device__ __forceinline__ void store_slot(const u32 *v, uint4 *__restrict__ tile_base, u32 slot, u32 bt_log2,
+                                           u32 inst) {
+    size_t i = ((size_t)slot << (bt_log2 + 1)) + inst;
+    tile_base[i] = make_uint4(v[0], v[1], v[2], v[3]);
+    tile_base[i + ((size_t)1 << bt_log2)] = make_uint4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void load_const(u32 *v, const uint4 *__restrict__ consts, u32 idx) {
+    uint4 lo = __ldg(&consts[2 * (size_t)idx]);
+    uint4 hi = __ldg(&consts[2 * (size_t)idx + 1]);
+    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+    v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+}
+__device__ __forceinline__ void load_operand(u32 *v, u32 operand, const uint4 *__restrict__ tile_base,
+                                             const uint4 *__restrict__ consts, u32 bt_log2, u32 inst) {
+    if (operand & 0x80000000u) load_const(v, consts, operand & 0x7FFFFFFFu);
+    else load_slot(v, tile_base, operand, bt_log2, inst);
+}
+
+struct TapeDev {
+    const uint4 *ops;          // {opcode, a, b, c}
+    const u32 *level_start;    // n_levels + 1
+    const uint4 *consts;       // 2 per constant
+    u32 n_levels;
+    u32 n_slots;
+    u32 n_pre;
+    u32 n_inputs;
+};
+
+// ---- inputs: inputs[batch][n_inputs][8 u32] canonical -> slots 1..n_inputs, slot 0 = 1 ----------
+__global__ void stage_inputs_kernel(TapeDev tp, const uint4 *__restrict__ inputs, uint4 *__restrict__ slots,
+                                    u32 batch, u32 batch_padded, u32 bt_log2) {
+    size_t total = (size_t)batch_padded * (tp.n_inputs + 1);
+    for (size_t w = blockIdx.x * (size_t)blockDim.x + threadIdx.x; w < total; w += (size_t)gridDim.x * blockDim.x) {
+        u32 inst = (u32)(w % batch_padded);
+        u32 k = (u32)(w / batch_padded);  // 0 = constant one, 1.. = input k-1
+        u32 tile = inst >> bt_log2, li = inst & ((1u << bt_log2) - 1);
+        uint4 *base = slots + (((size_t)tile * tp.n_slots) << (bt_log2 + 1));
+        u32 v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (k == 0) v[0] = 1;
+        else if (inst < batch) {
+            const uint4 *src = inputs + ((size_t)inst * tp.n_inputs + (k - 1)) * 2;
+            uint4 lo = src[0], hi = src[1];
+            v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+            v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+        }
+        store_slot(v, base, k, bt_log2, li);
+    }
+}
+
+// ---- the tape interpreter ---------------------------------------------------------------------
+// One CTA owns one tile of BT instances and walks the levels of the tape; within a level the work
+// items (op, instance) are spread over the CTA's threads, instance fastest.  Values produced in
+// level l are consumed in later levels by other threads of the same CTA only, so a CTA barrier
+// per level is the only synchronisation (no grid-wide sync, tiles are independent).
+template <int PRIME>
+__global__ void __launch_bounds__(1024) tape_exec_kernel(TapeDev tp, uint4 *__restrict__ slots, u32 bt_log2,
+                                                         u32 *__restrict__ first_assert, int *__restrict__ err,
+                                                         u32 batch) {
+    const FrParams &P = c_fr[PRIME];
+    const u32 tile = blockIdx.x;
+    const u32 bt_mask = (1u << bt_log2) - 1;
+    uint4 *base = slots + (((size_t)tile * tp.n_slots) << (bt_log2 + 1));
+    u32 lb = tp.level_start[0];
+    for (u32 l = 0; l < tp.n_levels; ++l) {
+        const u32 le = tp.level_start[l + 1];
+        const u32 n = (le - lb) << bt_log2;
+        for (u32 w = threadIdx.x; w < n; w += blockDim.x) {
+            const u32 oi = lb + (w >> bt_log2);
+            const u32 li = w & bt_mask;
+            const uint4 op = __ldg(&tp.ops[oi]);
+            u32 a[8], b[8], r[8];
+            load_operand(a, op.y, base, tp.consts, bt_log2, li);
+            load_operand(b, op.z, base, tp.consts, bt_log2, li);
+            const u32 inst = (tile << bt_log2) + li;
+            if (op.x == OP_SELECT) {
+                u32 c[8];
+                load_operand(c, op.w, base, tp.consts, bt_log2, li);
+                bool t = !u256_is_zero(c);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) r[i] = t ? a[i] : b[i];
+            } else if (op.x == OP_ASSERT_EQ || op.x == OP_ASSERT) {
+                bool ok = op.x == OP_ASSERT_EQ ? u256_eq(a, b) : !u256_is_zero(a);
+                if (!ok && inst < batch) atomicMin(&first_assert[inst], op.w);
+                continue;  // asserts have no destination value
+            } else {
+                int e = 0;
+                fr_exec(op.x, r, a, b, P, e);
+                if (e && inst < batch) err[inst] = 1;
+            }
+            store_slot(r, base, tp.n_pre + oi, bt_log2, li);
+        }
+        lb = le;
+        __syncthreads();
+    }
+}
+
+// ---- witness gather: out[inst][w][8 u32] canonical (getWitness + Fr_toLongNormal, main.cpp:328-332)
+template <int PRIME>
+__global__ void witness_gather_kernel(const uint4 *__restrict__ slots, const u32 *__restrict__ witness_slot,
+                                      uint4 *__restrict__ out, u32 n_slots, u32 n_witness, u32 batch, u32 bt_log2) {
+    const FrParams &P = c_fr[PRIME];
+    const u32 bt = 1u << bt_log2;
+    const u32 tiles = (batch + bt - 1) >> bt_log2;
+    size_t total = (size_t)tiles * n_witness * bt;
+    for (size_t w = blockIdx.x * (size_t)blockDim.x + threadIdx.x; w < total; w += (size_t)gridDim.x * blockDim.x) {
+        u32 li = (u32)(w & (bt - 1));
+        size_t rest = w >> bt_log2;
+        u32 wi = (u32)(rest % n_witness);
+        u32 tile = (u32)(rest / n_witness);
+        u32 inst = (tile << bt_log2) + li;
+        if (inst >= batch) continue;
+        const uint4 *base = slots + (((size_t)tile * n_slots) << (bt_log2 + 1));
+        u32 ws = witness_slot[wi];
+        u32 v[8];
+        load_slot(v, base, ws & 0x7FFFFFFFu, bt_log2, li);
+        if (ws & 0x80000000u) {
+            u32 t[8];
+            fr_from_mont(t, v, P);
+            u256_set(v, t);
+        }
+        uint4 *dst = out + ((size_t)inst * n_witness + wi) * 2;
+        dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+// ---- R1CS check: A.w * B.w == C.w for every row and instance ------------------------------------
+// row_ptr[3m+1], col[nnz], coef[nnz] (index into the dictionary; dictM = coefficient * R mod q,
+// kind: 0 general, 1 = one, 2 = minus one).  witness[inst][n_wires][8 u32] canonical.
+// Thread = (row, instance); rows along threadIdx.x so that neighbouring rows (which touch
+// neighbouring wires) share cache lines; blockIdx.y walks instances.
+struct R1csDev {
+    const unsigned long long *row_ptr;
+    const u32 *col;
+    const u32 *coef;
+    const uint4 *dictM;
+    const unsigned char *kind;
+    u32 n_constraints;
+    u32 n_wires;
+};
+
+template <int PRIME>
+__device__ __forceinline__ void r1cs_lc(u32 *acc, const R1csDev &R, unsigned long long b, unsigned long long e,
+                                        const uint4 *__restrict__ w, const FrParams &P) {
+    u256_set_u32(acc, 0);
+    for (unsigned long long k = b; k < e; ++k) {
+        u32 c = __ldg(&R.col[k]);
+        u32 ci = __ldg(&R.coef[k]);
+        uint4 lo = w[2 * (size_t)c], hi = w[2 * (size_t)c + 1];
+        u32 x[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        u32 t[8];
+        unsigned char kd = __ldg(&R.kind[ci]);
+        if (kd == 1) {
+            fr_add(t, acc, x, P);
+        } else if (kd == 2) {
+            fr_sub(t, acc, x, P);
+        } else {
+            u32 cm[8], p[8];
+            load_const(cm, R.dictM, ci);
+            fr_mont_mul(p, cm, x, P);  // (cR) * x / R = c*x
+            fr_add(t, acc, p, P);
+        }
+        u256_set(acc, t);
+    }
+}
+
+template <int PRIME>
+__global__ void __launch_bounds__(256) r1cs_check_kernel(R1csDev R, const uint4 *__restrict__ witness, u32 batch,
+                                                         unsigned long long *__restrict__ first_bad) {
+    const FrParams &P = c_fr[PRIME];
+    for (u32 inst = blockIdx.y; inst < batch; inst += gridDim.y) {
+        const uint4 *w = witness + (size_t)inst * R.n_wires * 2;
+        for (u32 row = blockIdx.x * blockDim.x + threadIdx.x; row < R.n_constraints; row += gridDim.x * blockDim.x) {
+            unsigned long long p0 = R.row_ptr[3 * (size_t)row], p1 = R.row_ptr[3 * (size_t)row + 1],
+                               p2 = R.row_ptr[3 * (size_t)row + 2], p3 = R.row_ptr[3 * (size_t)row + 3];
+            u32 a[8], b[8], c[8], ab[8], c1[8];
+            r1cs_lc<PRIME>(a, R, p0, p1, w, P);
+            r1cs_lc<PRIME>(b, R, p1, p2, w, P);
+            r1cs_lc<PRIME>(c, R, p2, p3, w, P);
+            fr_mont_mul(ab, a, b, P);  // a*b/R
+            fr_from_mont(c1, c, P);    // c/R
+            if (!u256_eq(ab, c1)) atomicMin(&first_bad[inst], (unsigned long long)row);
+        }
+    }
+}
+
+// ---- batched single field op (parity tests of the device Fr_* equivalents) ---------------------
+// canonical in / canonical out; the kernel applies the same representation rules as the lowering
+template <int PRIME>
+__global__ void fr_batch_op_kernel(int op, const uint4 *__restrict__ A, const uint4 *__restrict__ B,
+                                   const uint4 *__restrict__ C, uint4 *__restrict__ Rr, size_t n,
+                                   int *__restrict__ err) {
+    const FrParams &P = c_fr[PRIME];
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        u32 a[8], b[8] = {0, 0, 0, 0, 0, 0, 0, 0}, c[8] = {0, 0, 0, 0, 0, 0, 0, 0}, r[8];
+        load_const(a, A, (u32)i);
+        if (B) load_const(b, B, (u32)i);
+        if (C) load_const(c, C, (u32)i);
+        int e = 0;
+        if (op == OP_MUL) {  // canonical x canonical: convert one side
+            u32 am[8];
+            fr_to_mont(am, a, P);
+            fr_mont_mul(r, am, b, P);
+        } else if (op == 2 /* DIV */) {
+            u32 bm[8], im[8];
+            fr_to_mont(bm, b, P);
+            fr_inv_mont(im, bm, P);
+            fr_mont_mul(r, im, a, P);
+        } else if (op == OP_POW) {
+            u32 am[8], rm[8];
+            fr_to_mont(am, a, P);
+            fr_pow_mont(rm, am, b, P);
+            fr_from_mont(r, rm, P);
+        } else if (op == OP_INV) {
+            u32 am[8], rm[8];
+            fr_to_mont(am, a, P);
+            fr_inv_mont(rm, am, P);
+            fr_from_mont(r, rm, P);
+        } else if (op == OP_SELECT) {
+            bool t = !u256_is_zero(c);
+            for (int k = 0; k < 8; ++k) r[k] = t ? a[k] : b[k];
+        } else {
+            fr_exec((u32)op, r, a, b, P, e);
+        }
+        if (e) err[0] = 1;
+        Rr[2 * i] = make_uint4(r[0], r[1], r[2], r[3]);
+        Rr[2 * i + 1] = make_uint4(r[4], r[5], r[6], r[7]);
+    }
+}
+
+// ---- Montgomery-multiplication throughput probe ------------------------------------------------
+template <int PRIME>
+__global__ void fr_mul_bench_kernel(uint4 *__restrict__ data, size_t n, int iters) {
+    const FrParams &P = c_fr[PRIME];
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 x[8], y[8];
+    load_const(x, data, (u32)i);
+    u256_set(y, x);
+    y[0] ^= 0x9E3779B9u & 0x0FFFFFFFu;
+#pragma unroll 1
+    for (int k = 0; k < iters; ++k) {
+        u32 t[8];
+        fr_mont_mul(t, x, y, P);
+        u256_set(x, t);
+    }
+    data[2 * i] = make_uint4(x[0], x[1], x[2], x[3]);
+    data[2 * i + 1] = make_uint4(x[4], x[5], x[6], x[7]);
+}
+
+}  // namespace cw

@@ -1,0 +1,67 @@
+// Lowered circuit: the flat, levelised instruction tape + metadata + R1CS in CSR form.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "u256.h"
+
+namespace cw {
+
+constexpr uint32_t OPERAND_CONST = 0x80000000u;  // operand bit31: index into the constant table
+constexpr uint32_t WSLOT_MONT = 0x80000000u;     // witness_slot bit31: slot holds the Montgomery image
+constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
+
+struct InputInfo {
+    std::string name;
+    uint64_t hash;
+    uint64_t signal_id;
+    uint64_t size;
+};
+
+// same layout as HashSignalInfo (c_elements/common/circom.hpp:17-21)
+struct HashEntry {
+    uint64_t hash, signalid, signalsize;
+};
+
+struct R1csData {
+    int prime_id = 0;
+    uint64_t n_wires = 0;
+    uint64_t n_constraints = 0;
+    std::vector<uint64_t> row_ptr;  // 3*m+1 : row r of A at 3r, B at 3r+1, C at 3r+2
+    std::vector<uint32_t> col;      // wire ids
+    std::vector<uint32_t> coef;     // index into dict
+    std::vector<U256> dict;         // distinct coefficients, canonical
+    uint32_t n_pub_out = 0, n_pub_in = 0, n_prv_in = 0;
+};
+
+struct Tape {
+    FieldParams F;
+    uint32_t flags = 0;
+    uint64_t n_signals = 0, n_witness = 0, n_inputs = 0, n_outputs = 0, n_components = 0;
+    uint64_t n_ir_ops = 0, n_mul_ops = 0, n_conv_ops = 0, max_level_width = 0, n_asserts = 0;
+    uint32_t n_pre = 0;    // slot 0 = constant one, slots 1..n_inputs = main inputs
+    uint32_t n_slots = 0;  // n_pre + n_tape_ops (dst of tape op i is slot n_pre + i)
+    std::vector<uint32_t> ops;          // 4 words per op: opcode | a | b | c
+    std::vector<uint32_t> level_start;  // n_levels + 1
+    std::vector<U256> consts;           // raw limb patterns (already in the form the consumer needs)
+    std::vector<uint32_t> witness_slot; // per witness entry
+    std::vector<InputInfo> inputs;
+    std::vector<HashEntry> hashmap;
+    R1csData r1cs;
+    size_t n_tape_ops() const { return ops.size() / 4; }
+    size_t n_levels() const { return level_start.empty() ? 0 : level_start.size() - 1; }
+};
+
+// Parse a .cb2c description and lower it.  Throws std::runtime_error.
+void lower_circuit(const uint8_t *data, size_t len, uint32_t flags, Tape &out);
+
+uint64_t fnv1a(const char *s, size_t n);
+
+// file formats (formats.cpp)
+void write_r1cs(const R1csData &r, const FieldParams &F, const std::string &path);
+void read_r1cs(const std::string &path, R1csData &out);
+std::vector<uint8_t> wtns_bytes(const FieldParams &F, const uint64_t *witness, uint64_t n_witness);
+void write_dat(const Tape &t, const std::string &path);
+
+}  // namespace cw

@@ -1,0 +1,97 @@
+"""ctypes binding of the C ABI in include/circom_b200.h (libcircom_b200.so).
+
+The library is the product: if it is missing it is built with nvcc; if it cannot be
+loaded the import fails loudly (there is no Python / CPU fallback for the hot path).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint8, c_uint32, c_uint64, c_void_p
+
+from . import build as _build
+
+CW_OK, CW_EINVAL, CW_EIO, CW_EFORMAT, CW_ECUDA, CW_ENOTFOUND, CW_ESTATE, CW_ENODEV = 0, -1, -2, -3, -4, -5, -6, -7
+CW_FLAG_NO_ASSERTS, CW_FLAG_HOST_ONLY = 1, 2
+
+
+class CwError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("circom_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class CwStats(ctypes.Structure):
+    _fields_ = [(n, c_uint64) for n in (
+        "n_signals", "n_witness", "n_inputs", "n_outputs", "n_components", "n_constants", "n_ir_ops",
+        "n_tape_ops", "n_slots", "n_levels", "n_constraints", "n_nnz", "n_mul_ops", "n_conv_ops",
+        "max_level_width")] + [("reserved", c_uint64 * 3)]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
+
+
+def _load() -> ctypes.CDLL:
+    path = _build.LIB
+    if not os.path.exists(path):
+        _build.build()
+    lib = ctypes.CDLL(path)
+    P = c_void_p
+    sig = {
+        "cw_version": (c_int, []),
+        "cw_last_error": (c_char_p, []),
+        "cw_device_count": (c_int, []),
+        "cw_circuit_load": (c_int, [c_char_p, c_uint32, POINTER(P)]),
+        "cw_circuit_load_mem": (c_int, [c_void_p, c_size_t, c_uint32, POINTER(P)]),
+        "cw_circuit_destroy": (None, [P]),
+        "cw_circuit_stats": (c_int, [P, POINTER(CwStats)]),
+        "cw_circuit_prime": (c_int, [P, POINTER(c_int), POINTER(c_uint64)]),
+        "cw_get_main_input_signal_start": (c_uint32, [P]),
+        "cw_get_main_input_signal_no": (c_uint32, [P]),
+        "cw_get_total_signal_no": (c_uint32, [P]),
+        "cw_get_number_of_components": (c_uint32, [P]),
+        "cw_get_size_of_input_hashmap": (c_uint32, [P]),
+        "cw_get_size_of_witness": (c_uint32, [P]),
+        "cw_get_size_of_constants": (c_uint32, [P]),
+        "cw_fnv1a": (c_uint64, [c_char_p]),
+        "cw_get_input_signal_size": (c_int, [P, c_uint64, POINTER(c_uint64)]),
+        "cw_get_input_signal_id": (c_int, [P, c_uint64, POINTER(c_uint64)]),
+        "cw_circuit_tape": (c_int, [P, c_void_p, c_void_p, c_void_p]),
+        "cw_circuit_write_dat": (c_int, [P, c_char_p]),
+        "cw_batch_create": (c_int, [P, c_uint32, c_int, POINTER(P)]),
+        "cw_batch_destroy": (None, [P]),
+        "cw_batch_set_input": (c_int, [P, c_uint32, c_uint64, c_uint32, POINTER(c_uint64)]),
+        "cw_batch_remaining_inputs": (c_int, [P, c_uint32, POINTER(c_uint32)]),
+        "cw_batch_set_inputs": (c_int, [P, c_void_p, c_int]),
+        "cw_batch_run": (c_int, [P]),
+        "cw_batch_sync": (c_int, [P]),
+        "cw_batch_status": (c_int, [P, c_void_p]),
+        "cw_batch_get_witness": (c_int, [P, c_void_p]),
+        "cw_batch_witness_device": (c_int, [P, POINTER(c_void_p)]),
+        "cw_batch_stream": (c_void_p, [P]),
+        "cw_batch_last_ms": (c_int, [P, POINTER(c_float), POINTER(c_float)]),
+        "cw_batch_write_wtns": (c_int, [P, c_uint32, c_char_p]),
+        "cw_batch_wtns_bytes": (c_int, [P, c_uint32, c_void_p, c_size_t, POINTER(c_size_t)]),
+        "cw_r1cs_from_circuit": (c_int, [P, POINTER(P)]),
+        "cw_r1cs_load": (c_int, [c_char_p, POINTER(P)]),
+        "cw_r1cs_write": (c_int, [P, c_char_p, c_uint32, c_uint32, c_uint32]),
+        "cw_r1cs_info": (c_int, [P, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint64), POINTER(c_int)]),
+        "cw_r1cs_destroy": (None, [P]),
+        "cw_r1cs_check": (c_int, [P, c_void_p, c_int, c_uint32, c_int, c_void_p, POINTER(c_float)]),
+        "cw_fr_batch_op": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
+        "cw_fr_mul_bench": (c_int, [c_int, c_size_t, c_int, c_int, POINTER(c_float)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI is incomplete
+        fn.restype = res
+        fn.argtypes = args
+    lib._cw_symbols = sorted(sig)
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int) -> None:
+    if rc != CW_OK:
+        raise CwError(rc, (lib.cw_last_error() or b"").decode())

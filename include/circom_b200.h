@@ -1,0 +1,166 @@
+/*
+ * circom_b200 — C ABI of the Blackwell (sm_100a) witness-generation and R1CS
+ * evaluation back end for circom circuits.
+ *
+ * This is the drop-in boundary a `code_producers/src/cuda_elements` producer
+ * (sibling of c_elements / wasm_elements, code_producers/src/lib.rs:1-7) and its
+ * Rust host would bind through FFI.  Every entry point names the piece of the
+ * reference runtime it replaces.  Plain pointers and sizes only; all field
+ * elements crossing the ABI are CANONICAL integers in [0,q) as 4 little-endian
+ * uint64 limbs (the same 32 bytes the reference writes to .wtns,
+ * c_elements/common/main.cpp:328-332).  Montgomery form is internal.
+ *
+ * Error convention: functions return CW_OK (0) or a negative CW_E* code;
+ * cw_last_error() gives a thread-local message.  The reference instead
+ * assert()s / throws (calcwit.cpp:60-66,80-92, main.cpp:168,265-274).
+ *
+ * Threading: handles are not shared between threads; one CUDA stream per batch.
+ */
+#ifndef CIRCOM_B200_H
+#define CIRCOM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CW_OK 0
+#define CW_EINVAL (-1)   /* bad argument */
+#define CW_EIO (-2)      /* file problem */
+#define CW_EFORMAT (-3)  /* malformed .cb2c / .r1cs / .wtns */
+#define CW_ECUDA (-4)    /* CUDA runtime error (message in cw_last_error) */
+#define CW_ENOTFOUND (-5)/* "Signal not found" (calcwit.cpp:60-66) */
+#define CW_ESTATE (-6)   /* e.g. "Signal assigned twice" (calcwit.cpp:88-91), inputs missing */
+#define CW_ENODEV (-7)   /* no CUDA device: the product has NO CPU fallback */
+
+/* primes (program_structure/src/utils/constants.rs:3-6) */
+#define CW_PRIME_BN128 0
+#define CW_PRIME_BLS12381 1
+
+/* cw_circuit_load flags */
+#define CW_FLAG_NO_ASSERTS 1u /* --sanity_check 0: drop `===` asserts (assert_bucket.rs:73) */
+#define CW_FLAG_HOST_ONLY 2u  /* lower the tape but do not touch a GPU (CPU-side tests of the lowering) */
+
+/* IR opcodes = OperatorType, compiler/src/intermediate_representation/compute_bucket.rs:7-34 */
+enum cw_op {
+    CW_OP_NOP = 0, CW_OP_MUL = 1, CW_OP_DIV = 2, CW_OP_ADD = 3, CW_OP_SUB = 4, CW_OP_POW = 5,
+    CW_OP_IDIV = 6, CW_OP_MOD = 7, CW_OP_SHL = 8, CW_OP_SHR = 9, CW_OP_LEQ = 10, CW_OP_GEQ = 11,
+    CW_OP_LT = 12, CW_OP_GT = 13, CW_OP_EQ = 14, CW_OP_NEQ = 15, CW_OP_LOR = 16, CW_OP_LAND = 17,
+    CW_OP_LNOT = 18, CW_OP_BOR = 19, CW_OP_BAND = 20, CW_OP_BXOR = 21, CW_OP_BNOT = 22,
+    CW_OP_NEG = 23, CW_OP_COPY = 24, CW_OP_SELECT = 25, CW_OP_ASSERT = 26, CW_OP_ASSERT_EQ = 27,
+    /* device-only opcodes produced by the lowering */
+    CW_OP_INV = 28
+};
+
+typedef struct cw_circuit cw_circuit; /* replaces Circom_Circuit (circom.hpp:36-43) + generated <name>.cpp */
+typedef struct cw_batch cw_batch;     /* replaces Circom_CalcWit (calcwit.hpp:17-66), for `batch` inputs at once */
+typedef struct cw_r1cs cw_r1cs;       /* CSR form of a .r1cs (constraint_writers/src/r1cs_writer.rs) */
+
+typedef struct cw_stats {
+    uint64_t n_signals;      /* get_total_signal_no() */
+    uint64_t n_witness;      /* get_size_of_witness() */
+    uint64_t n_inputs;       /* get_main_input_signal_no() */
+    uint64_t n_outputs;      /* get_main_input_signal_start() - 1 */
+    uint64_t n_components;   /* get_number_of_components() */
+    uint64_t n_constants;    /* device constant-table entries */
+    uint64_t n_ir_ops;       /* field operations before lowering (incl. moves) */
+    uint64_t n_tape_ops;     /* device tape instructions after aliasing / form inference / DCE */
+    uint64_t n_slots;        /* value slots per instance (32 B each) */
+    uint64_t n_levels;       /* dependency levels */
+    uint64_t n_constraints;  /* R1CS rows */
+    uint64_t n_nnz;          /* nnz(A)+nnz(B)+nnz(C) */
+    uint64_t n_mul_ops;      /* Montgomery multiplications in the tape (incl. conversions) */
+    uint64_t n_conv_ops;     /* of which representation changes inserted by the lowering */
+    uint64_t max_level_width;
+    uint64_t reserved[3];
+} cw_stats;
+
+/* ---- library ---------------------------------------------------------------------------- */
+int cw_version(void);
+const char *cw_last_error(void);
+int cw_device_count(void); /* number of CUDA devices, 0 if none */
+
+/* ---- circuit: load + lower (replaces loadCircuit main.cpp:22-124 and the g++ build of <name>.cpp) */
+int cw_circuit_load(const char *cb2c_path, uint32_t flags, cw_circuit **out);
+int cw_circuit_load_mem(const void *data, size_t len, uint32_t flags, cw_circuit **out);
+void cw_circuit_destroy(cw_circuit *c);
+int cw_circuit_stats(const cw_circuit *c, cw_stats *out);
+int cw_circuit_prime(const cw_circuit *c, int *prime_id, uint64_t q[4]);
+/* size getters, same meaning as circom.hpp:79-87 */
+uint32_t cw_get_main_input_signal_start(const cw_circuit *c);
+uint32_t cw_get_main_input_signal_no(const cw_circuit *c);
+uint32_t cw_get_total_signal_no(const cw_circuit *c);
+uint32_t cw_get_number_of_components(const cw_circuit *c);
+uint32_t cw_get_size_of_input_hashmap(const cw_circuit *c);
+uint32_t cw_get_size_of_witness(const cw_circuit *c);
+uint32_t cw_get_size_of_constants(const cw_circuit *c);
+/* FNV-1a 64 of a qualified input name (calcwit.cpp:17-24) */
+uint64_t cw_fnv1a(const char *name);
+/* Circom_CalcWit::getInputSignalSize (calcwit.cpp:99-102); CW_ENOTFOUND if absent */
+int cw_get_input_signal_size(const cw_circuit *c, uint64_t name_hash, uint64_t *size);
+/* global signal id of element 0 of that input (InputHashMap[pos].signalid, calcwit.cpp:86) */
+int cw_get_input_signal_id(const cw_circuit *c, uint64_t name_hash, uint64_t *signal_id);
+/* copies of the lowered tape for inspection / tests (sizes from cw_circuit_stats):
+ * ops: n_tape_ops x 4 uint32 {opcode | flags<<8, a, b, c}; operand bit31 = constant-table index;
+ * level_start: n_levels+1 uint32; witness_slot: n_witness uint32 (bit31 = value held in Montgomery form) */
+int cw_circuit_tape(const cw_circuit *c, uint32_t *ops, uint32_t *level_start, uint32_t *witness_slot);
+/* save / load the reference's .dat layout for the input hash map + witness2signal list
+ * (c_code_generator.rs:575-603,605-614,818-865) */
+int cw_circuit_write_dat(const cw_circuit *c, const char *path);
+
+/* ---- batch: Circom_CalcWit for `batch` independent inputs on one GPU ------------------------ */
+int cw_batch_create(const cw_circuit *c, uint32_t batch, int device, cw_batch **out);
+void cw_batch_destroy(cw_batch *b);
+/* Circom_CalcWit::setInputSignal(h, i, val) for one instance (calcwit.cpp:77-97); host staging */
+int cw_batch_set_input(cw_batch *b, uint32_t instance, uint64_t name_hash, uint32_t idx, const uint64_t limbs[4]);
+/* getRemaingInputsToBeSet (calcwit.hpp:50-52) for one instance */
+int cw_batch_remaining_inputs(const cw_batch *b, uint32_t instance, uint32_t *remaining);
+/* bulk: inputs[batch][n_inputs][4] canonical, in main-input signal order; host or device pointer */
+int cw_batch_set_inputs(cw_batch *b, const uint64_t *inputs, int is_device_ptr);
+/* run(ctx) (calcwit.cpp:6, generated Main_run) for the whole batch; asynchronous on the batch stream */
+int cw_batch_run(cw_batch *b);
+int cw_batch_sync(cw_batch *b);
+/* per instance: 0 = ok, k>0 = first failed assert is IR assert number k-1, <0 = runtime error */
+int cw_batch_status(cw_batch *b, int32_t *status);
+/* getWitness(i) for all i and all instances, after Fr_toLongNormal (main.cpp:328-332):
+ * out[batch][n_witness][4]; host pointer */
+int cw_batch_get_witness(cw_batch *b, uint64_t *out);
+/* device pointer of the same array (valid until the next run / destroy) */
+int cw_batch_witness_device(cw_batch *b, const uint64_t **dptr);
+/* CUDA stream of the batch (cudaStream_t as void*) and last device time of run+gather in ms */
+void *cw_batch_stream(cw_batch *b);
+int cw_batch_last_ms(cw_batch *b, float *exec_ms, float *gather_ms);
+/* writeBinWitness (main.cpp:288-334): byte-identical .wtns for one instance */
+int cw_batch_write_wtns(cw_batch *b, uint32_t instance, const char *path);
+/* same bytes into a caller buffer of 76 + 32*n_witness bytes (calculateWTNSBin, witness_calculator.js:212-276) */
+int cw_batch_wtns_bytes(cw_batch *b, uint32_t instance, uint8_t *out, size_t cap, size_t *len);
+
+/* ---- R1CS --------------------------------------------------------------------------------- */
+/* constraints of the loaded circuit in witness numbering */
+int cw_r1cs_from_circuit(const cw_circuit *c, cw_r1cs **out);
+/* parse a .r1cs file (layout of constraint_writers/src/r1cs_writer.rs:93-101,49-72,246-269,328-341) */
+int cw_r1cs_load(const char *path, cw_r1cs **out);
+/* write it back in the reference's section order (constraint_list/src/r1cs_porting.rs:19-53) */
+int cw_r1cs_write(const cw_r1cs *r, const char *path, uint32_t n_pub_out, uint32_t n_pub_in, uint32_t n_prv_in);
+int cw_r1cs_info(const cw_r1cs *r, uint64_t *n_wires, uint64_t *n_constraints, uint64_t *nnz, int *prime_id);
+void cw_r1cs_destroy(cw_r1cs *r);
+/* A.w o B.w == C.w for `batch` witnesses w[batch][n_wires][4] (canonical).  first_bad[i] = -1 if
+ * instance i satisfies every constraint, else the smallest violated row.  New functionality: the
+ * reference has no evaluator (constraint_writers/src/r1cs_reader.rs has no caller). */
+int cw_r1cs_check(cw_r1cs *r, const uint64_t *witness, int is_device_ptr, uint32_t batch, int device,
+                  int64_t *first_bad, float *kernel_ms);
+
+/* ---- field library, batched (parity tests of the device Fr_* equivalents, fr.hpp:28-70) ------ */
+/* r[i] = op(a[i], b[i], c[i]) for i < n on `device`; canonical in / canonical out; b, c may be NULL */
+int cw_fr_batch_op(int prime_id, int op, const uint64_t *a, const uint64_t *b, const uint64_t *c,
+                   uint64_t *r, size_t n, int device);
+/* Montgomery-multiplication throughput probe: n independent chains of `iters` dependent multiplications;
+ * returns device milliseconds */
+int cw_fr_mul_bench(int prime_id, size_t n, int iters, int device, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,140 @@
+"""Pure-Python big-int execution of a circuit description (TEST INFRASTRUCTURE).
+
+Restates the reference runtime's execution model for generated code
+(compiler/src/circuit_design/template.rs:177-472): components are created with
+`inputCounter = number_of_inputs` (template.rs:204-209), a store into a
+sub-component input decrements the counter and runs the sub-component when it
+reaches zero (intermediate_representation/store_bucket.rs:660-734), templates
+without inputs run at creation (template.rs:274-278).  Signal numbering: global
+signal 0 is the constant 1 (common/calcwit.cpp:34), main starts at 1, each
+component owns [signalStart, signalStart + n_own) followed by its
+sub-components' blocks (create_component_bucket.rs:219-233).
+
+Small circuits only (python loops).  Only tests may import this.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence
+
+from .field_model import Field, OPS
+
+K_NONE, K_OWN, K_SUB, K_CONST, K_TMP, K_ONE = 0, 1, 2, 3, 4, 5
+
+
+class AssertFailed(Exception):
+    pass
+
+
+class _Comp:
+    __slots__ = ("tmpl", "start", "counter", "subs", "ran")
+
+
+def evaluate(desc, inputs: Dict[str, Sequence[int]], check_asserts: bool = True) -> List[int]:
+    """Returns the value of every signal, indexed by global signal id."""
+    F = Field(desc.prime)
+    S = desc.total_signals
+    sig = [None] * S
+    sig[0] = 1
+    consts = desc.consts
+
+    def create(tmpl, start):
+        c = _Comp()
+        c.tmpl, c.start, c.counter, c.ran = tmpl, start, tmpl.n_in, False
+        c.subs = [None] * len(tmpl.subs)
+        return c
+
+    def run(c):
+        assert not c.ran
+        c.ran = True
+        t = c.tmpl
+        tmp = [None] * t.n_tmp
+        off = c.start + t.n_own
+        for i, s in enumerate(t.subs):     # CreateCmp buckets
+            c.subs[i] = create(s.tmpl, off)
+            off += s.tmpl.total_signals
+            if s.tmpl.n_in == 0:
+                run(c.subs[i])
+
+        def load(r):
+            k = r[0]
+            if k == K_OWN: v = sig[c.start + r[2]]
+            elif k == K_SUB: v = sig[c.subs[r[1]].start + r[2]]
+            elif k == K_CONST: v = consts[r[2]]
+            elif k == K_TMP: v = tmp[r[2]]
+            elif k == K_ONE: v = 1
+            else: return 0
+            if v is None:
+                raise RuntimeError("read of unassigned value %r in %s" % (r, t.name))
+            return v
+
+        for op, d, a, b, cc in t.ops:
+            if op == OPS["ASSERT_EQ"]:
+                if check_asserts and load(a) != load(b):
+                    raise AssertFailed(t.name)
+                continue
+            if op == OPS["ASSERT"]:
+                if check_asserts and load(a) == 0:
+                    raise AssertFailed(t.name)
+                continue
+            v = F.apply(op, load(a), load(b), load(cc))
+            if d[0] == K_TMP:
+                tmp[d[2]] = v
+            elif d[0] == K_OWN:
+                g = c.start + d[2]
+                assert sig[g] is None, "signal assigned twice"
+                sig[g] = v
+            elif d[0] == K_SUB:
+                sc = c.subs[d[1]]
+                g = sc.start + d[2]
+                assert sig[g] is None, "signal assigned twice"
+                sig[g] = v
+                if sc.tmpl.n_out <= d[2] < sc.tmpl.n_out + sc.tmpl.n_in:
+                    sc.counter -= 1
+                    if sc.counter == 0:
+                        run(sc)
+        for sc in c.subs:
+            assert sc.ran, "sub-component never triggered"
+
+    main = create(desc.main, 1)
+    for name, gid, n in desc.main_inputs():
+        vals = inputs[name]
+        if n == 1 and not isinstance(vals, (list, tuple)):
+            vals = [vals]
+        assert len(vals) == n, name
+        for j, v in enumerate(vals):
+            sig[gid + j] = int(v) % F.q
+    run(main)
+    return sig
+
+
+def check_r1cs(desc, sig: List[int]) -> int:
+    """Number of violated constraints (A.w * B.w - C.w != 0), evaluated straight from the
+    description with python ints."""
+    q = desc.q
+    bad = 0
+
+    def walk(t, start):
+        nonlocal bad
+        offs = []
+        off = start + t.n_own
+        for s in t.subs:
+            offs.append(off)
+            off += s.tmpl.total_signals
+
+        def val(k):
+            if k[0] == K_OWN: return sig[start + k[2]]
+            if k[0] == K_SUB: return sig[offs[k[1]] + k[2]]
+            if k[0] == K_ONE: return 1
+            raise ValueError(k)
+
+        for A, B, C in t.constraints:
+            a = sum(v * val(k) for k, v in A.items()) % q
+            b = sum(v * val(k) for k, v in B.items()) % q
+            c = sum(v * val(k) for k, v in C.items()) % q
+            if (a * b - c) % q:
+                bad += 1
+        for s, o in zip(t.subs, offs):
+            walk(s.tmpl, o)
+
+    walk(desc.main, 1)
+    return bad

@@ -1,0 +1,227 @@
+// TEST INFRASTRUCTURE: executes the lowered tape on the CPU with the very same field/ops source the
+// kernels compile (circom_b200/csrc/fr_device.cuh is host+device code), so the lowering
+// (flatten.cpp) and the device arithmetic can be checked against the oracle without a GPU.
+// This is NOT a product code path: libcircom_b200.so has no CPU execution and tests that
+// need real kernels are marked `gpu`.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../circom_b200/csrc/fr_device.cuh"
+#include "../../circom_b200/csrc/tape.h"
+
+using namespace cw;
+
+static FrParams dev_params(const FieldParams &F) {
+    FrParams p;
+    memset(&p, 0, sizeof(p));
+    auto split = [](u32 *dst, const U256 &v) {
+        for (int i = 0; i < 4; ++i) {
+            dst[2 * i] = (u32)v.v[i];
+            dst[2 * i + 1] = (u32)(v.v[i] >> 32);
+        }
+    };
+    split(p.q, F.q);
+    split(p.half, F.half);
+    split(p.r1, F.r1);
+    split(p.r2, F.r2);
+    U256 two = u256_from_u64(2), qm2;
+    u256_sub(qm2, F.q, two);
+    split(p.qm2, qm2);
+    p.np32 = F.np32;
+    p.qbits = F.qbits;
+    p.top_mask = (1u << (F.qbits - 224)) - 1u;
+    return p;
+}
+
+static std::string g_err;
+
+extern "C" {
+
+const char *hs_last_error() { return g_err.c_str(); }
+
+// returns 0 on success; witness[batch][W][4 u64]; status[batch] like cw_batch_status
+int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inputs, uint32_t batch,
+           uint64_t *witness, int32_t *status, uint64_t *stats /*8*/) {
+    Tape t;
+    try {
+        lower_circuit(cb2c, len, flags, t);
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+    FrParams P = dev_params(t.F);
+    size_t n_ops = t.n_tape_ops();
+    if (stats) {
+        stats[0] = t.n_signals; stats[1] = n_ops; stats[2] = t.n_levels(); stats[3] = t.n_slots;
+        stats[4] = t.n_mul_ops; stats[5] = t.n_conv_ops; stats[6] = t.r1cs.n_constraints; stats[7] = t.n_ir_ops;
+    }
+    std::vector<u32> slots((size_t)t.n_slots * 8);
+    for (uint32_t inst = 0; inst < batch; ++inst) {
+        std::fill(slots.begin(), slots.end(), 0xDEADBEEFu);  // poison: reads before writes show up
+        u32 one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+        memcpy(&slots[0], one, 32);
+        memcpy(&slots[8], inputs + (size_t)inst * t.n_inputs * 4, t.n_inputs * 32);
+        uint32_t first_assert = 0xFFFFFFFFu;
+        int err = 0;
+        auto operand = [&](u32 o, u32 *v) {
+            if (o & OPERAND_CONST) memcpy(v, t.consts[o & 0x7FFFFFFFu].v, 32);
+            else memcpy(v, &slots[(size_t)o * 8], 32);
+        };
+        // level order == tape order
+        for (size_t i = 0; i < n_ops; ++i) {
+            const uint32_t *op = &t.ops[i * 4];
+            u32 a[8], b[8], r[8];
+            operand(op[1], a);
+            operand(op[2], b);
+            if (op[0] == OP_SELECT) {
+                u32 c[8];
+                operand(op[3], c);
+                memcpy(r, u256_is_zero(c) ? b : a, 32);
+            } else if (op[0] == OP_ASSERT_EQ || op[0] == OP_ASSERT) {
+                bool ok = op[0] == OP_ASSERT_EQ ? u256_eq(a, b) : !u256_is_zero(a);
+                if (!ok && op[3] < first_assert) first_assert = op[3];
+                continue;
+            } else {
+                fr_exec(op[0], r, a, b, P, err);
+            }
+            memcpy(&slots[((size_t)t.n_pre + i) * 8], r, 32);
+        }
+        for (uint64_t w = 0; w < t.n_witness; ++w) {
+            u32 ws = t.witness_slot[w];
+            u32 v[8];
+            memcpy(v, &slots[(size_t)(ws & 0x7FFFFFFFu) * 8], 32);
+            if (ws & WSLOT_MONT) {
+                u32 x[8];
+                fr_from_mont(x, v, P);
+                memcpy(v, x, 32);
+            }
+            memcpy(witness + ((size_t)inst * t.n_witness + w) * 4, v, 32);
+        }
+        status[inst] = err ? -1 : (first_assert == 0xFFFFFFFFu ? 0 : (int32_t)(first_assert + 1));
+    }
+    return 0;
+}
+
+// level structure check: every operand slot of an op in level l is produced in a level < l
+int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
+    Tape t;
+    try {
+        lower_circuit(cb2c, len, flags, t);
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+    std::vector<uint32_t> lvl(t.n_slots, 0);
+    for (size_t l = 0; l < t.n_levels(); ++l)
+        for (uint32_t i = t.level_start[l]; i < t.level_start[l + 1]; ++i) lvl[t.n_pre + i] = (uint32_t)l + 1;
+    if (t.n_levels() && t.level_start[t.n_levels()] != t.n_tape_ops()) { g_err = "level table does not cover the tape"; return -2; }
+    for (size_t i = 0; i < t.n_tape_ops(); ++i) {
+        const uint32_t *op = &t.ops[i * 4];
+        bool is_assert = op[0] == OP_ASSERT || op[0] == OP_ASSERT_EQ;
+        for (int k = 1; k <= 3; ++k) {
+            if (k == 3 && is_assert) break;
+            if (op[k] & OPERAND_CONST) {
+                if ((op[k] & 0x7FFFFFFFu) >= t.consts.size()) { g_err = "constant index out of range"; return -3; }
+                continue;
+            }
+            if (op[k] >= t.n_slots) { g_err = "slot out of range"; return -4; }
+            if (lvl[op[k]] >= lvl[t.n_pre + i]) { g_err = "operand not produced in an earlier level"; return -5; }
+        }
+    }
+    return 0;
+}
+
+// single field op with the same representation handling as fr_batch_op_kernel
+int hs_fr_op(int prime, int op, const uint64_t *A, const uint64_t *B, const uint64_t *C, uint64_t *R, size_t n) {
+    FieldParams F = make_field(prime);
+    FrParams P = dev_params(F);
+    int any_err = 0;
+    for (size_t i = 0; i < n; ++i) {
+        u32 a[8], b[8] = {0}, c[8] = {0}, r[8];
+        memcpy(a, A + 4 * i, 32);
+        if (B) memcpy(b, B + 4 * i, 32);
+        if (C) memcpy(c, C + 4 * i, 32);
+        int e = 0;
+        if (op == OP_MUL) {
+            u32 am[8];
+            fr_to_mont(am, a, P);
+            fr_mont_mul(r, am, b, P);
+        } else if (op == 2) {
+            u32 bm[8], im[8];
+            fr_to_mont(bm, b, P);
+            fr_inv_mont(im, bm, P);
+            fr_mont_mul(r, im, a, P);
+        } else if (op == OP_POW) {
+            u32 am[8], rm[8];
+            fr_to_mont(am, a, P);
+            fr_pow_mont(rm, am, b, P);
+            fr_from_mont(r, rm, P);
+        } else if (op == OP_INV) {
+            u32 am[8], rm[8];
+            fr_to_mont(am, a, P);
+            fr_inv_mont(rm, am, P);
+            fr_from_mont(r, rm, P);
+        } else if (op == OP_SELECT) {
+            memcpy(r, u256_is_zero(c) ? b : a, 32);
+        } else {
+            fr_exec((u32)op, r, a, b, P, e);
+        }
+        any_err |= e;
+        memcpy(R + 4 * i, r, 32);
+    }
+    return any_err;
+}
+
+// R1CS check with the kernel's arithmetic (Montgomery coefficient dictionary)
+int hs_r1cs_check(const uint8_t *cb2c, size_t len, const uint64_t *witness, uint32_t batch, int64_t *first_bad) {
+    Tape t;
+    try {
+        lower_circuit(cb2c, len, 0, t);
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+    FrParams P = dev_params(t.F);
+    const R1csData &R = t.r1cs;
+    std::vector<U256> dm(R.dict.size());
+    for (size_t i = 0; i < dm.size(); ++i) dm[i] = t.F.to_mont(R.dict[i]);
+    for (uint32_t inst = 0; inst < batch; ++inst) {
+        const uint64_t *w = witness + (size_t)inst * R.n_wires * 4;
+        first_bad[inst] = -1;
+        for (uint64_t row = 0; row < R.n_constraints && first_bad[inst] < 0; ++row) {
+            u32 acc[3][8];
+            for (int m = 0; m < 3; ++m) {
+                u256_set_u32(acc[m], 0);
+                for (uint64_t k = R.row_ptr[3 * row + m]; k < R.row_ptr[3 * row + m + 1]; ++k) {
+                    u32 x[8], cm[8], p[8], s[8];
+                    memcpy(x, w + 4 * (size_t)R.col[k], 32);
+                    memcpy(cm, dm[R.coef[k]].v, 32);
+                    fr_mont_mul(p, cm, x, P);
+                    fr_add(s, acc[m], p, P);
+                    memcpy(acc[m], s, 32);
+                }
+            }
+            u32 ab[8], c1[8];
+            fr_mont_mul(ab, acc[0], acc[1], P);
+            fr_from_mont(c1, acc[2], P);
+            if (!u256_eq(ab, c1)) first_bad[inst] = (int64_t)row;
+        }
+    }
+    return 0;
+}
+
+int hs_write_r1cs(const uint8_t *cb2c, size_t len, const char *path) {
+    Tape t;
+    try {
+        lower_circuit(cb2c, len, 0, t);
+        write_r1cs(t.r1cs, t.F, path);
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+    return 0;
+}
+
+}  // extern "C"

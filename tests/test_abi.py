@@ -1,0 +1,103 @@
+"""The C-ABI library builds, loads and exports every symbol include/circom_b200.h declares.
+No compute calls here (no GPU); lowering-only entry points are exercised with CW_FLAG_HOST_ONLY."""
+import ctypes
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+from circom_b200 import native
+from circom_b200.circuit import CircuitDesc
+from circom_b200 import circuits as C
+from circom_b200.witness_calculator import Circuit, R1cs, fnv_hash, qualify_input, parse_value
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_every_declared_symbol_is_exported():
+    hdr = open(os.path.join(ROOT, "include", "circom_b200.h")).read()
+    names = set(re.findall(r"\b(cw_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) > 35
+    for n in names:
+        assert hasattr(native.lib, n), "missing export " + n
+    assert native.lib.cw_version() >= 100
+
+
+def test_no_device_is_an_error_not_a_fallback():
+    if native.lib.cw_device_count() > 0:
+        pytest.skip("GPU present")
+    d = CircuitDesc("bn128")
+    d.set_main(C.multiplier2(d))
+    c = Circuit(d)
+    h = ctypes.c_void_p()
+    rc = native.lib.cw_batch_create(c._h, 4, 0, ctypes.byref(h))
+    assert rc == native.CW_ENODEV
+    assert b"no CPU execution path" in native.lib.cw_last_error()
+
+
+def test_metadata_matches_reference_getters():
+    d = CircuitDesc("bn128")
+    d.set_main(C.multiplier2(d))
+    c = Circuit(d, host_only=True)
+    L = native.lib
+    assert L.cw_get_main_input_signal_start(c._h) == 2      # get_main_input_signal_start = outputs + 1
+    assert L.cw_get_main_input_signal_no(c._h) == 2
+    assert L.cw_get_total_signal_no(c._h) == 4
+    assert L.cw_get_size_of_witness(c._h) == 4
+    assert L.cw_get_number_of_components(c._h) == 1
+    assert L.cw_get_size_of_input_hashmap(c._h) == 256      # max(256, 2^ceil(log2 n)) c_elements/mod.rs:167-169
+    assert c.input_signal_size("a") == 1 and c.input_signal_size("b") == 1
+    assert c.input_signal_id("a") == 2 and c.input_signal_id("b") == 3
+    assert c.input_signal_size("nope") == -1
+    assert fnv_hash("a") == L.cw_fnv1a(b"a")
+    assert c.prime == d.q
+
+
+def test_dat_layout(tmp_path):
+    """hash map (24-byte entries, linear probing on hash % size) + witness2signal list,
+    c_code_generator.rs:575-603,605-614."""
+    d = CircuitDesc("bn128")
+    d.set_main(C.multiplier2(d))
+    c = Circuit(d, host_only=True)
+    p = str(tmp_path / "m.dat")
+    c.write_dat(p)
+    raw = open(p, "rb").read()
+    assert len(raw) == 256 * 24 + 4 * 8
+    ent = {}
+    for i in range(256):
+        h, sid, sz = struct.unpack_from("<QQQ", raw, i * 24)
+        if sid:
+            ent[h] = (i, sid, sz)
+    assert ent[fnv_hash("a")][1:] == (2, 1) and ent[fnv_hash("b")][1:] == (3, 1)
+    assert ent[fnv_hash("a")][0] == fnv_hash("a") % 256
+    assert struct.unpack_from("<4Q", raw, 256 * 24) == (0, 1, 2, 3)
+
+
+def test_input_flattening_rules():
+    out = {}
+    qualify_input("", {"a": 1, "b": {"c": [1, 2], "d": [{"x": 1}, {"x": 2}]}}, out)
+    assert out == {"a": 1, "b.c": [1, 2], "b.d[0].x": 1, "b.d[1].x": 2}
+    q = 101
+    assert parse_value("0x10", q) == 16 and parse_value("0b11", q) == 3 and parse_value("0o17", q) == 15
+    assert parse_value("205", q) == 3 and parse_value(7, q) == 7
+    with pytest.raises(ValueError):
+        parse_value("-3", q)      # the reference accepts no sign (main.cpp:126-142)
+
+
+def test_r1cs_write_read_roundtrip(tmp_path):
+    d = CircuitDesc("bls12381")
+    d.set_main(C.less_than(d, 8))
+    c = Circuit(d, host_only=True)
+    r = R1cs(c)
+    assert r.n_constraints == c.stats["n_constraints"] and r.prime_id == 1
+    p1, p2 = str(tmp_path / "a.r1cs"), str(tmp_path / "b.r1cs")
+    r.write(p1, 1, 0, 2)
+    r2 = R1cs(p1)
+    assert (r2.n_wires, r2.n_constraints, r2.nnz) == (r.n_wires, r.n_constraints, r.nnz)
+    r2.write(p2, 1, 0, 2)
+    assert open(p1, "rb").read() == open(p2, "rb").read()
+    raw = open(p1, "rb").read()
+    assert raw[:4] == b"r1cs" and struct.unpack_from("<II", raw, 4) == (1, 3)
+    assert struct.unpack_from("<I", raw, 12)[0] == 2   # constraints section comes first (r1cs_porting.rs:19-53)

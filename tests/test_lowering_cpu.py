@@ -1,0 +1,110 @@
+"""CPU checks of the lowering (flatten.cpp) and of the host+device field source (fr_device.cuh):
+the tape is executed by tests/hostsim (which compiles the same source the kernels use) and
+compared bit-for-bit with the oracle.  No GPU needed; the GPU parity tests are in test_gpu_*.py."""
+import ctypes
+import random
+
+import numpy as np
+import pytest
+
+from circom_b200.circuit import CircuitDesc, OPS
+from circom_b200 import circuits as C
+from oracle.field_model import Field, OP_NAMES, DivisionByZero
+from oracle.ir_eval import evaluate, check_r1cs
+from tests.util import hostsim, hostsim_run, ints_to_limbs, limbs_to_ints, edge_values, rand_operand
+
+CIRCUITS = {
+    "multiplier2": (lambda d: C.multiplier2(d), lambda r, q: {"a": r.randrange(q), "b": r.randrange(q)}),
+    "all_ops": (lambda d: C.all_ops(d),
+                lambda r, q: {"a": r.choice([0, 1, q - 1, r.randrange(q), r.randrange(2**64)]),
+                              "b": r.choice([0, 1, 5, 255, q - 3, r.randrange(q), r.randrange(300)])}),
+    "less_than8": (lambda d: C.less_than(d, 8), lambda r, q: {"in": [r.randrange(256), r.randrange(256)]}),
+    "num2bits64": (lambda d: C.num2bits(d, 64), lambda r, q: {"in": r.randrange(2**64)}),
+    "multiplier_n6": (lambda d: C.multiplier_n(d, 6), lambda r, q: {"in": [r.randrange(q) for _ in range(6)]}),
+    "is_zero": (lambda d: C.is_zero(d), lambda r, q: {"in": r.choice([0, r.randrange(q)])}),
+}
+
+
+@pytest.mark.parametrize("prime", ["bn128", "bls12381"])
+@pytest.mark.parametrize("name", sorted(CIRCUITS))
+def test_tape_matches_oracle(prime, name):
+    mk, gen = CIRCUITS[name]
+    d = CircuitDesc(prime)
+    d.set_main(mk(d))
+    import zlib
+    rng = random.Random(zlib.crc32((prime + name).encode()))
+    ins = [gen(rng, d.q) for _ in range(24)]
+    wit, st, stats = hostsim_run(d, ins)
+    for i, inp in enumerate(ins):
+        exp = evaluate(d, inp)
+        assert check_r1cs(d, exp) == 0
+        assert limbs_to_ints(wit[i]) == exp, (prime, name, i)
+    assert not st.any()
+
+
+def test_assert_failure_is_reported():
+    """`===` violated -> status k+1 of the first failing assert (reference: assert(Fr_isTrue(..)) aborts,
+    assert_bucket.rs:70-88)."""
+    d = CircuitDesc("bn128")
+
+    def build(t):
+        a = t.input("a")
+        b = t.input("b")
+        o = t.output("o")
+        t.assign(o, a + b)
+        t.constrain(a * b, o)       # only true for special inputs
+        t.constrain(a, b)           # second assert
+    d.set_main(d.template("Bad", (), build))
+    wit, st, _ = hostsim_run(d, [{"a": 2, "b": 2}, {"a": 2, "b": 3}, {"a": 0, "b": 5}])
+    assert st.tolist() == [0, 1, 1]
+    wit, st, _ = hostsim_run(d, [{"a": 2, "b": 3}], flags=1)  # CW_FLAG_NO_ASSERTS
+    assert st.tolist() == [0]
+
+
+@pytest.mark.parametrize("prime", [0, 1])
+def test_device_field_source_vs_model(prime):
+    """every operator of fr_device.cuh (compiled for the host) against the python model"""
+    F = Field(["bn128", "bls12381"][prime])
+    q = F.q
+    rng = random.Random(77 + prime)
+    edges = edge_values(q)
+    hs = hostsim()
+    n = 3000
+    A = [rand_operand(rng, q, edges) for _ in range(n)]
+    B = [rand_operand(rng, q, edges) if rng.random() > 0.25 else rng.randrange(300) for _ in range(n)]
+    Cc = [rng.choice([0, 1, rng.randrange(q)]) for _ in range(n)]
+    a, b, c = ints_to_limbs(A), ints_to_limbs(B), ints_to_limbs(Cc)
+    r = np.zeros((n, 4), dtype=np.uint64)
+    for op in list(range(1, 24)) + [OPS["SELECT"], 28]:
+        m = n if op not in (OPS["POW"], OPS["DIV"], 28) else 150
+        err = hs.hs_fr_op(prime, op, a.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p),
+                          c.ctypes.data_as(ctypes.c_void_p), r.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(m))
+        got = limbs_to_ints(r[:m])
+        for i in range(m):
+            if op == 28:
+                exp = F.inv(A[i])
+            elif op in (OPS["IDIV"], OPS["MOD"]) and B[i] == 0:
+                assert err == 1
+                continue
+            else:
+                exp = F.apply(op, A[i], B[i], Cc[i])
+            assert got[i] == exp, (OP_NAMES.get(op, op), hex(A[i]), hex(B[i]), hex(got[i]), hex(exp))
+
+
+def test_r1cs_check_arithmetic_and_violation_detection():
+    hs = hostsim()
+    d = CircuitDesc("bn128")
+    d.set_main(C.less_than(d, 16))
+    blob = d.to_bytes()
+    rng = random.Random(3)
+    ins = [{"in": [rng.randrange(65536), rng.randrange(65536)]} for _ in range(6)]
+    wit, st, stats = hostsim_run(d, ins)
+    fb = np.zeros(len(ins), dtype=np.int64)
+    assert hs.hs_r1cs_check(blob, ctypes.c_size_t(len(blob)), wit.ctypes.data_as(ctypes.c_void_p), len(ins),
+                            fb.ctypes.data_as(ctypes.c_void_p)) == 0
+    assert (fb == -1).all()
+    bad = wit.copy()
+    bad[2, 5, 0] ^= 1  # flip one bit of one wire of instance 2
+    assert hs.hs_r1cs_check(blob, ctypes.c_size_t(len(blob)), bad.ctypes.data_as(ctypes.c_void_p), len(ins),
+                            fb.ctypes.data_as(ctypes.c_void_p)) == 0
+    assert fb[2] >= 0 and (np.delete(fb, 2) == -1).all()

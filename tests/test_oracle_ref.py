@@ -1,0 +1,95 @@
+"""The oracle is pinned against the compiled REFERENCE field library (oracle/_ref/libfr_<prime>.so,
+the reference's own generic/fr.cpp) over every operator and operand representation, and against
+the few worked values the reference tree contains (there are no golden vectors in its tests:
+SURVEY.md section 8(c))."""
+import os
+import random
+
+import pytest
+
+from oracle.field_model import Field, OPS, OP_NAMES, PRIMES
+from tests.util import edge_values, rand_operand
+
+REF_OK = os.path.exists(os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "libfr_bn128.so")) or \
+    os.path.isdir("/root/reference")
+needs_ref = pytest.mark.skipif(not REF_OK, reason="oracle/_ref not built and no reference tree")
+
+
+def _reps(R, v, q):
+    out = [("long", v), ("mont", v)]
+    sv = v if v < 2**31 else (v - q if q - v <= 2**31 else None)
+    if sv is not None:
+        out.append(("short", sv))
+    return out
+
+
+@needs_ref
+@pytest.mark.parametrize("prime", ["bn128", "bls12381"])
+def test_model_matches_reference_fr(prime):
+    from oracle.ref_fr import RefFr
+    F, R = Field(prime), RefFr(prime)
+    q = F.q
+    rng = random.Random(1234)
+    edges = edge_values(q)
+    n = 0
+    for it in range(700):
+        a, b = rand_operand(rng, q, edges), rand_operand(rng, q, edges)
+        if rng.random() < 0.25:
+            b = rng.randrange(300)
+        for op in range(1, 24):
+            if op in (OPS["IDIV"], OPS["MOD"]) and b == 0:
+                continue
+            if op == OPS["POW"] and it % 10:
+                continue
+            exp = F.apply(op, a, b)
+            for ra, va in _reps(R, a, q):
+                for rb, vb in _reps(R, b, q):
+                    got = R.apply(op, R.make(va, ra), R.make(vb, rb))
+                    n += 1
+                    assert got == exp, (prime, OP_NAMES[op], ra, rb, hex(a), hex(b), hex(got), hex(exp))
+    assert n > 50000
+
+
+@needs_ref
+def test_reference_division_by_zero_is_zero():
+    """Fr_inv ignores mpz_invert's failure (generic/fr.cpp:2895-2906): x/0 == 0 with GMP 6.3."""
+    from oracle.ref_fr import RefFr
+    R = RefFr("bn128")
+    for rep in ("long", "mont"):
+        assert R.apply(OPS["DIV"], R.make(7, rep), R.make(0, "long")) == 0
+    assert Field("bn128").div(7, 0) == 0
+
+
+@needs_ref
+def test_reference_str2element():
+    """Fr_str2element (generic/fr.cpp:2805-2811): base 10/16/2/8 strings reduced mod q."""
+    from oracle.ref_fr import RefFr
+    R = RefFr("bn128")
+    q = PRIMES["bn128"]
+    assert R.str2element("33") == 33
+    assert R.str2element(str(q + 5)) == 5
+    assert R.str2element("ff", 16) == 255
+    assert R.str2element("101", 2) == 5
+
+
+def test_toy_field_values_from_reference_unit_tests():
+    """circom_algebra/src/modular_arithmetic.rs:217-269 (p = 257): the only arithmetic values the
+    reference's own tests pin."""
+    F = Field(257)
+    assert (-8) % 5 == 2                     # mod_check: modulus(-8, 5) == 2
+    assert F.leq(0, 2) == 1                  # lesser_eq_test
+    assert F.lt(200, 3) == 1                 # comparison_check: 200 is negative in the signed view
+    for x in (0, 1, 5, 128, 256):            # complement_of_complement_is_the_original_test
+        assert F.bnot(F.bnot(x)) == x % 257 or x > F.mask
+
+
+def test_docs_worked_example_multiplier2():
+    """mkdocs/docs/getting-started/computing-the-witness.md:16-24: a=3, b=11 -> c=33."""
+    from circom_b200.circuit import CircuitDesc
+    from circom_b200 import circuits as C
+    from oracle.ir_eval import evaluate, check_r1cs
+    d = CircuitDesc("bn128")
+    d.set_main(C.multiplier2(d))
+    w = evaluate(d, {"a": 3, "b": 11})
+    assert w == [1, 33, 3, 11]
+    assert check_r1cs(d, w) == 0

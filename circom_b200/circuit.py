@@ -55,14 +55,26 @@ class Expr:
     most quadratic in the signals, its symbolic form (the role of
     circom_algebra::ArithmeticExpression, algebra.rs:9)."""
 
-    __slots__ = ("t", "ref", "lin", "quad", "const")
+    __slots__ = ("t", "_ref", "terms", "lin", "quad", "const")
 
-    def __init__(self, t: "Template", ref: Ref, lin=None, quad=None, const=None):
+    def __init__(self, t: "Template", ref: Optional[Ref], lin=None, quad=None, const=None, terms=None):
         self.t = t
-        self.ref = ref
+        self._ref = ref
+        self.terms = terms  # pending n-ary sum: list of (sign, Expr); materialised on first use
         self.lin = lin      # dict key->coeff ; key = Ref of a signal or ONE_REF
         self.quad = quad    # (A, B, C) dicts
         self.const = const  # int if compile-time constant
+
+    @property
+    def ref(self) -> Ref:
+        """Where the value lives.  A pending sum is emitted here as a balanced tree of ADD/SUB:
+        field addition is associative and commutative, so re-associating the accumulation chains
+        circom programs write (`lc += x*2**k`) changes no value but shortens the dependency
+        depth of the tape from n to log2(n)."""
+        if self._ref is None:
+            self._ref = self.t._materialise(self.terms)
+            self.terms = None
+        return self._ref
 
     # -- coercion -------------------------------------------------------------
     def _co(self, o) -> "Expr":
@@ -200,30 +212,58 @@ class Template:
             return self.const(v)
         return None
 
-    def _add(self, a: Expr, b: Expr) -> Expr:
-        f = self._fold("ADD", a, b)
+    @staticmethod
+    def _terms_of(e: Expr, sign: int):
+        if e._ref is None and e.terms is not None:
+            return [(sg * sign, x) for sg, x in e.terms]
+        return [(sign, e)]
+
+    def _materialise(self, terms) -> Ref:
+        pos = [x for sg, x in terms if sg > 0]
+        neg = [x for sg, x in terms if sg < 0]
+
+        def tree(xs):
+            xs = list(xs)
+            while len(xs) > 1:
+                nxt = []
+                for i in range(0, len(xs) - 1, 2):
+                    nxt.append(Expr(self, self._emit("ADD", xs[i], xs[i + 1])))
+                if len(xs) & 1:
+                    nxt.append(xs[-1])
+                xs = nxt
+            return xs[0]
+        if pos and neg:
+            return self._emit("SUB", tree(pos), tree(neg))
+        if pos:
+            p = tree(pos)
+            return p.ref
+        return self._emit("NEG", tree(neg))
+
+    def _addsub(self, a: Expr, b: Expr, sign: int) -> Expr:
+        f = self._fold("ADD" if sign > 0 else "SUB", a, b)
         if f: return f
-        r = Expr(self, self._emit("ADD", a, b))
+        if a.const == 0 and sign > 0:
+            return b
+        if b.const == 0:
+            return a
+        r = Expr(self, None, terms=self._terms_of(a, 1) + self._terms_of(b, sign))
+        q = self.q
         if a.lin is not None and b.lin is not None:
-            r.lin = _lin_add(a.lin, b.lin, self.q)
+            r.lin = _lin_add(a.lin, b.lin, q, sign)
         elif a.quad is not None and b.lin is not None:
-            r.quad = (a.quad[0], a.quad[1], _lin_add(a.quad[2], b.lin, self.q))
+            r.quad = (a.quad[0], a.quad[1], _lin_add(a.quad[2], b.lin, q, sign))
         elif b.quad is not None and a.lin is not None:
-            r.quad = (b.quad[0], b.quad[1], _lin_add(b.quad[2], a.lin, self.q))
+            if sign > 0:
+                r.quad = (b.quad[0], b.quad[1], _lin_add(b.quad[2], a.lin, q))
+            else:
+                r.quad = (_lin_scale(b.quad[0], q - 1, q), b.quad[1], _lin_add(a.lin, b.quad[2], q, -1))
         return r
 
+    def _add(self, a: Expr, b: Expr) -> Expr:
+        return self._addsub(a, b, 1)
+
     def _sub(self, a: Expr, b: Expr) -> Expr:
-        f = self._fold("SUB", a, b)
-        if f: return f
-        r = Expr(self, self._emit("SUB", a, b))
-        if a.lin is not None and b.lin is not None:
-            r.lin = _lin_add(a.lin, b.lin, self.q, -1)
-        elif a.quad is not None and b.lin is not None:
-            r.quad = (a.quad[0], a.quad[1], _lin_add(a.quad[2], b.lin, self.q, -1))
-        elif b.quad is not None and a.lin is not None:
-            nA = _lin_scale(b.quad[0], self.q - 1, self.q)
-            r.quad = (nA, b.quad[1], _lin_add(a.lin, b.quad[2], self.q, -1))
-        return r
+        return self._addsub(a, b, -1)
 
     def _mul(self, a: Expr, b: Expr) -> Expr:
         f = self._fold("MUL", a, b)

@@ -41,7 +41,10 @@ uint64_t fnv1a(const char *s, size_t n) {  // calcwit.cpp:17-24
 namespace {
 
 enum { K_NONE = 0, K_OWN = 1, K_SUB = 2, K_CONST = 3, K_TMP = 4, K_ONE = 5 };
-enum Form { FC = 0, FM = 1 };
+// FC canonical x; FM Montgomery x*R; FD "deferred" x*R^-1: the raw Montgomery product of two canonical
+// operands.  Zero tests read any form; FD is converted (one product, like converting an input would
+// have cost) only if a consumer needs the value itself.
+enum Form { FC = 0, FM = 1, FD = 2 };
 
 struct IrOp {
     uint32_t op;
@@ -58,6 +61,7 @@ struct Tmpl {
     std::vector<IrOp> ops;
     std::vector<uint32_t> lc_len;  // 3 per constraint
     std::vector<Term> terms;
+    std::vector<uint8_t> tmp_zero_only;  // temporary is consumed by zero / non-zero tests only
     uint64_t total_signals = 0, total_components = 0;
 };
 
@@ -89,7 +93,7 @@ struct Reader {
 };
 
 struct Val {
-    uint32_t slot[2] = {NO_SLOT, NO_SLOT};  // provisional slot holding the canonical / Montgomery image
+    uint32_t slot[3] = {NO_SLOT, NO_SLOT, NO_SLOT};  // provisional slot per representation (Form)
     int32_t cid = -1;                       // IR constant id if this value is a compile-time constant
 };
 
@@ -148,24 +152,44 @@ struct Lowerer {
     }
     bool has(int32_t vid, Form f) const { return vals[vid].cid >= 0 || vals[vid].slot[f] != NO_SLOT; }
     bool is_const(int32_t vid) const { return vals[vid].cid >= 0; }
-    // operand holding `vid` in form `f`, converting (once) if necessary
+    // operand holding `vid` in form `f` (FC or FM), converting (once) if necessary
     uint32_t need(int32_t vid, Form f) {
         Val &v = vals[vid];
         if (v.cid >= 0) return const_operand(v.cid, f);
         if (v.slot[f] != NO_SLOT) return v.slot[f];
         uint32_t src = v.slot[1 - f];
-        if (src == NO_SLOT) throw std::runtime_error("lowering: value without representation");
-        // to Montgomery: MontMul(x, R^2) = x*R ; to canonical: MontMul(xR, 1) = x
-        U256 k = (f == FM) ? F.r2 : u256_from_u64(1);
+        U256 k;
+        if (src != NO_SLOT) {
+            // to Montgomery: MontMul(x, R^2) = x*R ; to canonical: MontMul(xR, 1) = x
+            k = (f == FM) ? F.r2 : u256_from_u64(1);
+        } else {
+            src = v.slot[FD];
+            if (src == NO_SLOT) throw std::runtime_error("lowering: value without representation");
+            // from x/R: MontMul(x/R, R^2) = x ; MontMul(x/R, R^3) = x*R
+            k = (f == FC) ? F.r2 : F.mont_mul(F.r2, F.r2);
+        }
         uint32_t s = emit(CW_OP_MUL, src, OPERAND_CONST | raw_const(k));
         ++n_conv;
         vals[vid].slot[f] = s;
         return s;
     }
+    // operand for a zero / non-zero test: any representation will do
+    uint32_t need_any(int32_t vid) {
+        const Val &v = vals[vid];
+        if (v.cid >= 0) return const_operand(v.cid, FC);
+        for (int f = 0; f < 3; ++f)
+            if (v.slot[f] != NO_SLOT) return v.slot[f];
+        throw std::runtime_error("lowering: value without representation");
+    }
+    bool is_const_zero(int32_t vid) const { return vals[vid].cid >= 0 && ir_consts[vals[vid].cid].is_zero(); }
+    bool only_deferred(int32_t vid) const {
+        const Val &v = vals[vid];
+        return v.cid < 0 && v.slot[FC] == NO_SLOT && v.slot[FM] == NO_SLOT;
+    }
     Form any_form(int32_t vid) const {
         const Val &v = vals[vid];
         if (v.cid >= 0) return FC;
-        return v.slot[FM] != NO_SLOT ? FM : FC;
+        return v.slot[FM] != NO_SLOT ? FM : FC;  // a deferred-only value converts to canonical
     }
     // common form for an operation that needs both operands in the same representation
     Form common_form(int32_t x, int32_t y) const {
@@ -173,12 +197,11 @@ struct Lowerer {
         if (xc && yc) return FC;
         if (xc) return any_form(y);
         if (yc) return any_form(x);
-        if (has(x, FM) && has(y, FM)) return FM;
-        if (has(x, FC) && has(y, FC)) return FC;
-        return FM;
+        int cost_m = !has(x, FM) + !has(y, FM), cost_c = !has(x, FC) + !has(y, FC);
+        return cost_c < cost_m ? FC : FM;  // fewest conversions; ties stay in the Montgomery domain
     }
 
-    int32_t lower_op(uint32_t op, int32_t a, int32_t b, int32_t c) {
+    int32_t lower_op(uint32_t op, int32_t a, int32_t b, int32_t c, bool zero_test_only = false) {
         switch (op) {
             case CW_OP_ADD:
             case CW_OP_SUB: {
@@ -199,7 +222,9 @@ struct Lowerer {
                 if (has(a, FM) && has(b, FM)) return new_val(emit(op, need(a, FM), need(b, FM)), FM);
                 if (has(a, FM)) return new_val(emit(op, need(a, FM), need(b, FC)), FC);
                 if (has(b, FM)) return new_val(emit(op, need(a, FC), need(b, FM)), FC);
-                return new_val(emit(op, need(a, FM), need(b, FC)), FC);  // converts a once
+                if (zero_test_only && has(a, FC) && has(b, FC))
+                    return new_val(emit(op, need(a, FC), need(b, FC)), FD);  // x*y/R is all a zero test needs
+                return new_val(emit(op, need(a, FM), need(b, FC)), FC);
             }
             case CW_OP_DIV: {
                 uint32_t inv = emit(CW_OP_INV, need(b, FM));
@@ -217,17 +242,19 @@ struct Lowerer {
                 return new_val(emit(op, need(a, FC)), FC);
             case CW_OP_EQ:
             case CW_OP_NEQ: {
+                if (is_const_zero(b)) return new_val(emit(op, need_any(a), need(b, FC)), FC);
+                if (is_const_zero(a)) return new_val(emit(op, need(a, FC), need_any(b)), FC);
                 Form f = common_form(a, b);
                 return new_val(emit(op, need(a, f), need(b, f)), FC);
             }
             case CW_OP_LOR:
             case CW_OP_LAND:
-                return new_val(emit(op, need(a, any_form(a)), need(b, any_form(b))), FC);
+                return new_val(emit(op, need_any(a), need_any(b)), FC);
             case CW_OP_LNOT:
-                return new_val(emit(op, need(a, any_form(a))), FC);
+                return new_val(emit(op, need_any(a)), FC);
             case CW_OP_SELECT: {
                 Form f = common_form(a, b);
-                return new_val(emit(op, need(a, f), need(b, f), need(c, any_form(c))), f);
+                return new_val(emit(op, need(a, f), need(b, f), need_any(c)), f);
             }
             default:
                 throw std::runtime_error("lowering: unsupported opcode " + std::to_string(op));
@@ -276,11 +303,15 @@ struct Lowerer {
                 if (flags & CW_FLAG_NO_ASSERTS) continue;
                 if (o.op == CW_OP_ASSERT_EQ) {
                     int32_t a = load(o.a), b = load(o.b);
-                    Form f = common_form(a, b);
-                    emit(CW_OP_ASSERT_EQ, need(a, f), need(b, f), id, true);
+                    if (is_const_zero(b)) emit(CW_OP_ASSERT_EQ, need_any(a), need(b, FC), id, true);
+                    else if (is_const_zero(a)) emit(CW_OP_ASSERT_EQ, need(a, FC), need_any(b), id, true);
+                    else {
+                        Form f = common_form(a, b);
+                        emit(CW_OP_ASSERT_EQ, need(a, f), need(b, f), id, true);
+                    }
                 } else {
                     int32_t a = load(o.a);
-                    emit(CW_OP_ASSERT, need(a, any_form(a)), NO_SLOT, id, true);
+                    emit(CW_OP_ASSERT, need_any(a), NO_SLOT, id, true);
                 }
                 continue;
             }
@@ -289,7 +320,7 @@ struct Lowerer {
                 v = load(o.a);  // a move is an alias
             } else {
                 int32_t a = load(o.a), b = rk(o.b) ? load(o.b) : -1, cc = rk(o.c) ? load(o.c) : -1;
-                v = lower_op(o.op, a, b, cc);
+                v = lower_op(o.op, a, b, cc, rk(o.d) == K_TMP && t.tmp_zero_only[ridx(o.d)]);
             }
             switch (rk(o.d)) {
                 case K_TMP: tmp[ridx(o.d)] = v; break;
@@ -405,6 +436,26 @@ struct Lowerer {
                     t.terms.push_back(tr);
                 }
             }
+            // which temporaries feed only zero / non-zero tests (so a raw product x*y/R suffices)
+            t.tmp_zero_only.assign(t.n_tmp, 1);
+            auto is_zero_const = [&](uint64_t r) { return rk(r) == K_CONST && ridx(r) < n_consts && ir_consts[ridx(r)].is_zero(); };
+            auto mark = [&](uint64_t r, bool zero_use) {
+                if (rk(r) == K_TMP && ridx(r) < t.n_tmp && !zero_use) t.tmp_zero_only[ridx(r)] = 0;
+            };
+            for (const IrOp &o : t.ops) {
+                switch (o.op) {
+                    case CW_OP_ASSERT: case CW_OP_LNOT: case CW_OP_LAND: case CW_OP_LOR:
+                        break;  // every operand is only tested for zero
+                    case CW_OP_SELECT:
+                        mark(o.a, false); mark(o.b, false);
+                        break;
+                    case CW_OP_ASSERT_EQ: case CW_OP_EQ: case CW_OP_NEQ:
+                        mark(o.a, is_zero_const(o.b)); mark(o.b, is_zero_const(o.a));
+                        break;
+                    default:
+                        mark(o.a, false); mark(o.b, false); mark(o.c, false);
+                }
+            }
             t.total_signals = t.n_own;
             t.total_components = 1;
             for (auto s : t.subs) {
@@ -463,6 +514,11 @@ struct Lowerer {
                 vals[v].slot[FC] = s;
                 live.push_back(0);
                 ++n_prov;
+            }
+            if (vals[v].slot[FC] == NO_SLOT && vals[v].slot[FM] == NO_SLOT) {
+                size_t before = pops.size() / 4;
+                need(v, FC);  // a deferred product that is a witness value: convert it now
+                for (size_t k = before; k < pops.size() / 4; ++k) { live.push_back(0); ++n_prov; }
             }
             if (vals[v].slot[FC] != NO_SLOT) wslot[i] = vals[v].slot[FC];
             else wslot[i] = vals[v].slot[FM] | WSLOT_MONT;

@@ -1,0 +1,237 @@
+"""Hand-lowering of a circuit description into the C++ the reference compiler would print
+(TEST INFRASTRUCTURE), so that the REAL reference runtime — c_elements/common/{main,calcwit}.cpp +
+the rendered generic/fr.cpp, built by oracle/build_ref.py — can execute the same program and
+produce the `.wtns` our GPU path must match byte for byte.
+
+The Rust compiler cannot run here, so this module prints, per template instance, what
+compiler/src/circuit_design/template.rs:177-472 prints (`<T>_create` / `<T>_run`), with the bodies
+the bucket emitters would give for straight-line code:
+
+  Compute   Fr_<op>(&expaux[k], a, b)                          compute_bucket.rs:410-421
+  Load      &signalValues[mySignalStart + i] | &circuitConstants[c] |
+            &ctx->signalValues[ctx->componentMemory[mySubcomponents[s]].signalStart + i]
+                                                               load_bucket.rs:325-447, value_bucket.rs:81-87
+  Store     Fr_copy(dest, src); for a sub-component input: inputCounter -= 1 and run at zero
+                                                               store_bucket.rs:607-734
+  CreateCmp <Sub>_create(mySignalStart + off, ctx_index + coff + 1, ctx, name, myId)
+                                                               create_component_bucket.rs:204-352
+  `===`     Fr_eq + assert(Fr_isTrue)                          assert_bucket.rs:70-88
+  c ? a : b if (Fr_isTrue(c)) .. else ..                       branch_bucket.rs:100-122
+and the file prologue / epilogue of circuit.rs:420-563, plus the matching `.dat`
+(c_code_generator.rs:575-679,818-865: input hash map, witness2signal list, constants in
+Montgomery form with the short/long tag).
+"""
+from __future__ import annotations
+
+import os
+import struct
+from typing import List
+
+K_NONE, K_OWN, K_SUB, K_CONST, K_TMP, K_ONE = 0, 1, 2, 3, 4, 5
+
+_FN = {1: "mul", 2: "div", 3: "add", 4: "sub", 5: "pow", 6: "idiv", 7: "mod", 8: "shl", 9: "shr",
+       10: "leq", 11: "geq", 12: "lt", 13: "gt", 14: "eq", 15: "neq", 16: "lor", 17: "land", 19: "bor",
+       20: "band", 21: "bxor"}
+_FN1 = {18: "lnot", 22: "bnot", 23: "neg"}
+
+
+def fnv1a(s: str) -> int:
+    h = 0xCBF29CE484222325
+    for ch in s.encode():
+        h ^= ch
+        h = (h * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def _header(t) -> str:
+    return "%s_%d" % (t.name, t.id)
+
+
+def emit_cpp(desc) -> str:
+    out: List[str] = []
+    w = out.append
+    main = desc.main
+    for inc in ("<stdio.h>", "<iostream>", "<assert.h>", '"circom.hpp"', '"calcwit.hpp"', '"fr.hpp"'):
+        w("#include %s" % inc)
+    for t in desc.templates:
+        w("void %s_create(uint soffset,uint coffset,Circom_CalcWit* ctx,std::string componentName,uint componentFather);" % _header(t))
+        w("void %s_run(uint ctx_index,Circom_CalcWit* ctx);" % _header(t))
+    w("Circom_TemplateFunction _functionTable[%d] = { %s };" % (
+        len(desc.templates), ",".join("%s_run" % _header(t) for t in desc.templates)))
+    w("Circom_TemplateFunction _functionTableParallel[%d] = { %s };" % (
+        len(desc.templates), ",".join("NULL" for _ in desc.templates)))
+    w("uint get_main_input_signal_start() {return %d;}\n" % (main.n_out + 1))
+    w("uint get_main_input_signal_no() {return %d;}\n" % main.n_in)
+    w("uint get_total_signal_no() {return %d;}\n" % desc.total_signals)
+    w("uint get_number_of_components() {return %d;}\n" % main.total_components)
+    w("uint get_size_of_input_hashmap() {return %d;}\n" % hashmap_size(desc))
+    w("uint get_size_of_witness() {return %d;}\n" % desc.total_signals)
+    w("uint get_size_of_constants() {return %d;}\n" % len(desc.consts))
+    w("uint get_size_of_io_map() {return 0;}\n")
+    w("uint get_size_of_bus_field_map() {return 0;}\n")
+    w("void release_memory_component(Circom_CalcWit* ctx, uint pos) {{\n"
+      "if (pos != 0){{\n"
+      "if(ctx->componentMemory[pos].subcomponents)delete []ctx->componentMemory[pos].subcomponents;\n"
+      "if(ctx->componentMemory[pos].subcomponentsParallel)delete []ctx->componentMemory[pos].subcomponentsParallel;\n"
+      "if(ctx->componentMemory[pos].outputIsSet)delete []ctx->componentMemory[pos].outputIsSet;\n"
+      "if(ctx->componentMemory[pos].mutexes)delete []ctx->componentMemory[pos].mutexes;\n"
+      "if(ctx->componentMemory[pos].cvs)delete []ctx->componentMemory[pos].cvs;\n"
+      "if(ctx->componentMemory[pos].sbct)delete []ctx->componentMemory[pos].sbct;\n"
+      "}}\n}}\n")
+    w("// template declarations")
+    for t in desc.templates:
+        _emit_template(w, t)
+    w("void run(Circom_CalcWit* ctx){")
+    w('%s_create(1,0,ctx,"main",0);' % _header(main))
+    if main.n_in > 0:
+        w("%s_run(0,ctx);" % _header(main))
+    w("}\n")
+    return "\n".join(out)
+
+
+def _emit_template(w, t) -> None:
+    H = _header(t)
+    w("void %s_create(uint soffset,uint coffset,Circom_CalcWit* ctx,std::string componentName,uint componentFather){" % H)
+    w("ctx->componentMemory[coffset].templateId = %d;" % t.id)
+    w('ctx->componentMemory[coffset].templateName = "%s";' % t.name)
+    w("ctx->componentMemory[coffset].signalStart = soffset;")
+    w("ctx->componentMemory[coffset].inputCounter = %d;" % t.n_in)
+    w("ctx->componentMemory[coffset].componentName = componentName;")
+    w("ctx->componentMemory[coffset].idFather = componentFather;")
+    if t.subs:
+        w("ctx->componentMemory[coffset].subcomponents = new uint[%d]{0};" % len(t.subs))
+    else:
+        w("ctx->componentMemory[coffset].subcomponents = new uint[0];")
+    if t.n_in == 0:
+        w("%s_run(coffset,ctx);" % H)
+    w("}\n")
+
+    w("void %s_run(uint ctx_index,Circom_CalcWit* ctx){" % H)
+    w("FrElement* circuitConstants = ctx->circuitConstants;")
+    w("FrElement* signalValues = ctx->signalValues;")
+    # temporaries live in expaux (one slot per SSA temporary + one for assert comparisons)
+    w("static thread_local FrElement expaux_store[%d];" % (t.n_tmp + 1) if t.n_tmp > 4000 else
+      "FrElement expaux_store[%d];" % (t.n_tmp + 1))
+    w("FrElement* expaux = expaux_store;")
+    w("FrElement lvar[1];")
+    w("u64 mySignalStart = ctx->componentMemory[ctx_index].signalStart;")
+    w("std::string myTemplateName = ctx->componentMemory[ctx_index].templateName;")
+    w("std::string myComponentName = ctx->componentMemory[ctx_index].componentName;")
+    w("u64 myFather = ctx->componentMemory[ctx_index].idFather;")
+    w("u64 myId = ctx_index;")
+    w("u32* mySubcomponents = ctx->componentMemory[ctx_index].subcomponents;")
+    w("bool* mySubcomponentsParallel = ctx->componentMemory[ctx_index].subcomponentsParallel;")
+    w("uint sub_component_aux;")
+    w("uint index_multiple_eq;")
+    w("int cmp_index_ref_load = -1;")
+    # CreateCmp buckets
+    soff, coff = t.n_own, 0
+    for i, s in enumerate(t.subs):
+        w("{")
+        w('std::string new_cmp_name = "%s";' % s.name.replace('"', ""))
+        w("%s_create(mySignalStart+%d,%d+ctx_index+1,ctx,new_cmp_name,myId);" % (_header(s.tmpl), soff, coff))
+        w("mySubcomponents[%d] = %d+ctx_index+1;" % (i, coff))
+        w("}")
+        soff += s.tmpl.total_signals
+        coff += s.tmpl.total_components
+
+    def addr(r):
+        k = r[0]
+        if k == K_OWN:
+            return "&signalValues[mySignalStart + %d]" % r[2]
+        if k == K_SUB:
+            return "&ctx->signalValues[ctx->componentMemory[mySubcomponents[%d]].signalStart + %d]" % (r[1], r[2])
+        if k == K_CONST:
+            return "&circuitConstants[%d]" % r[2]
+        if k == K_TMP:
+            return "&expaux[%d]" % r[2]
+        if k == K_ONE:
+            return "&signalValues[0]"
+        raise ValueError(r)
+
+    cmp_slot = "&expaux[%d]" % t.n_tmp
+    for op, d, a, b, c in t.ops:
+        if op == 27:  # ASSERT_EQ
+            w("{")
+            w("Fr_eq(%s,%s,%s);" % (cmp_slot, addr(a), addr(b)))
+            w('if (!Fr_isTrue(%s)) std::cout << "Failed assert in template/function " << myTemplateName << std::endl;' % cmp_slot)
+            w("assert(Fr_isTrue(%s));" % cmp_slot)
+            w("}")
+            continue
+        if op == 26:  # ASSERT
+            w("assert(Fr_isTrue(%s));" % addr(a))
+            continue
+        dst = addr(d)
+        w("{")
+        if op == 24:
+            w("Fr_copy(%s,%s);" % (dst, addr(a)))
+        elif op == 25:
+            w("if (Fr_isTrue(%s)) { Fr_copy(%s,%s); } else { Fr_copy(%s,%s); }" % (addr(c), dst, addr(a), dst, addr(b)))
+        elif op in _FN:
+            w("Fr_%s(%s,%s,%s);" % (_FN[op], dst, addr(a), addr(b)))
+        elif op in _FN1:
+            w("Fr_%s(%s,%s);" % (_FN1[op], dst, addr(a)))
+        else:
+            raise ValueError("cannot emit op %d" % op)
+        if d[0] == K_SUB:
+            st = t.subs[d[1]].tmpl
+            if st.n_out <= d[2] < st.n_out + st.n_in:
+                w("if(!(ctx->componentMemory[mySubcomponents[%d]].inputCounter -= 1)){" % d[1])
+                w("%s_run(mySubcomponents[%d],ctx);" % (_header(st), d[1]))
+                w("}")
+        w("}")
+    w("for (uint i = 0; i < %d; i++){" % len(t.subs))
+    w("uint index_subc = ctx->componentMemory[ctx_index].subcomponents[i];")
+    w("if (index_subc != 0){")
+    w("assert(!(ctx->componentMemory[index_subc].inputCounter));")
+    w("release_memory_component(ctx,index_subc);")
+    w("}")
+    w("}")
+    w("}\n")
+
+
+def hashmap_size(desc) -> int:
+    n = len(desc.main_inputs())
+    s = 256
+    while s < n:
+        s <<= 1
+    return s
+
+
+def dat_bytes(desc) -> bytes:
+    size = hashmap_size(desc)
+    table = [(0, 0, 0)] * size
+    for name, gid, n in desc.main_inputs():
+        h = fnv1a(name)
+        p = h % size
+        while table[p][1] != 0:
+            p = (p + 1) % size
+        table[p] = (h, gid, n)
+    out = b"".join(struct.pack("<QQQ", *e) for e in table)
+    out += b"".join(struct.pack("<Q", i) for i in range(desc.total_signals))
+    q = desc.q
+    R = 1 << (((q.bit_length() + 63) // 64) * 64)
+    for v in desc.consts:
+        n = v % q
+        nn = n - q if n > q // 2 else n
+        if -2147483648 <= nn <= 2147483647:
+            out += struct.pack("<iI", nn, 0x40000000)
+        else:
+            out += struct.pack("<iI", 0, 0xC0000000)
+        out += ((n * R) % q).to_bytes(32, "little")
+    return out
+
+
+def build_reference_calculator(desc, out_dir: str, name: str | None = None, opt: str = "-O3") -> str:
+    """Writes <name>.cpp / <name>.dat and links the reference runtime; returns the binary path."""
+    from . import build_ref
+    name = name or desc.name
+    os.makedirs(out_dir, exist_ok=True)
+    cpp = os.path.join(out_dir, name + ".cpp")
+    binp = os.path.join(out_dir, name)
+    with open(cpp, "w") as f:
+        f.write(emit_cpp(desc))
+    with open(binp + ".dat", "wb") as f:
+        f.write(dat_bytes(desc))
+    build_ref.build_calculator(desc.prime, cpp, binp, opt=opt)
+    return binp

@@ -286,6 +286,12 @@ int cw_circuit_tape(const cw_circuit *c, uint32_t *ops, uint32_t *level_start, u
     return CW_OK;
 }
 
+int cw_circuit_witness2signal(const cw_circuit *c, uint64_t *out) {
+    if (!c || !out) return fail(CW_EINVAL, "null argument");
+    memcpy(out, c->tape.witness2signal.data(), c->tape.witness2signal.size() * 8);
+    return CW_OK;
+}
+
 int cw_circuit_write_dat(const cw_circuit *c, const char *path) {
     try {
         write_dat(c->tape, path);

@@ -95,7 +95,17 @@ struct Reader {
 struct Val {
     uint32_t slot[3] = {NO_SLOT, NO_SLOT, NO_SLOT};  // provisional slot per representation (Form)
     int32_t cid = -1;                       // IR constant id if this value is a compile-time constant
+    // static knowledge used by the peepholes
+    uint16_t bits = 256;                    // the canonical integer is < 2^bits (256 = nothing known)
+    uint8_t org_op = 0;                     // IR opcode that produced the value (0 = input / constant)
+    int32_t org_a = -1, org_b = -1;         // its operand values
 };
+
+// device-only opcodes (kernels.cuh / fr_device.cuh)
+enum { DOP_BITS = 29, DOP_ASSERT_BOOL = 30, DOP_MULSMALL = 31 };
+inline bool c_is_immediate(uint32_t opcode) {
+    return opcode == CW_OP_ASSERT || opcode == CW_OP_ASSERT_EQ || opcode == DOP_BITS || opcode == DOP_ASSERT_BOOL;
+}
 
 struct Lowerer {
     Tape &T;
@@ -201,7 +211,133 @@ struct Lowerer {
         return cost_c < cost_m ? FC : FM;  // fewest conversions; ties stay in the Montgomery domain
     }
 
+    uint32_t qb() const { return F.qbits; }
+    uint32_t vbits(int32_t v) const { return v < 0 ? 0 : std::min<uint32_t>(vals[v].bits, qb()); }
+    // value of a compile-time constant if it fits 64 bits
+    bool const_u64(int32_t v, uint64_t &out) const {
+        if (v < 0 || vals[v].cid < 0) return false;
+        const U256 &c = ir_consts[vals[v].cid];
+        if (c.v[1] | c.v[2] | c.v[3]) return false;
+        out = c.v[0];
+        return true;
+    }
+    static int u256_bitlen(const U256 &c) {
+        for (int i = 255; i >= 0; --i)
+            if ((c.v[i >> 6] >> (i & 63)) & 1) return i + 1;
+        return 0;
+    }
+    // is the constant 2^m - 1 (m >= 1)?  /  2^k ?
+    bool const_mask(int32_t v, uint32_t &m) const {
+        if (v < 0 || vals[v].cid < 0) return false;
+        U256 c = ir_consts[vals[v].cid], one = u256_from_u64(1), t;
+        if (u256_add(t, c, one)) return false;
+        int bl = u256_bitlen(t);
+        if (bl < 2) return false;
+        U256 p = u256_from_u64(0);
+        p.v[(bl - 1) >> 6] = 1ull << ((bl - 1) & 63);
+        if (!(p == t)) return false;
+        m = (uint32_t)bl - 1;
+        return true;
+    }
+    bool const_pow2(int32_t v, uint32_t &k) const {
+        if (v < 0 || vals[v].cid < 0) return false;
+        const U256 &c = ir_consts[vals[v].cid];
+        int bl = u256_bitlen(c);
+        if (bl < 1) return false;
+        U256 p = u256_from_u64(0);
+        p.v[(bl - 1) >> 6] = 1ull << ((bl - 1) & 63);
+        if (!(p == c)) return false;
+        k = (uint32_t)bl - 1;
+        return true;
+    }
+    uint32_t range_of(uint32_t op, int32_t a, int32_t b) const {
+        const uint32_t FULL = 256, lim = qb() - 1;
+        uint32_t ba = vbits(a), bb = vbits(b);
+        uint64_t k;
+        switch (op) {
+            case CW_OP_ADD: return std::max(ba, bb) + 1 <= lim ? std::max(ba, bb) + 1 : FULL;
+            case CW_OP_MUL: return ba + bb <= lim ? ba + bb : FULL;
+            case CW_OP_IDIV: return ba;
+            case CW_OP_MOD: return std::min(ba, bb);
+            case CW_OP_SHR: return const_u64(b, k) && k < qb() ? (ba > k ? ba - (uint32_t)k : 0) : ba;
+            case CW_OP_SHL: return const_u64(b, k) && ba + k <= lim ? ba + (uint32_t)k : FULL;
+            case CW_OP_BAND: return std::min(ba, bb);
+            case CW_OP_BOR: case CW_OP_BXOR: return std::max(ba, bb) <= lim ? std::max(ba, bb) : FULL;
+            case CW_OP_LEQ: case CW_OP_GEQ: case CW_OP_LT: case CW_OP_GT: case CW_OP_EQ: case CW_OP_NEQ:
+            case CW_OP_LOR: case CW_OP_LAND: case CW_OP_LNOT: return 1;
+            case CW_OP_SELECT: return std::max(ba, bb);
+            default: return FULL;
+        }
+    }
+
     int32_t lower_op(uint32_t op, int32_t a, int32_t b, int32_t c, bool zero_test_only = false) {
+        int32_t r = -1;
+        if (!(flags & CW_FLAG_NO_PEEPHOLE)) r = peephole(op, a, b);
+        if (r < 0) r = lower_op_plain(op, a, b, c, zero_test_only);
+        Val &v = vals[r];
+        v.bits = (uint16_t)range_of(op, a, b);
+        v.org_op = (uint8_t)op;
+        v.org_a = a;
+        v.org_b = b;
+        return r;
+    }
+
+    // pattern-directed replacements; each preserves the canonical value of the result exactly
+    int32_t peephole(uint32_t op, int32_t a, int32_t b) {
+        if (op == CW_OP_BAND) {
+            // (x >> k) & (2^m - 1)  ->  bit-field extract;  x & (2^m - 1) likewise with k = 0
+            uint32_t m;
+            int32_t x = -1;
+            if (const_mask(b, m)) x = a;
+            else if (const_mask(a, m)) x = b;
+            if (x >= 0 && !is_const(x) && m < qb()) {
+                uint32_t k = 0;
+                uint64_t kk;
+                const Val &vx = vals[x];
+                if (vx.org_op == CW_OP_SHR && const_u64(vx.org_b, kk) && kk < qb() && !is_const(vx.org_a)) {
+                    k = (uint32_t)kk;
+                    x = vx.org_a;
+                }
+                return new_val(emit(DOP_BITS, need(x, FC), NO_SLOT, k | (m << 16), true), FC);
+            }
+        }
+        if (op == CW_OP_MUL) {
+            // x * 2^k with x*2^k < q known statically: a shift of the canonical value
+            uint32_t k;
+            int32_t x = -1;
+            if (const_pow2(b, k)) x = a;
+            else if (const_pow2(a, k)) x = b;
+            if (x >= 0 && !is_const(x) && has(x, FC) && vbits(x) + k <= qb() - 1) {
+                if (k == 0) return -1;
+                U256 kc = u256_from_u64(k);
+                return new_val(emit(CW_OP_SHL, need(x, FC), OPERAND_CONST | raw_const(kc)), FC);
+            }
+            // small * small with the integer product < q: plain product, no reduction
+            if (!is_const(a) && !is_const(b) && has(a, FC) && has(b, FC) && vbits(a) + vbits(b) <= qb() - 1)
+                return new_val(emit(DOP_MULSMALL, need(a, FC), need(b, FC)), FC);
+        }
+        return -1;
+    }
+
+    // `x*(x-1) === 0`  ->  one boolean assert on x
+    bool try_assert_bool(int32_t a, uint32_t id) {
+        const Val &va = vals[a];
+        if (va.org_op != CW_OP_MUL || va.org_a < 0 || va.org_b < 0) return false;
+        for (int s = 0; s < 2; ++s) {
+            int32_t x = s ? va.org_b : va.org_a, y = s ? va.org_a : va.org_b;
+            const Val &vy = vals[y];
+            uint64_t one;
+            if (vy.org_op == CW_OP_SUB && vy.org_a == x && const_u64(vy.org_b, one) && one == 1 && !is_const(x)) {
+                Form f = has(x, FC) ? FC : FM;
+                U256 o = f == FC ? u256_from_u64(1) : F.r1;
+                emit(DOP_ASSERT_BOOL, need(x, f), OPERAND_CONST | raw_const(o), id, true);
+                return true;
+            }
+        }
+        return false;
+    }
+
+    int32_t lower_op_plain(uint32_t op, int32_t a, int32_t b, int32_t c, bool zero_test_only) {
         switch (op) {
             case CW_OP_ADD:
             case CW_OP_SUB: {
@@ -303,6 +439,8 @@ struct Lowerer {
                 if (flags & CW_FLAG_NO_ASSERTS) continue;
                 if (o.op == CW_OP_ASSERT_EQ) {
                     int32_t a = load(o.a), b = load(o.b);
+                    if (!(flags & CW_FLAG_NO_PEEPHOLE) && is_const_zero(b) && try_assert_bool(a, id)) continue;
+                    if (!(flags & CW_FLAG_NO_PEEPHOLE) && is_const_zero(a) && try_assert_bool(b, id)) continue;
                     if (is_const_zero(b)) emit(CW_OP_ASSERT_EQ, need_any(a), need(b, FC), id, true);
                     else if (is_const_zero(a)) emit(CW_OP_ASSERT_EQ, need(a, FC), need_any(b), id, true);
                     else {
@@ -381,6 +519,86 @@ struct Lowerer {
             R.row_ptr.push_back(R.col.size());
         }
         for (size_t i = 0; i < t.subs.size(); ++i) collect_constraints(t.subs[i], offs[i]);
+    }
+
+    // union-find over signals for the `signal = signal` eliminations; rewrites T.r1cs into witness numbering
+    void simplify_constraints(uint64_t S, uint64_t n_fixed, std::vector<uint32_t> &sig2wit) {
+        R1csData &R = T.r1cs;
+        std::vector<uint32_t> parent(S);
+        for (uint64_t i = 0; i < S; ++i) parent[i] = (uint32_t)i;
+        auto find = [&](uint32_t x) {
+            while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; }
+            return x;
+        };
+        size_t m = (R.row_ptr.size() - 1) / 3;
+        if (!(flags & CW_FLAG_O0)) {
+            for (size_t r = 0; r < m; ++r) {
+                uint64_t a0 = R.row_ptr[3 * r], b0 = R.row_ptr[3 * r + 1], c0 = R.row_ptr[3 * r + 2], c1 = R.row_ptr[3 * r + 3];
+                if (b0 != a0 || c0 != b0 || c1 - c0 != 2) continue;
+                uint32_t x = R.col[c0], y = R.col[c0 + 1];
+                if (x == 0 || y == 0) continue;
+                const U256 &cx = R.dict[R.coef[c0]], &cy = R.dict[R.coef[c0 + 1]];
+                if (cx.is_zero() || !(F.addm(cx, cy).is_zero())) continue;
+                uint32_t rx = find(x), ry = find(y);
+                if (rx == ry) continue;
+                if (rx > ry) std::swap(rx, ry);
+                if (ry < n_fixed) continue;  // both classes contain a main input/output: keep the constraint
+                parent[ry] = rx;             // representative = smallest signal id
+            }
+        }
+        sig2wit.assign(S, 0);
+        T.witness2signal.clear();
+        for (uint64_t i = 0; i < S; ++i)
+            if (find((uint32_t)i) == i) {
+                sig2wit[i] = (uint32_t)T.witness2signal.size();
+                T.witness2signal.push_back(i);
+            }
+        for (uint64_t i = 0; i < S; ++i) sig2wit[i] = sig2wit[find((uint32_t)i)];
+        // rewrite rows: map columns, merge duplicates, drop zero terms and trivial rows
+        std::vector<uint64_t> row_ptr(1, 0);
+        std::vector<uint32_t> col, coef;
+        col.reserve(R.col.size());
+        coef.reserve(R.coef.size());
+        std::unordered_map<std::string, uint32_t> dict_index;
+        for (size_t i = 0; i < R.dict.size(); ++i) dict_index.emplace(std::string((const char *)R.dict[i].v, 32), (uint32_t)i);
+        std::vector<std::pair<uint32_t, U256>> lc[3];
+        for (size_t r = 0; r < m; ++r) {
+            for (int k = 0; k < 3; ++k) {
+                lc[k].clear();
+                for (uint64_t i = R.row_ptr[3 * r + k]; i < R.row_ptr[3 * r + k + 1]; ++i)
+                    lc[k].emplace_back(sig2wit[R.col[i]], R.dict[R.coef[i]]);
+                std::sort(lc[k].begin(), lc[k].end(), [](const std::pair<uint32_t, U256> &x, const std::pair<uint32_t, U256> &y) { return x.first < y.first; });
+                size_t o = 0;
+                for (size_t i = 0; i < lc[k].size(); ++i) {
+                    if (o && lc[k][o - 1].first == lc[k][i].first) lc[k][o - 1].second = F.addm(lc[k][o - 1].second, lc[k][i].second);
+                    else lc[k][o++] = lc[k][i];
+                }
+                lc[k].resize(o);
+                o = 0;
+                for (size_t i = 0; i < lc[k].size(); ++i)
+                    if (!lc[k][i].second.is_zero()) lc[k][o++] = lc[k][i];
+                lc[k].resize(o);
+            }
+            if ((lc[0].empty() || lc[1].empty()) && lc[2].empty()) continue;  // 0 = 0
+            for (int k = 0; k < 3; ++k) {
+                for (auto &e : lc[k]) {
+                    std::string key((const char *)e.second.v, 32);
+                    auto it = dict_index.find(key);
+                    uint32_t id;
+                    if (it == dict_index.end()) {
+                        id = (uint32_t)R.dict.size();
+                        R.dict.push_back(e.second);
+                        dict_index.emplace(std::move(key), id);
+                    } else id = it->second;
+                    col.push_back(e.first);
+                    coef.push_back(id);
+                }
+                row_ptr.push_back(col.size());
+            }
+        }
+        R.row_ptr.swap(row_ptr);
+        R.col.swap(col);
+        R.coef.swap(coef);
     }
 
     void parse(const uint8_t *data, size_t len) {
@@ -486,10 +704,14 @@ struct Lowerer {
         n_pre = 1 + M.n_in;
         // constants are vids [0, n_consts)
         vals.resize(ir_consts.size());
-        for (size_t i = 0; i < ir_consts.size(); ++i) vals[i].cid = (int32_t)i;
+        for (size_t i = 0; i < ir_consts.size(); ++i) {
+            vals[i].cid = (int32_t)i;
+            vals[i].bits = (uint16_t)u256_bitlen(ir_consts[i]);
+        }
         sig_vid.assign(S, -1);
         slot_level.assign(n_pre, 0);
         vid_one = new_val(0, FC);  // slot 0: the constant-one signal (calcwit.cpp:34)
+        vals[vid_one].bits = 1;
         sig_vid[0] = vid_one;
         for (uint32_t i = 0; i < M.n_in; ++i) sig_vid[1 + M.n_out + i] = new_val(1 + i, FC);
         Comp mc;
@@ -498,15 +720,32 @@ struct Lowerer {
         mc.counter = 0;
         run(mc);
 
-        // witness = every signal, in signal order (O0-style witness list, dag/src/witness_producer.rs:3-19)
-        uint64_t W = S;
+        // R1CS rows in signal numbering (component pre-order), then the witness list:
+        //   --O0 : every signal, in signal order (dag/src/witness_producer.rs:3-19)
+        //   default (the reference's --O1 core): constraints `c*x - c*y = 0` between two signals are
+        //   removed by merging the signals (constraint_list/src/constraint_simplification.rs "signal = signal"
+        //   eliminations); the witness keeps one representative per class, main inputs/outputs always stay.
+        R1csData &R = T.r1cs;
+        R.prime_id = F.prime_id;
+        R.row_ptr.push_back(0);
+        R.dict = ir_consts;
+        collect_constraints(main_tid, 1);
+        std::vector<uint32_t> sig2wit;
+        simplify_constraints(S, 1 + M.n_out + M.n_in, sig2wit);
+        uint64_t W = T.witness2signal.size();
         T.n_witness = W;
+        R.n_wires = W;
+        R.n_constraints = (R.row_ptr.size() - 1) / 3;
+        R.n_pub_out = (uint32_t)M.n_out;
+        R.n_pub_in = 0;
+        R.n_prv_in = (uint32_t)M.n_in;
         std::vector<uint32_t> wslot(W);
         size_t n_prov = pops.size() / 4;
         std::vector<uint8_t> live(n_pre + n_prov, 0);
+        for (uint64_t i = 0; i < S; ++i)
+            if (sig_vid[i] < 0) throw std::runtime_error("lowering: signal " + std::to_string(i) + " is never assigned");
         for (uint64_t i = 0; i < W; ++i) {
-            int32_t v = sig_vid[i];
-            if (v < 0) throw std::runtime_error("lowering: signal " + std::to_string(i) + " is never assigned");
+            int32_t v = sig_vid[T.witness2signal[i]];
             if (vals[v].cid >= 0) {
                 // a signal that is a compile-time constant: materialise it once
                 uint32_t s = emit(CW_OP_COPY, const_operand(vals[v].cid, FC));
@@ -527,11 +766,11 @@ struct Lowerer {
         // dead-value elimination (reverse sweep; provisional order is topological)
         for (size_t i = n_prov; i-- > 0;) {
             uint32_t *o = &pops[i * 4];
-            bool is_assert = o[0] == CW_OP_ASSERT || o[0] == CW_OP_ASSERT_EQ;
+            bool is_assert = o[0] == CW_OP_ASSERT || o[0] == CW_OP_ASSERT_EQ || o[0] == DOP_ASSERT_BOOL;
             if (!is_assert && !live[n_pre + i]) continue;
             live[n_pre + i] = 1;
             for (int k = 1; k <= 3; ++k) {
-                if (k == 3 && is_assert) break;
+                if (k == 3 && c_is_immediate(o[0])) break;
                 if (o[k] != NO_SLOT && !(o[k] & OPERAND_CONST)) live[o[k]] = 1;
             }
         }
@@ -561,10 +800,9 @@ struct Lowerer {
         for (size_t r = 0; r < order.size(); ++r) {
             const uint32_t *o = &pops[(size_t)order[r] * 4];
             uint32_t *d = &T.ops[r * 4];
-            bool is_assert = o[0] == CW_OP_ASSERT || o[0] == CW_OP_ASSERT_EQ;
             d[0] = o[0];
             for (int k = 1; k <= 3; ++k) {
-                if (k == 3 && is_assert) d[k] = o[k];          // immediate: IR assert number
+                if (k == 3 && c_is_immediate(o[0])) d[k] = o[k];  // immediate: IR assert number / bit-field spec
                 else if (o[k] == NO_SLOT) d[k] = OPERAND_CONST;  // unused operand: constant 0 (never read for its value)
                 else if (o[k] & OPERAND_CONST) d[k] = o[k];
                 else d[k] = remap[o[k]];
@@ -607,17 +845,6 @@ struct Lowerer {
             T.hashmap[p] = HashEntry{in.hash, in.signal_id, in.size};
         }
 
-        // R1CS in witness numbering (identity map here)
-        R1csData &R = T.r1cs;
-        R.prime_id = F.prime_id;
-        R.n_wires = W;
-        R.row_ptr.push_back(0);
-        R.dict = ir_consts;
-        collect_constraints(main_tid, 1);
-        R.n_constraints = (R.row_ptr.size() - 1) / 3;
-        R.n_pub_out = (uint32_t)M.n_out;
-        R.n_pub_in = 0;
-        R.n_prv_in = (uint32_t)M.n_in;
     }
 };
 

@@ -196,7 +196,7 @@ void write_dat(const Tape &t, const std::string &path) {
         f.put<uint64_t>(e.signalid);
         f.put<uint64_t>(e.signalsize);
     }
-    for (uint64_t i = 0; i < t.n_witness; ++i) f.put<uint64_t>(i);
+    for (uint64_t i = 0; i < t.n_witness; ++i) f.put<uint64_t>(t.witness2signal[i]);
 }
 
 }  // namespace cw

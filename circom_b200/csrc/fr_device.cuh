@@ -372,11 +372,45 @@ enum {
     OP_MUL = 1, OP_ADD = 3, OP_SUB = 4, OP_POW = 5, OP_IDIV = 6, OP_MOD = 7, OP_SHL = 8, OP_SHR = 9,
     OP_LEQ = 10, OP_GEQ = 11, OP_LT = 12, OP_GT = 13, OP_EQ = 14, OP_NEQ = 15, OP_LOR = 16, OP_LAND = 17,
     OP_LNOT = 18, OP_BOR = 19, OP_BAND = 20, OP_BXOR = 21, OP_BNOT = 22, OP_NEG = 23, OP_COPY = 24,
-    OP_SELECT = 25, OP_ASSERT = 26, OP_ASSERT_EQ = 27, OP_INV = 28
+    OP_SELECT = 25, OP_ASSERT = 26, OP_ASSERT_EQ = 27, OP_INV = 28,
+    OP_BITS = 29,         // (a >> k) & (2^m - 1), imm = k | m << 16  (fused `(x >> k) & mask` hints)
+    OP_ASSERT_BOOL = 30,  // a == 0 || a == b  (b = the constant one in a's representation)
+    OP_MULSMALL = 31      // a * b as integers, statically known to stay below q (no reduction)
 };
 
-CW_HD void fr_exec(u32 opcode, u32 *r, const u32 *a, const u32 *b, const FrParams &P, int &err) {
+// low 256 bits of the integer product (36 limb products instead of CIOS' 128)
+CW_HD void u256_mul_lo(u32 *r, const u32 *a, const u32 *b) {
+    u32 t[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        u64 c = 0;
+#pragma unroll
+        for (int j = 0; j + i < 8; ++j) {
+            c += (u64)a[j] * b[i] + t[i + j];
+            t[i + j] = (u32)c;
+            c >>= 32;
+        }
+    }
+    u256_set(r, t);
+}
+CW_HD void u256_bits(u32 *r, const u32 *a, u32 imm) {
+    u32 k = imm & 0xFFFFu, m = imm >> 16;
+    u32 t[8];
+    u256_shr(t, a, k);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int lo = i * 32;
+        u32 mask = (int)m >= lo + 32 ? 0xFFFFFFFFu : ((int)m <= lo ? 0u : ((1u << (m - lo)) - 1u));
+        r[i] = t[i] & mask;
+    }
+}
+
+CW_HD void fr_exec(u32 opcode, u32 *r, const u32 *a, const u32 *b, u32 imm, const FrParams &P, int &err) {
     switch (opcode) {
+        case OP_BITS: u256_bits(r, a, imm); break;
+        case OP_MULSMALL: u256_mul_lo(r, a, b); break;
         case OP_MUL: fr_mont_mul(r, a, b, P); break;
         case OP_ADD: fr_add(r, a, b, P); break;
         case OP_SUB: fr_sub(r, a, b, P); break;

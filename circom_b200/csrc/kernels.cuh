@@ -105,13 +105,15 @@ __global__ void __launch_bounds__(1024) tape_exec_kernel(TapeDev tp, uint4 *__re
                 bool t = !u256_is_zero(c);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) r[i] = t ? a[i] : b[i];
-            } else if (op.x == OP_ASSERT_EQ || op.x == OP_ASSERT) {
-                bool ok = op.x == OP_ASSERT_EQ ? u256_eq(a, b) : !u256_is_zero(a);
+            } else if (op.x == OP_ASSERT_EQ || op.x == OP_ASSERT || op.x == OP_ASSERT_BOOL) {
+                bool ok = op.x == OP_ASSERT_EQ ? u256_eq(a, b)
+                          : op.x == OP_ASSERT  ? !u256_is_zero(a)
+                                               : (u256_is_zero(a) || u256_eq(a, b));
                 if (!ok && inst < batch) atomicMin(&first_assert[inst], op.w);
                 continue;  // asserts have no destination value
             } else {
                 int e = 0;
-                fr_exec(op.x, r, a, b, P, e);
+                fr_exec(op.x, r, a, b, op.w, P, e);
                 if (e && inst < batch) err[inst] = 1;
             }
             store_slot(r, base, tp.n_pre + oi, bt_log2, li);
@@ -247,7 +249,7 @@ __global__ void fr_batch_op_kernel(int op, const uint4 *__restrict__ A, const ui
             bool t = !u256_is_zero(c);
             for (int k = 0; k < 8; ++k) r[k] = t ? a[k] : b[k];
         } else {
-            fr_exec((u32)op, r, a, b, P, e);
+            fr_exec((u32)op, r, a, b, 0, P, e);
         }
         if (e) err[0] = 1;
         Rr[2 * i] = make_uint4(r[0], r[1], r[2], r[3]);

@@ -46,6 +46,7 @@ struct Tape {
     std::vector<uint32_t> level_start;  // n_levels + 1
     std::vector<U256> consts;           // raw limb patterns (already in the form the consumer needs)
     std::vector<uint32_t> witness_slot; // per witness entry
+    std::vector<uint64_t> witness2signal; // witness2SignalList (calcwit.hpp:54-56)
     std::vector<InputInfo> inputs;
     std::vector<HashEntry> hashmap;
     R1csData r1cs;

@@ -12,7 +12,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t
 from . import build as _build
 
 CW_OK, CW_EINVAL, CW_EIO, CW_EFORMAT, CW_ECUDA, CW_ENOTFOUND, CW_ESTATE, CW_ENODEV = 0, -1, -2, -3, -4, -5, -6, -7
-CW_FLAG_NO_ASSERTS, CW_FLAG_HOST_ONLY = 1, 2
+CW_FLAG_NO_ASSERTS, CW_FLAG_HOST_ONLY, CW_FLAG_O0 = 1, 2, 4
 
 
 class CwError(RuntimeError):
@@ -57,6 +57,7 @@ def _load() -> ctypes.CDLL:
         "cw_get_input_signal_size": (c_int, [P, c_uint64, POINTER(c_uint64)]),
         "cw_get_input_signal_id": (c_int, [P, c_uint64, POINTER(c_uint64)]),
         "cw_circuit_tape": (c_int, [P, c_void_p, c_void_p, c_void_p]),
+        "cw_circuit_witness2signal": (c_int, [P, c_void_p]),
         "cw_circuit_write_dat": (c_int, [P, c_char_p]),
         "cw_batch_create": (c_int, [P, c_uint32, c_int, POINTER(P)]),
         "cw_batch_destroy": (None, [P]),

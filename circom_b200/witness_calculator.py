@@ -115,8 +115,10 @@ def limbs_to_ints(a: np.ndarray) -> List[int]:
 class Circuit:
     """A lowered circuit (replaces Circom_Circuit + the compiled <name>.cpp)."""
 
-    def __init__(self, src: Union[CircuitDesc, bytes, str], sanity_check: bool = True, host_only: bool = False):
-        flags = (0 if sanity_check else native.CW_FLAG_NO_ASSERTS) | (native.CW_FLAG_HOST_ONLY if host_only else 0)
+    def __init__(self, src: Union[CircuitDesc, bytes, str], sanity_check: bool = True, host_only: bool = False,
+                 o0: bool = False):
+        flags = (0 if sanity_check else native.CW_FLAG_NO_ASSERTS) | (native.CW_FLAG_HOST_ONLY if host_only else 0) | \
+            (native.CW_FLAG_O0 if o0 else 0)
         self._h = ctypes.c_void_p()
         if isinstance(src, CircuitDesc):
             src = src.to_bytes()
@@ -162,6 +164,11 @@ class Circuit:
         ws = np.zeros(self.n_witness, dtype=np.uint32)
         check(lib.cw_circuit_tape(self._h, ops.ctypes.data, ls.ctypes.data, ws.ctypes.data))
         return ops, ls, ws
+
+    def witness2signal(self) -> np.ndarray:
+        out = np.zeros(self.n_witness, dtype=np.uint64)
+        check(lib.cw_circuit_witness2signal(self._h, out.ctypes.data))
+        return out
 
     def write_dat(self, path: str) -> None:
         check(lib.cw_circuit_write_dat(self._h, path.encode()))

@@ -42,6 +42,8 @@ extern "C" {
 /* cw_circuit_load flags */
 #define CW_FLAG_NO_ASSERTS 1u /* --sanity_check 0: drop `===` asserts (assert_bucket.rs:73) */
 #define CW_FLAG_HOST_ONLY 2u  /* lower the tape but do not touch a GPU (CPU-side tests of the lowering) */
+#define CW_FLAG_NO_PEEPHOLE 8u /* lower IR ops one to one (no bit-field / boolean-assert / shift fusions) */
+#define CW_FLAG_O0 4u         /* --O0: keep every signal in the witness and every `signal = signal` constraint */
 
 /* IR opcodes = OperatorType, compiler/src/intermediate_representation/compute_bucket.rs:7-34 */
 enum cw_op {
@@ -106,6 +108,8 @@ int cw_get_input_signal_id(const cw_circuit *c, uint64_t name_hash, uint64_t *si
  * ops: n_tape_ops x 4 uint32 {opcode | flags<<8, a, b, c}; operand bit31 = constant-table index;
  * level_start: n_levels+1 uint32; witness_slot: n_witness uint32 (bit31 = value held in Montgomery form) */
 int cw_circuit_tape(const cw_circuit *c, uint32_t *ops, uint32_t *level_start, uint32_t *witness_slot);
+/* witness2SignalList (calcwit.hpp:54-56, c_code_generator.rs:605-614): n_witness entries */
+int cw_circuit_witness2signal(const cw_circuit *c, uint64_t *out);
 /* save / load the reference's .dat layout for the input hash map + witness2signal list
  * (c_code_generator.rs:575-603,605-614,818-865) */
 int cw_circuit_write_dat(const cw_circuit *c, const char *path);

@@ -79,12 +79,12 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
                 u32 c[8];
                 operand(op[3], c);
                 memcpy(r, u256_is_zero(c) ? b : a, 32);
-            } else if (op[0] == OP_ASSERT_EQ || op[0] == OP_ASSERT) {
-                bool ok = op[0] == OP_ASSERT_EQ ? u256_eq(a, b) : !u256_is_zero(a);
+            } else if (op[0] == OP_ASSERT_EQ || op[0] == OP_ASSERT || op[0] == OP_ASSERT_BOOL) {
+                bool ok = op[0] == OP_ASSERT_EQ ? u256_eq(a, b) : op[0] == OP_ASSERT ? !u256_is_zero(a) : (u256_is_zero(a) || u256_eq(a, b));
                 if (!ok && op[3] < first_assert) first_assert = op[3];
                 continue;
             } else {
-                fr_exec(op[0], r, a, b, P, err);
+                fr_exec(op[0], r, a, b, op[3], P, err);
             }
             memcpy(&slots[((size_t)t.n_pre + i) * 8], r, 32);
         }
@@ -104,6 +104,19 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
     return 0;
 }
 
+// witness2SignalList of the lowered circuit; returns n_witness (or <0)
+long hs_witness2signal(const uint8_t *cb2c, size_t len, uint32_t flags, uint64_t *out, size_t cap) {
+    Tape t;
+    try {
+        lower_circuit(cb2c, len, flags, t);
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+    if (out && cap >= t.witness2signal.size()) memcpy(out, t.witness2signal.data(), t.witness2signal.size() * 8);
+    return (long)t.witness2signal.size();
+}
+
 // level structure check: every operand slot of an op in level l is produced in a level < l
 int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
     Tape t;
@@ -119,9 +132,9 @@ int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
     if (t.n_levels() && t.level_start[t.n_levels()] != t.n_tape_ops()) { g_err = "level table does not cover the tape"; return -2; }
     for (size_t i = 0; i < t.n_tape_ops(); ++i) {
         const uint32_t *op = &t.ops[i * 4];
-        bool is_assert = op[0] == OP_ASSERT || op[0] == OP_ASSERT_EQ;
+        bool c_imm = op[0] == OP_ASSERT || op[0] == OP_ASSERT_EQ || op[0] == OP_ASSERT_BOOL || op[0] == OP_BITS;
         for (int k = 1; k <= 3; ++k) {
-            if (k == 3 && is_assert) break;
+            if (k == 3 && c_imm) break;
             if (op[k] & OPERAND_CONST) {
                 if ((op[k] & 0x7FFFFFFFu) >= t.consts.size()) { g_err = "constant index out of range"; return -3; }
                 continue;
@@ -166,7 +179,7 @@ int hs_fr_op(int prime, int op, const uint64_t *A, const uint64_t *B, const uint
         } else if (op == OP_SELECT) {
             memcpy(r, u256_is_zero(c) ? b : a, 32);
         } else {
-            fr_exec((u32)op, r, a, b, P, e);
+            fr_exec((u32)op, r, a, b, 0, P, e);
         }
         any_err |= e;
         memcpy(R + 4 * i, r, 32);

@@ -1,0 +1,98 @@
+"""GPU parity on the configuration circuits (BASELINE.json configs): Poseidon(2), Sha256compression,
+Sha256(512) over BLS12-381 with the full R1CS check, and the ~1M-constraint ecdsa-scale circuit.
+Checked against the C oracle (bit-exact), external known answers (circomlibjs' Poseidon test
+value, hashlib.sha256, python-int secp256k1 arithmetic) and the algebraic self-check A.w o B.w = C.w."""
+import hashlib
+import random
+
+import numpy as np
+import pytest
+
+from circom_b200.circuit import CircuitDesc
+from circom_b200 import circuits as C
+from circom_b200.circuits.sha256 import H0
+from circom_b200.witness_calculator import Circuit, Batch, R1cs, builder, limbs_to_ints
+from oracle.c_oracle import COracle
+from tests.util import flat_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(d, ins, check_r1cs=True):
+    c = Circuit(d)
+    b = Batch(c, len(ins))
+    arr = flat_inputs(d, ins)
+    b.set_inputs(arr)
+    b.run()
+    assert not b.status().any()
+    wit = b.witness()
+    if check_r1cs:
+        fb, _ = R1cs(c).check(None, batch=len(ins), device_ptr=b.witness_device_ptr())
+        assert (fb == -1).all()
+    return c, wit, arr, c.witness2signal().astype(np.int64)
+
+
+def test_poseidon2_kat_and_oracle():
+    d = CircuitDesc("bn128")
+    d.set_main(C.poseidon(d, 2))
+    rng = random.Random(1)
+    ins = [{"inputs": [1, 2]}] + [{"inputs": [rng.randrange(d.q), rng.randrange(d.q)]} for _ in range(130)]
+    c, wit, arr, w2s = _run(d, ins)
+    assert limbs_to_ints(wit[0][1:2])[0] == 0x115cc0f5e7d690413df64c6b9662e9cf2a3617f2743245519e19607a4417189a
+    for i in (1, 77, 130):
+        assert limbs_to_ints(wit[i][1:2])[0] == C.poseidon_hash(ins[i]["inputs"])
+    ow, st = COracle(d.to_bytes()).run(arr)
+    assert not st.any() and (ow[:, w2s] == wit).all()
+
+
+def test_sha256compression_batch_vs_oracle_and_hashlib():
+    d = CircuitDesc("bn128")
+    d.set_main(C.sha256_compression(d))
+    rng = np.random.default_rng(2)
+    batch = 96
+    ins = []
+    msgs = []
+    for i in range(batch):
+        msg = rng.integers(0, 256, 55, dtype=np.uint8).tobytes()
+        block = msg + b"\x80" + (55 * 8).to_bytes(8, "big")
+        msgs.append(msg)
+        ins.append({"hin": [(H0[j] >> k) & 1 for j in range(8) for k in range(32)],
+                    "inp": [(block[j // 8] >> (7 - j % 8)) & 1 for j in range(512)]})
+    c, wit, arr, w2s = _run(d, ins)
+    for i in range(batch):
+        bits = wit[i, 1:257, 0]
+        digest = int("".join(str(int(x)) for x in bits), 2).to_bytes(32, "big")
+        assert digest == hashlib.sha256(msgs[i]).digest()
+    ow, st = COracle(d.to_bytes()).run(arr[:8])
+    assert not st.any() and (ow[:, w2s] == wit[:8]).all()
+
+
+def test_sha256_512_bls12381_with_r1cs():
+    d = CircuitDesc("bls12381")
+    d.set_main(C.sha256(d, 512))
+    rng = np.random.default_rng(4)
+    batch = 48
+    msgs = [rng.integers(0, 256, 64, dtype=np.uint8).tobytes() for _ in range(batch)]
+    ins = [{"in": [(m[j // 8] >> (7 - j % 8)) & 1 for j in range(512)]} for m in msgs]
+    c, wit, arr, w2s = _run(d, ins)
+    for i in range(batch):
+        digest = int("".join(str(int(x)) for x in wit[i, 1:257, 0]), 2).to_bytes(32, "big")
+        assert digest == hashlib.sha256(msgs[i]).digest()
+    ow, st = COracle(d.to_bytes()).run(arr[:4])
+    assert (ow[:, w2s] == wit[:4]).all()
+
+
+@pytest.mark.parametrize("lanes,steps,batch", [(2, 5, 33), (8, 132, 6)])
+def test_ecdsa_scale_vs_oracle_and_python_ints(lanes, steps, batch):
+    d = CircuitDesc("bn128")
+    d.set_main(C.ecdsa_scale(d, lanes, steps))
+    rng = random.Random(3)
+    ins = [{"a": [rng.randrange(2**64) for _ in range(lanes * 4)], "b": [rng.randrange(2**64) for _ in range(lanes * 4)]}
+           for _ in range(batch)]
+    ins[0] = {"a": [2**64 - 1] * (lanes * 4), "b": [2**64 - 1] * (lanes * 4)}
+    c, wit, arr, w2s = _run(d, ins)
+    for i in range(batch):
+        assert limbs_to_ints(wit[i][1:1 + lanes * 4]) == C.ecdsa_scale_expected(ins[i]["a"], ins[i]["b"], lanes, steps)
+    n = 2
+    ow, st = COracle(d.to_bytes()).run(arr[:n], threads=n)
+    assert not st.any() and (ow[:, w2s] == wit[:n]).all()

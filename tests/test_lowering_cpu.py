@@ -34,12 +34,17 @@ def test_tape_matches_oracle(prime, name):
     import zlib
     rng = random.Random(zlib.crc32((prime + name).encode()))
     ins = [gen(rng, d.q) for _ in range(24)]
-    wit, st, stats = hostsim_run(d, ins)
-    for i, inp in enumerate(ins):
-        exp = evaluate(d, inp)
-        assert check_r1cs(d, exp) == 0
-        assert limbs_to_ints(wit[i]) == exp, (prime, name, i)
-    assert not st.any()
+    for flags in (0, 4):  # default (signal = signal eliminated) and CW_FLAG_O0
+        wit, st, stats, w2s = hostsim_run(d, ins, flags=flags)
+        if flags == 4:
+            assert w2s.tolist() == list(range(d.total_signals))
+        assert w2s[0] == 0 and (np.diff(w2s) > 0).all()
+        assert set(range(1, 1 + d.main.n_out + d.main.n_in)) <= set(w2s.tolist())
+        for i, inp in enumerate(ins):
+            exp = evaluate(d, inp)
+            assert check_r1cs(d, exp) == 0
+            assert limbs_to_ints(wit[i]) == [exp[k] for k in w2s], (prime, name, i)
+        assert not st.any()
 
 
 def test_assert_failure_is_reported():
@@ -55,9 +60,9 @@ def test_assert_failure_is_reported():
         t.constrain(a * b, o)       # only true for special inputs
         t.constrain(a, b)           # second assert
     d.set_main(d.template("Bad", (), build))
-    wit, st, _ = hostsim_run(d, [{"a": 2, "b": 2}, {"a": 2, "b": 3}, {"a": 0, "b": 5}])
+    wit, st, _, _ = hostsim_run(d, [{"a": 2, "b": 2}, {"a": 2, "b": 3}, {"a": 0, "b": 5}])
     assert st.tolist() == [0, 1, 1]
-    wit, st, _ = hostsim_run(d, [{"a": 2, "b": 3}], flags=1)  # CW_FLAG_NO_ASSERTS
+    wit, st, _, _ = hostsim_run(d, [{"a": 2, "b": 3}], flags=1)  # CW_FLAG_NO_ASSERTS
     assert st.tolist() == [0]
 
 
@@ -98,13 +103,13 @@ def test_r1cs_check_arithmetic_and_violation_detection():
     blob = d.to_bytes()
     rng = random.Random(3)
     ins = [{"in": [rng.randrange(65536), rng.randrange(65536)]} for _ in range(6)]
-    wit, st, stats = hostsim_run(d, ins)
+    wit, st, stats, w2s = hostsim_run(d, ins)
     fb = np.zeros(len(ins), dtype=np.int64)
     assert hs.hs_r1cs_check(blob, ctypes.c_size_t(len(blob)), wit.ctypes.data_as(ctypes.c_void_p), len(ins),
                             fb.ctypes.data_as(ctypes.c_void_p)) == 0
     assert (fb == -1).all()
     bad = wit.copy()
-    bad[2, 5, 0] ^= 1  # flip one bit of one wire of instance 2
+    bad[2, 3, 0] ^= 1  # flip one bit of one wire of instance 2
     assert hs.hs_r1cs_check(blob, ctypes.c_size_t(len(blob)), bad.ctypes.data_as(ctypes.c_void_p), len(ins),
                             fb.ctypes.data_as(ctypes.c_void_p)) == 0
     assert fb[2] >= 0 and (np.delete(fb, 2) == -1).all()

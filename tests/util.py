@@ -66,7 +66,12 @@ def hostsim_run(desc, inputs_list, flags=0):
     B = len(inputs_list)
     S = desc.total_signals
     inp = flat_inputs(desc, inputs_list)
-    wit = np.zeros((B, S, 4), dtype=np.uint64)
+    hs.hs_witness2signal.restype = ctypes.c_long
+    w2s = np.zeros(S, dtype=np.uint64)
+    W = hs.hs_witness2signal(blob, ctypes.c_size_t(len(blob)), flags, w2s.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(S))
+    assert W > 0, hs.hs_last_error()
+    w2s = w2s[:W].astype(np.int64)
+    wit = np.zeros((B, W, 4), dtype=np.uint64)
     st = np.zeros(B, dtype=np.int32)
     stats = np.zeros(8, dtype=np.uint64)
     rc = hs.hs_run(blob, ctypes.c_size_t(len(blob)), flags, inp.ctypes.data_as(ctypes.c_void_p), B,
@@ -75,7 +80,7 @@ def hostsim_run(desc, inputs_list, flags=0):
     assert rc == 0, hs.hs_last_error()
     rc = hs.hs_check_levels(blob, ctypes.c_size_t(len(blob)), flags)
     assert rc == 0, (rc, hs.hs_last_error())
-    return wit, st, stats
+    return wit, st, stats, w2s
 
 
 def edge_values(q):

@@ -5,6 +5,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -84,7 +85,8 @@ struct DevR1cs {
     unsigned long long *row_ptr = nullptr;
     u32 *col = nullptr, *coef = nullptr;
     uint4 *dictM = nullptr;
-    unsigned char *kind = nullptr;
+    unsigned short *kind = nullptr;
+    u32 *perm = nullptr;
 };
 
 template <class T>
@@ -595,6 +597,7 @@ void cw_r1cs_destroy(cw_r1cs *r) {
         cudaFree(kv.second.coef);
         cudaFree(kv.second.dictM);
         cudaFree(kv.second.kind);
+        cudaFree(kv.second.perm);
     }
     delete r;
 }
@@ -611,18 +614,47 @@ int cw_r1cs_check(cw_r1cs *r, const uint64_t *witness, int is_device_ptr, uint32
         if (it == r->dev.end()) {
             const R1csData &R = r->data;
             std::vector<U256> dm(R.dict.size());
-            std::vector<unsigned char> kind(R.dict.size());
-            U256 one = u256_from_u64(1), m1;
-            u256_sub(m1, r->F.q, one);
+            std::vector<unsigned short> kind(R.dict.size());
+            auto pow2_exp = [](const U256 &v) -> int {  // k if v == 2^k, else -1
+                int k = -1;
+                for (int i = 0; i < 256; ++i)
+                    if ((v.v[i >> 6] >> (i & 63)) & 1) {
+                        if (k >= 0) return -1;
+                        k = i;
+                    }
+                return k;
+            };
             for (size_t i = 0; i < R.dict.size(); ++i) {
                 dm[i] = r->F.to_mont(R.dict[i]);
-                kind[i] = R.dict[i] == one ? 1 : (R.dict[i] == m1 ? 2 : 0);
+                U256 negv;
+                u256_sub(negv, r->F.q, R.dict[i]);
+                int kp = pow2_exp(R.dict[i]), kn = R.dict[i].is_zero() ? -1 : pow2_exp(negv);
+                if (kp == 0) kind[i] = 1;
+                else if (kn == 0) kind[i] = 2;
+                else if (kp > 0 && kp < 250) kind[i] = (unsigned short)(3 | (kp << 8));
+                else if (kn > 0 && kn < 250) kind[i] = (unsigned short)(4 | (kn << 8));
+                else kind[i] = 0;
             }
+            // rows sorted by structure so that the rows of a warp have equal length and branch alike
+            size_t m = R.n_constraints;
+            std::vector<uint64_t> sig(m);
+            for (size_t row = 0; row < m; ++row) {
+                uint64_t na = R.row_ptr[3 * row + 1] - R.row_ptr[3 * row], nb = R.row_ptr[3 * row + 2] - R.row_ptr[3 * row + 1],
+                         nc = R.row_ptr[3 * row + 3] - R.row_ptr[3 * row + 2];
+                uint64_t h = 1469598103934665603ull;
+                for (uint64_t k = R.row_ptr[3 * row]; k < R.row_ptr[3 * row + 3]; ++k) h = (h ^ (kind[R.coef[k]] & 0xFF)) * 1099511628211ull;
+                uint64_t total = std::min<uint64_t>(na + nb + nc, 0xFFFF);
+                sig[row] = (total << 48) | ((std::min<uint64_t>(na, 255)) << 40) | ((std::min<uint64_t>(nb, 255)) << 32) | (h & 0xFFFFFFFFull);
+            }
+            std::vector<u32> perm(m);
+            for (size_t i = 0; i < m; ++i) perm[i] = (u32)i;
+            std::stable_sort(perm.begin(), perm.end(), [&](u32 x, u32 y) { return sig[x] > sig[y]; });
             if ((rc = upload(&d.row_ptr, R.row_ptr.data(), R.row_ptr.size() * 8))) return rc;
             if ((rc = upload(&d.col, R.col.data(), R.col.size() * 4))) return rc;
             if ((rc = upload(&d.coef, R.coef.data(), R.coef.size() * 4))) return rc;
             if ((rc = upload(&d.dictM, dm.data(), dm.size() * 32))) return rc;
-            if ((rc = upload(&d.kind, kind.data(), kind.size()))) return rc;
+            if ((rc = upload(&d.kind, kind.data(), kind.size() * 2))) return rc;
+            if ((rc = upload(&d.perm, perm.data(), perm.size() * 4))) return rc;
             r->dev[device] = d;
         } else d = it->second;
     }
@@ -643,13 +675,20 @@ int cw_r1cs_check(cw_r1cs *r, const uint64_t *witness, int is_device_ptr, uint32
     rd.coef = d.coef;
     rd.dictM = d.dictM;
     rd.kind = d.kind;
+    rd.perm = d.perm;
     rd.n_constraints = (u32)R.n_constraints;
     rd.n_wires = (u32)R.n_wires;
+    // instance groups: enough blocks to fill the GPU, as many instances per block as that allows
+    u32 row_blocks = (u32)std::min<uint64_t>((R.n_constraints + 255) / 256, 148 * 8);
+    if (row_blocks == 0) row_blocks = 1;
+    u32 ipb = 1;
+    while (ipb < 8 && (uint64_t)row_blocks * ((batch + 2 * ipb - 1) / (2 * ipb)) >= 148ull * 16) ipb *= 2;
+    ipb = (u32)env_int("CW_R1CS_IPB", (int)ipb);
+    rd.inst_per_block = ipb;
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
-    dim3 grid((u32)std::min<uint64_t>((R.n_constraints + 255) / 256, 148 * 8), std::min<u32>(batch, 65535u));
-    if (grid.x == 0) grid.x = 1;
+    dim3 grid(row_blocks, std::min<u32>((batch + ipb - 1) / ipb, 65535u));
     CU(cudaEventRecord(e0));
     if (R.prime_id == 0) r1cs_check_kernel<0><<<grid, 256>>>(rd, w_d, batch, fb_d);
     else r1cs_check_kernel<1><<<grid, 256>>>(rd, w_d, batch, fb_d);

@@ -154,19 +154,40 @@ __global__ void witness_gather_kernel(const uint4 *__restrict__ slots, const u32
 }
 
 // ---- R1CS check: A.w * B.w == C.w for every row and instance ------------------------------------
-// row_ptr[3m+1], col[nnz], coef[nnz] (index into the dictionary; dictM = coefficient * R mod q,
-// kind: 0 general, 1 = one, 2 = minus one).  witness[inst][n_wires][8 u32] canonical.
-// Thread = (row, instance); rows along threadIdx.x so that neighbouring rows (which touch
-// neighbouring wires) share cache lines; blockIdx.y walks instances.
+// CSR: row_ptr[3m+1] (A, B, C blocks per row), col[nnz] (wire), coef[nnz] (dictionary index).
+// Per dictionary entry: dictM = coefficient * R mod q and a kind word
+//     bits 0-7  : 0 general, 1 = +1, 2 = -1, 3 = +2^k, 4 = -2^k        bits 8-15 : k
+// witness[inst][n_wires][8 u32] canonical.
+//
+// Work decomposition: thread = (row, instance).  Rows are visited through `perm`, a host-side stable
+// sort of the rows by structure (term counts and coefficient kinds), so that the 32 rows of a warp have
+// the same length and take the same branches: circuits mix 3-term boolean rows with 65-term
+// bit-sum rows, and with the natural order every warp would run at the speed of its longest row.
+// blockIdx.y walks groups of instances; a thread re-walks its row for each instance of the group,
+// so the row's col/coef words come from L1 after the first instance.
+//
+// Arithmetic: +-1 coefficients are modular add/sub; +-2^k coefficients shift the witness value when
+// the shifted value provably stays below q (runtime check of the value's bit length; a Montgomery
+// product otherwise); the row product a*b is skipped when a or b is 0 or 1 (boolean-constraint rows).
 struct R1csDev {
     const unsigned long long *row_ptr;
     const u32 *col;
     const u32 *coef;
     const uint4 *dictM;
-    const unsigned char *kind;
+    const unsigned short *kind;
+    const u32 *perm;
     u32 n_constraints;
     u32 n_wires;
+    u32 inst_per_block;
 };
+
+__device__ __forceinline__ u32 u256_bitlen_dev(const u32 *a) {
+    u32 n = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (a[i]) n = 32u * i + (32u - __clz(a[i]));
+    return n;
+}
 
 template <int PRIME>
 __device__ __forceinline__ void r1cs_lc(u32 *acc, const R1csDev &R, unsigned long long b, unsigned long long e,
@@ -178,17 +199,29 @@ __device__ __forceinline__ void r1cs_lc(u32 *acc, const R1csDev &R, unsigned lon
         uint4 lo = w[2 * (size_t)c], hi = w[2 * (size_t)c + 1];
         u32 x[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
         u32 t[8];
-        unsigned char kd = __ldg(&R.kind[ci]);
-        if (kd == 1) {
-            fr_add(t, acc, x, P);
-        } else if (kd == 2) {
-            fr_sub(t, acc, x, P);
-        } else {
+        u32 kw = __ldg(&R.kind[ci]);
+        u32 kd = kw & 0xFF, sh = kw >> 8;
+        bool neg = (kd == 2) || (kd == 4);
+        if (kd >= 3) {
+            if (u256_bitlen_dev(x) + sh < P.qbits) {   // x * 2^sh < 2^(qbits-1) < q : plain shift
+                u32 y[8];
+                u256_shl(y, x, sh);
+                u256_set(x, y);
+            } else {
+                u32 cm[8], p[8];
+                load_const(cm, R.dictM, ci);
+                fr_mont_mul(p, cm, x, P);           // (cR) * x / R = c*x, sign included
+                u256_set(x, p);
+                neg = false;
+            }
+        } else if (kd == 0) {
             u32 cm[8], p[8];
             load_const(cm, R.dictM, ci);
-            fr_mont_mul(p, cm, x, P);  // (cR) * x / R = c*x
-            fr_add(t, acc, p, P);
+            fr_mont_mul(p, cm, x, P);
+            u256_set(x, p);
         }
+        if (neg) fr_sub(t, acc, x, P);
+        else fr_add(t, acc, x, P);
         u256_set(acc, t);
     }
 }
@@ -197,18 +230,31 @@ template <int PRIME>
 __global__ void __launch_bounds__(256) r1cs_check_kernel(R1csDev R, const uint4 *__restrict__ witness, u32 batch,
                                                          unsigned long long *__restrict__ first_bad) {
     const FrParams &P = c_fr[PRIME];
-    for (u32 inst = blockIdx.y; inst < batch; inst += gridDim.y) {
-        const uint4 *w = witness + (size_t)inst * R.n_wires * 2;
-        for (u32 row = blockIdx.x * blockDim.x + threadIdx.x; row < R.n_constraints; row += gridDim.x * blockDim.x) {
-            unsigned long long p0 = R.row_ptr[3 * (size_t)row], p1 = R.row_ptr[3 * (size_t)row + 1],
-                               p2 = R.row_ptr[3 * (size_t)row + 2], p3 = R.row_ptr[3 * (size_t)row + 3];
-            u32 a[8], b[8], c[8], ab[8], c1[8];
+    const u32 i0 = blockIdx.y * R.inst_per_block;
+    const u32 i1 = min(batch, i0 + R.inst_per_block);
+    for (u32 rs = blockIdx.x * blockDim.x + threadIdx.x; rs < R.n_constraints; rs += gridDim.x * blockDim.x) {
+        const u32 row = __ldg(&R.perm[rs]);
+        const unsigned long long p0 = R.row_ptr[3 * (size_t)row], p1 = R.row_ptr[3 * (size_t)row + 1],
+                                 p2 = R.row_ptr[3 * (size_t)row + 2], p3 = R.row_ptr[3 * (size_t)row + 3];
+        for (u32 inst = i0; inst < i1; ++inst) {
+            const uint4 *w = witness + (size_t)inst * R.n_wires * 2;
+            u32 a[8], b[8], c[8];
             r1cs_lc<PRIME>(a, R, p0, p1, w, P);
             r1cs_lc<PRIME>(b, R, p1, p2, w, P);
             r1cs_lc<PRIME>(c, R, p2, p3, w, P);
-            fr_mont_mul(ab, a, b, P);  // a*b/R
-            fr_from_mont(c1, c, P);    // c/R
-            if (!u256_eq(ab, c1)) atomicMin(&first_bad[inst], (unsigned long long)row);
+            bool ok;
+            u32 ha = a[1] | a[2] | a[3] | a[4] | a[5] | a[6] | a[7];
+            u32 hb = b[1] | b[2] | b[3] | b[4] | b[5] | b[6] | b[7];
+            if ((!ha && a[0] == 0) || (!hb && b[0] == 0)) ok = u256_is_zero(c);
+            else if (!ha && a[0] == 1) ok = u256_eq(b, c);
+            else if (!hb && b[0] == 1) ok = u256_eq(a, c);
+            else {
+                u32 ab[8], c1[8];
+                fr_mont_mul(ab, a, b, P);  // a*b/R
+                fr_from_mont(c1, c, P);    // c/R
+                ok = u256_eq(ab, c1);
+            }
+            if (!ok) atomicMin(&first_bad[inst], (unsigned long long)row);
         }
     }
 }

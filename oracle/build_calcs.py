@@ -1,0 +1,59 @@
+"""Builds the REAL reference witness calculators (reference runtime + hand-lowered <circuit>.cpp,
+see emit_ref_cpp.py) for the circuits the parity tests and the CPU baseline use, into
+oracle/_ref/calc/ (TEST INFRASTRUCTURE).  Needs /root/reference; on the GPU box the prebuilt
+binaries are used.  A calculator is rebuilt only when missing (the big ones take minutes of g++)."""
+from __future__ import annotations
+
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+CALC_DIR = os.path.join(HERE, "_ref", "calc")
+
+
+def circuits():
+    """name -> (prime, builder(desc) -> main template)"""
+    from circom_b200 import circuits as C
+    return {
+        "multiplier2": ("bn128", lambda d: C.multiplier2(d)),
+        "all_ops": ("bn128", lambda d: C.all_ops(d)),
+        "all_ops_bls": ("bls12381", lambda d: C.all_ops(d)),
+        "less_than8": ("bn128", lambda d: C.less_than(d, 8)),
+        "poseidon2": ("bn128", lambda d: C.poseidon(d, 2)),
+        "ecdsa_scale_2x5": ("bn128", lambda d: C.ecdsa_scale(d, 2, 5)),
+        "ecdsa_scale_8x132": ("bn128", lambda d: C.ecdsa_scale(d, 8, 132)),
+    }
+
+
+def make_desc(name: str):
+    from circom_b200.circuit import CircuitDesc
+    prime, mk = circuits()[name]
+    d = CircuitDesc(prime)
+    d.set_main(mk(d), name)
+    return d
+
+
+def calc_path(name: str) -> str:
+    return os.path.join(CALC_DIR, name)
+
+
+def build(names=None, force: bool = False):
+    from . import build_ref
+    from .emit_ref_cpp import build_reference_calculator
+    if not build_ref.have_reference():
+        return []
+    built = []
+    for name in (names or list(circuits())):
+        p = calc_path(name)
+        if not force and os.path.exists(p) and os.path.exists(p + ".dat"):
+            continue
+        build_reference_calculator(make_desc(name), CALC_DIR, name)
+        built.append(name)
+    return built
+
+
+if __name__ == "__main__":
+    print("built:", build(sys.argv[1:] or None, force="--force" in sys.argv))

@@ -15,7 +15,7 @@ SO = os.path.join(HERE, "libcw_oracle.so")
 
 def build(force: bool = False) -> str:
     if force or not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(SRC):
-        subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", SO, SRC])
+        subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-pthread", "-o", SO, SRC])
     return SO
 
 
@@ -40,6 +40,8 @@ def lib():
         _lib.orc_apply.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p,
                                    ctypes.c_void_p, ctypes.c_void_p]
         _lib.orc_free.argtypes = [ctypes.c_void_p]
+        _lib.orc_run_many.restype = ctypes.c_long
+        _lib.orc_run_many.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_int]
     return _lib
 
 
@@ -75,6 +77,11 @@ class COracle:
             for i in range(B):
                 one(i)
         return wit, st
+
+    def run_many(self, inputs: np.ndarray, threads: int) -> int:
+        """throughput mode (witnesses are not kept): returns how many instances finished with status 0"""
+        inputs = np.ascontiguousarray(inputs, dtype=np.uint64).reshape(-1, self.n_inputs, 4)
+        return int(lib().orc_run_many(self._h, inputs.ctypes.data, inputs.shape[0], threads))
 
     def r1cs_check(self, witness: np.ndarray) -> np.ndarray:
         witness = np.ascontiguousarray(witness, dtype=np.uint64).reshape(-1, self.n_signals, 4)

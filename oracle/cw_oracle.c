@@ -420,6 +420,39 @@ int orc_apply(u32 prime, u32 op, const u64 *a, const u64 *b, const u64 *c3, u64 
     return f_apply(&F[prime], op, (fe *)r, (const fe *)a, b ? (const fe *)b : &z, c3 ? (const fe *)c3 : &z);
 }
 
+/* ---- throughput runner for the CPU baseline: `threads` workers, each reusing one witness buffer
+ * (the reference allocates signalValues once per process, calcwit.cpp:33); returns the number of
+ * instances whose status was 0.  inputs[n][n_in][4]. */
+#include <pthread.h>
+typedef struct { const circuit *c; const u64 *inputs; long n; volatile long *next; long ok; } many_t;
+static void *many_worker(void *p) {
+    many_t *m = (many_t *)p;
+    u64 S = orc_total_signals(m->c);
+    u32 n_in = orc_n_inputs(m->c);
+    u64 *wit = (u64 *)malloc(S * 32);
+    for (;;) {
+        long i = __sync_fetch_and_add(m->next, 1);
+        if (i >= m->n) break;
+        if (orc_run(m->c, m->inputs + (u64)i * n_in * 4, wit) == 0) m->ok++;
+    }
+    free(wit);
+    return NULL;
+}
+long orc_run_many(const circuit *c, const u64 *inputs, long n, int threads) {
+    if (threads < 1) threads = 1;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * threads);
+    many_t *ms = (many_t *)calloc(threads, sizeof(many_t));
+    volatile long next = 0;
+    for (int t = 0; t < threads; ++t) {
+        ms[t].c = c; ms[t].inputs = inputs; ms[t].n = n; ms[t].next = &next; ms[t].ok = 0;
+        pthread_create(&th[t], NULL, many_worker, &ms[t]);
+    }
+    long ok = 0;
+    for (int t = 0; t < threads; ++t) { pthread_join(th[t], NULL); ok += ms[t].ok; }
+    free(th); free(ms);
+    return ok;
+}
+
 void orc_free(circuit *c) {
     if (!c) return;
     for (u32 i = 0; i < c->n_tm; ++i) { free(c->tm[i].subs); free(c->tm[i].ops); free(c->tm[i].lc_len); free(c->tm[i].terms); }

@@ -96,3 +96,42 @@ def test_ecdsa_scale_vs_oracle_and_python_ints(lanes, steps, batch):
     n = 2
     ow, st = COracle(d.to_bytes()).run(arr[:n], threads=n)
     assert not st.any() and (ow[:, w2s] == wit[:n]).all()
+
+
+@pytest.mark.parametrize("name", ["multiplier2", "all_ops", "all_ops_bls", "poseidon2", "ecdsa_scale_2x5", "ecdsa_scale_8x132"])
+def test_wtns_bytes_equal_reference_runtime(name, tmp_path):
+    """`.wtns` written by the GPU path == bytes written by the reference's own C++ calculator
+    (oracle/_ref/calc/<name>: reference main.cpp + calcwit.cpp + fr.cpp + hand-lowered circuit) for the
+    same input.json.  --O0 witness list on both sides (the reference .dat carries the identity list)."""
+    import json
+    import os
+    import subprocess
+    from oracle import build_calcs
+    from tests.test_oracle_c import input_json
+    calc = build_calcs.calc_path(name)
+    if not (os.path.exists(calc) and os.path.exists(calc + ".dat")):
+        pytest.skip("reference calculator not prebuilt")
+    d = build_calcs.make_desc(name)
+    rng = np.random.default_rng(21)
+    n_in = d.main.n_in
+    n = 1 if "8x132" in name else 3
+    arr = np.zeros((n, n_in, 4), dtype=np.uint64)
+    if name.startswith("ecdsa"):
+        arr[:, :, 0] = rng.integers(0, 2**64, size=(n, n_in), dtype=np.uint64)
+    else:
+        arr[:, :, :] = rng.integers(0, 2**64, size=(n, n_in, 4), dtype=np.uint64)
+        arr[:, :, 3] &= np.uint64(0x0FFFFFFFFFFFFFFF)
+        if name.startswith("all_ops"):
+            arr[:, 1, 1:] = 0
+    c = Circuit(d, o0=True)
+    b = Batch(c, n)
+    b.set_inputs(arr)
+    b.run()
+    assert not b.status().any()
+    for i in range(n):
+        jp, wp, gp = str(tmp_path / "in.json"), str(tmp_path / "ref.wtns"), str(tmp_path / "gpu.wtns")
+        json.dump(input_json(d, arr[i]), open(jp, "w"))
+        r = subprocess.run([calc, jp, wp], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-300:]
+        b.write_wtns(i, gp)
+        assert open(gp, "rb").read() == open(wp, "rb").read()

@@ -52,7 +52,7 @@ def make_workload(args):
     if args.workload == "ecdsa_scale":
         d.set_main(C.ecdsa_scale(d, args.lanes, args.chain), "ecdsa_scale_%dx%d" % (args.lanes, args.chain))
         label = "ecdsa-scale synthetic (secp256k1 BigMultModP chains %dx%d, 4x64-bit limbs), BN254" % (args.lanes, args.chain)
-        batch = args.batch_per_gpu or 64
+        batch = args.batch_per_gpu or 256
     elif args.workload == "sha256compression":
         d.set_main(C.sha256_compression(d), "sha256compression")
         label = "Sha256compression, BN254"
@@ -247,14 +247,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     # one-time collective: rank 0's circuit description is broadcast over NCCL, every rank lowers it
-    blob = desc.to_bytes()
-    if world > 1:
-        n = torch.tensor([len(blob)], dtype=torch.int64, device="cuda")
-        dist.broadcast(n, 0)
-        buf = torch.frombuffer(bytearray(blob), dtype=torch.uint8).cuda() if rank == 0 else \
-            torch.empty(int(n.item()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(buf, 0)
-        blob = bytes(buf.cpu().numpy().tobytes())
+    from circom_b200.distributed import broadcast_blob
+    blob = broadcast_blob(desc.to_bytes() if rank == 0 else None, rank, world, device="cuda")
     circuit = Circuit(blob)
     st = circuit.stats
     b = Batch(circuit, batch, local_rank)

@@ -99,12 +99,23 @@ struct Val {
     uint16_t bits = 256;                    // the canonical integer is < 2^bits (256 = nothing known)
     uint8_t org_op = 0;                     // IR opcode that produced the value (0 = input / constant)
     int32_t org_a = -1, org_b = -1;         // its operand values
+    // bit-field provenance (integer identities on the canonical value of `src`):
+    //   fld_src >= 0 : value == (src >> fld_k) & (2^fld_m - 1)                (a field moved to position 0)
+    //   bf_src  >= 0 : value == src & ((2^bf_len - 1) << bf_lo)               (a field left in place)
+    // An in-place field may be *virtual* (no slot yet): sums of adjacent in-place fields of the same
+    // source are again in-place fields, so `sum_i ((x >> i) & 1) << i` never materialises its terms.
+    int32_t fld_src = -1, bf_src = -1;
+    uint16_t fld_k = 0, fld_m = 0, bf_lo = 0, bf_len = 0;
 };
 
 // device-only opcodes (kernels.cuh / fr_device.cuh)
-enum { DOP_BITS = 29, DOP_ASSERT_BOOL = 30, DOP_MULSMALL = 31 };
+enum { DOP_BITS = 29, DOP_ASSERT_BOOL = 30, DOP_MULSMALL = 31, DOP_BITSIP = 32, DOP_ASSERT_FITS = 33 };
 inline bool c_is_immediate(uint32_t opcode) {
-    return opcode == CW_OP_ASSERT || opcode == CW_OP_ASSERT_EQ || opcode == DOP_BITS || opcode == DOP_ASSERT_BOOL;
+    return opcode == CW_OP_ASSERT || opcode == CW_OP_ASSERT_EQ || opcode == DOP_BITS || opcode == DOP_ASSERT_BOOL ||
+           opcode == DOP_BITSIP || opcode == DOP_ASSERT_FITS;
+}
+inline bool is_assert_op(uint32_t opcode) {
+    return opcode == CW_OP_ASSERT || opcode == CW_OP_ASSERT_EQ || opcode == DOP_ASSERT_BOOL || opcode == DOP_ASSERT_FITS;
 }
 
 struct Lowerer {
@@ -123,7 +134,7 @@ struct Lowerer {
     std::vector<U256> consts;
     std::unordered_map<std::string, uint32_t> const_index;
     uint32_t n_pre = 0;
-    uint64_t n_ir_ops = 0, n_conv = 0, n_asserts = 0;
+    uint64_t n_ir_ops = 0, n_conv = 0, n_asserts = 0, n_static_asserts = 0;
     int32_t vid_one = -1;
 
     Lowerer(Tape &t, uint32_t fl) : T(t), F(t.F), flags(fl) {}
@@ -160,10 +171,25 @@ struct Lowerer {
         vals.push_back(v);
         return (int32_t)vals.size() - 1;
     }
-    bool has(int32_t vid, Form f) const { return vals[vid].cid >= 0 || vals[vid].slot[f] != NO_SLOT; }
+    bool is_virtual(int32_t vid) const {
+        const Val &v = vals[vid];
+        return v.cid < 0 && v.bf_src >= 0 && v.slot[FC] == NO_SLOT && v.slot[FM] == NO_SLOT && v.slot[FD] == NO_SLOT;
+    }
+    // a virtual in-place field gets its slot on first real use: one mask op on the source
+    void materialise(int32_t vid) {
+        if (!is_virtual(vid)) return;
+        int32_t src = vals[vid].bf_src;
+        uint32_t imm = (uint32_t)vals[vid].bf_lo | ((uint32_t)vals[vid].bf_len << 8);
+        uint32_t s = emit(DOP_BITSIP, need(src, FC), NO_SLOT, imm, true);
+        vals[vid].slot[FC] = s;
+    }
+    bool has(int32_t vid, Form f) const {
+        return vals[vid].cid >= 0 || vals[vid].slot[f] != NO_SLOT || (f == FC && is_virtual(vid));
+    }
     bool is_const(int32_t vid) const { return vals[vid].cid >= 0; }
     // operand holding `vid` in form `f` (FC or FM), converting (once) if necessary
     uint32_t need(int32_t vid, Form f) {
+        materialise(vid);
         Val &v = vals[vid];
         if (v.cid >= 0) return const_operand(v.cid, f);
         if (v.slot[f] != NO_SLOT) return v.slot[f];
@@ -185,6 +211,7 @@ struct Lowerer {
     }
     // operand for a zero / non-zero test: any representation will do
     uint32_t need_any(int32_t vid) {
+        materialise(vid);
         const Val &v = vals[vid];
         if (v.cid >= 0) return const_operand(v.cid, FC);
         for (int f = 0; f < 3; ++f)
@@ -272,7 +299,9 @@ struct Lowerer {
 
     int32_t lower_op(uint32_t op, int32_t a, int32_t b, int32_t c, bool zero_test_only = false) {
         int32_t r = -1;
+        size_t n_before = vals.size();
         if (!(flags & CW_FLAG_NO_PEEPHOLE)) r = peephole(op, a, b);
+        if (r >= 0 && (size_t)r < n_before) return r;  // the result is an existing value (x * 1)
         if (r < 0) r = lower_op_plain(op, a, b, c, zero_test_only);
         Val &v = vals[r];
         v.bits = (uint16_t)range_of(op, a, b);
@@ -298,7 +327,31 @@ struct Lowerer {
                     k = (uint32_t)kk;
                     x = vx.org_a;
                 }
-                return new_val(emit(DOP_BITS, need(x, FC), NO_SLOT, k | (m << 16), true), FC);
+                int32_t r = new_val(emit(DOP_BITS, need(x, FC), NO_SLOT, k | (m << 16), true), FC);
+                vals[r].fld_src = x;
+                vals[r].fld_k = (uint16_t)k;
+                vals[r].fld_m = (uint16_t)m;
+                if (k == 0) {  // a low field is already in place
+                    vals[r].bf_src = x;
+                    vals[r].bf_lo = 0;
+                    vals[r].bf_len = (uint16_t)m;
+                }
+                return r;
+            }
+        }
+        if (op == CW_OP_ADD && a >= 0 && b >= 0) {
+            // adjacent in-place fields of one source add up to the covering field (no carries)
+            const Val &va = vals[a], &vb = vals[b];
+            if (va.bf_src >= 0 && va.bf_src == vb.bf_src && va.cid < 0 && vb.cid < 0) {
+                const Val &lo = va.bf_lo <= vb.bf_lo ? va : vb, &hi = va.bf_lo <= vb.bf_lo ? vb : va;
+                if ((uint32_t)lo.bf_lo + lo.bf_len == hi.bf_lo && (uint32_t)lo.bf_lo + lo.bf_len + hi.bf_len <= 256) {
+                    Val nv;
+                    nv.bf_src = va.bf_src;
+                    nv.bf_lo = lo.bf_lo;
+                    nv.bf_len = (uint16_t)(lo.bf_len + hi.bf_len);
+                    vals.push_back(nv);  // virtual: materialised by need() if anything reads it
+                    return (int32_t)vals.size() - 1;
+                }
             }
         }
         if (op == CW_OP_MUL) {
@@ -307,8 +360,16 @@ struct Lowerer {
             int32_t x = -1;
             if (const_pow2(b, k)) x = a;
             else if (const_pow2(a, k)) x = b;
+            if (x >= 0 && !is_const(x) && k == 0) return x;  // x * 1
+            if (x >= 0 && !is_const(x) && vals[x].fld_src >= 0 && vals[x].fld_k == k && k + vals[x].fld_m <= 256) {
+                Val nv;  // ((src >> k) & mask) << k  ==  src & (mask << k)
+                nv.bf_src = vals[x].fld_src;
+                nv.bf_lo = (uint16_t)k;
+                nv.bf_len = vals[x].fld_m;
+                vals.push_back(nv);
+                return (int32_t)vals.size() - 1;
+            }
             if (x >= 0 && !is_const(x) && has(x, FC) && vbits(x) + k <= qb() - 1) {
-                if (k == 0) return -1;
                 U256 kc = u256_from_u64(k);
                 return new_val(emit(CW_OP_SHL, need(x, FC), OPERAND_CONST | raw_const(kc)), FC);
             }
@@ -317,6 +378,21 @@ struct Lowerer {
                 return new_val(emit(DOP_MULSMALL, need(a, FC), need(b, FC)), FC);
         }
         return -1;
+    }
+
+    // `x & (2^m - 1) === x` (the recomposition check of a bit decomposition)  ->  x < 2^m
+    bool try_assert_fits(int32_t a, int32_t b, uint32_t id) {
+        for (int s = 0; s < 2; ++s) {
+            int32_t f = s ? b : a, x = s ? a : b;
+            const Val &vf = vals[f];
+            if (vf.cid < 0 && vf.bf_src == x && vf.bf_lo == 0 && !is_const(x)) {
+                if (vbits(x) <= vf.bf_len) { ++n_static_asserts; return true; }
+                U256 m = u256_from_u64(vf.bf_len);
+                emit(DOP_ASSERT_FITS, need(x, FC), OPERAND_CONST | raw_const(m), id, true);
+                return true;
+            }
+        }
+        return false;
     }
 
     // `x*(x-1) === 0`  ->  one boolean assert on x
@@ -328,6 +404,7 @@ struct Lowerer {
             const Val &vy = vals[y];
             uint64_t one;
             if (vy.org_op == CW_OP_SUB && vy.org_a == x && const_u64(vy.org_b, one) && one == 1 && !is_const(x)) {
+                if (vbits(x) <= 1) { ++n_static_asserts; return true; }  // x is a bit by construction: cannot fail
                 Form f = has(x, FC) ? FC : FM;
                 U256 o = f == FC ? u256_from_u64(1) : F.r1;
                 emit(DOP_ASSERT_BOOL, need(x, f), OPERAND_CONST | raw_const(o), id, true);
@@ -439,6 +516,7 @@ struct Lowerer {
                 if (flags & CW_FLAG_NO_ASSERTS) continue;
                 if (o.op == CW_OP_ASSERT_EQ) {
                     int32_t a = load(o.a), b = load(o.b);
+                    if (!(flags & CW_FLAG_NO_PEEPHOLE) && try_assert_fits(a, b, id)) continue;
                     if (!(flags & CW_FLAG_NO_PEEPHOLE) && is_const_zero(b) && try_assert_bool(a, id)) continue;
                     if (!(flags & CW_FLAG_NO_PEEPHOLE) && is_const_zero(a) && try_assert_bool(b, id)) continue;
                     if (is_const_zero(b)) emit(CW_OP_ASSERT_EQ, need_any(a), need(b, FC), id, true);
@@ -766,7 +844,7 @@ struct Lowerer {
         // dead-value elimination (reverse sweep; provisional order is topological)
         for (size_t i = n_prov; i-- > 0;) {
             uint32_t *o = &pops[i * 4];
-            bool is_assert = o[0] == CW_OP_ASSERT || o[0] == CW_OP_ASSERT_EQ || o[0] == DOP_ASSERT_BOOL;
+            bool is_assert = is_assert_op(o[0]);
             if (!is_assert && !live[n_pre + i]) continue;
             live[n_pre + i] = 1;
             for (int k = 1; k <= 3; ++k) {

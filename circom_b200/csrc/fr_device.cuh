@@ -375,7 +375,9 @@ enum {
     OP_SELECT = 25, OP_ASSERT = 26, OP_ASSERT_EQ = 27, OP_INV = 28,
     OP_BITS = 29,         // (a >> k) & (2^m - 1), imm = k | m << 16  (fused `(x >> k) & mask` hints)
     OP_ASSERT_BOOL = 30,  // a == 0 || a == b  (b = the constant one in a's representation)
-    OP_MULSMALL = 31      // a * b as integers, statically known to stay below q (no reduction)
+    OP_MULSMALL = 31,     // a * b as integers, statically known to stay below q (no reduction)
+    OP_BITSIP = 32,       // a & ((2^len - 1) << lo), imm = lo | len << 8  (sum of adjacent bit fields)
+    OP_ASSERT_FITS = 33   // a < 2^m, m = b[0]  (recomposition check of a bit decomposition)
 };
 
 // low 256 bits of the integer product (36 limb products instead of CIOS' 128)
@@ -407,8 +409,36 @@ CW_HD void u256_bits(u32 *r, const u32 *a, u32 imm) {
     }
 }
 
+CW_HD void u256_bits_in_place(u32 *r, const u32 *a, u32 imm) {
+    u32 lo = imm & 0xFFu, len = imm >> 8, hi = lo + len;  // keep bits [lo, hi)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        u32 b0 = 32u * i, b1 = b0 + 32u;
+        u32 m = 0;
+        if (hi > b0 && lo < b1) {
+            u32 from = lo > b0 ? lo - b0 : 0u, to = hi < b1 ? hi - b0 : 32u;  // bit range inside this limb
+            u32 w = to - from;
+            m = (w >= 32u ? 0xFFFFFFFFu : ((1u << w) - 1u)) << from;
+        }
+        r[i] = a[i] & m;
+    }
+}
+CW_HD u32 u256_bitlen(const u32 *a) {
+    u32 n = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (a[i]) {
+            u32 x = a[i], c = 0;
+            while (x) { x >>= 1; ++c; }
+            n = 32u * i + c;
+        }
+    }
+    return n;
+}
+
 CW_HD void fr_exec(u32 opcode, u32 *r, const u32 *a, const u32 *b, u32 imm, const FrParams &P, int &err) {
     switch (opcode) {
+        case OP_BITSIP: u256_bits_in_place(r, a, imm); break;
         case OP_BITS: u256_bits(r, a, imm); break;
         case OP_MULSMALL: u256_mul_lo(r, a, b); break;
         case OP_MUL: fr_mont_mul(r, a, b, P); break;

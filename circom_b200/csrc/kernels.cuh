@@ -43,6 +43,14 @@ __device__ __forceinline__ void load_operand(u32 *v, u32 operand, const uint4 *_
     else load_slot(v, tile_base, operand, bt_log2, inst);
 }
 
+__device__ __forceinline__ u32 u256_bitlen_dev(const u32 *a) {
+    u32 n = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (a[i]) n = 32u * i + (32u - __clz(a[i]));
+    return n;
+}
+
 struct TapeDev {
     const uint4 *ops;          // {opcode, a, b, c}
     const u32 *level_start;    // n_levels + 1
@@ -105,10 +113,11 @@ __global__ void __launch_bounds__(1024) tape_exec_kernel(TapeDev tp, uint4 *__re
                 bool t = !u256_is_zero(c);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) r[i] = t ? a[i] : b[i];
-            } else if (op.x == OP_ASSERT_EQ || op.x == OP_ASSERT || op.x == OP_ASSERT_BOOL) {
-                bool ok = op.x == OP_ASSERT_EQ ? u256_eq(a, b)
-                          : op.x == OP_ASSERT  ? !u256_is_zero(a)
-                                               : (u256_is_zero(a) || u256_eq(a, b));
+            } else if (op.x == OP_ASSERT_EQ || op.x == OP_ASSERT || op.x == OP_ASSERT_BOOL || op.x == OP_ASSERT_FITS) {
+                bool ok = op.x == OP_ASSERT_EQ     ? u256_eq(a, b)
+                          : op.x == OP_ASSERT      ? !u256_is_zero(a)
+                          : op.x == OP_ASSERT_BOOL ? (u256_is_zero(a) || u256_eq(a, b))
+                                                   : (u256_bitlen_dev(a) <= b[0]);
                 if (!ok && inst < batch) atomicMin(&first_assert[inst], op.w);
                 continue;  // asserts have no destination value
             } else {
@@ -180,14 +189,6 @@ struct R1csDev {
     u32 n_wires;
     u32 inst_per_block;
 };
-
-__device__ __forceinline__ u32 u256_bitlen_dev(const u32 *a) {
-    u32 n = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-        if (a[i]) n = 32u * i + (32u - __clz(a[i]));
-    return n;
-}
 
 template <int PRIME>
 __device__ __forceinline__ void r1cs_lc(u32 *acc, const R1csDev &R, unsigned long long b, unsigned long long e,

@@ -79,8 +79,9 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
                 u32 c[8];
                 operand(op[3], c);
                 memcpy(r, u256_is_zero(c) ? b : a, 32);
-            } else if (op[0] == OP_ASSERT_EQ || op[0] == OP_ASSERT || op[0] == OP_ASSERT_BOOL) {
-                bool ok = op[0] == OP_ASSERT_EQ ? u256_eq(a, b) : op[0] == OP_ASSERT ? !u256_is_zero(a) : (u256_is_zero(a) || u256_eq(a, b));
+            } else if (op[0] == OP_ASSERT_EQ || op[0] == OP_ASSERT || op[0] == OP_ASSERT_BOOL || op[0] == OP_ASSERT_FITS) {
+                bool ok = op[0] == OP_ASSERT_EQ ? u256_eq(a, b) : op[0] == OP_ASSERT ? !u256_is_zero(a)
+                          : op[0] == OP_ASSERT_BOOL ? (u256_is_zero(a) || u256_eq(a, b)) : (u256_bitlen(a) <= b[0]);
                 if (!ok && op[3] < first_assert) first_assert = op[3];
                 continue;
             } else {
@@ -132,7 +133,7 @@ int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
     if (t.n_levels() && t.level_start[t.n_levels()] != t.n_tape_ops()) { g_err = "level table does not cover the tape"; return -2; }
     for (size_t i = 0; i < t.n_tape_ops(); ++i) {
         const uint32_t *op = &t.ops[i * 4];
-        bool c_imm = op[0] == OP_ASSERT || op[0] == OP_ASSERT_EQ || op[0] == OP_ASSERT_BOOL || op[0] == OP_BITS;
+        bool c_imm = op[0] == OP_ASSERT || op[0] == OP_ASSERT_EQ || op[0] == OP_ASSERT_BOOL || op[0] == OP_BITS || op[0] == OP_BITSIP || op[0] == OP_ASSERT_FITS;
         for (int k = 1; k <= 3; ++k) {
             if (k == 3 && c_imm) break;
             if (op[k] & OPERAND_CONST) {

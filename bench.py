@@ -52,7 +52,7 @@ def make_workload(args):
     if args.workload == "ecdsa_scale":
         d.set_main(C.ecdsa_scale(d, args.lanes, args.chain), "ecdsa_scale_%dx%d" % (args.lanes, args.chain))
         label = "ecdsa-scale synthetic (secp256k1 BigMultModP chains %dx%d, 4x64-bit limbs), BN254" % (args.lanes, args.chain)
-        batch = args.batch_per_gpu or 256
+        batch = args.batch_per_gpu or 1024
     elif args.workload == "sha256compression":
         d.set_main(C.sha256_compression(d), "sha256compression")
         label = "Sha256compression, BN254"
@@ -97,7 +97,7 @@ class ClockSampler:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
                                           "--format=csv,noheader,nounits", "-lms", "50", "-f", self.path],
                                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-            time.sleep(0.3)
+            time.sleep(0.5)
         except Exception:
             self.proc = None
 
@@ -276,12 +276,12 @@ def main():
         b.witness(out=pin_out.numpy().view(np.uint64))
 
     # ---- device-resident timing ------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()            # nvidia-smi needs a moment to attach: it samples warm-up + timed steps (all under load)
     for _ in range(args.warmup):
         step_resident()
     b.sync()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     t0 = time.perf_counter()
     exec_ms = gather_ms = 0.0
     for _ in range(args.steps):

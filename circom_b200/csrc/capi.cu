@@ -330,6 +330,11 @@ int cw_batch_create(const cw_circuit *c, uint32_t batch, int device, cw_batch **
         uint64_t avg = t.n_levels() ? (t.n_tape_ops() / t.n_levels() + 1) * btn : 64;
         th = 64;
         while (th < 512 && (uint64_t)th < avg) th <<= 1;
+        // many tiles per SM hide latency better than wide CTAs: keep <= ~1024 resident threads per SM
+        // (measured on B200: batch 256 -> 512 threads, 512 -> 256, 1024 -> 128)
+        u32 tiles = b->batch_padded >> bt;
+        u32 per_sm = (tiles + 147) / 148;
+        while (th > 64 && (u32)th * per_sm > 1024) th >>= 1;
     }
     th = (th + 31) / 32 * 32;
     if (th > 1024) th = 1024;

@@ -7,17 +7,19 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcircom_b200.so")
+CLI = os.path.join(HERE, "circom_cuda_witness")
 SOURCES = ["capi.cu", "flatten.cpp", "formats.cpp"]
+CLI_SOURCES = ["cli.cpp"]
 HEADERS = ["kernels.cuh", "fr_device.cuh", "tape.h", "u256.h", os.path.join("..", "..", "include", "circom_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 
 
 def _stale() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(CLI):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS + CLI_SOURCES)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -31,6 +33,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + r.stdout[-3000:] + r.stderr[-6000:])
     if verbose:
         print(r.stderr)
+    # command-line calculator (client of the C ABI only)
+    r = subprocess.run(["g++", "-O2", "-std=c++17", "-o", CLI, os.path.join(CSRC, "cli.cpp"), "-L" + HERE,
+                        "-lcircom_b200", "-Wl,-rpath,$ORIGIN"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ (cli) failed:\n" + r.stderr[-4000:])
     return LIB
 
 

@@ -1,0 +1,239 @@
+// circom_cuda_witness <circuit.cb2c> <input.json> <output.wtns>
+//
+// Same command-line shape as the reference's generated calculator (`<bin> <input.json> <output.wtns>`,
+// c_elements/common/main.cpp:336-373), on top of the C ABI only.  input.json is one input object, or an
+// array of input objects (a batch: witnesses are computed together on the GPU and written to
+// <output>.0.wtns, <output>.1.wtns, ...).  Input handling follows loadJson / qualify_input /
+// json2FrElements (main.cpp:126-286): nested objects and arrays of objects give qualified names
+// `a.b[i].c`, values are decimal / 0x / 0b / 0o strings or JSON integers, reduced modulo the prime.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/circom_b200.h"
+#include "u256.h"
+
+namespace {
+
+// ---- a very small JSON reader (objects, arrays, strings, numbers, true/false/null) -------------------
+struct JValue {
+    enum Kind { Null, Bool, Number, String, Array, Object } kind = Null;
+    std::string text;  // Number (verbatim) / String
+    bool b = false;
+    std::vector<JValue> arr;
+    std::vector<std::pair<std::string, JValue>> obj;  // insertion order (nlohmann sorts keys; order is irrelevant here)
+};
+
+struct JParser {
+    const std::string &s;
+    size_t p = 0;
+    explicit JParser(const std::string &str) : s(str) {}
+    void ws() { while (p < s.size() && (s[p] == ' ' || s[p] == '\n' || s[p] == '\t' || s[p] == '\r')) ++p; }
+    [[noreturn]] void fail(const char *m) { throw std::runtime_error(std::string("JSON: ") + m + " at offset " + std::to_string(p)); }
+    JValue parse() {
+        ws();
+        if (p >= s.size()) fail("unexpected end");
+        JValue v;
+        char c = s[p];
+        if (c == '{') {
+            v.kind = JValue::Object;
+            ++p;
+            ws();
+            if (p < s.size() && s[p] == '}') { ++p; return v; }
+            for (;;) {
+                ws();
+                if (p >= s.size() || s[p] != '"') fail("expected key");
+                std::string k = str();
+                ws();
+                if (p >= s.size() || s[p] != ':') fail("expected ':'");
+                ++p;
+                v.obj.emplace_back(k, parse());
+                ws();
+                if (p < s.size() && s[p] == ',') { ++p; continue; }
+                if (p < s.size() && s[p] == '}') { ++p; break; }
+                fail("expected ',' or '}'");
+            }
+        } else if (c == '[') {
+            v.kind = JValue::Array;
+            ++p;
+            ws();
+            if (p < s.size() && s[p] == ']') { ++p; return v; }
+            for (;;) {
+                v.arr.push_back(parse());
+                ws();
+                if (p < s.size() && s[p] == ',') { ++p; continue; }
+                if (p < s.size() && s[p] == ']') { ++p; break; }
+                fail("expected ',' or ']'");
+            }
+        } else if (c == '"') {
+            v.kind = JValue::String;
+            v.text = str();
+        } else if (c == 't' && s.compare(p, 4, "true") == 0) { v.kind = JValue::Bool; v.b = true; p += 4; }
+        else if (c == 'f' && s.compare(p, 5, "false") == 0) { v.kind = JValue::Bool; p += 5; }
+        else if (c == 'n' && s.compare(p, 4, "null") == 0) { p += 4; }
+        else {
+            size_t b = p;
+            while (p < s.size() && (isdigit((unsigned char)s[p]) || s[p] == '-' || s[p] == '+' || s[p] == '.' || s[p] == 'e' || s[p] == 'E')) ++p;
+            if (b == p) fail("unexpected character");
+            v.kind = JValue::Number;
+            v.text = s.substr(b, p - b);
+        }
+        return v;
+    }
+    std::string str() {
+        std::string out;
+        ++p;
+        while (p < s.size() && s[p] != '"') {
+            if (s[p] == '\\' && p + 1 < s.size()) {
+                char e = s[p + 1];
+                out.push_back(e == 'n' ? '\n' : e == 't' ? '\t' : e);
+                p += 2;
+            } else out.push_back(s[p++]);
+        }
+        if (p >= s.size()) fail("unterminated string");
+        ++p;
+        return out;
+    }
+};
+
+// ---- json2FrElements (main.cpp:144-188) -----------------------------------------------------------------
+cw::U256 parse_number(const std::string &text_in, bool is_string, const cw::FieldParams &F) {
+    std::string t = text_in;
+    unsigned base = 10;
+    if (is_string && t.size() >= 2 && t[0] == '0') {
+        char c = (char)tolower(t[1]);
+        if (c == 'x') { base = 16; t = t.substr(2); }
+        else if (c == 'b') { base = 2; t = t.substr(2); }
+        else if (c == 'o') { base = 8; t = t.substr(2); }
+    }
+    if (!is_string) {  // JSON number: integers only (the reference prints the double with %.0f)
+        size_t dot = t.find_first_of(".eE");
+        if (dot != std::string::npos) {
+            std::ostringstream o;
+            o.setf(std::ios::fixed);
+            o.precision(0);
+            o << atof(t.c_str());
+            t = o.str();
+        }
+    }
+    if (t.empty()) throw std::runtime_error("Invalid number in JSON input: " + text_in);
+    cw::U256 acc = cw::u256_from_u64(0), b = cw::u256_from_u64(base);
+    for (char ch : t) {
+        int d = ch >= '0' && ch <= '9' ? ch - '0' : (ch >= 'a' && ch <= 'f') ? ch - 'a' + 10 : (ch >= 'A' && ch <= 'F') ? ch - 'A' + 10 : 99;
+        if (d >= (int)base) throw std::runtime_error("Invalid number in JSON input: " + text_in);
+        acc = F.addm(F.mulm(acc, b), cw::u256_from_u64((uint64_t)d));
+    }
+    return acc;
+}
+
+void flatten_values(const JValue &v, std::vector<cw::U256> &out, const cw::FieldParams &F) {
+    if (v.kind == JValue::Array) {
+        for (const JValue &e : v.arr) flatten_values(e, out, F);
+    } else if (v.kind == JValue::String) out.push_back(parse_number(v.text, true, F));
+    else if (v.kind == JValue::Number) out.push_back(parse_number(v.text, false, F));
+    else throw std::runtime_error("Invalid JSON type");
+}
+
+bool contains_object(const JValue &v) {
+    if (v.kind == JValue::Object) return true;
+    if (v.kind == JValue::Array)
+        for (const JValue &e : v.arr)
+            if (contains_object(e)) return true;
+    return false;
+}
+void qualify(const std::string &prefix, const JValue &in, std::vector<std::pair<std::string, const JValue *>> &out);
+void qualify_list(const std::string &prefix, const JValue &in, std::vector<std::pair<std::string, const JValue *>> &out) {
+    if (in.kind == JValue::Array) {
+        for (size_t i = 0; i < in.arr.size(); ++i) qualify_list(prefix + "[" + std::to_string(i) + "]", in.arr[i], out);
+    } else qualify(prefix, in, out);
+}
+// qualify_input (main.cpp:221-241)
+void qualify(const std::string &prefix, const JValue &in, std::vector<std::pair<std::string, const JValue *>> &out) {
+    if (in.kind == JValue::Array) {
+        if (!in.arr.empty() && contains_object(in)) qualify_list(prefix, in, out);
+        else out.emplace_back(prefix, &in);
+    } else if (in.kind == JValue::Object) {
+        for (const auto &kv : in.obj) qualify(prefix.empty() ? kv.first : prefix + "." + kv.first, kv.second, out);
+    } else out.emplace_back(prefix, &in);
+}
+
+#define CK(call)                                                                      \
+    do {                                                                              \
+        int rc_ = (call);                                                             \
+        if (rc_ != CW_OK) throw std::runtime_error(std::string(#call) + ": " + cw_last_error()); \
+    } while (0)
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    if (argc != 4) {
+        fprintf(stderr, "Usage: %s <circuit.cb2c> <input.json> <output.wtns>\n", argv[0]);
+        return 1;
+    }
+    try {
+        cw_circuit *c = nullptr;
+        // CW_O0=1 keeps every signal in the witness (the layout of a reference build with --O0)
+        CK(cw_circuit_load(argv[1], getenv("CW_O0") ? CW_FLAG_O0 : 0, &c));
+        int prime_id = 0;
+        CK(cw_circuit_prime(c, &prime_id, nullptr));
+        cw::FieldParams F = cw::make_field(prime_id);
+        std::ifstream f(argv[2]);
+        if (!f) throw std::runtime_error(std::string("cannot open ") + argv[2]);
+        std::stringstream ss;
+        ss << f.rdbuf();
+        std::string text = ss.str();
+        JValue root = JParser(text).parse();
+        std::vector<const JValue *> instances;
+        bool is_batch = root.kind == JValue::Array;
+        if (is_batch) for (const JValue &e : root.arr) instances.push_back(&e);
+        else instances.push_back(&root);
+        if (instances.empty()) throw std::runtime_error("no inputs");
+        cw_batch *b = nullptr;
+        CK(cw_batch_create(c, (uint32_t)instances.size(), 0, &b));
+        for (size_t i = 0; i < instances.size(); ++i) {
+            std::vector<std::pair<std::string, const JValue *>> items;
+            qualify("", *instances[i], items);
+            for (auto &it : items) {
+                uint64_t h = cw_fnv1a(it.first.c_str()), size = 0;
+                if (cw_get_input_signal_size(c, h, &size) != CW_OK) throw std::runtime_error("Signal " + it.first + " not found");
+                std::vector<cw::U256> vals;
+                flatten_values(*it.second, vals, F);
+                if (vals.size() < size) throw std::runtime_error("Error loading signal " + it.first + ": Not enough values");
+                if (vals.size() > size) throw std::runtime_error("Error loading signal " + it.first + ": Too many values");
+                for (size_t k = 0; k < vals.size(); ++k) CK(cw_batch_set_input(b, (uint32_t)i, h, (uint32_t)k, vals[k].v));
+            }
+            uint32_t rem = 0;
+            CK(cw_batch_remaining_inputs(b, (uint32_t)i, &rem));
+            if (rem) {
+                fprintf(stderr, "Not all inputs have been set. Only %u out of %u\n", cw_get_main_input_signal_no(c) - rem, cw_get_main_input_signal_no(c));
+                return 1;
+            }
+        }
+        CK(cw_batch_run(b));
+        CK(cw_batch_sync(b));
+        std::vector<int32_t> status(instances.size());
+        CK(cw_batch_status(b, status.data()));
+        for (size_t i = 0; i < instances.size(); ++i) {
+            if (status[i] != 0) {
+                fprintf(stderr, "Failed assert (instance %zu, status %d)\n", i, status[i]);
+                return 1;
+            }
+            std::string out = argv[3];
+            if (is_batch) out += "." + std::to_string(i) + ".wtns";
+            CK(cw_batch_write_wtns(b, (uint32_t)i, out.c_str()));
+        }
+        cw_batch_destroy(b);
+        cw_circuit_destroy(c);
+    } catch (const std::exception &e) {
+        fprintf(stderr, "%s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

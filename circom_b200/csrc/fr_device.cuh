@@ -32,25 +32,61 @@ struct FrParams {
 };
 
 // ---- raw 256-bit helpers -----------------------------------------------------------------------
+// On the device the 8-limb add / subtract are single carry chains (add.cc / addc.cc: 9 integer
+// instructions instead of ~24 with 64-bit emulation); the host build keeps the portable form.
 CW_HD u32 u256_add(u32 *r, const u32 *a, const u32 *b) {  // returns carry
+#if defined(__CUDA_ARCH__)
+    u32 r0, r1, r2, r3, r4, r5, r6, r7, c;
+    asm("add.cc.u32 %0, %9, %17;\n\t"
+        "addc.cc.u32 %1, %10, %18;\n\t"
+        "addc.cc.u32 %2, %11, %19;\n\t"
+        "addc.cc.u32 %3, %12, %20;\n\t"
+        "addc.cc.u32 %4, %13, %21;\n\t"
+        "addc.cc.u32 %5, %14, %22;\n\t"
+        "addc.cc.u32 %6, %15, %23;\n\t"
+        "addc.cc.u32 %7, %16, %24;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3), "=&r"(r4), "=&r"(r5), "=&r"(r6), "=&r"(r7), "=&r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    r[0] = r0; r[1] = r1; r[2] = r2; r[3] = r3; r[4] = r4; r[5] = r5; r[6] = r6; r[7] = r7;
+    return c;
+#else
     u64 c = 0;
-#pragma unroll
     for (int i = 0; i < 8; ++i) {
         c += (u64)a[i] + b[i];
         r[i] = (u32)c;
         c >>= 32;
     }
     return (u32)c;
+#endif
 }
-CW_HD u32 u256_sub(u32 *r, const u32 *a, const u32 *b) {  // returns borrow
+CW_HD u32 u256_sub(u32 *r, const u32 *a, const u32 *b) {  // returns borrow (0 / 1)
+#if defined(__CUDA_ARCH__)
+    u32 r0, r1, r2, r3, r4, r5, r6, r7, c;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3), "=&r"(r4), "=&r"(r5), "=&r"(r6), "=&r"(r7), "=&r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    r[0] = r0; r[1] = r1; r[2] = r2; r[3] = r3; r[4] = r4; r[5] = r5; r[6] = r6; r[7] = r7;
+    return c & 1u;  // 0xFFFFFFFF when the chain ends with a borrow
+#else
     u32 br = 0;
-#pragma unroll
     for (int i = 0; i < 8; ++i) {
         u64 t = (u64)a[i] - b[i] - br;
         r[i] = (u32)t;
         br = (u32)(t >> 63);
     }
     return br;
+#endif
 }
 CW_HD bool u256_geq(const u32 *a, const u32 *b) {  // a >= b
     u32 t[8];

@@ -135,3 +135,41 @@ def test_wtns_bytes_equal_reference_runtime(name, tmp_path):
         assert r.returncode == 0, r.stderr[-300:]
         b.write_wtns(i, gp)
         assert open(gp, "rb").read() == open(wp, "rb").read()
+
+
+def test_cli_matches_reference_calculator(tmp_path):
+    """`circom_cuda_witness circuit.cb2c input.json out.wtns` (client of the C ABI, same command line as
+    the reference's generated binary) writes the bytes the reference calculator writes; a JSON array of
+    inputs is a batch."""
+    import json
+    import os
+    import subprocess
+    from circom_b200 import build as cbuild
+    from oracle import build_calcs
+    from tests.test_oracle_c import input_json
+    calc = build_calcs.calc_path("all_ops")
+    if not os.path.exists(calc):
+        pytest.skip("reference calculator not prebuilt")
+    d = build_calcs.make_desc("all_ops")
+    cb = str(tmp_path / "all_ops.cb2c")
+    d.save(cb)
+    ins = [{"a": "0x1234567890abcdef1234", "b": "77"}, {"a": "5", "b": "0b101"}, {"a": 123456789, "b": "0o17"}]
+    env = dict(os.environ, CW_O0="1")
+    jp = str(tmp_path / "batch.json")
+    json.dump(ins, open(jp, "w"))
+    r = subprocess.run([cbuild.CLI, cb, jp, str(tmp_path / "gpu")], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    for i, inp in enumerate(ins):
+        one = str(tmp_path / ("in%d.json" % i))
+        json.dump(inp, open(one, "w"))
+        ref = str(tmp_path / ("ref%d.wtns" % i))
+        rr = subprocess.run([calc, one, ref], capture_output=True, text=True)
+        assert rr.returncode == 0, rr.stderr
+        assert open(str(tmp_path / ("gpu.%d.wtns" % i)), "rb").read() == open(ref, "rb").read()
+    # reference-style failures
+    json.dump({"a": "1"}, open(jp, "w"))
+    r = subprocess.run([cbuild.CLI, cb, jp, str(tmp_path / "x.wtns")], capture_output=True, text=True, env=env)
+    assert r.returncode != 0 and "Not all inputs have been set" in r.stderr
+    json.dump({"a": "1", "b": ["1", "2"]}, open(jp, "w"))
+    r = subprocess.run([cbuild.CLI, cb, jp, str(tmp_path / "x.wtns")], capture_output=True, text=True, env=env)
+    assert r.returncode != 0 and "Too many values" in r.stderr

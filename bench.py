@@ -318,11 +318,11 @@ def main():
     r1cs_ms = None
     if not args.no_r1cs:
         r = R1cs(circuit)
-        fb, _ = r.check(None, batch=batch, device=local_rank, device_ptr=b.witness_device_ptr())
+        fb, _ = r.check_batch(b, device=local_rank)
         assert (fb == -1).all(), "R1CS check failed on generated witnesses"
         ms = []
         for _ in range(max(2, args.steps)):
-            fb, m = r.check(None, batch=batch, device=local_rank, device_ptr=b.witness_device_ptr())
+            fb, m = r.check_batch(b, device=local_rank)
             ms.append(m)
         t = torch.tensor([float(np.mean(ms))], dtype=torch.float64, device="cuda")
         if world > 1:
@@ -338,7 +338,7 @@ def main():
     peak, peak_src = measured_peaks()
     # algorithmic bytes per instance: every written slot once + witness + inputs
     s_w = st["n_slots"] - 1 - n_in
-    b_wit = 32 * s_w + 32 * W + 32 * n_in
+    b_wit = 32 * s_w + 32 * n_in   # witness entries are slots: written once by the tape, no gather pass
     exec_per_launch_ms = exec_ms / args.steps
     achieved = batch * (32 * s_w + 32 * n_in) / (exec_per_launch_ms / 1e3) / 1e9
     out = {
@@ -350,10 +350,10 @@ def main():
                    "n_levels": st["n_levels"], "parallelism": "batch-sharded x%d" % world,
                    "l2": "working set %.1f GB per step >> L2, rewritten every step" % (batch * st["n_slots"] * 32 / 1e9)},
         "wall_ms_per_step": wall_ms / args.steps,
-        "kernel_ms": {"tape_exec+stage": exec_ms / args.steps, "witness_gather": gather_ms / args.steps},
+        "kernel_ms": {"tape_exec+stage": exec_ms / args.steps},
         "e2e": {"value": total_batch * args.steps / e2e_s, "unit": "witnesses/s",
                 "h2d_bytes_per_step": int(batch * n_in * 32), "d2h_bytes_per_step": int(batch * W * 32)},
-        "gpu_launches": 3 * args.steps,
+        "gpu_launches": 2 * args.steps,   # stage_inputs_kernel + tape_exec_kernel per step
         "clocks": clocks,
         "roofline": {"kernel": "tape_exec_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src,

@@ -79,7 +79,7 @@ struct DevTape {
     uint4 *ops = nullptr;
     u32 *level_start = nullptr;
     uint4 *consts = nullptr;
-    u32 *witness_slot = nullptr;
+    u32 *input_slot = nullptr;
 };
 struct DevR1cs {
     unsigned long long *row_ptr = nullptr;
@@ -131,6 +131,7 @@ struct cw_batch {
     bool host_inputs_dirty = false;
     bool inputs_on_device = false;
     bool ran = false;
+    bool compact_valid = false;  // witness_d holds the contiguous copy of the current run
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
 };
 
@@ -147,7 +148,7 @@ static int get_dev_tape(const cw_circuit *c, int device, DevTape &out) {
     if ((rc = upload(&d.ops, t.ops.data(), t.ops.size() * 4))) return rc;
     if ((rc = upload(&d.level_start, t.level_start.data(), t.level_start.size() * 4))) return rc;
     if ((rc = upload(&d.consts, t.consts.data(), t.consts.size() * 32))) return rc;
-    if ((rc = upload(&d.witness_slot, t.witness_slot.data(), t.witness_slot.size() * 4))) return rc;
+    if ((rc = upload(&d.input_slot, t.input_slot.data(), t.input_slot.size() * 4))) return rc;
     c->dev[device] = d;
     out = d;
     return CW_OK;
@@ -200,7 +201,7 @@ void cw_circuit_destroy(cw_circuit *c) {
         cudaFree(kv.second.ops);
         cudaFree(kv.second.level_start);
         cudaFree(kv.second.consts);
-        cudaFree(kv.second.witness_slot);
+        cudaFree(kv.second.input_slot);
     }
     delete c;
 }
@@ -316,10 +317,7 @@ int cw_batch_create(const cw_circuit *c, uint32_t batch, int device, cw_batch **
     b->batch = batch;
     // tile size: keep at least ~4 CTAs per SM in flight before widening tiles for coalescing
     int bt = env_int("CW_BT_LOG2", -1);
-    if (bt < 0) {
-        bt = 0;
-        while (bt < 5 && (batch >> (bt + 1)) >= 148u * 4u) ++bt;
-    }
+    if (bt < 0) bt = 0;  // BT = 1: a slot is one 32-byte sector and witness rows are contiguous in the slot store
     if (bt > 5) bt = 5;
     b->bt_log2 = (u32)bt;
     u32 btn = 1u << bt;
@@ -342,7 +340,7 @@ int cw_batch_create(const cw_circuit *c, uint32_t batch, int device, cw_batch **
     size_t slot_bytes = (size_t)b->batch_padded * t.n_slots * 32;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    size_t need = slot_bytes + (size_t)batch * (t.n_witness + t.n_inputs) * 32 + (64u << 20);
+    size_t need = slot_bytes + (size_t)batch * t.n_inputs * 32 + (64u << 20);
     if (need > free_b) {
         delete b;
         return fail(CW_ECUDA, "batch needs " + std::to_string(need >> 20) + " MiB of device memory, " +
@@ -352,7 +350,6 @@ int cw_batch_create(const cw_circuit *c, uint32_t batch, int device, cw_batch **
     CU(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     CU(cudaMalloc((void **)&b->slots, slot_bytes));
     CU(cudaMalloc((void **)&b->inputs_d, std::max<size_t>((size_t)batch * t.n_inputs * 32, 32)));
-    CU(cudaMalloc((void **)&b->witness_d, (size_t)batch * t.n_witness * 32));
     CU(cudaMalloc((void **)&b->first_assert_d, (size_t)batch * 4));
     CU(cudaMalloc((void **)&b->err_d, (size_t)batch * 4));
     for (auto &e : b->ev) CU(cudaEventCreate(&e));
@@ -438,7 +435,7 @@ int cw_batch_run(cw_batch *b) {
     tp.consts = b->dt.consts;
     tp.n_levels = (u32)t.n_levels();
     tp.n_slots = t.n_slots;
-    tp.n_pre = t.n_pre;
+    tp.input_slot = b->dt.input_slot;
     tp.n_inputs = (u32)t.n_inputs;
     CU(cudaMemsetAsync(b->first_assert_d, 0xFF, (size_t)b->batch * 4, b->stream));
     CU(cudaMemsetAsync(b->err_d, 0, (size_t)b->batch * 4, b->stream));
@@ -456,14 +453,7 @@ int cw_batch_run(cw_batch *b) {
             tape_exec_kernel<1><<<tiles, b->threads, 0, b->stream>>>(tp, b->slots, b->bt_log2, b->first_assert_d, b->err_d, b->batch);
     }
     CU(cudaEventRecord(b->ev[1], b->stream));
-    {
-        size_t total = (size_t)tiles * t.n_witness << b->bt_log2;
-        u32 grid = (u32)std::min<size_t>((total + 255) / 256, 148 * 16);
-        if (t.F.prime_id == 0)
-            witness_gather_kernel<0><<<grid, 256, 0, b->stream>>>(b->slots, b->dt.witness_slot, b->witness_d, t.n_slots, (u32)t.n_witness, b->batch, b->bt_log2);
-        else
-            witness_gather_kernel<1><<<grid, 256, 0, b->stream>>>(b->slots, b->dt.witness_slot, b->witness_d, t.n_slots, (u32)t.n_witness, b->batch, b->bt_log2);
-    }
+    b->compact_valid = false;  // witness rows are slots [0, n_witness) of each instance: nothing to gather
     CU(cudaEventRecord(b->ev[2], b->stream));
     CU(cudaGetLastError());
     b->ran = true;
@@ -493,19 +483,64 @@ int cw_batch_status(cw_batch *b, int32_t *status) {
     return CW_OK;
 }
 
+// contiguous [batch][n_witness] copy in device memory (only needed for tile layouts with BT > 1 or when
+// a caller insists on a dense device array)
+static int compact_witness(cw_batch *b) {
+    if (b->compact_valid) return CW_OK;
+    const Tape &t = b->c->tape;
+    if (!b->witness_d) CU(cudaMalloc((void **)&b->witness_d, (size_t)b->batch * t.n_witness * 32));
+    if (b->bt_log2 == 0) {
+        CU(cudaMemcpy2DAsync(b->witness_d, (size_t)t.n_witness * 32, b->slots, (size_t)t.n_slots * 32,
+                             (size_t)t.n_witness * 32, b->batch, cudaMemcpyDeviceToDevice, b->stream));
+    } else {
+        u32 tiles = b->batch_padded >> b->bt_log2;
+        size_t total = (size_t)tiles * t.n_witness << b->bt_log2;
+        u32 grid = (u32)std::min<size_t>((total + 255) / 256, 148 * 16);
+        witness_compact_kernel<<<grid, 256, 0, b->stream>>>(b->slots, b->witness_d, t.n_slots, (u32)t.n_witness, b->batch, b->bt_log2);
+        CU(cudaGetLastError());
+    }
+    b->compact_valid = true;
+    return CW_OK;
+}
+
 int cw_batch_get_witness(cw_batch *b, uint64_t *out) {
     if (!b || !out) return fail(CW_EINVAL, "null argument");
     if (!b->ran) return fail(CW_ESTATE, "batch has not been run");
+    const Tape &t = b->c->tape;
     CU(cudaSetDevice(b->device));
-    CU(cudaMemcpyAsync(out, b->witness_d, (size_t)b->batch * b->c->tape.n_witness * 32, cudaMemcpyDeviceToHost, b->stream));
+    if (b->bt_log2 == 0) {  // rows are read in place: pitched device-to-host copy
+        CU(cudaMemcpy2DAsync(out, (size_t)t.n_witness * 32, b->slots, (size_t)t.n_slots * 32, (size_t)t.n_witness * 32,
+                             b->batch, cudaMemcpyDeviceToHost, b->stream));
+    } else {
+        int rc = compact_witness(b);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(out, b->witness_d, (size_t)b->batch * t.n_witness * 32, cudaMemcpyDeviceToHost, b->stream));
+    }
     CU(cudaStreamSynchronize(b->stream));
     return CW_OK;
 }
 
 int cw_batch_witness_device(cw_batch *b, const uint64_t **dptr) {
     if (!b || !dptr) return fail(CW_EINVAL, "null argument");
+    if (!b->ran) return fail(CW_ESTATE, "batch has not been run");
+    CU(cudaSetDevice(b->device));
+    int rc = compact_witness(b);
+    if (rc) return rc;
     *dptr = (const uint64_t *)b->witness_d;
     return CW_OK;
+}
+
+int cw_batch_witness_strided(cw_batch *b, const uint64_t **dptr, uint64_t *stride_elems) {
+    if (!b || !dptr || !stride_elems) return fail(CW_EINVAL, "null argument");
+    if (!b->ran) return fail(CW_ESTATE, "batch has not been run");
+    if (b->bt_log2 == 0) {
+        *dptr = (const uint64_t *)b->slots;
+        *stride_elems = b->c->tape.n_slots;
+        return CW_OK;
+    }
+    int rc = cw_batch_witness_device(b, dptr);
+    *stride_elems = b->c->tape.n_witness;
+    return rc;
 }
 
 void *cw_batch_stream(cw_batch *b) { return b ? (void *)b->stream : nullptr; }
@@ -515,7 +550,7 @@ int cw_batch_last_ms(cw_batch *b, float *exec_ms, float *gather_ms) {
     CU(cudaSetDevice(b->device));
     CU(cudaEventSynchronize(b->ev[2]));
     if (exec_ms) CU(cudaEventElapsedTime(exec_ms, b->ev[0], b->ev[1]));
-    if (gather_ms) CU(cudaEventElapsedTime(gather_ms, b->ev[1], b->ev[2]));
+    if (gather_ms) *gather_ms = 0.f;  // no gather pass: witness rows are written in place by the tape
     return CW_OK;
 }
 
@@ -529,8 +564,14 @@ int cw_batch_wtns_bytes(cw_batch *b, uint32_t inst, uint8_t *out, size_t cap, si
     if (cap < need) return fail(CW_EINVAL, "buffer too small");
     CU(cudaSetDevice(b->device));
     std::vector<uint64_t> w((size_t)t.n_witness * 4);
-    CU(cudaMemcpyAsync(w.data(), b->witness_d + (size_t)inst * t.n_witness * 2, (size_t)t.n_witness * 32,
-                       cudaMemcpyDeviceToHost, b->stream));
+    const uint4 *row;
+    if (b->bt_log2 == 0) row = b->slots + (size_t)inst * t.n_slots * 2;
+    else {
+        int rc = compact_witness(b);
+        if (rc) return rc;
+        row = b->witness_d + (size_t)inst * t.n_witness * 2;
+    }
+    CU(cudaMemcpyAsync(w.data(), row, (size_t)t.n_witness * 32, cudaMemcpyDeviceToHost, b->stream));
     CU(cudaStreamSynchronize(b->stream));
     std::vector<uint8_t> bytes = wtns_bytes(t.F, w.data(), t.n_witness);
     memcpy(out, bytes.data(), need);
@@ -609,7 +650,13 @@ void cw_r1cs_destroy(cw_r1cs *r) {
 
 int cw_r1cs_check(cw_r1cs *r, const uint64_t *witness, int is_device_ptr, uint32_t batch, int device,
                   int64_t *first_bad, float *kernel_ms) {
-    if (!r || !witness || !first_bad || batch == 0) return fail(CW_EINVAL, "bad argument");
+    if (!r) return fail(CW_EINVAL, "bad argument");
+    return cw_r1cs_check_strided(r, witness, r->data.n_wires, is_device_ptr, batch, device, first_bad, kernel_ms);
+}
+
+int cw_r1cs_check_strided(cw_r1cs *r, const uint64_t *witness, uint64_t stride_elems, int is_device_ptr, uint32_t batch,
+                          int device, int64_t *first_bad, float *kernel_ms) {
+    if (!r || !witness || !first_bad || batch == 0 || stride_elems < r->data.n_wires) return fail(CW_EINVAL, "bad argument");
     int rc = ensure_device(device);
     if (rc) return rc;
     DevR1cs d;
@@ -668,8 +715,10 @@ int cw_r1cs_check(cw_r1cs *r, const uint64_t *witness, int is_device_ptr, uint32
     uint4 *tmp = nullptr;
     if (!is_device_ptr) {
         CU(cudaMalloc((void **)&tmp, (size_t)batch * R.n_wires * 32));
-        CU(cudaMemcpy(tmp, witness, (size_t)batch * R.n_wires * 32, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy2D(tmp, (size_t)R.n_wires * 32, witness, (size_t)stride_elems * 32, (size_t)R.n_wires * 32, batch,
+                        cudaMemcpyHostToDevice));
         w_d = tmp;
+        stride_elems = R.n_wires;
     }
     unsigned long long *fb_d = nullptr;
     CU(cudaMalloc((void **)&fb_d, (size_t)batch * 8));
@@ -683,6 +732,7 @@ int cw_r1cs_check(cw_r1cs *r, const uint64_t *witness, int is_device_ptr, uint32
     rd.perm = d.perm;
     rd.n_constraints = (u32)R.n_constraints;
     rd.n_wires = (u32)R.n_wires;
+    rd.w_stride = stride_elems;
     // instance groups: enough blocks to fill the GPU, as many instances per block as that allows
     u32 row_blocks = (u32)std::min<uint64_t>((R.n_constraints + 255) / 256, 148 * 8);
     if (row_blocks == 0) row_blocks = 1;

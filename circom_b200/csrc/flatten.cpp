@@ -817,30 +817,32 @@ struct Lowerer {
         R.n_pub_out = (uint32_t)M.n_out;
         R.n_pub_in = 0;
         R.n_prv_in = (uint32_t)M.n_in;
-        std::vector<uint32_t> wslot(W);
-        size_t n_prov = pops.size() / 4;
-        std::vector<uint8_t> live(n_pre + n_prov, 0);
+        // ---- witness values live IN the slot store: slot i (i < W) is witness entry i, canonical ---------
+        // Each witness entry claims the slot of the op that produces its canonical value (so the tape
+        // writes the witness rows directly and no gather pass exists); a second entry with the same
+        // value, or a value only held in another representation, costs one move / conversion op.
         for (uint64_t i = 0; i < S; ++i)
             if (sig_vid[i] < 0) throw std::runtime_error("lowering: signal " + std::to_string(i) + " is never assigned");
+        std::vector<int64_t> claimed;  // provisional slot -> witness index
+        std::vector<uint32_t> wsrc(W);
+        auto grow = [&]() { claimed.resize(n_pre + pops.size() / 4, -1); };
+        grow();
         for (uint64_t i = 0; i < W; ++i) {
             int32_t v = sig_vid[T.witness2signal[i]];
-            if (vals[v].cid >= 0) {
-                // a signal that is a compile-time constant: materialise it once
-                uint32_t s = emit(CW_OP_COPY, const_operand(vals[v].cid, FC));
-                vals[v].cid = -1;
-                vals[v].slot[FC] = s;
-                live.push_back(0);
-                ++n_prov;
+            uint32_t src;
+            if (vals[v].cid >= 0) src = emit(CW_OP_COPY, const_operand(vals[v].cid, FC));  // constant signal
+            else src = need(v, FC);
+            grow();
+            if (claimed[src] >= 0) {  // value already is another witness entry: one move
+                src = emit(CW_OP_COPY, src);
+                grow();
             }
-            if (vals[v].slot[FC] == NO_SLOT && vals[v].slot[FM] == NO_SLOT) {
-                size_t before = pops.size() / 4;
-                need(v, FC);  // a deferred product that is a witness value: convert it now
-                for (size_t k = before; k < pops.size() / 4; ++k) { live.push_back(0); ++n_prov; }
-            }
-            if (vals[v].slot[FC] != NO_SLOT) wslot[i] = vals[v].slot[FC];
-            else wslot[i] = vals[v].slot[FM] | WSLOT_MONT;
-            live[wslot[i] & ~WSLOT_MONT] = 1;
+            claimed[src] = (int64_t)i;
+            wsrc[i] = src;
         }
+        size_t n_prov = pops.size() / 4;
+        std::vector<uint8_t> live(n_pre + n_prov, 0);
+        for (uint64_t i = 0; i < W; ++i) live[wsrc[i]] = 1;
         // dead-value elimination (reverse sweep; provisional order is topological)
         for (size_t i = n_prov; i-- > 0;) {
             uint32_t *o = &pops[i * 4];
@@ -852,7 +854,7 @@ struct Lowerer {
                 if (o[k] != NO_SLOT && !(o[k] & OPERAND_CONST)) live[o[k]] = 1;
             }
         }
-        // counting sort by (level, opcode)
+        // sort by (level, opcode)
         uint32_t max_level = 0;
         size_t n_live = 0;
         for (size_t i = 0; i < n_prov; ++i)
@@ -869,16 +871,27 @@ struct Lowerer {
             if (lx != ly) return lx < ly;
             return pops[x * 4] < pops[y * 4];
         });
+        // final slots: witness entries first (slot = witness index), other values after them in tape order
         std::vector<uint32_t> remap(n_pre + n_prov, NO_SLOT);
-        for (uint32_t i = 0; i < n_pre; ++i) remap[i] = i;
-        for (size_t r = 0; r < order.size(); ++r) remap[n_pre + order[r]] = n_pre + (uint32_t)r;
+        uint32_t next_tmp = (uint32_t)W;
+        for (uint32_t i = 0; i < n_pre; ++i) {
+            if (claimed[i] < 0) throw std::runtime_error("lowering: main input outside the witness");
+            remap[i] = (uint32_t)claimed[i];
+        }
+        for (size_t r = 0; r < order.size(); ++r) {
+            uint32_t p = n_pre + order[r];
+            if (claimed[p] >= 0) remap[p] = (uint32_t)claimed[p];
+            else if (!is_assert_op(pops[(size_t)order[r] * 4])) remap[p] = next_tmp++;
+        }
+        if (next_tmp >= (1u << 24)) throw std::runtime_error("circuit too large for the packed tape word (2^24 slots)");
         T.ops.resize(n_live * 4);
         T.level_start.assign(max_level + 1, 0);
         T.n_mul_ops = 0;
         for (size_t r = 0; r < order.size(); ++r) {
             const uint32_t *o = &pops[(size_t)order[r] * 4];
             uint32_t *d = &T.ops[r * 4];
-            d[0] = o[0];
+            uint32_t dst = is_assert_op(o[0]) ? 0u : remap[n_pre + order[r]];
+            d[0] = o[0] | (dst << 8);  // opcode in bits 0-7, destination slot in bits 8-31
             for (int k = 1; k <= 3; ++k) {
                 if (k == 3 && c_is_immediate(o[0])) d[k] = o[k];  // immediate: IR assert number / bit-field spec
                 else if (o[k] == NO_SLOT) d[k] = OPERAND_CONST;  // unused operand: constant 0 (never read for its value)
@@ -903,11 +916,14 @@ struct Lowerer {
             T.max_level_width = widest;
         }
         T.witness_slot.resize(W);
-        for (uint64_t i = 0; i < W; ++i) T.witness_slot[i] = remap[wslot[i] & ~WSLOT_MONT] | (wslot[i] & WSLOT_MONT);
+        for (uint64_t i = 0; i < W; ++i) T.witness_slot[i] = (uint32_t)i;
+        T.input_slot.resize(M.n_in);
+        for (uint32_t i = 0; i < M.n_in; ++i) T.input_slot[i] = remap[1 + i];
+        if (remap[0] != 0) throw std::runtime_error("lowering: constant-one signal is not witness entry 0");
         T.consts = consts;
         if (T.consts.empty()) T.consts.push_back(u256_from_u64(0));
         T.n_pre = n_pre;
-        T.n_slots = n_pre + (uint32_t)n_live;
+        T.n_slots = next_tmp;
         T.n_ir_ops = n_ir_ops;
         T.n_conv_ops = n_conv;
         T.n_asserts = n_asserts;

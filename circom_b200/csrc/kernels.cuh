@@ -55,9 +55,9 @@ struct TapeDev {
     const uint4 *ops;          // {opcode, a, b, c}
     const u32 *level_start;    // n_levels + 1
     const uint4 *consts;       // 2 per constant
+    const u32 *input_slot;     // slot of main input k
     u32 n_levels;
     u32 n_slots;
-    u32 n_pre;
     u32 n_inputs;
 };
 
@@ -78,7 +78,7 @@ __global__ void stage_inputs_kernel(TapeDev tp, const uint4 *__restrict__ inputs
             v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
             v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
         }
-        store_slot(v, base, k, bt_log2, li);
+        store_slot(v, base, k == 0 ? 0u : __ldg(&tp.input_slot[k - 1]), bt_log2, li);
     }
 }
 
@@ -102,41 +102,60 @@ __global__ void __launch_bounds__(1024) tape_exec_kernel(TapeDev tp, uint4 *__re
         for (u32 w = threadIdx.x; w < n; w += blockDim.x) {
             const u32 oi = lb + (w >> bt_log2);
             const u32 li = w & bt_mask;
-            const uint4 op = __ldg(&tp.ops[oi]);
-            u32 a[8], b[8], r[8];
-            load_operand(a, op.y, base, tp.consts, bt_log2, li);
-            load_operand(b, op.z, base, tp.consts, bt_log2, li);
+            const uint4 opw = __ldg(&tp.ops[oi]);
+            const u32 opcode = opw.x & 0xFFu, dst = opw.x >> 8;
             const u32 inst = (tile << bt_log2) + li;
-            if (op.x == OP_SELECT) {
-                u32 c[8];
-                load_operand(c, op.w, base, tp.consts, bt_log2, li);
-                bool t = !u256_is_zero(c);
+            u32 r[8];
+            if (opcode == OP_BITS && (opw.w >> 16) <= 32u && !(opw.y & 0x80000000u)) {
+                // narrow bit-field of a slot value: fetch only the one or two 32-bit words that hold it
+                const u32 k = opw.w & 0xFFFFu, m = opw.w >> 16, wd = k >> 5, sh = k & 31u;
+                const u32 *words = reinterpret_cast<const u32 *>(base);
+                const size_t e0 = ((((size_t)opw.y << (bt_log2 + 1)) + ((size_t)(wd >> 2) << bt_log2) + li) << 2) + (wd & 3u);
+                const u32 lo = words[e0];
+                u32 hi = 0;
+                if (sh + m > 32u && wd < 7u) {
+                    const u32 w1 = wd + 1u;
+                    hi = words[((((size_t)opw.y << (bt_log2 + 1)) + ((size_t)(w1 >> 2) << bt_log2) + li) << 2) + (w1 & 3u)];
+                }
+                r[0] = __funnelshift_r(lo, hi, sh) & (m >= 32u ? 0xFFFFFFFFu : ((1u << m) - 1u));
 #pragma unroll
-                for (int i = 0; i < 8; ++i) r[i] = t ? a[i] : b[i];
-            } else if (op.x == OP_ASSERT_EQ || op.x == OP_ASSERT || op.x == OP_ASSERT_BOOL || op.x == OP_ASSERT_FITS) {
-                bool ok = op.x == OP_ASSERT_EQ     ? u256_eq(a, b)
-                          : op.x == OP_ASSERT      ? !u256_is_zero(a)
-                          : op.x == OP_ASSERT_BOOL ? (u256_is_zero(a) || u256_eq(a, b))
-                                                   : (u256_bitlen_dev(a) <= b[0]);
-                if (!ok && inst < batch) atomicMin(&first_assert[inst], op.w);
-                continue;  // asserts have no destination value
+                for (int i = 1; i < 8; ++i) r[i] = 0;
             } else {
-                int e = 0;
-                fr_exec(op.x, r, a, b, op.w, P, e);
-                if (e && inst < batch) err[inst] = 1;
+                u32 a[8], b[8];
+                load_operand(a, opw.y, base, tp.consts, bt_log2, li);
+                load_operand(b, opw.z, base, tp.consts, bt_log2, li);
+                if (opcode == OP_SELECT) {
+                    u32 c[8];
+                    load_operand(c, opw.w, base, tp.consts, bt_log2, li);
+                    bool t = !u256_is_zero(c);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) r[i] = t ? a[i] : b[i];
+                } else if (opcode == OP_ASSERT_EQ || opcode == OP_ASSERT || opcode == OP_ASSERT_BOOL ||
+                           opcode == OP_ASSERT_FITS) {
+                    bool ok = opcode == OP_ASSERT_EQ     ? u256_eq(a, b)
+                              : opcode == OP_ASSERT      ? !u256_is_zero(a)
+                              : opcode == OP_ASSERT_BOOL ? (u256_is_zero(a) || u256_eq(a, b))
+                                                         : (u256_bitlen_dev(a) <= b[0]);
+                    if (!ok && inst < batch) atomicMin(&first_assert[inst], opw.w);
+                    continue;  // asserts have no destination value
+                } else {
+                    int e = 0;
+                    fr_exec(opcode, r, a, b, opw.w, P, e);
+                    if (e && inst < batch) err[inst] = 1;
+                }
             }
-            store_slot(r, base, tp.n_pre + oi, bt_log2, li);
+            store_slot(r, base, dst, bt_log2, li);
         }
         lb = le;
         __syncthreads();
     }
 }
 
-// ---- witness gather: out[inst][w][8 u32] canonical (getWitness + Fr_toLongNormal, main.cpp:328-332)
-template <int PRIME>
-__global__ void witness_gather_kernel(const uint4 *__restrict__ slots, const u32 *__restrict__ witness_slot,
-                                      uint4 *__restrict__ out, u32 n_slots, u32 n_witness, u32 batch, u32 bt_log2) {
-    const FrParams &P = c_fr[PRIME];
+// ---- witness compaction for tile layouts with BT > 1: out[inst][w] = slot w (witness entries are the
+// first n_witness slots, already canonical).  With BT = 1 the witness rows are contiguous inside the slot
+// store and are read in place (strided) or copied with cudaMemcpy2D.
+__global__ void witness_compact_kernel(const uint4 *__restrict__ slots, uint4 *__restrict__ out, u32 n_slots,
+                                       u32 n_witness, u32 batch, u32 bt_log2) {
     const u32 bt = 1u << bt_log2;
     const u32 tiles = (batch + bt - 1) >> bt_log2;
     size_t total = (size_t)tiles * n_witness * bt;
@@ -148,14 +167,8 @@ __global__ void witness_gather_kernel(const uint4 *__restrict__ slots, const u32
         u32 inst = (tile << bt_log2) + li;
         if (inst >= batch) continue;
         const uint4 *base = slots + (((size_t)tile * n_slots) << (bt_log2 + 1));
-        u32 ws = witness_slot[wi];
         u32 v[8];
-        load_slot(v, base, ws & 0x7FFFFFFFu, bt_log2, li);
-        if (ws & 0x80000000u) {
-            u32 t[8];
-            fr_from_mont(t, v, P);
-            u256_set(v, t);
-        }
+        load_slot(v, base, wi, bt_log2, li);
         uint4 *dst = out + ((size_t)inst * n_witness + wi) * 2;
         dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
         dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
@@ -188,6 +201,7 @@ struct R1csDev {
     u32 n_constraints;
     u32 n_wires;
     u32 inst_per_block;
+    unsigned long long w_stride;  // distance between two instances' witness rows, in 32-byte elements
 };
 
 template <int PRIME>
@@ -238,7 +252,7 @@ __global__ void __launch_bounds__(256) r1cs_check_kernel(R1csDev R, const uint4 
         const unsigned long long p0 = R.row_ptr[3 * (size_t)row], p1 = R.row_ptr[3 * (size_t)row + 1],
                                  p2 = R.row_ptr[3 * (size_t)row + 2], p3 = R.row_ptr[3 * (size_t)row + 3];
         for (u32 inst = i0; inst < i1; ++inst) {
-            const uint4 *w = witness + (size_t)inst * R.n_wires * 2;
+            const uint4 *w = witness + (size_t)inst * R.w_stride * 2;
             u32 a[8], b[8], c[8];
             r1cs_lc<PRIME>(a, R, p0, p1, w, P);
             r1cs_lc<PRIME>(b, R, p1, p2, w, P);

@@ -41,11 +41,12 @@ struct Tape {
     uint64_t n_signals = 0, n_witness = 0, n_inputs = 0, n_outputs = 0, n_components = 0;
     uint64_t n_ir_ops = 0, n_mul_ops = 0, n_conv_ops = 0, max_level_width = 0, n_asserts = 0;
     uint32_t n_pre = 0;    // slot 0 = constant one, slots 1..n_inputs = main inputs
-    uint32_t n_slots = 0;  // n_pre + n_tape_ops (dst of tape op i is slot n_pre + i)
-    std::vector<uint32_t> ops;          // 4 words per op: opcode | a | b | c
+    uint32_t n_slots = 0;  // witness entries [0, n_witness) then the other values
+    std::vector<uint32_t> ops;          // 4 words per op: opcode | dst << 8, a, b, c
     std::vector<uint32_t> level_start;  // n_levels + 1
     std::vector<U256> consts;           // raw limb patterns (already in the form the consumer needs)
-    std::vector<uint32_t> witness_slot; // per witness entry
+    std::vector<uint32_t> witness_slot; // per witness entry (identity: witness entry i lives in slot i)
+    std::vector<uint32_t> input_slot;   // slot of main input i
     std::vector<uint64_t> witness2signal; // witness2SignalList (calcwit.hpp:54-56)
     std::vector<InputInfo> inputs;
     std::vector<HashEntry> hashmap;

@@ -69,6 +69,7 @@ def _load() -> ctypes.CDLL:
         "cw_batch_status": (c_int, [P, c_void_p]),
         "cw_batch_get_witness": (c_int, [P, c_void_p]),
         "cw_batch_witness_device": (c_int, [P, POINTER(c_void_p)]),
+        "cw_batch_witness_strided": (c_int, [P, POINTER(c_void_p), POINTER(c_uint64)]),
         "cw_batch_stream": (c_void_p, [P]),
         "cw_batch_last_ms": (c_int, [P, POINTER(c_float), POINTER(c_float)]),
         "cw_batch_write_wtns": (c_int, [P, c_uint32, c_char_p]),
@@ -79,6 +80,7 @@ def _load() -> ctypes.CDLL:
         "cw_r1cs_info": (c_int, [P, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint64), POINTER(c_int)]),
         "cw_r1cs_destroy": (None, [P]),
         "cw_r1cs_check": (c_int, [P, c_void_p, c_int, c_uint32, c_int, c_void_p, POINTER(c_float)]),
+        "cw_r1cs_check_strided": (c_int, [P, c_void_p, c_uint64, c_int, c_uint32, c_int, c_void_p, POINTER(c_float)]),
         "cw_fr_batch_op": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int]),
         "cw_fr_mul_bench": (c_int, [c_int, c_size_t, c_int, c_int, POINTER(c_float)]),
     }

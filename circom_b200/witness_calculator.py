@@ -257,6 +257,12 @@ class Batch:
         check(lib.cw_batch_witness_device(self._h, ctypes.byref(p)))
         return p.value
 
+    def witness_strided(self):
+        """(device pointer, stride in 32-byte elements): the witness rows where the tape wrote them"""
+        p, st = ctypes.c_void_p(), ctypes.c_uint64()
+        check(lib.cw_batch_witness_strided(self._h, ctypes.byref(p), ctypes.byref(st)))
+        return p.value, st.value
+
     def stream(self) -> int:
         return lib.cw_batch_stream(self._h) or 0
 
@@ -292,16 +298,24 @@ class R1cs:
         if h:
             lib.cw_r1cs_destroy(h)
 
+    def check_batch(self, b: "Batch", device: int = 0):
+        """check the witnesses of a Batch where they lie (no copy)"""
+        ptr, stride = b.witness_strided()
+        return self.check(None, batch=b.batch, device=device, device_ptr=ptr, stride=stride)
+
     def write(self, path: str, n_pub_out: int = 0, n_pub_in: int = 0, n_prv_in: int = 0) -> None:
         check(lib.cw_r1cs_write(self._h, path.encode(), n_pub_out, n_pub_in, n_prv_in))
 
-    def check(self, witness, batch: Optional[int] = None, device: int = 0, device_ptr: Optional[int] = None):
-        """A.w o B.w == C.w for each instance.  Returns (first_bad[batch] int64, -1 = satisfied; kernel ms)."""
+    def check(self, witness, batch: Optional[int] = None, device: int = 0, device_ptr: Optional[int] = None,
+              stride: Optional[int] = None):
+        """A.w o B.w == C.w for each instance.  Returns (first_bad[batch] int64, -1 = satisfied; kernel ms).
+        `stride` (32-byte elements between witness rows) lets the check read a Batch's slot store in place."""
         ms = ctypes.c_float()
         if device_ptr is not None:
             assert batch is not None
             fb = np.zeros(batch, dtype=np.int64)
-            check(lib.cw_r1cs_check(self._h, ctypes.c_void_p(device_ptr), 1, batch, device, fb.ctypes.data, ctypes.byref(ms)))
+            check(lib.cw_r1cs_check_strided(self._h, ctypes.c_void_p(device_ptr), stride or self.n_wires, 1, batch, device,
+                                            fb.ctypes.data, ctypes.byref(ms)))
             return fb, ms.value
         w = np.ascontiguousarray(witness, dtype=np.uint64)
         batch = w.size // (self.n_wires * 4)

@@ -133,6 +133,9 @@ int cw_batch_status(cw_batch *b, int32_t *status);
 int cw_batch_get_witness(cw_batch *b, uint64_t *out);
 /* device pointer of the same array (valid until the next run / destroy) */
 int cw_batch_witness_device(cw_batch *b, const uint64_t **dptr);
+/* zero-copy view: witness row i starts at dptr + i*stride_elems*4 uint64 (the tape writes witness entries into
+ * the first n_witness slots of each instance's slot store; stride_elems = slots per instance) */
+int cw_batch_witness_strided(cw_batch *b, const uint64_t **dptr, uint64_t *stride_elems);
 /* CUDA stream of the batch (cudaStream_t as void*) and last device time of run+gather in ms */
 void *cw_batch_stream(cw_batch *b);
 int cw_batch_last_ms(cw_batch *b, float *exec_ms, float *gather_ms);
@@ -155,6 +158,10 @@ void cw_r1cs_destroy(cw_r1cs *r);
  * reference has no evaluator (constraint_writers/src/r1cs_reader.rs has no caller). */
 int cw_r1cs_check(cw_r1cs *r, const uint64_t *witness, int is_device_ptr, uint32_t batch, int device,
                   int64_t *first_bad, float *kernel_ms);
+
+/* same, for witness rows `stride_elems` 32-byte elements apart (stride_elems >= n_wires) */
+int cw_r1cs_check_strided(cw_r1cs *r, const uint64_t *witness, uint64_t stride_elems, int is_device_ptr, uint32_t batch,
+                          int device, int64_t *first_bad, float *kernel_ms);
 
 /* ---- field library, batched (parity tests of the device Fr_* equivalents, fr.hpp:28-70) ------ */
 /* r[i] = op(a[i], b[i], c[i]) for i < n on `device`; canonical in / canonical out; b, c may be NULL */

@@ -62,7 +62,8 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
         std::fill(slots.begin(), slots.end(), 0xDEADBEEFu);  // poison: reads before writes show up
         u32 one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
         memcpy(&slots[0], one, 32);
-        memcpy(&slots[8], inputs + (size_t)inst * t.n_inputs * 4, t.n_inputs * 32);
+        for (uint64_t k = 0; k < t.n_inputs; ++k)
+            memcpy(&slots[(size_t)t.input_slot[k] * 8], inputs + ((size_t)inst * t.n_inputs + k) * 4, 32);
         uint32_t first_assert = 0xFFFFFFFFu;
         int err = 0;
         auto operand = [&](u32 o, u32 *v) {
@@ -71,7 +72,9 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
         };
         // level order == tape order
         for (size_t i = 0; i < n_ops; ++i) {
-            const uint32_t *op = &t.ops[i * 4];
+            const uint32_t *opw = &t.ops[i * 4];
+            const uint32_t op[4] = {opw[0] & 0xFFu, opw[1], opw[2], opw[3]};
+            const uint32_t dst = opw[0] >> 8;
             u32 a[8], b[8], r[8];
             operand(op[1], a);
             operand(op[2], b);
@@ -87,18 +90,10 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
             } else {
                 fr_exec(op[0], r, a, b, op[3], P, err);
             }
-            memcpy(&slots[((size_t)t.n_pre + i) * 8], r, 32);
+            memcpy(&slots[(size_t)dst * 8], r, 32);
         }
         for (uint64_t w = 0; w < t.n_witness; ++w) {
-            u32 ws = t.witness_slot[w];
-            u32 v[8];
-            memcpy(v, &slots[(size_t)(ws & 0x7FFFFFFFu) * 8], 32);
-            if (ws & WSLOT_MONT) {
-                u32 x[8];
-                fr_from_mont(x, v, P);
-                memcpy(v, x, 32);
-            }
-            memcpy(witness + ((size_t)inst * t.n_witness + w) * 4, v, 32);
+            memcpy(witness + ((size_t)inst * t.n_witness + w) * 4, &slots[(size_t)w * 8], 32);  // slot w IS witness entry w
         }
         status[inst] = err ? -1 : (first_assert == 0xFFFFFFFFu ? 0 : (int32_t)(first_assert + 1));
     }
@@ -127,12 +122,25 @@ int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
         g_err = e.what();
         return -1;
     }
-    std::vector<uint32_t> lvl(t.n_slots, 0);
+    std::vector<uint32_t> lvl(t.n_slots, 0), oplvl(t.n_tape_ops(), 0), writes(t.n_slots, 0);
     for (size_t l = 0; l < t.n_levels(); ++l)
-        for (uint32_t i = t.level_start[l]; i < t.level_start[l + 1]; ++i) lvl[t.n_pre + i] = (uint32_t)l + 1;
+        for (uint32_t i = t.level_start[l]; i < t.level_start[l + 1]; ++i) {
+            oplvl[i] = (uint32_t)l + 1;
+            uint32_t opc = t.ops[(size_t)i * 4] & 0xFFu, dst = t.ops[(size_t)i * 4] >> 8;
+            bool is_assert = opc == OP_ASSERT || opc == OP_ASSERT_EQ || opc == OP_ASSERT_BOOL || opc == OP_ASSERT_FITS;
+            if (is_assert) continue;
+            if (dst >= t.n_slots) { g_err = "destination out of range"; return -6; }
+            if (++writes[dst] > 1) { g_err = "slot written twice"; return -7; }
+            lvl[dst] = (uint32_t)l + 1;
+        }
+    writes[0]++;
+    for (uint64_t k = 0; k < t.n_inputs; ++k) writes[t.input_slot[k]]++;
+    for (uint64_t w = 0; w < t.n_witness; ++w)
+        if (writes[w] != 1) { g_err = "witness slot not written exactly once"; return -8; }
     if (t.n_levels() && t.level_start[t.n_levels()] != t.n_tape_ops()) { g_err = "level table does not cover the tape"; return -2; }
     for (size_t i = 0; i < t.n_tape_ops(); ++i) {
-        const uint32_t *op = &t.ops[i * 4];
+        const uint32_t *opw = &t.ops[i * 4];
+        const uint32_t op[4] = {opw[0] & 0xFFu, opw[1], opw[2], opw[3]};
         bool c_imm = op[0] == OP_ASSERT || op[0] == OP_ASSERT_EQ || op[0] == OP_ASSERT_BOOL || op[0] == OP_BITS || op[0] == OP_BITSIP || op[0] == OP_ASSERT_FITS;
         for (int k = 1; k <= 3; ++k) {
             if (k == 3 && c_imm) break;
@@ -141,7 +149,7 @@ int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
                 continue;
             }
             if (op[k] >= t.n_slots) { g_err = "slot out of range"; return -4; }
-            if (lvl[op[k]] >= lvl[t.n_pre + i]) { g_err = "operand not produced in an earlier level"; return -5; }
+            if (lvl[op[k]] >= oplvl[i]) { g_err = "operand not produced in an earlier level"; return -5; }
         }
     }
     return 0;

@@ -141,3 +141,28 @@ def test_assert_and_r1cs_violation_detected():
     # the same check straight from device memory
     fb2, _ = R1cs(c).check(None, batch=3, device_ptr=b.witness_device_ptr())
     assert fb2.tolist() == [-1, 0, -1]
+
+
+def test_r1cs_check_reads_witness_in_place():
+    """the tape writes witness entries into the first slots of each instance: the R1CS check and the
+    host copy read them there (strided), the dense device copy is made only on request"""
+    d = CircuitDesc("bn128")
+    d.set_main(C.less_than(d, 16))
+    c = Circuit(d)
+    rng = random.Random(8)
+    ins = [{"in": [rng.randrange(65536), rng.randrange(65536)]} for _ in range(50)]
+    b = Batch(c, len(ins))
+    b.set_inputs(flat_inputs(d, ins))
+    b.run()
+    r = R1cs(c)
+    fb1, _ = r.check_batch(b)
+    ptr, stride = b.witness_strided()
+    assert stride == c.stats["n_slots"] and stride >= c.n_witness
+    wit = b.witness()
+    fb2, _ = r.check(wit)
+    fb3, _ = r.check(None, batch=len(ins), device_ptr=b.witness_device_ptr())
+    assert (fb1 == -1).all() and (fb2 == -1).all() and (fb3 == -1).all()
+    w2s = c.witness2signal().astype(np.int64)
+    for i, inp in enumerate(ins):
+        exp = evaluate(d, inp)
+        assert limbs_to_ints(wit[i]) == [exp[k] for k in w2s]

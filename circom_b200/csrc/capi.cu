@@ -86,7 +86,8 @@ struct DevR1cs {
     u32 *col = nullptr, *coef = nullptr;
     uint4 *dictM = nullptr;
     unsigned short *kind = nullptr;
-    u32 *perm = nullptr;
+    u32 *perm = nullptr, *bool_wire = nullptr, *bool_row = nullptr;
+    u32 n_general = 0, n_bool = 0;
 };
 
 template <class T>
@@ -644,6 +645,8 @@ void cw_r1cs_destroy(cw_r1cs *r) {
         cudaFree(kv.second.dictM);
         cudaFree(kv.second.kind);
         cudaFree(kv.second.perm);
+        cudaFree(kv.second.bool_wire);
+        cudaFree(kv.second.bool_row);
     }
     delete r;
 }
@@ -698,9 +701,31 @@ int cw_r1cs_check_strided(cw_r1cs *r, const uint64_t *witness, uint64_t stride_e
                 uint64_t total = std::min<uint64_t>(na + nb + nc, 0xFFFF);
                 sig[row] = (total << 48) | ((std::min<uint64_t>(na, 255)) << 40) | ((std::min<uint64_t>(nb, 255)) << 32) | (h & 0xFFFFFFFFull);
             }
-            std::vector<u32> perm(m);
-            for (size_t i = 0; i < m; ++i) perm[i] = (u32)i;
+            // boolean rows  x * (x - 1) = 0  (A = {x:1}, B = {x:1, one:-1}, C = {} or A/B swapped) are the bulk
+            // of circom circuits (every Num2Bits / range-check bit): they only need `w[x] in {0,1}` and
+            // get their own memory-bound kernel; the remaining rows go through the general kernel.
+            std::vector<u32> perm, bool_wire, bool_row;
+            auto is_unit = [&](uint64_t k, int want) { return (kind[R.coef[k]] & 0xFF) == want && (kind[R.coef[k]] >> 8) == 0; };
+            for (size_t row = 0; row < m; ++row) {
+                uint64_t p0 = R.row_ptr[3 * row], p1 = R.row_ptr[3 * row + 1], p2 = R.row_ptr[3 * row + 2], p3 = R.row_ptr[3 * row + 3];
+                bool is_bool = false;
+                u32 wire = 0;
+                if (p3 == p2 && (p1 - p0) + (p2 - p1) == 3) {
+                    uint64_t s0 = (p1 - p0 == 1) ? p0 : p1, l0 = (p1 - p0 == 1) ? p1 : p0;  // single-term block / two-term block
+                    // two-term block is sorted by wire: {one: -1, x: +1}
+                    if (is_unit(s0, 1) && R.col[s0] != 0 && R.col[l0] == 0 && is_unit(l0, 2) && R.col[l0 + 1] == R.col[s0] && is_unit(l0 + 1, 1)) {
+                        is_bool = true;
+                        wire = R.col[s0];
+                    }
+                }
+                if (is_bool) { bool_wire.push_back(wire); bool_row.push_back((u32)row); }
+                else perm.push_back((u32)row);
+            }
             std::stable_sort(perm.begin(), perm.end(), [&](u32 x, u32 y) { return sig[x] > sig[y]; });
+            d.n_general = (u32)perm.size();
+            d.n_bool = (u32)bool_wire.size();
+            if ((rc = upload(&d.bool_wire, bool_wire.data(), bool_wire.size() * 4))) return rc;
+            if ((rc = upload(&d.bool_row, bool_row.data(), bool_row.size() * 4))) return rc;
             if ((rc = upload(&d.row_ptr, R.row_ptr.data(), R.row_ptr.size() * 8))) return rc;
             if ((rc = upload(&d.col, R.col.data(), R.col.size() * 4))) return rc;
             if ((rc = upload(&d.coef, R.coef.data(), R.coef.size() * 4))) return rc;
@@ -730,11 +755,11 @@ int cw_r1cs_check_strided(cw_r1cs *r, const uint64_t *witness, uint64_t stride_e
     rd.dictM = d.dictM;
     rd.kind = d.kind;
     rd.perm = d.perm;
-    rd.n_constraints = (u32)R.n_constraints;
+    rd.n_constraints = d.n_general;  // rows visited through perm
     rd.n_wires = (u32)R.n_wires;
     rd.w_stride = stride_elems;
     // instance groups: enough blocks to fill the GPU, as many instances per block as that allows
-    u32 row_blocks = (u32)std::min<uint64_t>((R.n_constraints + 255) / 256, 148 * 8);
+    u32 row_blocks = (u32)std::min<uint64_t>(((uint64_t)d.n_general + 255) / 256, 148 * 8);
     if (row_blocks == 0) row_blocks = 1;
     u32 ipb = 1;
     while (ipb < 8 && (uint64_t)row_blocks * ((batch + 2 * ipb - 1) / (2 * ipb)) >= 148ull * 16) ipb *= 2;
@@ -745,8 +770,14 @@ int cw_r1cs_check_strided(cw_r1cs *r, const uint64_t *witness, uint64_t stride_e
     CU(cudaEventCreate(&e1));
     dim3 grid(row_blocks, std::min<u32>((batch + ipb - 1) / ipb, 65535u));
     CU(cudaEventRecord(e0));
-    if (R.prime_id == 0) r1cs_check_kernel<0><<<grid, 256>>>(rd, w_d, batch, fb_d);
-    else r1cs_check_kernel<1><<<grid, 256>>>(rd, w_d, batch, fb_d);
+    if (d.n_general) {
+        if (R.prime_id == 0) r1cs_check_kernel<0><<<grid, 256>>>(rd, w_d, batch, fb_d);
+        else r1cs_check_kernel<1><<<grid, 256>>>(rd, w_d, batch, fb_d);
+    }
+    if (d.n_bool) {
+        dim3 bgrid((u32)std::min<uint64_t>(((uint64_t)d.n_bool + 255) / 256, 148 * 8), std::min<u32>(batch, 65535u));
+        r1cs_bool_kernel<<<bgrid, 256>>>(d.bool_wire, d.bool_row, d.n_bool, w_d, stride_elems, batch, fb_d);
+    }
     CU(cudaEventRecord(e1));
     CU(cudaGetLastError());
     std::vector<unsigned long long> fb(batch);

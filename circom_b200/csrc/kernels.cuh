@@ -274,6 +274,24 @@ __global__ void __launch_bounds__(256) r1cs_check_kernel(R1csDev R, const uint4 
     }
 }
 
+// boolean rows x*(x-1) = 0: the witness value must be 0 or 1.  Thread = (boolean row, instance); the
+// wires of consecutive boolean rows are consecutive witness entries (the bits of one decomposition), so
+// a warp reads a contiguous 1 KB run of the instance's witness row.  Purely memory-bound (32 B per row).
+__global__ void __launch_bounds__(256) r1cs_bool_kernel(const u32 *__restrict__ wire, const u32 *__restrict__ rows,
+                                                        u32 n_bool, const uint4 *__restrict__ witness,
+                                                        unsigned long long w_stride, u32 batch,
+                                                        unsigned long long *__restrict__ first_bad) {
+    for (u32 inst = blockIdx.y; inst < batch; inst += gridDim.y) {
+        const uint4 *w = witness + (size_t)inst * w_stride * 2;
+        for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n_bool; k += gridDim.x * blockDim.x) {
+            const u32 c = __ldg(&wire[k]);
+            const uint4 lo = w[2 * (size_t)c], hi = w[2 * (size_t)c + 1];
+            const u32 rest = lo.y | lo.z | lo.w | hi.x | hi.y | hi.z | hi.w;
+            if (rest || lo.x > 1u) atomicMin(&first_bad[inst], (unsigned long long)__ldg(&rows[k]));
+        }
+    }
+}
+
 // ---- batched single field op (parity tests of the device Fr_* equivalents) ---------------------
 // canonical in / canonical out; the kernel applies the same representation rules as the lowering
 template <int PRIME>

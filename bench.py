@@ -134,6 +134,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(workload_name: str, batch: int, kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture, if it was taken on this configuration"""
+    try:
+        j = json.load(open(os.path.join(ROOT, "profiles", "r01b_traffic.json")))
+        if j["workload"] == workload_name and j["batch_per_gpu"] == batch:
+            return int(j[kernel]["dram_bytes_read"] + j[kernel]["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -360,7 +371,8 @@ def main():
         "gpu_launches": 2 * args.steps,   # stage_inputs_kernel + tape_exec_kernel per step
         "clocks": clocks,
         "roofline": {"kernel": "tape_exec_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": ncu_traffic(desc.name, batch, "tape_exec_kernel"),
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_witness": b_wit,
                      "operand_traffic_upper_bound_GBps": batch * st["n_tape_ops"] * 96 / (exec_per_launch_ms / 1e3) / 1e9},
     }

@@ -184,14 +184,83 @@ CW_HD void fr_mont_mul_c(u32 *r, const u32 *a, const u32 *b, const FrParams &P) 
 }
 
 #if defined(__CUDA_ARCH__)
-// PTX carry-chain version: operand-scanning CIOS with mad.lo.cc / madc.hi.cc chains on
-// the integer (IMAD) pipe; even/odd columns are accumulated separately so that each chain
-// is a pure carry chain (no 64-bit adds).  Same result as fr_mont_mul_c.
-__device__ __forceinline__ void fr_mont_mul_ptx(u32 *r, const u32 *a, const u32 *b, const FrParams &P);
+// PTX carry-chain CIOS on the integer (IMAD) pipe: per outer iteration the 8 low halves and the 8 high
+// halves of a*b[i] are accumulated as two pure carry chains (mad.lo.cc / madc.lo.cc, mad.hi.cc /
+// madc.hi.cc), likewise for m*q, then the accumulator moves down one limb.  39 integer instructions per
+// iteration, 8 iterations, one conditional subtraction.  Same result as fr_mont_mul_c (GPU parity tests
+// compare both against the oracle; CW_MONT_C selects the portable form).
+__device__ __forceinline__ void fr_mont_step(u32 *t, const u32 *a, u32 bi, const FrParams &P) {
+    u32 m;
+    asm("{\n\t"
+        "mad.lo.cc.u32   %0, %11, %19, %0;\n\t"
+        "madc.lo.cc.u32  %1, %12, %19, %1;\n\t"
+        "madc.lo.cc.u32  %2, %13, %19, %2;\n\t"
+        "madc.lo.cc.u32  %3, %14, %19, %3;\n\t"
+        "madc.lo.cc.u32  %4, %15, %19, %4;\n\t"
+        "madc.lo.cc.u32  %5, %16, %19, %5;\n\t"
+        "madc.lo.cc.u32  %6, %17, %19, %6;\n\t"
+        "madc.lo.cc.u32  %7, %18, %19, %7;\n\t"
+        "addc.cc.u32     %8, %8, 0;\n\t"
+        "addc.u32        %9, 0, 0;\n\t"
+        "mad.hi.cc.u32   %1, %11, %19, %1;\n\t"
+        "madc.hi.cc.u32  %2, %12, %19, %2;\n\t"
+        "madc.hi.cc.u32  %3, %13, %19, %3;\n\t"
+        "madc.hi.cc.u32  %4, %14, %19, %4;\n\t"
+        "madc.hi.cc.u32  %5, %15, %19, %5;\n\t"
+        "madc.hi.cc.u32  %6, %16, %19, %6;\n\t"
+        "madc.hi.cc.u32  %7, %17, %19, %7;\n\t"
+        "madc.hi.cc.u32  %8, %18, %19, %8;\n\t"
+        "addc.u32        %9, %9, 0;\n\t"
+        "mul.lo.u32      %10, %0, %28;\n\t"
+        "mad.lo.cc.u32   %0, %10, %20, %0;\n\t"
+        "madc.lo.cc.u32  %1, %10, %21, %1;\n\t"
+        "madc.lo.cc.u32  %2, %10, %22, %2;\n\t"
+        "madc.lo.cc.u32  %3, %10, %23, %3;\n\t"
+        "madc.lo.cc.u32  %4, %10, %24, %4;\n\t"
+        "madc.lo.cc.u32  %5, %10, %25, %5;\n\t"
+        "madc.lo.cc.u32  %6, %10, %26, %6;\n\t"
+        "madc.lo.cc.u32  %7, %10, %27, %7;\n\t"
+        "addc.cc.u32     %8, %8, 0;\n\t"
+        "addc.u32        %9, %9, 0;\n\t"
+        "mad.hi.cc.u32   %1, %10, %20, %1;\n\t"
+        "madc.hi.cc.u32  %2, %10, %21, %2;\n\t"
+        "madc.hi.cc.u32  %3, %10, %22, %3;\n\t"
+        "madc.hi.cc.u32  %4, %10, %23, %4;\n\t"
+        "madc.hi.cc.u32  %5, %10, %24, %5;\n\t"
+        "madc.hi.cc.u32  %6, %10, %25, %6;\n\t"
+        "madc.hi.cc.u32  %7, %10, %26, %7;\n\t"
+        "madc.hi.cc.u32  %8, %10, %27, %8;\n\t"
+        "addc.u32        %9, %9, 0;\n\t"
+        "}"
+        : "+r"(t[0]), "+r"(t[1]), "+r"(t[2]), "+r"(t[3]), "+r"(t[4]), "+r"(t[5]), "+r"(t[6]), "+r"(t[7]), "+r"(t[8]),
+          "+r"(t[9]), "=&r"(m)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(bi),
+          "r"(P.q[0]), "r"(P.q[1]), "r"(P.q[2]), "r"(P.q[3]), "r"(P.q[4]), "r"(P.q[5]), "r"(P.q[6]), "r"(P.q[7]),
+          "r"(P.np32));
+    // t[0] is now zero: move the accumulator down one limb
+#pragma unroll
+    for (int j = 0; j < 9; ++j) t[j] = t[j + 1];
+    t[9] = 0;
+}
+__device__ __forceinline__ void fr_mont_mul_ptx(u32 *r, const u32 *a, const u32 *b, const FrParams &P) {
+    u32 t[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) t[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) fr_mont_step(t, a, b[i], P);
+    u32 d[8];
+    u32 br = u256_sub(d, t, P.q);  // result < 2q < 2^256 (t[8] == 0)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = br ? t[i] : d[i];
+}
 #endif
 
 CW_HD void fr_mont_mul(u32 *r, const u32 *a, const u32 *b, const FrParams &P) {
+#if defined(__CUDA_ARCH__) && !defined(CW_MONT_C)
+    fr_mont_mul_ptx(r, a, b, P);
+#else
     fr_mont_mul_c(r, a, b, P);
+#endif
 }
 
 CW_HD void fr_to_mont(u32 *r, const u32 *a, const FrParams &P) { fr_mont_mul(r, a, P.r2, P); }

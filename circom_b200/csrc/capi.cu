@@ -318,7 +318,14 @@ int cw_batch_create(const cw_circuit *c, uint32_t batch, int device, cw_batch **
     b->batch = batch;
     // tile size: keep at least ~4 CTAs per SM in flight before widening tiles for coalescing
     int bt = env_int("CW_BT_LOG2", -1);
-    if (bt < 0) bt = 0;  // BT = 1: a slot is one 32-byte sector and witness rows are contiguous in the slot store
+    if (bt < 0) {
+        // BT = 1 keeps witness rows contiguous in the slot store (no compaction) and is as fast as wider tiles
+        // whenever a level has enough ops to fill warps; very narrow tapes (Poseidon: ~3 ops per level)
+        // need instances side by side in a warp instead
+        uint64_t avg_w = t.n_levels() ? t.n_tape_ops() / t.n_levels() + 1 : 1;
+        bt = 0;
+        while (bt < 5 && (avg_w << bt) < 64 && (batch >> (bt + 1)) >= 296u) ++bt;
+    }
     if (bt > 5) bt = 5;
     b->bt_log2 = (u32)bt;
     u32 btn = 1u << bt;

@@ -34,7 +34,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="ecdsa_scale", choices=["ecdsa_scale", "sha256compression", "poseidon2"])
+    ap.add_argument("--workload", default="ecdsa_scale", choices=["ecdsa_scale", "sha256compression", "poseidon2", "sha256_512_bls"])
     ap.add_argument("--batch-per-gpu", type=int, default=0)
     ap.add_argument("--lanes", type=int, default=8)
     ap.add_argument("--chain", type=int, default=132)
@@ -50,7 +50,10 @@ def parse_args():
 def make_workload(args):
     from circom_b200.circuit import CircuitDesc
     from circom_b200 import circuits as C
-    d = CircuitDesc("bn128")
+    d = CircuitDesc("bls12381" if args.workload == "sha256_512_bls" else "bn128")
+    if args.workload == "sha256_512_bls":   # BASELINE.json configs[4]
+        d.set_main(C.sha256(d, 512), "sha256_512_bls")
+        return d, "Sha256(512) full preimage, BLS12-381 Fr", args.batch_per_gpu or 1024
     if args.workload == "ecdsa_scale":
         d.set_main(C.ecdsa_scale(d, args.lanes, args.chain), "ecdsa_scale_%dx%d" % (args.lanes, args.chain))
         label = "ecdsa-scale synthetic (secp256k1 BigMultModP chains %dx%d, 4x64-bit limbs), BN254" % (args.lanes, args.chain)
@@ -73,7 +76,7 @@ def synth_inputs(desc, workload: str, batch: int, seed: int) -> np.ndarray:
     a = np.zeros((batch, n_in, 4), dtype=np.uint64)
     if workload == "ecdsa_scale":      # 64-bit limbs
         a[:, :, 0] = rng.integers(0, 2**64, size=(batch, n_in), dtype=np.uint64)
-    elif workload == "sha256compression":  # bits
+    elif workload in ("sha256compression", "sha256_512_bls"):  # bits
         a[:, :, 0] = rng.integers(0, 2, size=(batch, n_in), dtype=np.uint64)
     else:                                # field elements (top limb kept below q's)
         a[:, :, :] = rng.integers(0, 2**64, size=(batch, n_in, 4), dtype=np.uint64)

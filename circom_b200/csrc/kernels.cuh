@@ -96,13 +96,18 @@ __global__ void __launch_bounds__(1024) tape_exec_kernel(TapeDev tp, uint4 *__re
     const u32 bt_mask = (1u << bt_log2) - 1;
     uint4 *base = slots + (((size_t)tile * tp.n_slots) << (bt_log2 + 1));
     u32 lb = tp.level_start[0];
+    u32 le = tp.n_levels ? tp.level_start[1] : lb;
+    // the tape word of a thread's first work item of the next level is fetched before the barrier of the
+    // current one, taking one memory round trip off the per-level critical path
+    uint4 pre = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x < ((le - lb) << bt_log2)) pre = __ldg(&tp.ops[lb + (threadIdx.x >> bt_log2)]);
     for (u32 l = 0; l < tp.n_levels; ++l) {
-        const u32 le = tp.level_start[l + 1];
         const u32 n = (le - lb) << bt_log2;
+        const u32 le_next = (l + 1 < tp.n_levels) ? tp.level_start[l + 2] : le;
         for (u32 w = threadIdx.x; w < n; w += blockDim.x) {
             const u32 oi = lb + (w >> bt_log2);
             const u32 li = w & bt_mask;
-            const uint4 opw = __ldg(&tp.ops[oi]);
+            const uint4 opw = (w == threadIdx.x) ? pre : __ldg(&tp.ops[oi]);
             const u32 opcode = opw.x & 0xFFu, dst = opw.x >> 8;
             const u32 inst = (tile << bt_log2) + li;
             u32 r[8];
@@ -146,7 +151,9 @@ __global__ void __launch_bounds__(1024) tape_exec_kernel(TapeDev tp, uint4 *__re
             }
             store_slot(r, base, dst, bt_log2, li);
         }
+        if (threadIdx.x < ((le_next - le) << bt_log2)) pre = __ldg(&tp.ops[le + (threadIdx.x >> bt_log2)]);
         lb = le;
+        le = le_next;
         __syncthreads();
     }
 }

@@ -1,0 +1,130 @@
+"""File formats checked with an independent python reader: the `.r1cs` the back end writes is parsed here
+from the format definition (constraint_writers/src/r1cs_writer.rs:6-14,49-72,246-269,328-341) and its
+constraints are evaluated with python integers on oracle witnesses; plus lowering edge cases."""
+import struct
+
+import numpy as np
+import pytest
+
+from circom_b200.circuit import CircuitDesc
+from circom_b200 import circuits as C
+from circom_b200.witness_calculator import Circuit, R1cs
+from oracle.ir_eval import evaluate
+from tests.util import hostsim_run, limbs_to_ints
+
+
+def parse_r1cs(raw: bytes):
+    assert raw[:4] == b"r1cs"
+    version, nsec = struct.unpack_from("<II", raw, 4)
+    assert version == 1
+    pos, secs = 12, {}
+    for _ in range(nsec):
+        ty, ln = struct.unpack_from("<IQ", raw, pos)
+        secs[ty] = (pos + 12, ln)
+        pos += 12 + ln
+    assert pos == len(raw)
+    h, _ = secs[1]
+    fs = struct.unpack_from("<I", raw, h)[0]
+    q = int.from_bytes(raw[h + 4:h + 4 + fs], "little")
+    n_wires, n_out, n_pub, n_prv, n_labels, m = struct.unpack_from("<IIIIQI", raw, h + 4 + fs)
+    c, _ = secs[2]
+    cons = []
+    for _ in range(m):
+        row = []
+        for _k in range(3):
+            n = struct.unpack_from("<I", raw, c)[0]
+            c += 4
+            lc = {}
+            prev = None
+            for _j in range(n):
+                w = struct.unpack_from("<I", raw, c)[0]
+                key = w.to_bytes(4, "little").rstrip(b"\0") or b"\0"
+                assert prev is None or prev < key, "wire ids must be sorted as little-endian byte strings"
+                prev = key
+                lc[w] = int.from_bytes(raw[c + 4:c + 4 + fs], "little")
+                c += 4 + fs
+            row.append(lc)
+        cons.append(row)
+    l, ln = secs[3]
+    labels = struct.unpack_from("<%dQ" % n_wires, raw, l)
+    return dict(q=q, n_wires=n_wires, n_out=n_out, n_pub=n_pub, n_prv=n_prv, n_labels=n_labels, cons=cons, labels=labels)
+
+
+@pytest.mark.parametrize("name,mk,inp", [
+    ("less_than", lambda d: C.less_than(d, 12), {"in": [77, 3000]}),
+    ("poseidon", lambda d: C.poseidon(d, 2), {"inputs": [1, 2]}),
+    ("ecdsa_small", lambda d: C.ecdsa_scale(d, 1, 2), {"a": [2**64 - 1, 5, 7, 11], "b": [13, 17, 19, 2**63]}),
+])
+@pytest.mark.parametrize("o0", [False, True])
+def test_written_r1cs_is_satisfied_by_oracle_witness(name, mk, inp, o0, tmp_path):
+    d = CircuitDesc("bn128")
+    d.set_main(mk(d))
+    c = Circuit(d, host_only=True, o0=o0)
+    p = str(tmp_path / "c.r1cs")
+    R1cs(c).write(p, d.main.n_out, 0, d.main.n_in)
+    r = parse_r1cs(open(p, "rb").read())
+    assert r["q"] == d.q and r["n_wires"] == c.n_witness and len(r["cons"]) == c.stats["n_constraints"]
+    assert (r["n_out"], r["n_prv"]) == (d.main.n_out, d.main.n_in)
+    sig = evaluate(d, inp)
+    w2s = c.witness2signal().astype(np.int64)
+    w = [sig[k] for k in w2s]
+    if o0:
+        assert w2s.tolist() == list(range(d.total_signals))
+    for A, B, Cc in r["cons"]:
+        a = sum(v * w[k] for k, v in A.items()) % d.q
+        b = sum(v * w[k] for k, v in B.items()) % d.q
+        cc = sum(v * w[k] for k, v in Cc.items()) % d.q
+        assert (a * b - cc) % d.q == 0
+    if not o0:   # no `signal = signal` row survives
+        for A, B, Cc in r["cons"]:
+            trivial = not A and not B and len(Cc) == 2 and 0 not in Cc and sum(Cc.values()) % d.q == 0
+            assert not trivial
+
+
+def test_constant_and_inputless_circuits():
+    """signals that are compile-time constants, a sub-component without inputs (runs at creation,
+    template.rs:274-278), two outputs with the same value, an output equal to an input"""
+    d = CircuitDesc("bn128")
+
+    def k(t):
+        o = t.output("k", 2)
+        t.assign_constrained(o[0], 41)
+        t.assign_constrained(o[1], t.const(41) + 1)
+    kt = d.template("Konst", (), k)
+
+    def main(t):
+        x = t.input("x")
+        o = t.output("o", 4)
+        c = t.component("k", kt)
+        t.assign(o[0], c["k", 0] + x)
+        t.assign(o[1], c["k", 1])
+        t.assign(o[2], x)          # output aliases an input without a constraint
+        t.assign(o[3], x * 1)      # and a second alias of the same value
+    d.set_main(d.template("Main", (), main))
+    wit, st, stats, w2s = hostsim_run(d, [{"x": 5}, {"x": 0}])
+    for i, x in enumerate((5, 0)):
+        exp = evaluate(d, {"x": x})
+        assert exp[1:5] == [41 + x, 42, x, x]
+        assert limbs_to_ints(wit[i]) == [exp[k] for k in w2s]
+
+
+def test_batch_of_one_and_status_of_bad_input():
+    d = CircuitDesc("bn128")
+    d.set_main(C.num2bits(d, 8))
+    wit, st, _, w2s = hostsim_run(d, [{"in": 255}])
+    assert st.tolist() == [0]
+    wit, st, _, _ = hostsim_run(d, [{"in": 256}, {"in": 3}])   # 256 does not fit 8 bits: recomposition assert fails
+    assert st[0] > 0 and st[1] == 0
+
+
+def test_failing_assert_number_matches_oracle():
+    """status = 1 + number of the first failing `===` in the reference's execution order, also after the
+    lowering fused / dropped asserts"""
+    from oracle.c_oracle import COracle
+    from tests.util import flat_inputs
+    d = CircuitDesc("bn128")
+    d.set_main(C.num2bits(d, 8))
+    ins = [{"in": 256}, {"in": 255}, {"in": 2**200}]
+    wit, st, _, _ = hostsim_run(d, ins)
+    ow, ost = COracle(d.to_bytes()).run(flat_inputs(d, ins))
+    assert st.tolist() == ost.tolist() == [9, 0, 9]

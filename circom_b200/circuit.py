@@ -36,6 +36,8 @@ OPS = {
     "SHL": 8, "SHR": 9, "LEQ": 10, "GEQ": 11, "LT": 12, "GT": 13, "EQ": 14, "NEQ": 15,
     "LOR": 16, "LAND": 17, "LNOT": 18, "BOR": 19, "BAND": 20, "BXOR": 21, "BNOT": 22,
     "NEG": 23, "COPY": 24, "SELECT": 25, "ASSERT": 26, "ASSERT_EQ": 27,
+    # function bodies (FunctionCodeInfo, compiler/src/circuit_design/function.rs) and their call sites
+    "JMP": 40, "JZ": 41, "RET": 42, "LOADX": 43, "STOREX": 44, "CALL": 45, "ARG": 46,
 }
 OP_NAMES = {v: k for k, v in OPS.items()}
 
@@ -308,6 +310,18 @@ class Template:
         b = b if isinstance(b, Expr) else self.const(b)
         return Expr(self, self._emit("SELECT", a, b, cond))
 
+    def call(self, fn: "Function", args: Sequence) -> Expr:
+        """`f(args...)` inside an expression (CallBucket, call_bucket.rs:466-533): the arguments are copied to
+        the callee's variables, the body runs with its own data-dependent loops and branches, one field
+        element comes back.  Functions returning arrays are called once per element (extra index argument)."""
+        assert len(args) == fn.n_params, "wrong number of arguments for %s" % fn.name
+        exprs = [a if isinstance(a, Expr) else self.const(a) for a in args]
+        for e in exprs:
+            self.ops.append((OPS["ARG"], NONE_REF, e.ref, NONE_REF, NONE_REF))
+        dst = self._tmp()
+        self.ops.append((OPS["CALL"], dst, (K_NONE, 0, fn.id), (K_NONE, 0, len(exprs)), NONE_REF))
+        return Expr(self, dst)
+
     # -- statements -------------------------------------------------------------------
     def assign(self, dst: Expr, src) -> None:
         """`dst <-- src` (StoreBucket, store_bucket.rs:607-646)."""
@@ -381,11 +395,153 @@ class Template:
         return self
 
 
+class FReg:
+    """A variable (register) of a function body.  Arithmetic on registers emits instructions into the
+    function and yields fresh registers; `fb.set(var, value)` assigns (circom `var` semantics: mutable)."""
+
+    __slots__ = ("fb", "idx")
+
+    def __init__(self, fb: "Function", idx: int):
+        self.fb, self.idx = fb, idx
+
+    def _b(self, op, o): return self.fb._emit_bin(op, self, o)
+    def _rb(self, op, o): return self.fb._emit_bin(op, o, self)
+    def __add__(self, o): return self._b("ADD", o)
+    def __radd__(self, o): return self._rb("ADD", o)
+    def __sub__(self, o): return self._b("SUB", o)
+    def __rsub__(self, o): return self._rb("SUB", o)
+    def __mul__(self, o): return self._b("MUL", o)
+    def __rmul__(self, o): return self._rb("MUL", o)
+    def __truediv__(self, o): return self._b("DIV", o)
+    def __floordiv__(self, o): return self._b("IDIV", o)
+    def __mod__(self, o): return self._b("MOD", o)
+    def __pow__(self, o): return self._b("POW", o)
+    def __lshift__(self, o): return self._b("SHL", o)
+    def __rshift__(self, o): return self._b("SHR", o)
+    def __and__(self, o): return self._b("BAND", o)
+    def __or__(self, o): return self._b("BOR", o)
+    def __xor__(self, o): return self._b("BXOR", o)
+    def __neg__(self): return self.fb._emit_bin("NEG", self, None)
+    def lt(self, o): return self._b("LT", o)
+    def gt(self, o): return self._b("GT", o)
+    def leq(self, o): return self._b("LEQ", o)
+    def geq(self, o): return self._b("GEQ", o)
+    def eq(self, o): return self._b("EQ", o)
+    def neq(self, o): return self._b("NEQ", o)
+    def land(self, o): return self._b("LAND", o)
+    def lor(self, o): return self._b("LOR", o)
+    def lnot(self): return self.fb._emit_bin("LNOT", self, None)
+
+
+class Function:
+    """A circom `function`: parameters and `var`s are registers, the body is a list of register
+    instructions with jumps, so loops and branches may depend on run-time values (LoopBucket /
+    BranchBucket with Fr_isTrue conditions, loop_bucket.rs:76-91, branch_bucket.rs:100-122; array
+    variables indexed through Fr_toInt, compute_bucket.rs:361-363)."""
+
+    def __init__(self, desc: "CircuitDesc", name: str, n_params: int):
+        self.desc, self.name, self.n_params = desc, name, n_params
+        self.n_regs = n_params
+        self.code: List[Tuple[int, Ref, Ref, Ref, Ref]] = []
+        self._loops: List[Tuple[int, List[int]]] = []
+        self._ifs: List[List[int]] = []
+        self.id = -1
+
+    # -- registers -----------------------------------------------------------------------
+    def param(self, i: int) -> FReg:
+        assert 0 <= i < self.n_params
+        return FReg(self, i)
+
+    def var(self, init=0) -> FReg:
+        r = FReg(self, self.n_regs)
+        self.n_regs += 1
+        self.set(r, init)
+        return r
+
+    def array(self, n: int, init=0) -> int:
+        """n consecutive registers; returns the index of the first (for load/store with a run-time index)"""
+        base = self.n_regs
+        self.n_regs += n
+        for k in range(n):
+            self.set(FReg(self, base + k), init)
+        return base
+
+    def _operand(self, o) -> Ref:
+        if isinstance(o, FReg):
+            return (K_TMP, 0, o.idx)
+        return (K_CONST, 0, self.desc.const_id(int(o)))
+
+    def _emit_bin(self, op: str, a, b) -> FReg:
+        r = FReg(self, self.n_regs)
+        self.n_regs += 1
+        self.code.append((OPS[op], (K_TMP, 0, r.idx), self._operand(a), self._operand(b) if b is not None else NONE_REF,
+                          NONE_REF))
+        return r
+
+    # -- statements ------------------------------------------------------------------------
+    def set(self, dst: FReg, src) -> None:
+        self.code.append((OPS["COPY"], (K_TMP, 0, dst.idx), self._operand(src), NONE_REF, NONE_REF))
+
+    def load(self, base: int, idx: FReg) -> FReg:
+        r = FReg(self, self.n_regs)
+        self.n_regs += 1
+        self.code.append((OPS["LOADX"], (K_TMP, 0, r.idx), (K_NONE, 0, base), (K_TMP, 0, idx.idx), NONE_REF))
+        return r
+
+    def store(self, base: int, idx: FReg, src) -> None:
+        self.code.append((OPS["STOREX"], NONE_REF, (K_NONE, 0, base), (K_TMP, 0, idx.idx), self._operand(src)))
+
+    def loop_begin(self) -> None:
+        self._loops.append((len(self.code), []))
+
+    def loop_break_if_zero(self, cond: FReg) -> None:
+        """`while (cond)`: leaves the innermost loop when cond is zero"""
+        self._loops[-1][1].append(len(self.code))
+        self.code.append((OPS["JZ"], NONE_REF, (K_TMP, 0, cond.idx), (K_NONE, 0, 0), NONE_REF))
+
+    def loop_end(self) -> None:
+        head, breaks = self._loops.pop()
+        self.code.append((OPS["JMP"], NONE_REF, (K_NONE, 0, head), NONE_REF, NONE_REF))
+        for pc in breaks:
+            op, d, a, _b, c = self.code[pc]
+            self.code[pc] = (op, d, a, (K_NONE, 0, len(self.code)), c)
+
+    def if_begin(self, cond: FReg) -> None:
+        self._ifs.append([len(self.code)])
+        self.code.append((OPS["JZ"], NONE_REF, (K_TMP, 0, cond.idx), (K_NONE, 0, 0), NONE_REF))
+
+    def if_else(self) -> None:
+        pcs = self._ifs[-1]
+        pcs.append(len(self.code))
+        self.code.append((OPS["JMP"], NONE_REF, (K_NONE, 0, 0), NONE_REF, NONE_REF))
+        op, d, a, _b, c = self.code[pcs[0]]
+        self.code[pcs[0]] = (op, d, a, (K_NONE, 0, len(self.code)), c)
+
+    def if_end(self) -> None:
+        pcs = self._ifs.pop()
+        if len(pcs) == 1:
+            op, d, a, _b, c = self.code[pcs[0]]
+            self.code[pcs[0]] = (op, d, a, (K_NONE, 0, len(self.code)), c)
+        else:
+            op, d, _a, b, c = self.code[pcs[1]]
+            self.code[pcs[1]] = (op, d, (K_NONE, 0, len(self.code)), b, c)
+
+    def ret(self, value) -> None:
+        self.code.append((OPS["RET"], NONE_REF, self._operand(value), NONE_REF, NONE_REF))
+
+    def finalize(self) -> "Function":
+        assert not self._loops and not self._ifs and self.code and self.code[-1][0] == OPS["RET"]
+        self.id = len(self.desc.functions)
+        self.desc.functions.append(self)
+        return self
+
+
 class CircuitDesc:
     def __init__(self, prime: str = "bn128"):
         self.prime = prime
         self.q = PRIMES[prime]
         self.templates: List[Template] = []
+        self.functions: List[Function] = []
         self.consts: List[int] = []
         self._cid: Dict[int, int] = {}
         self._cache: Dict[tuple, Template] = {}
@@ -412,6 +568,16 @@ class CircuitDesc:
             t.finalize()
             self._cache[key] = t
         return t
+
+    def function(self, name: str, n_params: int, build: Callable[[Function], None]) -> Function:
+        key = ("fn", name, n_params)
+        f = self._cache.get(key)
+        if f is None:
+            f = Function(self, name, n_params)
+            build(f)
+            f.finalize()
+            self._cache[key] = f
+        return f
 
     def set_main(self, t: Template, name: Optional[str] = None) -> "CircuitDesc":
         self.main = t
@@ -471,10 +637,17 @@ class CircuitDesc:
             nb = name.encode()
             names += struct.pack("<I", len(nb)) + nb + b"\0" * ((-len(nb)) % 4)
             names += struct.pack("<II", gid, n)
+        funcs = b""
+        for f in self.functions:
+            nb = f.name.encode()
+            funcs += struct.pack("<I", len(nb)) + nb + b"\0" * ((-len(nb)) % 4)
+            funcs += struct.pack("<3I", f.n_params, f.n_regs, len(f.code))
+            funcs += np.array([[op, pack_ref(d), pack_ref(a), pack_ref(b), pack_ref(c)] for op, d, a, b, c in f.code],
+                              dtype="<u8").reshape(-1, 5).tobytes()
         head = b"CB2C" + struct.pack("<7I", 1, PRIME_IDS[self.prime], len(self.consts), len(self.templates),
-                                     self.main.id, len(ins), 0)
+                                     self.main.id, len(ins), len(self.functions))
         consts = b"".join(int(c).to_bytes(32, "little") for c in self.consts)
-        return head + consts + b"".join(blobs) + names
+        return head + consts + b"".join(blobs) + names + funcs
 
     def save(self, path: str) -> str:
         with open(path, "wb") as f:

@@ -1,0 +1,90 @@
+"""Circuits whose `<--` hints are computed by circom *functions* with data-dependent control flow
+(the style of circom-ecdsa's bigint_func.circom: `long_div`, `log_ceil`, ...): loops whose trip count
+depends on run-time values, branches on run-time conditions, `var` arrays indexed by loop counters."""
+from __future__ import annotations
+
+from ..circuit import CircuitDesc, Function, Template
+from .basic import less_than, num2bits
+
+
+def fn_bit_length(d: CircuitDesc) -> Function:
+    """function bit_length(x) { var n = 0; while (x > 0) { x = x >> 1; n++; } return n; }"""
+    def build(f: Function):
+        x = f.var(f.param(0))
+        n = f.var(0)
+        f.loop_begin()
+        f.loop_break_if_zero(x.neq(0))
+        f.set(x, x >> 1)
+        f.set(n, n + 1)
+        f.loop_end()
+        f.ret(n)
+    return d.function("bit_length", 1, build)
+
+
+def fn_divmod(d: CircuitDesc, nbits: int = 64) -> Function:
+    """function divmod(a, b, sel): schoolbook restoring division over the bits of `a` (kept in a `var`
+    array filled by a loop and read back with a run-time index), returns the quotient (sel == 0) or the
+    remainder (sel != 0).  b == 0 returns 0."""
+    def build(f: Function):
+        a, b, sel = f.param(0), f.param(1), f.param(2)
+        bits = f.array(nbits)
+        i = f.var(0)
+        t = f.var(a)
+        top = f.var(0)
+        # bits[i] = (a >> i) & 1, remember the highest set bit
+        f.loop_begin()
+        f.loop_break_if_zero(t.neq(0))
+        f.store(bits, i, t & 1)
+        f.set(t, t >> 1)
+        f.set(i, i + 1)
+        f.loop_end()
+        f.set(top, i)
+        q = f.var(0)
+        r = f.var(0)
+        f.if_begin(b.neq(0))
+        f.loop_begin()
+        f.loop_break_if_zero(top.neq(0))
+        f.set(top, top - 1)
+        f.set(r, r * 2 + f.load(bits, top))
+        f.set(q, q * 2)
+        f.if_begin(r.geq(b))
+        f.set(r, r - b)
+        f.set(q, q + 1)
+        f.if_end()
+        f.loop_end()
+        f.if_end()
+        res = f.var(q)
+        f.if_begin(sel.neq(0))
+        f.set(res, r)
+        f.if_end()
+        f.ret(res)
+    return d.function("divmod%d" % nbits, 3, build)
+
+
+def int_div(d: CircuitDesc, nbits: int = 32) -> Template:
+    """q, r with a = q*b + r, 0 <= r < b (b != 0), hints from the `divmod` function, constrained with
+    range checks on q, r and LessThan(r, b)."""
+    fdiv = fn_divmod(d, 64)
+    fbl = fn_bit_length(d)
+    n2b = num2bits(d, nbits)
+    lt = less_than(d, nbits)
+
+    def build(t: Template):
+        a = t.input("a")
+        b = t.input("b")
+        q = t.output("q")
+        r = t.output("r")
+        nb = t.output("nbits")
+        t.assign(q, t.call(fdiv, [a, b, 0]))
+        t.assign(r, t.call(fdiv, [a, b, 1]))
+        t.assign(nb, t.call(fbl, [a]))
+        t.constrain(q * b + r, a)
+        cq = t.component("rq", n2b)
+        t.assign_constrained(cq["in"], q)
+        cr = t.component("rr", n2b)
+        t.assign_constrained(cr["in"], r)
+        c = t.component("lt", lt)
+        t.assign_constrained(c["in", 0], r)
+        t.assign_constrained(c["in", 1], b)
+        t.constrain(c["out"], 1)
+    return d.template("IntDiv", (nbits,), build)

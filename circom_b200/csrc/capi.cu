@@ -79,7 +79,7 @@ struct DevTape {
     uint4 *ops = nullptr;
     u32 *level_start = nullptr;
     uint4 *consts = nullptr;
-    u32 *input_slot = nullptr;
+    u32 *input_slot = nullptr, *fn_code = nullptr, *fn_info = nullptr, *call_tab = nullptr;
 };
 struct DevR1cs {
     unsigned long long *row_ptr = nullptr;
@@ -150,6 +150,9 @@ static int get_dev_tape(const cw_circuit *c, int device, DevTape &out) {
     if ((rc = upload(&d.level_start, t.level_start.data(), t.level_start.size() * 4))) return rc;
     if ((rc = upload(&d.consts, t.consts.data(), t.consts.size() * 32))) return rc;
     if ((rc = upload(&d.input_slot, t.input_slot.data(), t.input_slot.size() * 4))) return rc;
+    if ((rc = upload(&d.fn_code, t.fn_code.data(), t.fn_code.size() * 4))) return rc;
+    if ((rc = upload(&d.fn_info, t.fn_info.data(), t.fn_info.size() * 4))) return rc;
+    if ((rc = upload(&d.call_tab, t.call_tab.data(), t.call_tab.size() * 4))) return rc;
     c->dev[device] = d;
     out = d;
     return CW_OK;
@@ -203,6 +206,9 @@ void cw_circuit_destroy(cw_circuit *c) {
         cudaFree(kv.second.level_start);
         cudaFree(kv.second.consts);
         cudaFree(kv.second.input_slot);
+        cudaFree(kv.second.fn_code);
+        cudaFree(kv.second.fn_info);
+        cudaFree(kv.second.call_tab);
     }
     delete c;
 }
@@ -444,6 +450,9 @@ int cw_batch_run(cw_batch *b) {
     tp.n_levels = (u32)t.n_levels();
     tp.n_slots = t.n_slots;
     tp.input_slot = b->dt.input_slot;
+    tp.fn_code = b->dt.fn_code;
+    tp.fn_info = b->dt.fn_info;
+    tp.call_tab = b->dt.call_tab;
     tp.n_inputs = (u32)t.n_inputs;
     CU(cudaMemsetAsync(b->first_assert_d, 0xFF, (size_t)b->batch * 4, b->stream));
     CU(cudaMemsetAsync(b->err_d, 0, (size_t)b->batch * 4, b->stream));
@@ -455,10 +464,15 @@ int cw_batch_run(cw_batch *b) {
     }
     u32 tiles = b->batch_padded >> b->bt_log2;
     if (tp.n_levels) {
-        if (t.F.prime_id == 0)
-            tape_exec_kernel<0><<<tiles, b->threads, 0, b->stream>>>(tp, b->slots, b->bt_log2, b->first_assert_d, b->err_d, b->batch);
-        else
-            tape_exec_kernel<1><<<tiles, b->threads, 0, b->stream>>>(tp, b->slots, b->bt_log2, b->first_assert_d, b->err_d, b->batch);
+        const bool calls = !t.call_tab.empty();
+        const u32 th = calls ? std::min<u32>(b->threads, 256u) : b->threads;  // the interpreter build has a large frame
+        if (t.F.prime_id == 0) {
+            if (calls) tape_exec_kernel<0, true><<<tiles, th, 0, b->stream>>>(tp, b->slots, b->bt_log2, b->first_assert_d, b->err_d, b->batch);
+            else tape_exec_kernel<0, false><<<tiles, th, 0, b->stream>>>(tp, b->slots, b->bt_log2, b->first_assert_d, b->err_d, b->batch);
+        } else {
+            if (calls) tape_exec_kernel<1, true><<<tiles, th, 0, b->stream>>>(tp, b->slots, b->bt_log2, b->first_assert_d, b->err_d, b->batch);
+            else tape_exec_kernel<1, false><<<tiles, th, 0, b->stream>>>(tp, b->slots, b->bt_log2, b->first_assert_d, b->err_d, b->batch);
+        }
     }
     CU(cudaEventRecord(b->ev[1], b->stream));
     b->compact_valid = false;  // witness rows are slots [0, n_witness) of each instance: nothing to gather

@@ -128,6 +128,7 @@ struct Lowerer {
     std::vector<int32_t> sig_vid;
     // provisional tape
     std::vector<uint32_t> pops;  // 4 words per op
+    std::vector<uint32_t> pcalls;  // provisional call table: {function, n_args, arg operands...}
     std::vector<uint32_t> plevel;
     std::vector<uint32_t> slot_level;  // per provisional slot
     // constant table (raw patterns)
@@ -509,8 +510,35 @@ struct Lowerer {
             if (v < 0) throw std::runtime_error("lowering: read of unassigned value in template " + t.name);
             return v;
         };
+        std::vector<int32_t> argstack;
         for (const IrOp &o : t.ops) {
             ++n_ir_ops;
+            if (o.op == 46 /* ARG */) {
+                argstack.push_back(load(o.a));
+                continue;
+            }
+            if (o.op == 45 /* CALL */) {
+                uint32_t fid = ridx(o.a), n = ridx(o.b);
+                if ((size_t)fid * 4 + 3 >= T.fn_info.size() || n != T.fn_info[fid * 4 + 3] || n > argstack.size())
+                    throw std::runtime_error("lowering: bad function call in " + t.name);
+                // one tape op per call; arguments are read canonical, the result is canonical
+                uint32_t off = (uint32_t)pcalls.size();
+                pcalls.push_back(fid);
+                pcalls.push_back(n);
+                uint32_t lvl = 0;
+                for (uint32_t k = 0; k < n; ++k) {
+                    uint32_t opnd = need(argstack[argstack.size() - n + k], FC);
+                    pcalls.push_back(opnd);
+                    lvl = std::max(lvl, operand_level(opnd));
+                }
+                argstack.resize(argstack.size() - n);
+                uint32_t slot = emit(45, NO_SLOT, NO_SLOT, NO_SLOT, true);
+                pops[pops.size() - 3] = off;  // operand `a` is the call-table offset, not a slot
+                slot_level.back() = lvl + 1;
+                if (rk(o.d) != K_TMP) throw std::runtime_error("lowering: bad call destination");
+                tmp[ridx(o.d)] = new_val(slot, FC);
+                continue;
+            }
             if (o.op == CW_OP_ASSERT_EQ || o.op == CW_OP_ASSERT) {
                 uint32_t id = (uint32_t)n_asserts++;
                 if (flags & CW_FLAG_NO_ASSERTS) continue;
@@ -687,7 +715,7 @@ struct Lowerer {
         uint32_t prime = r.get<uint32_t>(), n_consts = r.get<uint32_t>(), n_tm = r.get<uint32_t>();
         main_tid = r.get<uint32_t>();
         uint32_t n_names = r.get<uint32_t>();
-        r.get<uint32_t>();
+        uint32_t n_funcs = r.get<uint32_t>();
         if (prime > 1) throw std::runtime_error("cb2c: unknown prime");
         T.F = make_field((int)prime);
         ir_consts.resize(n_consts);
@@ -767,6 +795,36 @@ struct Lowerer {
             in.size = r.get<uint32_t>();
             in.hash = fnv1a(in.name.data(), in.name.size());
             T.inputs.push_back(in);
+        }
+        // function bodies -> device register-machine code (fr_device.cuh: vm_run)
+        for (uint32_t i = 0; i < n_funcs; ++i) {
+            r.str();
+            uint32_t n_params = r.get<uint32_t>(), n_regs = r.get<uint32_t>(), n_instr = r.get<uint32_t>();
+            if (n_regs > 192 || n_params > n_regs) throw std::runtime_error("cb2c: function needs too many registers");
+            T.fn_info.push_back((uint32_t)(T.fn_code.size() / 5));
+            T.fn_info.push_back(n_instr);
+            T.fn_info.push_back(n_regs);
+            T.fn_info.push_back(n_params);
+            for (uint32_t k = 0; k < n_instr; ++k) {
+                uint64_t w[5];
+                for (auto &x : w) x = r.get<uint64_t>();
+                T.fn_code.push_back((uint32_t)w[0]);
+                for (int j = 1; j < 5; ++j) {
+                    uint32_t enc;
+                    switch (rk(w[j])) {
+                        case K_TMP:
+                            if (ridx(w[j]) >= n_regs) throw std::runtime_error("cb2c: bad register");
+                            enc = ridx(w[j]);
+                            break;
+                        case K_CONST:
+                            if (ridx(w[j]) >= n_consts) throw std::runtime_error("cb2c: bad constant");
+                            enc = OPERAND_CONST | raw_const(ir_consts[ridx(w[j])]);  // canonical
+                            break;
+                        default: enc = 0x40000000u | (ridx(w[j]) & 0x3FFFFFFFu); break;  // immediate / unused
+                    }
+                    T.fn_code.push_back(enc);
+                }
+            }
         }
     }
     uint32_t main_tid = 0;
@@ -849,6 +907,14 @@ struct Lowerer {
             bool is_assert = is_assert_op(o[0]);
             if (!is_assert && !live[n_pre + i]) continue;
             live[n_pre + i] = 1;
+            if (o[0] == 45) {  // CALL: operands live in the call table
+                uint32_t n = pcalls[o[1] + 1];
+                for (uint32_t k = 0; k < n; ++k) {
+                    uint32_t a = pcalls[o[1] + 2 + k];
+                    if (!(a & OPERAND_CONST)) live[a] = 1;
+                }
+                continue;
+            }
             for (int k = 1; k <= 3; ++k) {
                 if (k == 3 && c_is_immediate(o[0])) break;
                 if (o[k] != NO_SLOT && !(o[k] & OPERAND_CONST)) live[o[k]] = 1;
@@ -892,6 +958,19 @@ struct Lowerer {
             uint32_t *d = &T.ops[r * 4];
             uint32_t dst = is_assert_op(o[0]) ? 0u : remap[n_pre + order[r]];
             d[0] = o[0] | (dst << 8);  // opcode in bits 0-7, destination slot in bits 8-31
+            if (o[0] == 45) {
+                uint32_t n = pcalls[o[1] + 1];
+                d[1] = (uint32_t)T.call_tab.size();
+                d[2] = d[3] = OPERAND_CONST;
+                T.call_tab.push_back(pcalls[o[1]]);
+                T.call_tab.push_back(n);
+                for (uint32_t k = 0; k < n; ++k) {
+                    uint32_t a = pcalls[o[1] + 2 + k];
+                    T.call_tab.push_back((a & OPERAND_CONST) ? a : remap[a]);
+                }
+                T.level_start[slot_level[n_pre + order[r]]]++;
+                continue;
+            }
             for (int k = 1; k <= 3; ++k) {
                 if (k == 3 && c_is_immediate(o[0])) d[k] = o[k];  // immediate: IR assert number / bit-field spec
                 else if (o[k] == NO_SLOT) d[k] = OPERAND_CONST;  // unused operand: constant 0 (never read for its value)

@@ -6,6 +6,7 @@
 // same source for the CPU and check it against the oracle without a GPU; the PTX fast
 // path of the Montgomery product is selected only under __CUDA_ARCH__.
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)
@@ -589,6 +590,102 @@ CW_HD void fr_exec(u32 opcode, u32 *r, const u32 *a, const u32 *b, u32 imm, cons
         case OP_COPY: u256_set(r, a); break;
         default: u256_set_u32(r, 0); break;
     }
+}
+
+// ---- canonical-in / canonical-out application of one IR operator ---------------------------------------
+// (function bodies keep their variables canonical: a run-time loop cannot have its representations
+// inferred statically)
+CW_HD void fr_apply_canonical(u32 op, u32 *r, const u32 *a, const u32 *b, const u32 *c, const FrParams &P, int &err) {
+    if (op == OP_MUL) {
+        u32 am[8];
+        fr_to_mont(am, a, P);
+        fr_mont_mul(r, am, b, P);
+    } else if (op == 2 /* DIV */) {
+        u32 bm[8], im[8];
+        fr_to_mont(bm, b, P);
+        fr_inv_mont(im, bm, P);
+        fr_mont_mul(r, im, a, P);
+    } else if (op == OP_POW) {
+        u32 am[8], rm[8];
+        fr_to_mont(am, a, P);
+        fr_pow_mont(rm, am, b, P);
+        fr_from_mont(r, rm, P);
+    } else if (op == OP_SELECT) {
+        bool t = !u256_is_zero(c);
+        for (int k = 0; k < 8; ++k) r[k] = t ? a[k] : b[k];
+    } else {
+        fr_exec(op, r, a, b, 0, P, err);
+    }
+}
+
+// ---- function bodies: a small register machine run by ONE thread per call --------------------------------
+// circom `function`s (FunctionCodeInfo, compiler/src/circuit_design/function.rs:91-126) carry the
+// data-dependent loops and branches of `<--` hints (LoopBucket / BranchBucket on Fr_isTrue,
+// loop_bucket.rs:76-91, branch_bucket.rs:100-122) and index `var` arrays with run-time values
+// (Fr_toInt, compute_bucket.rs:361-363).  They cannot be unrolled into the tape; a call is one tape op
+// whose thread interprets the body over private registers.  Instruction = 5 words {op, d, a, b, c};
+// operand: bit31 = constant-table index, bit30 = immediate, else register index.
+enum { FOP_JMP = 40, FOP_JZ = 41, FOP_RET = 42, FOP_LOADX = 43, FOP_STOREX = 44, OP_CALL = 45 };
+enum { VM_MAX_REGS = 192, VM_MAX_STEPS = 1 << 22 };
+struct FnInfo {
+    u32 code_off, n_instr, n_regs, n_params;
+};
+
+CW_HD void vm_operand(u32 *v, u32 o, const u32 *regs, const u32 *consts32) {
+    if (o & 0x80000000u) {
+        const u32 *p = consts32 + 8 * (size_t)(o & 0x3FFFFFFFu);
+        for (int k = 0; k < 8; ++k) v[k] = p[k];
+    } else if (o & 0x40000000u) {
+        u256_set_u32(v, o & 0x3FFFFFFFu);
+    } else {
+        const u32 *p = regs + 8 * (size_t)o;
+        for (int k = 0; k < 8; ++k) v[k] = p[k];
+    }
+}
+// index operand -> int through the signed view (Fr_toInt, generic/fr.cpp:1146); -1 if out of range
+CW_HD int vm_index(const u32 *v, u32 base, u32 n_regs) {
+    u32 hi = v[1] | v[2] | v[3] | v[4] | v[5] | v[6] | v[7];
+    if (hi || (u64)v[0] + base >= n_regs) return -1;
+    return (int)(v[0] + base);
+}
+// regs: n_regs * 8 words, parameters already stored in registers 0..n_params-1.  err: 1 division by zero,
+// 2 bad index / runaway loop.
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline void vm_run(const u32 *code, FnInfo fi, u32 *regs, const u32 *consts32, u32 *result, const FrParams &P, int &err) {
+    const u32 *ins = code + 5 * (size_t)fi.code_off;
+    u32 pc = 0;
+    u256_set_u32(result, 0);
+    for (u32 step = 0; step < (u32)VM_MAX_STEPS; ++step) {
+        if (pc >= fi.n_instr) { err = 2; return; }
+        const u32 op = ins[5 * pc], d = ins[5 * pc + 1], a = ins[5 * pc + 2], b = ins[5 * pc + 3], c = ins[5 * pc + 4];
+        ++pc;
+        u32 va[8], vb[8], vc[8], r[8];
+        if (op == FOP_JMP) { pc = a & 0x3FFFFFFFu; continue; }
+        vm_operand(va, a, regs, consts32);
+        if (op == FOP_JZ) { if (u256_is_zero(va)) pc = b & 0x3FFFFFFFu; continue; }
+        if (op == FOP_RET) { u256_set(result, va); return; }
+        vm_operand(vb, b, regs, consts32);
+        if (op == FOP_LOADX) {
+            int i = vm_index(vb, a & 0x3FFFFFFFu, fi.n_regs);
+            if (i < 0) { err = 2; return; }
+            for (int k = 0; k < 8; ++k) regs[8 * (size_t)d + k] = regs[8 * (size_t)i + k];
+            continue;
+        }
+        vm_operand(vc, c, regs, consts32);
+        if (op == FOP_STOREX) {
+            int i = vm_index(vb, a & 0x3FFFFFFFu, fi.n_regs);
+            if (i < 0) { err = 2; return; }
+            for (int k = 0; k < 8; ++k) regs[8 * (size_t)i + k] = vc[k];
+            continue;
+        }
+        int e = 0;
+        fr_apply_canonical(op, r, va, vb, vc, P, e);
+        if (e) err = 1;
+        for (int k = 0; k < 8; ++k) regs[8 * (size_t)d + k] = r[k];
+    }
+    err = 2;
 }
 
 }  // namespace cw

@@ -56,6 +56,9 @@ struct TapeDev {
     const u32 *level_start;    // n_levels + 1
     const uint4 *consts;       // 2 per constant
     const u32 *input_slot;     // slot of main input k
+    const u32 *fn_code;        // register-machine code of the circuit's functions (5 words per instruction)
+    const u32 *fn_info;        // per function {code offset, n_instr, n_regs, n_params}
+    const u32 *call_tab;       // per call {function, n_args, arg operands...}
     u32 n_levels;
     u32 n_slots;
     u32 n_inputs;
@@ -87,7 +90,34 @@ __global__ void stage_inputs_kernel(TapeDev tp, const uint4 *__restrict__ inputs
 // items (op, instance) are spread over the CTA's threads, instance fastest.  Values produced in
 // level l are consumed in later levels by other threads of the same CTA only, so a CTA barrier
 // per level is the only synchronisation (no grid-wide sync, tiles are independent).
+// A function call (circom `function` with run-time loops / branches): the thread copies the arguments into
+// the callee's registers (local memory: they are indexed dynamically) and interprets the body.
 template <int PRIME>
+__device__ __noinline__ void exec_call(const TapeDev &tp, u32 call_off, const uint4 *base, u32 bt_log2, u32 li, u32 *r,
+                                       int *err) {
+    const FrParams &P = c_fr[PRIME];
+    const u32 *ct = tp.call_tab + call_off;
+    const u32 f = __ldg(&ct[0]), n_args = __ldg(&ct[1]);
+    FnInfo fi;
+    fi.code_off = __ldg(&tp.fn_info[4 * f]);
+    fi.n_instr = __ldg(&tp.fn_info[4 * f + 1]);
+    fi.n_regs = __ldg(&tp.fn_info[4 * f + 2]);
+    fi.n_params = __ldg(&tp.fn_info[4 * f + 3]);
+    u32 regs[VM_MAX_REGS * 8];
+    for (u32 k = 0; k < fi.n_regs * 8; ++k) regs[k] = 0;
+    for (u32 k = 0; k < n_args; ++k) {
+        u32 v[8];
+        load_operand(v, __ldg(&ct[2 + k]), base, tp.consts, bt_log2, li);
+        for (int j = 0; j < 8; ++j) regs[8 * k + j] = v[j];
+    }
+    int e = 0;
+    vm_run(tp.fn_code, fi, regs, reinterpret_cast<const u32 *>(tp.consts), r, P, e);
+    *err = e;
+}
+
+// HAS_CALLS selects the build that contains the function interpreter (more registers, a local-memory
+// frame); tapes without calls - all circuits whose hints are straight-line - use the lean build.
+template <int PRIME, bool HAS_CALLS>
 __global__ void __launch_bounds__(1024) tape_exec_kernel(TapeDev tp, uint4 *__restrict__ slots, u32 bt_log2,
                                                          u32 *__restrict__ first_assert, int *__restrict__ err,
                                                          u32 batch) {
@@ -111,7 +141,11 @@ __global__ void __launch_bounds__(1024) tape_exec_kernel(TapeDev tp, uint4 *__re
             const u32 opcode = opw.x & 0xFFu, dst = opw.x >> 8;
             const u32 inst = (tile << bt_log2) + li;
             u32 r[8];
-            if (opcode == OP_BITS && (opw.w >> 16) <= 32u && !(opw.y & 0x80000000u)) {
+            if (HAS_CALLS && opcode == OP_CALL) {
+                int e = 0;
+                exec_call<PRIME>(tp, opw.y, base, bt_log2, li, r, &e);
+                if (e && inst < batch) err[inst] = 1;
+            } else if (opcode == OP_BITS && (opw.w >> 16) <= 32u && !(opw.y & 0x80000000u)) {
                 // narrow bit-field of a slot value: fetch only the one or two 32-bit words that hold it
                 const u32 k = opw.w & 0xFFFFu, m = opw.w >> 16, wd = k >> 5, sh = k & 31u;
                 const u32 *words = reinterpret_cast<const u32 *>(base);

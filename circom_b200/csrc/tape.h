@@ -47,6 +47,9 @@ struct Tape {
     std::vector<U256> consts;           // raw limb patterns (already in the form the consumer needs)
     std::vector<uint32_t> witness_slot; // per witness entry (identity: witness entry i lives in slot i)
     std::vector<uint32_t> input_slot;   // slot of main input i
+    // circom functions (data-dependent control flow): register-machine code, per-function
+    // {code offset, n_instr, n_regs, n_params}, and the per-call tables {function, n_args, arg operands...}
+    std::vector<uint32_t> fn_code, fn_info, call_tab;
     std::vector<uint64_t> witness2signal; // witness2SignalList (calcwit.hpp:54-56)
     std::vector<InputInfo> inputs;
     std::vector<HashEntry> hashmap;

@@ -23,6 +23,7 @@ def circuits():
         "all_ops_bls": ("bls12381", lambda d: C.all_ops(d)),
         "less_than8": ("bn128", lambda d: C.less_than(d, 8)),
         "poseidon2": ("bn128", lambda d: C.poseidon(d, 2)),
+        "int_div32": ("bn128", lambda d: C.int_div(d, 32)),
         "ecdsa_scale_2x5": ("bn128", lambda d: C.ecdsa_scale(d, 2, 5)),
         "ecdsa_scale_8x132": ("bn128", lambda d: C.ecdsa_scale(d, 8, 132)),
     }

@@ -220,11 +220,15 @@ typedef struct {
     u32 *subs; irop *ops; u32 *lc_len; term *terms;
     u64 total_signals;
 } tmpl;
+/* function bodies (FunctionCodeInfo, compiler/src/circuit_design/function.rs:91-126): register code with
+ * jumps; called through CallBucket (call_bucket.rs:466-533) */
+typedef struct { u32 n_params, n_regs, n_instr; irop *code; } func;
 typedef struct {
     field_t F;
-    u32 prime, n_consts, n_tm, main_tid;
+    u32 prime, n_consts, n_tm, main_tid, n_funcs;
     fe *consts;
     tmpl *tm;
+    func *fn;
 } circuit;
 
 #define RK(r) ((int)((r) >> 56))
@@ -257,7 +261,8 @@ circuit *orc_load(const uint8_t *data, size_t len) {
     if (rd32(&r) != 1) return NULL;
     circuit *c = (circuit *)calloc(1, sizeof(circuit));
     c->prime = rd32(&r); c->n_consts = rd32(&r); c->n_tm = rd32(&r); c->main_tid = rd32(&r);
-    rd32(&r); rd32(&r);
+    u32 n_names = rd32(&r);
+    c->n_funcs = rd32(&r);
     field_init(&c->F, c->prime);
     c->consts = (fe *)calloc(c->n_consts ? c->n_consts : 1, sizeof(fe));
     for (u32 i = 0; i < c->n_consts; ++i) { if (r.p + 32 > r.end) { r.bad = 1; break; } memcpy(c->consts[i].v, r.p, 32); r.p += 32; }
@@ -283,7 +288,17 @@ circuit *orc_load(const uint8_t *data, size_t len) {
             for (u32 j = 0; j < n && ti < t->n_terms; ++j, ++ti) { t->terms[ti].ref = rd64(&r); t->terms[ti].cid = (u32)rd64(&r); }
         }
     }
-    if (r.bad) return NULL;
+    for (u32 i = 0; i < n_names && !r.bad; ++i) { u32 nl = rd32(&r); r.p += ((nl + 3) & ~3u) + 8; }
+    c->fn = (func *)calloc(c->n_funcs ? c->n_funcs : 1, sizeof(func));
+    for (u32 i = 0; i < c->n_funcs && !r.bad; ++i) {
+        func *f = &c->fn[i];
+        u32 nl = rd32(&r);
+        r.p += (nl + 3) & ~3u;
+        f->n_params = rd32(&r); f->n_regs = rd32(&r); f->n_instr = rd32(&r);
+        f->code = (irop *)calloc(f->n_instr ? f->n_instr : 1, sizeof(irop));
+        for (u32 k = 0; k < f->n_instr; ++k) { f->code[k].op = (u32)rd64(&r); f->code[k].d = rd64(&r); f->code[k].a = rd64(&r); f->code[k].b = rd64(&r); f->code[k].c = rd64(&r); }
+    }
+    if (r.bad || r.p > r.end) return NULL;
     return c;
 }
 
@@ -301,6 +316,41 @@ typedef struct {
     int stop_on_assert;
 } ctx_t;
 
+/* one function call: variables are registers, loops / branches test Fr_isTrue (loop_bucket.rs:76-91,
+ * branch_bucket.rs:100-122), array variables are indexed through Fr_toInt (compute_bucket.rs:361-363).
+ * returns 0 ok, -1 division by zero, -2 bad index / runaway */
+static int run_func(const circuit *c, const func *f, const fe *args, fe *result) {
+    fe *regs = (fe *)calloc(f->n_regs ? f->n_regs : 1, sizeof(fe));
+    for (u32 i = 0; i < f->n_params; ++i) regs[i] = args[i];
+    fe zero = fe_u64(0);
+    u32 pc = 0;
+    int rc = -2;
+    for (long step = 0; step < (1L << 22) && pc < f->n_instr; ++step) {
+        const irop *o = &f->code[pc++];
+        const fe *arg[3] = {&zero, &zero, &zero};
+        u64 refs[3] = {o->a, o->b, o->c};
+        for (int j = 0; j < 3; ++j) {
+            if (RK(refs[j]) == K_TMP) arg[j] = &regs[RIDX(refs[j])];
+            else if (RK(refs[j]) == K_CONST) arg[j] = &c->consts[RIDX(refs[j])];
+        }
+        if (o->op == 40) { pc = RIDX(o->a); continue; }                          /* JMP */
+        if (o->op == 41) { if (is_zero4(arg[0])) pc = RIDX(o->b); continue; }      /* JZ */
+        if (o->op == 42) { *result = *arg[0]; rc = 0; break; }                     /* RET */
+        if (o->op == 43 || o->op == 44) {                                          /* LOADX / STOREX */
+            const fe *ix = arg[1];
+            if (ix->v[1] | ix->v[2] | ix->v[3] || ix->v[0] + RIDX(o->a) >= f->n_regs) break;
+            u32 i = (u32)ix->v[0] + RIDX(o->a);
+            if (o->op == 43) regs[RIDX(o->d)] = regs[i]; else regs[i] = *arg[2];
+            continue;
+        }
+        fe v;
+        if (!f_apply(&c->F, o->op, &v, arg[0], arg[1], arg[2])) { rc = -1; break; }
+        regs[RIDX(o->d)] = v;
+    }
+    free(regs);
+    return rc;
+}
+
 static void run_comp(ctx_t *x, comp *me) {
     const circuit *c = x->c;
     const tmpl *t = &c->tm[me->tid];
@@ -315,6 +365,8 @@ static void run_comp(ctx_t *x, comp *me) {
         if (st->n_in == 0) run_comp(x, &subs[i]);
     }
     fe zero = fe_u64(0), one = fe_u64(1);
+    fe argstack[64];
+    u32 n_args = 0;
     for (u32 k = 0; k < t->n_ops && x->status != -1 && x->status != -2; ++k) {
         const irop *o = &t->ops[k];
         const fe *arg[3] = {&zero, &zero, &zero};
@@ -331,6 +383,17 @@ static void run_comp(ctx_t *x, comp *me) {
             }
         }
         if (x->status == -2) break;
+        if (o->op == 46) { if (n_args < 64) argstack[n_args++] = *arg[0]; continue; }     /* ARG */
+        if (o->op == 45) {                                                              /* CALL */
+            u32 fid = RIDX(o->a), n = RIDX(o->b);
+            fe res = fe_u64(0);
+            if (fid >= c->n_funcs || n > n_args) { x->status = -2; break; }
+            int rc = run_func(c, &c->fn[fid], &argstack[n_args - n], &res);
+            n_args -= n;
+            if (rc) { x->status = rc; break; }
+            tmp[RIDX(o->d)] = res;
+            continue;
+        }
         if (o->op == OP_ASSERT_EQ || o->op == OP_ASSERT) {
             u32 id = x->n_asserts++;
             int ok = o->op == OP_ASSERT_EQ ? cmp4(arg[0], arg[1]) == 0 : !is_zero4(arg[0]);
@@ -456,5 +519,6 @@ long orc_run_many(const circuit *c, const u64 *inputs, long n, int threads) {
 void orc_free(circuit *c) {
     if (!c) return;
     for (u32 i = 0; i < c->n_tm; ++i) { free(c->tm[i].subs); free(c->tm[i].ops); free(c->tm[i].lc_len); free(c->tm[i].terms); }
-    free(c->tm); free(c->consts); free(c);
+    for (u32 i = 0; i < c->n_funcs; ++i) free(c->fn[i].code);
+    free(c->fn); free(c->tm); free(c->consts); free(c);
 }

@@ -56,6 +56,9 @@ def emit_cpp(desc) -> str:
     for t in desc.templates:
         w("void %s_create(uint soffset,uint coffset,Circom_CalcWit* ctx,std::string componentName,uint componentFather);" % _header(t))
         w("void %s_run(uint ctx_index,Circom_CalcWit* ctx);" % _header(t))
+    for f in getattr(desc, "functions", []):
+        w("void %s_%d(Circom_CalcWit* ctx,FrElement* lvar,uint componentFather,FrElement* destination,int destination_size);"
+          % (f.name, f.id))
     w("Circom_TemplateFunction _functionTable[%d] = { %s };" % (
         len(desc.templates), ",".join("%s_run" % _header(t) for t in desc.templates)))
     w("Circom_TemplateFunction _functionTableParallel[%d] = { %s };" % (
@@ -78,6 +81,9 @@ def emit_cpp(desc) -> str:
       "if(ctx->componentMemory[pos].cvs)delete []ctx->componentMemory[pos].cvs;\n"
       "if(ctx->componentMemory[pos].sbct)delete []ctx->componentMemory[pos].sbct;\n"
       "}}\n}}\n")
+    w("// function declarations")
+    for f in getattr(desc, "functions", []):
+        _emit_function(w, f)
     w("// template declarations")
     for t in desc.templates:
         _emit_template(w, t)
@@ -87,6 +93,45 @@ def emit_cpp(desc) -> str:
         w("%s_run(0,ctx);" % _header(main))
     w("}\n")
     return "\n".join(out)
+
+
+def _emit_function(w, f) -> None:
+    """function.rs:91-126 prints `void f_k(Circom_CalcWit* ctx,FrElement* lvar,uint componentFather,
+    FrElement* destination,int destination_size)`; variables are lvar[] slots, loops are
+    `while(Fr_isTrue(..))` (loop_bucket.rs:76-91) - printed here with labels and gotos, which the same
+    Fr_isTrue / Fr_toInt / Fr_* calls drive."""
+    w("void %s_%d(Circom_CalcWit* ctx,FrElement* lvar,uint componentFather,FrElement* destination,int destination_size){"
+      % (f.name, f.id))
+    w("FrElement* circuitConstants = ctx->circuitConstants;")
+
+    def addr(r):
+        if r[0] == K_TMP:
+            return "&lvar[%d]" % r[2]
+        if r[0] == K_CONST:
+            return "&circuitConstants[%d]" % r[2]
+        raise ValueError(r)
+    for pc, (op, d, a, b, c) in enumerate(f.code):
+        w("L%d: ;" % pc)
+        if op == 40:
+            w("goto L%d;" % a[2])
+        elif op == 41:
+            w("if (!Fr_isTrue(%s)) goto L%d;" % (addr(a), b[2]))
+        elif op == 42:
+            w("Fr_copy(destination,%s); return;" % addr(a))
+        elif op == 43:
+            w("Fr_copy(&lvar[%d],&lvar[%d + Fr_toInt(%s)]);" % (d[2], a[2], addr(b)))
+        elif op == 44:
+            w("Fr_copy(&lvar[%d + Fr_toInt(%s)],%s);" % (a[2], addr(b), addr(c)))
+        elif op == 24:
+            w("Fr_copy(%s,%s);" % (addr(d), addr(a)))
+        elif op in _FN:
+            w("Fr_%s(%s,%s,%s);" % (_FN[op], addr(d), addr(a), addr(b)))
+        elif op in _FN1:
+            w("Fr_%s(%s,%s);" % (_FN1[op], addr(d), addr(a)))
+        else:
+            raise ValueError("cannot emit function op %d" % op)
+    w("L%d: ;" % len(f.code))
+    w("}\n")
 
 
 def _emit_template(w, t) -> None:
@@ -150,7 +195,23 @@ def _emit_template(w, t) -> None:
         raise ValueError(r)
 
     cmp_slot = "&expaux[%d]" % t.n_tmp
+    pending_args = []
     for op, d, a, b, c in t.ops:
+        if op == 46:  # ARG
+            pending_args.append(a)
+            continue
+        if op == 45:  # CALL (call_bucket.rs:466-533): arguments are copied into the callee's lvar array
+            fn = t.desc.functions[a[2]]
+            n = b[2]
+            args = pending_args[len(pending_args) - n:]
+            del pending_args[len(pending_args) - n:]
+            w("{")
+            w("FrElement lvarcall[%d];" % fn.n_regs)
+            for k, r in enumerate(args):
+                w("Fr_copy(&lvarcall[%d],%s);" % (k, addr(r)))
+            w("%s_%d(ctx,lvarcall,myId,%s,1);" % (fn.name, fn.id, addr(d)))
+            w("}")
+            continue
         if op == 27:  # ASSERT_EQ
             w("{")
             w("Fr_eq(%s,%s,%s);" % (cmp_slot, addr(a), addr(b)))

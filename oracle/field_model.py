@@ -27,6 +27,7 @@ OPS = {
     "SHL": 8, "SHR": 9, "LEQ": 10, "GEQ": 11, "LT": 12, "GT": 13, "EQ": 14, "NEQ": 15,
     "LOR": 16, "LAND": 17, "LNOT": 18, "BOR": 19, "BAND": 20, "BXOR": 21, "BNOT": 22,
     "NEG": 23, "COPY": 24, "SELECT": 25, "ASSERT": 26, "ASSERT_EQ": 27,
+    "JMP": 40, "JZ": 41, "RET": 42, "LOADX": 43, "STOREX": 44, "CALL": 45, "ARG": 46,
 }
 OP_NAMES = {v: k for k, v in OPS.items()}
 

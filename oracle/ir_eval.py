@@ -25,6 +25,50 @@ class AssertFailed(Exception):
     pass
 
 
+def run_function(desc, F, fn, args):
+    """A function body: registers are mutable variables, loops / branches test Fr_isTrue of run-time values
+    (loop_bucket.rs:76-91, branch_bucket.rs:100-122), array variables are indexed through Fr_toInt
+    (compute_bucket.rs:361-363; signed view, must be a valid index)."""
+    regs = [0] * fn.n_regs
+    regs[:fn.n_params] = list(args)
+    consts = desc.consts
+
+    def val(r):
+        if r[0] == K_TMP: return regs[r[2]]
+        if r[0] == K_CONST: return consts[r[2]]
+        return 0
+
+    def to_int(v):
+        v = F.val(v)
+        assert -(1 << 31) <= v < (1 << 31)
+        return v
+
+    pc, steps = 0, 0
+    while True:
+        steps += 1
+        if steps > 10_000_000:
+            raise RuntimeError("function %s does not terminate" % fn.name)
+        op, d, a, b, c = fn.code[pc]
+        pc += 1
+        if op == OPS["JMP"]:
+            pc = a[2]
+        elif op == OPS["JZ"]:
+            if val(a) == 0:
+                pc = b[2]
+        elif op == OPS["RET"]:
+            return val(a)
+        elif op == OPS["LOADX"]:
+            i = a[2] + to_int(val(b))
+            assert 0 <= i < fn.n_regs
+            regs[d[2]] = regs[i]
+        elif op == OPS["STOREX"]:
+            i = a[2] + to_int(val(b))
+            assert 0 <= i < fn.n_regs
+            regs[i] = val(c)
+        else:
+            regs[d[2]] = F.apply(op, val(a), val(b), val(c))
+
+
 class _Comp:
     __slots__ = ("tmpl", "start", "counter", "subs", "ran")
 
@@ -67,7 +111,17 @@ def evaluate(desc, inputs: Dict[str, Sequence[int]], check_asserts: bool = True)
                 raise RuntimeError("read of unassigned value %r in %s" % (r, t.name))
             return v
 
+        argstack = []
         for op, d, a, b, cc in t.ops:
+            if op == OPS["ARG"]:
+                argstack.append(load(a))
+                continue
+            if op == OPS["CALL"]:
+                n = b[2]
+                args = argstack[len(argstack) - n:]
+                del argstack[len(argstack) - n:]
+                tmp[d[2]] = run_function(desc, F, desc.functions[a[2]], args)
+                continue
             if op == OPS["ASSERT_EQ"]:
                 if check_asserts and load(a) != load(b):
                     raise AssertFailed(t.name)

@@ -76,6 +76,17 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
             const uint32_t op[4] = {opw[0] & 0xFFu, opw[1], opw[2], opw[3]};
             const uint32_t dst = opw[0] >> 8;
             u32 a[8], b[8], r[8];
+            if (op[0] == OP_CALL) {  // function call: one work item interprets the body
+                const uint32_t *ct = &t.call_tab[op[1]];
+                FnInfo fi{t.fn_info[ct[0] * 4], t.fn_info[ct[0] * 4 + 1], t.fn_info[ct[0] * 4 + 2], t.fn_info[ct[0] * 4 + 3]};
+                std::vector<u32> regs((size_t)fi.n_regs * 8, 0);
+                for (uint32_t k = 0; k < ct[1]; ++k) operand(ct[2 + k], &regs[(size_t)k * 8]);
+                int e = 0;
+                vm_run(t.fn_code.data(), fi, regs.data(), (const u32 *)t.consts.data(), r, P, e);
+                if (e) err = 1;
+                memcpy(&slots[(size_t)dst * 8], r, 32);
+                continue;
+            }
             operand(op[1], a);
             operand(op[2], b);
             if (op[0] == OP_SELECT) {
@@ -141,6 +152,15 @@ int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
     for (size_t i = 0; i < t.n_tape_ops(); ++i) {
         const uint32_t *opw = &t.ops[i * 4];
         const uint32_t op[4] = {opw[0] & 0xFFu, opw[1], opw[2], opw[3]};
+        if (op[0] == OP_CALL) {
+            const uint32_t *ct = &t.call_tab[op[1]];
+            for (uint32_t k = 0; k < ct[1]; ++k) {
+                uint32_t a = ct[2 + k];
+                if (a & OPERAND_CONST) continue;
+                if (a >= t.n_slots || lvl[a] >= oplvl[i]) { g_err = "call argument not produced in an earlier level"; return -9; }
+            }
+            continue;
+        }
         bool c_imm = op[0] == OP_ASSERT || op[0] == OP_ASSERT_EQ || op[0] == OP_ASSERT_BOOL || op[0] == OP_BITS || op[0] == OP_BITSIP || op[0] == OP_ASSERT_FITS;
         for (int k = 1; k <= 3; ++k) {
             if (k == 3 && c_imm) break;

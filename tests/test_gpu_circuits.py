@@ -98,7 +98,8 @@ def test_ecdsa_scale_vs_oracle_and_python_ints(lanes, steps, batch):
     assert not st.any() and (ow[:, w2s] == wit[:n]).all()
 
 
-@pytest.mark.parametrize("name", ["multiplier2", "all_ops", "all_ops_bls", "poseidon2", "ecdsa_scale_2x5", "ecdsa_scale_8x132"])
+@pytest.mark.parametrize("name", ["multiplier2", "all_ops", "all_ops_bls", "poseidon2", "int_div32", "ecdsa_scale_2x5",
+                                  "ecdsa_scale_8x132"])
 def test_wtns_bytes_equal_reference_runtime(name, tmp_path):
     """`.wtns` written by the GPU path == bytes written by the reference's own C++ calculator
     (oracle/_ref/calc/<name>: reference main.cpp + calcwit.cpp + fr.cpp + hand-lowered circuit) for the
@@ -118,6 +119,9 @@ def test_wtns_bytes_equal_reference_runtime(name, tmp_path):
     arr = np.zeros((n, n_in, 4), dtype=np.uint64)
     if name.startswith("ecdsa"):
         arr[:, :, 0] = rng.integers(0, 2**64, size=(n, n_in), dtype=np.uint64)
+    elif name.startswith("int_div"):
+        arr[:, 0, 0] = rng.integers(0, 2**32, size=n, dtype=np.uint64)
+        arr[:, 1, 0] = rng.integers(1, 2**20, size=n, dtype=np.uint64)
     else:
         arr[:, :, :] = rng.integers(0, 2**64, size=(n, n_in, 4), dtype=np.uint64)
         arr[:, :, 3] &= np.uint64(0x0FFFFFFFFFFFFFFF)
@@ -173,3 +177,17 @@ def test_cli_matches_reference_calculator(tmp_path):
     json.dump({"a": "1", "b": ["1", "2"]}, open(jp, "w"))
     r = subprocess.run([cbuild.CLI, cb, jp, str(tmp_path / "x.wtns")], capture_output=True, text=True, env=env)
     assert r.returncode != 0 and "Too many values" in r.stderr
+
+
+def test_function_hints_large_batch_and_runtime_errors():
+    """circom functions (run-time loops / branches / indexed arrays) as one tape op per call: a batch whose
+    instances take different numbers of loop iterations, and the division-by-zero path inside a function"""
+    d = CircuitDesc("bn128")
+    d.set_main(C.int_div(d, 32))
+    rng = random.Random(12)
+    ins = [{"a": rng.randrange(2**rng.randrange(1, 33)), "b": rng.randrange(1, 2**rng.randrange(1, 33))} for _ in range(700)]
+    c, wit, arr, w2s = _run(d, ins)
+    for i, inp in enumerate(ins):
+        assert limbs_to_ints(wit[i][1:4]) == [inp["a"] // inp["b"], inp["a"] % inp["b"], inp["a"].bit_length()]
+    ow, st = COracle(d.to_bytes()).run(arr[:64])
+    assert not st.any() and (ow[:, w2s] == wit[:64]).all()

@@ -22,6 +22,10 @@ CIRCUITS = {
     "num2bits64": (lambda d: C.num2bits(d, 64), lambda r, q: {"in": r.randrange(2**64)}),
     "multiplier_n6": (lambda d: C.multiplier_n(d, 6), lambda r, q: {"in": [r.randrange(q) for _ in range(6)]}),
     "is_zero": (lambda d: C.is_zero(d), lambda r, q: {"in": r.choice([0, r.randrange(q)])}),
+    # hints computed by circom functions with run-time loops, branches and array indexing
+    "int_div32": (lambda d: C.int_div(d, 32),
+                  lambda r, q: {"a": r.choice([0, 1, 2**32 - 1, r.randrange(2**32)]),
+                                "b": r.choice([1, 2**32 - 1, r.randrange(1, 2**r.randrange(1, 33))])}),
 }
 
 

@@ -86,7 +86,7 @@ struct DevR1cs {
     u32 *col = nullptr, *coef = nullptr;
     uint4 *dictM = nullptr;
     unsigned short *kind = nullptr;
-    u32 *perm = nullptr, *bool_wire = nullptr, *bool_row = nullptr;
+    u32 *perm = nullptr, *bool_wire = nullptr, *bool_row = nullptr, *term_bool_row = nullptr;
     u32 n_general = 0, n_bool = 0;
 };
 
@@ -668,6 +668,7 @@ void cw_r1cs_destroy(cw_r1cs *r) {
         cudaFree(kv.second.perm);
         cudaFree(kv.second.bool_wire);
         cudaFree(kv.second.bool_row);
+        cudaFree(kv.second.term_bool_row);
     }
     delete r;
 }
@@ -743,6 +744,30 @@ int cw_r1cs_check_strided(cw_r1cs *r, const uint64_t *witness, uint64_t stride_e
                 else perm.push_back((u32)row);
             }
             std::stable_sort(perm.begin(), perm.end(), [&](u32 x, u32 y) { return sig[x] > sig[y]; });
+            // a boolean row whose wire is a term of a general row (the bit of a decomposition inside its
+            // recomposition sum) is checked by that term's thread while the value is in registers: the witness
+            // is then read once instead of twice
+            std::vector<u32> term_bool(R.col.size(), 0xFFFFFFFFu);
+            {
+                std::vector<u32> wire2bool(R.n_wires, 0xFFFFFFFFu);
+                for (size_t i = 0; i < bool_wire.size(); ++i)
+                    if (wire2bool[bool_wire[i]] == 0xFFFFFFFFu) wire2bool[bool_wire[i]] = (u32)i;
+                std::vector<uint8_t> absorbed(bool_wire.size(), 0);
+                for (u32 row : perm)
+                    for (uint64_t k = R.row_ptr[3 * (size_t)row]; k < R.row_ptr[3 * (size_t)row + 3]; ++k) {
+                        u32 bi = wire2bool[R.col[k]];
+                        if (bi != 0xFFFFFFFFu && !absorbed[bi]) {
+                            absorbed[bi] = 1;
+                            term_bool[k] = bool_row[bi];
+                        }
+                    }
+                size_t o = 0;
+                for (size_t i = 0; i < bool_wire.size(); ++i)
+                    if (!absorbed[i]) { bool_wire[o] = bool_wire[i]; bool_row[o] = bool_row[i]; ++o; }
+                bool_wire.resize(o);
+                bool_row.resize(o);
+            }
+            if ((rc = upload(&d.term_bool_row, term_bool.data(), term_bool.size() * 4))) return rc;
             d.n_general = (u32)perm.size();
             d.n_bool = (u32)bool_wire.size();
             if ((rc = upload(&d.bool_wire, bool_wire.data(), bool_wire.size() * 4))) return rc;
@@ -776,6 +801,7 @@ int cw_r1cs_check_strided(cw_r1cs *r, const uint64_t *witness, uint64_t stride_e
     rd.dictM = d.dictM;
     rd.kind = d.kind;
     rd.perm = d.perm;
+    rd.term_bool_row = d.term_bool_row;
     rd.n_constraints = d.n_general;  // rows visited through perm
     rd.n_wires = (u32)R.n_wires;
     rd.w_stride = stride_elems;

@@ -239,6 +239,7 @@ struct R1csDev {
     const uint4 *dictM;
     const unsigned short *kind;
     const u32 *perm;
+    const u32 *term_bool_row;  // per term: row id of the boolean constraint of its wire checked alongside, or ~0
     u32 n_constraints;
     u32 n_wires;
     u32 inst_per_block;
@@ -247,7 +248,8 @@ struct R1csDev {
 
 template <int PRIME>
 __device__ __forceinline__ void r1cs_lc(u32 *acc, const R1csDev &R, unsigned long long b, unsigned long long e,
-                                        const uint4 *__restrict__ w, const FrParams &P) {
+                                        const uint4 *__restrict__ w, const FrParams &P,
+                                        unsigned long long *__restrict__ first_bad_inst) {
     u256_set_u32(acc, 0);
     for (unsigned long long k = b; k < e; ++k) {
         u32 c = __ldg(&R.col[k]);
@@ -258,8 +260,18 @@ __device__ __forceinline__ void r1cs_lc(u32 *acc, const R1csDev &R, unsigned lon
         u32 kw = __ldg(&R.kind[ci]);
         u32 kd = kw & 0xFF, sh = kw >> 8;
         bool neg = (kd == 2) || (kd == 4);
+        const u32 upper = x[1] | x[2] | x[3] | x[4] | x[5] | x[6] | x[7];
+        // the boolean constraint x*(x-1) = 0 of this wire is checked here, while its value is in registers
+        const u32 brow = __ldg(&R.term_bool_row[k]);
+        if (brow != 0xFFFFFFFFu && (upper || x[0] > 1u)) atomicMin(first_bad_inst, (unsigned long long)brow);
         if (kd >= 3) {
-            if (u256_bitlen_dev(x) + sh < P.qbits) {   // x * 2^sh < 2^(qbits-1) < q : plain shift
+            if (!upper && sh <= 222u) {
+                // one-limb value times 2^sh: place the (at most 64-bit) shifted value, no reduction needed
+                const u32 wd = sh >> 5, s = sh & 31u;
+                const u32 l = x[0] << s, h = s ? (x[0] >> (32u - s)) : 0u;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = ((u32)i == wd) ? l : (((u32)i == wd + 1u) ? h : 0u);
+            } else if (u256_bitlen_dev(x) + sh < P.qbits) {   // x * 2^sh < 2^(qbits-1) < q : plain shift
                 u32 y[8];
                 u256_shl(y, x, sh);
                 u256_set(x, y);
@@ -295,9 +307,9 @@ __global__ void __launch_bounds__(256) r1cs_check_kernel(R1csDev R, const uint4 
         for (u32 inst = i0; inst < i1; ++inst) {
             const uint4 *w = witness + (size_t)inst * R.w_stride * 2;
             u32 a[8], b[8], c[8];
-            r1cs_lc<PRIME>(a, R, p0, p1, w, P);
-            r1cs_lc<PRIME>(b, R, p1, p2, w, P);
-            r1cs_lc<PRIME>(c, R, p2, p3, w, P);
+            r1cs_lc<PRIME>(a, R, p0, p1, w, P, &first_bad[inst]);
+            r1cs_lc<PRIME>(b, R, p1, p2, w, P, &first_bad[inst]);
+            r1cs_lc<PRIME>(c, R, p2, p3, w, P, &first_bad[inst]);
             bool ok;
             u32 ha = a[1] | a[2] | a[3] | a[4] | a[5] | a[6] | a[7];
             u32 hb = b[1] | b[2] | b[3] | b[4] | b[5] | b[6] | b[7];

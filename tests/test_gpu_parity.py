@@ -166,3 +166,28 @@ def test_r1cs_check_reads_witness_in_place():
     for i, inp in enumerate(ins):
         exp = evaluate(d, inp)
         assert limbs_to_ints(wit[i]) == [exp[k] for k in w2s]
+
+
+def test_r1cs_first_violated_row_matches_oracle():
+    """corrupt single witness entries (bits set to 2, the packed value changed): the smallest violated row
+    reported by the GPU check equals the oracle's, also for boolean rows that are checked inside the
+    recomposition-sum thread"""
+    from oracle.c_oracle import COracle
+    d = CircuitDesc("bn128")
+    d.set_main(C.num2bits(d, 16))     # no signal=signal rows: row numbering equals the oracle's
+    c = Circuit(d)
+    b = Batch(c, 1)
+    b.set_inputs(flat_inputs(d, [{"in": 0xBEEF}]))
+    b.run()
+    good = b.witness()
+    orc = COracle(d.to_bytes())
+    r = R1cs(c)
+    cases = []
+    for wire in (1, 5, 16, 17):       # out[0], out[4], out[15], in
+        bad = good.copy()
+        bad[0, wire, 0] = 2 if wire != 17 else 0xBEEE
+        cases.append(bad)
+    batch = np.concatenate(cases, axis=0)
+    fb, _ = r.check(batch)
+    exp = orc.r1cs_check(batch)
+    assert (exp >= 0).all() and fb.tolist() == exp.tolist()

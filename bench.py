@@ -65,7 +65,7 @@ def make_workload(args):
     else:
         d.set_main(C.poseidon(d, 2), "poseidon2")
         label = "Poseidon(2), BN254"
-        batch = args.batch_per_gpu or 4096
+        batch = args.batch_per_gpu or 65536
     return d, label, batch
 
 

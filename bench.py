@@ -382,7 +382,9 @@ def main():
         "kernel_ms": {"tape_exec+stage": exec_ms / args.steps},
         "e2e": {"value": (e2e_batch * world * e2e_steps / e2e_s) if e2e_s else None, "unit": "witnesses/s",
                 "steps": e2e_steps, "batch_per_gpu": e2e_batch,
-                "h2d_bytes_per_step": int(e2e_batch * n_in * 32), "d2h_bytes_per_step": int(e2e_batch * W * 32)},
+                "h2d_bytes_per_step": int(e2e_batch * n_in * 32),
+                "d2h_bytes_per_step": (e2e_state["b"].last_d2h_bytes() if e2e_state else int(e2e_batch * W * 32)),
+                "host_witness_bytes_per_step": int(e2e_batch * W * 32)},
         "gpu_launches": 2 * args.steps,   # stage_inputs_kernel + tape_exec_kernel per step
         "clocks": clocks,
         "roofline": {"kernel": "tape_exec_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -80,6 +81,7 @@ struct DevTape {
     u32 *level_start = nullptr;
     uint4 *consts = nullptr;
     u32 *input_slot = nullptr, *fn_code = nullptr, *fn_info = nullptr, *call_tab = nullptr;
+    u32 *pk_bit = nullptr, *pk_u64 = nullptr, *pk_full = nullptr;
 };
 struct DevR1cs {
     unsigned long long *row_ptr = nullptr;
@@ -133,6 +135,9 @@ struct cw_batch {
     bool inputs_on_device = false;
     bool ran = false;
     bool compact_valid = false;  // witness_d holds the contiguous copy of the current run
+    u32 *packed_d = nullptr, *packed_h = nullptr;  // packed witness staging (device / pinned host)
+    int *pack_flag_d = nullptr;
+    uint64_t last_d2h_bytes = 0;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
 };
 
@@ -153,6 +158,9 @@ static int get_dev_tape(const cw_circuit *c, int device, DevTape &out) {
     if ((rc = upload(&d.fn_code, t.fn_code.data(), t.fn_code.size() * 4))) return rc;
     if ((rc = upload(&d.fn_info, t.fn_info.data(), t.fn_info.size() * 4))) return rc;
     if ((rc = upload(&d.call_tab, t.call_tab.data(), t.call_tab.size() * 4))) return rc;
+    if ((rc = upload(&d.pk_bit, t.pk_bit_wire.data(), t.pk_bit_wire.size() * 4))) return rc;
+    if ((rc = upload(&d.pk_u64, t.pk_u64_wire.data(), t.pk_u64_wire.size() * 4))) return rc;
+    if ((rc = upload(&d.pk_full, t.pk_full_wire.data(), t.pk_full_wire.size() * 4))) return rc;
     c->dev[device] = d;
     out = d;
     return CW_OK;
@@ -209,6 +217,9 @@ void cw_circuit_destroy(cw_circuit *c) {
         cudaFree(kv.second.fn_code);
         cudaFree(kv.second.fn_info);
         cudaFree(kv.second.call_tab);
+        cudaFree(kv.second.pk_bit);
+        cudaFree(kv.second.pk_u64);
+        cudaFree(kv.second.pk_full);
     }
     delete c;
 }
@@ -380,6 +391,9 @@ void cw_batch_destroy(cw_batch *b) {
     cudaFree(b->slots);
     cudaFree(b->inputs_d);
     cudaFree(b->witness_d);
+    cudaFree(b->packed_d);
+    cudaFree(b->pack_flag_d);
+    if (b->packed_h) cudaFreeHost(b->packed_h);
     cudaFree(b->first_assert_d);
     cudaFree(b->err_d);
     for (auto &e : b->ev)
@@ -525,22 +539,90 @@ static int compact_witness(cw_batch *b) {
     return CW_OK;
 }
 
+// Packed transfer: entries the lowering proved to be one bit / <= 64 bits cross PCIe as that, the host
+// expands them to the canonical 32-byte rows (zero-extension only - no field arithmetic happens on the CPU).
+// For circuits made of bit decompositions this cuts the device->host bytes by an order of magnitude; the
+// expansion runs on a few host threads at memory speed.  CW_PACKED_D2H=0 forces the plain pitched copy.
+static int get_witness_packed(cw_batch *b, uint64_t *out, bool *done) {
+    const Tape &t = b->c->tape;
+    *done = false;
+    const size_t n0 = t.pk_bit_wire.size(), n1 = t.pk_u64_wire.size(), n2 = t.pk_full_wire.size();
+    const size_t bit_words = (n0 + 31) / 32;
+    size_t words = bit_words + 2 * n1 + 8 * n2;
+    words = (words + 3) & ~(size_t)3;
+    if (b->bt_log2 != 0 || env_int("CW_PACKED_D2H", 1) == 0 || words * 4 * 2 > (size_t)t.n_witness * 32) return CW_OK;
+    const size_t bytes = words * 4 * b->batch;
+    if (!b->packed_d) {
+        CU(cudaMalloc((void **)&b->packed_d, bytes));
+        CU(cudaMallocHost((void **)&b->packed_h, bytes));
+        CU(cudaMalloc((void **)&b->pack_flag_d, 4));
+    }
+    CU(cudaMemsetAsync(b->pack_flag_d, 0, 4, b->stream));
+    dim3 grid((u32)std::min<size_t>((bit_words + n1 + n2 + 255) / 256, 148 * 4), std::min<u32>(b->batch, 65535u));
+    if (grid.x == 0) grid.x = 1;
+    witness_pack_kernel<<<grid, 256, 0, b->stream>>>(b->slots, t.n_slots, b->dt.pk_bit, (u32)n0, b->dt.pk_u64, (u32)n1,
+                                                     b->dt.pk_full, (u32)n2, b->packed_d, words, b->batch, b->pack_flag_d);
+    CU(cudaGetLastError());
+    int flag = 0;
+    CU(cudaMemcpyAsync(b->packed_h, b->packed_d, bytes, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaMemcpyAsync(&flag, b->pack_flag_d, 4, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    if (flag) return CW_OK;  // a value exceeded its static class (never expected): caller does the plain copy
+    b->last_d2h_bytes = bytes;
+    // host-side expansion, one instance per task
+    const uint32_t *bw = t.pk_bit_wire.data(), *uw = t.pk_u64_wire.data(), *fw = t.pk_full_wire.data();
+    const size_t W = t.n_witness;
+    unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)env_int("CW_UNPACK_THREADS", 32)));
+    nt = std::min<unsigned>(nt, b->batch);
+    std::vector<std::thread> th;
+    for (unsigned tid = 0; tid < nt; ++tid)
+        th.emplace_back([=]() {
+            for (uint32_t inst = tid; inst < b->batch; inst += nt) {
+                const uint32_t *p = b->packed_h + (size_t)inst * words;
+                uint64_t *row = out + (size_t)inst * W * 4;
+                memset(row, 0, W * 32);
+                for (size_t wd = 0; wd < bit_words; ++wd) {
+                    uint32_t x = p[wd];
+                    while (x) {
+                        int j = __builtin_ctz(x);
+                        x &= x - 1;
+                        row[(size_t)bw[wd * 32 + j] * 4] = 1;
+                    }
+                }
+                const uint32_t *pu = p + bit_words;
+                for (size_t k = 0; k < n1; ++k) row[(size_t)uw[k] * 4] = (uint64_t)pu[2 * k] | ((uint64_t)pu[2 * k + 1] << 32);
+                const uint32_t *pf = pu + 2 * n1;
+                for (size_t k = 0; k < n2; ++k) memcpy(&row[(size_t)fw[k] * 4], pf + 8 * k, 32);
+            }
+        });
+    for (auto &x : th) x.join();
+    *done = true;
+    return CW_OK;
+}
+
 int cw_batch_get_witness(cw_batch *b, uint64_t *out) {
     if (!b || !out) return fail(CW_EINVAL, "null argument");
     if (!b->ran) return fail(CW_ESTATE, "batch has not been run");
     const Tape &t = b->c->tape;
     CU(cudaSetDevice(b->device));
+    bool done = false;
+    int rc = get_witness_packed(b, out, &done);
+    if (rc) return rc;
+    if (done) return CW_OK;
+    b->last_d2h_bytes = (uint64_t)b->batch * t.n_witness * 32;
     if (b->bt_log2 == 0) {  // rows are read in place: pitched device-to-host copy
         CU(cudaMemcpy2DAsync(out, (size_t)t.n_witness * 32, b->slots, (size_t)t.n_slots * 32, (size_t)t.n_witness * 32,
                              b->batch, cudaMemcpyDeviceToHost, b->stream));
     } else {
-        int rc = compact_witness(b);
+        rc = compact_witness(b);
         if (rc) return rc;
         CU(cudaMemcpyAsync(out, b->witness_d, (size_t)b->batch * t.n_witness * 32, cudaMemcpyDeviceToHost, b->stream));
     }
     CU(cudaStreamSynchronize(b->stream));
     return CW_OK;
 }
+
+uint64_t cw_batch_last_d2h_bytes(const cw_batch *b) { return b ? b->last_d2h_bytes : 0; }
 
 int cw_batch_witness_device(cw_batch *b, const uint64_t **dptr) {
     if (!b || !dptr) return fail(CW_EINVAL, "null argument");

@@ -216,6 +216,56 @@ __global__ void witness_compact_kernel(const uint4 *__restrict__ slots, uint4 *_
     }
 }
 
+// ---- packed witness for the device->host transfer -------------------------------------------------------
+// Most witness entries of real circuits are bits or 64-bit limbs stored as 32-byte field elements.  The
+// lowering knows an upper bound of every entry's bit length (range analysis); entries proven to be one bit
+// travel as one bit, entries proven <= 64 bits as 8 bytes, the rest as 32 bytes, and the host expands them
+// back to the canonical 32-byte rows.  Each value is re-checked here against its class: a violation raises
+// `flag` and the caller falls back to the plain copy.  Per-instance packed layout (32-bit words):
+// [bit words][u64 entries][full entries].  BT = 1 layout only.
+__global__ void witness_pack_kernel(const uint4 *__restrict__ slots, u32 n_slots, const u32 *__restrict__ bit_wire,
+                                    u32 n_bits, const u32 *__restrict__ u64_wire, u32 n_u64,
+                                    const u32 *__restrict__ full_wire, u32 n_full, u32 *__restrict__ packed,
+                                    size_t words_per_inst, u32 batch, int *__restrict__ flag) {
+    const u32 n_bit_words = (n_bits + 31u) >> 5;
+    const size_t items = (size_t)n_bit_words + n_u64 + n_full;
+    for (u32 inst = blockIdx.y; inst < batch; inst += gridDim.y) {
+        const uint4 *base = slots + (size_t)inst * n_slots * 2;
+        u32 *out = packed + (size_t)inst * words_per_inst;
+        for (size_t it = blockIdx.x * (size_t)blockDim.x + threadIdx.x; it < items; it += (size_t)gridDim.x * blockDim.x) {
+            if (it < n_bit_words) {
+                u32 word = 0, bad = 0;
+                const u32 j0 = (u32)it << 5;
+#pragma unroll 4
+                for (u32 j = 0; j < 32u; ++j) {
+                    if (j0 + j < n_bits) {
+                        const u32 w = __ldg(&bit_wire[j0 + j]);
+                        const uint4 lo = base[2 * (size_t)w], hi = base[2 * (size_t)w + 1];
+                        bad |= lo.y | lo.z | lo.w | hi.x | hi.y | hi.z | hi.w | (lo.x & ~1u);
+                        word |= (lo.x & 1u) << j;
+                    }
+                }
+                out[it] = word;
+                if (bad) *flag = 1;
+            } else if (it < (size_t)n_bit_words + n_u64) {
+                const u32 k = (u32)(it - n_bit_words);
+                const u32 w = __ldg(&u64_wire[k]);
+                const uint4 lo = base[2 * (size_t)w], hi = base[2 * (size_t)w + 1];
+                if (lo.z | lo.w | hi.x | hi.y | hi.z | hi.w) *flag = 1;
+                out[n_bit_words + 2 * (size_t)k] = lo.x;
+                out[n_bit_words + 2 * (size_t)k + 1] = lo.y;
+            } else {
+                const u32 k = (u32)(it - n_bit_words - n_u64);
+                const u32 w = __ldg(&full_wire[k]);
+                const uint4 lo = base[2 * (size_t)w], hi = base[2 * (size_t)w + 1];
+                u32 *o = out + n_bit_words + 2 * (size_t)n_u64 + 8 * (size_t)k;
+                o[0] = lo.x; o[1] = lo.y; o[2] = lo.z; o[3] = lo.w;
+                o[4] = hi.x; o[5] = hi.y; o[6] = hi.z; o[7] = hi.w;
+            }
+        }
+    }
+}
+
 // ---- R1CS check: A.w * B.w == C.w for every row and instance ------------------------------------
 // CSR: row_ptr[3m+1] (A, B, C blocks per row), col[nnz] (wire), coef[nnz] (dictionary index).
 // Per dictionary entry: dictM = coefficient * R mod q and a kind word

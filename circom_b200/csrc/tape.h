@@ -47,6 +47,8 @@ struct Tape {
     std::vector<U256> consts;           // raw limb patterns (already in the form the consumer needs)
     std::vector<uint32_t> witness_slot; // per witness entry (identity: witness entry i lives in slot i)
     std::vector<uint32_t> input_slot;   // slot of main input i
+    // witness entries by static size class, for the packed device->host transfer
+    std::vector<uint32_t> pk_bit_wire, pk_u64_wire, pk_full_wire;
     // circom functions (data-dependent control flow): register-machine code, per-function
     // {code offset, n_instr, n_regs, n_params}, and the per-call tables {function, n_args, arg operands...}
     std::vector<uint32_t> fn_code, fn_info, call_tab;

@@ -68,6 +68,7 @@ def _load() -> ctypes.CDLL:
         "cw_batch_sync": (c_int, [P]),
         "cw_batch_status": (c_int, [P, c_void_p]),
         "cw_batch_get_witness": (c_int, [P, c_void_p]),
+        "cw_batch_last_d2h_bytes": (c_uint64, [P]),
         "cw_batch_witness_device": (c_int, [P, POINTER(c_void_p)]),
         "cw_batch_witness_strided": (c_int, [P, POINTER(c_void_p), POINTER(c_uint64)]),
         "cw_batch_stream": (c_void_p, [P]),

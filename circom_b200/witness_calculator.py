@@ -252,6 +252,9 @@ class Batch:
         check(lib.cw_batch_get_witness(self._h, out.ctypes.data))
         return out
 
+    def last_d2h_bytes(self) -> int:
+        return int(lib.cw_batch_last_d2h_bytes(self._h))
+
     def witness_device_ptr(self) -> int:
         p = ctypes.c_void_p()
         check(lib.cw_batch_witness_device(self._h, ctypes.byref(p)))

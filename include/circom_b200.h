@@ -131,6 +131,9 @@ int cw_batch_status(cw_batch *b, int32_t *status);
 /* getWitness(i) for all i and all instances, after Fr_toLongNormal (main.cpp:328-332):
  * out[batch][n_witness][4]; host pointer */
 int cw_batch_get_witness(cw_batch *b, uint64_t *out);
+/* bytes that crossed PCIe in the last cw_batch_get_witness (entries proven to be bits / 64-bit values travel
+ * packed and are zero-extended on the host; CW_PACKED_D2H=0 disables) */
+uint64_t cw_batch_last_d2h_bytes(const cw_batch *b);
 /* device pointer of the same array (valid until the next run / destroy) */
 int cw_batch_witness_device(cw_batch *b, const uint64_t **dptr);
 /* zero-copy view: witness row i starts at dptr + i*stride_elems*4 uint64 (the tape writes witness entries into

@@ -191,3 +191,27 @@ def test_r1cs_first_violated_row_matches_oracle():
     fb, _ = r.check(batch)
     exp = orc.r1cs_check(batch)
     assert (exp >= 0).all() and fb.tolist() == exp.tolist()
+
+
+def test_packed_device_to_host_transfer_equals_plain_copy(monkeypatch):
+    """witness entries proven to be bits / 64-bit values cross PCIe packed and are zero-extended on the
+    host: the host array must equal the plain pitched copy, with fewer bytes transferred"""
+    d = CircuitDesc("bn128")
+    d.set_main(C.ecdsa_scale(d, 2, 3))
+    c = Circuit(d)
+    rng = random.Random(2)
+    ins = [{"a": [rng.randrange(2**64) for _ in range(8)], "b": [rng.randrange(2**64) for _ in range(8)]} for _ in range(37)]
+    b = Batch(c, len(ins))
+    b.set_inputs(flat_inputs(d, ins))
+    b.run()
+    monkeypatch.setenv("CW_PACKED_D2H", "0")
+    plain = b.witness().copy()
+    plain_bytes = b.last_d2h_bytes()
+    monkeypatch.setenv("CW_PACKED_D2H", "1")
+    packed = b.witness().copy()
+    packed_bytes = b.last_d2h_bytes()
+    assert (plain == packed).all()
+    assert plain_bytes == len(ins) * c.n_witness * 32 and packed_bytes * 4 < plain_bytes
+    w2s = c.witness2signal().astype(np.int64)
+    exp = evaluate(d, ins[5])
+    assert limbs_to_ints(packed[5]) == [exp[k] for k in w2s]

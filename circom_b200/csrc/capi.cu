@@ -2,6 +2,7 @@
 // sm_100a kernels (kernels.cuh).  There is no CPU execution path: every compute entry point
 // returns CW_ENODEV when no CUDA device is present.
 #include <cuda_runtime.h>
+#include <emmintrin.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -569,31 +570,46 @@ static int get_witness_packed(cw_batch *b, uint64_t *out, bool *done) {
     CU(cudaStreamSynchronize(b->stream));
     if (flag) return CW_OK;  // a value exceeded its static class (never expected): caller does the plain copy
     b->last_d2h_bytes = bytes;
-    // host-side expansion, one instance per task
-    const uint32_t *bw = t.pk_bit_wire.data(), *uw = t.pk_u64_wire.data(), *fw = t.pk_full_wire.data();
+    // host-side expansion: one sequential pass per instance over the witness entries, each 32-byte row
+    // written exactly once with streaming stores (the three packed streams are in witness order)
+    const uint8_t *cls = t.wit_class.data();
     const size_t W = t.n_witness;
-    unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)env_int("CW_UNPACK_THREADS", 32)));
+    unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)env_int("CW_UNPACK_THREADS", 16)));
     nt = std::min<unsigned>(nt, b->batch);
+    const bool aligned = (((uintptr_t)out) & 15u) == 0;
     std::vector<std::thread> th;
     for (unsigned tid = 0; tid < nt; ++tid)
         th.emplace_back([=]() {
             for (uint32_t inst = tid; inst < b->batch; inst += nt) {
                 const uint32_t *p = b->packed_h + (size_t)inst * words;
+                const uint32_t *pu = p + bit_words, *pf = pu + 2 * n1;
                 uint64_t *row = out + (size_t)inst * W * 4;
-                memset(row, 0, W * 32);
-                for (size_t wd = 0; wd < bit_words; ++wd) {
-                    uint32_t x = p[wd];
-                    while (x) {
-                        int j = __builtin_ctz(x);
-                        x &= x - 1;
-                        row[(size_t)bw[wd * 32 + j] * 4] = 1;
+                size_t bi = 0, ui = 0, fi = 0;
+                const __m128i zero = _mm_setzero_si128();
+                for (size_t i = 0; i < W; ++i) {
+                    __m128i lo, hi = zero;
+                    const uint8_t cl = cls[i];
+                    if (cl == 0) {
+                        lo = _mm_cvtsi64_si128((long long)((p[bi >> 5] >> (bi & 31)) & 1u));
+                        ++bi;
+                    } else if (cl == 1) {
+                        lo = _mm_cvtsi64_si128((long long)((uint64_t)pu[2 * ui] | ((uint64_t)pu[2 * ui + 1] << 32)));
+                        ++ui;
+                    } else {
+                        lo = _mm_loadu_si128((const __m128i *)(pf + 8 * fi));
+                        hi = _mm_loadu_si128((const __m128i *)(pf + 8 * fi + 4));
+                        ++fi;
+                    }
+                    if (aligned) {
+                        _mm_stream_si128((__m128i *)(row + 4 * i), lo);
+                        _mm_stream_si128((__m128i *)(row + 4 * i + 2), hi);
+                    } else {
+                        _mm_storeu_si128((__m128i *)(row + 4 * i), lo);
+                        _mm_storeu_si128((__m128i *)(row + 4 * i + 2), hi);
                     }
                 }
-                const uint32_t *pu = p + bit_words;
-                for (size_t k = 0; k < n1; ++k) row[(size_t)uw[k] * 4] = (uint64_t)pu[2 * k] | ((uint64_t)pu[2 * k + 1] << 32);
-                const uint32_t *pf = pu + 2 * n1;
-                for (size_t k = 0; k < n2; ++k) memcpy(&row[(size_t)fw[k] * 4], pf + 8 * k, 32);
             }
+            _mm_sfence();
         });
     for (auto &x : th) x.join();
     *done = true;

@@ -900,9 +900,9 @@ struct Lowerer {
             // static size class of the entry (range analysis): 1 bit / <= 64 bits / full.  Used only to pack
             // the device->host transfer of witnesses; the pack kernel re-checks every value at run time.
             uint32_t wb = vbits(v);
-            if (wb <= 1) T.pk_bit_wire.push_back((uint32_t)i);
-            else if (wb <= 64) T.pk_u64_wire.push_back((uint32_t)i);
-            else T.pk_full_wire.push_back((uint32_t)i);
+            if (wb <= 1) { T.pk_bit_wire.push_back((uint32_t)i); T.wit_class.push_back(0); }
+            else if (wb <= 64) { T.pk_u64_wire.push_back((uint32_t)i); T.wit_class.push_back(1); }
+            else { T.pk_full_wire.push_back((uint32_t)i); T.wit_class.push_back(2); }
         }
         size_t n_prov = pops.size() / 4;
         std::vector<uint8_t> live(n_pre + n_prov, 0);

@@ -49,6 +49,7 @@ struct Tape {
     std::vector<uint32_t> input_slot;   // slot of main input i
     // witness entries by static size class, for the packed device->host transfer
     std::vector<uint32_t> pk_bit_wire, pk_u64_wire, pk_full_wire;
+    std::vector<uint8_t> wit_class;  // per witness entry: 0 bit, 1 <= 64 bits, 2 full
     // circom functions (data-dependent control flow): register-machine code, per-function
     // {code offset, n_instr, n_regs, n_params}, and the per-call tables {function, n_args, arg operands...}
     std::vector<uint32_t> fn_code, fn_info, call_tab;

@@ -956,12 +956,15 @@ struct Lowerer {
             else if (!is_assert_op(pops[(size_t)order[r] * 4])) remap[p] = next_tmp++;
         }
         if (next_tmp >= (1u << 24)) throw std::runtime_error("circuit too large for the packed tape word (2^24 slots)");
-        T.ops.resize(n_live * 4);
+        T.ops.clear();
+        T.ops.reserve(n_live * 4);
         T.level_start.assign(max_level + 1, 0);
         T.n_mul_ops = 0;
+        uint32_t prev_level = 0;
         for (size_t r = 0; r < order.size(); ++r) {
             const uint32_t *o = &pops[(size_t)order[r] * 4];
-            uint32_t *d = &T.ops[r * 4];
+            const uint32_t lvl = slot_level[n_pre + order[r]];
+            uint32_t d[4];
             uint32_t dst = is_assert_op(o[0]) ? 0u : remap[n_pre + order[r]];
             d[0] = o[0] | (dst << 8);  // opcode in bits 0-7, destination slot in bits 8-31
             if (o[0] == 45) {
@@ -974,17 +977,31 @@ struct Lowerer {
                     uint32_t a = pcalls[o[1] + 2 + k];
                     T.call_tab.push_back((a & OPERAND_CONST) ? a : remap[a]);
                 }
-                T.level_start[slot_level[n_pre + order[r]]]++;
-                continue;
+            } else {
+                for (int k = 1; k <= 3; ++k) {
+                    if (k == 3 && c_is_immediate(o[0])) d[k] = o[k];  // immediate: IR assert number / bit-field spec
+                    else if (o[k] == NO_SLOT) d[k] = OPERAND_CONST;  // unused operand: constant 0 (never read for its value)
+                    else if (o[k] & OPERAND_CONST) d[k] = o[k];
+                    else d[k] = remap[o[k]];
+                }
             }
-            for (int k = 1; k <= 3; ++k) {
-                if (k == 3 && c_is_immediate(o[0])) d[k] = o[k];  // immediate: IR assert number / bit-field spec
-                else if (o[k] == NO_SLOT) d[k] = OPERAND_CONST;  // unused operand: constant 0 (never read for its value)
-                else if (o[k] & OPERAND_CONST) d[k] = o[k];
-                else d[k] = remap[o[k]];
+            // runs of single-bit extractions of one source into consecutive slots (the bits of a decomposition
+            // are consecutive witness entries) become ONE tape op that writes the whole run: imm bits 24-31 hold
+            // (run length - 1).  One thread then fetches the source word once and streams out up to 16 slots.
+            if (o[0] == DOP_BITS && !(flags & CW_FLAG_NO_PEEPHOLE) && lvl == prev_level && !T.ops.empty()) {
+                uint32_t *p = &T.ops[T.ops.size() - 4];
+                if ((p[0] & 0xFFu) == DOP_BITS && p[1] == d[1] && ((p[3] >> 16) & 0xFFu) == 1u && ((d[3] >> 16) & 0xFFu) == 1u) {
+                    uint32_t cnt = (p[3] >> 24) + 1u, pk = p[3] & 0xFFFFu, pdst = p[0] >> 8;
+                    if (cnt < 16u && (d[3] & 0xFFFFu) == pk + cnt && dst == pdst + cnt) {
+                        p[3] += 1u << 24;
+                        continue;
+                    }
+                }
             }
+            prev_level = lvl;
+            T.ops.insert(T.ops.end(), d, d + 4);
             if (o[0] == CW_OP_MUL) ++T.n_mul_ops;
-            T.level_start[slot_level[n_pre + order[r]]]++;  // count per level (levels start at 1)
+            T.level_start[lvl]++;  // count per level (levels start at 1)
         }
         // prefix sums: level_start[l-1] = first op of level l
         {

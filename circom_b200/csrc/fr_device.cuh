@@ -505,7 +505,7 @@ CW_HD void u256_mul_lo(u32 *r, const u32 *a, const u32 *b) {
     u256_set(r, t);
 }
 CW_HD void u256_bits(u32 *r, const u32 *a, u32 imm) {
-    u32 k = imm & 0xFFFFu, m = imm >> 16;
+    u32 k = imm & 0xFFFFu, m = (imm >> 16) & 0xFFu;
     u32 t[8];
     u256_shr(t, a, k);
 #pragma unroll

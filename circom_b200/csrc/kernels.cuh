@@ -145,20 +145,30 @@ __global__ void __launch_bounds__(1024) tape_exec_kernel(TapeDev tp, uint4 *__re
                 int e = 0;
                 exec_call<PRIME>(tp, opw.y, base, bt_log2, li, r, &e);
                 if (e && inst < batch) err[inst] = 1;
-            } else if (opcode == OP_BITS && (opw.w >> 16) <= 32u && !(opw.y & 0x80000000u)) {
+            } else if (opcode == OP_BITS && ((opw.w >> 16) & 0xFFu) <= 32u && !(opw.y & 0x80000000u)) {
                 // narrow bit-field of a slot value: fetch only the one or two 32-bit words that hold it
-                const u32 k = opw.w & 0xFFFFu, m = opw.w >> 16, wd = k >> 5, sh = k & 31u;
+                const u32 k = opw.w & 0xFFFFu, m = (opw.w >> 16) & 0xFFu, run = (opw.w >> 24) + 1u;
+                const u32 wd = k >> 5, sh = k & 31u;
                 const u32 *words = reinterpret_cast<const u32 *>(base);
                 const size_t e0 = ((((size_t)opw.y << (bt_log2 + 1)) + ((size_t)(wd >> 2) << bt_log2) + li) << 2) + (wd & 3u);
                 const u32 lo = words[e0];
                 u32 hi = 0;
-                if (sh + m > 32u && wd < 7u) {
+                if (sh + m + run - 1u > 32u && wd < 7u) {
                     const u32 w1 = wd + 1u;
                     hi = words[((((size_t)opw.y << (bt_log2 + 1)) + ((size_t)(w1 >> 2) << bt_log2) + li) << 2) + (w1 & 3u)];
                 }
-                r[0] = __funnelshift_r(lo, hi, sh) & (m >= 32u ? 0xFFFFFFFFu : ((1u << m) - 1u));
+                const unsigned long long window = (((unsigned long long)hi << 32) | lo) >> sh;
 #pragma unroll
                 for (int i = 1; i < 8; ++i) r[i] = 0;
+                // a run writes `run` consecutive slots, one bit each (run == 1: the plain field)
+                for (u32 j = 0; j + 1u < run; ++j) {
+                    r[0] = (u32)(window >> j) & 1u;
+                    store_slot(r, base, dst + j, bt_log2, li);
+                }
+                r[0] = run > 1u ? ((u32)(window >> (run - 1u)) & 1u)
+                                : ((u32)window & (m >= 32u ? 0xFFFFFFFFu : ((1u << m) - 1u)));
+                store_slot(r, base, dst + run - 1u, bt_log2, li);
+                continue;
             } else {
                 u32 a[8], b[8];
                 load_operand(a, opw.y, base, tp.consts, bt_log2, li);

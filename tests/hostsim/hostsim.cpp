@@ -89,6 +89,14 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
             }
             operand(op[1], a);
             operand(op[2], b);
+            if (op[0] == OP_BITS && (op[3] >> 24)) {  // run of single-bit extractions into consecutive slots
+                u32 run = (op[3] >> 24) + 1u, k = op[3] & 0xFFFFu;
+                for (u32 j = 0; j < run; ++j) {
+                    u256_bits(r, a, (k + j) | (1u << 16));
+                    memcpy(&slots[((size_t)dst + j) * 8], r, 32);
+                }
+                continue;
+            }
             if (op[0] == OP_SELECT) {
                 u32 c[8];
                 operand(op[3], c);
@@ -140,9 +148,12 @@ int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
             uint32_t opc = t.ops[(size_t)i * 4] & 0xFFu, dst = t.ops[(size_t)i * 4] >> 8;
             bool is_assert = opc == OP_ASSERT || opc == OP_ASSERT_EQ || opc == OP_ASSERT_BOOL || opc == OP_ASSERT_FITS;
             if (is_assert) continue;
-            if (dst >= t.n_slots) { g_err = "destination out of range"; return -6; }
-            if (++writes[dst] > 1) { g_err = "slot written twice"; return -7; }
-            lvl[dst] = (uint32_t)l + 1;
+            uint32_t run = opc == OP_BITS ? (t.ops[(size_t)i * 4 + 3] >> 24) + 1u : 1u;
+            for (uint32_t j = 0; j < run; ++j) {
+                if (dst + j >= t.n_slots) { g_err = "destination out of range"; return -6; }
+                if (++writes[dst + j] > 1) { g_err = "slot written twice"; return -7; }
+                lvl[dst + j] = (uint32_t)l + 1;
+            }
         }
     writes[0]++;
     for (uint64_t k = 0; k < t.n_inputs; ++k) writes[t.input_slot[k]]++;

@@ -118,7 +118,10 @@ __device__ __noinline__ void exec_call(const TapeDev &tp, u32 call_off, const ui
 // HAS_CALLS selects the build that contains the function interpreter (more registers, a local-memory
 // frame); tapes without calls - all circuits whose hints are straight-line - use the lean build.
 template <int PRIME, bool HAS_CALLS>
-__global__ void __launch_bounds__(1024) tape_exec_kernel(TapeDev tp, uint4 *__restrict__ slots, u32 bt_log2,
+#ifndef CW_TAPE_LB
+#define CW_TAPE_LB 1024
+#endif
+__global__ void __launch_bounds__(CW_TAPE_LB) tape_exec_kernel(TapeDev tp, uint4 *__restrict__ slots, u32 bt_log2,
                                                          u32 *__restrict__ first_assert, int *__restrict__ err,
                                                          u32 batch) {
     const FrParams &P = c_fr[PRIME];

@@ -339,7 +339,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, wall_ms, exec_ms, gather_ms = [float(x) for x in t.tolist()]
     status = b.status()
-    assert not status.any(), "witness generation reported failing asserts: %r" % status[:8]
+    # CW_BENCH_NOCHECK: only for the diagnostic kernel builds of scripts/sweep_wrap.sh (garbage results)
+    assert os.environ.get("CW_BENCH_NOCHECK") or not status.any(), "witness generation reported failing asserts: %r" % status[:8]
 
     # ---- end to end through the API with host buffers --------------------------------------------
     e2e_steps = min(args.steps, 3) if args.e2e_steps < 0 else args.e2e_steps

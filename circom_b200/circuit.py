@@ -340,11 +340,14 @@ class Template:
 
     def _record_constraint(self, lhs: Expr, rhs: Expr) -> None:
         q = self.q
-        # lhs - rhs == 0  as  A*B - C == 0
+        # The reference forms E = lhs - rhs (sub = add(lhs, -1 * rhs); a constant times a quadratic a*b + c scales
+        # a and c, algebra.rs:387-395,441-450) and stores A = E.a, B = E.b, C = -E.c
+        # (transform_expression_to_constraint_form, algebra.rs:113-145).  Same normal form here, so that the
+        # coefficients of the written .r1cs are the reference's (`out <== x*y` is (-x) * y = -out).
         if lhs.quad is not None and rhs.lin is not None:
             A, B, C = lhs.quad[0], lhs.quad[1], _lin_add(rhs.lin, lhs.quad[2], q, -1)
         elif rhs.quad is not None and lhs.lin is not None:
-            A, B, C = rhs.quad[0], rhs.quad[1], _lin_add(lhs.lin, rhs.quad[2], q, -1)
+            A, B, C = _lin_scale(rhs.quad[0], q - 1, q), rhs.quad[1], _lin_add(rhs.quad[2], lhs.lin, q, -1)
         elif lhs.lin is not None and rhs.lin is not None:
             A, B, C = {}, {}, _lin_add(rhs.lin, lhs.lin, q, -1)
         else:

@@ -21,6 +21,7 @@
 
 using namespace cw;
 
+static_assert(cw::RING_N == cw::CW_RING_SIZE, "kernel ring size must match the lowering's");
 namespace {
 
 thread_local std::string g_err;
@@ -244,6 +245,8 @@ int cw_circuit_stats(const cw_circuit *c, cw_stats *o) {
     o->n_mul_ops = t.n_mul_ops;
     o->n_conv_ops = t.n_conv_ops;
     o->max_level_width = t.max_level_width;
+    o->n_slot_operands = t.n_slot_operands;
+    o->n_ring_operands = t.n_ring_operands;
     return CW_OK;
 }
 
@@ -481,13 +484,24 @@ int cw_batch_run(cw_batch *b) {
     if (tp.n_levels) {
         const bool calls = !t.call_tab.empty();
         const u32 th = calls ? std::min<u32>(b->threads, 256u) : b->threads;  // the interpreter build has a large frame
+        // The shared-memory forwarding ring (kernels.cuh) is opt-in (env CW_RING=1; BT = 1 layouts): measured on
+        // B200 it does not shorten the step (21.99 ms with, 21.51 ms without, batch 1024 of the bench circuit -
+        // operand latency is not what bounds the interpreter) and its 16 KB per CTA come out of L1.
+        const bool ring = !calls && b->bt_log2 == 0 && env_int("CW_RING", 0) != 0;
+        const size_t smem = ring ? (size_t)2 * RING_N * sizeof(uint4) : 0;
+#define CW_LAUNCH_TAPE(PR, CALLS, RING_)                                                                      \
+    tape_exec_kernel<PR, CALLS, RING_><<<tiles, th, smem, b->stream>>>(tp, b->slots, b->bt_log2, b->first_assert_d, \
+                                                                         b->err_d, b->batch)
         if (t.F.prime_id == 0) {
-            if (calls) tape_exec_kernel<0, true><<<tiles, th, 0, b->stream>>>(tp, b->slots, b->bt_log2, b->first_assert_d, b->err_d, b->batch);
-            else tape_exec_kernel<0, false><<<tiles, th, 0, b->stream>>>(tp, b->slots, b->bt_log2, b->first_assert_d, b->err_d, b->batch);
+            if (calls) CW_LAUNCH_TAPE(0, true, false);
+            else if (ring) CW_LAUNCH_TAPE(0, false, true);
+            else CW_LAUNCH_TAPE(0, false, false);
         } else {
-            if (calls) tape_exec_kernel<1, true><<<tiles, th, 0, b->stream>>>(tp, b->slots, b->bt_log2, b->first_assert_d, b->err_d, b->batch);
-            else tape_exec_kernel<1, false><<<tiles, th, 0, b->stream>>>(tp, b->slots, b->bt_log2, b->first_assert_d, b->err_d, b->batch);
+            if (calls) CW_LAUNCH_TAPE(1, true, false);
+            else if (ring) CW_LAUNCH_TAPE(1, false, true);
+            else CW_LAUNCH_TAPE(1, false, false);
         }
+#undef CW_LAUNCH_TAPE
     }
     CU(cudaEventRecord(b->ev[1], b->stream));
     b->compact_valid = false;  // witness rows are slots [0, n_witness) of each instance: nothing to gather

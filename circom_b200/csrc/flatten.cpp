@@ -362,6 +362,9 @@ struct Lowerer {
             if (const_pow2(b, k)) x = a;
             else if (const_pow2(a, k)) x = b;
             if (x >= 0 && !is_const(x) && k == 0) return x;  // x * 1
+            // x * 0 (polynomial evaluations at the point 0): the constant itself
+            if (a >= 0 && b >= 0 && is_const(a) != is_const(b) && is_const_zero(is_const(a) ? a : b))
+                return is_const(a) ? a : b;
             if (x >= 0 && !is_const(x) && vals[x].fld_src >= 0 && vals[x].fld_k == k && k + vals[x].fld_m <= 256) {
                 Val nv;  // ((src >> k) & mask) << k  ==  src & (mask << k)
                 nv.bf_src = vals[x].fld_src;
@@ -375,7 +378,9 @@ struct Lowerer {
                 return new_val(emit(CW_OP_SHL, need(x, FC), OPERAND_CONST | raw_const(kc)), FC);
             }
             // small * small with the integer product < q: plain product, no reduction
-            if (!is_const(a) && !is_const(b) && has(a, FC) && has(b, FC) && vbits(a) + vbits(b) <= qb() - 1)
+            // (one factor may be a constant: polynomial evaluation points, limb weights)
+            if (a >= 0 && b >= 0 && !(is_const(a) && is_const(b)) && (is_const(a) || has(a, FC)) &&
+                (is_const(b) || has(b, FC)) && vbits(a) + vbits(b) <= qb() - 1)
                 return new_val(emit(DOP_MULSMALL, need(a, FC), need(b, FC)), FC);
         }
         return -1;
@@ -1016,6 +1021,43 @@ struct Lowerer {
             ls[max_level] = acc;
             T.level_start.swap(ls);
             T.max_level_width = widest;
+        }
+        // Shared-memory forwarding.  The interpreter keeps, per instance, a ring of the CW_RING_SIZE most recent
+        // results (index = destination slot % CW_RING_SIZE; temporaries are numbered in tape order, so they walk
+        // the ring sequentially; multi-slot bit runs bypass it).  An operand may be read from the ring iff its
+        // entry still belongs to it when the consumer's level ends - other work items of that level may already
+        // have deposited their results when the consumer reads.  Slots are written once, so "the owner of the
+        // index after all writes of the consumer's level is still this slot" is exactly that condition.
+        {
+            const uint32_t M = CW_RING_SIZE - 1;
+            // Two deposits of ONE level into the same index land in an unknown order: that index is unusable
+            // until a later level writes it again.
+            std::vector<uint32_t> owner(CW_RING_SIZE, NO_SLOT), stamp(CW_RING_SIZE, NO_SLOT);
+            T.n_slot_operands = T.n_ring_operands = 0;
+            for (size_t l = 0; l + 1 < T.level_start.size(); ++l) {
+                for (uint32_t i = T.level_start[l]; i < T.level_start[l + 1]; ++i) {
+                    const uint32_t *o = &T.ops[(size_t)i * 4];
+                    const uint32_t opc = o[0] & 0xFFu;
+                    if (is_assert_op(opc) || (opc == DOP_BITS && (o[3] >> 24))) continue;
+                    const uint32_t idx = (o[0] >> 8) & M;
+                    owner[idx] = stamp[idx] == (uint32_t)l ? NO_SLOT : o[0] >> 8;
+                    stamp[idx] = (uint32_t)l;
+                }
+                for (uint32_t i = T.level_start[l]; i < T.level_start[l + 1]; ++i) {
+                    uint32_t *o = &T.ops[(size_t)i * 4];
+                    const uint32_t opc = o[0] & 0xFFu;
+                    if (opc == 45) continue;  // call arguments are read through the call table
+                    for (int k = 1; k <= 3; ++k) {
+                        if (k == 3 && c_is_immediate(opc)) break;
+                        if (o[k] & OPERAND_CONST) continue;
+                        ++T.n_slot_operands;
+                        if (owner[o[k] & M] == o[k]) {
+                            o[k] |= OPERAND_RING;
+                            ++T.n_ring_operands;
+                        }
+                    }
+                }
+            }
         }
         T.witness_slot.resize(W);
         for (uint64_t i = 0; i < W; ++i) T.witness_slot[i] = (uint32_t)i;

@@ -107,7 +107,7 @@ __device__ __noinline__ void exec_call(const TapeDev &tp, u32 call_off, const ui
     for (u32 k = 0; k < fi.n_regs * 8; ++k) regs[k] = 0;
     for (u32 k = 0; k < n_args; ++k) {
         u32 v[8];
-        load_operand(v, __ldg(&ct[2 + k]), base, tp.consts, bt_log2, li);
+        load_operand(v, __ldg(&ct[2 + k]), base, tp.consts, bt_log2, li);  // call-table operands carry no ring flag
         for (int j = 0; j < 8; ++j) regs[8 * k + j] = v[j];
     }
     int e = 0;
@@ -115,15 +115,43 @@ __device__ __noinline__ void exec_call(const TapeDev &tp, u32 call_off, const ui
     *err = e;
 }
 
+// Shared-memory forwarding ring (BT = 1 layouts): every single-value result is also deposited at
+// ring[dst % RING_N] (two 16-byte halves in separate arrays: consecutive entries are conflict-free), and an
+// operand the lowering flagged with bit 30 is read from there instead of from L2 - most operands of a level
+// were produced a few levels earlier by the same CTA.  RING_N must equal CW_RING_SIZE of tape.h: the flags
+// are computed for exactly this size.
+constexpr u32 RING_N = 512;
+constexpr u32 OPD_CONST = 0x80000000u, OPD_RING = 0x40000000u, OPD_SLOT = 0x00FFFFFFu;
+
+template <bool RING>
+__device__ __forceinline__ void load_operand_t(u32 *v, u32 operand, const uint4 *__restrict__ tile_base,
+                                               const uint4 *__restrict__ consts, u32 bt_log2, u32 li,
+                                               const uint4 *ring) {
+    if (operand & OPD_CONST) {
+        load_const(v, consts, operand & 0x7FFFFFFFu);
+    } else if (RING && (operand & OPD_RING)) {
+        const u32 i = operand & (RING_N - 1u);
+        const uint4 lo = ring[i], hi = ring[RING_N + i];
+        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+        v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+    } else {
+        load_slot(v, tile_base, operand & OPD_SLOT, bt_log2, li);
+    }
+}
+
 // HAS_CALLS selects the build that contains the function interpreter (more registers, a local-memory
 // frame); tapes without calls - all circuits whose hints are straight-line - use the lean build.
-template <int PRIME, bool HAS_CALLS>
 #ifndef CW_TAPE_LB
 #define CW_TAPE_LB 1024
 #endif
-__global__ void __launch_bounds__(CW_TAPE_LB) tape_exec_kernel(TapeDev tp, uint4 *__restrict__ slots, u32 bt_log2,
-                                                         u32 *__restrict__ first_assert, int *__restrict__ err,
-                                                         u32 batch) {
+#ifndef CW_TAPE_MINB
+#define CW_TAPE_MINB 1
+#endif
+template <int PRIME, bool HAS_CALLS, bool RING>
+__global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
+    tape_exec_kernel(TapeDev tp, uint4 *__restrict__ slots, u32 bt_log2, u32 *__restrict__ first_assert,
+                     int *__restrict__ err, u32 batch) {
+    extern __shared__ uint4 ring[];  // RING: 2 * RING_N entries (16 KB)
     const FrParams &P = c_fr[PRIME];
     const u32 tile = blockIdx.x;
     const u32 bt_mask = (1u << bt_log2) - 1;
@@ -148,37 +176,43 @@ __global__ void __launch_bounds__(CW_TAPE_LB) tape_exec_kernel(TapeDev tp, uint4
                 int e = 0;
                 exec_call<PRIME>(tp, opw.y, base, bt_log2, li, r, &e);
                 if (e && inst < batch) err[inst] = 1;
-            } else if (opcode == OP_BITS && ((opw.w >> 16) & 0xFFu) <= 32u && !(opw.y & 0x80000000u)) {
+            } else if (opcode == OP_BITS && ((opw.w >> 16) & 0xFFu) <= 32u && !(opw.y & OPD_CONST)) {
                 // narrow bit-field of a slot value: fetch only the one or two 32-bit words that hold it
                 const u32 k = opw.w & 0xFFFFu, m = (opw.w >> 16) & 0xFFu, run = (opw.w >> 24) + 1u;
                 const u32 wd = k >> 5, sh = k & 31u;
-                const u32 *words = reinterpret_cast<const u32 *>(base);
-                const size_t e0 = ((((size_t)opw.y << (bt_log2 + 1)) + ((size_t)(wd >> 2) << bt_log2) + li) << 2) + (wd & 3u);
-                const u32 lo = words[e0];
-                u32 hi = 0;
-                if (sh + m + run - 1u > 32u && wd < 7u) {
+                const bool two = sh + m + run - 1u > 32u && wd < 7u;
+                u32 lo, hi = 0;
+                if (RING && (opw.y & OPD_RING)) {
+                    const u32 *rw = reinterpret_cast<const u32 *>(ring);
+                    const u32 i = opw.y & (RING_N - 1u), w1 = wd + 1u;
+                    lo = rw[(((wd >> 2) * RING_N + i) << 2) + (wd & 3u)];
+                    if (two) hi = rw[(((w1 >> 2) * RING_N + i) << 2) + (w1 & 3u)];
+                } else {
+                    const u32 *words = reinterpret_cast<const u32 *>(base);
+                    const size_t src = (size_t)(opw.y & OPD_SLOT) << (bt_log2 + 1);
                     const u32 w1 = wd + 1u;
-                    hi = words[((((size_t)opw.y << (bt_log2 + 1)) + ((size_t)(w1 >> 2) << bt_log2) + li) << 2) + (w1 & 3u)];
+                    lo = words[((src + ((size_t)(wd >> 2) << bt_log2) + li) << 2) + (wd & 3u)];
+                    if (two) hi = words[((src + ((size_t)(w1 >> 2) << bt_log2) + li) << 2) + (w1 & 3u)];
                 }
                 const unsigned long long window = (((unsigned long long)hi << 32) | lo) >> sh;
 #pragma unroll
                 for (int i = 1; i < 8; ++i) r[i] = 0;
-                // a run writes `run` consecutive slots, one bit each (run == 1: the plain field)
-                for (u32 j = 0; j + 1u < run; ++j) {
-                    r[0] = (u32)(window >> j) & 1u;
-                    store_slot(r, base, dst + j, bt_log2, li);
+                if (run > 1u) {
+                    // a run writes `run` consecutive slots, one bit each; runs bypass the ring
+                    for (u32 j = 0; j < run; ++j) {
+                        r[0] = (u32)(window >> j) & 1u;
+                        store_slot(r, base, dst + j, bt_log2, li);
+                    }
+                    continue;
                 }
-                r[0] = run > 1u ? ((u32)(window >> (run - 1u)) & 1u)
-                                : ((u32)window & (m >= 32u ? 0xFFFFFFFFu : ((1u << m) - 1u)));
-                store_slot(r, base, dst + run - 1u, bt_log2, li);
-                continue;
+                r[0] = (u32)window & (m >= 32u ? 0xFFFFFFFFu : ((1u << m) - 1u));
             } else {
                 u32 a[8], b[8];
-                load_operand(a, opw.y, base, tp.consts, bt_log2, li);
-                load_operand(b, opw.z, base, tp.consts, bt_log2, li);
+                load_operand_t<RING>(a, opw.y, base, tp.consts, bt_log2, li, ring);
+                load_operand_t<RING>(b, opw.z, base, tp.consts, bt_log2, li, ring);
                 if (opcode == OP_SELECT) {
                     u32 c[8];
-                    load_operand(c, opw.w, base, tp.consts, bt_log2, li);
+                    load_operand_t<RING>(c, opw.w, base, tp.consts, bt_log2, li, ring);
                     bool t = !u256_is_zero(c);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) r[i] = t ? a[i] : b[i];
@@ -197,6 +231,10 @@ __global__ void __launch_bounds__(CW_TAPE_LB) tape_exec_kernel(TapeDev tp, uint4
                 }
             }
             store_slot(r, base, dst, bt_log2, li);
+            if (RING) {
+                ring[dst & (RING_N - 1u)] = make_uint4(r[0], r[1], r[2], r[3]);
+                ring[RING_N + (dst & (RING_N - 1u))] = make_uint4(r[4], r[5], r[6], r[7]);
+            }
         }
         if (threadIdx.x < ((le_next - le) << bt_log2)) pre = __ldg(&tp.ops[le + (threadIdx.x >> bt_log2)]);
         lb = le;
@@ -379,7 +417,14 @@ __global__ void __launch_bounds__(256) r1cs_check_kernel(R1csDev R, const uint4 
             if ((!ha && a[0] == 0) || (!hb && b[0] == 0)) ok = u256_is_zero(c);
             else if (!ha && a[0] == 1) ok = u256_eq(b, c);
             else if (!hb && b[0] == 1) ok = u256_eq(a, c);
-            else {
+            else if (a[0] + 1u == P.q[0] && a[1] == P.q[1] && a[2] == P.q[2] && a[3] == P.q[3] && a[4] == P.q[4] &&
+                     a[5] == P.q[5] && a[6] == P.q[6] && a[7] == P.q[7]) {
+                // a = -1: rows `out <== x*y` are stored as (-x) * y = -out (the reference's normal form), so a
+                // bit-valued x = 1 lands here: -b == c
+                u32 s[8];
+                fr_add(s, b, c, P);
+                ok = u256_is_zero(s);
+            } else {
                 u32 ab[8], c1[8];
                 fr_mont_mul(ab, a, b, P);  // a*b/R
                 fr_from_mont(c1, c, P);    // c/R

@@ -9,6 +9,12 @@
 namespace cw {
 
 constexpr uint32_t OPERAND_CONST = 0x80000000u;  // operand bit31: index into the constant table
+// operand bit30: the value is also held in the CTA's shared-memory forwarding ring at index (slot % CW_RING_SIZE).
+// Every single-value op deposits its result there; the lowering sets the bit when it can prove that no later
+// write to the same ring index happens before the end of the consumer's level (see flatten.cpp).
+constexpr uint32_t OPERAND_RING = 0x40000000u;
+constexpr uint32_t OPERAND_SLOT_MASK = 0x00FFFFFFu;
+constexpr uint32_t CW_RING_LOG2 = 9, CW_RING_SIZE = 1u << CW_RING_LOG2;
 constexpr uint32_t WSLOT_MONT = 0x80000000u;     // witness_slot bit31: slot holds the Montgomery image
 constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
 
@@ -40,6 +46,7 @@ struct Tape {
     uint32_t flags = 0;
     uint64_t n_signals = 0, n_witness = 0, n_inputs = 0, n_outputs = 0, n_components = 0;
     uint64_t n_ir_ops = 0, n_mul_ops = 0, n_conv_ops = 0, max_level_width = 0, n_asserts = 0;
+    uint64_t n_slot_operands = 0, n_ring_operands = 0;  // operand reads of slots / of which forwarded through the ring
     uint32_t n_pre = 0;    // slot 0 = constant one, slots 1..n_inputs = main inputs
     uint32_t n_slots = 0;  // witness entries [0, n_witness) then the other values
     std::vector<uint32_t> ops;          // 4 words per op: opcode | dst << 8, a, b, c

@@ -25,7 +25,7 @@ class CwStats(ctypes.Structure):
     _fields_ = [(n, c_uint64) for n in (
         "n_signals", "n_witness", "n_inputs", "n_outputs", "n_components", "n_constants", "n_ir_ops",
         "n_tape_ops", "n_slots", "n_levels", "n_constraints", "n_nnz", "n_mul_ops", "n_conv_ops",
-        "max_level_width")] + [("reserved", c_uint64 * 3)]
+        "max_level_width", "n_slot_operands", "n_ring_operands")] + [("reserved", c_uint64 * 1)]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}

@@ -76,7 +76,9 @@ typedef struct cw_stats {
     uint64_t n_mul_ops;      /* Montgomery multiplications in the tape (incl. conversions) */
     uint64_t n_conv_ops;     /* of which representation changes inserted by the lowering */
     uint64_t max_level_width;
-    uint64_t reserved[3];
+    uint64_t n_slot_operands; /* operand reads of value slots in the tape */
+    uint64_t n_ring_operands; /* of which served from the shared-memory forwarding ring */
+    uint64_t reserved[1];
 } cw_stats;
 
 /* ---- library ---------------------------------------------------------------------------- */

@@ -1,0 +1,82 @@
+"""Generates the golden fixtures of tests/golden/: `.wtns` files written by the REFERENCE witness calculators
+(reference runtime common/main.cpp + calcwit.cpp + rendered generic/fr.cpp + the hand-lowered <circuit>.cpp of
+oracle/emit_ref_cpp.py, built by oracle/build_calcs.py into oracle/_ref/calc/) for fixed, seeded inputs.
+
+Run it in a container that has /root/reference (the calculators are built from the reference sources where they
+lie); the fixtures are committed so that the oracle and the GPU path stay pinned to reference outputs on machines
+where the reference tree (and oracle/_ref) is absent.
+
+    python tests/golden/make_golden.py
+
+Layout: <name>.json = {"prime", "inputs": [input.json objects], "sha256": [...]};  <name>_<i>.wtns.z = zlib of the
+bytes the reference binary wrote for inputs[i].
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import random
+import subprocess
+import sys
+import tempfile
+import zlib
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import build_calcs  # noqa: E402
+
+NAMES = ["multiplier2", "all_ops", "all_ops_bls", "less_than8", "poseidon2", "int_div32", "ecdsa_scale_2x5"]
+
+
+def gen_inputs(name: str, d, rng: random.Random):
+    q = d.q
+    if name == "multiplier2":
+        return [{"a": "3", "b": "11"}] + [{"a": str(rng.randrange(q)), "b": str(rng.randrange(q))} for _ in range(3)]
+    if name.startswith("all_ops"):
+        edge = [0, 1, q - 1, (q - 1) // 2, (q - 1) // 2 + 1, 2**31 - 1, 2**31]
+        return [{"a": str(a), "b": str(b)} for a, b in
+                [(edge[i % len(edge)], [0, 1, 5, 255, 13][i % 5]) for i in range(7)] +
+                [(rng.randrange(q), rng.randrange(300)) for _ in range(5)] +
+                [(rng.randrange(2**64), rng.randrange(q)) for _ in range(2)]]
+    if name == "less_than8":
+        return [{"in": [str(a), str(b)]} for a, b in [(0, 0), (255, 0), (0, 255), (17, 17), (200, 201), (201, 200)]]
+    if name == "poseidon2":
+        return [{"inputs": ["1", "2"]}] + [{"inputs": [str(rng.randrange(q)), str(rng.randrange(q))]} for _ in range(2)]
+    if name == "int_div32":
+        return [{"a": str(a), "b": str(b)} for a, b in
+                [(0, 1), (2**32 - 1, 1), (2**32 - 1, 2**32 - 1), (12345678, 1000), (rng.randrange(2**32), rng.randrange(1, 2**16))]]
+    if name.startswith("ecdsa_scale"):
+        n = d.main.n_in // 2
+        return [{"a": [str(rng.getrandbits(64)) for _ in range(n)], "b": [str(rng.getrandbits(64)) for _ in range(n)]}
+                for _ in range(2)] + [{"a": [str(2**64 - 1)] * n, "b": [str(2**64 - 1)] * n}]
+    raise KeyError(name)
+
+
+def main():
+    build_calcs.build(NAMES)
+    for name in NAMES:
+        calc = build_calcs.calc_path(name)
+        assert os.path.exists(calc) and os.path.exists(calc + ".dat"), "reference calculator %s not built" % name
+        d = build_calcs.make_desc(name)
+        rng = random.Random(zlib.crc32(name.encode()))
+        inputs = gen_inputs(name, d, rng)
+        shas = []
+        with tempfile.TemporaryDirectory() as tmp:
+            for i, inp in enumerate(inputs):
+                jp, wp = os.path.join(tmp, "in.json"), os.path.join(tmp, "out.wtns")
+                json.dump(inp, open(jp, "w"))
+                r = subprocess.run([calc, jp, wp], capture_output=True, text=True)
+                assert r.returncode == 0, (name, i, r.stderr[-400:])
+                raw = open(wp, "rb").read()
+                shas.append(hashlib.sha256(raw).hexdigest())
+                open(os.path.join(HERE, "%s_%d.wtns.z" % (name, i)), "wb").write(zlib.compress(raw, 9))
+        json.dump({"prime": d.prime, "inputs": inputs, "sha256": shas},
+                  open(os.path.join(HERE, name + ".json"), "w"), indent=1)
+        print(name, len(inputs), "cases")
+
+
+if __name__ == "__main__":
+    main()

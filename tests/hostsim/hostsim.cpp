@@ -66,51 +66,93 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
             memcpy(&slots[(size_t)t.input_slot[k] * 8], inputs + ((size_t)inst * t.n_inputs + k) * 4, 32);
         uint32_t first_assert = 0xFFFFFFFFu;
         int err = 0;
+        // shared-memory forwarding ring of the device interpreter, emulated with the worst-case ordering: an
+        // operand flagged OPERAND_RING is read from the ring as it was when the level started AND re-checked
+        // after all deposits of the level (another work item of the level may run first on the device)
+        std::vector<u32> ring((size_t)CW_RING_SIZE * 8, 0xBADC0DEu);
+        std::vector<u32> ring_stamp(CW_RING_SIZE, 0xFFFFFFFFu);
+        bool ring_bad = false;
         auto operand = [&](u32 o, u32 *v) {
-            if (o & OPERAND_CONST) memcpy(v, t.consts[o & 0x7FFFFFFFu].v, 32);
-            else memcpy(v, &slots[(size_t)o * 8], 32);
-        };
-        // level order == tape order
-        for (size_t i = 0; i < n_ops; ++i) {
-            const uint32_t *opw = &t.ops[i * 4];
-            const uint32_t op[4] = {opw[0] & 0xFFu, opw[1], opw[2], opw[3]};
-            const uint32_t dst = opw[0] >> 8;
-            u32 a[8], b[8], r[8];
-            if (op[0] == OP_CALL) {  // function call: one work item interprets the body
-                const uint32_t *ct = &t.call_tab[op[1]];
-                FnInfo fi{t.fn_info[ct[0] * 4], t.fn_info[ct[0] * 4 + 1], t.fn_info[ct[0] * 4 + 2], t.fn_info[ct[0] * 4 + 3]};
-                std::vector<u32> regs((size_t)fi.n_regs * 8, 0);
-                for (uint32_t k = 0; k < ct[1]; ++k) operand(ct[2 + k], &regs[(size_t)k * 8]);
-                int e = 0;
-                vm_run(t.fn_code.data(), fi, regs.data(), (const u32 *)t.consts.data(), r, P, e);
-                if (e) err = 1;
-                memcpy(&slots[(size_t)dst * 8], r, 32);
-                continue;
-            }
-            operand(op[1], a);
-            operand(op[2], b);
-            if (op[0] == OP_BITS && (op[3] >> 24)) {  // run of single-bit extractions into consecutive slots
-                u32 run = (op[3] >> 24) + 1u, k = op[3] & 0xFFFFu;
-                for (u32 j = 0; j < run; ++j) {
-                    u256_bits(r, a, (k + j) | (1u << 16));
-                    memcpy(&slots[((size_t)dst + j) * 8], r, 32);
-                }
-                continue;
-            }
-            if (op[0] == OP_SELECT) {
-                u32 c[8];
-                operand(op[3], c);
-                memcpy(r, u256_is_zero(c) ? b : a, 32);
-            } else if (op[0] == OP_ASSERT_EQ || op[0] == OP_ASSERT || op[0] == OP_ASSERT_BOOL || op[0] == OP_ASSERT_FITS) {
-                bool ok = op[0] == OP_ASSERT_EQ ? u256_eq(a, b) : op[0] == OP_ASSERT ? !u256_is_zero(a)
-                          : op[0] == OP_ASSERT_BOOL ? (u256_is_zero(a) || u256_eq(a, b)) : (u256_bitlen(a) <= b[0]);
-                if (!ok && op[3] < first_assert) first_assert = op[3];
-                continue;
+            if (o & OPERAND_CONST) { memcpy(v, t.consts[o & 0x7FFFFFFFu].v, 32); return; }
+            const u32 slot = o & OPERAND_SLOT_MASK;
+            if (o & OPERAND_RING) {
+                memcpy(v, &ring[(size_t)(slot & (CW_RING_SIZE - 1)) * 8], 32);
+                if (memcmp(v, &slots[(size_t)slot * 8], 32)) ring_bad = true;
             } else {
-                fr_exec(op[0], r, a, b, op[3], P, err);
+                memcpy(v, &slots[(size_t)slot * 8], 32);
             }
-            memcpy(&slots[(size_t)dst * 8], r, 32);
+        };
+        std::vector<u32> results;   // results of one level: {dst, 8 words, to_ring}
+        for (size_t l = 0; l < t.n_levels(); ++l) {
+            results.clear();
+            auto put = [&](u32 dst, const u32 *r, bool to_ring) {
+                results.push_back(dst);
+                results.insert(results.end(), r, r + 8);
+                results.push_back(to_ring ? 1u : 0u);
+            };
+            for (size_t i = t.level_start[l]; i < t.level_start[l + 1]; ++i) {
+                const uint32_t *opw = &t.ops[i * 4];
+                const uint32_t op[4] = {opw[0] & 0xFFu, opw[1], opw[2], opw[3]};
+                const uint32_t dst = opw[0] >> 8;
+                u32 a[8], b[8], r[8];
+                if (op[0] == OP_CALL) {  // function call: one work item interprets the body
+                    const uint32_t *ct = &t.call_tab[op[1]];
+                    FnInfo fi{t.fn_info[ct[0] * 4], t.fn_info[ct[0] * 4 + 1], t.fn_info[ct[0] * 4 + 2], t.fn_info[ct[0] * 4 + 3]};
+                    std::vector<u32> regs((size_t)fi.n_regs * 8, 0);
+                    for (uint32_t k = 0; k < ct[1]; ++k) operand(ct[2 + k], &regs[(size_t)k * 8]);
+                    int e = 0;
+                    vm_run(t.fn_code.data(), fi, regs.data(), (const u32 *)t.consts.data(), r, P, e);
+                    if (e) err = 1;
+                    put(dst, r, true);
+                    continue;
+                }
+                operand(op[1], a);
+                operand(op[2], b);
+                if (op[0] == OP_BITS && (op[3] >> 24)) {  // run of single-bit extractions into consecutive slots
+                    u32 run = (op[3] >> 24) + 1u, k = op[3] & 0xFFFFu;
+                    for (u32 j = 0; j < run; ++j) {
+                        u256_bits(r, a, (k + j) | (1u << 16));
+                        put(dst + j, r, false);
+                    }
+                    continue;
+                }
+                if (op[0] == OP_SELECT) {
+                    u32 c[8];
+                    operand(op[3], c);
+                    memcpy(r, u256_is_zero(c) ? b : a, 32);
+                } else if (op[0] == OP_ASSERT_EQ || op[0] == OP_ASSERT || op[0] == OP_ASSERT_BOOL || op[0] == OP_ASSERT_FITS) {
+                    bool ok = op[0] == OP_ASSERT_EQ ? u256_eq(a, b) : op[0] == OP_ASSERT ? !u256_is_zero(a)
+                              : op[0] == OP_ASSERT_BOOL ? (u256_is_zero(a) || u256_eq(a, b)) : (u256_bitlen(a) <= b[0]);
+                    if (!ok && op[3] < first_assert) first_assert = op[3];
+                    continue;
+                } else {
+                    fr_exec(op[0], r, a, b, op[3], P, err);
+                }
+                put(dst, r, true);
+            }
+            for (size_t k = 0; k < results.size(); k += 10) {
+                memcpy(&slots[(size_t)results[k] * 8], &results[k + 1], 32);
+                if (!results[k + 9]) continue;
+                // two deposits of one level into the same ring index arrive in an unknown order on the device:
+                // the entry is garbage from then on
+                const u32 idx = results[k] & (CW_RING_SIZE - 1);
+                if (ring_stamp[idx] == (u32)l) std::fill(&ring[(size_t)idx * 8], &ring[(size_t)idx * 8 + 8], 0xBADC0DEu);
+                else memcpy(&ring[(size_t)idx * 8], &results[k + 1], 32);
+                ring_stamp[idx] = (u32)l;
+            }
+            // the level's own deposits must not have displaced anything the level reads from the ring
+            for (size_t i = t.level_start[l]; i < t.level_start[l + 1]; ++i) {
+                const uint32_t *opw = &t.ops[i * 4];
+                if ((opw[0] & 0xFFu) == OP_CALL) continue;
+                for (int k = 1; k <= 3; ++k) {
+                    if ((opw[k] & OPERAND_CONST) || !(opw[k] & OPERAND_RING)) continue;
+                    if (k == 3 && (opw[0] & 0xFFu) != OP_SELECT) continue;
+                    const u32 slot = opw[k] & OPERAND_SLOT_MASK;
+                    if (memcmp(&ring[(size_t)(slot & (CW_RING_SIZE - 1)) * 8], &slots[(size_t)slot * 8], 32)) ring_bad = true;
+                }
+            }
         }
+        if (ring_bad) { g_err = "forwarding ring: a flagged operand was not (or no longer) in the ring"; return -4; }
         for (uint64_t w = 0; w < t.n_witness; ++w) {
             memcpy(witness + ((size_t)inst * t.n_witness + w) * 4, &slots[(size_t)w * 8], 32);  // slot w IS witness entry w
         }
@@ -162,7 +204,7 @@ int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
     if (t.n_levels() && t.level_start[t.n_levels()] != t.n_tape_ops()) { g_err = "level table does not cover the tape"; return -2; }
     for (size_t i = 0; i < t.n_tape_ops(); ++i) {
         const uint32_t *opw = &t.ops[i * 4];
-        const uint32_t op[4] = {opw[0] & 0xFFu, opw[1], opw[2], opw[3]};
+        uint32_t op[4] = {opw[0] & 0xFFu, opw[1], opw[2], opw[3]};
         if (op[0] == OP_CALL) {
             const uint32_t *ct = &t.call_tab[op[1]];
             for (uint32_t k = 0; k < ct[1]; ++k) {
@@ -175,6 +217,12 @@ int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
         bool c_imm = op[0] == OP_ASSERT || op[0] == OP_ASSERT_EQ || op[0] == OP_ASSERT_BOOL || op[0] == OP_BITS || op[0] == OP_BITSIP || op[0] == OP_ASSERT_FITS;
         for (int k = 1; k <= 3; ++k) {
             if (k == 3 && c_imm) break;
+            if (!(op[k] & OPERAND_CONST)) {
+                if ((op[k] & OPERAND_RING) && (op[k] & OPERAND_SLOT_MASK) < t.n_slots && !lvl[op[k] & OPERAND_SLOT_MASK]) {
+                    g_err = "ring flag on a slot the tape does not write"; return -10;
+                }
+                op[k] &= OPERAND_SLOT_MASK;
+            }
             if (op[k] & OPERAND_CONST) {
                 if ((op[k] & 0x7FFFFFFFu) >= t.consts.size()) { g_err = "constant index out of range"; return -3; }
                 continue;

@@ -81,6 +81,53 @@ def test_written_r1cs_is_satisfied_by_oracle_witness(name, mk, inp, o0, tmp_path
             assert not trivial
 
 
+def _basic_circom(d):
+    """`basic.circom` of the reference's documentation (formats/constraints-json.md:34-50)."""
+    def internal(t):
+        i = t.input("in", 2)
+        out = t.output("out")
+        t.assign_constrained(out, i[0] * i[1])
+    internal_t = d.template("Internal", (), internal)
+
+    def main(t):
+        i = t.input("in", 2)
+        out = t.output("out")
+        c = t.component("c", internal_t)
+        t.assign_constrained(c.sig("in", 0), i[0])
+        t.assign_constrained(c.sig("in", 1), i[1] + 2 * i[0] + 1)
+        t.assign_constrained(out, c.sig("out"))
+    return d.template("Main", (), main)
+
+
+def test_r1cs_of_the_documented_basic_circuit(tmp_path):
+    """The only constraint data pinned anywhere in the reference tree: the R1CS of `basic.circom` printed in
+    formats/constraints-json.md:57-59 (default --O1) and :77-81 (--O0), with the signal -> witness maps of
+    formats/sym.md:50-55 / :69-74.  Wire numbering and every coefficient (q-1 for -1) must agree; the order
+    of the rows is the compiler's DAG order and is compared as a set."""
+    q = 21888242871839275222246405745257275088548364400416034343698204186575808495616 + 1
+    m1 = q - 1
+    doc_o1 = [({2: m1}, {4: 1}, {1: m1}), ({}, {}, {0: 1, 2: 2, 3: 1, 4: m1})]
+    doc_o0 = [({}, {}, {2: 1, 5: m1}), ({}, {}, {0: 1, 2: 2, 3: 1, 6: m1}), ({}, {}, {1: m1, 4: 1}),
+              ({5: m1}, {6: 1}, {4: m1})]
+    sym_o1 = [0, 1, 2, 3, 6]            # witness -> signal: sym.md lines "6,4,0,main.c.in[1]"; 4 and 5 eliminated
+    for o0, doc, sym in ((False, doc_o1, sym_o1), (True, doc_o0, list(range(7)))):
+        d = CircuitDesc("bn128")
+        assert d.q == q
+        d.set_main(_basic_circom(d))
+        c = Circuit(d, host_only=True, o0=o0)
+        assert c.witness2signal().tolist() == sym
+        p = str(tmp_path / ("basic_o%d.r1cs" % (0 if o0 else 1)))
+        R1cs(c).write(p, 1, 0, 2)
+        r = parse_r1cs(open(p, "rb").read())
+        key = lambda row: tuple(tuple(sorted(lc.items())) for lc in row)  # noqa: E731
+        assert sorted(map(key, r["cons"])) == sorted(map(key, doc)), (o0, r["cons"])
+        # and the witness of the documented shape [1, x*(y+2x+1), x, y, y+2x+1] satisfies it
+        x, y = 3, 11
+        sig = evaluate(d, {"in": [x, y]})
+        w = [sig[k] for k in sym]
+        assert w[:4] == [1, x * (y + 2 * x + 1), x, y]
+
+
 def test_constant_and_inputless_circuits():
     """signals that are compile-time constants, a sub-component without inputs (runs at creation,
     template.rs:274-278), two outputs with the same value, an output equal to an input"""

@@ -67,6 +67,22 @@ def test_sha256compression_batch_vs_oracle_and_hashlib():
     assert not st.any() and (ow[:, w2s] == wit[:8]).all()
 
 
+def test_forwarding_ring_build_matches(monkeypatch):
+    """The opt-in shared-memory forwarding ring (CW_RING=1) must not change a single bit."""
+    d = CircuitDesc("bn128")
+    d.set_main(C.ecdsa_scale(d, 2, 5))
+    rng = np.random.default_rng(9)
+    ins = [{"a": [int(x) for x in rng.integers(0, 2**63, 8)], "b": [int(x) for x in rng.integers(0, 2**63, 8)]}
+           for _ in range(40)]
+    monkeypatch.setenv("CW_RING", "0")
+    c0, wit0, arr, w2s = _run(d, ins)
+    monkeypatch.setenv("CW_RING", "1")
+    c1, wit1, _, _ = _run(d, ins)
+    assert (wit0 == wit1).all()
+    ow, st = COracle(d.to_bytes()).run(arr[:8])
+    assert not st.any() and (ow[:, w2s] == wit1[:8]).all()
+
+
 def test_sha256_512_bls12381_with_r1cs():
     d = CircuitDesc("bls12381")
     d.set_main(C.sha256(d, 512))

@@ -51,6 +51,35 @@ def test_tape_matches_oracle(prime, name):
         assert not st.any()
 
 
+def test_wide_tapes_and_forwarding_ring():
+    """Tapes with levels wider than the shared-memory forwarding ring (512 entries): the simulator replays the
+    ring with the device's worst-case deposit order and fails if an operand the lowering flagged as
+    ring-resident is not there.  Known answers: hashlib / python-int secp256k1 arithmetic."""
+    import hashlib
+    from circom_b200.circuits.bigint import ecdsa_scale_expected
+    from circom_b200.witness_calculator import Circuit
+    rng = random.Random(77)
+    d = CircuitDesc("bn128")
+    d.set_main(C.ecdsa_scale(d, 2, 5))
+    a = [rng.getrandbits(64) for _ in range(8)]
+    b = [rng.getrandbits(64) for _ in range(8)]
+    wit, st, stats, w2s = hostsim_run(d, [{"a": a, "b": b}])
+    assert not st.any()
+    assert limbs_to_ints(wit[0])[1:9] == ecdsa_scale_expected(a, b, 2, 5)
+    stc = Circuit(d, host_only=True).stats
+    assert 0 < stc["n_ring_operands"] <= stc["n_slot_operands"]
+
+    d = CircuitDesc("bn128")
+    d.set_main(C.sha256(d, 64))
+    msg = bytes(rng.getrandbits(8) for _ in range(8))
+    bits = [(byte >> (7 - k)) & 1 for byte in msg for k in range(8)]
+    wit, st, stats, w2s = hostsim_run(d, [{"in": bits}])
+    assert not st.any()
+    out = limbs_to_ints(wit[0])[1:257]
+    digest = hashlib.sha256(msg).digest()
+    assert out == [(byte >> (7 - k)) & 1 for byte in digest for k in range(8)]
+
+
 def test_assert_failure_is_reported():
     """`===` violated -> status k+1 of the first failing assert (reference: assert(Fr_isTrue(..)) aborts,
     assert_bucket.rs:70-88)."""

@@ -57,7 +57,7 @@ def make_workload(args):
     if args.workload == "ecdsa_scale":
         d.set_main(C.ecdsa_scale(d, args.lanes, args.chain), "ecdsa_scale_%dx%d" % (args.lanes, args.chain))
         label = "ecdsa-scale synthetic (secp256k1 BigMultModP chains %dx%d, 4x64-bit limbs), BN254" % (args.lanes, args.chain)
-        batch = args.batch_per_gpu or 1024
+        batch = args.batch_per_gpu or 2048   # 2048 x 50 MB of value slots = 103 GB of the 180 GB
     elif args.workload == "sha256compression":
         d.set_main(C.sha256_compression(d), "sha256compression")
         label = "Sha256compression, BN254"

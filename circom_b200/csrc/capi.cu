@@ -92,7 +92,10 @@ struct DevR1cs {
     unsigned short *kind = nullptr;
     u32 *perm = nullptr, *bool_wire = nullptr, *bool_row = nullptr, *term_bool_row = nullptr;
     u32 n_general = 0, n_bool = 0;
+    u32 n_long = 0;  // perm[0, n_long): rows with >= R1CS_SPLIT_MIN terms, checked by lane groups
 };
+constexpr uint64_t R1CS_SPLIT_MIN = 16;
+constexpr int R1CS_SPLIT_G = 8;
 
 template <class T>
 int upload(T **dst, const void *src, size_t bytes) {
@@ -489,17 +492,22 @@ int cw_batch_run(cw_batch *b) {
         // operand latency is not what bounds the interpreter) and its 16 KB per CTA come out of L1.
         const bool ring = !calls && b->bt_log2 == 0 && env_int("CW_RING", 0) != 0;
         const size_t smem = ring ? (size_t)2 * RING_N * sizeof(uint4) : 0;
-#define CW_LAUNCH_TAPE(PR, CALLS, RING_)                                                                      \
-    tape_exec_kernel<PR, CALLS, RING_><<<tiles, th, smem, b->stream>>>(tp, b->slots, b->bt_log2, b->first_assert_d, \
-                                                                         b->err_d, b->batch)
+#define CW_LAUNCH_TAPE(PR, CALLS, RING_, BT_)                                                                  \
+    tape_exec_kernel<PR, CALLS, RING_, BT_><<<tiles, th, smem, b->stream>>>(tp, b->slots, b->bt_log2,            \
+                                                                              b->first_assert_d, b->err_d, b->batch)
+        // builds: calls (runtime tile size), ring (BT = 1 instance), plain with BT = 1 instance fixed at compile
+        // time, plain with the tile size as an argument
+        const bool bt0 = b->bt_log2 == 0;
         if (t.F.prime_id == 0) {
-            if (calls) CW_LAUNCH_TAPE(0, true, false);
-            else if (ring) CW_LAUNCH_TAPE(0, false, true);
-            else CW_LAUNCH_TAPE(0, false, false);
+            if (calls) CW_LAUNCH_TAPE(0, true, false, -1);
+            else if (ring) CW_LAUNCH_TAPE(0, false, true, 0);
+            else if (bt0) CW_LAUNCH_TAPE(0, false, false, 0);
+            else CW_LAUNCH_TAPE(0, false, false, -1);
         } else {
-            if (calls) CW_LAUNCH_TAPE(1, true, false);
-            else if (ring) CW_LAUNCH_TAPE(1, false, true);
-            else CW_LAUNCH_TAPE(1, false, false);
+            if (calls) CW_LAUNCH_TAPE(1, true, false, -1);
+            else if (ring) CW_LAUNCH_TAPE(1, false, true, 0);
+            else if (bt0) CW_LAUNCH_TAPE(1, false, false, 0);
+            else CW_LAUNCH_TAPE(1, false, false, -1);
         }
 #undef CW_LAUNCH_TAPE
     }
@@ -796,6 +804,8 @@ int cw_r1cs_check(cw_r1cs *r, const uint64_t *witness, int is_device_ptr, uint32
 int cw_r1cs_check_strided(cw_r1cs *r, const uint64_t *witness, uint64_t stride_elems, int is_device_ptr, uint32_t batch,
                           int device, int64_t *first_bad, float *kernel_ms) {
     if (!r || !witness || !first_bad || batch == 0 || stride_elems < r->data.n_wires) return fail(CW_EINVAL, "bad argument");
+    if (is_device_ptr && ((uintptr_t)witness & 31u))
+        return fail(CW_EINVAL, "device witness pointer must be 32-byte aligned (elements are read with 256-bit loads)");
     int rc = ensure_device(device);
     if (rc) return rc;
     DevR1cs d;
@@ -884,6 +894,8 @@ int cw_r1cs_check_strided(cw_r1cs *r, const uint64_t *witness, uint64_t stride_e
             if ((rc = upload(&d.term_bool_row, term_bool.data(), term_bool.size() * 4))) return rc;
             d.n_general = (u32)perm.size();
             d.n_bool = (u32)bool_wire.size();
+            d.n_long = 0;  // perm is sorted by decreasing term count
+            while (d.n_long < d.n_general && (sig[perm[d.n_long]] >> 48) >= R1CS_SPLIT_MIN) ++d.n_long;
             if ((rc = upload(&d.bool_wire, bool_wire.data(), bool_wire.size() * 4))) return rc;
             if ((rc = upload(&d.bool_row, bool_row.data(), bool_row.size() * 4))) return rc;
             if ((rc = upload(&d.row_ptr, R.row_ptr.data(), R.row_ptr.size() * 8))) return rc;
@@ -916,22 +928,41 @@ int cw_r1cs_check_strided(cw_r1cs *r, const uint64_t *witness, uint64_t stride_e
     rd.kind = d.kind;
     rd.perm = d.perm;
     rd.term_bool_row = d.term_bool_row;
-    rd.n_constraints = d.n_general;  // rows visited through perm
     rd.n_wires = (u32)R.n_wires;
     rd.w_stride = stride_elems;
+    // general rows: the long ones (perm[0, n_long)) by lane groups, the rest one thread per (row, instance)
+    // (lane groups are opt-in, env CW_R1CS_SPLIT=1: measured 20.7 ms against 18.4 ms for the one-thread-per-row
+    // kernel on the bench circuit, batch 1024 - the butterfly costs more than the coalescing gains)
+    const u32 n_long = env_int("CW_R1CS_SPLIT", 0) ? d.n_long : 0u, n_short = d.n_general - n_long;
     // instance groups: enough blocks to fill the GPU, as many instances per block as that allows
-    u32 row_blocks = (u32)std::min<uint64_t>(((uint64_t)d.n_general + 255) / 256, 148 * 8);
-    if (row_blocks == 0) row_blocks = 1;
-    u32 ipb = 1;
-    while (ipb < 8 && (uint64_t)row_blocks * ((batch + 2 * ipb - 1) / (2 * ipb)) >= 148ull * 16) ipb *= 2;
-    ipb = (u32)env_int("CW_R1CS_IPB", (int)ipb);
-    rd.inst_per_block = ipb;
+    auto plan = [&](u32 rows_per_block, u32 n_rows, u32 *row_blocks) {
+        *row_blocks = (u32)std::min<uint64_t>(((uint64_t)n_rows + rows_per_block - 1) / rows_per_block, 148 * 8);
+        if (*row_blocks == 0) *row_blocks = 1;
+        u32 ipb = 1;
+        while (ipb < 8 && (uint64_t)*row_blocks * ((batch + 2 * ipb - 1) / (2 * ipb)) >= 148ull * 16) ipb *= 2;
+        ipb = (u32)std::max(1, env_int("CW_R1CS_IPB", (int)ipb));
+        while ((batch + ipb - 1) / ipb > 65535u) ipb *= 2;  // grid.y limit: every instance must have a block
+        return ipb;
+    };
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
-    dim3 grid(row_blocks, std::min<u32>((batch + ipb - 1) / ipb, 65535u));
     CU(cudaEventRecord(e0));
-    if (d.n_general) {
+    if (n_long) {
+        u32 row_blocks;
+        rd.inst_per_block = plan(256 / R1CS_SPLIT_G, n_long, &row_blocks);
+        rd.perm = d.perm;
+        rd.n_constraints = n_long;
+        dim3 grid(row_blocks, std::min<u32>((batch + rd.inst_per_block - 1) / rd.inst_per_block, 65535u));
+        if (R.prime_id == 0) r1cs_check_split_kernel<0, R1CS_SPLIT_G><<<grid, 256>>>(rd, w_d, batch, fb_d);
+        else r1cs_check_split_kernel<1, R1CS_SPLIT_G><<<grid, 256>>>(rd, w_d, batch, fb_d);
+    }
+    if (n_short) {
+        u32 row_blocks;
+        rd.inst_per_block = plan(256, n_short, &row_blocks);
+        rd.perm = d.perm + n_long;
+        rd.n_constraints = n_short;  // rows visited through perm
+        dim3 grid(row_blocks, std::min<u32>((batch + rd.inst_per_block - 1) / rd.inst_per_block, 65535u));
         if (R.prime_id == 0) r1cs_check_kernel<0><<<grid, 256>>>(rd, w_d, batch, fb_d);
         else r1cs_check_kernel<1><<<grid, 256>>>(rd, w_d, batch, fb_d);
     }

@@ -992,12 +992,12 @@ struct Lowerer {
             }
             // runs of single-bit extractions of one source into consecutive slots (the bits of a decomposition
             // are consecutive witness entries) become ONE tape op that writes the whole run: imm bits 24-31 hold
-            // (run length - 1).  One thread then fetches the source word once and streams out up to 16 slots.
+            // (run length - 1).  One thread fetches the source word once; the run (up to 32 slots) is stored by the whole warp, lane j writing bit j.
             if (o[0] == DOP_BITS && !(flags & CW_FLAG_NO_PEEPHOLE) && lvl == prev_level && !T.ops.empty()) {
                 uint32_t *p = &T.ops[T.ops.size() - 4];
                 if ((p[0] & 0xFFu) == DOP_BITS && p[1] == d[1] && ((p[3] >> 16) & 0xFFu) == 1u && ((d[3] >> 16) & 0xFFu) == 1u) {
                     uint32_t cnt = (p[3] >> 24) + 1u, pk = p[3] & 0xFFFFu, pdst = p[0] >> 8;
-                    if (cnt < 16u && (d[3] & 0xFFFFu) == pk + cnt && dst == pdst + cnt) {
+                    if (cnt < 32u && (d[3] & 0xFFFFu) == pk + cnt && dst == pdst + cnt) {
                         p[3] += 1u << 24;
                         continue;
                     }

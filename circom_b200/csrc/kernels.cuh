@@ -17,8 +17,31 @@ __constant__ FrParams c_fr[2];
 //     uint4 index = (tile * n_slots + slot) * 2 * BT + half * BT + instance_in_tile
 // so a (warp of) thread(s) working on BT instances of one op issues 128-bit loads over
 // BT*16 contiguous bytes per half; with BT = 1 this is the plain 32-byte element (one DRAM sector).
+// sm_100 moves a whole 32-byte element with one instruction (LDG/STG.E.ENL2.256): half the memory
+// instructions and half the L1/L2 requests of a pair of 128-bit accesses.  32-byte alignment required.
+__device__ __forceinline__ void ldg256(u32 *v, const void *p) {
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p)
+                 : "memory");
+}
+__device__ __forceinline__ void ldg256_nc(u32 *v, const void *p) {  // data that no thread of the kernel writes
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+        : "l"(p));
+}
+__device__ __forceinline__ void stg256(void *p, const u32 *v) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+
 __device__ __forceinline__ void load_slot(u32 *v, const uint4 *__restrict__ tile_base, u32 slot, u32 bt_log2,
                                           u32 inst) {
+    if (bt_log2 == 0) {  // one instance per tile: the element is contiguous
+        ldg256(v, tile_base + ((size_t)slot << 1));
+        return;
+    }
     size_t i = ((size_t)slot << (bt_log2 + 1)) + inst;
     uint4 lo = tile_base[i];
     uint4 hi = tile_base[i + ((size_t)1 << bt_log2)];
@@ -27,6 +50,10 @@ __device__ __forceinline__ void load_slot(u32 *v, const uint4 *__restrict__ tile
 }
 __device__ __forceinline__ void store_slot(const u32 *v, uint4 *__restrict__ tile_base, u32 slot, u32 bt_log2,
                                            u32 inst) {
+    if (bt_log2 == 0) {
+        stg256(tile_base + ((size_t)slot << 1), v);
+        return;
+    }
     size_t i = ((size_t)slot << (bt_log2 + 1)) + inst;
     tile_base[i] = make_uint4(v[0], v[1], v[2], v[3]);
     tile_base[i + ((size_t)1 << bt_log2)] = make_uint4(v[4], v[5], v[6], v[7]);
@@ -147,12 +174,16 @@ __device__ __forceinline__ void load_operand_t(u32 *v, u32 operand, const uint4 
 #ifndef CW_TAPE_MINB
 #define CW_TAPE_MINB 1
 #endif
-template <int PRIME, bool HAS_CALLS, bool RING>
+// BT >= 0 fixes the tile size at compile time (BT = 0, one instance per CTA, is the common layout: the slot
+// address arithmetic then folds to `base + slot * 32`); BT < 0 takes it from the launch argument.
+template <int PRIME, bool HAS_CALLS, bool RING, int BT>
 __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
-    tape_exec_kernel(TapeDev tp, uint4 *__restrict__ slots, u32 bt_log2, u32 *__restrict__ first_assert,
+    tape_exec_kernel(TapeDev tp, uint4 *__restrict__ slots, u32 bt_log2_arg, u32 *__restrict__ first_assert,
                      int *__restrict__ err, u32 batch) {
     extern __shared__ uint4 ring[];  // RING: 2 * RING_N entries (16 KB)
     const FrParams &P = c_fr[PRIME];
+    const u32 bt_log2 = BT >= 0 ? (u32)BT : bt_log2_arg;
+    constexpr bool COOP = BT == 0 && !HAS_CALLS;  // warp-cooperative bit-run stores (needs blockDim % 32 == 0)
     const u32 tile = blockIdx.x;
     const u32 bt_mask = (1u << bt_log2) - 1;
     uint4 *base = slots + (((size_t)tile * tp.n_slots) << (bt_log2 + 1));
@@ -165,7 +196,12 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
     for (u32 l = 0; l < tp.n_levels; ++l) {
         const u32 n = (le - lb) << bt_log2;
         const u32 le_next = (l + 1 < tp.n_levels) ? tp.level_start[l + 2] : le;
-        for (u32 w = threadIdx.x; w < n; w += blockDim.x) {
+        // COOP (one instance per CTA): the warp walks the level together - lanes beyond the level's end idle in
+        // the body - so that the bit runs of its lanes can be stored cooperatively afterwards
+        for (u32 w0 = COOP ? (threadIdx.x & ~31u) : threadIdx.x; w0 < n; w0 += blockDim.x) {
+            const u32 w = COOP ? w0 + (threadIdx.x & 31u) : w0;
+            u32 run_dst = 0, run_n = 0, run_bits = 0;
+            if (!COOP || w < n) do {
             const u32 oi = lb + (w >> bt_log2);
             const u32 li = w & bt_mask;
             const uint4 opw = (w == threadIdx.x) ? pre : __ldg(&tp.ops[oi]);
@@ -198,12 +234,18 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
 #pragma unroll
                 for (int i = 1; i < 8; ++i) r[i] = 0;
                 if (run > 1u) {
-                    // a run writes `run` consecutive slots, one bit each; runs bypass the ring
-                    for (u32 j = 0; j < run; ++j) {
-                        r[0] = (u32)(window >> j) & 1u;
-                        store_slot(r, base, dst + j, bt_log2, li);
+                    // a run writes `run` (<= 32) consecutive slots, one bit each; runs bypass the ring
+                    if (COOP) {  // stored by the whole warp after the body
+                        run_dst = dst;
+                        run_n = run;
+                        run_bits = (u32)window;
+                    } else {
+                        for (u32 j = 0; j < run; ++j) {
+                            r[0] = (u32)(window >> j) & 1u;
+                            store_slot(r, base, dst + j, bt_log2, li);
+                        }
                     }
-                    continue;
+                    continue;  // (leaves the do { } while (0) body)
                 }
                 r[0] = (u32)window & (m >= 32u ? 0xFFFFFFFFu : ((1u << m) - 1u));
             } else {
@@ -234,6 +276,25 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
             if (RING) {
                 ring[dst & (RING_N - 1u)] = make_uint4(r[0], r[1], r[2], r[3]);
                 ring[RING_N + (dst & (RING_N - 1u))] = make_uint4(r[4], r[5], r[6], r[7]);
+            }
+            } while (0);
+            if (COOP) {
+                // Bit runs, warp-cooperatively: the slots of a run are consecutive, so lane j stores bit j and one
+                // store instruction covers run * 32 contiguous bytes (whole 128-byte lines) - a lane streaming its
+                // own run would touch one line per instruction and lane, 32 different lines per instruction.
+                unsigned pending = __ballot_sync(0xFFFFFFFFu, run_n != 0u);
+                const u32 lane = threadIdx.x & 31u;
+                while (pending) {
+                    const int src = __ffs(pending) - 1;
+                    pending &= pending - 1u;
+                    const u32 d = __shfl_sync(0xFFFFFFFFu, run_dst, src);
+                    const u32 cnt = __shfl_sync(0xFFFFFFFFu, run_n, src);
+                    const u32 bits = __shfl_sync(0xFFFFFFFFu, run_bits, src);
+                    if (lane < cnt) {
+                        u32 r[8] = {(bits >> lane) & 1u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                        stg256(base + ((size_t)(d + lane) << 1), r);
+                    }
+                }
             }
         }
         if (threadIdx.x < ((le_next - le) << bt_log2)) pre = __ldg(&tp.ops[le + (threadIdx.x >> bt_log2)]);
@@ -291,9 +352,10 @@ __global__ void witness_pack_kernel(const uint4 *__restrict__ slots, u32 n_slots
                 for (u32 j = 0; j < 32u; ++j) {
                     if (j0 + j < n_bits) {
                         const u32 w = __ldg(&bit_wire[j0 + j]);
-                        const uint4 lo = base[2 * (size_t)w], hi = base[2 * (size_t)w + 1];
-                        bad |= lo.y | lo.z | lo.w | hi.x | hi.y | hi.z | hi.w | (lo.x & ~1u);
-                        word |= (lo.x & 1u) << j;
+                        u32 x[8];
+                        ldg256_nc(x, base + 2 * (size_t)w);
+                        bad |= x[1] | x[2] | x[3] | x[4] | x[5] | x[6] | x[7] | (x[0] & ~1u);
+                        word |= (x[0] & 1u) << j;
                     }
                 }
                 out[it] = word;
@@ -301,17 +363,19 @@ __global__ void witness_pack_kernel(const uint4 *__restrict__ slots, u32 n_slots
             } else if (it < (size_t)n_bit_words + n_u64) {
                 const u32 k = (u32)(it - n_bit_words);
                 const u32 w = __ldg(&u64_wire[k]);
-                const uint4 lo = base[2 * (size_t)w], hi = base[2 * (size_t)w + 1];
-                if (lo.z | lo.w | hi.x | hi.y | hi.z | hi.w) *flag = 1;
-                out[n_bit_words + 2 * (size_t)k] = lo.x;
-                out[n_bit_words + 2 * (size_t)k + 1] = lo.y;
+                u32 x[8];
+                ldg256_nc(x, base + 2 * (size_t)w);
+                if (x[2] | x[3] | x[4] | x[5] | x[6] | x[7]) *flag = 1;
+                out[n_bit_words + 2 * (size_t)k] = x[0];
+                out[n_bit_words + 2 * (size_t)k + 1] = x[1];
             } else {
                 const u32 k = (u32)(it - n_bit_words - n_u64);
                 const u32 w = __ldg(&full_wire[k]);
-                const uint4 lo = base[2 * (size_t)w], hi = base[2 * (size_t)w + 1];
+                u32 x[8];
+                ldg256_nc(x, base + 2 * (size_t)w);
                 u32 *o = out + n_bit_words + 2 * (size_t)n_u64 + 8 * (size_t)k;
-                o[0] = lo.x; o[1] = lo.y; o[2] = lo.z; o[3] = lo.w;
-                o[4] = hi.x; o[5] = hi.y; o[6] = hi.z; o[7] = hi.w;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = x[i];
             }
         }
     }
@@ -350,13 +414,13 @@ struct R1csDev {
 template <int PRIME>
 __device__ __forceinline__ void r1cs_lc(u32 *acc, const R1csDev &R, unsigned long long b, unsigned long long e,
                                         const uint4 *__restrict__ w, const FrParams &P,
-                                        unsigned long long *__restrict__ first_bad_inst) {
+                                        unsigned long long *__restrict__ first_bad_inst, u32 step = 1) {
     u256_set_u32(acc, 0);
-    for (unsigned long long k = b; k < e; ++k) {
+    for (unsigned long long k = b; k < e; k += step) {
         u32 c = __ldg(&R.col[k]);
         u32 ci = __ldg(&R.coef[k]);
-        uint4 lo = w[2 * (size_t)c], hi = w[2 * (size_t)c + 1];
-        u32 x[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        u32 x[8];
+        ldg256_nc(x, w + 2 * (size_t)c);
         u32 t[8];
         u32 kw = __ldg(&R.kind[ci]);
         u32 kd = kw & 0xFF, sh = kw >> 8;
@@ -395,6 +459,30 @@ __device__ __forceinline__ void r1cs_lc(u32 *acc, const R1csDev &R, unsigned lon
     }
 }
 
+// a * b == c for canonical a, b, c; the product is skipped for a or b in {0, 1, -1}
+__device__ __forceinline__ bool r1cs_row_holds(const u32 *a, const u32 *b, const u32 *c, const FrParams &P) {
+    bool ok;
+    u32 ha = a[1] | a[2] | a[3] | a[4] | a[5] | a[6] | a[7];
+    u32 hb = b[1] | b[2] | b[3] | b[4] | b[5] | b[6] | b[7];
+    if ((!ha && a[0] == 0) || (!hb && b[0] == 0)) ok = u256_is_zero(c);
+    else if (!ha && a[0] == 1) ok = u256_eq(b, c);
+    else if (!hb && b[0] == 1) ok = u256_eq(a, c);
+    else if (a[0] + 1u == P.q[0] && a[1] == P.q[1] && a[2] == P.q[2] && a[3] == P.q[3] && a[4] == P.q[4] &&
+             a[5] == P.q[5] && a[6] == P.q[6] && a[7] == P.q[7]) {
+        // a = -1: rows `out <== x*y` are stored as (-x) * y = -out (the reference's normal form), so a
+        // bit-valued x = 1 lands here: -b == c
+        u32 s[8];
+        fr_add(s, b, c, P);
+        ok = u256_is_zero(s);
+    } else {
+        u32 ab[8], c1[8];
+        fr_mont_mul(ab, a, b, P);  // a*b/R
+        fr_from_mont(c1, c, P);    // c/R
+        ok = u256_eq(ab, c1);
+    }
+    return ok;
+}
+
 template <int PRIME>
 __global__ void __launch_bounds__(256) r1cs_check_kernel(R1csDev R, const uint4 *__restrict__ witness, u32 batch,
                                                          unsigned long long *__restrict__ first_bad) {
@@ -411,26 +499,48 @@ __global__ void __launch_bounds__(256) r1cs_check_kernel(R1csDev R, const uint4 
             r1cs_lc<PRIME>(a, R, p0, p1, w, P, &first_bad[inst]);
             r1cs_lc<PRIME>(b, R, p1, p2, w, P, &first_bad[inst]);
             r1cs_lc<PRIME>(c, R, p2, p3, w, P, &first_bad[inst]);
-            bool ok;
-            u32 ha = a[1] | a[2] | a[3] | a[4] | a[5] | a[6] | a[7];
-            u32 hb = b[1] | b[2] | b[3] | b[4] | b[5] | b[6] | b[7];
-            if ((!ha && a[0] == 0) || (!hb && b[0] == 0)) ok = u256_is_zero(c);
-            else if (!ha && a[0] == 1) ok = u256_eq(b, c);
-            else if (!hb && b[0] == 1) ok = u256_eq(a, c);
-            else if (a[0] + 1u == P.q[0] && a[1] == P.q[1] && a[2] == P.q[2] && a[3] == P.q[3] && a[4] == P.q[4] &&
-                     a[5] == P.q[5] && a[6] == P.q[6] && a[7] == P.q[7]) {
-                // a = -1: rows `out <== x*y` are stored as (-x) * y = -out (the reference's normal form), so a
-                // bit-valued x = 1 lands here: -b == c
-                u32 s[8];
-                fr_add(s, b, c, P);
-                ok = u256_is_zero(s);
-            } else {
-                u32 ab[8], c1[8];
-                fr_mont_mul(ab, a, b, P);  // a*b/R
-                fr_from_mont(c1, c, P);    // c/R
-                ok = u256_eq(ab, c1);
-            }
+            const bool ok = r1cs_row_holds(a, b, c, P);
             if (!ok) atomicMin(&first_bad[inst], (unsigned long long)row);
+        }
+    }
+}
+
+// Long rows (the 65-term recomposition sums of range checks, polynomial identities): G lanes share one
+// (row, instance); lane g takes terms g, g + G, ... of each linear combination and the partial sums are
+// combined with a butterfly of modular additions.  The terms of such a row reference consecutive witness
+// entries, so the G lanes read G adjacent 32-byte elements (whole 128-byte lines) where one thread walking
+// the row alone touches one sector per load; and the dependent chain per thread is G times shorter.
+template <int PRIME, int G>
+__global__ void __launch_bounds__(256) r1cs_check_split_kernel(R1csDev R, const uint4 *__restrict__ witness, u32 batch,
+                                                               unsigned long long *__restrict__ first_bad) {
+    const FrParams &P = c_fr[PRIME];
+    const u32 i0 = blockIdx.y * R.inst_per_block;
+    const u32 i1 = min(batch, i0 + R.inst_per_block);
+    const u32 g = threadIdx.x & (G - 1);
+    const u32 gmask = ((G == 32) ? 0xFFFFFFFFu : ((1u << G) - 1u)) << ((threadIdx.x & 31u) & ~(u32)(G - 1));
+    const u32 per_block = blockDim.x / G;
+    for (u32 rs = blockIdx.x * per_block + threadIdx.x / G; rs < R.n_constraints; rs += gridDim.x * per_block) {
+        const u32 row = __ldg(&R.perm[rs]);
+        unsigned long long p[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) p[j] = R.row_ptr[3 * (size_t)row + j];
+        for (u32 inst = i0; inst < i1; ++inst) {
+            const uint4 *w = witness + (size_t)inst * R.w_stride * 2;
+            u32 lc[3][8];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                r1cs_lc<PRIME>(lc[j], R, p[j] + g, p[j + 1], w, P, &first_bad[inst], G);
+                if (p[j + 1] == p[j]) continue;  // empty combination: every lane holds 0
+#pragma unroll
+                for (int off = G / 2; off > 0; off >>= 1) {
+                    u32 o[8], t[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o[i] = __shfl_xor_sync(gmask, lc[j][i], off);
+                    fr_add(t, lc[j], o, P);
+                    u256_set(lc[j], t);
+                }
+            }
+            if (g == 0 && !r1cs_row_holds(lc[0], lc[1], lc[2], P)) atomicMin(&first_bad[inst], (unsigned long long)row);
         }
     }
 }
@@ -446,9 +556,10 @@ __global__ void __launch_bounds__(256) r1cs_bool_kernel(const u32 *__restrict__ 
         const uint4 *w = witness + (size_t)inst * w_stride * 2;
         for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n_bool; k += gridDim.x * blockDim.x) {
             const u32 c = __ldg(&wire[k]);
-            const uint4 lo = w[2 * (size_t)c], hi = w[2 * (size_t)c + 1];
-            const u32 rest = lo.y | lo.z | lo.w | hi.x | hi.y | hi.z | hi.w;
-            if (rest || lo.x > 1u) atomicMin(&first_bad[inst], (unsigned long long)__ldg(&rows[k]));
+            u32 x[8];
+            ldg256_nc(x, w + 2 * (size_t)c);
+            const u32 rest = x[1] | x[2] | x[3] | x[4] | x[5] | x[6] | x[7];
+            if (rest || x[0] > 1u) atomicMin(&first_bad[inst], (unsigned long long)__ldg(&rows[k]));
         }
     }
 }

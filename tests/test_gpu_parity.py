@@ -193,6 +193,33 @@ def test_r1cs_first_violated_row_matches_oracle():
     assert (exp >= 0).all() and fb.tolist() == exp.tolist()
 
 
+def test_r1cs_lane_group_kernel_matches(monkeypatch):
+    """the opt-in kernel that checks long rows with 8 lanes per (row, instance) (CW_R1CS_SPLIT=1) reports the
+    same first violated row as the default kernel and the oracle"""
+    from oracle.c_oracle import COracle
+    d = CircuitDesc("bn128")
+    d.set_main(C.num2bits(d, 64))     # one 65-term recomposition row, 64 boolean rows
+    c = Circuit(d)
+    b = Batch(c, 1)
+    b.set_inputs(flat_inputs(d, [{"in": 0xDEADBEEFCAFEF00D}]))
+    b.run()
+    good = b.witness()
+    cases = [good.copy()]
+    for wire in (1, 9, 40, 64, 65):   # out[0], out[8], out[39], out[63], in
+        bad = good.copy()
+        bad[0, wire, 0] = 2 if wire != 65 else 0xDEADBEEFCAFEF00C
+        cases.append(bad)
+    batch = np.concatenate(cases, axis=0)
+    exp = COracle(d.to_bytes()).r1cs_check(batch)
+    r = R1cs(c)
+    monkeypatch.setenv("CW_R1CS_SPLIT", "0")
+    fb0, _ = r.check(batch)
+    monkeypatch.setenv("CW_R1CS_SPLIT", "1")
+    fb1, _ = r.check(batch)
+    assert exp[0] == -1 and (exp[1:] >= 0).all()
+    assert fb0.tolist() == exp.tolist() and fb1.tolist() == exp.tolist()
+
+
 def test_packed_device_to_host_transfer_equals_plain_copy(monkeypatch):
     """witness entries proven to be bits / 64-bit values cross PCIe packed and are zero-extended on the
     host: the host array must equal the plain pitched copy, with fewer bytes transferred"""

@@ -87,10 +87,9 @@ struct DevTape {
 };
 struct DevR1cs {
     unsigned long long *row_ptr = nullptr;
-    u32 *col = nullptr, *coef = nullptr;
+    uint4 *terms = nullptr;  // per term {wire, dictionary index, kind word, absorbed boolean row}
     uint4 *dictM = nullptr;
-    unsigned short *kind = nullptr;
-    u32 *perm = nullptr, *bool_wire = nullptr, *bool_row = nullptr, *term_bool_row = nullptr;
+    u32 *perm = nullptr, *bool_wire = nullptr, *bool_row = nullptr;
     u32 n_general = 0, n_bool = 0;
     u32 n_long = 0;  // perm[0, n_long): rows with >= R1CS_SPLIT_MIN terms, checked by lane groups
 };
@@ -783,14 +782,11 @@ void cw_r1cs_destroy(cw_r1cs *r) {
     for (auto &kv : r->dev) {
         cudaSetDevice(kv.first);
         cudaFree(kv.second.row_ptr);
-        cudaFree(kv.second.col);
-        cudaFree(kv.second.coef);
+        cudaFree(kv.second.terms);
         cudaFree(kv.second.dictM);
-        cudaFree(kv.second.kind);
         cudaFree(kv.second.perm);
         cudaFree(kv.second.bool_wire);
         cudaFree(kv.second.bool_row);
-        cudaFree(kv.second.term_bool_row);
     }
     delete r;
 }
@@ -891,7 +887,12 @@ int cw_r1cs_check_strided(cw_r1cs *r, const uint64_t *witness, uint64_t stride_e
                 bool_wire.resize(o);
                 bool_row.resize(o);
             }
-            if ((rc = upload(&d.term_bool_row, term_bool.data(), term_bool.size() * 4))) return rc;
+            {
+                std::vector<uint4> terms(R.col.size());
+                for (size_t k = 0; k < R.col.size(); ++k)
+                    terms[k] = make_uint4(R.col[k], R.coef[k], kind[R.coef[k]], term_bool[k]);
+                if ((rc = upload(&d.terms, terms.data(), terms.size() * sizeof(uint4)))) return rc;
+            }
             d.n_general = (u32)perm.size();
             d.n_bool = (u32)bool_wire.size();
             d.n_long = 0;  // perm is sorted by decreasing term count
@@ -899,10 +900,7 @@ int cw_r1cs_check_strided(cw_r1cs *r, const uint64_t *witness, uint64_t stride_e
             if ((rc = upload(&d.bool_wire, bool_wire.data(), bool_wire.size() * 4))) return rc;
             if ((rc = upload(&d.bool_row, bool_row.data(), bool_row.size() * 4))) return rc;
             if ((rc = upload(&d.row_ptr, R.row_ptr.data(), R.row_ptr.size() * 8))) return rc;
-            if ((rc = upload(&d.col, R.col.data(), R.col.size() * 4))) return rc;
-            if ((rc = upload(&d.coef, R.coef.data(), R.coef.size() * 4))) return rc;
             if ((rc = upload(&d.dictM, dm.data(), dm.size() * 32))) return rc;
-            if ((rc = upload(&d.kind, kind.data(), kind.size() * 2))) return rc;
             if ((rc = upload(&d.perm, perm.data(), perm.size() * 4))) return rc;
             r->dev[device] = d;
         } else d = it->second;
@@ -922,12 +920,9 @@ int cw_r1cs_check_strided(cw_r1cs *r, const uint64_t *witness, uint64_t stride_e
     CU(cudaMemset(fb_d, 0xFF, (size_t)batch * 8));
     R1csDev rd;
     rd.row_ptr = d.row_ptr;
-    rd.col = d.col;
-    rd.coef = d.coef;
+    rd.terms = d.terms;
     rd.dictM = d.dictM;
-    rd.kind = d.kind;
     rd.perm = d.perm;
-    rd.term_bool_row = d.term_bool_row;
     rd.n_wires = (u32)R.n_wires;
     rd.w_stride = stride_elems;
     // general rows: the long ones (perm[0, n_long)) by lane groups, the rest one thread per (row, instance)

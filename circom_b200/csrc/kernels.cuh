@@ -399,12 +399,11 @@ __global__ void witness_pack_kernel(const uint4 *__restrict__ slots, u32 n_slots
 // product otherwise); the row product a*b is skipped when a or b is 0 or 1 (boolean-constraint rows).
 struct R1csDev {
     const unsigned long long *row_ptr;
-    const u32 *col;
-    const u32 *coef;
+    // per term {wire, coefficient dictionary index, kind word of the coefficient, row id of the boolean constraint
+    // of the wire that is checked alongside or ~0}: one 128-bit load per term
+    const uint4 *terms;
     const uint4 *dictM;
-    const unsigned short *kind;
     const u32 *perm;
-    const u32 *term_bool_row;  // per term: row id of the boolean constraint of its wire checked alongside, or ~0
     u32 n_constraints;
     u32 n_wires;
     u32 inst_per_block;
@@ -417,17 +416,16 @@ __device__ __forceinline__ void r1cs_lc(u32 *acc, const R1csDev &R, unsigned lon
                                         unsigned long long *__restrict__ first_bad_inst, u32 step = 1) {
     u256_set_u32(acc, 0);
     for (unsigned long long k = b; k < e; k += step) {
-        u32 c = __ldg(&R.col[k]);
-        u32 ci = __ldg(&R.coef[k]);
+        // one 16-byte record per term: {wire, dictionary index, kind word, absorbed boolean row}
+        const uint4 term = __ldg(&R.terms[k]);
+        const u32 c = term.x, ci = term.y, kw = term.z, brow = term.w;
         u32 x[8];
         ldg256_nc(x, w + 2 * (size_t)c);
         u32 t[8];
-        u32 kw = __ldg(&R.kind[ci]);
         u32 kd = kw & 0xFF, sh = kw >> 8;
         bool neg = (kd == 2) || (kd == 4);
         const u32 upper = x[1] | x[2] | x[3] | x[4] | x[5] | x[6] | x[7];
         // the boolean constraint x*(x-1) = 0 of this wire is checked here, while its value is in registers
-        const u32 brow = __ldg(&R.term_bool_row[k]);
         if (brow != 0xFFFFFFFFu && (upper || x[0] > 1u)) atomicMin(first_bad_inst, (unsigned long long)brow);
         if (kd >= 3) {
             if (!upper && sh <= 222u) {

@@ -140,12 +140,13 @@ class ClockSampler:
 
 def ncu_traffic(workload_name: str, batch: int, kernel: str):
     """DRAM bytes per launch of `kernel` from the committed ncu capture, if it was taken on this configuration"""
-    try:
-        j = json.load(open(os.path.join(ROOT, "profiles", "r01b_traffic.json")))
-        if j["workload"] == workload_name and j["batch_per_gpu"] == batch:
-            return int(j[kernel]["dram_bytes_read"] + j[kernel]["dram_bytes_write"])
-    except Exception:
-        pass
+    for name in ("r01c_traffic.json", "r01b_traffic.json"):   # newest capture first
+        try:
+            j = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if j["workload"] == workload_name and j["batch_per_gpu"] == batch:
+                return int(j[kernel]["dram_bytes_read"] + j[kernel]["dram_bytes_write"])
+        except Exception:
+            pass
     return None
 
 

@@ -482,7 +482,13 @@ __device__ __forceinline__ bool r1cs_row_holds(const u32 *a, const u32 *b, const
 }
 
 template <int PRIME>
-__global__ void __launch_bounds__(256) r1cs_check_kernel(R1csDev R, const uint4 *__restrict__ witness, u32 batch,
+#ifndef CW_R1CS_MINB
+// CTAs per SM the register budget is cut for.  Measured on the bench circuit, batch 1024: 3 (78 registers, no
+// spills) 16.4 ms, 4 (64) 13.7 ms, 5 (48, 240 B spilled) 13.0 ms, 6 (40) 17.0 ms - the kernel is bound by memory
+// latency, resident warps buy more than the spills cost
+#define CW_R1CS_MINB 5
+#endif
+__global__ void __launch_bounds__(256, CW_R1CS_MINB) r1cs_check_kernel(R1csDev R, const uint4 *__restrict__ witness, u32 batch,
                                                          unsigned long long *__restrict__ first_bad) {
     const FrParams &P = c_fr[PRIME];
     const u32 i0 = blockIdx.y * R.inst_per_block;

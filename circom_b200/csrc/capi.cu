@@ -92,6 +92,7 @@ struct DevR1cs {
     u32 *perm = nullptr, *bool_wire = nullptr, *bool_row = nullptr;
     u32 n_general = 0, n_bool = 0;
     u32 n_long = 0;  // perm[0, n_long): rows with >= R1CS_SPLIT_MIN terms, checked by lane groups
+    u32 mean_row_terms = 0;  // terms per general row
 };
 constexpr uint64_t R1CS_SPLIT_MIN = 16;
 constexpr int R1CS_SPLIT_G = 8;
@@ -895,6 +896,11 @@ int cw_r1cs_check_strided(cw_r1cs *r, const uint64_t *witness, uint64_t stride_e
             }
             d.n_general = (u32)perm.size();
             d.n_bool = (u32)bool_wire.size();
+            {
+                uint64_t terms_general = 0;
+                for (u32 row : perm) terms_general += R.row_ptr[3 * (size_t)row + 3] - R.row_ptr[3 * (size_t)row];
+                d.mean_row_terms = perm.empty() ? 0 : (u32)(terms_general / perm.size());
+            }
             d.n_long = 0;  // perm is sorted by decreasing term count
             while (d.n_long < d.n_general && (sig[perm[d.n_long]] >> 48) >= R1CS_SPLIT_MIN) ++d.n_long;
             if ((rc = upload(&d.bool_wire, bool_wire.data(), bool_wire.size() * 4))) return rc;
@@ -958,8 +964,15 @@ int cw_r1cs_check_strided(cw_r1cs *r, const uint64_t *witness, uint64_t stride_e
         rd.perm = d.perm + n_long;
         rd.n_constraints = n_short;  // rows visited through perm
         dim3 grid(row_blocks, std::min<u32>((batch + rd.inst_per_block - 1) / rd.inst_per_block, 65535u));
-        if (R.prime_id == 0) r1cs_check_kernel<0><<<grid, 256>>>(rd, w_d, batch, fb_d);
-        else r1cs_check_kernel<1><<<grid, 256>>>(rd, w_d, batch, fb_d);
+        // long rows: many resident warps (48 registers); short rows: the unspilled build (78 registers)
+        const bool lean = env_int("CW_R1CS_LEAN", d.mean_row_terms >= 12 ? 1 : 0) != 0;
+        if (R.prime_id == 0) {
+            if (lean) r1cs_check_kernel<0, 5><<<grid, 256>>>(rd, w_d, batch, fb_d);
+            else r1cs_check_kernel<0, 3><<<grid, 256>>>(rd, w_d, batch, fb_d);
+        } else {
+            if (lean) r1cs_check_kernel<1, 5><<<grid, 256>>>(rd, w_d, batch, fb_d);
+            else r1cs_check_kernel<1, 3><<<grid, 256>>>(rd, w_d, batch, fb_d);
+        }
     }
     if (d.n_bool) {
         dim3 bgrid((u32)std::min<uint64_t>(((uint64_t)d.n_bool + 255) / 256, 148 * 8), std::min<u32>(batch, 65535u));

@@ -481,14 +481,13 @@ __device__ __forceinline__ bool r1cs_row_holds(const u32 *a, const u32 *b, const
     return ok;
 }
 
-template <int PRIME>
-#ifndef CW_R1CS_MINB
-// CTAs per SM the register budget is cut for.  Measured on the bench circuit, batch 1024: 3 (78 registers, no
-// spills) 16.4 ms, 4 (64) 13.7 ms, 5 (48, 240 B spilled) 13.0 ms, 6 (40) 17.0 ms - the kernel is bound by memory
-// latency, resident warps buy more than the spills cost
-#define CW_R1CS_MINB 5
-#endif
-__global__ void __launch_bounds__(256, CW_R1CS_MINB) r1cs_check_kernel(R1csDev R, const uint4 *__restrict__ witness, u32 batch,
+// MINB = CTAs per SM the register budget is cut for.  Measured on the bench circuit (long rows, bound by memory
+// latency), batch 1024: 3 (78 registers, no spills) 16.4 ms, 4 (64) 13.7 ms, 5 (48, 240 B spilled) 13.0 ms, 6 (40)
+// 17.0 ms - resident warps buy more than the spills cost.  Circuits of short rows (SHA-256: ~5 terms and a
+// Montgomery product per row) are arithmetic-bound and prefer the unspilled build; the host picks by the mean
+// row length.
+template <int PRIME, int MINB>
+__global__ void __launch_bounds__(256, MINB) r1cs_check_kernel(R1csDev R, const uint4 *__restrict__ witness, u32 batch,
                                                          unsigned long long *__restrict__ first_bad) {
     const FrParams &P = c_fr[PRIME];
     const u32 i0 = blockIdx.y * R.inst_per_block;

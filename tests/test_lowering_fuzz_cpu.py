@@ -1,0 +1,124 @@
+"""Randomised circuits against the Python evaluator: the lowering's value-preserving rewrites (range analysis,
+bit-field fusion, shifts for x * 2^k, products without reduction, x * 0, representation inference, bit runs, the
+forwarding-ring flags) are exercised on expression DAGs they were not hand-written for.  The tape runs on the CPU
+build of the device code (tests/hostsim) with all rewrites, with CW_FLAG_NO_PEEPHOLE and with CW_FLAG_O0; every
+witness entry must equal the evaluator's, which follows the reference's operator semantics
+(circom_algebra/src/modular_arithmetic.rs:26-215, generic/fr.cpp)."""
+import random
+
+import pytest
+
+from circom_b200.circuit import CircuitDesc
+from circom_b200 import circuits as C
+from oracle.ir_eval import evaluate, check_r1cs
+from tests.util import hostsim_run, limbs_to_ints, edge_values
+
+CW_FLAG_O0, CW_FLAG_NO_PEEPHOLE = 4, 8
+
+
+def random_template(d, rng, n_in, n_vals, with_components):
+    """values are `<--` hints (no constraint restricts the inputs); sub-components get masked values so that
+    their own constraints (Num2Bits recomposition, LessThan) hold for every input"""
+    n2b = {n: C.num2bits(d, n) for n in (5, 33, 64)} if with_components else {}
+    q = d.q
+
+    def build(t):
+        ins = t.input("x", n_in)
+        outs = t.output("o", n_vals)
+        pool = [ins[i] for i in range(n_in)]
+        small = []    # values known (by construction) to be < 2^64
+
+        def pick():
+            return rng.choice(pool)
+
+        def const():
+            return rng.choice([0, 1, 2, 3, 5, 255, 2**16, 2**31 - 1, 2**32, 2**63, 2**64 - 1, q - 1, q - 2,
+                               rng.randrange(q), rng.randrange(2**20), 1 << rng.randrange(0, 253)])
+
+        for k in range(n_vals):
+            kind = rng.randrange(16)
+            a, b = pick(), pick()
+            if kind == 0:      # bit-field of a value
+                v = (a >> rng.randrange(0, 254)) & ((1 << rng.randrange(1, 65)) - 1)
+                small.append(v)
+            elif kind == 1:    # low mask
+                v = a & ((1 << rng.randrange(1, 200)) - 1)
+            elif kind == 2:    # product with a constant (0, 1, powers of two, small, large)
+                v = (rng.choice(small) if small and rng.random() < 0.6 else a) * const()
+            elif kind == 3:    # product of two values, often both small
+                v = (rng.choice(small) * rng.choice(small)) if len(small) >= 2 and rng.random() < 0.7 else a * b
+                if len(small) >= 2 and rng.random() < 0.3:
+                    small.append(v & ((1 << 64) - 1))
+            elif kind == 4:
+                v = a + b if rng.random() < 0.5 else a - b
+            elif kind == 5:    # recomposition of a few bits of one source, in and out of order
+                src = pick()
+                lo = rng.randrange(0, 200)
+                terms = [((src >> (lo + i)) & 1) * (1 << (lo + i)) for i in range(rng.randrange(2, 12))]
+                rng.shuffle(terms) if rng.random() < 0.3 else None
+                v = terms[0]
+                for x in terms[1:]:
+                    v = v + x
+            elif kind == 6:
+                v = a << rng.choice([0, 1, 7, 64, 200, 253, 254, 300]) if rng.random() < 0.5 else a >> rng.choice([0, 1, 31, 32, 33, 64, 253, 254, 300])
+            elif kind == 7:
+                v = rng.choice([a.lt(b), a.gt(b), a.leq(b), a.geq(b), a.eq(b), a.neq(b), a.lor(b), a.land(b), a.lnot()])
+                small.append(v)
+            elif kind == 8:
+                v = t.select(a.lt(b), a, b) if rng.random() < 0.5 else t.select(a & 1, b, const())
+            elif kind == 9:    # integer division / remainder by a non-zero value
+                dv = (b & ((1 << rng.randrange(1, 64)) - 1)) + 1
+                v = a // dv if rng.random() < 0.5 else a % dv
+            elif kind == 10:
+                v = rng.choice([a | b, a ^ b, a & b, ~a, -a])
+            elif kind == 11:   # field division and small powers
+                v = a / (b + 1) if rng.random() < 0.5 else a ** (b & 7)
+            elif kind == 12 and small:   # sums and scaled sums of small values (no reduction needed)
+                v = rng.choice(small) * rng.choice([3, 10, 2**20, 2**64]) + rng.choice(small)
+            elif kind == 13:
+                v = (a * b + a) * const()
+            elif kind == 14 and n2b:     # a range-checked value: Num2Bits on a masked value
+                n = rng.choice(sorted(n2b))
+                comp = t.component("n2b_%d" % k, n2b[n])
+                masked = t.signal("m_%d" % k)
+                t.assign(masked, a & ((1 << n) - 1))
+                t.assign_constrained(comp["in"], masked)
+                v = comp["out"][rng.randrange(n)] + comp["out"][rng.randrange(n)] * 2
+                small.append(masked)
+            else:
+                v = a * const() + b
+            t.assign(outs[k], v)
+            pool.append(outs[k])
+    return d.template("Fuzz", (), build)
+
+
+def rand_input(rng, q, edges):
+    r = rng.random()
+    if r < 0.35:
+        return rng.choice(edges)
+    if r < 0.6:
+        return rng.randrange(2 ** rng.choice([1, 8, 31, 32, 64, 128]))
+    return rng.randrange(q)
+
+
+@pytest.mark.parametrize("prime", ["bn128", "bls12381"])
+@pytest.mark.parametrize("seed", range(40))
+def test_random_circuits_match_the_evaluator(prime, seed):
+    rng = random.Random(1000 * seed + (7 if prime == "bn128" else 13))
+    d = CircuitDesc(prime)
+    n_in = rng.randrange(2, 5)
+    d.set_main(random_template(d, rng, n_in, n_vals=rng.randrange(20, 70), with_components=seed % 2 == 0))
+    edges = edge_values(d.q)
+    ins = [{"x": [rand_input(rng, d.q, edges) for _ in range(n_in)]} for _ in range(10)]
+    expected = [evaluate(d, inp) for inp in ins]
+    for e in expected:
+        assert check_r1cs(d, e) == 0
+    for flags in (0, CW_FLAG_NO_PEEPHOLE, CW_FLAG_O0):
+        wit, st, stats, w2s = hostsim_run(d, ins, flags=flags)
+        assert not st.any(), (prime, seed, flags, st)
+        for i, e in enumerate(expected):
+            got = limbs_to_ints(wit[i])
+            want = [e[k] for k in w2s]
+            if got != want:
+                bad = [j for j in range(len(got)) if got[j] != want[j]][:5]
+                raise AssertionError("prime %s seed %d flags %d input %d: witness entries %s differ" % (prime, seed, flags, i, bad))

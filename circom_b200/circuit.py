@@ -608,6 +608,45 @@ class CircuitDesc:
             out.append((name, 1 + off, n))
         return out
 
+    # -- .sym -------------------------------------------------------------------------------
+    def sym_lines(self, witness2signal: Sequence[int]) -> List[str]:
+        """The lines of the reference's `--sym` file (`#s,#w,#c,name`, mkdocs/docs/circom-language/formats/sym.md;
+        writer constraint_writers/src/sym_writer.rs:4-14, traversal constraint_list/src/sym_porting.rs:14-38):
+        pre-order over the component tree, `s` the signal number, `w` its witness position or -1 when the signal
+        was merged away, `c` the DAG node of the component's template instance (nodes are numbered when their
+        first instance finishes executing: children before parents), `name` the qualified name."""
+        w_of = {int(s): i for i, s in enumerate(witness2signal)}
+        node_id: Dict[int, int] = {}
+
+        def number(t: "Template"):
+            if t.id in node_id:
+                return
+            for s in t.subs:
+                number(s.tmpl)
+            node_id[t.id] = len(node_id)
+        number(self.main)
+        lines: List[str] = []
+
+        def visit(t: "Template", start: int, path: str):
+            off = start
+            for cat in ("out", "in", "inter"):
+                for name, n in t.sigs[cat]:
+                    for j in range(n):
+                        sig = off + j
+                        label = "%s.%s%s" % (path, name, "[%d]" % j if t.sig_is_array[name] else "")
+                        lines.append("%d,%d,%d,%s" % (sig, w_of.get(sig, -1), node_id[t.id], label))
+                    off += n
+            for s in t.subs:
+                visit(s.tmpl, off, path + "." + s.name)
+                off += s.tmpl.total_signals
+        visit(self.main, 1, "main")
+        return lines
+
+    def write_sym(self, path: str, witness2signal: Sequence[int]) -> str:
+        with open(path, "w") as f:
+            f.write("".join(line + "\n" for line in self.sym_lines(witness2signal)))
+        return path
+
     # -- serialisation -------------------------------------------------------------------
     def to_bytes(self) -> bytes:
         import numpy as np

@@ -110,6 +110,18 @@ def test_r1cs_of_the_documented_basic_circuit(tmp_path):
     doc_o0 = [({}, {}, {2: 1, 5: m1}), ({}, {}, {0: 1, 2: 2, 3: 1, 6: m1}), ({}, {}, {1: m1, 4: 1}),
               ({5: m1}, {6: 1}, {4: m1})]
     sym_o1 = [0, 1, 2, 3, 6]            # witness -> signal: sym.md lines "6,4,0,main.c.in[1]"; 4 and 5 eliminated
+    # the `--sym` files printed in formats/sym.md:50-55 (--O1) and :69-74 (--O0)
+    symfile_o1 = ["1,1,1,main.out", "2,2,1,main.in[0]", "3,3,1,main.in[1]", "4,-1,0,main.c.out", "5,-1,0,main.c.in[0]",
+                  "6,4,0,main.c.in[1]"]
+    symfile_o0 = ["1,1,1,main.out", "2,2,1,main.in[0]", "3,3,1,main.in[1]", "4,4,0,main.c.out", "5,5,0,main.c.in[0]",
+                  "6,6,0,main.c.in[1]"]
+    for o0, symfile in ((False, symfile_o1), (True, symfile_o0)):
+        d = CircuitDesc("bn128")
+        d.set_main(_basic_circom(d))
+        c = Circuit(d, host_only=True, o0=o0)
+        assert d.sym_lines(c.witness2signal()) == symfile
+        p = d.write_sym(str(tmp_path / "basic.sym"), c.witness2signal())
+        assert open(p).read() == "".join(x + "\n" for x in symfile)
     for o0, doc, sym in ((False, doc_o1, sym_o1), (True, doc_o0, list(range(7)))):
         d = CircuitDesc("bn128")
         assert d.q == q

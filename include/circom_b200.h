@@ -160,7 +160,8 @@ int cw_r1cs_info(const cw_r1cs *r, uint64_t *n_wires, uint64_t *n_constraints, u
 void cw_r1cs_destroy(cw_r1cs *r);
 /* A.w o B.w == C.w for `batch` witnesses w[batch][n_wires][4] (canonical).  first_bad[i] = -1 if
  * instance i satisfies every constraint, else the smallest violated row.  New functionality: the
- * reference has no evaluator (constraint_writers/src/r1cs_reader.rs has no caller). */
+ * reference has no evaluator (constraint_writers/src/r1cs_reader.rs has no caller).
+ * A device pointer must be 32-byte aligned (elements are read with 256-bit loads); CW_EINVAL otherwise. */
 int cw_r1cs_check(cw_r1cs *r, const uint64_t *witness, int is_device_ptr, uint32_t batch, int device,
                   int64_t *first_bad, float *kernel_ms);
 

@@ -80,14 +80,19 @@ struct Reader {
         return v;
     }
     const uint8_t *bytes(size_t n) {
-        if (p + n > end) throw std::runtime_error("cb2c: truncated");
+        if (n > (size_t)(end - p)) throw std::runtime_error("cb2c: truncated");
         const uint8_t *r = p;
         p += n;
         return r;
     }
+    size_t left() const { return (size_t)(end - p); }
+    // a count read from the file must be backed by that many records of `bytes_each` bytes
+    void expect(uint64_t count, uint64_t bytes_each) const {
+        if (count * bytes_each > left()) throw std::runtime_error("cb2c: truncated (count exceeds the file)");
+    }
     std::string str() {
         uint32_t n = get<uint32_t>();
-        const uint8_t *b = bytes((n + 3) & ~3u);
+        const uint8_t *b = bytes((size_t)(((uint64_t)n + 3) & ~3ull));  // (64-bit: n = 2^32 - 1 must not wrap to 0)
         return std::string((const char *)b, n);
     }
 };
@@ -723,6 +728,8 @@ struct Lowerer {
         uint32_t n_funcs = r.get<uint32_t>();
         if (prime > 1) throw std::runtime_error("cb2c: unknown prime");
         T.F = make_field((int)prime);
+        r.expect(n_consts, 32);
+        r.expect(n_tm, 36);
         ir_consts.resize(n_consts);
         for (auto &c : ir_consts) {
             memcpy(c.v, r.bytes(32), 32);
@@ -738,7 +745,13 @@ struct Lowerer {
             uint32_t n_sub = r.get<uint32_t>();
             t.n_tmp = r.get<uint32_t>();
             uint32_t n_ops = r.get<uint32_t>(), n_cons = r.get<uint32_t>(), n_terms = r.get<uint32_t>();
+            if ((uint64_t)t.n_out + t.n_in + t.n_inter > (1u << 28) || t.n_tmp > (1u << 28))
+                throw std::runtime_error("cb2c: template too large");
             t.n_own = t.n_out + t.n_in + t.n_inter;
+            r.expect(n_sub, 4);
+            r.expect(n_ops, 40);
+            r.expect((uint64_t)n_cons * 3, 8);
+            r.expect(n_terms, 16);
             t.subs.resize(n_sub);
             for (auto &s : t.subs) {
                 s = r.get<uint32_t>();
@@ -765,6 +778,51 @@ struct Lowerer {
                     t.terms.push_back(tr);
                 }
             }
+            // The description is an untrusted file: every reference must stay inside the objects it names.
+            auto check_ref = [&](uint64_t ref, bool may_be_none, bool is_dst) {
+                bool ok = false;
+                switch (rk(ref)) {
+                    case K_NONE: ok = may_be_none; break;
+                    case K_OWN: ok = ridx(ref) < t.n_own; break;
+                    case K_SUB:
+                        ok = rsub(ref) < t.subs.size() &&
+                             ridx(ref) < (uint64_t)tm[t.subs[rsub(ref)]].n_out + tm[t.subs[rsub(ref)]].n_in;
+                        break;
+                    case K_CONST: ok = !is_dst && ridx(ref) < n_consts; break;
+                    case K_TMP: ok = ridx(ref) < t.n_tmp; break;
+                    case K_ONE: ok = !is_dst; break;
+                    default: break;
+                }
+                if (!ok) throw std::runtime_error("cb2c: reference out of range in template " + t.name);
+            };
+            for (const IrOp &o : t.ops) {
+                if (o.op == 46 /* ARG */) {
+                    check_ref(o.a, false, false);
+                } else if (o.op == 45 /* CALL */) {
+                    if (rk(o.d) != K_TMP) throw std::runtime_error("cb2c: bad call destination in template " + t.name);
+                    check_ref(o.d, false, true);
+                } else {
+                    if (o.op < CW_OP_MUL || o.op > CW_OP_INV) throw std::runtime_error("cb2c: unknown opcode in template " + t.name);
+                    const bool is_assert = o.op == CW_OP_ASSERT || o.op == CW_OP_ASSERT_EQ;
+                    int arity = 2;
+                    switch (o.op) {
+                        case CW_OP_NEG: case CW_OP_LNOT: case CW_OP_BNOT: case CW_OP_COPY: case CW_OP_INV: case CW_OP_ASSERT:
+                            arity = 1;
+                            break;
+                        case CW_OP_SELECT: arity = 3; break;
+                        default: break;
+                    }
+                    check_ref(o.d, is_assert, true);
+                    check_ref(o.a, false, false);
+                    check_ref(o.b, arity < 2, false);
+                    check_ref(o.c, arity < 3, false);
+                }
+            }
+            for (const Term &tr : t.terms) {
+                const int k = rk(tr.ref);
+                if (k != K_OWN && k != K_SUB && k != K_ONE) throw std::runtime_error("cb2c: bad constraint reference");
+                check_ref(tr.ref, false, false);
+            }
             // which temporaries feed only zero / non-zero tests (so a raw product x*y/R suffices)
             t.tmp_zero_only.assign(t.n_tmp, 1);
             auto is_zero_const = [&](uint64_t r) { return rk(r) == K_CONST && ridx(r) < n_consts && ir_consts[ridx(r)].is_zero(); };
@@ -790,6 +848,9 @@ struct Lowerer {
             for (auto s : t.subs) {
                 t.total_signals += tm[s].total_signals;
                 t.total_components += tm[s].total_components;
+                // a few nested templates can describe an astronomically large tree: stop before instantiating it
+                if (t.total_signals > (1ull << 28) || t.total_components > (1ull << 26))
+                    throw std::runtime_error("cb2c: circuit too large (more than 2^28 signals or 2^26 components)");
             }
         }
         if (main_tid >= n_tm) throw std::runtime_error("cb2c: bad main template");

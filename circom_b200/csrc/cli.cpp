@@ -34,10 +34,18 @@ struct JValue {
 struct JParser {
     const std::string &s;
     size_t p = 0;
+    int depth = 0;  // nesting is bounded: an input file is untrusted and the reader recurses
+    static constexpr int MAX_DEPTH = 256;
     explicit JParser(const std::string &str) : s(str) {}
     void ws() { while (p < s.size() && (s[p] == ' ' || s[p] == '\n' || s[p] == '\t' || s[p] == '\r')) ++p; }
     [[noreturn]] void fail(const char *m) { throw std::runtime_error(std::string("JSON: ") + m + " at offset " + std::to_string(p)); }
     JValue parse() {
+        struct Guard {
+            int &d;
+            explicit Guard(int &x) : d(x) { ++d; }
+            ~Guard() { --d; }
+        } guard(depth);
+        if (depth > MAX_DEPTH) fail("nesting too deep");
         ws();
         if (p >= s.size()) fail("unexpected end");
         JValue v;

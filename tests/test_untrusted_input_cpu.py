@@ -124,3 +124,23 @@ def test_mutated_r1cs_files(tmp_path):
         else:
             bad += 1
     assert ok > 20 and bad > 200
+
+
+def test_cli_rejects_pathological_json(tmp_path):
+    """input.json is untrusted too: the CLI's reader bounds its recursion (a 2-million-deep array used to
+    overflow the stack) and reports malformed files as errors"""
+    import os
+    import subprocess
+    from circom_b200 import build
+    cli = os.path.join(os.path.dirname(build.LIB), "circom_cuda_witness")
+    if not os.path.exists(cli):
+        pytest.skip("CLI not built")
+    d = CircuitDesc("bn128")
+    d.set_main(C.less_than(d, 8))
+    cb = d.save(str(tmp_path / "lt.cb2c"))
+    for text, needle in (('{"in":[' + "[" * 2000000 + "1" + "]" * 2000000 + ",2]}", b"nesting too deep"),
+                         ('{"in":[1,2', b"JSON"), ("", b"JSON"), ('{"in":["12', b"JSON")):
+        p = str(tmp_path / "in.json")
+        open(p, "w").write(text)
+        r = subprocess.run([cli, cb, p, str(tmp_path / "o.wtns")], capture_output=True)
+        assert r.returncode == 1 and needle in r.stderr, (text[:20], r.returncode, r.stderr[-200:])

@@ -296,7 +296,8 @@ def main():
     # end-to-end leg: its own batch, capped so that the pinned host buffer for the witnesses stays bounded
     # (e2e is PCIe-bound and independent of the batch size; 8 ranks x 38.8 GB of pinned memory is not)
     e2e_batch = batch
-    while e2e_batch > 64 and e2e_batch * W * 32 > args.e2e_pinned_gb * 1e9:
+    pinned_cap = min(args.e2e_pinned_gb, 48.0 / world) * 1e9   # all ranks pin memory of the same host
+    while e2e_batch > 64 and e2e_batch * W * 32 > pinned_cap:
         e2e_batch //= 2
 
     def barrier():

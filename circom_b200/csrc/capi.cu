@@ -314,6 +314,12 @@ int cw_circuit_tape(const cw_circuit *c, uint32_t *ops, uint32_t *level_start, u
     return CW_OK;
 }
 
+int cw_circuit_slot_census(const cw_circuit *c, uint64_t out[4]) {
+    if (!c || !out) return fail(CW_EINVAL, "null argument");
+    memcpy(out, c->tape.slot_census, sizeof(c->tape.slot_census));
+    return CW_OK;
+}
+
 int cw_circuit_witness2signal(const cw_circuit *c, uint64_t *out) {
     if (!c || !out) return fail(CW_EINVAL, "null argument");
     memcpy(out, c->tape.witness2signal.data(), c->tape.witness2signal.size() * 8);

@@ -971,6 +971,15 @@ struct Lowerer {
             else { T.pk_full_wire.push_back((uint32_t)i); T.wit_class.push_back(2); }
         }
         size_t n_prov = pops.size() / 4;
+        // static width of every provisional slot (range analysis; Montgomery / deferred images are full width)
+        std::vector<uint16_t> slot_bits(n_pre + n_prov, 256);
+        for (const Val &v : vals)
+            if (v.cid < 0 && v.slot[FC] != NO_SLOT && v.slot[FC] < slot_bits.size())
+                slot_bits[v.slot[FC]] = std::min<uint16_t>(slot_bits[v.slot[FC]], v.bits);
+        for (uint64_t i = 0; i < W; ++i) {  // copies made for the witness carry their entry's width
+            uint32_t wb = vbits(sig_vid[T.witness2signal[i]]);
+            slot_bits[wsrc[i]] = std::min<uint16_t>(slot_bits[wsrc[i]], (uint16_t)wb);
+        }
         std::vector<uint8_t> live(n_pre + n_prov, 0);
         for (uint64_t i = 0; i < W; ++i) live[wsrc[i]] = 1;
         // dead-value elimination (reverse sweep; provisional order is topological)
@@ -1127,6 +1136,13 @@ struct Lowerer {
         if (remap[0] != 0) throw std::runtime_error("lowering: constant-one signal is not witness entry 0");
         T.consts = consts;
         if (T.consts.empty()) T.consts.push_back(u256_from_u64(0));
+        // census of the value slots by static width (what narrow slots would store in 4 / 8 bytes)
+        for (int k = 0; k < 4; ++k) T.slot_census[k] = 0;
+        for (size_t i = 0; i < n_pre + n_prov; ++i) {
+            if (remap[i] == NO_SLOT) continue;
+            const uint16_t b = slot_bits[i];
+            T.slot_census[b <= 1 ? 0 : b <= 32 ? 1 : b <= 64 ? 2 : 3]++;
+        }
         T.n_pre = n_pre;
         T.n_slots = next_tmp;
         T.n_ir_ops = n_ir_ops;

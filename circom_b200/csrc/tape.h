@@ -46,6 +46,7 @@ struct Tape {
     uint32_t flags = 0;
     uint64_t n_signals = 0, n_witness = 0, n_inputs = 0, n_outputs = 0, n_components = 0;
     uint64_t n_ir_ops = 0, n_mul_ops = 0, n_conv_ops = 0, max_level_width = 0, n_asserts = 0;
+    uint64_t slot_census[4] = {0, 0, 0, 0};  // value slots by static width: 1 bit, <= 32, <= 64 bits, wider
     uint64_t n_slot_operands = 0, n_ring_operands = 0;  // operand reads of slots / of which forwarded through the ring
     uint32_t n_pre = 0;    // slot 0 = constant one, slots 1..n_inputs = main inputs
     uint32_t n_slots = 0;  // witness entries [0, n_witness) then the other values

@@ -57,6 +57,7 @@ def _load() -> ctypes.CDLL:
         "cw_get_input_signal_size": (c_int, [P, c_uint64, POINTER(c_uint64)]),
         "cw_get_input_signal_id": (c_int, [P, c_uint64, POINTER(c_uint64)]),
         "cw_circuit_tape": (c_int, [P, c_void_p, c_void_p, c_void_p]),
+        "cw_circuit_slot_census": (c_int, [P, POINTER(c_uint64)]),
         "cw_circuit_witness2signal": (c_int, [P, c_void_p]),
         "cw_circuit_write_dat": (c_int, [P, c_char_p]),
         "cw_batch_create": (c_int, [P, c_uint32, c_int, POINTER(P)]),

@@ -110,6 +110,9 @@ int cw_get_input_signal_id(const cw_circuit *c, uint64_t name_hash, uint64_t *si
  * ops: n_tape_ops x 4 uint32 {opcode | flags<<8, a, b, c}; operand bit31 = constant-table index;
  * level_start: n_levels+1 uint32; witness_slot: n_witness uint32 (bit31 = value held in Montgomery form) */
 int cw_circuit_tape(const cw_circuit *c, uint32_t *ops, uint32_t *level_start, uint32_t *witness_slot);
+/* value slots of one instance by the width the lowering's range analysis proves: out[0] one bit, out[1] <= 32 bits,
+ * out[2] <= 64 bits, out[3] wider (today every slot is a 32-byte element; the census sizes a narrow-slot layout) */
+int cw_circuit_slot_census(const cw_circuit *c, uint64_t out[4]);
 /* witness2SignalList (calcwit.hpp:54-56, c_code_generator.rs:605-614): n_witness entries */
 int cw_circuit_witness2signal(const cw_circuit *c, uint64_t *out);
 /* save / load the reference's .dat layout for the input hash map + witness2signal list

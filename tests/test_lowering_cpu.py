@@ -68,6 +68,12 @@ def test_wide_tapes_and_forwarding_ring():
     assert limbs_to_ints(wit[0])[1:9] == ecdsa_scale_expected(a, b, 2, 5)
     stc = Circuit(d, host_only=True).stats
     assert 0 < stc["n_ring_operands"] <= stc["n_slot_operands"]
+    # census of the slots by proven width: every slot is counted once, the range-checked bits dominate
+    from circom_b200 import native
+    cc = Circuit(d, host_only=True)
+    census = (ctypes.c_uint64 * 4)()
+    assert native.lib.cw_circuit_slot_census(cc._h, census) == 0
+    assert sum(census) == stc["n_slots"] and census[0] > stc["n_slots"] // 2
 
     d = CircuitDesc("bn128")
     d.set_main(C.sha256(d, 64))

@@ -1092,6 +1092,50 @@ struct Lowerer {
             T.level_start.swap(ls);
             T.max_level_width = widest;
         }
+        // Bit plane (CW_FLAG_BITPLANE).  The outputs of bit runs - the bits of range checks, 98 % of the witness
+        // of limb-arithmetic circuits - leave the 32-byte slot store: a run of up to 32 bits becomes ONE 32-bit
+        // word of a per-instance bit plane (one 4-byte store instead of 32 x 32 bytes; 32 x 32 bits per 128-byte
+        // line instead of 4).  A reference to such a bit is OPERAND_BIT | (word * 32 + bit); the remaining slots
+        // are renumbered densely, witness entry i is found through witness_slot[i].
+        std::vector<uint32_t> newid;
+        T.n_bitwords = 0;
+        if ((flags & CW_FLAG_BITPLANE) && T.call_tab.empty()) {
+            std::vector<uint32_t> code(next_tmp, NO_SLOT);
+            uint32_t n_words = 0;
+            const size_t n_ops = T.ops.size() / 4;
+            for (size_t i = 0; i < n_ops; ++i) {
+                const uint32_t *o = &T.ops[i * 4];
+                if ((o[0] & 0xFFu) != DOP_BITS || !(o[3] >> 24)) continue;
+                const uint32_t run = (o[3] >> 24) + 1u, d0 = o[0] >> 8;
+                for (uint32_t j = 0; j < run; ++j) code[d0 + j] = OPERAND_BIT | (n_words * 32u + j);
+                ++n_words;
+            }
+            bool ok = n_words > 0 && n_words < (1u << 24);
+            for (size_t i = 0; ok && i < n_ops; ++i) {  // a run whose source is itself a packed bit stays unsupported
+                const uint32_t *o = &T.ops[i * 4];
+                if ((o[0] & 0xFFu) == DOP_BITS && (o[3] >> 24) && !(o[1] & OPERAND_CONST) && code[o[1]] != NO_SLOT) ok = false;
+            }
+            for (uint32_t i = 0; ok && i < M.n_in + 1; ++i)
+                if (code[remap[i]] != NO_SLOT) ok = false;
+            if (ok) {
+                newid.resize(next_tmp);
+                uint32_t nw = 0;
+                for (uint32_t s = 0; s < next_tmp; ++s) newid[s] = code[s] == NO_SLOT ? nw++ : code[s];
+                uint32_t word = 0;
+                for (size_t i = 0; i < n_ops; ++i) {
+                    uint32_t *o = &T.ops[i * 4];
+                    const uint32_t opc = o[0] & 0xFFu;
+                    if (opc == DOP_BITS && (o[3] >> 24)) o[0] = opc | (word++ << 8);        // destination = bit-plane word
+                    else if (!is_assert_op(opc)) o[0] = opc | (newid[o[0] >> 8] << 8);
+                    for (int k = 1; k <= 3; ++k) {
+                        if (k == 3 && c_is_immediate(opc)) break;
+                        if (!(o[k] & OPERAND_CONST)) o[k] = newid[o[k]];
+                    }
+                }
+                T.n_bitwords = n_words;
+                next_tmp = nw;
+            }
+        }
         // Shared-memory forwarding.  The interpreter keeps, per instance, a ring of the CW_RING_SIZE most recent
         // results (index = destination slot % CW_RING_SIZE; temporaries are numbered in tape order, so they walk
         // the ring sequentially; multi-slot bit runs bypass it).  An operand may be read from the ring iff its
@@ -1119,7 +1163,7 @@ struct Lowerer {
                     if (opc == 45) continue;  // call arguments are read through the call table
                     for (int k = 1; k <= 3; ++k) {
                         if (k == 3 && c_is_immediate(opc)) break;
-                        if (o[k] & OPERAND_CONST) continue;
+                        if (o[k] & (OPERAND_CONST | OPERAND_BIT)) continue;
                         ++T.n_slot_operands;
                         if (owner[o[k] & M] == o[k]) {
                             o[k] |= OPERAND_RING;
@@ -1130,9 +1174,9 @@ struct Lowerer {
             }
         }
         T.witness_slot.resize(W);
-        for (uint64_t i = 0; i < W; ++i) T.witness_slot[i] = (uint32_t)i;
+        for (uint64_t i = 0; i < W; ++i) T.witness_slot[i] = newid.empty() ? (uint32_t)i : newid[i];
         T.input_slot.resize(M.n_in);
-        for (uint32_t i = 0; i < M.n_in; ++i) T.input_slot[i] = remap[1 + i];
+        for (uint32_t i = 0; i < M.n_in; ++i) T.input_slot[i] = newid.empty() ? remap[1 + i] : newid[remap[1 + i]];
         if (remap[0] != 0) throw std::runtime_error("lowering: constant-one signal is not witness entry 0");
         T.consts = consts;
         if (T.consts.empty()) T.consts.push_back(u256_from_u64(0));

@@ -14,6 +14,9 @@ constexpr uint32_t OPERAND_CONST = 0x80000000u;  // operand bit31: index into th
 // write to the same ring index happens before the end of the consumer's level (see flatten.cpp).
 constexpr uint32_t OPERAND_RING = 0x40000000u;
 constexpr uint32_t OPERAND_SLOT_MASK = 0x00FFFFFFu;
+// operand bit29 (tapes lowered with CW_FLAG_BITPLANE): the value is one bit of the instance's bit plane,
+// bits 0-28 = word * 32 + bit.  witness_slot[] entries use the same encoding.
+constexpr uint32_t OPERAND_BIT = 0x20000000u, OPERAND_BITPOS_MASK = 0x1FFFFFFFu;
 constexpr uint32_t CW_RING_LOG2 = 9, CW_RING_SIZE = 1u << CW_RING_LOG2;
 constexpr uint32_t WSLOT_MONT = 0x80000000u;     // witness_slot bit31: slot holds the Montgomery image
 constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
@@ -50,6 +53,7 @@ struct Tape {
     uint64_t n_slot_operands = 0, n_ring_operands = 0;  // operand reads of slots / of which forwarded through the ring
     uint32_t n_pre = 0;    // slot 0 = constant one, slots 1..n_inputs = main inputs
     uint32_t n_slots = 0;  // witness entries [0, n_witness) then the other values
+    uint32_t n_bitwords = 0;  // 32-bit words of the bit plane per instance (0: every value is a 32-byte slot)
     std::vector<uint32_t> ops;          // 4 words per op: opcode | dst << 8, a, b, c
     std::vector<uint32_t> level_start;  // n_levels + 1
     std::vector<U256> consts;           // raw limb patterns (already in the form the consumer needs)

@@ -43,6 +43,7 @@ extern "C" {
 #define CW_FLAG_NO_ASSERTS 1u /* --sanity_check 0: drop `===` asserts (assert_bucket.rs:73) */
 #define CW_FLAG_HOST_ONLY 2u  /* lower the tape but do not touch a GPU (CPU-side tests of the lowering) */
 #define CW_FLAG_NO_PEEPHOLE 8u /* lower IR ops one to one (no bit-field / boolean-assert / shift fusions) */
+#define CW_FLAG_BITPLANE 16u   /* bits written by bit runs live in a packed per-instance bit plane (experimental) */
 #define CW_FLAG_O0 4u         /* --O0: keep every signal in the witness and every `signal = signal` constraint */
 
 /* IR opcodes = OperatorType, compiler/src/intermediate_representation/compute_bucket.rs:7-34 */

@@ -58,8 +58,12 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
         stats[4] = t.n_mul_ops; stats[5] = t.n_conv_ops; stats[6] = t.r1cs.n_constraints; stats[7] = t.n_ir_ops;
     }
     std::vector<u32> slots((size_t)t.n_slots * 8);
+    std::vector<u32> bitplane(t.n_bitwords);   // CW_FLAG_BITPLANE tapes: one word per bit run
+    std::vector<uint8_t> bit_written((size_t)t.n_bitwords * 32);
     for (uint32_t inst = 0; inst < batch; ++inst) {
         std::fill(slots.begin(), slots.end(), 0xDEADBEEFu);  // poison: reads before writes show up
+        std::fill(bitplane.begin(), bitplane.end(), 0xDEADBEEFu);
+        std::fill(bit_written.begin(), bit_written.end(), 0);
         u32 one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
         memcpy(&slots[0], one, 32);
         for (uint64_t k = 0; k < t.n_inputs; ++k)
@@ -74,6 +78,13 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
         bool ring_bad = false;
         auto operand = [&](u32 o, u32 *v) {
             if (o & OPERAND_CONST) { memcpy(v, t.consts[o & 0x7FFFFFFFu].v, 32); return; }
+            if (o & OPERAND_BIT) {  // one bit of the bit plane
+                const u32 pos = o & OPERAND_BITPOS_MASK;
+                if ((pos >> 5) >= t.n_bitwords || !bit_written[pos]) ring_bad = true;   // (reported below)
+                memset(v, 0, 32);
+                v[0] = (pos >> 5) < t.n_bitwords ? (bitplane[pos >> 5] >> (pos & 31u)) & 1u : 0u;
+                return;
+            }
             const u32 slot = o & OPERAND_SLOT_MASK;
             if (o & OPERAND_RING) {
                 memcpy(v, &ring[(size_t)(slot & (CW_RING_SIZE - 1)) * 8], 32);
@@ -83,8 +94,10 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
             }
         };
         std::vector<u32> results;   // results of one level: {dst, 8 words, to_ring}
+        std::vector<u32> bit_results;  // bit-plane words of one level: {word index, value, run length}
         for (size_t l = 0; l < t.n_levels(); ++l) {
             results.clear();
+            bit_results.clear();
             auto put = [&](u32 dst, const u32 *r, bool to_ring) {
                 results.push_back(dst);
                 results.insert(results.end(), r, r + 8);
@@ -110,6 +123,17 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
                 operand(op[2], b);
                 if (op[0] == OP_BITS && (op[3] >> 24)) {  // run of single-bit extractions into consecutive slots
                     u32 run = (op[3] >> 24) + 1u, k = op[3] & 0xFFFFu;
+                    if (t.n_bitwords) {  // the run is one word of the bit plane (dst = word index)
+                        u32 word = 0;
+                        for (u32 j = 0; j < run; ++j) {
+                            u256_bits(r, a, (k + j) | (1u << 16));
+                            word |= (r[0] & 1u) << j;
+                        }
+                        bit_results.push_back(dst);
+                        bit_results.push_back(word);
+                        bit_results.push_back(run);
+                        continue;
+                    }
                     for (u32 j = 0; j < run; ++j) {
                         u256_bits(r, a, (k + j) | (1u << 16));
                         put(dst + j, r, false);
@@ -140,6 +164,11 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
                 else memcpy(&ring[(size_t)idx * 8], &results[k + 1], 32);
                 ring_stamp[idx] = (u32)l;
             }
+            for (size_t k = 0; k < bit_results.size(); k += 3) {
+                if (bit_results[k] >= t.n_bitwords) { g_err = "bit-plane word out of range"; return -5; }
+                bitplane[bit_results[k]] = bit_results[k + 1];
+                for (u32 j = 0; j < bit_results[k + 2]; ++j) bit_written[(size_t)bit_results[k] * 32 + j] = 1;
+            }
             // the level's own deposits must not have displaced anything the level reads from the ring
             for (size_t i = t.level_start[l]; i < t.level_start[l + 1]; ++i) {
                 const uint32_t *opw = &t.ops[i * 4];
@@ -154,8 +183,12 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
         }
         if (ring_bad) { g_err = "forwarding ring: a flagged operand was not (or no longer) in the ring"; return -4; }
         for (uint64_t w = 0; w < t.n_witness; ++w) {
-            memcpy(witness + ((size_t)inst * t.n_witness + w) * 4, &slots[(size_t)w * 8], 32);  // slot w IS witness entry w
+            // without a bit plane witness_slot is the identity: slot w IS witness entry w
+            u32 v[8];
+            operand(t.witness_slot[w], v);
+            memcpy(witness + ((size_t)inst * t.n_witness + w) * 4, v, 32);
         }
+        if (ring_bad) { g_err = "bit plane: a bit was read before it was written (or is out of range)"; return -6; }
         status[inst] = err ? -1 : (first_assert == 0xFFFFFFFFu ? 0 : (int32_t)(first_assert + 1));
     }
     return 0;
@@ -184,6 +217,7 @@ int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
         return -1;
     }
     std::vector<uint32_t> lvl(t.n_slots, 0), oplvl(t.n_tape_ops(), 0), writes(t.n_slots, 0);
+    std::vector<uint32_t> bitlvl(t.n_bitwords, 0), bitrun(t.n_bitwords, 0);
     for (size_t l = 0; l < t.n_levels(); ++l)
         for (uint32_t i = t.level_start[l]; i < t.level_start[l + 1]; ++i) {
             oplvl[i] = (uint32_t)l + 1;
@@ -191,6 +225,13 @@ int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
             bool is_assert = opc == OP_ASSERT || opc == OP_ASSERT_EQ || opc == OP_ASSERT_BOOL || opc == OP_ASSERT_FITS;
             if (is_assert) continue;
             uint32_t run = opc == OP_BITS ? (t.ops[(size_t)i * 4 + 3] >> 24) + 1u : 1u;
+            if (t.n_bitwords && run > 1) {  // bit plane: the run is word `dst`
+                if (dst >= t.n_bitwords) { g_err = "bit-plane word out of range"; return -11; }
+                if (bitlvl[dst]) { g_err = "bit-plane word written twice"; return -12; }
+                bitlvl[dst] = (uint32_t)l + 1;
+                bitrun[dst] = run;
+                continue;
+            }
             for (uint32_t j = 0; j < run; ++j) {
                 if (dst + j >= t.n_slots) { g_err = "destination out of range"; return -6; }
                 if (++writes[dst + j] > 1) { g_err = "slot written twice"; return -7; }
@@ -199,8 +240,20 @@ int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
         }
     writes[0]++;
     for (uint64_t k = 0; k < t.n_inputs; ++k) writes[t.input_slot[k]]++;
-    for (uint64_t w = 0; w < t.n_witness; ++w)
-        if (writes[w] != 1) { g_err = "witness slot not written exactly once"; return -8; }
+    {   // every witness entry is produced exactly once and no two entries share a place
+        std::vector<uint8_t> seen_slot(t.n_slots, 0), seen_bit((size_t)t.n_bitwords * 32, 0);
+        for (uint64_t w = 0; w < t.n_witness; ++w) {
+            const uint32_t ws = t.witness_slot[w];
+            if (ws & OPERAND_BIT) {
+                const uint32_t pos = ws & OPERAND_BITPOS_MASK;
+                if ((pos >> 5) >= t.n_bitwords || (pos & 31u) >= bitrun[pos >> 5] || seen_bit[pos]++) {
+                    g_err = "witness entry maps to a bad bit-plane position"; return -8;
+                }
+            } else {
+                if (ws >= t.n_slots || writes[ws] != 1 || seen_slot[ws]++) { g_err = "witness slot not written exactly once"; return -8; }
+            }
+        }
+    }
     if (t.n_levels() && t.level_start[t.n_levels()] != t.n_tape_ops()) { g_err = "level table does not cover the tape"; return -2; }
     for (size_t i = 0; i < t.n_tape_ops(); ++i) {
         const uint32_t *opw = &t.ops[i * 4];
@@ -217,6 +270,12 @@ int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
         bool c_imm = op[0] == OP_ASSERT || op[0] == OP_ASSERT_EQ || op[0] == OP_ASSERT_BOOL || op[0] == OP_BITS || op[0] == OP_BITSIP || op[0] == OP_ASSERT_FITS;
         for (int k = 1; k <= 3; ++k) {
             if (k == 3 && c_imm) break;
+            if (!(op[k] & OPERAND_CONST) && (op[k] & OPERAND_BIT)) {
+                const uint32_t pos = op[k] & OPERAND_BITPOS_MASK;
+                if ((pos >> 5) >= t.n_bitwords || (pos & 31u) >= bitrun[pos >> 5]) { g_err = "bit operand out of range"; return -13; }
+                if (bitlvl[pos >> 5] >= oplvl[i]) { g_err = "bit operand not produced in an earlier level"; return -5; }
+                continue;
+            }
             if (!(op[k] & OPERAND_CONST)) {
                 if ((op[k] & OPERAND_RING) && (op[k] & OPERAND_SLOT_MASK) < t.n_slots && !lvl[op[k] & OPERAND_SLOT_MASK]) {
                     g_err = "ring flag on a slot the tape does not write"; return -10;

@@ -38,7 +38,7 @@ def test_tape_matches_oracle(prime, name):
     import zlib
     rng = random.Random(zlib.crc32((prime + name).encode()))
     ins = [gen(rng, d.q) for _ in range(24)]
-    for flags in (0, 4):  # default (signal = signal eliminated) and CW_FLAG_O0
+    for flags in (0, 4, 16):  # default (signal = signal eliminated), CW_FLAG_O0, CW_FLAG_BITPLANE
         wit, st, stats, w2s = hostsim_run(d, ins, flags=flags)
         if flags == 4:
             assert w2s.tolist() == list(range(d.total_signals))
@@ -66,6 +66,10 @@ def test_wide_tapes_and_forwarding_ring():
     wit, st, stats, w2s = hostsim_run(d, [{"a": a, "b": b}])
     assert not st.any()
     assert limbs_to_ints(wit[0])[1:9] == ecdsa_scale_expected(a, b, 2, 5)
+    # bit-plane layout (CW_FLAG_BITPLANE): the range-check bits leave the 32-byte slot store, same witness
+    wit_bp, st_bp, stats_bp, w2s_bp = hostsim_run(d, [{"a": a, "b": b}], flags=16)
+    assert not st_bp.any() and (wit_bp == wit).all() and (w2s_bp == w2s).all()
+    assert int(stats_bp[3]) < int(stats[3]) // 2
     stc = Circuit(d, host_only=True).stats
     assert 0 < stc["n_ring_operands"] <= stc["n_slot_operands"]
     # census of the slots by proven width: every slot is counted once, the range-checked bits dominate

@@ -13,7 +13,7 @@ from circom_b200 import circuits as C
 from oracle.ir_eval import evaluate, check_r1cs
 from tests.util import hostsim_run, limbs_to_ints, edge_values
 
-CW_FLAG_O0, CW_FLAG_NO_PEEPHOLE = 4, 8
+CW_FLAG_O0, CW_FLAG_NO_PEEPHOLE, CW_FLAG_BITPLANE = 4, 8, 16
 
 
 def random_template(d, rng, n_in, n_vals, with_components):
@@ -113,7 +113,7 @@ def test_random_circuits_match_the_evaluator(prime, seed):
     expected = [evaluate(d, inp) for inp in ins]
     for e in expected:
         assert check_r1cs(d, e) == 0
-    for flags in (0, CW_FLAG_NO_PEEPHOLE, CW_FLAG_O0):
+    for flags in (0, CW_FLAG_NO_PEEPHOLE, CW_FLAG_O0, CW_FLAG_BITPLANE, CW_FLAG_BITPLANE | CW_FLAG_O0):
         wit, st, stats, w2s = hostsim_run(d, ins, flags=flags)
         assert not st.any(), (prime, seed, flags, st)
         for i, e in enumerate(expected):

@@ -339,6 +339,8 @@ int cw_circuit_write_dat(const cw_circuit *c, const char *path) {
 int cw_batch_create(const cw_circuit *c, uint32_t batch, int device, cw_batch **out) {
     if (!c || !out || batch == 0) return fail(CW_EINVAL, "bad argument");
     if (c->tape.flags & CW_FLAG_HOST_ONLY) return fail(CW_ESTATE, "circuit was loaded with CW_FLAG_HOST_ONLY");
+    if (c->tape.n_bitwords)  // the lowering and its CPU verification exist (tests), the kernels do not read the layout yet
+        return fail(CW_ESTATE, "CW_FLAG_BITPLANE tapes cannot be executed by this build (lowering-only preview)");
     int rc = ensure_device(device);
     if (rc) return rc;
     const Tape &t = c->tape;

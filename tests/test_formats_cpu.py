@@ -187,3 +187,25 @@ def test_failing_assert_number_matches_oracle():
     wit, st, _, _ = hostsim_run(d, ins)
     ow, ost = COracle(d.to_bytes()).run(flat_inputs(d, ins))
     assert st.tolist() == ost.tolist() == [9, 0, 9]
+
+
+def test_r1cs_with_custom_gate_sections_loads(tmp_path):
+    """circom writes two more sections (types 4 and 5: custom gates list / applications,
+    constraint_writers/src/r1cs_writer.rs:356-454) when a circuit uses custom templates; a reader must skip
+    sections it does not consume (r1cs_reader.rs walks sections by type and size)."""
+    import ctypes
+    from circom_b200 import native
+    d = CircuitDesc("bn128")
+    d.set_main(C.less_than(d, 8))
+    c = Circuit(d, host_only=True)
+    p = str(tmp_path / "a.r1cs")
+    R1cs(c).write(p, 1, 0, 2)
+    raw = bytearray(open(p, "rb").read())
+    nsec = struct.unpack_from("<I", raw, 8)[0]
+    raw[8:12] = struct.pack("<I", nsec + 2)
+    raw += struct.pack("<IQ", 4, 4) + struct.pack("<I", 0)
+    raw += struct.pack("<IQ", 5, 4) + struct.pack("<I", 0)
+    p2 = str(tmp_path / "b.r1cs")
+    open(p2, "wb").write(raw)
+    r = R1cs(p2)
+    assert r.n_constraints == c.stats["n_constraints"] and r.n_wires == c.n_witness

@@ -25,8 +25,15 @@ def circuits():
         "poseidon2": ("bn128", lambda d: C.poseidon(d, 2)),
         "int_div32": ("bn128", lambda d: C.int_div(d, 32)),
         "ecdsa_scale_2x5": ("bn128", lambda d: C.ecdsa_scale(d, 2, 5)),
+        "sha256compression": ("bn128", lambda d: C.sha256_compression(d)),
+        "sha256_64_bls": ("bls12381", lambda d: C.sha256(d, 64)),
         "ecdsa_scale_8x132": ("bn128", lambda d: C.ecdsa_scale(d, 8, 132)),
     }
+
+
+# calculators whose generated C++ takes g++ -O3 more than ten minutes each: built only when asked for by name
+# (tests/golden/make_golden.py), never by the default build
+SLOW = ("sha256compression", "sha256_64_bls")
 
 
 def make_desc(name: str):
@@ -47,7 +54,7 @@ def build(names=None, force: bool = False):
     if not build_ref.have_reference():
         return []
     built = []
-    for name in (names or list(circuits())):
+    for name in (names or [n for n in circuits() if n not in SLOW]):
         p = calc_path(name)
         if not force and os.path.exists(p) and os.path.exists(p + ".dat"):
             continue

@@ -28,7 +28,8 @@ sys.path.insert(0, ROOT)
 
 from oracle import build_calcs  # noqa: E402
 
-NAMES = ["multiplier2", "all_ops", "all_ops_bls", "less_than8", "poseidon2", "int_div32", "ecdsa_scale_2x5"]
+NAMES = ["multiplier2", "all_ops", "all_ops_bls", "less_than8", "poseidon2", "int_div32", "ecdsa_scale_2x5",
+         "sha256compression", "sha256_64_bls"]   # the two SHA calculators take ~11 min of g++ each
 
 
 def gen_inputs(name: str, d, rng: random.Random):
@@ -48,6 +49,16 @@ def gen_inputs(name: str, d, rng: random.Random):
     if name == "int_div32":
         return [{"a": str(a), "b": str(b)} for a, b in
                 [(0, 1), (2**32 - 1, 1), (2**32 - 1, 2**32 - 1), (12345678, 1000), (rng.randrange(2**32), rng.randrange(1, 2**16))]]
+    if name == "sha256compression":   # config C2: hin = SHA-256 IV, inp = one padded block (known answer: hashlib)
+        from circom_b200.circuits.sha256 import H0
+        outs = []
+        for msg in (b"", b"abc", bytes(rng.getrandbits(8) for _ in range(55))):
+            block = msg + b"\x80" + b"\0" * (55 - len(msg)) + (8 * len(msg)).to_bytes(8, "big")
+            outs.append({"hin": [str((H0[j] >> k) & 1) for j in range(8) for k in range(32)],
+                         "inp": [str((block[j // 8] >> (7 - j % 8)) & 1) for j in range(512)]})
+        return outs
+    if name == "sha256_64_bls":
+        return [{"in": [str(rng.getrandbits(1)) for _ in range(64)]} for _ in range(2)] + [{"in": ["0"] * 64}]
     if name.startswith("ecdsa_scale"):
         n = d.main.n_in // 2
         return [{"a": [str(rng.getrandbits(64)) for _ in range(n)], "b": [str(rng.getrandbits(64)) for _ in range(n)]}

@@ -29,7 +29,8 @@ sys.path.insert(0, ROOT)
 from oracle import build_calcs  # noqa: E402
 
 NAMES = ["multiplier2", "all_ops", "all_ops_bls", "less_than8", "poseidon2", "int_div32", "ecdsa_scale_2x5",
-         "sha256compression", "sha256_64_bls"]   # the two SHA calculators take ~11 min of g++ each
+         "sha256compression", "sha256_64_bls",   # the two SHA calculators take ~11 min of g++ each
+         "ecdsa_scale_8x132"]                    # the bench circuit (1.2 M constraints): one case, 38 MB -> 1 MB
 
 
 def gen_inputs(name: str, d, rng: random.Random):
@@ -59,6 +60,9 @@ def gen_inputs(name: str, d, rng: random.Random):
         return outs
     if name == "sha256_64_bls":
         return [{"in": [str(rng.getrandbits(1)) for _ in range(64)]} for _ in range(2)] + [{"in": ["0"] * 64}]
+    if name == "ecdsa_scale_8x132":
+        n = d.main.n_in // 2
+        return [{"a": [str(rng.getrandbits(64)) for _ in range(n)], "b": [str(rng.getrandbits(64)) for _ in range(n)]}]
     if name.startswith("ecdsa_scale"):
         n = d.main.n_in // 2
         return [{"a": [str(rng.getrandbits(64)) for _ in range(n)], "b": [str(rng.getrandbits(64)) for _ in range(n)]}

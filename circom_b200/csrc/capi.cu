@@ -427,6 +427,7 @@ int cw_batch_set_input(cw_batch *b, uint32_t inst, uint64_t h, uint32_t idx, con
     if (idx >= t.hashmap[p].signalsize) return fail(CW_EINVAL, "Input signal array access exceeds the size");
     uint64_t si = t.hashmap[p].signalid + idx;
     uint64_t k = si - (t.n_outputs + 1);
+    if (si < t.n_outputs + 1 || k >= t.n_inputs) return fail(CW_EINVAL, "input signal outside the main inputs");
     if (b->assigned[(size_t)inst * t.n_inputs + k]) return fail(CW_ESTATE, "Signal assigned twice: " + std::to_string(si));
     U256 v;
     memcpy(v.v, limbs, 32);
@@ -768,10 +769,10 @@ int cw_r1cs_load(const char *path, cw_r1cs **out) {
 int cw_r1cs_write(const cw_r1cs *r, const char *path, uint32_t n_pub_out, uint32_t n_pub_in, uint32_t n_prv_in) {
     if (!r || !path) return fail(CW_EINVAL, "null argument");
     try {
-        R1csData d = r->data;
-        d.n_pub_out = n_pub_out;
-        d.n_pub_in = n_pub_in;
-        d.n_prv_in = n_prv_in;
+        R1csData d = r->data;  // CW_KEEP: the count the circuit / the loaded file carries
+        if (n_pub_out != CW_KEEP) d.n_pub_out = n_pub_out;
+        if (n_pub_in != CW_KEEP) d.n_pub_in = n_pub_in;
+        if (n_prv_in != CW_KEEP) d.n_prv_in = n_prv_in;
         write_r1cs(d, r->F, path);
     } catch (const std::exception &e) {
         return fail(CW_EIO, e.what());

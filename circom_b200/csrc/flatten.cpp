@@ -292,7 +292,13 @@ struct Lowerer {
             case CW_OP_MUL: return ba + bb <= lim ? ba + bb : FULL;
             case CW_OP_IDIV: return ba;
             case CW_OP_MOD: return std::min(ba, bb);
-            case CW_OP_SHR: return const_u64(b, k) && k < qb() ? (ba > k ? ba - (uint32_t)k : 0) : ba;
+            // Fr_shr / Fr_shl reverse direction for amounts >= q - qbits ("negative" amounts,
+            // generic/fr.cpp:2157-2173,2233-2249): `a >> b` is then a LEFT shift and can be qbits wide.  The
+            // operand's width is only a bound of the result when the amount provably is a plain one: a constant
+            // below qbits, or a value narrower than qbits - 1 bits (2^(qbits-2) < q - qbits for both primes).
+            case CW_OP_SHR:
+                if (const_u64(b, k)) return k < qb() ? (ba > k ? ba - (uint32_t)k : 0) : FULL;
+                return (b >= 0 && !is_const(b) && bb + 2 <= qb()) ? ba : FULL;
             case CW_OP_SHL: return const_u64(b, k) && ba + k <= lim ? ba + (uint32_t)k : FULL;
             case CW_OP_BAND: return std::min(ba, bb);
             case CW_OP_BOR: case CW_OP_BXOR: return std::max(ba, bb) <= lim ? std::max(ba, bb) : FULL;
@@ -854,42 +860,79 @@ struct Lowerer {
             }
         }
         if (main_tid >= n_tm) throw std::runtime_error("cb2c: bad main template");
-        for (uint32_t i = 0; i < n_names; ++i) {
-            InputInfo in;
-            in.name = r.str();
-            in.signal_id = r.get<uint32_t>();
-            in.size = r.get<uint32_t>();
-            in.hash = fnv1a(in.name.data(), in.name.size());
-            T.inputs.push_back(in);
+        {
+            // main-input name table: every name covers a run of the main component's input signals
+            // (signal ids 1 + n_out ... n_out + n_in), no two names overlap
+            const Tmpl &M = tm[main_tid];
+            const uint64_t in_lo = 1 + (uint64_t)M.n_out, in_hi = in_lo + M.n_in;
+            std::vector<uint8_t> covered(M.n_in, 0);
+            for (uint32_t i = 0; i < n_names; ++i) {
+                InputInfo in;
+                in.name = r.str();
+                in.signal_id = r.get<uint32_t>();
+                in.size = r.get<uint32_t>();
+                if (in.size < 1 || in.signal_id < in_lo || in.signal_id + in.size > in_hi)
+                    throw std::runtime_error("cb2c: input name '" + in.name + "' lies outside the main inputs");
+                for (uint64_t k = in.signal_id - in_lo; k < in.signal_id - in_lo + in.size; ++k)
+                    if (covered[k]++) throw std::runtime_error("cb2c: input names overlap at '" + in.name + "'");
+                in.hash = fnv1a(in.name.data(), in.name.size());
+                T.inputs.push_back(in);
+            }
         }
-        // function bodies -> device register-machine code (fr_device.cuh: vm_run)
+        // function bodies -> device register-machine code (fr_device.cuh: vm_run).  Untrusted like everything else
+        // in the file: every register, array base, jump target and opcode is checked here, the interpreter then
+        // only bounds-checks run-time indices.
         for (uint32_t i = 0; i < n_funcs; ++i) {
             r.str();
             uint32_t n_params = r.get<uint32_t>(), n_regs = r.get<uint32_t>(), n_instr = r.get<uint32_t>();
             if (n_regs > 192 || n_params > n_regs) throw std::runtime_error("cb2c: function needs too many registers");
+            r.expect(n_instr, 40);
             T.fn_info.push_back((uint32_t)(T.fn_code.size() / 5));
             T.fn_info.push_back(n_instr);
             T.fn_info.push_back(n_regs);
             T.fn_info.push_back(n_params);
+            auto bad = [&](const char *what) { throw std::runtime_error(std::string("cb2c: function body: ") + what); };
+            auto reg = [&](uint64_t w) -> uint32_t {   // a register
+                if (rk(w) != K_TMP || ridx(w) >= n_regs) bad("bad register");
+                return ridx(w);
+            };
+            auto val = [&](uint64_t w, bool may_be_none) -> uint32_t {   // a value operand: register, constant, or unused
+                if (rk(w) == K_TMP) return reg(w);
+                if (rk(w) == K_CONST) {
+                    if (ridx(w) >= n_consts) bad("bad constant");
+                    return OPERAND_CONST | raw_const(ir_consts[ridx(w)]);  // canonical
+                }
+                if (rk(w) != K_NONE || !may_be_none) bad("bad operand");
+                return 0x40000000u;  // unused: the immediate 0
+            };
+            auto imm = [&](uint64_t w, uint32_t limit) -> uint32_t {     // an immediate below `limit`
+                if (rk(w) != K_NONE || ridx(w) >= limit) bad("immediate out of range");
+                return 0x40000000u | ridx(w);
+            };
             for (uint32_t k = 0; k < n_instr; ++k) {
                 uint64_t w[5];
                 for (auto &x : w) x = r.get<uint64_t>();
-                T.fn_code.push_back((uint32_t)w[0]);
-                for (int j = 1; j < 5; ++j) {
-                    uint32_t enc;
-                    switch (rk(w[j])) {
-                        case K_TMP:
-                            if (ridx(w[j]) >= n_regs) throw std::runtime_error("cb2c: bad register");
-                            enc = ridx(w[j]);
-                            break;
-                        case K_CONST:
-                            if (ridx(w[j]) >= n_consts) throw std::runtime_error("cb2c: bad constant");
-                            enc = OPERAND_CONST | raw_const(ir_consts[ridx(w[j])]);  // canonical
-                            break;
-                        default: enc = 0x40000000u | (ridx(w[j]) & 0x3FFFFFFFu); break;  // immediate / unused
-                    }
-                    T.fn_code.push_back(enc);
+                uint32_t op = (uint32_t)w[0], e[4] = {0x40000000u, 0x40000000u, 0x40000000u, 0x40000000u};
+                if (w[0] >> 32) bad("unknown opcode");
+                switch (op) {
+                    case 40 /* JMP */: e[1] = imm(w[2], n_instr); break;
+                    case 41 /* JZ */: e[1] = val(w[2], false); e[2] = imm(w[3], n_instr); break;
+                    case 42 /* RET */: e[1] = val(w[2], false); break;
+                    case 43 /* LOADX: d = regs[base + b] */:
+                        e[0] = reg(w[1]); e[1] = imm(w[2], n_regs); e[2] = val(w[3], false);
+                        break;
+                    case 44 /* STOREX: regs[base + b] = c */:
+                        e[1] = imm(w[2], n_regs); e[2] = val(w[3], false); e[3] = val(w[4], false);
+                        break;
+                    default:
+                        if (op < CW_OP_MUL || op > CW_OP_INV || op == CW_OP_ASSERT || op == CW_OP_ASSERT_EQ) bad("unknown opcode");
+                        e[0] = reg(w[1]);
+                        e[1] = val(w[2], false);
+                        e[2] = val(w[3], true);
+                        e[3] = val(w[4], true);
                 }
+                T.fn_code.push_back(op);
+                for (uint32_t x : e) T.fn_code.push_back(x);
             }
         }
     }

@@ -90,7 +90,7 @@ void read_r1cs(const std::string &path, R1csData &out) {
     std::vector<uint8_t> buf(sz);
     if (sz && fread(buf.data(), 1, sz, f.f) != (size_t)sz) throw std::runtime_error("r1cs: read failed");
     auto need = [&](size_t off, size_t n) {
-        if (off + n > buf.size()) throw std::runtime_error("r1cs: truncated file");
+        if (n > buf.size() || off > buf.size() - n) throw std::runtime_error("r1cs: truncated file");  // (no wrap for n near 2^64)
     };
     auto u32 = [&](size_t off) { need(off, 4); uint32_t v; memcpy(&v, &buf[off], 4); return v; };
     auto u64 = [&](size_t off) { need(off, 8); uint64_t v; memcpy(&v, &buf[off], 8); return v; };
@@ -109,6 +109,7 @@ void read_r1cs(const std::string &path, R1csData &out) {
         pos += len;
     }
     if (!hdr || !cons) throw std::runtime_error("r1cs: missing header or constraint section");
+    need(hdr, 4 + 32 + 28);
     uint32_t fs = u32(hdr);
     if (fs != 32 || hdr_len < 4 + 32 + 28) throw std::runtime_error("r1cs: only 32-byte fields are supported");
     U256 q;

@@ -428,7 +428,7 @@ __device__ __forceinline__ void r1cs_lc(u32 *acc, const R1csDev &R, unsigned lon
         // the boolean constraint x*(x-1) = 0 of this wire is checked here, while its value is in registers
         if (brow != 0xFFFFFFFFu && (upper || x[0] > 1u)) atomicMin(first_bad_inst, (unsigned long long)brow);
         if (kd >= 3) {
-            if (!upper && sh <= 222u) {
+            if (!upper && sh + 32u < P.qbits) {  // x < 2^32 and x * 2^sh < 2^(qbits-1) < q
                 // one-limb value times 2^sh: place the (at most 64-bit) shifted value, no reduction needed
                 const u32 wd = sh >> 5, s = sh & 31u;
                 const u32 l = x[0] << s, h = s ? (x[0] >> (32u - s)) : 0u;

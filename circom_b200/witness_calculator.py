@@ -190,6 +190,8 @@ class Circuit:
             if len(arr) > size:
                 raise ValueError("Too many values for input signal %s\n" % k)
             sid = self.input_signal_id(k)
+            if sid < base or sid - base + size > self.n_inputs:
+                raise ValueError("Signal %s lies outside the main inputs\n" % k)
             for i, x in enumerate(arr):
                 if vals[sid - base + i] is not None:
                     raise ValueError("Signal assigned twice: %d" % (sid + i))
@@ -306,8 +308,12 @@ class R1cs:
         ptr, stride = b.witness_strided()
         return self.check(None, batch=b.batch, device=device, device_ptr=ptr, stride=stride)
 
-    def write(self, path: str, n_pub_out: int = 0, n_pub_in: int = 0, n_prv_in: int = 0) -> None:
-        check(lib.cw_r1cs_write(self._h, path.encode(), n_pub_out, n_pub_in, n_prv_in))
+    def write(self, path: str, n_pub_out: Optional[int] = None, n_pub_in: Optional[int] = None,
+              n_prv_in: Optional[int] = None) -> None:
+        """None keeps the count the circuit / the loaded file carries (the header feeds snarkjs' public-signal count)"""
+        keep = 0xFFFFFFFF
+        check(lib.cw_r1cs_write(self._h, path.encode(), keep if n_pub_out is None else n_pub_out,
+                                keep if n_pub_in is None else n_pub_in, keep if n_prv_in is None else n_prv_in))
 
     def check(self, witness, batch: Optional[int] = None, device: int = 0, device_ptr: Optional[int] = None,
               stride: Optional[int] = None):

@@ -158,7 +158,9 @@ int cw_batch_wtns_bytes(cw_batch *b, uint32_t instance, uint8_t *out, size_t cap
 int cw_r1cs_from_circuit(const cw_circuit *c, cw_r1cs **out);
 /* parse a .r1cs file (layout of constraint_writers/src/r1cs_writer.rs:93-101,49-72,246-269,328-341) */
 int cw_r1cs_load(const char *path, cw_r1cs **out);
-/* write it back in the reference's section order (constraint_list/src/r1cs_porting.rs:19-53) */
+/* write it back in the reference's section order (constraint_list/src/r1cs_porting.rs:19-53); a count given as
+ * CW_KEEP keeps the value the circuit / the loaded file carries */
+#define CW_KEEP 0xFFFFFFFFu
 int cw_r1cs_write(const cw_r1cs *r, const char *path, uint32_t n_pub_out, uint32_t n_pub_in, uint32_t n_prv_in);
 int cw_r1cs_info(const cw_r1cs *r, uint64_t *n_wires, uint64_t *n_constraints, uint64_t *nnz, int *prime_id);
 void cw_r1cs_destroy(cw_r1cs *r);

@@ -59,6 +59,11 @@ def random_template(d, rng, n_in, n_vals, with_components):
                 v = terms[0]
                 for x in terms[1:]:
                     v = v + x
+            elif kind == 6 and rng.random() < 0.4:
+                # shift by a SIGNAL: amounts >= q - qbits reverse the direction (generic/fr.cpp:2157-2173), so the
+                # operand's width bounds nothing; the result then feeds a rewrite that trusts the width
+                sh = (a & 0xFF) >> b if rng.random() < 0.5 else (a & 0xFF) << b
+                v = sh * (1 << rng.choice([1, 100, 200])) if rng.random() < 0.7 else sh + (b & 0xFFFF) * 3
             elif kind == 6:
                 v = a << rng.choice([0, 1, 7, 64, 200, 253, 254, 300]) if rng.random() < 0.5 else a >> rng.choice([0, 1, 31, 32, 33, 64, 253, 254, 300])
             elif kind == 7:
@@ -122,3 +127,28 @@ def test_random_circuits_match_the_evaluator(prime, seed):
             if got != want:
                 bad = [j for j in range(len(got)) if got[j] != want[j]][:5]
                 raise AssertionError("prime %s seed %d flags %d input %d: witness entries %s differ" % (prime, seed, flags, i, bad))
+
+
+@pytest.mark.parametrize("prime", ["bn128", "bls12381"])
+def test_shift_by_negative_signal_amount_is_not_treated_as_narrow(prime):
+    """r = (x & 0xFF) >> y with y = q - 200 is a LEFT shift by 200 (Fr_shr, generic/fr.cpp:2189-2263): r is ~208 bits
+    wide, and r * 2^100 must be reduced modulo q - the range analysis once took r for an 8-bit value"""
+    d = CircuitDesc(prime)
+
+    def build(t):
+        x, y = t.input("x"), t.input("y")
+        o = t.output("o", 3)
+        r = (x & 0xFF) >> y
+        t.assign(o[0], r * (1 << 100))
+        l = (x & 0xFF) << y
+        t.assign(o[1], l * (1 << 100))
+        t.assign(o[2], ((x & 0xFFFF) >> (y & 0xF)) * (1 << 230))   # a provably plain amount keeps the fast path
+    d.set_main(d.template("ShiftNeg", (), build))
+    q = d.q
+    ins = [{"x": xv, "y": yv} for xv in (0xAB, q - 1, 0x1FF) for yv in (q - 200, q - 1, q - 253, 3, 0, 254, 255, q - 254, 2**64)]
+    expected = [evaluate(d, inp) for inp in ins]
+    for flags in (0, CW_FLAG_NO_PEEPHOLE, CW_FLAG_BITPLANE):
+        wit, st, stats, w2s = hostsim_run(d, ins, flags=flags)
+        assert not st.any()
+        for i, e in enumerate(expected):
+            assert limbs_to_ints(wit[i]) == [e[k] for k in w2s], (prime, flags, ins[i])

@@ -144,3 +144,62 @@ def test_cli_rejects_pathological_json(tmp_path):
         open(p, "w").write(text)
         r = subprocess.run([cli, cb, p, str(tmp_path / "o.wtns")], capture_output=True)
         assert r.returncode == 1 and needle in r.stderr, (text[:20], r.returncode, r.stderr[-200:])
+
+
+def test_hostile_input_name_table_and_function_bodies():
+    """(signal id, size) of a main-input name and every register / array base / jump target / opcode of a function
+    body come from the file: out-of-range values used to reach host and device memory unchecked"""
+    d = CircuitDesc("bn128")
+    d.set_main(C.int_div(d, 32))          # has a function with loops, LOADX / STOREX
+    good = d.to_bytes()
+    assert try_load(good) == 0
+    # -- the name table: locate the first name record (u32 len, padded name, u32 signal_id, u32 size)
+    name = d.main_inputs()[0][0].encode()
+    at = good.index(struct.pack("<I", len(name)) + name)
+    rec = at + 4 + ((len(name) + 3) & ~3)
+    sid, size = struct.unpack_from("<II", good, rec)
+    for nsid, nsize in ((0x7FFFFF00, 0xFFFFFFFF), (sid, 0), (sid, size + 1000), (0, size), (sid - 1, size), (sid + 1, size + 5)):
+        bad = good[:rec] + struct.pack("<II", nsid, nsize) + good[rec + 8:]
+        assert try_load(bad) == native.CW_EFORMAT, (nsid, nsize)
+        assert b"input name" in lib.cw_last_error()
+    # -- function bodies: 40-byte instructions {op, d, a, b, c} after (name, n_params, n_regs, n_instr)
+    f = d.functions[0]
+    fname = f.name.encode()
+    fat = good.rindex(struct.pack("<I", len(fname)) + fname)
+    code = fat + 4 + ((len(fname) + 3) & ~3) + 12
+    n_instr = struct.unpack_from("<I", good, code - 4)[0]
+    assert n_instr == len(f.code)
+    K_TMP, K_NONE, K_CONST = 4 << 56, 0, 3 << 56
+    rejected = 0
+    for k in range(n_instr):
+        op, dd, a, b, c = struct.unpack_from("<5Q", good, code + 40 * k)
+        trials = [(op, K_NONE | 0x3FFFFF00, a, b, c), (op, K_TMP | 5000, a, b, c), (op, dd, K_TMP | 193, b, c),
+                  (op, dd, a, K_TMP | 100000, c), (0x1FF, dd, a, b, c), (47, dd, a, b, c), (26, dd, a, b, c)]
+        if op in (40,):
+            trials += [(op, dd, K_NONE | n_instr, b, c), (op, dd, K_NONE | 0x3FFFFFFF, b, c)]
+        if op in (41,):
+            trials += [(op, dd, a, K_NONE | (n_instr + 7), c)]
+        if op in (43, 44):
+            trials += [(op, dd, K_NONE | 192, b, c), (op, dd, K_NONE | 0x3FFFFFF0, b, c)]
+        for t in trials:
+            if t == (op, dd, a, b, c):
+                continue
+            bad = good[:code + 40 * k] + struct.pack("<5Q", *t) + good[code + 40 * (k + 1):]
+            rc = try_load(bad)
+            # replacing an unused field (e.g. the destination of a jump) is harmless; everything else must be refused
+            assert rc in (0, native.CW_EFORMAT)
+            rejected += rc == native.CW_EFORMAT
+    assert rejected > 5 * n_instr
+    # truncated in the middle of the code
+    assert try_load(good[:code + 40 * (n_instr // 2) + 3]) == native.CW_EFORMAT
+
+
+def test_set_input_outside_main_inputs_is_refused():
+    """cw_batch_set_input indexes host arrays with (signal id - first input): a hash-map entry pointing elsewhere must
+    not be followed (defence in depth behind the parser's check) - exercised through the Python twin of the lookup"""
+    d = CircuitDesc("bn128")
+    d.set_main(C.multiplier2(d))
+    c = Circuit(d, host_only=True)
+    assert c.flatten_inputs({"a": 3, "b": 11}) == [3, 11]
+    with pytest.raises(ValueError):
+        c.flatten_inputs({"a": 3})

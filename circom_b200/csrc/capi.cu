@@ -7,7 +7,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <thread>
@@ -21,7 +23,6 @@
 
 using namespace cw;
 
-static_assert(cw::RING_N == cw::CW_RING_SIZE, "kernel ring size must match the lowering's");
 namespace {
 
 thread_local std::string g_err;
@@ -83,19 +84,19 @@ struct DevTape {
     u32 *level_start = nullptr;
     uint4 *consts = nullptr;
     u32 *input_slot = nullptr, *fn_code = nullptr, *fn_info = nullptr, *call_tab = nullptr;
+    u32 *wloc = nullptr;  // per witness entry: where its value lives (slot id, or OPD_BIT | plane position)
+    // witness entries outside the bit plane by static size class (slot ids), for the packed device->host transfer
     u32 *pk_bit = nullptr, *pk_u64 = nullptr, *pk_full = nullptr;
 };
 struct DevR1cs {
     unsigned long long *row_ptr = nullptr;
-    uint4 *terms = nullptr;  // per term {wire, dictionary index, kind word, absorbed boolean row}
+    uint4 *terms = nullptr;  // per term {location, dictionary index, kind word, absorbed boolean row}
     uint4 *dictM = nullptr;
-    u32 *perm = nullptr, *bool_wire = nullptr, *bool_row = nullptr;
+    u32 *perm = nullptr, *bool_loc = nullptr, *bool_row = nullptr;
     u32 n_general = 0, n_bool = 0;
-    u32 n_long = 0;  // perm[0, n_long): rows with >= R1CS_SPLIT_MIN terms, checked by lane groups
-    u32 mean_row_terms = 0;  // terms per general row
+    u32 mean_row_terms = 0;  // compiled terms per general row
+    uint64_t n_terms = 0;
 };
-constexpr uint64_t R1CS_SPLIT_MIN = 16;
-constexpr int R1CS_SPLIT_G = 8;
 
 template <class T>
 int upload(T **dst, const void *src, size_t bytes) {
@@ -109,19 +110,220 @@ int env_int(const char *name, int dflt) {
     return s && *s ? atoi(s) : dflt;
 }
 
+// ---- host side of the packed transfer --------------------------------------------------------------------
+// The witness of one instance arrives as the packed record written by witness_pack_kernel.  The expansion to
+// the reference's 32-byte rows is zero-extension only (no field arithmetic on the CPU) and is described once
+// per circuit by segments of consecutive witness entries that come from the same section of the record.
+struct PackSeg {
+    uint32_t kind;   // 0 plane run, 1 bits outside the plane, 2 u64 entries, 3 full entries
+    uint32_t start;  // first witness entry
+    uint32_t count;
+    uint32_t src;    // plane run: word * 32 + first bit; otherwise the index inside the section
+};
+struct PackLayout {
+    std::vector<PackSeg> segs;
+    std::vector<uint32_t> bit_loc, u64_loc, full_loc;  // slot ids of the entries outside the plane, in witness order
+    size_t n_plane_words = 0, n_bit_words = 0, words = 0;  // words: per instance, rounded to 16 bytes
+};
+
+void build_pack_layout(const Tape &t, PackLayout &L) {
+    const size_t W = t.n_witness;
+    L.n_plane_words = t.n_bitwords;
+    for (size_t i = 0; i < W; ++i) {
+        const uint32_t loc = t.witness_slot[i];
+        PackSeg sg;
+        sg.start = (uint32_t)i;
+        sg.count = 1;
+        if (loc & OPERAND_BIT) {
+            sg.kind = 0;
+            sg.src = loc & OPERAND_BITPOS_MASK;
+        } else if (t.wit_class[i] == 0) {
+            sg.kind = 1;
+            sg.src = (uint32_t)L.bit_loc.size();
+            L.bit_loc.push_back(loc);
+        } else if (t.wit_class[i] == 1) {
+            sg.kind = 2;
+            sg.src = (uint32_t)L.u64_loc.size();
+            L.u64_loc.push_back(loc);
+        } else {
+            sg.kind = 3;
+            sg.src = (uint32_t)L.full_loc.size();
+            L.full_loc.push_back(loc);
+        }
+        if (!L.segs.empty()) {
+            PackSeg &p = L.segs.back();
+            // (a plane run stays inside its word)
+            const bool same_word = sg.kind != 0 || ((p.src + p.count) >> 5) == (p.src >> 5);
+            if (p.kind == sg.kind && p.src + p.count == sg.src && same_word) {
+                ++p.count;
+                continue;
+            }
+        }
+        L.segs.push_back(sg);
+    }
+    L.n_bit_words = (L.bit_loc.size() + 31) / 32;
+    L.words = (L.n_plane_words + L.n_bit_words + 2 * L.u64_loc.size() + 8 * L.full_loc.size() + 3) & ~(size_t)3;
+}
+
+// one instance: packed record -> W rows of 32 bytes, written once, front to back, with streaming stores
+void expand_record(const PackLayout &L, const uint32_t *rec, uint64_t *row_out) {
+    const uint32_t *plane = rec, *xb = rec + L.n_plane_words, *pu = xb + L.n_bit_words, *pf = pu + 2 * L.u64_loc.size();
+    const bool aligned = (((uintptr_t)row_out) & 15u) == 0;
+    const __m128i zero = _mm_setzero_si128();
+    auto put = [&](uint64_t *dst, __m128i lo, __m128i hi) {
+        if (aligned) {
+            _mm_stream_si128((__m128i *)dst, lo);
+            _mm_stream_si128((__m128i *)(dst + 2), hi);
+        } else {
+            _mm_storeu_si128((__m128i *)dst, lo);
+            _mm_storeu_si128((__m128i *)(dst + 2), hi);
+        }
+    };
+    for (const PackSeg &sg : L.segs) {
+        uint64_t *dst = row_out + 4 * (size_t)sg.start;
+        switch (sg.kind) {
+            case 0: {
+                uint32_t bits = plane[sg.src >> 5] >> (sg.src & 31u);
+                for (uint32_t j = 0; j < sg.count; ++j, dst += 4, bits >>= 1)
+                    put(dst, _mm_cvtsi64_si128((long long)(bits & 1u)), zero);
+                break;
+            }
+            case 1:
+                for (uint32_t j = 0; j < sg.count; ++j, dst += 4) {
+                    const uint32_t k = sg.src + j;
+                    put(dst, _mm_cvtsi64_si128((long long)((xb[k >> 5] >> (k & 31u)) & 1u)), zero);
+                }
+                break;
+            case 2:
+                for (uint32_t j = 0; j < sg.count; ++j, dst += 4)
+                    put(dst, _mm_loadl_epi64((const __m128i *)(pu + 2 * (size_t)(sg.src + j))), zero);
+                break;
+            default:
+                for (uint32_t j = 0; j < sg.count; ++j, dst += 4) {
+                    const uint32_t *f = pf + 8 * (size_t)(sg.src + j);
+                    put(dst, _mm_loadu_si128((const __m128i *)f), _mm_loadu_si128((const __m128i *)(f + 4)));
+                }
+        }
+    }
+    _mm_sfence();
+}
+
+// persistent worker threads for the host-side expansion (created on first use, shared by all batches of the process)
+class Pool {
+  public:
+    static Pool &get() {
+        static Pool p;
+        return p;
+    }
+    unsigned size() const { return (unsigned)th_.size() + 1; }
+    // runs fn(i) for i in [0, n) on the workers and the calling thread; returns when all are done
+    void parallel_for(size_t n, const std::function<void(size_t)> &fn) {
+        if (n == 0) return;
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return !busy_; });  // one parallel_for at a time
+        busy_ = true;
+        fn_ = &fn;
+        n_ = n;
+        next_ = 0;
+        pending_ = n;
+        ++gen_;
+        lk.unlock();
+        cv_.notify_all();
+        work();
+        lk.lock();
+        done_cv_.wait(lk, [&] { return pending_ == 0; });
+        busy_ = false;
+        fn_ = nullptr;
+        lk.unlock();
+        done_cv_.notify_all();
+    }
+
+  private:
+    Pool() {
+        unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        // several ranks of one host share its cores (torchrun sets LOCAL_WORLD_SIZE)
+        unsigned ranks = (unsigned)std::max(1, env_int("LOCAL_WORLD_SIZE", 1));
+        unsigned dflt = std::max(4u, std::min(32u, hw / ranks));
+        unsigned nt = (unsigned)std::max(1, env_int("CW_UNPACK_THREADS", (int)dflt));
+        nt = std::min(nt, hw);
+        for (unsigned i = 1; i < nt; ++i) th_.emplace_back([this] { loop(); });
+    }
+    ~Pool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    void work() {
+        for (;;) {
+            size_t i;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (!fn_ || next_ >= n_) return;
+                i = next_++;
+            }
+            (*fn_)(i);
+            bool last;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                last = --pending_ == 0;
+            }
+            if (last) done_cv_.notify_all();
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+            }
+            work();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(size_t)> *fn_ = nullptr;
+    size_t n_ = 0, next_ = 0, pending_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false, busy_ = false;
+};
+
 }  // namespace
 
 struct cw_circuit {
     Tape tape;
     mutable std::mutex mu;
     mutable std::map<int, DevTape> dev;
+    mutable PackLayout pack;
+    mutable bool pack_ready = false;
+    const PackLayout &pack_layout() const {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!pack_ready) {
+            build_pack_layout(tape, pack);
+            pack_ready = true;
+        }
+        return pack;
+    }
 };
 
+struct R1csKey {
+    int device;
+    const cw_circuit *layout;  // nullptr: dense witness rows (location = wire id)
+    bool operator<(const R1csKey &o) const { return device != o.device ? device < o.device : layout < o.layout; }
+};
 struct cw_r1cs {
     R1csData data;
     FieldParams F;
     std::mutex mu;
-    std::map<int, DevR1cs> dev;
+    std::map<R1csKey, DevR1cs> dev;
+    cw_r1cs *eval_twin = nullptr;  // the same constraints compiled without boolean-row special cases (cw_r1cs_eval_batch)
+    bool no_bool_rows = false;
 };
 
 struct cw_batch {
@@ -130,8 +332,10 @@ struct cw_batch {
     u32 batch = 0, batch_padded = 0, bt_log2 = 0, threads = 256;
     cudaStream_t stream = nullptr;
     uint4 *slots = nullptr, *inputs_d = nullptr, *witness_d = nullptr;
+    u32 *plane = nullptr;
     u32 *first_assert_d = nullptr;
     int *err_d = nullptr;
+    unsigned long long *fb_d = nullptr;  // per-instance result of the R1CS check
     DevTape dt;
     std::vector<uint64_t> host_inputs;  // [batch][n_inputs][4]
     std::vector<uint8_t> assigned;      // [batch][n_inputs]
@@ -139,14 +343,39 @@ struct cw_batch {
     bool host_inputs_dirty = false;
     bool inputs_on_device = false;
     bool ran = false;
-    bool compact_valid = false;  // witness_d holds the contiguous copy of the current run
-    u32 *packed_d = nullptr, *packed_h = nullptr;  // packed witness staging (device / pinned host)
+    bool dense_valid = false;  // witness_d holds the dense rows of the current run
+    // packed transfer: two staging buffers (device + pinned host) so that the pack kernel and the copy of one
+    // chunk overlap the host-side expansion of the previous one
+    u32 *packed_d[2] = {nullptr, nullptr}, *packed_h[2] = {nullptr, nullptr};
+    size_t packed_cap = 0;  // instances per staging buffer
+    uint4 *dense_chunk_d = nullptr;
+    size_t dense_chunk_cap = 0;
     int *pack_flag_d = nullptr;
+    cudaEvent_t pack_ev[2] = {nullptr, nullptr};
     uint64_t last_d2h_bytes = 0;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    std::thread async_th;  // cw_batch_get_witness_async
+    int async_rc = 0;
+    std::string async_err;
+    bool async_active = false;
+    bool identity_layout() const {  // witness row i = the first n_witness slots of instance i's slot store
+        const Tape &t = c->tape;
+        return bt_log2 == 0 && t.n_bitwords == 0 && t.n_resident == t.n_witness;
+    }
+    StoreDev store() const {
+        StoreDev S;
+        S.slots = slots;
+        S.plane = plane;
+        S.n_slots = c->tape.n_slots;
+        S.n_bitwords = c->tape.n_bitwords;
+        S.bt_log2 = bt_log2;
+        S.batch = batch;
+        return S;
+    }
 };
 
 static int get_dev_tape(const cw_circuit *c, int device, DevTape &out) {
+    const PackLayout &L = c->pack_layout();
     std::lock_guard<std::mutex> lk(c->mu);
     auto it = c->dev.find(device);
     if (it != c->dev.end()) {
@@ -163,9 +392,10 @@ static int get_dev_tape(const cw_circuit *c, int device, DevTape &out) {
     if ((rc = upload(&d.fn_code, t.fn_code.data(), t.fn_code.size() * 4))) return rc;
     if ((rc = upload(&d.fn_info, t.fn_info.data(), t.fn_info.size() * 4))) return rc;
     if ((rc = upload(&d.call_tab, t.call_tab.data(), t.call_tab.size() * 4))) return rc;
-    if ((rc = upload(&d.pk_bit, t.pk_bit_wire.data(), t.pk_bit_wire.size() * 4))) return rc;
-    if ((rc = upload(&d.pk_u64, t.pk_u64_wire.data(), t.pk_u64_wire.size() * 4))) return rc;
-    if ((rc = upload(&d.pk_full, t.pk_full_wire.data(), t.pk_full_wire.size() * 4))) return rc;
+    if ((rc = upload(&d.wloc, t.witness_slot.data(), t.witness_slot.size() * 4))) return rc;
+    if ((rc = upload(&d.pk_bit, L.bit_loc.data(), L.bit_loc.size() * 4))) return rc;
+    if ((rc = upload(&d.pk_u64, L.u64_loc.data(), L.u64_loc.size() * 4))) return rc;
+    if ((rc = upload(&d.pk_full, L.full_loc.data(), L.full_loc.size() * 4))) return rc;
     c->dev[device] = d;
     out = d;
     return CW_OK;
@@ -222,6 +452,7 @@ void cw_circuit_destroy(cw_circuit *c) {
         cudaFree(kv.second.fn_code);
         cudaFree(kv.second.fn_info);
         cudaFree(kv.second.call_tab);
+        cudaFree(kv.second.wloc);
         cudaFree(kv.second.pk_bit);
         cudaFree(kv.second.pk_u64);
         cudaFree(kv.second.pk_full);
@@ -249,7 +480,8 @@ int cw_circuit_stats(const cw_circuit *c, cw_stats *o) {
     o->n_conv_ops = t.n_conv_ops;
     o->max_level_width = t.max_level_width;
     o->n_slot_operands = t.n_slot_operands;
-    o->n_ring_operands = t.n_ring_operands;
+    o->n_bitwords = t.n_bitwords;
+    o->n_resident_slots = t.n_resident;
     return CW_OK;
 }
 
@@ -339,8 +571,6 @@ int cw_circuit_write_dat(const cw_circuit *c, const char *path) {
 int cw_batch_create(const cw_circuit *c, uint32_t batch, int device, cw_batch **out) {
     if (!c || !out || batch == 0) return fail(CW_EINVAL, "bad argument");
     if (c->tape.flags & CW_FLAG_HOST_ONLY) return fail(CW_ESTATE, "circuit was loaded with CW_FLAG_HOST_ONLY");
-    if (c->tape.n_bitwords)  // the lowering and its CPU verification exist (tests), the kernels do not read the layout yet
-        return fail(CW_ESTATE, "CW_FLAG_BITPLANE tapes cannot be executed by this build (lowering-only preview)");
     int rc = ensure_device(device);
     if (rc) return rc;
     const Tape &t = c->tape;
@@ -348,15 +578,19 @@ int cw_batch_create(const cw_circuit *c, uint32_t batch, int device, cw_batch **
     b->c = c;
     b->device = device;
     b->batch = batch;
-    // tile size: keep at least ~4 CTAs per SM in flight before widening tiles for coalescing
+    // Tile size (instances side by side in the slot store).  Lanes along instances (32-instance tiles: a warp is one
+    // op, every access coalesced, no divergence) need enough tiles to fill the GPU with CTAs; below that, lanes run
+    // along the ops of a level (one-instance tiles).  Tapes with function calls keep one-instance tiles (the
+    // interpreter's frame is per thread and lanes diverge inside calls anyway).
     int bt = env_int("CW_BT_LOG2", -1);
+    const uint64_t avg_w = t.n_levels() ? t.n_tape_ops() / t.n_levels() + 1 : 1;
     if (bt < 0) {
-        // BT = 1 keeps witness rows contiguous in the slot store (no compaction) and is as fast as wider tiles
-        // whenever a level has enough ops to fill warps; very narrow tapes (Poseidon: ~3 ops per level)
-        // need instances side by side in a warp instead
-        uint64_t avg_w = t.n_levels() ? t.n_tape_ops() / t.n_levels() + 1 : 1;
         bt = 0;
-        while (bt < 5 && (avg_w << bt) < 64 && (batch >> (bt + 1)) >= 296u) ++bt;
+        if (t.call_tab.empty()) {
+            if (batch >= 32u * 148u * 2u) bt = 5;
+            else
+                while (bt < 5 && (avg_w << bt) < 64 && (batch >> (bt + 1)) >= 296u) ++bt;  // very narrow tapes (Poseidon)
+        }
     }
     if (bt > 5) bt = 5;
     b->bt_log2 = (u32)bt;
@@ -365,7 +599,7 @@ int cw_batch_create(const cw_circuit *c, uint32_t batch, int device, cw_batch **
     int th = env_int("CW_THREADS", 0);
     if (th <= 0) {
         // enough threads for a typical level: average width x tile, clamped to [64, 512]
-        uint64_t avg = t.n_levels() ? (t.n_tape_ops() / t.n_levels() + 1) * btn : 64;
+        uint64_t avg = avg_w * btn;
         th = 64;
         while (th < 512 && (uint64_t)th < avg) th <<= 1;
         // many tiles per SM hide latency better than wide CTAs: keep <= ~1024 resident threads per SM
@@ -373,14 +607,16 @@ int cw_batch_create(const cw_circuit *c, uint32_t batch, int device, cw_batch **
         u32 tiles = b->batch_padded >> bt;
         u32 per_sm = (tiles + 147) / 148;
         while (th > 64 && (u32)th * per_sm > 1024) th >>= 1;
+        if (tiles < 148u) th = (int)std::min<uint64_t>(1024, std::max<uint64_t>(th, (avg + 31) / 32 * 32));  // few tiles: wide CTAs
     }
     th = (th + 31) / 32 * 32;
     if (th > 1024) th = 1024;
     b->threads = (u32)th;
     size_t slot_bytes = (size_t)b->batch_padded * t.n_slots * 32;
+    size_t plane_bytes = (size_t)b->batch_padded * t.n_bitwords * 4;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    size_t need = slot_bytes + (size_t)batch * t.n_inputs * 32 + (64u << 20);
+    size_t need = slot_bytes + plane_bytes + (size_t)batch * t.n_inputs * 32 + (64u << 20);
     if (need > free_b) {
         delete b;
         return fail(CW_ECUDA, "batch needs " + std::to_string(need >> 20) + " MiB of device memory, " +
@@ -389,10 +625,13 @@ int cw_batch_create(const cw_circuit *c, uint32_t batch, int device, cw_batch **
     if ((rc = get_dev_tape(c, device, b->dt))) { delete b; return rc; }
     CU(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     CU(cudaMalloc((void **)&b->slots, slot_bytes));
+    CU(cudaMalloc((void **)&b->plane, std::max<size_t>(plane_bytes, 16)));
     CU(cudaMalloc((void **)&b->inputs_d, std::max<size_t>((size_t)batch * t.n_inputs * 32, 32)));
     CU(cudaMalloc((void **)&b->first_assert_d, (size_t)batch * 4));
     CU(cudaMalloc((void **)&b->err_d, (size_t)batch * 4));
+    CU(cudaMalloc((void **)&b->fb_d, (size_t)batch * 8));
     for (auto &e : b->ev) CU(cudaEventCreate(&e));
+    for (auto &e : b->pack_ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     b->host_inputs.assign((size_t)batch * t.n_inputs * 4, 0);
     b->assigned.assign((size_t)batch * t.n_inputs, 0);
     b->remaining.assign(batch, (u32)t.n_inputs);
@@ -400,21 +639,41 @@ int cw_batch_create(const cw_circuit *c, uint32_t batch, int device, cw_batch **
     return CW_OK;
 }
 
+static void join_async(cw_batch *b) {
+    if (b->async_th.joinable()) b->async_th.join();
+    b->async_active = false;
+}
+
 void cw_batch_destroy(cw_batch *b) {
     if (!b) return;
+    join_async(b);
     cudaSetDevice(b->device);
     cudaFree(b->slots);
+    cudaFree(b->plane);
     cudaFree(b->inputs_d);
     cudaFree(b->witness_d);
-    cudaFree(b->packed_d);
+    cudaFree(b->dense_chunk_d);
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(b->packed_d[k]);
+        if (b->packed_h[k]) cudaFreeHost(b->packed_h[k]);
+        if (b->pack_ev[k]) cudaEventDestroy(b->pack_ev[k]);
+    }
     cudaFree(b->pack_flag_d);
-    if (b->packed_h) cudaFreeHost(b->packed_h);
     cudaFree(b->first_assert_d);
     cudaFree(b->err_d);
+    cudaFree(b->fb_d);
     for (auto &e : b->ev)
         if (e) cudaEventDestroy(e);
     if (b->stream) cudaStreamDestroy(b->stream);
     delete b;
+}
+
+int cw_batch_layout(const cw_batch *b, uint32_t *bt_log2, uint32_t *threads, uint64_t *bytes_per_instance) {
+    if (!b) return fail(CW_EINVAL, "null argument");
+    if (bt_log2) *bt_log2 = b->bt_log2;
+    if (threads) *threads = b->threads;
+    if (bytes_per_instance) *bytes_per_instance = (uint64_t)b->c->tape.n_slots * 32 + (uint64_t)b->c->tape.n_bitwords * 4;
+    return CW_OK;
 }
 
 int cw_batch_set_input(cw_batch *b, uint32_t inst, uint64_t h, uint32_t idx, const uint64_t limbs[4]) {
@@ -447,6 +706,7 @@ int cw_batch_remaining_inputs(const cw_batch *b, uint32_t inst, uint32_t *rem) {
 
 int cw_batch_set_inputs(cw_batch *b, const uint64_t *inputs, int is_device_ptr) {
     if (!b || !inputs) return fail(CW_EINVAL, "null argument");
+    if (b->async_active) return fail(CW_ESTATE, "a witness transfer of this batch is in flight (cw_batch_get_witness_wait)");
     const Tape &t = b->c->tape;
     CU(cudaSetDevice(b->device));
     size_t bytes = (size_t)b->batch * t.n_inputs * 32;
@@ -460,6 +720,7 @@ int cw_batch_set_inputs(cw_batch *b, const uint64_t *inputs, int is_device_ptr) 
 
 int cw_batch_run(cw_batch *b) {
     if (!b) return fail(CW_EINVAL, "null argument");
+    if (b->async_active) return fail(CW_ESTATE, "a witness transfer of this batch is in flight (cw_batch_get_witness_wait)");
     const Tape &t = b->c->tape;
     CU(cudaSetDevice(b->device));
     if (b->host_inputs_dirty || !b->inputs_on_device) {
@@ -484,6 +745,7 @@ int cw_batch_run(cw_batch *b) {
     tp.fn_info = b->dt.fn_info;
     tp.call_tab = b->dt.call_tab;
     tp.n_inputs = (u32)t.n_inputs;
+    tp.n_bitwords = t.n_bitwords;
     CU(cudaMemsetAsync(b->first_assert_d, 0xFF, (size_t)b->batch * 4, b->stream));
     CU(cudaMemsetAsync(b->err_d, 0, (size_t)b->batch * 4, b->stream));
     CU(cudaEventRecord(b->ev[0], b->stream));
@@ -495,33 +757,34 @@ int cw_batch_run(cw_batch *b) {
     u32 tiles = b->batch_padded >> b->bt_log2;
     if (tp.n_levels) {
         const bool calls = !t.call_tab.empty();
+        const bool bp = t.n_bitwords != 0;
         const u32 th = calls ? std::min<u32>(b->threads, 256u) : b->threads;  // the interpreter build has a large frame
-        // The shared-memory forwarding ring (kernels.cuh) is opt-in (env CW_RING=1; BT = 1 layouts): measured on
-        // B200 it does not shorten the step (21.99 ms with, 21.51 ms without, batch 1024 of the bench circuit -
-        // operand latency is not what bounds the interpreter) and its 16 KB per CTA come out of L1.
-        const bool ring = !calls && b->bt_log2 == 0 && env_int("CW_RING", 0) != 0;
-        const size_t smem = ring ? (size_t)2 * RING_N * sizeof(uint4) : 0;
-#define CW_LAUNCH_TAPE(PR, CALLS, RING_, BT_)                                                                  \
-    tape_exec_kernel<PR, CALLS, RING_, BT_><<<tiles, th, smem, b->stream>>>(tp, b->slots, b->bt_log2,            \
-                                                                              b->first_assert_d, b->err_d, b->batch)
-        // builds: calls (runtime tile size), ring (BT = 1 instance), plain with BT = 1 instance fixed at compile
-        // time, plain with the tile size as an argument
-        const bool bt0 = b->bt_log2 == 0;
-        if (t.F.prime_id == 0) {
-            if (calls) CW_LAUNCH_TAPE(0, true, false, -1);
-            else if (ring) CW_LAUNCH_TAPE(0, false, true, 0);
-            else if (bt0) CW_LAUNCH_TAPE(0, false, false, 0);
-            else CW_LAUNCH_TAPE(0, false, false, -1);
-        } else {
-            if (calls) CW_LAUNCH_TAPE(1, true, false, -1);
-            else if (ring) CW_LAUNCH_TAPE(1, false, true, 0);
-            else if (bt0) CW_LAUNCH_TAPE(1, false, false, 0);
-            else CW_LAUNCH_TAPE(1, false, false, -1);
-        }
+#define CW_LAUNCH_TAPE(PR, CALLS, BP_, BT_)                                                                   \
+    tape_exec_kernel<PR, CALLS, BP_, BT_><<<tiles, th, 0, b->stream>>>(tp, b->slots, b->plane, b->bt_log2,     \
+                                                                         b->first_assert_d, b->err_d, b->batch)
+        // builds: calls (runtime tile size), and per bit-plane mode: one instance per tile / a warp per op (tile sizes
+        // fixed at compile time) / tile size as an argument
+#define CW_LAUNCH_PRIME(PR)                                          \
+    do {                                                             \
+        if (calls) {                                                 \
+            if (bp) CW_LAUNCH_TAPE(PR, true, true, -1);              \
+            else CW_LAUNCH_TAPE(PR, true, false, -1);                \
+        } else if (bp) {                                             \
+            if (b->bt_log2 == 0) CW_LAUNCH_TAPE(PR, false, true, 0); \
+            else if (b->bt_log2 == 5) CW_LAUNCH_TAPE(PR, false, true, 5); \
+            else CW_LAUNCH_TAPE(PR, false, true, -1);                \
+        } else {                                                     \
+            if (b->bt_log2 == 0) CW_LAUNCH_TAPE(PR, false, false, 0); \
+            else CW_LAUNCH_TAPE(PR, false, false, -1);               \
+        }                                                            \
+    } while (0)
+        if (t.F.prime_id == 0) CW_LAUNCH_PRIME(0);
+        else CW_LAUNCH_PRIME(1);
+#undef CW_LAUNCH_PRIME
 #undef CW_LAUNCH_TAPE
     }
     CU(cudaEventRecord(b->ev[1], b->stream));
-    b->compact_valid = false;  // witness rows are slots [0, n_witness) of each instance: nothing to gather
+    b->dense_valid = false;
     CU(cudaEventRecord(b->ev[2], b->stream));
     CU(cudaGetLastError());
     b->ran = true;
@@ -551,107 +814,114 @@ int cw_batch_status(cw_batch *b, int32_t *status) {
     return CW_OK;
 }
 
-// contiguous [batch][n_witness] copy in device memory (only needed for tile layouts with BT > 1 or when
-// a caller insists on a dense device array)
-static int compact_witness(cw_batch *b) {
-    if (b->compact_valid) return CW_OK;
+// dense witness rows of instances [first, first + count) into `dst` (device, 32-byte aligned), on the batch stream
+static int expand_rows(cw_batch *b, u32 first, u32 count, uint4 *dst) {
     const Tape &t = b->c->tape;
-    if (!b->witness_d) CU(cudaMalloc((void **)&b->witness_d, (size_t)b->batch * t.n_witness * 32));
-    if (b->bt_log2 == 0) {
-        CU(cudaMemcpy2DAsync(b->witness_d, (size_t)t.n_witness * 32, b->slots, (size_t)t.n_slots * 32,
-                             (size_t)t.n_witness * 32, b->batch, cudaMemcpyDeviceToDevice, b->stream));
-    } else {
-        u32 tiles = b->batch_padded >> b->bt_log2;
-        size_t total = (size_t)tiles * t.n_witness << b->bt_log2;
-        u32 grid = (u32)std::min<size_t>((total + 255) / 256, 148 * 16);
-        witness_compact_kernel<<<grid, 256, 0, b->stream>>>(b->slots, b->witness_d, t.n_slots, (u32)t.n_witness, b->batch, b->bt_log2);
-        CU(cudaGetLastError());
-    }
-    b->compact_valid = true;
+    if (count == 0) return CW_OK;
+    dim3 grid((u32)std::min<size_t>((t.n_witness + 255) / 256, 148 * 4), std::min<u32>(count, 65535u));
+    witness_expand_kernel<<<grid, 256, 0, b->stream>>>(b->store(), b->dt.wloc, (u32)t.n_witness, first, count, dst);
+    CU(cudaGetLastError());
     return CW_OK;
 }
 
-// Packed transfer: entries the lowering proved to be one bit / <= 64 bits cross PCIe as that, the host
-// expands them to the canonical 32-byte rows (zero-extension only - no field arithmetic happens on the CPU).
-// For circuits made of bit decompositions this cuts the device->host bytes by an order of magnitude; the
-// expansion runs on a few host threads at memory speed.  CW_PACKED_D2H=0 forces the plain pitched copy.
+// contiguous [batch][n_witness] copy in device memory, for callers that want the reference's layout on the device
+static int dense_witness(cw_batch *b) {
+    if (b->dense_valid) return CW_OK;
+    const Tape &t = b->c->tape;
+    if (!b->witness_d) {
+        size_t bytes = (size_t)b->batch * t.n_witness * 32, free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (bytes + (64u << 20) > free_b)
+            return fail(CW_ECUDA, "dense witness rows of the whole batch need " + std::to_string(bytes >> 20) +
+                                      " MiB of device memory (" + std::to_string(free_b >> 20) +
+                                      " MiB free): use cw_batch_expand_witness on a range of instances");
+        CU(cudaMalloc((void **)&b->witness_d, bytes));
+    }
+    int rc = expand_rows(b, 0, b->batch, b->witness_d);
+    if (rc) return rc;
+    b->dense_valid = true;
+    return CW_OK;
+}
+
+int cw_batch_expand_witness(cw_batch *b, uint32_t first, uint32_t count, uint64_t *dst_device) {
+    if (!b || !dst_device || (uint64_t)first + count > b->batch) return fail(CW_EINVAL, "bad argument");
+    if (!b->ran) return fail(CW_ESTATE, "batch has not been run");
+    if ((uintptr_t)dst_device & 31u) return fail(CW_EINVAL, "destination must be 32-byte aligned");
+    CU(cudaSetDevice(b->device));
+    return expand_rows(b, first, count, (uint4 *)dst_device);
+}
+
+static size_t pack_chunk_instances(const cw_batch *b, const PackLayout &L) {
+    size_t mb = (size_t)std::max(8, env_int("CW_PACK_CHUNK_MB", 96));
+    size_t n = std::max<size_t>(1, (mb << 20) / (L.words * 4));
+    return std::min<size_t>(n, b->batch);
+}
+
+static int ensure_pack_buffers(cw_batch *b, const PackLayout &L) {
+    if (b->packed_cap) return CW_OK;
+    size_t n = pack_chunk_instances(b, L);
+    for (int k = 0; k < 2; ++k) {
+        CU(cudaMalloc((void **)&b->packed_d[k], n * L.words * 4));
+        CU(cudaMallocHost((void **)&b->packed_h[k], n * L.words * 4));
+    }
+    CU(cudaMalloc((void **)&b->pack_flag_d, 4));
+    b->packed_cap = n;
+    return CW_OK;
+}
+
+// packed records of instances [first, first + count) into `dst_d` (device), on the batch stream
+static int pack_rows(cw_batch *b, const PackLayout &L, u32 first, u32 count, u32 *dst_d) {
+    const size_t items = L.n_plane_words + L.n_bit_words + L.u64_loc.size() + L.full_loc.size();
+    dim3 grid((u32)std::max<size_t>(1, std::min<size_t>((items + 255) / 256, 148 * 4)), std::min<u32>(count, 65535u));
+    witness_pack_kernel<<<grid, 256, 0, b->stream>>>(b->store(), b->dt.pk_bit, (u32)L.bit_loc.size(), b->dt.pk_u64,
+                                                     (u32)L.u64_loc.size(), b->dt.pk_full, (u32)L.full_loc.size(), dst_d,
+                                                     L.words, first, count, b->pack_flag_d);
+    CU(cudaGetLastError());
+    return CW_OK;
+}
+
+// Packed transfer: entries the lowering proved to be one bit / <= 64 bits cross PCIe as that, the host expands
+// them to the canonical 32-byte rows (zero-extension only - no field arithmetic happens on the CPU).  The batch
+// moves in chunks through two staging buffers: while the worker threads expand chunk k, the pack kernel and the
+// copy of chunk k + 1 run on the GPU / the copy engine.  CW_PACKED_D2H=0 forces the dense copy.
 static int get_witness_packed(cw_batch *b, uint64_t *out, bool *done) {
     const Tape &t = b->c->tape;
+    const PackLayout &L = b->c->pack_layout();
     *done = false;
-    const size_t n0 = t.pk_bit_wire.size(), n1 = t.pk_u64_wire.size(), n2 = t.pk_full_wire.size();
-    const size_t bit_words = (n0 + 31) / 32;
-    size_t words = bit_words + 2 * n1 + 8 * n2;
-    words = (words + 3) & ~(size_t)3;
-    if (b->bt_log2 != 0 || env_int("CW_PACKED_D2H", 1) == 0 || words * 4 * 2 > (size_t)t.n_witness * 32) return CW_OK;
-    const size_t bytes = words * 4 * b->batch;
-    if (!b->packed_d) {
-        CU(cudaMalloc((void **)&b->packed_d, bytes));
-        CU(cudaMallocHost((void **)&b->packed_h, bytes));
-        CU(cudaMalloc((void **)&b->pack_flag_d, 4));
-    }
+    if (env_int("CW_PACKED_D2H", 1) == 0 || L.words * 4 * 2 > (size_t)t.n_witness * 32) return CW_OK;
+    int rc = ensure_pack_buffers(b, L);
+    if (rc) return rc;
     CU(cudaMemsetAsync(b->pack_flag_d, 0, 4, b->stream));
-    dim3 grid((u32)std::min<size_t>((bit_words + n1 + n2 + 255) / 256, 148 * 4), std::min<u32>(b->batch, 65535u));
-    if (grid.x == 0) grid.x = 1;
-    witness_pack_kernel<<<grid, 256, 0, b->stream>>>(b->slots, t.n_slots, b->dt.pk_bit, (u32)n0, b->dt.pk_u64, (u32)n1,
-                                                     b->dt.pk_full, (u32)n2, b->packed_d, words, b->batch, b->pack_flag_d);
-    CU(cudaGetLastError());
+    const size_t W = t.n_witness, cap = b->packed_cap;
+    const size_t n_chunks = (b->batch + cap - 1) / cap;
+    Pool &pool = Pool::get();
+    auto expand_chunk = [&](size_t k) {
+        const size_t first = k * cap, cnt = std::min(cap, b->batch - first);
+        const uint32_t *src = b->packed_h[k & 1];
+        pool.parallel_for(cnt, [&](size_t i) { expand_record(L, src + i * L.words, out + (first + i) * W * 4); });
+    };
+    for (size_t k = 0; k < n_chunks; ++k) {
+        const size_t first = k * cap, cnt = std::min(cap, b->batch - first);
+        // staging buffer k & 1 was consumed by the expansion of chunk k - 2, which finished before chunk k - 1 was waited for
+        if ((rc = pack_rows(b, L, (u32)first, (u32)cnt, b->packed_d[k & 1]))) return rc;
+        CU(cudaMemcpyAsync(b->packed_h[k & 1], b->packed_d[k & 1], cnt * L.words * 4, cudaMemcpyDeviceToHost, b->stream));
+        CU(cudaEventRecord(b->pack_ev[k & 1], b->stream));
+        if (k > 0) {
+            CU(cudaEventSynchronize(b->pack_ev[(k - 1) & 1]));
+            expand_chunk(k - 1);
+        }
+    }
     int flag = 0;
-    CU(cudaMemcpyAsync(b->packed_h, b->packed_d, bytes, cudaMemcpyDeviceToHost, b->stream));
     CU(cudaMemcpyAsync(&flag, b->pack_flag_d, 4, cudaMemcpyDeviceToHost, b->stream));
     CU(cudaStreamSynchronize(b->stream));
-    if (flag) return CW_OK;  // a value exceeded its static class (never expected): caller does the plain copy
-    b->last_d2h_bytes = bytes;
-    // host-side expansion: one sequential pass per instance over the witness entries, each 32-byte row
-    // written exactly once with streaming stores (the three packed streams are in witness order).  The pass
-    // is bound by host memory write bandwidth; measured on the B200 host: 8 threads 3.4 k witnesses/s,
-    // 16 threads 3.2 k, 32 threads 2.6 k (37.9 MB rows), against 1.27 k for the plain PCIe copy.
-    const uint8_t *cls = t.wit_class.data();
-    const size_t W = t.n_witness;
-    unsigned nt = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)env_int("CW_UNPACK_THREADS", 8)));
-    nt = std::min<unsigned>(nt, b->batch);
-    const bool aligned = (((uintptr_t)out) & 15u) == 0;
-    std::vector<std::thread> th;
-    for (unsigned tid = 0; tid < nt; ++tid)
-        th.emplace_back([=]() {
-            for (uint32_t inst = tid; inst < b->batch; inst += nt) {
-                const uint32_t *p = b->packed_h + (size_t)inst * words;
-                const uint32_t *pu = p + bit_words, *pf = pu + 2 * n1;
-                uint64_t *row = out + (size_t)inst * W * 4;
-                size_t bi = 0, ui = 0, fi = 0;
-                const __m128i zero = _mm_setzero_si128();
-                for (size_t i = 0; i < W; ++i) {
-                    __m128i lo, hi = zero;
-                    const uint8_t cl = cls[i];
-                    if (cl == 0) {
-                        lo = _mm_cvtsi64_si128((long long)((p[bi >> 5] >> (bi & 31)) & 1u));
-                        ++bi;
-                    } else if (cl == 1) {
-                        lo = _mm_cvtsi64_si128((long long)((uint64_t)pu[2 * ui] | ((uint64_t)pu[2 * ui + 1] << 32)));
-                        ++ui;
-                    } else {
-                        lo = _mm_loadu_si128((const __m128i *)(pf + 8 * fi));
-                        hi = _mm_loadu_si128((const __m128i *)(pf + 8 * fi + 4));
-                        ++fi;
-                    }
-                    if (aligned) {
-                        _mm_stream_si128((__m128i *)(row + 4 * i), lo);
-                        _mm_stream_si128((__m128i *)(row + 4 * i + 2), hi);
-                    } else {
-                        _mm_storeu_si128((__m128i *)(row + 4 * i), lo);
-                        _mm_storeu_si128((__m128i *)(row + 4 * i + 2), hi);
-                    }
-                }
-            }
-            _mm_sfence();
-        });
-    for (auto &x : th) x.join();
+    if (flag) return CW_OK;  // a value exceeded its static class (never expected): the caller does the dense copy
+    expand_chunk(n_chunks - 1);
+    b->last_d2h_bytes = (uint64_t)b->batch * L.words * 4;
     *done = true;
     return CW_OK;
 }
 
-int cw_batch_get_witness(cw_batch *b, uint64_t *out) {
-    if (!b || !out) return fail(CW_EINVAL, "null argument");
-    if (!b->ran) return fail(CW_ESTATE, "batch has not been run");
+static int get_witness_impl(cw_batch *b, uint64_t *out) {
     const Tape &t = b->c->tape;
     CU(cudaSetDevice(b->device));
     bool done = false;
@@ -659,25 +929,87 @@ int cw_batch_get_witness(cw_batch *b, uint64_t *out) {
     if (rc) return rc;
     if (done) return CW_OK;
     b->last_d2h_bytes = (uint64_t)b->batch * t.n_witness * 32;
-    if (b->bt_log2 == 0) {  // rows are read in place: pitched device-to-host copy
+    if (b->identity_layout()) {  // rows are read in place: pitched device-to-host copy
         CU(cudaMemcpy2DAsync(out, (size_t)t.n_witness * 32, b->slots, (size_t)t.n_slots * 32, (size_t)t.n_witness * 32,
                              b->batch, cudaMemcpyDeviceToHost, b->stream));
-    } else {
-        rc = compact_witness(b);
-        if (rc) return rc;
-        CU(cudaMemcpyAsync(out, b->witness_d, (size_t)b->batch * t.n_witness * 32, cudaMemcpyDeviceToHost, b->stream));
+        CU(cudaStreamSynchronize(b->stream));
+        return CW_OK;
     }
-    CU(cudaStreamSynchronize(b->stream));
+    // dense rows, a bounded number of instances at a time
+    const size_t row = (size_t)t.n_witness * 32;
+    if (!b->dense_chunk_d) {
+        size_t n = std::max<size_t>(1, std::min<size_t>(b->batch, ((size_t)512 << 20) / row));
+        CU(cudaMalloc((void **)&b->dense_chunk_d, n * row));
+        b->dense_chunk_cap = n;
+    }
+    for (size_t first = 0; first < b->batch; first += b->dense_chunk_cap) {
+        const size_t cnt = std::min(b->dense_chunk_cap, b->batch - first);
+        if ((rc = expand_rows(b, (u32)first, (u32)cnt, b->dense_chunk_d))) return rc;
+        CU(cudaMemcpyAsync((uint8_t *)out + first * row, b->dense_chunk_d, cnt * row, cudaMemcpyDeviceToHost, b->stream));
+        CU(cudaStreamSynchronize(b->stream));
+    }
+    return CW_OK;
+}
+
+int cw_batch_get_witness(cw_batch *b, uint64_t *out) {
+    if (!b || !out) return fail(CW_EINVAL, "null argument");
+    if (!b->ran) return fail(CW_ESTATE, "batch has not been run");
+    if (b->async_active) return fail(CW_ESTATE, "a witness transfer of this batch is in flight (cw_batch_get_witness_wait)");
+    return get_witness_impl(b, out);
+}
+
+// The same transfer on a helper thread: the caller may run OTHER batches (their own streams) meanwhile, so that the
+// tape of batch k + 1 executes while the witnesses of batch k are packed, copied and expanded.
+int cw_batch_get_witness_async(cw_batch *b, uint64_t *out) {
+    if (!b || !out) return fail(CW_EINVAL, "null argument");
+    if (!b->ran) return fail(CW_ESTATE, "batch has not been run");
+    if (b->async_active) return fail(CW_ESTATE, "a witness transfer of this batch is already in flight");
+    join_async(b);
+    b->async_active = true;
+    b->async_th = std::thread([b, out] {
+        b->async_rc = get_witness_impl(b, out);
+        b->async_err = g_err;  // (thread-local message of the helper thread)
+    });
+    return CW_OK;
+}
+
+int cw_batch_get_witness_wait(cw_batch *b) {
+    if (!b) return fail(CW_EINVAL, "null argument");
+    if (!b->async_active) return CW_OK;
+    join_async(b);
+    if (b->async_rc) return fail(b->async_rc, b->async_err);
     return CW_OK;
 }
 
 uint64_t cw_batch_last_d2h_bytes(const cw_batch *b) { return b ? b->last_d2h_bytes : 0; }
 
+// The packed records themselves, for consumers that do not need 32-byte rows (layout: cw_circuit_pack_info)
+int cw_batch_get_witness_packed(cw_batch *b, uint32_t *out_words) {
+    if (!b || !out_words) return fail(CW_EINVAL, "null argument");
+    if (!b->ran) return fail(CW_ESTATE, "batch has not been run");
+    if (b->async_active) return fail(CW_ESTATE, "a witness transfer of this batch is in flight (cw_batch_get_witness_wait)");
+    CU(cudaSetDevice(b->device));
+    const PackLayout &L = b->c->pack_layout();
+    int rc = ensure_pack_buffers(b, L);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(b->pack_flag_d, 0, 4, b->stream));
+    for (size_t first = 0; first < b->batch; first += b->packed_cap) {
+        const size_t cnt = std::min(b->packed_cap, b->batch - first);
+        if ((rc = pack_rows(b, L, (u32)first, (u32)cnt, b->packed_d[0]))) return rc;
+        CU(cudaMemcpyAsync(out_words + first * L.words, b->packed_d[0], cnt * L.words * 4, cudaMemcpyDeviceToHost, b->stream));
+        CU(cudaStreamSynchronize(b->stream));
+    }
+    int flag = 0;
+    CU(cudaMemcpy(&flag, b->pack_flag_d, 4, cudaMemcpyDeviceToHost));
+    if (flag) return fail(CW_ESTATE, "a witness value exceeds the width the lowering proved for it");
+    return CW_OK;
+}
+
 int cw_batch_witness_device(cw_batch *b, const uint64_t **dptr) {
     if (!b || !dptr) return fail(CW_EINVAL, "null argument");
     if (!b->ran) return fail(CW_ESTATE, "batch has not been run");
     CU(cudaSetDevice(b->device));
-    int rc = compact_witness(b);
+    int rc = dense_witness(b);
     if (rc) return rc;
     *dptr = (const uint64_t *)b->witness_d;
     return CW_OK;
@@ -686,7 +1018,7 @@ int cw_batch_witness_device(cw_batch *b, const uint64_t **dptr) {
 int cw_batch_witness_strided(cw_batch *b, const uint64_t **dptr, uint64_t *stride_elems) {
     if (!b || !dptr || !stride_elems) return fail(CW_EINVAL, "null argument");
     if (!b->ran) return fail(CW_ESTATE, "batch has not been run");
-    if (b->bt_log2 == 0) {
+    if (b->identity_layout()) {
         *dptr = (const uint64_t *)b->slots;
         *stride_elems = b->c->tape.n_slots;
         return CW_OK;
@@ -703,7 +1035,7 @@ int cw_batch_last_ms(cw_batch *b, float *exec_ms, float *gather_ms) {
     CU(cudaSetDevice(b->device));
     CU(cudaEventSynchronize(b->ev[2]));
     if (exec_ms) CU(cudaEventElapsedTime(exec_ms, b->ev[0], b->ev[1]));
-    if (gather_ms) *gather_ms = 0.f;  // no gather pass: witness rows are written in place by the tape
+    if (gather_ms) *gather_ms = 0.f;  // no gather pass: witness entries are written in place by the tape
     return CW_OK;
 }
 
@@ -717,15 +1049,16 @@ int cw_batch_wtns_bytes(cw_batch *b, uint32_t inst, uint8_t *out, size_t cap, si
     if (cap < need) return fail(CW_EINVAL, "buffer too small");
     CU(cudaSetDevice(b->device));
     std::vector<uint64_t> w((size_t)t.n_witness * 4);
-    const uint4 *row;
-    if (b->bt_log2 == 0) row = b->slots + (size_t)inst * t.n_slots * 2;
-    else {
-        int rc = compact_witness(b);
-        if (rc) return rc;
-        row = b->witness_d + (size_t)inst * t.n_witness * 2;
+    uint4 *row = nullptr;
+    CU(cudaMalloc((void **)&row, (size_t)t.n_witness * 32));
+    int rc = expand_rows(b, inst, 1, row);
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(w.data(), row, (size_t)t.n_witness * 32, cudaMemcpyDeviceToHost, b->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+        if (e != cudaSuccess) rc = fail(CW_ECUDA, cudaGetErrorString(e));
     }
-    CU(cudaMemcpyAsync(w.data(), row, (size_t)t.n_witness * 32, cudaMemcpyDeviceToHost, b->stream));
-    CU(cudaStreamSynchronize(b->stream));
+    cudaFree(row);
+    if (rc) return rc;
     std::vector<uint8_t> bytes = wtns_bytes(t.F, w.data(), t.n_witness);
     memcpy(out, bytes.data(), need);
     return CW_OK;
@@ -742,6 +1075,25 @@ int cw_batch_write_wtns(cw_batch *b, uint32_t inst, const char *path) {
     size_t wr = fwrite(buf.data(), 1, need, f);
     fclose(f);
     return wr == need ? CW_OK : fail(CW_EIO, "short write");
+}
+
+// packed-record layout of the circuit: per witness entry (class << 30) | index - class 0: bit `index` of the plane
+// section, 1: bit `index` of the extra-bit section, 2: u64 entry `index`, 3: full entry `index`; sections follow each
+// other in that order; info = {words per instance, plane words, extra-bit words, u64 entries, full entries}
+int cw_circuit_pack_info(const cw_circuit *c, uint64_t info[5], uint32_t *entry) {
+    if (!c) return fail(CW_EINVAL, "null argument");
+    const PackLayout &L = c->pack_layout();
+    if (info) {
+        info[0] = L.words;
+        info[1] = L.n_plane_words;
+        info[2] = L.n_bit_words;
+        info[3] = L.u64_loc.size();
+        info[4] = L.full_loc.size();
+    }
+    if (entry)
+        for (const PackSeg &sg : L.segs)
+            for (uint32_t j = 0; j < sg.count; ++j) entry[sg.start + j] = (sg.kind << 30) | (sg.src + j);
+    return CW_OK;
 }
 
 // ---- R1CS -------------------------------------------------------------------------------------
@@ -789,16 +1141,221 @@ int cw_r1cs_info(const cw_r1cs *r, uint64_t *n_wires, uint64_t *n_constraints, u
 }
 void cw_r1cs_destroy(cw_r1cs *r) {
     if (!r) return;
+    if (r->eval_twin) cw_r1cs_destroy(r->eval_twin);
     for (auto &kv : r->dev) {
-        cudaSetDevice(kv.first);
+        cudaSetDevice(kv.first.device);
         cudaFree(kv.second.row_ptr);
         cudaFree(kv.second.terms);
         cudaFree(kv.second.dictM);
         cudaFree(kv.second.perm);
-        cudaFree(kv.second.bool_wire);
+        cudaFree(kv.second.bool_loc);
         cudaFree(kv.second.bool_row);
     }
     delete r;
+}
+
+// Compile the CSR for one value layout: wire ids become locations (slot / plane bit; identity for dense witness
+// rows), runs of plane bits with consecutive power-of-two coefficients become one term, boolean rows are absorbed
+// or dropped where the storage makes them tautologies, rows are sorted by structure.
+static int compile_r1cs(cw_r1cs *r, int device, const cw_circuit *layout, DevR1cs &d) {
+    const R1csData &R = r->data;
+    const Tape *T = layout ? &layout->tape : nullptr;
+    if (T && T->n_witness != R.n_wires) return fail(CW_EINVAL, "the R1CS and the batch's circuit have different numbers of wires");
+    auto loc_of = [&](u32 wire) -> u32 { return T ? T->witness_slot[wire] : wire; };
+    int rc;
+    std::vector<U256> dm(R.dict.size());
+    std::vector<unsigned short> kind(R.dict.size());
+    auto pow2_exp = [](const U256 &v) -> int {  // k if v == 2^k, else -1
+        int k = -1;
+        for (int i = 0; i < 256; ++i)
+            if ((v.v[i >> 6] >> (i & 63)) & 1) {
+                if (k >= 0) return -1;
+                k = i;
+            }
+        return k;
+    };
+    for (size_t i = 0; i < R.dict.size(); ++i) {
+        dm[i] = r->F.to_mont(R.dict[i]);
+        U256 negv;
+        u256_sub(negv, r->F.q, R.dict[i]);
+        int kp = pow2_exp(R.dict[i]), kn = R.dict[i].is_zero() ? -1 : pow2_exp(negv);
+        if (kp == 0) kind[i] = 1;
+        else if (kn == 0) kind[i] = 2;
+        else if (kp > 0 && kp < 250) kind[i] = (unsigned short)(3 | (kp << 8));
+        else if (kn > 0 && kn < 250) kind[i] = (unsigned short)(4 | (kn << 8));
+        else kind[i] = 0;
+    }
+    const size_t m = R.n_constraints;
+    // boolean rows  x * (x - 1) = 0  (A = {x:1}, B = {x:1, one:-1}, C = {} or A/B swapped): they only need
+    // `w[x] in {0,1}`.  A wire stored as one bit of the bit plane satisfies it by construction (the row is dropped);
+    // otherwise the check rides on a term of a general row that reads the wire anyway, or goes to r1cs_bool_kernel.
+    std::vector<u32> general, bool_wire, bool_row;
+    auto is_unit = [&](uint64_t k, int want) { return (kind[R.coef[k]] & 0xFF) == want && (kind[R.coef[k]] >> 8) == 0; };
+    for (size_t row = 0; row < m; ++row) {
+        uint64_t p0 = R.row_ptr[3 * row], p1 = R.row_ptr[3 * row + 1], p2 = R.row_ptr[3 * row + 2], p3 = R.row_ptr[3 * row + 3];
+        bool is_bool = false;
+        u32 wire = 0;
+        if (p3 == p2 && (p1 - p0) + (p2 - p1) == 3) {
+            uint64_t s0 = (p1 - p0 == 1) ? p0 : p1, l0 = (p1 - p0 == 1) ? p1 : p0;  // single-term block / two-term block
+            // two-term block is sorted by wire: {one: -1, x: +1}
+            if (is_unit(s0, 1) && R.col[s0] != 0 && R.col[l0] == 0 && is_unit(l0, 2) && R.col[l0 + 1] == R.col[s0] && is_unit(l0 + 1, 1)) {
+                is_bool = true;
+                wire = R.col[s0];
+            }
+        }
+        if (is_bool && !r->no_bool_rows) {
+            if (loc_of(wire) & OPERAND_BIT) continue;  // a stored bit is 0 or 1
+            bool_wire.push_back(wire);
+            bool_row.push_back((u32)row);
+        } else general.push_back((u32)row);
+    }
+    // compiled terms of the general rows
+    std::vector<unsigned long long> row_ptr(3 * m + 1, 0);
+    std::vector<uint4> terms;
+    terms.reserve(R.col.size());
+    std::vector<uint64_t> sig(m, 0);
+    std::vector<u32> wire2bool(R.n_wires, 0xFFFFFFFFu);
+    for (size_t i = 0; i < bool_wire.size(); ++i)
+        if (wire2bool[bool_wire[i]] == 0xFFFFFFFFu) wire2bool[bool_wire[i]] = (u32)i;
+    std::vector<uint8_t> absorbed(bool_wire.size(), 0);
+    const uint32_t qbits = r->F.qbits;
+    uint64_t terms_general = 0;
+    {
+        size_t gi = 0;
+        for (size_t row = 0; row < m; ++row) {
+            const bool is_general = gi < general.size() && general[gi] == row;
+            if (is_general) ++gi;
+            uint64_t h = 1469598103934665603ull, cnt[3] = {0, 0, 0};
+            for (int blk = 0; blk < 3; ++blk) {
+                row_ptr[3 * row + blk] = terms.size();
+                if (!is_general) continue;
+                uint64_t k = R.row_ptr[3 * row + blk];
+                const uint64_t e = R.row_ptr[3 * row + blk + 1];
+                while (k < e) {
+                    const u32 loc = loc_of(R.col[k]);
+                    const unsigned short kd = kind[R.coef[k]];
+                    const int kk = kd & 0xFF;
+                    // a run: plane bits at consecutive positions of one word, coefficients +-2^(s), +-2^(s+1), ...
+                    if ((loc & OPERAND_BIT) && kk >= 1 && kk <= 4) {
+                        const bool negc = kk == 2 || kk == 4;
+                        const u32 s0 = kk <= 2 ? 0u : (u32)(kd >> 8), pos0 = loc & OPERAND_BITPOS_MASK;
+                        uint64_t j = k + 1;
+                        while (j < e) {
+                            const u32 lj = loc_of(R.col[j]);
+                            const unsigned short kj = kind[R.coef[j]];
+                            const int kkj = kj & 0xFF;
+                            if (!(lj & OPERAND_BIT) || kkj < 1 || kkj > 4 || (kkj == 2 || kkj == 4) != negc) break;
+                            const u32 sj = kkj <= 2 ? 0u : (u32)(kj >> 8), pj = lj & OPERAND_BITPOS_MASK;
+                            if (pj != pos0 + (u32)(j - k) || (pj >> 5) != (pos0 >> 5) || sj != s0 + (u32)(j - k)) break;
+                            ++j;
+                        }
+                        const u32 n = (u32)(j - k);
+                        if (s0 + n < qbits && s0 < 256) {  // the run's value is below 2^(s0 + n) <= 2^(qbits-1) < q
+                            terms.push_back(make_uint4(pos0 >> 5, 0u,
+                                                       (negc ? 6u : 5u) | (s0 << 8) | ((pos0 & 31u) << 16) | ((n - 1u) << 21),
+                                                       0xFFFFFFFFu));
+                            h = (h ^ (negc ? 6u : 5u)) * 1099511628211ull;
+                            ++cnt[blk];
+                            k = j;
+                            continue;
+                        }
+                    }
+                    u32 brow = 0xFFFFFFFFu;
+                    const u32 bi = wire2bool[R.col[k]];
+                    if (bi != 0xFFFFFFFFu && !absorbed[bi]) {
+                        absorbed[bi] = 1;
+                        brow = bool_row[bi];
+                    }
+                    terms.push_back(make_uint4(loc, R.coef[k], kd, brow));
+                    h = (h ^ (u32)kk) * 1099511628211ull;
+                    ++cnt[blk];
+                    ++k;
+                }
+            }
+            if (is_general) {
+                const uint64_t total = std::min<uint64_t>(cnt[0] + cnt[1] + cnt[2], 0xFFFF);
+                terms_general += cnt[0] + cnt[1] + cnt[2];
+                sig[row] = (total << 48) | ((std::min<uint64_t>(cnt[0], 255)) << 40) | ((std::min<uint64_t>(cnt[1], 255)) << 32) | (h & 0xFFFFFFFFull);
+            }
+        }
+        row_ptr[3 * m] = terms.size();
+    }
+    // rows sorted by structure so that neighbouring work items have equal length and branch alike
+    std::stable_sort(general.begin(), general.end(), [&](u32 x, u32 y) { return sig[x] > sig[y]; });
+    {
+        size_t o = 0;
+        for (size_t i = 0; i < bool_wire.size(); ++i)
+            if (!absorbed[i]) { bool_wire[o] = loc_of(bool_wire[i]); bool_row[o] = bool_row[i]; ++o; }
+        bool_wire.resize(o);
+        bool_row.resize(o);
+    }
+    d.n_general = (u32)general.size();
+    d.n_bool = (u32)bool_wire.size();
+    d.n_terms = terms.size();
+    d.mean_row_terms = general.empty() ? 0 : (u32)(terms_general / general.size());
+    if ((rc = upload(&d.terms, terms.data(), terms.size() * sizeof(uint4)))) return rc;
+    if ((rc = upload(&d.bool_loc, bool_wire.data(), bool_wire.size() * 4))) return rc;
+    if ((rc = upload(&d.bool_row, bool_row.data(), bool_row.size() * 4))) return rc;
+    if ((rc = upload(&d.row_ptr, row_ptr.data(), row_ptr.size() * 8))) return rc;
+    if ((rc = upload(&d.dictM, dm.data(), dm.size() * 32))) return rc;
+    if ((rc = upload(&d.perm, general.data(), general.size() * 4))) return rc;
+    (void)device;
+    return CW_OK;
+}
+
+static int get_dev_r1cs(cw_r1cs *r, int device, const cw_circuit *layout, DevR1cs &d) {
+    std::lock_guard<std::mutex> lk(r->mu);
+    R1csKey key{device, layout};
+    auto it = r->dev.find(key);
+    if (it != r->dev.end()) {
+        d = it->second;
+        return CW_OK;
+    }
+    int rc = compile_r1cs(r, device, layout, d);
+    if (rc) return rc;
+    r->dev[key] = d;
+    return CW_OK;
+}
+
+struct R1csOut {
+    uint4 *a = nullptr, *b = nullptr, *c = nullptr;
+};
+
+// launches on `stream`; fb_d[batch] must hold ~0 on entry
+static int launch_r1cs(cw_r1cs *r, const DevR1cs &d, const StoreDev &S, cudaStream_t stream, unsigned long long *fb_d,
+                       const R1csOut *eval) {
+    const R1csData &R = r->data;
+    R1csDev rd;
+    rd.row_ptr = d.row_ptr;
+    rd.terms = d.terms;
+    rd.dictM = d.dictM;
+    rd.perm = d.perm;
+    rd.n_rows = d.n_general;
+    const u32 n_tiles = (S.batch + (1u << S.bt_log2) - 1) >> S.bt_log2;
+    if (d.n_general) {
+        const uint64_t items = (uint64_t)d.n_general << S.bt_log2;
+        dim3 grid((u32)std::max<uint64_t>(1, std::min<uint64_t>((items + 255) / 256, 148 * 8)), std::min<u32>(n_tiles, 65535u));
+        // long rows: many resident warps (48 registers); short rows: the unspilled build
+        const bool lean = env_int("CW_R1CS_LEAN", d.mean_row_terms >= 12 ? 1 : 0) != 0;
+        EvalOut eo;
+        if (eval) { eo.a = eval->a; eo.b = eval->b; eo.c = eval->c; eo.m = R.n_constraints; }
+#define CW_LAUNCH_R1CS(PR)                                                                              \
+    do {                                                                                                \
+        if (eval) r1cs_check_kernel<PR, 3, true><<<grid, 256, 0, stream>>>(rd, S, fb_d, eo);             \
+        else if (lean) r1cs_check_kernel<PR, 5, false><<<grid, 256, 0, stream>>>(rd, S, fb_d, eo);       \
+        else r1cs_check_kernel<PR, 3, false><<<grid, 256, 0, stream>>>(rd, S, fb_d, eo);                 \
+    } while (0)
+        if (R.prime_id == 0) CW_LAUNCH_R1CS(0);
+        else CW_LAUNCH_R1CS(1);
+#undef CW_LAUNCH_R1CS
+    }
+    if (d.n_bool && !eval) {
+        const uint64_t items = (uint64_t)d.n_bool << S.bt_log2;
+        dim3 bgrid((u32)std::max<uint64_t>(1, std::min<uint64_t>((items + 255) / 256, 148 * 8)), std::min<u32>(n_tiles, 65535u));
+        r1cs_bool_kernel<<<bgrid, 256, 0, stream>>>(d.bool_loc, d.bool_row, d.n_bool, S, fb_d);
+    }
+    CU(cudaGetLastError());
+    return CW_OK;
 }
 
 int cw_r1cs_check(cw_r1cs *r, const uint64_t *witness, int is_device_ptr, uint32_t batch, int device,
@@ -807,119 +1364,17 @@ int cw_r1cs_check(cw_r1cs *r, const uint64_t *witness, int is_device_ptr, uint32
     return cw_r1cs_check_strided(r, witness, r->data.n_wires, is_device_ptr, batch, device, first_bad, kernel_ms);
 }
 
+// dense witness rows handed in by the caller (host or device memory)
 int cw_r1cs_check_strided(cw_r1cs *r, const uint64_t *witness, uint64_t stride_elems, int is_device_ptr, uint32_t batch,
                           int device, int64_t *first_bad, float *kernel_ms) {
-    if (!r || !witness || !first_bad || batch == 0 || stride_elems < r->data.n_wires) return fail(CW_EINVAL, "bad argument");
+    if (!r || !witness || !first_bad || batch == 0 || stride_elems < r->data.n_wires || stride_elems >> 32)
+        return fail(CW_EINVAL, "bad argument");
     if (is_device_ptr && ((uintptr_t)witness & 31u))
         return fail(CW_EINVAL, "device witness pointer must be 32-byte aligned (elements are read with 256-bit loads)");
     int rc = ensure_device(device);
     if (rc) return rc;
     DevR1cs d;
-    {
-        std::lock_guard<std::mutex> lk(r->mu);
-        auto it = r->dev.find(device);
-        if (it == r->dev.end()) {
-            const R1csData &R = r->data;
-            std::vector<U256> dm(R.dict.size());
-            std::vector<unsigned short> kind(R.dict.size());
-            auto pow2_exp = [](const U256 &v) -> int {  // k if v == 2^k, else -1
-                int k = -1;
-                for (int i = 0; i < 256; ++i)
-                    if ((v.v[i >> 6] >> (i & 63)) & 1) {
-                        if (k >= 0) return -1;
-                        k = i;
-                    }
-                return k;
-            };
-            for (size_t i = 0; i < R.dict.size(); ++i) {
-                dm[i] = r->F.to_mont(R.dict[i]);
-                U256 negv;
-                u256_sub(negv, r->F.q, R.dict[i]);
-                int kp = pow2_exp(R.dict[i]), kn = R.dict[i].is_zero() ? -1 : pow2_exp(negv);
-                if (kp == 0) kind[i] = 1;
-                else if (kn == 0) kind[i] = 2;
-                else if (kp > 0 && kp < 250) kind[i] = (unsigned short)(3 | (kp << 8));
-                else if (kn > 0 && kn < 250) kind[i] = (unsigned short)(4 | (kn << 8));
-                else kind[i] = 0;
-            }
-            // rows sorted by structure so that the rows of a warp have equal length and branch alike
-            size_t m = R.n_constraints;
-            std::vector<uint64_t> sig(m);
-            for (size_t row = 0; row < m; ++row) {
-                uint64_t na = R.row_ptr[3 * row + 1] - R.row_ptr[3 * row], nb = R.row_ptr[3 * row + 2] - R.row_ptr[3 * row + 1],
-                         nc = R.row_ptr[3 * row + 3] - R.row_ptr[3 * row + 2];
-                uint64_t h = 1469598103934665603ull;
-                for (uint64_t k = R.row_ptr[3 * row]; k < R.row_ptr[3 * row + 3]; ++k) h = (h ^ (kind[R.coef[k]] & 0xFF)) * 1099511628211ull;
-                uint64_t total = std::min<uint64_t>(na + nb + nc, 0xFFFF);
-                sig[row] = (total << 48) | ((std::min<uint64_t>(na, 255)) << 40) | ((std::min<uint64_t>(nb, 255)) << 32) | (h & 0xFFFFFFFFull);
-            }
-            // boolean rows  x * (x - 1) = 0  (A = {x:1}, B = {x:1, one:-1}, C = {} or A/B swapped) are the bulk
-            // of circom circuits (every Num2Bits / range-check bit): they only need `w[x] in {0,1}` and
-            // get their own memory-bound kernel; the remaining rows go through the general kernel.
-            std::vector<u32> perm, bool_wire, bool_row;
-            auto is_unit = [&](uint64_t k, int want) { return (kind[R.coef[k]] & 0xFF) == want && (kind[R.coef[k]] >> 8) == 0; };
-            for (size_t row = 0; row < m; ++row) {
-                uint64_t p0 = R.row_ptr[3 * row], p1 = R.row_ptr[3 * row + 1], p2 = R.row_ptr[3 * row + 2], p3 = R.row_ptr[3 * row + 3];
-                bool is_bool = false;
-                u32 wire = 0;
-                if (p3 == p2 && (p1 - p0) + (p2 - p1) == 3) {
-                    uint64_t s0 = (p1 - p0 == 1) ? p0 : p1, l0 = (p1 - p0 == 1) ? p1 : p0;  // single-term block / two-term block
-                    // two-term block is sorted by wire: {one: -1, x: +1}
-                    if (is_unit(s0, 1) && R.col[s0] != 0 && R.col[l0] == 0 && is_unit(l0, 2) && R.col[l0 + 1] == R.col[s0] && is_unit(l0 + 1, 1)) {
-                        is_bool = true;
-                        wire = R.col[s0];
-                    }
-                }
-                if (is_bool) { bool_wire.push_back(wire); bool_row.push_back((u32)row); }
-                else perm.push_back((u32)row);
-            }
-            std::stable_sort(perm.begin(), perm.end(), [&](u32 x, u32 y) { return sig[x] > sig[y]; });
-            // a boolean row whose wire is a term of a general row (the bit of a decomposition inside its
-            // recomposition sum) is checked by that term's thread while the value is in registers: the witness
-            // is then read once instead of twice
-            std::vector<u32> term_bool(R.col.size(), 0xFFFFFFFFu);
-            {
-                std::vector<u32> wire2bool(R.n_wires, 0xFFFFFFFFu);
-                for (size_t i = 0; i < bool_wire.size(); ++i)
-                    if (wire2bool[bool_wire[i]] == 0xFFFFFFFFu) wire2bool[bool_wire[i]] = (u32)i;
-                std::vector<uint8_t> absorbed(bool_wire.size(), 0);
-                for (u32 row : perm)
-                    for (uint64_t k = R.row_ptr[3 * (size_t)row]; k < R.row_ptr[3 * (size_t)row + 3]; ++k) {
-                        u32 bi = wire2bool[R.col[k]];
-                        if (bi != 0xFFFFFFFFu && !absorbed[bi]) {
-                            absorbed[bi] = 1;
-                            term_bool[k] = bool_row[bi];
-                        }
-                    }
-                size_t o = 0;
-                for (size_t i = 0; i < bool_wire.size(); ++i)
-                    if (!absorbed[i]) { bool_wire[o] = bool_wire[i]; bool_row[o] = bool_row[i]; ++o; }
-                bool_wire.resize(o);
-                bool_row.resize(o);
-            }
-            {
-                std::vector<uint4> terms(R.col.size());
-                for (size_t k = 0; k < R.col.size(); ++k)
-                    terms[k] = make_uint4(R.col[k], R.coef[k], kind[R.coef[k]], term_bool[k]);
-                if ((rc = upload(&d.terms, terms.data(), terms.size() * sizeof(uint4)))) return rc;
-            }
-            d.n_general = (u32)perm.size();
-            d.n_bool = (u32)bool_wire.size();
-            {
-                uint64_t terms_general = 0;
-                for (u32 row : perm) terms_general += R.row_ptr[3 * (size_t)row + 3] - R.row_ptr[3 * (size_t)row];
-                d.mean_row_terms = perm.empty() ? 0 : (u32)(terms_general / perm.size());
-            }
-            d.n_long = 0;  // perm is sorted by decreasing term count
-            while (d.n_long < d.n_general && (sig[perm[d.n_long]] >> 48) >= R1CS_SPLIT_MIN) ++d.n_long;
-            if ((rc = upload(&d.bool_wire, bool_wire.data(), bool_wire.size() * 4))) return rc;
-            if ((rc = upload(&d.bool_row, bool_row.data(), bool_row.size() * 4))) return rc;
-            if ((rc = upload(&d.row_ptr, R.row_ptr.data(), R.row_ptr.size() * 8))) return rc;
-            if ((rc = upload(&d.dictM, dm.data(), dm.size() * 32))) return rc;
-            if ((rc = upload(&d.perm, perm.data(), perm.size() * 4))) return rc;
-            r->dev[device] = d;
-        } else d = it->second;
-    }
+    if ((rc = get_dev_r1cs(r, device, nullptr, d))) return rc;
     const R1csData &R = r->data;
     const uint4 *w_d = (const uint4 *)witness;
     uint4 *tmp = nullptr;
@@ -933,73 +1388,103 @@ int cw_r1cs_check_strided(cw_r1cs *r, const uint64_t *witness, uint64_t stride_e
     unsigned long long *fb_d = nullptr;
     CU(cudaMalloc((void **)&fb_d, (size_t)batch * 8));
     CU(cudaMemset(fb_d, 0xFF, (size_t)batch * 8));
-    R1csDev rd;
-    rd.row_ptr = d.row_ptr;
-    rd.terms = d.terms;
-    rd.dictM = d.dictM;
-    rd.perm = d.perm;
-    rd.n_wires = (u32)R.n_wires;
-    rd.w_stride = stride_elems;
-    // general rows: the long ones (perm[0, n_long)) by lane groups, the rest one thread per (row, instance)
-    // (lane groups are opt-in, env CW_R1CS_SPLIT=1: measured 20.7 ms against 18.4 ms for the one-thread-per-row
-    // kernel on the bench circuit, batch 1024 - the butterfly costs more than the coalescing gains)
-    const u32 n_long = env_int("CW_R1CS_SPLIT", 0) ? d.n_long : 0u, n_short = d.n_general - n_long;
-    // instance groups: enough blocks to fill the GPU, as many instances per block as that allows
-    auto plan = [&](u32 rows_per_block, u32 n_rows, u32 *row_blocks) {
-        *row_blocks = (u32)std::min<uint64_t>(((uint64_t)n_rows + rows_per_block - 1) / rows_per_block, 148 * 8);
-        if (*row_blocks == 0) *row_blocks = 1;
-        u32 ipb = 1;
-        while (ipb < 8 && (uint64_t)*row_blocks * ((batch + 2 * ipb - 1) / (2 * ipb)) >= 148ull * 16) ipb *= 2;
-        ipb = (u32)std::max(1, env_int("CW_R1CS_IPB", (int)ipb));
-        while ((batch + ipb - 1) / ipb > 65535u) ipb *= 2;  // grid.y limit: every instance must have a block
-        return ipb;
-    };
+    StoreDev S;
+    S.slots = w_d;
+    S.plane = nullptr;
+    S.n_slots = (u32)stride_elems;
+    S.n_bitwords = 0;
+    S.bt_log2 = 0;
+    S.batch = batch;
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0));
-    if (n_long) {
-        u32 row_blocks;
-        rd.inst_per_block = plan(256 / R1CS_SPLIT_G, n_long, &row_blocks);
-        rd.perm = d.perm;
-        rd.n_constraints = n_long;
-        dim3 grid(row_blocks, std::min<u32>((batch + rd.inst_per_block - 1) / rd.inst_per_block, 65535u));
-        if (R.prime_id == 0) r1cs_check_split_kernel<0, R1CS_SPLIT_G><<<grid, 256>>>(rd, w_d, batch, fb_d);
-        else r1cs_check_split_kernel<1, R1CS_SPLIT_G><<<grid, 256>>>(rd, w_d, batch, fb_d);
-    }
-    if (n_short) {
-        u32 row_blocks;
-        rd.inst_per_block = plan(256, n_short, &row_blocks);
-        rd.perm = d.perm + n_long;
-        rd.n_constraints = n_short;  // rows visited through perm
-        dim3 grid(row_blocks, std::min<u32>((batch + rd.inst_per_block - 1) / rd.inst_per_block, 65535u));
-        // long rows: many resident warps (48 registers); short rows: the unspilled build (78 registers)
-        const bool lean = env_int("CW_R1CS_LEAN", d.mean_row_terms >= 12 ? 1 : 0) != 0;
-        if (R.prime_id == 0) {
-            if (lean) r1cs_check_kernel<0, 5><<<grid, 256>>>(rd, w_d, batch, fb_d);
-            else r1cs_check_kernel<0, 3><<<grid, 256>>>(rd, w_d, batch, fb_d);
-        } else {
-            if (lean) r1cs_check_kernel<1, 5><<<grid, 256>>>(rd, w_d, batch, fb_d);
-            else r1cs_check_kernel<1, 3><<<grid, 256>>>(rd, w_d, batch, fb_d);
-        }
-    }
-    if (d.n_bool) {
-        dim3 bgrid((u32)std::min<uint64_t>(((uint64_t)d.n_bool + 255) / 256, 148 * 8), std::min<u32>(batch, 65535u));
-        r1cs_bool_kernel<<<bgrid, 256>>>(d.bool_wire, d.bool_row, d.n_bool, w_d, stride_elems, batch, fb_d);
-    }
+    rc = launch_r1cs(r, d, S, nullptr, fb_d, nullptr);
     CU(cudaEventRecord(e1));
-    CU(cudaGetLastError());
-    std::vector<unsigned long long> fb(batch);
-    CU(cudaMemcpy(fb.data(), fb_d, (size_t)batch * 8, cudaMemcpyDeviceToHost));
-    float ms = 0;
-    CU(cudaEventElapsedTime(&ms, e0, e1));
-    if (kernel_ms) *kernel_ms = ms;
-    for (u32 i = 0; i < batch; ++i) first_bad[i] = fb[i] == ~0ull ? -1 : (int64_t)fb[i];
+    if (!rc) {
+        std::vector<unsigned long long> fb(batch);
+        CU(cudaMemcpy(fb.data(), fb_d, (size_t)batch * 8, cudaMemcpyDeviceToHost));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (kernel_ms) *kernel_ms = ms;
+        for (u32 i = 0; i < batch; ++i) first_bad[i] = fb[i] == ~0ull ? -1 : (int64_t)fb[i];
+    }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(fb_d);
     if (tmp) cudaFree(tmp);
-    return CW_OK;
+    return rc;
+}
+
+// The witnesses of a batch where the tape left them (resident slots + bit plane, any tile layout): no dense rows
+// are materialised, plane bits are read as bits, recomposition sums as words.  Runs on the batch's stream, behind
+// the tape; the per-instance result buffer belongs to the batch (no allocation per call).
+int cw_r1cs_check_batch(cw_r1cs *r, cw_batch *b, int64_t *first_bad, float *kernel_ms) {
+    if (!r || !b || !first_bad) return fail(CW_EINVAL, "null argument");
+    if (!b->ran) return fail(CW_ESTATE, "batch has not been run");
+    if (r->data.prime_id != b->c->tape.F.prime_id) return fail(CW_EINVAL, "the R1CS and the batch use different primes");
+    CU(cudaSetDevice(b->device));
+    DevR1cs d;
+    int rc = get_dev_r1cs(r, b->device, b->c, d);
+    if (rc) return rc;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaMemsetAsync(b->fb_d, 0xFF, (size_t)b->batch * 8, b->stream));
+    CU(cudaEventRecord(e0, b->stream));
+    rc = launch_r1cs(r, d, b->store(), b->stream, b->fb_d, nullptr);
+    CU(cudaEventRecord(e1, b->stream));
+    if (!rc) {
+        std::vector<unsigned long long> fb(b->batch);
+        CU(cudaMemcpyAsync(fb.data(), b->fb_d, (size_t)b->batch * 8, cudaMemcpyDeviceToHost, b->stream));
+        CU(cudaStreamSynchronize(b->stream));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        if (kernel_ms) *kernel_ms = ms;
+        for (u32 i = 0; i < b->batch; ++i) first_bad[i] = fb[i] == ~0ull ? -1 : (int64_t)fb[i];
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+}
+
+// A.w, B.w, C.w of every constraint for instances [first, first + count) of a batch, left in device memory for a
+// prover (the QAP evaluation / rapidsnark-style pipeline that follows witness generation): three arrays
+// [count][n_constraints][4 x u64], canonical.  Rows the check treats specially (boolean rows) are evaluated like
+// all others here.
+int cw_r1cs_eval_batch(cw_r1cs *r, cw_batch *b, uint32_t first, uint32_t count, uint64_t *a_dev, uint64_t *b_dev,
+                       uint64_t *c_dev) {
+    if (!r || !b || !a_dev || !b_dev || !c_dev || (uint64_t)first + count > b->batch || count == 0)
+        return fail(CW_EINVAL, "bad argument");
+    if (((uintptr_t)a_dev | (uintptr_t)b_dev | (uintptr_t)c_dev) & 31u) return fail(CW_EINVAL, "outputs must be 32-byte aligned");
+    if (!b->ran) return fail(CW_ESTATE, "batch has not been run");
+    if (b->bt_log2 != 0) return fail(CW_ESTATE, "cw_r1cs_eval_batch needs a one-instance tile layout (CW_BT_LOG2=0)");
+    CU(cudaSetDevice(b->device));
+    // all rows through the general path: a layout key of its own (no boolean-row special cases)
+    cw_r1cs *all = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(r->mu);
+        if (!r->eval_twin) {
+            r->eval_twin = new cw_r1cs();
+            r->eval_twin->data = r->data;
+            r->eval_twin->F = r->F;
+            r->eval_twin->no_bool_rows = true;
+        }
+        all = r->eval_twin;
+    }
+    DevR1cs d;
+    int rc = get_dev_r1cs(all, b->device, b->c, d);
+    if (rc) return rc;
+    StoreDev S = b->store();
+    S.slots += (size_t)first * S.n_slots * 2;
+    S.plane += (size_t)first * S.n_bitwords;
+    S.batch = count;
+    R1csOut eo;
+    eo.a = (uint4 *)a_dev;
+    eo.b = (uint4 *)b_dev;
+    eo.c = (uint4 *)c_dev;
+    CU(cudaMemsetAsync(b->fb_d, 0xFF, (size_t)b->batch * 8, b->stream));
+    return launch_r1cs(all, d, S, b->stream, b->fb_d, &eo);
 }
 
 // ---- field batch ops ---------------------------------------------------------------------------

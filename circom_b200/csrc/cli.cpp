@@ -188,7 +188,10 @@ int main(int argc, char **argv) {
     try {
         cw_circuit *c = nullptr;
         // CW_O0=1 keeps every signal in the witness (the layout of a reference build with --O0)
-        CK(cw_circuit_load(argv[1], getenv("CW_O0") ? CW_FLAG_O0 : 0, &c));
+        // CW_COMPACT=0: one 32-byte slot per value instead of the compact value store (bit plane + shared temporaries)
+        const char *cenv = getenv("CW_COMPACT");
+        const uint32_t compact = (cenv && cenv[0] == '0') ? 0u : (uint32_t)CW_FLAG_COMPACT;
+        CK(cw_circuit_load(argv[1], (getenv("CW_O0") ? CW_FLAG_O0 : 0) | compact, &c));
         int prime_id = 0;
         CK(cw_circuit_prime(c, &prime_id, nullptr));
         cw::FieldParams F = cw::make_field(prime_id);

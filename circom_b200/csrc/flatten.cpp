@@ -1142,7 +1142,7 @@ struct Lowerer {
         // are renumbered densely, witness entry i is found through witness_slot[i].
         std::vector<uint32_t> newid;
         T.n_bitwords = 0;
-        if ((flags & CW_FLAG_BITPLANE) && T.call_tab.empty()) {
+        if (flags & CW_FLAG_BITPLANE) {
             std::vector<uint32_t> code(next_tmp, NO_SLOT);
             uint32_t n_words = 0;
             const size_t n_ops = T.ops.size() / 4;
@@ -1160,6 +1160,7 @@ struct Lowerer {
             }
             for (uint32_t i = 0; ok && i < M.n_in + 1; ++i)
                 if (code[remap[i]] != NO_SLOT) ok = false;
+            if (next_tmp >= OPERAND_BIT) ok = false;
             if (ok) {
                 newid.resize(next_tmp);
                 uint32_t nw = 0;
@@ -1170,49 +1171,107 @@ struct Lowerer {
                     const uint32_t opc = o[0] & 0xFFu;
                     if (opc == DOP_BITS && (o[3] >> 24)) o[0] = opc | (word++ << 8);        // destination = bit-plane word
                     else if (!is_assert_op(opc)) o[0] = opc | (newid[o[0] >> 8] << 8);
+                    if (opc == 45) continue;  // operand a is the call-table offset; the table is renumbered below
                     for (int k = 1; k <= 3; ++k) {
                         if (k == 3 && c_is_immediate(opc)) break;
                         if (!(o[k] & OPERAND_CONST)) o[k] = newid[o[k]];
                     }
                 }
+                for (size_t i = 0; i < T.call_tab.size();) {  // {function, n_args, operands...}
+                    const uint32_t n = T.call_tab[i + 1];
+                    for (uint32_t k = 0; k < n; ++k)
+                        if (!(T.call_tab[i + 2 + k] & OPERAND_CONST)) T.call_tab[i + 2 + k] = newid[T.call_tab[i + 2 + k]];
+                    i += 2 + n;
+                }
                 T.n_bitwords = n_words;
                 next_tmp = nw;
             }
         }
-        // Shared-memory forwarding.  The interpreter keeps, per instance, a ring of the CW_RING_SIZE most recent
-        // results (index = destination slot % CW_RING_SIZE; temporaries are numbered in tape order, so they walk
-        // the ring sequentially; multi-slot bit runs bypass it).  An operand may be read from the ring iff its
-        // entry still belongs to it when the consumer's level ends - other work items of that level may already
-        // have deposited their results when the consumer reads.  Slots are written once, so "the owner of the
-        // index after all writes of the consumer's level is still this slot" is exactly that condition.
-        {
-            const uint32_t M = CW_RING_SIZE - 1;
-            // Two deposits of ONE level into the same index land in an unknown order: that index is unusable
-            // until a later level writes it again.
-            std::vector<uint32_t> owner(CW_RING_SIZE, NO_SLOT), stamp(CW_RING_SIZE, NO_SLOT);
-            T.n_slot_operands = T.n_ring_operands = 0;
-            for (size_t l = 0; l + 1 < T.level_start.size(); ++l) {
+        // Slot reuse (CW_FLAG_REUSE).  Values that are not witness entries only live from their op to their last
+        // reader; numbering every one of them keeps 386 k dead 32-byte values per instance for the bench circuit
+        // while at most 25 k are live at any level.  Temporaries are therefore allocated like registers: an id is
+        // released when the level of its last reader has completed (the interpreter's barrier) and handed out
+        // again, most recently released first (still in cache).  Witness-resident slots are never reused.
+        const uint32_t n_resident = newid.empty() ? (uint32_t)W : [&]() {
+            uint32_t n = 0;
+            for (uint64_t i = 0; i < W; ++i) n += !(newid[i] & OPERAND_BIT);
+            return n;
+        }();
+        if (flags & CW_FLAG_REUSE) {
+            const size_t n_ops = T.ops.size() / 4;
+            const size_t n_lv = T.level_start.size() - 1;
+            std::vector<uint32_t> last(next_tmp, 0), phys(next_tmp, NO_SLOT);
+            auto is_tmp = [&](uint32_t o) { return !(o & (OPERAND_CONST | OPERAND_BIT)) && o >= n_resident; };
+            for (size_t l = 0; l < n_lv; ++l)
                 for (uint32_t i = T.level_start[l]; i < T.level_start[l + 1]; ++i) {
                     const uint32_t *o = &T.ops[(size_t)i * 4];
                     const uint32_t opc = o[0] & 0xFFu;
-                    if (is_assert_op(opc) || (opc == DOP_BITS && (o[3] >> 24))) continue;
-                    const uint32_t idx = (o[0] >> 8) & M;
-                    owner[idx] = stamp[idx] == (uint32_t)l ? NO_SLOT : o[0] >> 8;
-                    stamp[idx] = (uint32_t)l;
-                }
-                for (uint32_t i = T.level_start[l]; i < T.level_start[l + 1]; ++i) {
-                    uint32_t *o = &T.ops[(size_t)i * 4];
-                    const uint32_t opc = o[0] & 0xFFu;
-                    if (opc == 45) continue;  // call arguments are read through the call table
+                    if (opc == 45) {
+                        const uint32_t n = T.call_tab[o[1] + 1];
+                        for (uint32_t k = 0; k < n; ++k)
+                            if (is_tmp(T.call_tab[o[1] + 2 + k])) last[T.call_tab[o[1] + 2 + k]] = (uint32_t)l;
+                        continue;
+                    }
                     for (int k = 1; k <= 3; ++k) {
                         if (k == 3 && c_is_immediate(opc)) break;
-                        if (o[k] & (OPERAND_CONST | OPERAND_BIT)) continue;
-                        ++T.n_slot_operands;
-                        if (owner[o[k] & M] == o[k]) {
-                            o[k] |= OPERAND_RING;
-                            ++T.n_ring_operands;
-                        }
+                        if (is_tmp(o[k])) last[o[k]] = (uint32_t)l;
                     }
+                }
+            std::vector<std::vector<uint32_t>> release(n_lv + 1);  // physical ids that become free when level l starts
+            std::vector<uint32_t> free_ids;
+            uint32_t next_phys = n_resident;
+            for (size_t l = 0; l < n_lv; ++l) {
+                for (uint32_t p : release[l]) free_ids.push_back(p);
+                for (uint32_t i = T.level_start[l]; i < T.level_start[l + 1]; ++i) {
+                    uint32_t *o = &T.ops[(size_t)i * 4];
+                    const uint32_t opc = o[0] & 0xFFu, d = o[0] >> 8;
+                    if (is_assert_op(opc)) continue;
+                    const uint32_t run = opc == DOP_BITS ? (o[3] >> 24) + 1u : 1u;
+                    if (run > 1) {
+                        if (T.n_bitwords || d < n_resident) continue;  // a word of the bit plane / witness entries
+                        for (uint32_t j = 0; j < run; ++j) phys[d + j] = next_phys++;  // consecutive, never released
+                        continue;
+                    }
+                    if (d < n_resident) continue;
+                    uint32_t p;
+                    if (!free_ids.empty()) { p = free_ids.back(); free_ids.pop_back(); }
+                    else p = next_phys++;
+                    phys[d] = p;
+                    // readers are in levels (l, last[d]]; a value nobody reads (cannot happen after the dead-value
+                    // sweep) would be released at once
+                    release[std::min<size_t>(std::max<size_t>(last[d], l) + 1, n_lv)].push_back(p);
+                }
+            }
+            auto map = [&](uint32_t o) { return is_tmp(o) ? phys[o] : o; };
+            for (size_t i = 0; i < n_ops; ++i) {
+                uint32_t *o = &T.ops[i * 4];
+                const uint32_t opc = o[0] & 0xFFu;
+                if (!is_assert_op(opc) && !(opc == DOP_BITS && (o[3] >> 24) && T.n_bitwords) && (o[0] >> 8) >= n_resident)
+                    o[0] = opc | (phys[o[0] >> 8] << 8);
+                if (opc == 45) continue;
+                for (int k = 1; k <= 3; ++k) {
+                    if (k == 3 && c_is_immediate(opc)) break;
+                    o[k] = map(o[k]);
+                }
+            }
+            for (size_t i = 0; i < T.call_tab.size();) {
+                const uint32_t n = T.call_tab[i + 1];
+                for (uint32_t k = 0; k < n; ++k) T.call_tab[i + 2 + k] = map(T.call_tab[i + 2 + k]);
+                i += 2 + n;
+            }
+            next_tmp = next_phys;
+        }
+        T.n_resident = n_resident;
+        {   // operand statistics
+            T.n_slot_operands = 0;
+            const size_t n_ops = T.ops.size() / 4;
+            for (size_t i = 0; i < n_ops; ++i) {
+                const uint32_t *o = &T.ops[i * 4];
+                const uint32_t opc = o[0] & 0xFFu;
+                if (opc == 45) continue;
+                for (int k = 1; k <= 3; ++k) {
+                    if (k == 3 && c_is_immediate(opc)) break;
+                    if (!(o[k] & (OPERAND_CONST | OPERAND_BIT))) ++T.n_slot_operands;
                 }
             }
         }

@@ -64,10 +64,28 @@ __device__ __forceinline__ void load_const(u32 *v, const uint4 *__restrict__ con
     v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
     v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
 }
+constexpr u32 OPD_CONST = 0x80000000u, OPD_BIT = 0x20000000u, OPD_SLOT = 0x00FFFFFFu, OPD_BITPOS = 0x1FFFFFFFu;
+
+// ---- the bit plane (CW_FLAG_BITPLANE) ----------------------------------------------------------------
+// Bits produced by bit runs (the outputs of Num2Bits-style decompositions: most of the witness of limb
+// arithmetic) are not 32-byte slots: a run of up to 32 bits is ONE 32-bit word.  Word w of instance li of a tile:
+//     u32 index = (tile * n_bitwords + w) * BT + li
+__device__ __forceinline__ u32 load_plane_bit(const u32 *__restrict__ plane_base, u32 pos, u32 bt_log2, u32 li) {
+    return (plane_base[((size_t)(pos >> 5) << bt_log2) + li] >> (pos & 31u)) & 1u;
+}
+
+// operand of a tape op: constant-table entry, a bit of the bit plane, or a value slot
+template <bool BP>
 __device__ __forceinline__ void load_operand(u32 *v, u32 operand, const uint4 *__restrict__ tile_base,
-                                             const uint4 *__restrict__ consts, u32 bt_log2, u32 inst) {
-    if (operand & 0x80000000u) load_const(v, consts, operand & 0x7FFFFFFFu);
-    else load_slot(v, tile_base, operand, bt_log2, inst);
+                                             const u32 *__restrict__ plane_base, const uint4 *__restrict__ consts,
+                                             u32 bt_log2, u32 li) {
+    if (operand & OPD_CONST) {
+        load_const(v, consts, operand & 0x7FFFFFFFu);
+    } else if (BP && (operand & OPD_BIT)) {
+        u256_set_u32(v, load_plane_bit(plane_base, operand & OPD_BITPOS, bt_log2, li));
+    } else {
+        load_slot(v, tile_base, operand & OPD_SLOT, bt_log2, li);
+    }
 }
 
 __device__ __forceinline__ u32 u256_bitlen_dev(const u32 *a) {
@@ -89,6 +107,7 @@ struct TapeDev {
     u32 n_levels;
     u32 n_slots;
     u32 n_inputs;
+    u32 n_bitwords;            // words of the bit plane per instance (0: no bit plane)
 };
 
 // ---- inputs: inputs[batch][n_inputs][8 u32] canonical -> slots 1..n_inputs, slot 0 = 1 ----------
@@ -116,12 +135,14 @@ __global__ void stage_inputs_kernel(TapeDev tp, const uint4 *__restrict__ inputs
 // One CTA owns one tile of BT instances and walks the levels of the tape; within a level the work
 // items (op, instance) are spread over the CTA's threads, instance fastest.  Values produced in
 // level l are consumed in later levels by other threads of the same CTA only, so a CTA barrier
-// per level is the only synchronisation (no grid-wide sync, tiles are independent).
+// per level is the only synchronisation (no grid-wide sync, tiles are independent).  With BT = 32 a warp
+// is ONE op for 32 instances: no divergence, every slot access is 2 x 512 contiguous bytes, the tape word
+// is a broadcast; with BT = 1 a warp is 32 ops of one instance (small batches: lanes along ops).
 // A function call (circom `function` with run-time loops / branches): the thread copies the arguments into
 // the callee's registers (local memory: they are indexed dynamically) and interprets the body.
-template <int PRIME>
-__device__ __noinline__ void exec_call(const TapeDev &tp, u32 call_off, const uint4 *base, u32 bt_log2, u32 li, u32 *r,
-                                       int *err) {
+template <int PRIME, bool BP>
+__device__ __noinline__ void exec_call(const TapeDev &tp, u32 call_off, const uint4 *base, const u32 *plane_base,
+                                       u32 bt_log2, u32 li, u32 *r, int *err) {
     const FrParams &P = c_fr[PRIME];
     const u32 *ct = tp.call_tab + call_off;
     const u32 f = __ldg(&ct[0]), n_args = __ldg(&ct[1]);
@@ -134,7 +155,7 @@ __device__ __noinline__ void exec_call(const TapeDev &tp, u32 call_off, const ui
     for (u32 k = 0; k < fi.n_regs * 8; ++k) regs[k] = 0;
     for (u32 k = 0; k < n_args; ++k) {
         u32 v[8];
-        load_operand(v, __ldg(&ct[2 + k]), base, tp.consts, bt_log2, li);  // call-table operands carry no ring flag
+        load_operand<BP>(v, __ldg(&ct[2 + k]), base, plane_base, tp.consts, bt_log2, li);
         for (int j = 0; j < 8; ++j) regs[8 * k + j] = v[j];
     }
     int e = 0;
@@ -142,51 +163,28 @@ __device__ __noinline__ void exec_call(const TapeDev &tp, u32 call_off, const ui
     *err = e;
 }
 
-// Shared-memory forwarding ring (BT = 1 layouts): every single-value result is also deposited at
-// ring[dst % RING_N] (two 16-byte halves in separate arrays: consecutive entries are conflict-free), and an
-// operand the lowering flagged with bit 30 is read from there instead of from L2 - most operands of a level
-// were produced a few levels earlier by the same CTA.  RING_N must equal CW_RING_SIZE of tape.h: the flags
-// are computed for exactly this size.
-constexpr u32 RING_N = 512;
-constexpr u32 OPD_CONST = 0x80000000u, OPD_RING = 0x40000000u, OPD_SLOT = 0x00FFFFFFu;
-
-template <bool RING>
-__device__ __forceinline__ void load_operand_t(u32 *v, u32 operand, const uint4 *__restrict__ tile_base,
-                                               const uint4 *__restrict__ consts, u32 bt_log2, u32 li,
-                                               const uint4 *ring) {
-    if (operand & OPD_CONST) {
-        load_const(v, consts, operand & 0x7FFFFFFFu);
-    } else if (RING && (operand & OPD_RING)) {
-        const u32 i = operand & (RING_N - 1u);
-        const uint4 lo = ring[i], hi = ring[RING_N + i];
-        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
-        v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
-    } else {
-        load_slot(v, tile_base, operand & OPD_SLOT, bt_log2, li);
-    }
-}
-
 // HAS_CALLS selects the build that contains the function interpreter (more registers, a local-memory
 // frame); tapes without calls - all circuits whose hints are straight-line - use the lean build.
+// BP: the tape was lowered with a bit plane (bit runs write plane words, operands may be plane bits).
 #ifndef CW_TAPE_LB
 #define CW_TAPE_LB 1024
 #endif
 #ifndef CW_TAPE_MINB
 #define CW_TAPE_MINB 1
 #endif
-// BT >= 0 fixes the tile size at compile time (BT = 0, one instance per CTA, is the common layout: the slot
-// address arithmetic then folds to `base + slot * 32`); BT < 0 takes it from the launch argument.
-template <int PRIME, bool HAS_CALLS, bool RING, int BT>
+// BT >= 0 fixes the tile size at compile time (BT = 0, one instance per CTA: the slot address arithmetic then
+// folds to `base + slot * 32`; BT = 5, a warp per op); BT < 0 takes it from the launch argument.
+template <int PRIME, bool HAS_CALLS, bool BP, int BT>
 __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
-    tape_exec_kernel(TapeDev tp, uint4 *__restrict__ slots, u32 bt_log2_arg, u32 *__restrict__ first_assert,
-                     int *__restrict__ err, u32 batch) {
-    extern __shared__ uint4 ring[];  // RING: 2 * RING_N entries (16 KB)
+    tape_exec_kernel(TapeDev tp, uint4 *__restrict__ slots, u32 *__restrict__ plane, u32 bt_log2_arg,
+                     u32 *__restrict__ first_assert, int *__restrict__ err, u32 batch) {
     const FrParams &P = c_fr[PRIME];
     const u32 bt_log2 = BT >= 0 ? (u32)BT : bt_log2_arg;
-    constexpr bool COOP = BT == 0 && !HAS_CALLS;  // warp-cooperative bit-run stores (needs blockDim % 32 == 0)
+    constexpr bool COOP = BT == 0 && !HAS_CALLS && !BP;  // warp-cooperative bit-run stores (needs blockDim % 32 == 0)
     const u32 tile = blockIdx.x;
     const u32 bt_mask = (1u << bt_log2) - 1;
     uint4 *base = slots + (((size_t)tile * tp.n_slots) << (bt_log2 + 1));
+    u32 *plane_base = BP ? plane + (((size_t)tile * tp.n_bitwords) << bt_log2) : nullptr;
     u32 lb = tp.level_start[0];
     u32 le = tp.n_levels ? tp.level_start[1] : lb;
     // the tape word of a thread's first work item of the next level is fetched before the barrier of the
@@ -210,20 +208,15 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
             u32 r[8];
             if (HAS_CALLS && opcode == OP_CALL) {
                 int e = 0;
-                exec_call<PRIME>(tp, opw.y, base, bt_log2, li, r, &e);
+                exec_call<PRIME, BP>(tp, opw.y, base, plane_base, bt_log2, li, r, &e);
                 if (e && inst < batch) err[inst] = 1;
-            } else if (opcode == OP_BITS && ((opw.w >> 16) & 0xFFu) <= 32u && !(opw.y & OPD_CONST)) {
+            } else if (opcode == OP_BITS && ((opw.w >> 16) & 0xFFu) <= 32u && !(opw.y & (OPD_CONST | OPD_BIT))) {
                 // narrow bit-field of a slot value: fetch only the one or two 32-bit words that hold it
                 const u32 k = opw.w & 0xFFFFu, m = (opw.w >> 16) & 0xFFu, run = (opw.w >> 24) + 1u;
                 const u32 wd = k >> 5, sh = k & 31u;
                 const bool two = sh + m + run - 1u > 32u && wd < 7u;
                 u32 lo, hi = 0;
-                if (RING && (opw.y & OPD_RING)) {
-                    const u32 *rw = reinterpret_cast<const u32 *>(ring);
-                    const u32 i = opw.y & (RING_N - 1u), w1 = wd + 1u;
-                    lo = rw[(((wd >> 2) * RING_N + i) << 2) + (wd & 3u)];
-                    if (two) hi = rw[(((w1 >> 2) * RING_N + i) << 2) + (w1 & 3u)];
-                } else {
+                {
                     const u32 *words = reinterpret_cast<const u32 *>(base);
                     const size_t src = (size_t)(opw.y & OPD_SLOT) << (bt_log2 + 1);
                     const u32 w1 = wd + 1u;
@@ -234,8 +227,10 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
 #pragma unroll
                 for (int i = 1; i < 8; ++i) r[i] = 0;
                 if (run > 1u) {
-                    // a run writes `run` (<= 32) consecutive slots, one bit each; runs bypass the ring
-                    if (COOP) {  // stored by the whole warp after the body
+                    if (BP) {  // the run is ONE word of the bit plane (dst = word index): a single 4-byte store
+                        plane_base[((size_t)dst << bt_log2) + li] =
+                            (u32)window & (run >= 32u ? 0xFFFFFFFFu : ((1u << run) - 1u));
+                    } else if (COOP) {  // `run` (<= 32) consecutive slots, one bit each: stored by the whole warp after the body
                         run_dst = dst;
                         run_n = run;
                         run_bits = (u32)window;
@@ -250,11 +245,11 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
                 r[0] = (u32)window & (m >= 32u ? 0xFFFFFFFFu : ((1u << m) - 1u));
             } else {
                 u32 a[8], b[8];
-                load_operand_t<RING>(a, opw.y, base, tp.consts, bt_log2, li, ring);
-                load_operand_t<RING>(b, opw.z, base, tp.consts, bt_log2, li, ring);
+                load_operand<BP>(a, opw.y, base, plane_base, tp.consts, bt_log2, li);
+                load_operand<BP>(b, opw.z, base, plane_base, tp.consts, bt_log2, li);
                 if (opcode == OP_SELECT) {
                     u32 c[8];
-                    load_operand_t<RING>(c, opw.w, base, tp.consts, bt_log2, li, ring);
+                    load_operand<BP>(c, opw.w, base, plane_base, tp.consts, bt_log2, li);
                     bool t = !u256_is_zero(c);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) r[i] = t ? a[i] : b[i];
@@ -273,10 +268,6 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
                 }
             }
             store_slot(r, base, dst, bt_log2, li);
-            if (RING) {
-                ring[dst & (RING_N - 1u)] = make_uint4(r[0], r[1], r[2], r[3]);
-                ring[RING_N + (dst & (RING_N - 1u))] = make_uint4(r[4], r[5], r[6], r[7]);
-            }
             } while (0);
             if (COOP) {
                 // Bit runs, warp-cooperatively: the slots of a run are consecutive, so lane j stores bit j and one
@@ -304,152 +295,196 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
     }
 }
 
-// ---- witness compaction for tile layouts with BT > 1: out[inst][w] = slot w (witness entries are the
-// first n_witness slots, already canonical).  With BT = 1 the witness rows are contiguous inside the slot
-// store and are read in place (strided) or copied with cudaMemcpy2D.
-__global__ void witness_compact_kernel(const uint4 *__restrict__ slots, uint4 *__restrict__ out, u32 n_slots,
-                                       u32 n_witness, u32 batch, u32 bt_log2) {
-    const u32 bt = 1u << bt_log2;
-    const u32 tiles = (batch + bt - 1) >> bt_log2;
-    size_t total = (size_t)tiles * n_witness * bt;
-    for (size_t w = blockIdx.x * (size_t)blockDim.x + threadIdx.x; w < total; w += (size_t)gridDim.x * blockDim.x) {
-        u32 li = (u32)(w & (bt - 1));
-        size_t rest = w >> bt_log2;
-        u32 wi = (u32)(rest % n_witness);
-        u32 tile = (u32)(rest / n_witness);
-        u32 inst = (tile << bt_log2) + li;
-        if (inst >= batch) continue;
-        const uint4 *base = slots + (((size_t)tile * n_slots) << (bt_log2 + 1));
-        u32 v[8];
-        load_slot(v, base, wi, bt_log2, li);
-        uint4 *dst = out + ((size_t)inst * n_witness + wi) * 2;
-        dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
-        dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
+// ---- where the values of an instance live --------------------------------------------------------------
+// The tape's value store (tile layout, optional bit plane) or - for witnesses handed in by a caller - a dense
+// array of 32-byte rows (bt_log2 = 0, n_bitwords = 0, n_slots = row stride, location = wire id).
+// A *location* is an operand word of the tape: OPD_BIT | (word * 32 + bit), or a slot id.
+struct StoreDev {
+    const uint4 *slots;
+    const u32 *plane;
+    u32 n_slots, n_bitwords, bt_log2, batch;
+};
+__device__ __forceinline__ const uint4 *store_tile(const StoreDev &S, u32 tile) {
+    return S.slots + (((size_t)tile * S.n_slots) << (S.bt_log2 + 1));
+}
+__device__ __forceinline__ const u32 *store_plane(const StoreDev &S, u32 tile) {
+    return S.plane + (((size_t)tile * S.n_bitwords) << S.bt_log2);
+}
+// (slot values of other kernels' output: read-only here, through the non-coherent path)
+__device__ __forceinline__ void load_slot_nc(u32 *v, const uint4 *__restrict__ tile_base, u32 slot, u32 bt_log2, u32 li) {
+    if (bt_log2 == 0) {
+        ldg256_nc(v, tile_base + ((size_t)slot << 1));
+        return;
+    }
+    size_t i = ((size_t)slot << (bt_log2 + 1)) + li;
+    uint4 lo = __ldg(&tile_base[i]);
+    uint4 hi = __ldg(&tile_base[i + ((size_t)1 << bt_log2)]);
+    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+    v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+}
+__device__ __forceinline__ void load_loc(u32 *v, const StoreDev &S, const uint4 *__restrict__ tile_base,
+                                         const u32 *__restrict__ plane_base, u32 loc, u32 li) {
+    if (loc & OPD_BIT) {
+        const u32 pos = loc & OPD_BITPOS;
+        u256_set_u32(v, (__ldg(&plane_base[((size_t)(pos >> 5) << S.bt_log2) + li]) >> (pos & 31u)) & 1u);
+    } else {
+        load_slot_nc(v, tile_base, loc, S.bt_log2, li);
+    }
+}
+
+// ---- dense witness rows on demand: out[i - first][w] = witness entry w of instance i, canonical 32 bytes ----
+// The tape keeps the witness where it produced it (resident slots + bit plane); the reference's layout - W
+// consecutive 32-byte elements per witness (calcwit.hpp:54-56, main.cpp:328-332) - is materialised only for
+// consumers that ask for it (cw_batch_witness_device, .wtns, the plain device->host copy).
+__global__ void witness_expand_kernel(StoreDev S, const u32 *__restrict__ wloc, u32 n_witness, u32 first, u32 count,
+                                      uint4 *__restrict__ out) {
+    const u32 bt_mask = (1u << S.bt_log2) - 1u;
+    for (u32 i = blockIdx.y; i < count; i += gridDim.y) {
+        const u32 inst = first + i, tile = inst >> S.bt_log2, li = inst & bt_mask;
+        const uint4 *tb = store_tile(S, tile);
+        const u32 *pb = store_plane(S, tile);
+        uint4 *row = out + (size_t)i * n_witness * 2;
+        for (u32 w = blockIdx.x * blockDim.x + threadIdx.x; w < n_witness; w += gridDim.x * blockDim.x) {
+            u32 v[8];
+            load_loc(v, S, tb, pb, __ldg(&wloc[w]), li);
+            stg256(row + 2 * (size_t)w, v);
+        }
     }
 }
 
 // ---- packed witness for the device->host transfer -------------------------------------------------------
-// Most witness entries of real circuits are bits or 64-bit limbs stored as 32-byte field elements.  The
-// lowering knows an upper bound of every entry's bit length (range analysis); entries proven to be one bit
-// travel as one bit, entries proven <= 64 bits as 8 bytes, the rest as 32 bytes, and the host expands them
-// back to the canonical 32-byte rows.  Each value is re-checked here against its class: a violation raises
-// `flag` and the caller falls back to the plain copy.  Per-instance packed layout (32-bit words):
-// [bit words][u64 entries][full entries].  BT = 1 layout only.
-__global__ void witness_pack_kernel(const uint4 *__restrict__ slots, u32 n_slots, const u32 *__restrict__ bit_wire,
-                                    u32 n_bits, const u32 *__restrict__ u64_wire, u32 n_u64,
-                                    const u32 *__restrict__ full_wire, u32 n_full, u32 *__restrict__ packed,
-                                    size_t words_per_inst, u32 batch, int *__restrict__ flag) {
+// Most witness entries of real circuits are bits or 64-bit limbs.  The lowering knows an upper bound of every
+// entry's bit length (range analysis); entries proven to be one bit travel as one bit, entries proven <= 64 bits
+// as 8 bytes, the rest as 32 bytes, and the host expands them back to the canonical 32-byte rows.  Per-instance
+// packed record (32-bit words):
+//     [the instance's bit plane, as it is][bits outside the plane, 32 per word][u64 entries][full entries]
+// Values outside the plane are re-checked against their class: a violation raises `flag` and the caller falls
+// back to the dense copy.  (Plane bits are single bits by construction.)
+__global__ void witness_pack_kernel(StoreDev S, const u32 *__restrict__ bit_loc, u32 n_bits,
+                                    const u32 *__restrict__ u64_loc, u32 n_u64, const u32 *__restrict__ full_loc,
+                                    u32 n_full, u32 *__restrict__ packed, size_t words_per_inst, u32 first, u32 count,
+                                    int *__restrict__ flag) {
     const u32 n_bit_words = (n_bits + 31u) >> 5;
-    const size_t items = (size_t)n_bit_words + n_u64 + n_full;
-    for (u32 inst = blockIdx.y; inst < batch; inst += gridDim.y) {
-        const uint4 *base = slots + (size_t)inst * n_slots * 2;
-        u32 *out = packed + (size_t)inst * words_per_inst;
+    const size_t items = (size_t)S.n_bitwords + n_bit_words + n_u64 + n_full;
+    const u32 bt_mask = (1u << S.bt_log2) - 1u;
+    for (u32 i = blockIdx.y; i < count; i += gridDim.y) {
+        const u32 inst = first + i, tile = inst >> S.bt_log2, li = inst & bt_mask;
+        const uint4 *tb = store_tile(S, tile);
+        const u32 *pb = store_plane(S, tile);
+        u32 *out = packed + (size_t)i * words_per_inst;
         for (size_t it = blockIdx.x * (size_t)blockDim.x + threadIdx.x; it < items; it += (size_t)gridDim.x * blockDim.x) {
-            if (it < n_bit_words) {
+            if (it < S.n_bitwords) {
+                out[it] = __ldg(&pb[(it << S.bt_log2) + li]);
+                continue;
+            }
+            u32 *o = out + S.n_bitwords;
+            size_t k = it - S.n_bitwords;
+            if (k < n_bit_words) {
                 u32 word = 0, bad = 0;
-                const u32 j0 = (u32)it << 5;
+                const u32 j0 = (u32)k << 5;
 #pragma unroll 4
                 for (u32 j = 0; j < 32u; ++j) {
                     if (j0 + j < n_bits) {
-                        const u32 w = __ldg(&bit_wire[j0 + j]);
                         u32 x[8];
-                        ldg256_nc(x, base + 2 * (size_t)w);
+                        load_slot_nc(x, tb, __ldg(&bit_loc[j0 + j]), S.bt_log2, li);
                         bad |= x[1] | x[2] | x[3] | x[4] | x[5] | x[6] | x[7] | (x[0] & ~1u);
                         word |= (x[0] & 1u) << j;
                     }
                 }
-                out[it] = word;
+                o[k] = word;
                 if (bad) *flag = 1;
-            } else if (it < (size_t)n_bit_words + n_u64) {
-                const u32 k = (u32)(it - n_bit_words);
-                const u32 w = __ldg(&u64_wire[k]);
+            } else if (k < (size_t)n_bit_words + n_u64) {
+                const u32 e = (u32)(k - n_bit_words);
                 u32 x[8];
-                ldg256_nc(x, base + 2 * (size_t)w);
+                load_slot_nc(x, tb, __ldg(&u64_loc[e]), S.bt_log2, li);
                 if (x[2] | x[3] | x[4] | x[5] | x[6] | x[7]) *flag = 1;
-                out[n_bit_words + 2 * (size_t)k] = x[0];
-                out[n_bit_words + 2 * (size_t)k + 1] = x[1];
+                o[n_bit_words + 2 * (size_t)e] = x[0];
+                o[n_bit_words + 2 * (size_t)e + 1] = x[1];
             } else {
-                const u32 k = (u32)(it - n_bit_words - n_u64);
-                const u32 w = __ldg(&full_wire[k]);
+                const u32 e = (u32)(k - n_bit_words - n_u64);
                 u32 x[8];
-                ldg256_nc(x, base + 2 * (size_t)w);
-                u32 *o = out + n_bit_words + 2 * (size_t)n_u64 + 8 * (size_t)k;
+                load_slot_nc(x, tb, __ldg(&full_loc[e]), S.bt_log2, li);
+                u32 *oo = o + n_bit_words + 2 * (size_t)n_u64 + 8 * (size_t)e;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = x[i];
+                for (int q = 0; q < 8; ++q) oo[q] = x[q];
             }
         }
     }
 }
 
 // ---- R1CS check: A.w * B.w == C.w for every row and instance ------------------------------------
-// CSR: row_ptr[3m+1] (A, B, C blocks per row), col[nnz] (wire), coef[nnz] (dictionary index).
-// Per dictionary entry: dictM = coefficient * R mod q and a kind word
-//     bits 0-7  : 0 general, 1 = +1, 2 = -1, 3 = +2^k, 4 = -2^k        bits 8-15 : k
-// witness[inst][n_wires][8 u32] canonical.
+// Compiled CSR: row_ptr[3m+1] (A, B, C blocks per row) over 16-byte term records
+//     {location of the wire's value, coefficient dictionary index, kind word, absorbed boolean row or ~0}
+// kind word: bits 0-7  : 0 general (Montgomery product with dictM), 1 = +1, 2 = -1, 3 = +2^k, 4 = -2^k, with k in
+//                        bits 8-15;  5 / 6 = +- RUN: `count` consecutive bits of ONE bit-plane word, whose
+//                        coefficients are consecutive powers of two - the recomposition sums of range checks,
+//                        65 terms in the file, are two such records: value = ((word >> first) & mask) << k,
+//                        first in bits 16-20, count - 1 in bits 21-25, location = word index.
 //
-// Work decomposition: thread = (row, instance).  Rows are visited through `perm`, a host-side stable
-// sort of the rows by structure (term counts and coefficient kinds), so that the 32 rows of a warp have
-// the same length and take the same branches: circuits mix 3-term boolean rows with 65-term
-// bit-sum rows, and with the natural order every warp would run at the speed of its longest row.
-// blockIdx.y walks groups of instances; a thread re-walks its row for each instance of the group,
-// so the row's col/coef words come from L1 after the first instance.
+// Work decomposition: work item = (row, instance), instance fastest inside a tile, rows visited through `perm`,
+// a host-side stable sort of the rows by structure (term counts and coefficient kinds).  With 32-instance tiles
+// a warp is ONE row for 32 instances: the term records are broadcasts, the witness loads 512 contiguous bytes,
+// nothing diverges but the data-dependent product skips; with one-instance tiles a warp is 32 rows of equal
+// structure.  blockIdx.y walks the tiles.
 //
 // Arithmetic: +-1 coefficients are modular add/sub; +-2^k coefficients shift the witness value when
 // the shifted value provably stays below q (runtime check of the value's bit length; a Montgomery
-// product otherwise); the row product a*b is skipped when a or b is 0 or 1 (boolean-constraint rows).
+// product otherwise); the row product a*b is skipped when a or b is 0, 1 or -1.
 struct R1csDev {
     const unsigned long long *row_ptr;
-    // per term {wire, coefficient dictionary index, kind word of the coefficient, row id of the boolean constraint
-    // of the wire that is checked alongside or ~0}: one 128-bit load per term
     const uint4 *terms;
     const uint4 *dictM;
     const u32 *perm;
-    u32 n_constraints;
-    u32 n_wires;
-    u32 inst_per_block;
-    unsigned long long w_stride;  // distance between two instances' witness rows, in 32-byte elements
+    u32 n_rows;  // rows in perm
 };
 
 template <int PRIME>
 __device__ __forceinline__ void r1cs_lc(u32 *acc, const R1csDev &R, unsigned long long b, unsigned long long e,
-                                        const uint4 *__restrict__ w, const FrParams &P,
-                                        unsigned long long *__restrict__ first_bad_inst, u32 step = 1) {
+                                        const StoreDev &S, const uint4 *__restrict__ tb, const u32 *__restrict__ pb,
+                                        u32 li, const FrParams &P, unsigned long long *__restrict__ first_bad_inst) {
     u256_set_u32(acc, 0);
-    for (unsigned long long k = b; k < e; k += step) {
-        // one 16-byte record per term: {wire, dictionary index, kind word, absorbed boolean row}
+    for (unsigned long long k = b; k < e; ++k) {
         const uint4 term = __ldg(&R.terms[k]);
-        const u32 c = term.x, ci = term.y, kw = term.z, brow = term.w;
-        u32 x[8];
-        ldg256_nc(x, w + 2 * (size_t)c);
-        u32 t[8];
-        u32 kd = kw & 0xFF, sh = kw >> 8;
-        bool neg = (kd == 2) || (kd == 4);
-        const u32 upper = x[1] | x[2] | x[3] | x[4] | x[5] | x[6] | x[7];
-        // the boolean constraint x*(x-1) = 0 of this wire is checked here, while its value is in registers
-        if (brow != 0xFFFFFFFFu && (upper || x[0] > 1u)) atomicMin(first_bad_inst, (unsigned long long)brow);
-        if (kd >= 3) {
-            if (!upper && sh + 32u < P.qbits) {  // x < 2^32 and x * 2^sh < 2^(qbits-1) < q
-                // one-limb value times 2^sh: place the (at most 64-bit) shifted value, no reduction needed
-                const u32 wd = sh >> 5, s = sh & 31u;
-                const u32 l = x[0] << s, h = s ? (x[0] >> (32u - s)) : 0u;
+        const u32 loc = term.x, ci = term.y, kw = term.z, brow = term.w;
+        const u32 kd = kw & 0xFF, sh = (kw >> 8) & 0xFF;
+        u32 x[8], t[8];
+        bool neg = (kd == 2) || (kd == 4) || (kd == 6);
+        if (kd >= 5) {
+            // run of plane bits times consecutive powers of two: an integer below 2^(sh + count) < q
+            const u32 first = (kw >> 16) & 31u, cnt = ((kw >> 21) & 31u) + 1u;
+            const u32 word = (__ldg(&pb[((size_t)loc << S.bt_log2) + li]) >> first) & (cnt >= 32u ? 0xFFFFFFFFu : ((1u << cnt) - 1u));
+            const u32 wd = sh >> 5, s = sh & 31u;
+            const u32 l = word << s, h = s ? (word >> (32u - s)) : 0u;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = ((u32)i == wd) ? l : (((u32)i == wd + 1u) ? h : 0u);
-            } else if (u256_bitlen_dev(x) + sh < P.qbits) {   // x * 2^sh < 2^(qbits-1) < q : plain shift
-                u32 y[8];
-                u256_shl(y, x, sh);
-                u256_set(x, y);
-            } else {
+            for (int i = 0; i < 8; ++i) x[i] = ((u32)i == wd) ? l : (((u32)i == wd + 1u) ? h : 0u);
+        } else {
+            load_loc(x, S, tb, pb, loc, li);
+            const u32 upper = x[1] | x[2] | x[3] | x[4] | x[5] | x[6] | x[7];
+            // the boolean constraint x*(x-1) = 0 of this wire is checked here, while its value is in registers
+            if (brow != 0xFFFFFFFFu && (upper || x[0] > 1u)) atomicMin(first_bad_inst, (unsigned long long)brow);
+            if (kd >= 3) {
+                if (!upper && sh + 32u < P.qbits) {  // x < 2^32: x * 2^sh < 2^(qbits-1) < q, placed without a reduction
+                    const u32 wd = sh >> 5, s = sh & 31u;
+                    const u32 l = x[0] << s, h = s ? (x[0] >> (32u - s)) : 0u;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) x[i] = ((u32)i == wd) ? l : (((u32)i == wd + 1u) ? h : 0u);
+                } else if (u256_bitlen_dev(x) + sh < P.qbits) {   // x * 2^sh < 2^(qbits-1) < q : plain shift
+                    u32 y[8];
+                    u256_shl(y, x, sh);
+                    u256_set(x, y);
+                } else {
+                    u32 cm[8], p[8];
+                    load_const(cm, R.dictM, ci);
+                    fr_mont_mul(p, cm, x, P);           // (cR) * x / R = c*x, sign included
+                    u256_set(x, p);
+                    neg = false;
+                }
+            } else if (kd == 0) {
                 u32 cm[8], p[8];
                 load_const(cm, R.dictM, ci);
-                fr_mont_mul(p, cm, x, P);           // (cR) * x / R = c*x, sign included
+                fr_mont_mul(p, cm, x, P);
                 u256_set(x, p);
-                neg = false;
             }
-        } else if (kd == 0) {
-            u32 cm[8], p[8];
-            load_const(cm, R.dictM, ci);
-            fr_mont_mul(p, cm, x, P);
-            u256_set(x, p);
         }
         if (neg) fr_sub(t, acc, x, P);
         else fr_add(t, acc, x, P);
@@ -481,86 +516,63 @@ __device__ __forceinline__ bool r1cs_row_holds(const u32 *a, const u32 *b, const
     return ok;
 }
 
-// MINB = CTAs per SM the register budget is cut for.  Measured on the bench circuit (long rows, bound by memory
-// latency), batch 1024: 3 (78 registers, no spills) 16.4 ms, 4 (64) 13.7 ms, 5 (48, 240 B spilled) 13.0 ms, 6 (40)
-// 17.0 ms - resident warps buy more than the spills cost.  Circuits of short rows (SHA-256: ~5 terms and a
-// Montgomery product per row) are arithmetic-bound and prefer the unspilled build; the host picks by the mean
-// row length.
-template <int PRIME, int MINB>
-__global__ void __launch_bounds__(256, MINB) r1cs_check_kernel(R1csDev R, const uint4 *__restrict__ witness, u32 batch,
-                                                         unsigned long long *__restrict__ first_bad) {
+// MINB = CTAs per SM the register budget is cut for (r01 measurements on the bench circuit, long rows, bound by
+// memory latency: 3 -> 16.4 ms, 4 -> 13.7 ms, 5 -> 13.0 ms, 6 -> 17.0 ms per 1024 instances; circuits of short
+// rows prefer the unspilled build); the host picks by the mean row length.
+// EVAL: also leave A.w, B.w, C.w of every row in device memory ([instance][row] 32-byte elements) for a prover
+struct EvalOut {
+    uint4 *a = nullptr, *b = nullptr, *c = nullptr;
+    unsigned long long m = 0;  // rows per instance
+};
+template <int PRIME, int MINB, bool EVAL>
+__global__ void __launch_bounds__(256, MINB) r1cs_check_kernel(R1csDev R, StoreDev S, unsigned long long *__restrict__ first_bad,
+                                                         EvalOut out) {
     const FrParams &P = c_fr[PRIME];
-    const u32 i0 = blockIdx.y * R.inst_per_block;
-    const u32 i1 = min(batch, i0 + R.inst_per_block);
-    for (u32 rs = blockIdx.x * blockDim.x + threadIdx.x; rs < R.n_constraints; rs += gridDim.x * blockDim.x) {
-        const u32 row = __ldg(&R.perm[rs]);
-        const unsigned long long p0 = R.row_ptr[3 * (size_t)row], p1 = R.row_ptr[3 * (size_t)row + 1],
-                                 p2 = R.row_ptr[3 * (size_t)row + 2], p3 = R.row_ptr[3 * (size_t)row + 3];
-        for (u32 inst = i0; inst < i1; ++inst) {
-            const uint4 *w = witness + (size_t)inst * R.w_stride * 2;
+    const u32 bt_mask = (1u << S.bt_log2) - 1u;
+    const u32 n_tiles = (S.batch + bt_mask) >> S.bt_log2;
+    const unsigned long long n_items = (unsigned long long)R.n_rows << S.bt_log2;
+    for (u32 tile = blockIdx.y; tile < n_tiles; tile += gridDim.y) {
+        const uint4 *tb = store_tile(S, tile);
+        const u32 *pb = store_plane(S, tile);
+        for (unsigned long long w = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; w < n_items;
+             w += (unsigned long long)gridDim.x * blockDim.x) {
+            const u32 li = (u32)w & bt_mask, inst = (tile << S.bt_log2) + li;
+            if (inst >= S.batch) continue;
+            const u32 row = __ldg(&R.perm[w >> S.bt_log2]);
+            const unsigned long long p0 = __ldg(&R.row_ptr[3 * (size_t)row]), p1 = __ldg(&R.row_ptr[3 * (size_t)row + 1]),
+                                     p2 = __ldg(&R.row_ptr[3 * (size_t)row + 2]), p3 = __ldg(&R.row_ptr[3 * (size_t)row + 3]);
             u32 a[8], b[8], c[8];
-            r1cs_lc<PRIME>(a, R, p0, p1, w, P, &first_bad[inst]);
-            r1cs_lc<PRIME>(b, R, p1, p2, w, P, &first_bad[inst]);
-            r1cs_lc<PRIME>(c, R, p2, p3, w, P, &first_bad[inst]);
-            const bool ok = r1cs_row_holds(a, b, c, P);
-            if (!ok) atomicMin(&first_bad[inst], (unsigned long long)row);
-        }
-    }
-}
-
-// Long rows (the 65-term recomposition sums of range checks, polynomial identities): G lanes share one
-// (row, instance); lane g takes terms g, g + G, ... of each linear combination and the partial sums are
-// combined with a butterfly of modular additions.  The terms of such a row reference consecutive witness
-// entries, so the G lanes read G adjacent 32-byte elements (whole 128-byte lines) where one thread walking
-// the row alone touches one sector per load; and the dependent chain per thread is G times shorter.
-template <int PRIME, int G>
-__global__ void __launch_bounds__(256) r1cs_check_split_kernel(R1csDev R, const uint4 *__restrict__ witness, u32 batch,
-                                                               unsigned long long *__restrict__ first_bad) {
-    const FrParams &P = c_fr[PRIME];
-    const u32 i0 = blockIdx.y * R.inst_per_block;
-    const u32 i1 = min(batch, i0 + R.inst_per_block);
-    const u32 g = threadIdx.x & (G - 1);
-    const u32 gmask = ((G == 32) ? 0xFFFFFFFFu : ((1u << G) - 1u)) << ((threadIdx.x & 31u) & ~(u32)(G - 1));
-    const u32 per_block = blockDim.x / G;
-    for (u32 rs = blockIdx.x * per_block + threadIdx.x / G; rs < R.n_constraints; rs += gridDim.x * per_block) {
-        const u32 row = __ldg(&R.perm[rs]);
-        unsigned long long p[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) p[j] = R.row_ptr[3 * (size_t)row + j];
-        for (u32 inst = i0; inst < i1; ++inst) {
-            const uint4 *w = witness + (size_t)inst * R.w_stride * 2;
-            u32 lc[3][8];
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                r1cs_lc<PRIME>(lc[j], R, p[j] + g, p[j + 1], w, P, &first_bad[inst], G);
-                if (p[j + 1] == p[j]) continue;  // empty combination: every lane holds 0
-#pragma unroll
-                for (int off = G / 2; off > 0; off >>= 1) {
-                    u32 o[8], t[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) o[i] = __shfl_xor_sync(gmask, lc[j][i], off);
-                    fr_add(t, lc[j], o, P);
-                    u256_set(lc[j], t);
-                }
+            r1cs_lc<PRIME>(a, R, p0, p1, S, tb, pb, li, P, &first_bad[inst]);
+            r1cs_lc<PRIME>(b, R, p1, p2, S, tb, pb, li, P, &first_bad[inst]);
+            r1cs_lc<PRIME>(c, R, p2, p3, S, tb, pb, li, P, &first_bad[inst]);
+            if (EVAL) {
+                const size_t o = ((size_t)inst * out.m + row) * 2;
+                stg256(out.a + o, a);
+                stg256(out.b + o, b);
+                stg256(out.c + o, c);
             }
-            if (g == 0 && !r1cs_row_holds(lc[0], lc[1], lc[2], P)) atomicMin(&first_bad[inst], (unsigned long long)row);
+            if (!r1cs_row_holds(a, b, c, P)) atomicMin(&first_bad[inst], (unsigned long long)row);
         }
     }
 }
 
-// boolean rows x*(x-1) = 0: the witness value must be 0 or 1.  Thread = (boolean row, instance); the
-// wires of consecutive boolean rows are consecutive witness entries (the bits of one decomposition), so
-// a warp reads a contiguous 1 KB run of the instance's witness row.  Purely memory-bound (32 B per row).
-__global__ void __launch_bounds__(256) r1cs_bool_kernel(const u32 *__restrict__ wire, const u32 *__restrict__ rows,
-                                                        u32 n_bool, const uint4 *__restrict__ witness,
-                                                        unsigned long long w_stride, u32 batch,
-                                                        unsigned long long *__restrict__ first_bad) {
-    for (u32 inst = blockIdx.y; inst < batch; inst += gridDim.y) {
-        const uint4 *w = witness + (size_t)inst * w_stride * 2;
-        for (u32 k = blockIdx.x * blockDim.x + threadIdx.x; k < n_bool; k += gridDim.x * blockDim.x) {
-            const u32 c = __ldg(&wire[k]);
+// boolean rows x*(x-1) = 0 that no general row absorbs: the witness value must be 0 or 1.  Work item = (boolean
+// row, instance); the wires of consecutive boolean rows are consecutive witness entries.  (Rows whose wire is a
+// bit of the bit plane are not listed at all: a stored bit is 0 or 1.)
+__global__ void __launch_bounds__(256) r1cs_bool_kernel(const u32 *__restrict__ loc, const u32 *__restrict__ rows,
+                                                        u32 n_bool, StoreDev S, unsigned long long *__restrict__ first_bad) {
+    const u32 bt_mask = (1u << S.bt_log2) - 1u;
+    const u32 n_tiles = (S.batch + bt_mask) >> S.bt_log2;
+    const unsigned long long n_items = (unsigned long long)n_bool << S.bt_log2;
+    for (u32 tile = blockIdx.y; tile < n_tiles; tile += gridDim.y) {
+        const uint4 *tb = store_tile(S, tile);
+        for (unsigned long long w = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; w < n_items;
+             w += (unsigned long long)gridDim.x * blockDim.x) {
+            const u32 li = (u32)w & bt_mask, inst = (tile << S.bt_log2) + li;
+            if (inst >= S.batch) continue;
+            const u32 k = (u32)(w >> S.bt_log2);
             u32 x[8];
-            ldg256_nc(x, w + 2 * (size_t)c);
+            load_slot_nc(x, tb, __ldg(&loc[k]), S.bt_log2, li);
             const u32 rest = x[1] | x[2] | x[3] | x[4] | x[5] | x[6] | x[7];
             if (rest || x[0] > 1u) atomicMin(&first_bad[inst], (unsigned long long)__ldg(&rows[k]));
         }

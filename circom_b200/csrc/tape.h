@@ -9,15 +9,10 @@
 namespace cw {
 
 constexpr uint32_t OPERAND_CONST = 0x80000000u;  // operand bit31: index into the constant table
-// operand bit30: the value is also held in the CTA's shared-memory forwarding ring at index (slot % CW_RING_SIZE).
-// Every single-value op deposits its result there; the lowering sets the bit when it can prove that no later
-// write to the same ring index happens before the end of the consumer's level (see flatten.cpp).
-constexpr uint32_t OPERAND_RING = 0x40000000u;
 constexpr uint32_t OPERAND_SLOT_MASK = 0x00FFFFFFu;
 // operand bit29 (tapes lowered with CW_FLAG_BITPLANE): the value is one bit of the instance's bit plane,
 // bits 0-28 = word * 32 + bit.  witness_slot[] entries use the same encoding.
 constexpr uint32_t OPERAND_BIT = 0x20000000u, OPERAND_BITPOS_MASK = 0x1FFFFFFFu;
-constexpr uint32_t CW_RING_LOG2 = 9, CW_RING_SIZE = 1u << CW_RING_LOG2;
 constexpr uint32_t WSLOT_MONT = 0x80000000u;     // witness_slot bit31: slot holds the Montgomery image
 constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
 
@@ -50,7 +45,8 @@ struct Tape {
     uint64_t n_signals = 0, n_witness = 0, n_inputs = 0, n_outputs = 0, n_components = 0;
     uint64_t n_ir_ops = 0, n_mul_ops = 0, n_conv_ops = 0, max_level_width = 0, n_asserts = 0;
     uint64_t slot_census[4] = {0, 0, 0, 0};  // value slots by static width: 1 bit, <= 32, <= 64 bits, wider
-    uint64_t n_slot_operands = 0, n_ring_operands = 0;  // operand reads of slots / of which forwarded through the ring
+    uint64_t n_slot_operands = 0;  // operand reads of slots
+    uint32_t n_resident = 0;  // slots [0, n_resident) hold witness entries for the whole run; the rest are reused temporaries (CW_FLAG_REUSE)
     uint32_t n_pre = 0;    // slot 0 = constant one, slots 1..n_inputs = main inputs
     uint32_t n_slots = 0;  // witness entries [0, n_witness) then the other values
     uint32_t n_bitwords = 0;  // 32-bit words of the bit plane per instance (0: every value is a 32-byte slot)

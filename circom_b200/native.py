@@ -12,7 +12,8 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t
 from . import build as _build
 
 CW_OK, CW_EINVAL, CW_EIO, CW_EFORMAT, CW_ECUDA, CW_ENOTFOUND, CW_ESTATE, CW_ENODEV = 0, -1, -2, -3, -4, -5, -6, -7
-CW_FLAG_NO_ASSERTS, CW_FLAG_HOST_ONLY, CW_FLAG_O0 = 1, 2, 4
+CW_FLAG_NO_ASSERTS, CW_FLAG_HOST_ONLY, CW_FLAG_O0, CW_FLAG_NO_PEEPHOLE, CW_FLAG_BITPLANE, CW_FLAG_REUSE = 1, 2, 4, 8, 16, 32
+CW_FLAG_COMPACT = CW_FLAG_BITPLANE | CW_FLAG_REUSE
 
 
 class CwError(RuntimeError):
@@ -25,10 +26,10 @@ class CwStats(ctypes.Structure):
     _fields_ = [(n, c_uint64) for n in (
         "n_signals", "n_witness", "n_inputs", "n_outputs", "n_components", "n_constants", "n_ir_ops",
         "n_tape_ops", "n_slots", "n_levels", "n_constraints", "n_nnz", "n_mul_ops", "n_conv_ops",
-        "max_level_width", "n_slot_operands", "n_ring_operands")] + [("reserved", c_uint64 * 1)]
+        "max_level_width", "n_slot_operands", "n_bitwords", "n_resident_slots")]
 
     def as_dict(self):
-        return {n: int(getattr(self, n)) for n, _ in self._fields_ if n != "reserved"}
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
 def _load() -> ctypes.CDLL:
@@ -70,6 +71,14 @@ def _load() -> ctypes.CDLL:
         "cw_batch_status": (c_int, [P, c_void_p]),
         "cw_batch_get_witness": (c_int, [P, c_void_p]),
         "cw_batch_last_d2h_bytes": (c_uint64, [P]),
+        "cw_batch_layout": (c_int, [P, POINTER(c_uint32), POINTER(c_uint32), POINTER(c_uint64)]),
+        "cw_batch_get_witness_async": (c_int, [P, c_void_p]),
+        "cw_batch_get_witness_wait": (c_int, [P]),
+        "cw_batch_get_witness_packed": (c_int, [P, c_void_p]),
+        "cw_circuit_pack_info": (c_int, [P, POINTER(c_uint64), c_void_p]),
+        "cw_batch_expand_witness": (c_int, [P, c_uint32, c_uint32, c_void_p]),
+        "cw_r1cs_check_batch": (c_int, [P, P, c_void_p, POINTER(c_float)]),
+        "cw_r1cs_eval_batch": (c_int, [P, P, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p]),
         "cw_batch_witness_device": (c_int, [P, POINTER(c_void_p)]),
         "cw_batch_witness_strided": (c_int, [P, POINTER(c_void_p), POINTER(c_uint64)]),
         "cw_batch_stream": (c_void_p, [P]),

@@ -10,6 +10,7 @@ are the point of the GPU back end: one call computes the witnesses of many input
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, Iterable, List, Optional, Sequence, Union
 
 import numpy as np
@@ -116,9 +117,14 @@ class Circuit:
     """A lowered circuit (replaces Circom_Circuit + the compiled <name>.cpp)."""
 
     def __init__(self, src: Union[CircuitDesc, bytes, str], sanity_check: bool = True, host_only: bool = False,
-                 o0: bool = False):
-        flags = (0 if sanity_check else native.CW_FLAG_NO_ASSERTS) | (native.CW_FLAG_HOST_ONLY if host_only else 0) | \
-            (native.CW_FLAG_O0 if o0 else 0)
+                 o0: bool = False, flags: int = 0, compact: Optional[bool] = None):
+        """compact (default on; environment CW_COMPACT=0 turns it off): lower for the compact value store - bit runs in
+        a per-instance bit plane, temporaries sharing slots (CW_FLAG_COMPACT) - instead of one 32-byte slot per value"""
+        if compact is None:
+            compact = os.environ.get("CW_COMPACT", "1") != "0" and not (flags & native.CW_FLAG_COMPACT)
+        flags |= (0 if sanity_check else native.CW_FLAG_NO_ASSERTS) | (native.CW_FLAG_HOST_ONLY if host_only else 0) | \
+            (native.CW_FLAG_O0 if o0 else 0) | (native.CW_FLAG_COMPACT if compact else 0)
+        self.flags = flags
         self._h = ctypes.c_void_p()
         if isinstance(src, CircuitDesc):
             src = src.to_bytes()
@@ -169,6 +175,14 @@ class Circuit:
         out = np.zeros(self.n_witness, dtype=np.uint64)
         check(lib.cw_circuit_witness2signal(self._h, out.ctypes.data))
         return out
+
+    def pack_info(self, entries: bool = True):
+        """layout of the packed device->host records: ([words, plane words, extra-bit words, u64 entries, full
+        entries], per witness entry (class << 30) | index)"""
+        info = (ctypes.c_uint64 * 5)()
+        ent = np.zeros(self.n_witness, dtype=np.uint32) if entries else None
+        check(lib.cw_circuit_pack_info(self._h, info, ent.ctypes.data if entries else None))
+        return [int(x) for x in info], ent
 
     def write_dat(self, path: str) -> None:
         check(lib.cw_circuit_write_dat(self._h, path.encode()))
@@ -254,6 +268,30 @@ class Batch:
         check(lib.cw_batch_get_witness(self._h, out.ctypes.data))
         return out
 
+    def witness_async(self, out: np.ndarray) -> None:
+        """start the transfer on a helper thread (other batches may run meanwhile); finish with witness_wait()"""
+        self._async_out = out
+        check(lib.cw_batch_get_witness_async(self._h, out.ctypes.data))
+
+    def witness_wait(self) -> None:
+        check(lib.cw_batch_get_witness_wait(self._h))
+
+    def witness_packed(self) -> np.ndarray:
+        """uint32 [batch][words]: the packed records (see Circuit.pack_info)"""
+        info, _ = self.circuit.pack_info(entries=False)
+        out = np.empty((self.batch, info[0]), dtype=np.uint32)
+        check(lib.cw_batch_get_witness_packed(self._h, out.ctypes.data))
+        return out
+
+    def layout(self):
+        """(log2 instances per tile, threads per CTA, bytes of value store per instance)"""
+        bt, th, by = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint64()
+        check(lib.cw_batch_layout(self._h, ctypes.byref(bt), ctypes.byref(th), ctypes.byref(by)))
+        return bt.value, th.value, by.value
+
+    def expand_witness(self, first: int, count: int, device_ptr: int) -> None:
+        check(lib.cw_batch_expand_witness(self._h, first, count, ctypes.c_void_p(device_ptr)))
+
     def last_d2h_bytes(self) -> int:
         return int(lib.cw_batch_last_d2h_bytes(self._h))
 
@@ -304,9 +342,16 @@ class R1cs:
             lib.cw_r1cs_destroy(h)
 
     def check_batch(self, b: "Batch", device: int = 0):
-        """check the witnesses of a Batch where they lie (no copy)"""
-        ptr, stride = b.witness_strided()
-        return self.check(None, batch=b.batch, device=device, device_ptr=ptr, stride=stride)
+        """check the witnesses of a Batch where the tape left them (no copy, any layout)"""
+        ms = ctypes.c_float()
+        fb = np.zeros(b.batch, dtype=np.int64)
+        check(lib.cw_r1cs_check_batch(self._h, b._h, fb.ctypes.data, ctypes.byref(ms)))
+        return fb, ms.value
+
+    def eval_batch(self, b: "Batch", first: int, count: int, a_ptr: int, b_ptr: int, c_ptr: int) -> None:
+        """A.w, B.w, C.w of instances [first, first+count) into device arrays [count][n_constraints][4] uint64"""
+        check(lib.cw_r1cs_eval_batch(self._h, b._h, first, count, ctypes.c_void_p(a_ptr), ctypes.c_void_p(b_ptr),
+                                     ctypes.c_void_p(c_ptr)))
 
     def write(self, path: str, n_pub_out: Optional[int] = None, n_pub_in: Optional[int] = None,
               n_prv_in: Optional[int] = None) -> None:
@@ -336,8 +381,9 @@ class R1cs:
 class WitnessCalculator:
     """`builder(code, options)` of witness_calculator.js:1-106, for a circuit description."""
 
-    def __init__(self, circuit: Union[Circuit, CircuitDesc, bytes, str], sanity_check: bool = True, device: int = 0):
-        self.circuit = circuit if isinstance(circuit, Circuit) else Circuit(circuit, sanity_check=sanity_check)
+    def __init__(self, circuit: Union[Circuit, CircuitDesc, bytes, str], sanity_check: bool = True, device: int = 0,
+                 compact: Optional[bool] = None):
+        self.circuit = circuit if isinstance(circuit, Circuit) else Circuit(circuit, sanity_check=sanity_check, compact=compact)
         self.device = device
         self.prime = self.circuit.prime
         self.witnessSize = self.circuit.n_witness
@@ -393,4 +439,5 @@ class WitnessCalculator:
 
 def builder(code: Union[CircuitDesc, bytes, str], options: Optional[dict] = None) -> WitnessCalculator:
     options = options or {}
-    return WitnessCalculator(code, sanity_check=options.get("sanityCheck", True), device=options.get("device", 0))
+    return WitnessCalculator(code, sanity_check=options.get("sanityCheck", True), device=options.get("device", 0),
+                             compact=options.get("compact"))

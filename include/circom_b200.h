@@ -43,7 +43,9 @@ extern "C" {
 #define CW_FLAG_NO_ASSERTS 1u /* --sanity_check 0: drop `===` asserts (assert_bucket.rs:73) */
 #define CW_FLAG_HOST_ONLY 2u  /* lower the tape but do not touch a GPU (CPU-side tests of the lowering) */
 #define CW_FLAG_NO_PEEPHOLE 8u /* lower IR ops one to one (no bit-field / boolean-assert / shift fusions) */
-#define CW_FLAG_BITPLANE 16u   /* bits written by bit runs live in a packed per-instance bit plane (experimental) */
+#define CW_FLAG_BITPLANE 16u   /* bits written by bit runs live in a packed per-instance bit plane */
+#define CW_FLAG_REUSE 32u      /* values that are not witness entries share slots (allocated like registers) */
+#define CW_FLAG_COMPACT (CW_FLAG_BITPLANE | CW_FLAG_REUSE) /* the compact value store: what cw_batch_* runs best on */
 #define CW_FLAG_O0 4u         /* --O0: keep every signal in the witness and every `signal = signal` constraint */
 
 /* IR opcodes = OperatorType, compiler/src/intermediate_representation/compute_bucket.rs:7-34 */
@@ -78,8 +80,8 @@ typedef struct cw_stats {
     uint64_t n_conv_ops;     /* of which representation changes inserted by the lowering */
     uint64_t max_level_width;
     uint64_t n_slot_operands; /* operand reads of value slots in the tape */
-    uint64_t n_ring_operands; /* of which served from the shared-memory forwarding ring */
-    uint64_t reserved[1];
+    uint64_t n_bitwords;      /* 32-bit words of the per-instance bit plane (CW_FLAG_BITPLANE), else 0 */
+    uint64_t n_resident_slots;/* slots holding witness entries; slots beyond are reused temporaries (CW_FLAG_REUSE) */
 } cw_stats;
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -123,6 +125,10 @@ int cw_circuit_write_dat(const cw_circuit *c, const char *path);
 /* ---- batch: Circom_CalcWit for `batch` independent inputs on one GPU ------------------------ */
 int cw_batch_create(const cw_circuit *c, uint32_t batch, int device, cw_batch **out);
 void cw_batch_destroy(cw_batch *b);
+/* how the batch lays its values out on the device: log2 of the instances per tile (0: one instance per CTA, lanes
+ * along the ops of a level; 5: a warp per op over 32 instances), threads per CTA, bytes of value store per instance
+ * (32 * n_slots + 4 * n_bitwords).  Environment overrides: CW_BT_LOG2, CW_THREADS. */
+int cw_batch_layout(const cw_batch *b, uint32_t *bt_log2, uint32_t *threads, uint64_t *bytes_per_instance);
 /* Circom_CalcWit::setInputSignal(h, i, val) for one instance (calcwit.cpp:77-97); host staging */
 int cw_batch_set_input(cw_batch *b, uint32_t instance, uint64_t name_hash, uint32_t idx, const uint64_t limbs[4]);
 /* getRemaingInputsToBeSet (calcwit.hpp:50-52) for one instance */
@@ -137,11 +143,27 @@ int cw_batch_status(cw_batch *b, int32_t *status);
 /* getWitness(i) for all i and all instances, after Fr_toLongNormal (main.cpp:328-332):
  * out[batch][n_witness][4]; host pointer */
 int cw_batch_get_witness(cw_batch *b, uint64_t *out);
+/* the same on a helper thread, chunk by chunk (pack kernel + copy of chunk k+1 overlap the host-side expansion of
+ * chunk k); meanwhile the caller may stage and run OTHER batches, whose tapes then execute under the transfer.
+ * cw_batch_get_witness_wait returns the transfer's status; the batch must not be run again before it. */
+int cw_batch_get_witness_async(cw_batch *b, uint64_t *out);
+int cw_batch_get_witness_wait(cw_batch *b);
+/* the packed records themselves (out[batch][info[0]] uint32; layout: cw_circuit_pack_info) for consumers that do
+ * not need the reference's 32-byte rows */
+int cw_batch_get_witness_packed(cw_batch *b, uint32_t *out_words);
+/* packed-record layout: info = {words per instance, plane words, extra-bit words, u64 entries, full entries};
+ * entry[n_witness] = (class << 30) | index - class 0: bit `index` of the plane section, 1: bit `index` of the
+ * extra-bit section, 2: u64 entry `index`, 3: 32-byte entry `index`; the sections follow each other in that order */
+int cw_circuit_pack_info(const cw_circuit *c, uint64_t info[5], uint32_t *entry);
 /* bytes that crossed PCIe in the last cw_batch_get_witness (entries proven to be bits / 64-bit values travel
  * packed and are zero-extended on the host; CW_PACKED_D2H=0 disables) */
 uint64_t cw_batch_last_d2h_bytes(const cw_batch *b);
 /* device pointer of the same array (valid until the next run / destroy) */
 int cw_batch_witness_device(cw_batch *b, const uint64_t **dptr);
+/* dense rows of instances [first, first + count) into caller-provided device memory (32-byte aligned,
+ * count * n_witness * 32 bytes), asynchronously on the batch stream: the compact value store keeps the witness as
+ * resident slots + a bit plane and materialises the reference's layout only on request */
+int cw_batch_expand_witness(cw_batch *b, uint32_t first, uint32_t count, uint64_t *dst_device);
 /* zero-copy view: witness row i starts at dptr + i*stride_elems*4 uint64 (the tape writes witness entries into
  * the first n_witness slots of each instance's slot store; stride_elems = slots per instance) */
 int cw_batch_witness_strided(cw_batch *b, const uint64_t **dptr, uint64_t *stride_elems);
@@ -174,6 +196,15 @@ int cw_r1cs_check(cw_r1cs *r, const uint64_t *witness, int is_device_ptr, uint32
 /* same, for witness rows `stride_elems` 32-byte elements apart (stride_elems >= n_wires) */
 int cw_r1cs_check_strided(cw_r1cs *r, const uint64_t *witness, uint64_t stride_elems, int is_device_ptr, uint32_t batch,
                           int device, int64_t *first_bad, float *kernel_ms);
+
+/* the witnesses of a batch where the tape left them (any tile layout, bit plane, reused temporaries): nothing is
+ * copied or expanded, plane bits are read as bits, recomposition sums as words.  Runs on the batch's stream. */
+int cw_r1cs_check_batch(cw_r1cs *r, cw_batch *b, int64_t *first_bad, float *kernel_ms);
+/* A.w, B.w, C.w of every constraint for instances [first, first + count) of a batch, left in device memory
+ * ([count][n_constraints][4] uint64 each, canonical, 32-byte aligned) for the prover stage that follows witness
+ * generation; asynchronous on the batch stream (cw_batch_sync).  One-instance tile layouts only. */
+int cw_r1cs_eval_batch(cw_r1cs *r, cw_batch *b, uint32_t first, uint32_t count, uint64_t *a_dev, uint64_t *b_dev,
+                       uint64_t *c_dev);
 
 /* ---- field library, batched (parity tests of the device Fr_* equivalents, fr.hpp:28-70) ------ */
 /* r[i] = op(a[i], b[i], c[i]) for i < n on `device`; canonical in / canonical out; b, c may be NULL */

@@ -42,6 +42,10 @@ extern "C" {
 const char *hs_last_error() { return g_err.c_str(); }
 
 // returns 0 on success; witness[batch][W][4 u64]; status[batch] like cw_batch_status
+// Model of the device interpreter: all ops of a level read first, then all results of the level are written
+// (on the device the work items of a level run in any order between two barriers).  hs_check_levels proves that
+// no level reads a slot it also writes, which makes every device order equivalent to this one - also when
+// temporaries share slots (CW_FLAG_REUSE).
 int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inputs, uint32_t batch,
            uint64_t *witness, int32_t *status, uint64_t *stats /*8*/) {
     Tape t;
@@ -55,53 +59,47 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
     size_t n_ops = t.n_tape_ops();
     if (stats) {
         stats[0] = t.n_signals; stats[1] = n_ops; stats[2] = t.n_levels(); stats[3] = t.n_slots;
-        stats[4] = t.n_mul_ops; stats[5] = t.n_conv_ops; stats[6] = t.r1cs.n_constraints; stats[7] = t.n_ir_ops;
+        stats[4] = t.n_mul_ops; stats[5] = t.n_conv_ops; stats[6] = t.r1cs.n_constraints; stats[7] = t.n_bitwords;
     }
     std::vector<u32> slots((size_t)t.n_slots * 8);
     std::vector<u32> bitplane(t.n_bitwords);   // CW_FLAG_BITPLANE tapes: one word per bit run
-    std::vector<uint8_t> bit_written((size_t)t.n_bitwords * 32);
+    std::vector<uint8_t> bit_written((size_t)t.n_bitwords * 32), slot_written(t.n_slots);
     for (uint32_t inst = 0; inst < batch; ++inst) {
         std::fill(slots.begin(), slots.end(), 0xDEADBEEFu);  // poison: reads before writes show up
         std::fill(bitplane.begin(), bitplane.end(), 0xDEADBEEFu);
         std::fill(bit_written.begin(), bit_written.end(), 0);
+        std::fill(slot_written.begin(), slot_written.end(), 0);
         u32 one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
         memcpy(&slots[0], one, 32);
-        for (uint64_t k = 0; k < t.n_inputs; ++k)
+        slot_written[0] = 1;
+        for (uint64_t k = 0; k < t.n_inputs; ++k) {
             memcpy(&slots[(size_t)t.input_slot[k] * 8], inputs + ((size_t)inst * t.n_inputs + k) * 4, 32);
+            slot_written[t.input_slot[k]] = 1;
+        }
         uint32_t first_assert = 0xFFFFFFFFu;
         int err = 0;
-        // shared-memory forwarding ring of the device interpreter, emulated with the worst-case ordering: an
-        // operand flagged OPERAND_RING is read from the ring as it was when the level started AND re-checked
-        // after all deposits of the level (another work item of the level may run first on the device)
-        std::vector<u32> ring((size_t)CW_RING_SIZE * 8, 0xBADC0DEu);
-        std::vector<u32> ring_stamp(CW_RING_SIZE, 0xFFFFFFFFu);
-        bool ring_bad = false;
+        bool bad_read = false;
         auto operand = [&](u32 o, u32 *v) {
             if (o & OPERAND_CONST) { memcpy(v, t.consts[o & 0x7FFFFFFFu].v, 32); return; }
             if (o & OPERAND_BIT) {  // one bit of the bit plane
                 const u32 pos = o & OPERAND_BITPOS_MASK;
-                if ((pos >> 5) >= t.n_bitwords || !bit_written[pos]) ring_bad = true;   // (reported below)
+                if ((pos >> 5) >= t.n_bitwords || !bit_written[pos]) bad_read = true;   // (reported below)
                 memset(v, 0, 32);
                 v[0] = (pos >> 5) < t.n_bitwords ? (bitplane[pos >> 5] >> (pos & 31u)) & 1u : 0u;
                 return;
             }
             const u32 slot = o & OPERAND_SLOT_MASK;
-            if (o & OPERAND_RING) {
-                memcpy(v, &ring[(size_t)(slot & (CW_RING_SIZE - 1)) * 8], 32);
-                if (memcmp(v, &slots[(size_t)slot * 8], 32)) ring_bad = true;
-            } else {
-                memcpy(v, &slots[(size_t)slot * 8], 32);
-            }
+            if (slot >= t.n_slots || !slot_written[slot]) { bad_read = true; memset(v, 0, 32); return; }
+            memcpy(v, &slots[(size_t)slot * 8], 32);
         };
-        std::vector<u32> results;   // results of one level: {dst, 8 words, to_ring}
+        std::vector<u32> results;   // results of one level: {dst, 8 words}
         std::vector<u32> bit_results;  // bit-plane words of one level: {word index, value, run length}
         for (size_t l = 0; l < t.n_levels(); ++l) {
             results.clear();
             bit_results.clear();
-            auto put = [&](u32 dst, const u32 *r, bool to_ring) {
+            auto put = [&](u32 dst, const u32 *r) {
                 results.push_back(dst);
                 results.insert(results.end(), r, r + 8);
-                results.push_back(to_ring ? 1u : 0u);
             };
             for (size_t i = t.level_start[l]; i < t.level_start[l + 1]; ++i) {
                 const uint32_t *opw = &t.ops[i * 4];
@@ -116,7 +114,7 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
                     int e = 0;
                     vm_run(t.fn_code.data(), fi, regs.data(), (const u32 *)t.consts.data(), r, P, e);
                     if (e) err = 1;
-                    put(dst, r, true);
+                    put(dst, r);
                     continue;
                 }
                 operand(op[1], a);
@@ -136,7 +134,7 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
                     }
                     for (u32 j = 0; j < run; ++j) {
                         u256_bits(r, a, (k + j) | (1u << 16));
-                        put(dst + j, r, false);
+                        put(dst + j, r);
                     }
                     continue;
                 }
@@ -152,43 +150,26 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
                 } else {
                     fr_exec(op[0], r, a, b, op[3], P, err);
                 }
-                put(dst, r, true);
+                put(dst, r);
             }
-            for (size_t k = 0; k < results.size(); k += 10) {
+            for (size_t k = 0; k < results.size(); k += 9) {
+                if (results[k] >= t.n_slots) { g_err = "destination out of range"; return -5; }
                 memcpy(&slots[(size_t)results[k] * 8], &results[k + 1], 32);
-                if (!results[k + 9]) continue;
-                // two deposits of one level into the same ring index arrive in an unknown order on the device:
-                // the entry is garbage from then on
-                const u32 idx = results[k] & (CW_RING_SIZE - 1);
-                if (ring_stamp[idx] == (u32)l) std::fill(&ring[(size_t)idx * 8], &ring[(size_t)idx * 8 + 8], 0xBADC0DEu);
-                else memcpy(&ring[(size_t)idx * 8], &results[k + 1], 32);
-                ring_stamp[idx] = (u32)l;
+                slot_written[results[k]] = 1;
             }
             for (size_t k = 0; k < bit_results.size(); k += 3) {
                 if (bit_results[k] >= t.n_bitwords) { g_err = "bit-plane word out of range"; return -5; }
                 bitplane[bit_results[k]] = bit_results[k + 1];
                 for (u32 j = 0; j < bit_results[k + 2]; ++j) bit_written[(size_t)bit_results[k] * 32 + j] = 1;
             }
-            // the level's own deposits must not have displaced anything the level reads from the ring
-            for (size_t i = t.level_start[l]; i < t.level_start[l + 1]; ++i) {
-                const uint32_t *opw = &t.ops[i * 4];
-                if ((opw[0] & 0xFFu) == OP_CALL) continue;
-                for (int k = 1; k <= 3; ++k) {
-                    if ((opw[k] & OPERAND_CONST) || !(opw[k] & OPERAND_RING)) continue;
-                    if (k == 3 && (opw[0] & 0xFFu) != OP_SELECT) continue;
-                    const u32 slot = opw[k] & OPERAND_SLOT_MASK;
-                    if (memcmp(&ring[(size_t)(slot & (CW_RING_SIZE - 1)) * 8], &slots[(size_t)slot * 8], 32)) ring_bad = true;
-                }
-            }
         }
-        if (ring_bad) { g_err = "forwarding ring: a flagged operand was not (or no longer) in the ring"; return -4; }
         for (uint64_t w = 0; w < t.n_witness; ++w) {
             // without a bit plane witness_slot is the identity: slot w IS witness entry w
             u32 v[8];
             operand(t.witness_slot[w], v);
             memcpy(witness + ((size_t)inst * t.n_witness + w) * 4, v, 32);
         }
-        if (ring_bad) { g_err = "bit plane: a bit was read before it was written (or is out of range)"; return -6; }
+        if (bad_read) { g_err = "a slot or a bit of the bit plane was read before it was written (or is out of range)"; return -6; }
         status[inst] = err ? -1 : (first_assert == 0xFFFFFFFFu ? 0 : (int32_t)(first_assert + 1));
     }
     return 0;
@@ -207,7 +188,13 @@ long hs_witness2signal(const uint8_t *cb2c, size_t len, uint32_t flags, uint64_t
     return (long)t.witness2signal.size();
 }
 
-// level structure check: every operand slot of an op in level l is produced in a level < l
+// Structure of the lowered tape:
+//  * every operand was produced in an earlier level (and, with reused temporaries, the producer is the LATEST
+//    writer of that slot before the reader's level - there is no other notion of "the right value" in the tape,
+//    the value-level comparison against the evaluator in hs_run covers that);
+//  * no level reads a slot that the same level writes, and no level writes a slot twice: between two barriers
+//    the device runs the work items of a level in any order;
+//  * witness-resident slots [0, n_resident) are written exactly once; only temporaries are recycled.
 int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
     Tape t;
     try {
@@ -216,31 +203,86 @@ int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
         g_err = e.what();
         return -1;
     }
-    std::vector<uint32_t> lvl(t.n_slots, 0), oplvl(t.n_tape_ops(), 0), writes(t.n_slots, 0);
+    if (t.n_levels() && t.level_start[t.n_levels()] != t.n_tape_ops()) { g_err = "level table does not cover the tape"; return -2; }
+    const uint32_t n_res = (flags & 32u /* CW_FLAG_REUSE */) ? t.n_resident : t.n_slots;
+    std::vector<uint32_t> def(t.n_slots, 0), writes(t.n_slots, 0), read_stamp(t.n_slots, 0), write_stamp(t.n_slots, 0);
     std::vector<uint32_t> bitlvl(t.n_bitwords, 0), bitrun(t.n_bitwords, 0);
-    for (size_t l = 0; l < t.n_levels(); ++l)
+    def[0] = 0xFFFFFFFFu;  // "written before the tape starts"
+    writes[0]++;
+    for (uint64_t k = 0; k < t.n_inputs; ++k) {
+        if (t.input_slot[k] >= n_res) { g_err = "main input outside the resident slots"; return -8; }
+        def[t.input_slot[k]] = 0xFFFFFFFFu;
+        writes[t.input_slot[k]]++;
+    }
+    auto is_assert = [](uint32_t opc) { return opc == OP_ASSERT || opc == OP_ASSERT_EQ || opc == OP_ASSERT_BOOL || opc == OP_ASSERT_FITS; };
+    for (size_t l = 0; l < t.n_levels(); ++l) {
+        const uint32_t L = (uint32_t)l + 1;
+        auto read = [&](uint32_t o) -> int {
+            if (o & OPERAND_CONST) {
+                if ((o & 0x7FFFFFFFu) >= t.consts.size()) { g_err = "constant index out of range"; return -3; }
+                return 0;
+            }
+            if (o & OPERAND_BIT) {
+                const uint32_t pos = o & OPERAND_BITPOS_MASK;
+                if ((pos >> 5) >= t.n_bitwords || (pos & 31u) >= bitrun[pos >> 5] || !bitlvl[pos >> 5]) {
+                    g_err = "bit operand out of range or not produced in an earlier level"; return -13;
+                }
+                return 0;
+            }
+            if (o & ~OPERAND_SLOT_MASK) { g_err = "unknown operand flag"; return -4; }
+            if (o >= t.n_slots) { g_err = "slot out of range"; return -4; }
+            if (!def[o]) { g_err = "operand not produced in an earlier level"; return -5; }
+            read_stamp[o] = L;
+            return 0;
+        };
+        // reads of the level (definitions so far are all from earlier levels)
         for (uint32_t i = t.level_start[l]; i < t.level_start[l + 1]; ++i) {
-            oplvl[i] = (uint32_t)l + 1;
-            uint32_t opc = t.ops[(size_t)i * 4] & 0xFFu, dst = t.ops[(size_t)i * 4] >> 8;
-            bool is_assert = opc == OP_ASSERT || opc == OP_ASSERT_EQ || opc == OP_ASSERT_BOOL || opc == OP_ASSERT_FITS;
-            if (is_assert) continue;
-            uint32_t run = opc == OP_BITS ? (t.ops[(size_t)i * 4 + 3] >> 24) + 1u : 1u;
+            const uint32_t *opw = &t.ops[(size_t)i * 4];
+            const uint32_t opc = opw[0] & 0xFFu;
+            int rc;
+            if (opc == OP_CALL) {
+                const uint32_t *ct = &t.call_tab[opw[1]];
+                for (uint32_t k = 0; k < ct[1]; ++k)
+                    if ((rc = read(ct[2 + k]))) return rc;
+                continue;
+            }
+            const bool c_imm = is_assert(opc) || opc == OP_BITS || opc == OP_BITSIP;
+            for (int k = 1; k <= 3; ++k) {
+                if (k == 3 && c_imm) break;
+                if ((rc = read(opw[k]))) return rc;
+            }
+        }
+        // writes of the level
+        for (uint32_t i = t.level_start[l]; i < t.level_start[l + 1]; ++i) {
+            const uint32_t *opw = &t.ops[(size_t)i * 4];
+            const uint32_t opc = opw[0] & 0xFFu, dst = opw[0] >> 8;
+            if (is_assert(opc)) continue;
+            const uint32_t run = opc == OP_BITS ? (opw[3] >> 24) + 1u : 1u;
             if (t.n_bitwords && run > 1) {  // bit plane: the run is word `dst`
                 if (dst >= t.n_bitwords) { g_err = "bit-plane word out of range"; return -11; }
-                if (bitlvl[dst]) { g_err = "bit-plane word written twice"; return -12; }
-                bitlvl[dst] = (uint32_t)l + 1;
+                if (bitrun[dst]) { g_err = "bit-plane word written twice"; return -12; }
                 bitrun[dst] = run;
                 continue;
             }
             for (uint32_t j = 0; j < run; ++j) {
-                if (dst + j >= t.n_slots) { g_err = "destination out of range"; return -6; }
-                if (++writes[dst + j] > 1) { g_err = "slot written twice"; return -7; }
-                lvl[dst + j] = (uint32_t)l + 1;
+                const uint32_t s = dst + j;
+                if (s >= t.n_slots) { g_err = "destination out of range"; return -6; }
+                if (read_stamp[s] == L) { g_err = "a level writes a slot that the same level reads"; return -14; }
+                if (write_stamp[s] == L) { g_err = "a level writes a slot twice"; return -15; }
+                write_stamp[s] = L;
+                if (++writes[s] > 1 && s < n_res) { g_err = "slot written twice"; return -7; }
             }
         }
-    writes[0]++;
-    for (uint64_t k = 0; k < t.n_inputs; ++k) writes[t.input_slot[k]]++;
-    {   // every witness entry is produced exactly once and no two entries share a place
+        for (uint32_t i = t.level_start[l]; i < t.level_start[l + 1]; ++i) {  // ... become visible after the barrier
+            const uint32_t *opw = &t.ops[(size_t)i * 4];
+            const uint32_t opc = opw[0] & 0xFFu, dst = opw[0] >> 8;
+            if (is_assert(opc)) continue;
+            const uint32_t run = opc == OP_BITS ? (opw[3] >> 24) + 1u : 1u;
+            if (t.n_bitwords && run > 1) { bitlvl[dst] = L; continue; }
+            for (uint32_t j = 0; j < run; ++j) def[dst + j] = L;
+        }
+    }
+    {   // every witness entry is produced exactly once, in a resident place, and no two entries share a place
         std::vector<uint8_t> seen_slot(t.n_slots, 0), seen_bit((size_t)t.n_bitwords * 32, 0);
         for (uint64_t w = 0; w < t.n_witness; ++w) {
             const uint32_t ws = t.witness_slot[w];
@@ -250,44 +292,8 @@ int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
                     g_err = "witness entry maps to a bad bit-plane position"; return -8;
                 }
             } else {
-                if (ws >= t.n_slots || writes[ws] != 1 || seen_slot[ws]++) { g_err = "witness slot not written exactly once"; return -8; }
+                if (ws >= n_res || writes[ws] != 1 || seen_slot[ws]++) { g_err = "witness slot not written exactly once"; return -8; }
             }
-        }
-    }
-    if (t.n_levels() && t.level_start[t.n_levels()] != t.n_tape_ops()) { g_err = "level table does not cover the tape"; return -2; }
-    for (size_t i = 0; i < t.n_tape_ops(); ++i) {
-        const uint32_t *opw = &t.ops[i * 4];
-        uint32_t op[4] = {opw[0] & 0xFFu, opw[1], opw[2], opw[3]};
-        if (op[0] == OP_CALL) {
-            const uint32_t *ct = &t.call_tab[op[1]];
-            for (uint32_t k = 0; k < ct[1]; ++k) {
-                uint32_t a = ct[2 + k];
-                if (a & OPERAND_CONST) continue;
-                if (a >= t.n_slots || lvl[a] >= oplvl[i]) { g_err = "call argument not produced in an earlier level"; return -9; }
-            }
-            continue;
-        }
-        bool c_imm = op[0] == OP_ASSERT || op[0] == OP_ASSERT_EQ || op[0] == OP_ASSERT_BOOL || op[0] == OP_BITS || op[0] == OP_BITSIP || op[0] == OP_ASSERT_FITS;
-        for (int k = 1; k <= 3; ++k) {
-            if (k == 3 && c_imm) break;
-            if (!(op[k] & OPERAND_CONST) && (op[k] & OPERAND_BIT)) {
-                const uint32_t pos = op[k] & OPERAND_BITPOS_MASK;
-                if ((pos >> 5) >= t.n_bitwords || (pos & 31u) >= bitrun[pos >> 5]) { g_err = "bit operand out of range"; return -13; }
-                if (bitlvl[pos >> 5] >= oplvl[i]) { g_err = "bit operand not produced in an earlier level"; return -5; }
-                continue;
-            }
-            if (!(op[k] & OPERAND_CONST)) {
-                if ((op[k] & OPERAND_RING) && (op[k] & OPERAND_SLOT_MASK) < t.n_slots && !lvl[op[k] & OPERAND_SLOT_MASK]) {
-                    g_err = "ring flag on a slot the tape does not write"; return -10;
-                }
-                op[k] &= OPERAND_SLOT_MASK;
-            }
-            if (op[k] & OPERAND_CONST) {
-                if ((op[k] & 0x7FFFFFFFu) >= t.consts.size()) { g_err = "constant index out of range"; return -3; }
-                continue;
-            }
-            if (op[k] >= t.n_slots) { g_err = "slot out of range"; return -4; }
-            if (lvl[op[k]] >= oplvl[i]) { g_err = "operand not produced in an earlier level"; return -5; }
         }
     }
     return 0;

@@ -66,17 +66,16 @@ def test_oracle_and_host_build_reproduce_reference_wtns(name):
     arr = flat_inputs(d, ins)
     wit, st = c_oracle.COracle(d.to_bytes()).run(arr)
     assert not st.any()
-    hw, hst, _, w2s = hostsim_run(d, ins, flags=4)   # CW_FLAG_O0: every signal is a witness entry, as in the .dat
-    assert not hst.any() and w2s.tolist() == list(range(d.total_signals))
     for i, raw in enumerate(raws):
         assert wtns_frame(d.q, wit[i]) == raw, (name, i, "C oracle")
-        assert wtns_frame(d.q, hw[i]) == raw, (name, i, "device code built for the CPU")
+    for flags in (4, 4 | 48):   # CW_FLAG_O0: every signal is a witness entry, as in the .dat; + the compact value store
+        hw, hst, _, w2s = hostsim_run(d, ins, flags=flags)
+        assert not hst.any() and w2s.tolist() == list(range(d.total_signals))
+        for i, raw in enumerate(raws):
+            assert wtns_frame(d.q, hw[i]) == raw, (name, i, "device code built for the CPU", flags)
 
 
-# The two SHA-256 fixtures were generated after the round's last GPU session: on the GPU those circuits are pinned
-# through tests/test_gpu_circuits.py (bit-exact against the oracle, which the fixtures pin here, and hashlib).
-GPU_NAMES = [n for n in NAMES if not n.startswith("sha256") and n != "ecdsa_scale_8x132"]   # (8x132 on the GPU:
-# tests/test_gpu_circuits.py compares with the reference calculator itself)
+GPU_NAMES = NAMES   # every fixture, the SHA-256 circuits and the 1.2 M-constraint one included
 
 
 @pytest.mark.gpu

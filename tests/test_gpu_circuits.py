@@ -18,8 +18,8 @@ from tests.util import flat_inputs
 pytestmark = pytest.mark.gpu
 
 
-def _run(d, ins, check_r1cs=True):
-    c = Circuit(d)
+def _run(d, ins, check_r1cs=True, compact=None):
+    c = Circuit(d, compact=compact)
     b = Batch(c, len(ins))
     arr = flat_inputs(d, ins)
     b.set_inputs(arr)
@@ -27,7 +27,10 @@ def _run(d, ins, check_r1cs=True):
     assert not b.status().any()
     wit = b.witness()
     if check_r1cs:
-        fb, _ = R1cs(c).check(None, batch=len(ins), device_ptr=b.witness_device_ptr())
+        r = R1cs(c)
+        fb, _ = r.check_batch(b)                     # where the tape left the values
+        assert (fb == -1).all()
+        fb, _ = r.check(None, batch=len(ins), device_ptr=b.witness_device_ptr())   # the reference's dense rows
         assert (fb == -1).all()
     return c, wit, arr, c.witness2signal().astype(np.int64)
 
@@ -67,20 +70,53 @@ def test_sha256compression_batch_vs_oracle_and_hashlib():
     assert not st.any() and (ow[:, w2s] == wit[:8]).all()
 
 
-def test_forwarding_ring_build_matches(monkeypatch):
-    """The opt-in shared-memory forwarding ring (CW_RING=1) must not change a single bit."""
+@pytest.mark.parametrize("bt", ["0", "3", "5"])
+def test_compact_store_matches_plain_store(bt, monkeypatch):
+    """bit plane + shared temporaries (the default) against one 32-byte slot per value: not a single bit differs,
+    for lanes along ops and for a warp per op"""
     d = CircuitDesc("bn128")
     d.set_main(C.ecdsa_scale(d, 2, 5))
     rng = np.random.default_rng(9)
     ins = [{"a": [int(x) for x in rng.integers(0, 2**63, 8)], "b": [int(x) for x in rng.integers(0, 2**63, 8)]}
-           for _ in range(40)]
-    monkeypatch.setenv("CW_RING", "0")
-    c0, wit0, arr, w2s = _run(d, ins)
-    monkeypatch.setenv("CW_RING", "1")
-    c1, wit1, _, _ = _run(d, ins)
+           for _ in range(70)]
+    monkeypatch.setenv("CW_BT_LOG2", bt)
+    c0, wit0, arr, w2s = _run(d, ins, compact=False)
+    c1, wit1, _, _ = _run(d, ins, compact=True)
     assert (wit0 == wit1).all()
+    assert c1.stats["n_slots"] * 8 < c0.stats["n_slots"] and c1.stats["n_bitwords"] > 0
     ow, st = COracle(d.to_bytes()).run(arr[:8])
     assert not st.any() and (ow[:, w2s] == wit1[:8]).all()
+
+
+def test_overlapped_transfers_of_two_batches():
+    """cw_batch_get_witness_async: the witnesses of batch A are packed, copied and expanded on a helper thread while
+    batch B executes; both results equal the synchronous transfer"""
+    d = CircuitDesc("bn128")
+    d.set_main(C.ecdsa_scale(d, 2, 5))
+    rng = np.random.default_rng(10)
+    c = Circuit(d)
+    n = 300
+    arrs = []
+    for k in range(2):
+        ins = [{"a": [int(x) for x in rng.integers(0, 2**63, 8)], "b": [int(x) for x in rng.integers(0, 2**63, 8)]}
+               for _ in range(n)]
+        arrs.append(flat_inputs(d, ins))
+    A, B = Batch(c, n), Batch(c, n)
+    outA = np.empty((n, c.n_witness, 4), dtype=np.uint64)
+    outB = np.empty((n, c.n_witness, 4), dtype=np.uint64)
+    for rep in range(2):
+        A.set_inputs(arrs[0])
+        A.run(sync=False)
+        A.witness_async(outA)
+        B.set_inputs(arrs[1])
+        B.run(sync=False)
+        B.witness_async(outB)
+        A.witness_wait()
+        B.witness_wait()
+    assert (outA == A.witness()).all() and (outB == B.witness()).all()
+    ow, st = COracle(d.to_bytes()).run(arrs[1][:4])
+    w2s = c.witness2signal().astype(np.int64)
+    assert (ow[:, w2s] == outB[:4]).all()
 
 
 def test_sha256_512_bls12381_with_r1cs():
@@ -126,8 +162,8 @@ def test_wtns_bytes_equal_reference_runtime(name, tmp_path):
     from oracle import build_calcs
     from tests.test_oracle_c import input_json
     calc = build_calcs.calc_path(name)
-    if not (os.path.exists(calc) and os.path.exists(calc + ".dat")):
-        pytest.skip("reference calculator not prebuilt")
+    assert os.path.exists(calc) and os.path.exists(calc + ".dat"), \
+        "reference calculator %s missing: oracle/_ref must travel with the snapshot (python -m oracle.build_calcs)" % calc
     d = build_calcs.make_desc(name)
     rng = np.random.default_rng(21)
     n_in = d.main.n_in
@@ -168,8 +204,7 @@ def test_cli_matches_reference_calculator(tmp_path):
     from oracle import build_calcs
     from tests.test_oracle_c import input_json
     calc = build_calcs.calc_path("all_ops")
-    if not os.path.exists(calc):
-        pytest.skip("reference calculator not prebuilt")
+    assert os.path.exists(calc), "reference calculator missing: oracle/_ref must travel with the snapshot"
     d = build_calcs.make_desc("all_ops")
     cb = str(tmp_path / "all_ops.cb2c")
     d.save(cb)

@@ -51,13 +51,14 @@ def test_device_field_ops(prime):
 @pytest.mark.parametrize("prime", ["bn128", "bls12381"])
 @pytest.mark.parametrize("name", sorted(CIRCUITS))
 @pytest.mark.parametrize("batch", [1, 37])
-def test_circuit_witness_matches_oracle(prime, name, batch):
+@pytest.mark.parametrize("compact", [False, True])
+def test_circuit_witness_matches_oracle(prime, name, batch, compact):
     mk, gen = CIRCUITS[name]
     d = CircuitDesc(prime)
     d.set_main(mk(d))
     rng = random.Random(zlib.crc32((prime + name).encode()) + batch)
     ins = [gen(rng, d.q) for _ in range(batch)]
-    wc = builder(d)
+    wc = builder(d, {"compact": compact})
     wit = wc.calculate_witness_batch(ins)
     w2s = wc.circuit.witness2signal().astype(np.int64)
     for i, inp in enumerate(ins):
@@ -68,20 +69,54 @@ def test_circuit_witness_matches_oracle(prime, name, batch):
     assert (fb == -1).all()
 
 
-@pytest.mark.parametrize("bt", ["0", "2", "5"])
-def test_tile_layouts_agree(bt, monkeypatch):
-    """every instance-tile width of the slot layout gives the same witnesses"""
+@pytest.mark.parametrize("bt", ["0", "2", "3", "5"])
+@pytest.mark.parametrize("compact", [False, True])
+@pytest.mark.parametrize("name", ["all_ops", "less_than8", "int_div32"])
+def test_tile_layouts_agree(bt, compact, name, monkeypatch):
+    """every instance-tile width of the value store (lanes along ops ... a warp per op over 32 instances), with and
+    without the compact store, gives the same witnesses through every way out: packed transfer, dense copy, dense
+    device rows, .wtns; and the R1CS check reads every layout in place"""
     monkeypatch.setenv("CW_BT_LOG2", bt)
+    mk, gen = CIRCUITS[name]
     d = CircuitDesc("bn128")
-    d.set_main(C.all_ops(d))
+    d.set_main(mk(d))
     rng = random.Random(5)
-    ins = [CIRCUITS["all_ops"][1](rng, d.q) for _ in range(45)]
-    wc = builder(d)
-    wit = wc.calculate_witness_batch(ins)
-    w2s = wc.circuit.witness2signal().astype(np.int64)
-    for i, inp in enumerate(ins):
-        exp = evaluate(d, inp)
+    ins = [gen(rng, d.q) for _ in range(45)]
+    c = Circuit(d, compact=compact)
+    b = Batch(c, len(ins))
+    assert b.layout()[0] == int(bt)
+    b.set_inputs(flat_inputs(d, ins))
+    b.run()
+    assert not b.status().any()
+    wit = b.witness()
+    w2s = c.witness2signal().astype(np.int64)
+    expected = [evaluate(d, inp) for inp in ins]
+    for i, exp in enumerate(expected):
         assert limbs_to_ints(wit[i]) == [exp[k] for k in w2s]
+    monkeypatch.setenv("CW_PACKED_D2H", "0")
+    assert (b.witness() == wit).all()
+    monkeypatch.delenv("CW_PACKED_D2H")
+    r = R1cs(c)
+    fb, _ = r.check_batch(b)
+    assert (fb == -1).all()
+    fb, _ = r.check(None, batch=len(ins), device_ptr=b.witness_device_ptr())
+    assert (fb == -1).all()
+    assert b.wtns_bytes(7)[76:] == wit[7].tobytes()
+    # the packed records themselves, decoded with the published layout
+    info, ent = c.pack_info()
+    rec = b.witness_packed()
+    off = [0, info[1], info[1] + info[2], info[1] + info[2] + 2 * info[3]]
+    for i in (0, 44):
+        got = []
+        for e in ent.tolist():
+            cls, idx = e >> 30, e & 0x3FFFFFFF
+            if cls <= 1:
+                got.append((int(rec[i, off[cls] + (idx >> 5)]) >> (idx & 31)) & 1)
+            elif cls == 2:
+                got.append(int(rec[i, off[2] + 2 * idx]) | (int(rec[i, off[2] + 2 * idx + 1]) << 32))
+            else:
+                got.append(sum(int(rec[i, off[3] + 8 * idx + k]) << (32 * k) for k in range(8)))
+        assert got == [expected[i][k] for k in w2s]
 
 
 def test_reference_surface_single_input():
@@ -143,12 +178,13 @@ def test_assert_and_r1cs_violation_detected():
     assert fb2.tolist() == [-1, 0, -1]
 
 
-def test_r1cs_check_reads_witness_in_place():
-    """the tape writes witness entries into the first slots of each instance: the R1CS check and the
-    host copy read them there (strided), the dense device copy is made only on request"""
+@pytest.mark.parametrize("compact", [False, True])
+def test_r1cs_check_reads_witness_in_place(compact):
+    """the R1CS check reads the witness where the tape left it; the reference's dense rows exist on the device only
+    on request (zero-copy view of the slot store when witness entry i IS slot i, an expansion otherwise)"""
     d = CircuitDesc("bn128")
     d.set_main(C.less_than(d, 16))
-    c = Circuit(d)
+    c = Circuit(d, compact=compact)
     rng = random.Random(8)
     ins = [{"in": [rng.randrange(65536), rng.randrange(65536)]} for _ in range(50)]
     b = Batch(c, len(ins))
@@ -157,11 +193,15 @@ def test_r1cs_check_reads_witness_in_place():
     r = R1cs(c)
     fb1, _ = r.check_batch(b)
     ptr, stride = b.witness_strided()
-    assert stride == c.stats["n_slots"] and stride >= c.n_witness
+    if compact:
+        assert stride == c.n_witness and c.stats["n_bitwords"] > 0 and c.stats["n_slots"] < c.n_witness
+    else:
+        assert stride == c.stats["n_slots"] and stride >= c.n_witness
+    fb4, _ = r.check(None, batch=len(ins), device_ptr=ptr, stride=stride)
     wit = b.witness()
     fb2, _ = r.check(wit)
     fb3, _ = r.check(None, batch=len(ins), device_ptr=b.witness_device_ptr())
-    assert (fb1 == -1).all() and (fb2 == -1).all() and (fb3 == -1).all()
+    assert (fb1 == -1).all() and (fb2 == -1).all() and (fb3 == -1).all() and (fb4 == -1).all()
     w2s = c.witness2signal().astype(np.int64)
     for i, inp in enumerate(ins):
         exp = evaluate(d, inp)
@@ -193,9 +233,10 @@ def test_r1cs_first_violated_row_matches_oracle():
     assert (exp >= 0).all() and fb.tolist() == exp.tolist()
 
 
-def test_r1cs_lane_group_kernel_matches(monkeypatch):
-    """the opt-in kernel that checks long rows with 8 lanes per (row, instance) (CW_R1CS_SPLIT=1) reports the
-    same first violated row as the default kernel and the oracle"""
+def test_r1cs_long_rows_and_large_shifts_match_oracle():
+    """the 65-term recomposition row of Num2Bits(64) with single entries corrupted, and rows whose coefficients are
+    2^200 ... 2^252 on 32-bit wire values at the edge of the no-reduction fast path (x * 2^k >= q must take the
+    Montgomery product): the first violated row equals the oracle's"""
     from oracle.c_oracle import COracle
     d = CircuitDesc("bn128")
     d.set_main(C.num2bits(d, 64))     # one 65-term recomposition row, 64 boolean rows
@@ -211,13 +252,105 @@ def test_r1cs_lane_group_kernel_matches(monkeypatch):
         cases.append(bad)
     batch = np.concatenate(cases, axis=0)
     exp = COracle(d.to_bytes()).r1cs_check(batch)
-    r = R1cs(c)
-    monkeypatch.setenv("CW_R1CS_SPLIT", "0")
-    fb0, _ = r.check(batch)
-    monkeypatch.setenv("CW_R1CS_SPLIT", "1")
-    fb1, _ = r.check(batch)
+    fb0, _ = R1cs(c).check(batch)
     assert exp[0] == -1 and (exp[1:] >= 0).all()
-    assert fb0.tolist() == exp.tolist() and fb1.tolist() == exp.tolist()
+    assert fb0.tolist() == exp.tolist()
+    for prime in ("bn128", "bls12381"):
+        d = CircuitDesc(prime)
+        shifts = [200, 220, 221, 222, 223, 224, 230, 252]
+
+        def build(t):
+            x = t.input("x")
+            o = t.output("o", len(shifts))
+            for k, sh in enumerate(shifts):
+                t.assign_constrained(o[k], x * (1 << sh))          # linear row: coefficient 2^sh
+        d.set_main(d.template("BigShift", (), build))
+        c = Circuit(d)
+        xs = [0xC19139CB, 0xC19139CC, 0xFFFFFFFF, 0x73EDA753, 0x73EDA754, 1, 0, 0x80000000, 2**64 - 1, d.q - 1]
+        ins = [{"x": x} for x in xs]
+        b = Batch(c, len(ins))
+        b.set_inputs(flat_inputs(d, ins))
+        b.run()
+        wit = b.witness()
+        orc = COracle(d.to_bytes())
+        assert (orc.r1cs_check(wit) == -1).all()
+        r = R1cs(c)
+        assert (r.check(wit)[0] == -1).all() and (r.check_batch(b)[0] == -1).all()
+        bad = wit.copy()
+        bad[:, 1, 0] ^= np.uint64(1)      # o[0] off by one in every instance
+        assert r.check(bad)[0].tolist() == orc.r1cs_check(bad).tolist()
+
+
+def test_r1cs_check_on_the_compact_store_finds_violations():
+    """violations inside recomposition runs read as bit-plane words: bits are extracted from `x`, the recomposition is
+    constrained against another input `y`; instances with y != x violate that row (and fail the `===` assert)"""
+    from oracle.c_oracle import COracle
+    d = CircuitDesc("bn128")
+
+    def build(t):
+        x, y = t.input("x"), t.input("y")
+        out = t.output("out", 40)
+        lc = t.const(0)
+        for k in range(40):
+            t.assign(out[k], (x >> k) & 1)
+            t.constrain(out[k] * (out[k] - 1), 0)
+            lc = lc + out[k] * (1 << k)
+        t.constrain(lc, y)
+    d.set_main(d.template("Recompose", (), build))
+    ins = [{"x": 0xABCDE12345, "y": 0xABCDE12345}, {"x": 0xABCDE12345, "y": 0xABCDE12344}, {"x": 5, "y": 5}, {"x": 7, "y": 2**39 + 7}]
+    orc = COracle(d.to_bytes())
+    for compact in (False, True):
+        for bt in ("0", "5"):
+            import os
+            os.environ["CW_BT_LOG2"] = bt
+            try:
+                c = Circuit(d, compact=compact)
+                b = Batch(c, len(ins))
+                b.set_inputs(flat_inputs(d, ins))
+                b.run()
+                st = b.status()
+                assert (st != 0).tolist() == [False, True, False, True]
+                wit = b.witness()
+                exp = orc.r1cs_check(wit)
+                assert (exp >= 0).tolist() == [False, True, False, True]
+                r = R1cs(c)
+                assert r.check_batch(b)[0].tolist() == exp.tolist()
+                assert r.check(wit)[0].tolist() == exp.tolist()
+            finally:
+                del os.environ["CW_BT_LOG2"]
+
+
+def test_r1cs_eval_leaves_the_products_on_the_device():
+    """A.w, B.w, C.w of every row in device memory (the hand-off to a prover): equal to python-int evaluation of the
+    constraint system on the witness"""
+    import torch
+    d = CircuitDesc("bn128")
+    d.set_main(C.less_than(d, 8))
+    c = Circuit(d)
+    rng = random.Random(3)
+    ins = [{"in": [rng.randrange(256), rng.randrange(256)]} for _ in range(6)]
+    b = Batch(c, len(ins))
+    b.set_inputs(flat_inputs(d, ins))
+    b.run()
+    r = R1cs(c)
+    m = r.n_constraints
+    first, count = 2, 3
+    outs = [torch.zeros((count, m, 4), dtype=torch.int64, device="cuda") for _ in range(3)]
+    r.eval_batch(b, first, count, *[o.data_ptr() for o in outs])
+    b.sync()
+    wit = b.witness()
+    import tempfile, os
+    p = os.path.join(tempfile.mkdtemp(), "c.r1cs")
+    r.write(p)
+    from tests.test_formats_cpu import parse_r1cs
+    cons = parse_r1cs(open(p, "rb").read())["cons"]
+    q = d.q
+    for i in range(count):
+        w = limbs_to_ints(wit[first + i])
+        for k, o in enumerate(outs):
+            got = limbs_to_ints(o[i].cpu().numpy().view(np.uint64))
+            want = [sum(cf * w[wire] for wire, cf in row[k].items()) % q for row in cons]
+            assert got == want
 
 
 def test_packed_device_to_host_transfer_equals_plain_copy(monkeypatch):
@@ -225,7 +358,7 @@ def test_packed_device_to_host_transfer_equals_plain_copy(monkeypatch):
     host: the host array must equal the plain pitched copy, with fewer bytes transferred"""
     d = CircuitDesc("bn128")
     d.set_main(C.ecdsa_scale(d, 2, 3))
-    c = Circuit(d)
+    c = Circuit(d, compact=False)
     rng = random.Random(2)
     ins = [{"a": [rng.randrange(2**64) for _ in range(8)], "b": [rng.randrange(2**64) for _ in range(8)]} for _ in range(37)]
     b = Batch(c, len(ins))

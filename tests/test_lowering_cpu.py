@@ -38,7 +38,7 @@ def test_tape_matches_oracle(prime, name):
     import zlib
     rng = random.Random(zlib.crc32((prime + name).encode()))
     ins = [gen(rng, d.q) for _ in range(24)]
-    for flags in (0, 4, 16):  # default (signal = signal eliminated), CW_FLAG_O0, CW_FLAG_BITPLANE
+    for flags in (0, 4, 16, 32, 48, 52):  # default, CW_FLAG_O0, CW_FLAG_BITPLANE, CW_FLAG_REUSE, both (COMPACT), COMPACT + O0
         wit, st, stats, w2s = hostsim_run(d, ins, flags=flags)
         if flags == 4:
             assert w2s.tolist() == list(range(d.total_signals))
@@ -51,11 +51,11 @@ def test_tape_matches_oracle(prime, name):
         assert not st.any()
 
 
-def test_wide_tapes_and_forwarding_ring():
-    """Tapes with levels wider than the shared-memory forwarding ring (512 entries): the simulator replays the
-    ring with the device's worst-case deposit order and fails if an operand the lowering flagged as
-    ring-resident is not there.  Known answers: hashlib / python-int secp256k1 arithmetic."""
+def test_wide_tapes_and_compact_layouts():
     import hashlib
+    """Tapes with wide levels under the compact value store: bit runs in the bit plane (CW_FLAG_BITPLANE) and
+    temporaries sharing slots (CW_FLAG_REUSE).  The simulator checks that no level reads what it writes (the device
+    runs a level's work items in any order) and compares every value.  Known answers: python-int secp256k1 arithmetic."""
     from circom_b200.circuits.bigint import ecdsa_scale_expected
     from circom_b200.witness_calculator import Circuit
     rng = random.Random(77)
@@ -70,8 +70,14 @@ def test_wide_tapes_and_forwarding_ring():
     wit_bp, st_bp, stats_bp, w2s_bp = hostsim_run(d, [{"a": a, "b": b}], flags=16)
     assert not st_bp.any() and (wit_bp == wit).all() and (w2s_bp == w2s).all()
     assert int(stats_bp[3]) < int(stats[3]) // 2
+    # + slot reuse: the value store shrinks by another large factor, same witness
+    wit_c, st_c, stats_c, w2s_c = hostsim_run(d, [{"a": a, "b": b}], flags=48)
+    assert not st_c.any() and (wit_c == wit).all() and (w2s_c == w2s).all()
+    assert int(stats_c[3]) < int(stats_bp[3]) // 2 and int(stats_c[7]) > 0
     stc = Circuit(d, host_only=True).stats
-    assert 0 < stc["n_ring_operands"] <= stc["n_slot_operands"]
+    assert stc["n_bitwords"] == 0 and stc["n_resident_slots"] == stc["n_witness"]
+    stcc = Circuit(d, host_only=True, flags=48).stats
+    assert stcc["n_bitwords"] == int(stats_c[7]) and stcc["n_resident_slots"] < stcc["n_slots"] < stc["n_slots"] // 4
     # census of the slots by proven width: every slot is counted once, the range-checked bits dominate
     from circom_b200 import native
     cc = Circuit(d, host_only=True)

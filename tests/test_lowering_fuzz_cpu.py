@@ -13,7 +13,7 @@ from circom_b200 import circuits as C
 from oracle.ir_eval import evaluate, check_r1cs
 from tests.util import hostsim_run, limbs_to_ints, edge_values
 
-CW_FLAG_O0, CW_FLAG_NO_PEEPHOLE, CW_FLAG_BITPLANE = 4, 8, 16
+CW_FLAG_O0, CW_FLAG_NO_PEEPHOLE, CW_FLAG_BITPLANE, CW_FLAG_REUSE, CW_FLAG_COMPACT = 4, 8, 16, 32, 48
 
 
 def random_template(d, rng, n_in, n_vals, with_components):
@@ -118,7 +118,8 @@ def test_random_circuits_match_the_evaluator(prime, seed):
     expected = [evaluate(d, inp) for inp in ins]
     for e in expected:
         assert check_r1cs(d, e) == 0
-    for flags in (0, CW_FLAG_NO_PEEPHOLE, CW_FLAG_O0, CW_FLAG_BITPLANE, CW_FLAG_BITPLANE | CW_FLAG_O0):
+    for flags in (0, CW_FLAG_NO_PEEPHOLE, CW_FLAG_O0, CW_FLAG_BITPLANE, CW_FLAG_BITPLANE | CW_FLAG_O0, CW_FLAG_REUSE, CW_FLAG_COMPACT,
+                  CW_FLAG_COMPACT | CW_FLAG_O0, CW_FLAG_REUSE | CW_FLAG_NO_PEEPHOLE):
         wit, st, stats, w2s = hostsim_run(d, ins, flags=flags)
         assert not st.any(), (prime, seed, flags, st)
         for i, e in enumerate(expected):
@@ -147,7 +148,7 @@ def test_shift_by_negative_signal_amount_is_not_treated_as_narrow(prime):
     q = d.q
     ins = [{"x": xv, "y": yv} for xv in (0xAB, q - 1, 0x1FF) for yv in (q - 200, q - 1, q - 253, 3, 0, 254, 255, q - 254, 2**64)]
     expected = [evaluate(d, inp) for inp in ins]
-    for flags in (0, CW_FLAG_NO_PEEPHOLE, CW_FLAG_BITPLANE):
+    for flags in (0, CW_FLAG_NO_PEEPHOLE, CW_FLAG_BITPLANE, CW_FLAG_COMPACT):
         wit, st, stats, w2s = hostsim_run(d, ins, flags=flags)
         assert not st.any()
         for i, e in enumerate(expected):

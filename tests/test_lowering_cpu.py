@@ -74,13 +74,13 @@ def test_wide_tapes_and_compact_layouts():
     wit_c, st_c, stats_c, w2s_c = hostsim_run(d, [{"a": a, "b": b}], flags=48)
     assert not st_c.any() and (wit_c == wit).all() and (w2s_c == w2s).all()
     assert int(stats_c[3]) < int(stats_bp[3]) // 2 and int(stats_c[7]) > 0
-    stc = Circuit(d, host_only=True).stats
+    stc = Circuit(d, host_only=True, compact=False).stats
     assert stc["n_bitwords"] == 0 and stc["n_resident_slots"] == stc["n_witness"]
-    stcc = Circuit(d, host_only=True, flags=48).stats
+    stcc = Circuit(d, host_only=True).stats
     assert stcc["n_bitwords"] == int(stats_c[7]) and stcc["n_resident_slots"] < stcc["n_slots"] < stc["n_slots"] // 4
     # census of the slots by proven width: every slot is counted once, the range-checked bits dominate
     from circom_b200 import native
-    cc = Circuit(d, host_only=True)
+    cc = Circuit(d, host_only=True, compact=False)
     census = (ctypes.c_uint64 * 4)()
     assert native.lib.cw_circuit_slot_census(cc._h, census) == 0
     assert sum(census) == stc["n_slots"] and census[0] > stc["n_slots"] // 2

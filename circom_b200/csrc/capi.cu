@@ -2,7 +2,9 @@
 // sm_100a kernels (kernels.cuh).  There is no CPU execution path: every compute entry point
 // returns CW_ENODEV when no CUDA device is present.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <emmintrin.h>
+#include <nccl.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -20,6 +22,7 @@
 #include "../../include/circom_b200.h"
 #include "kernels.cuh"
 #include "tape.h"
+#include "hostpack.h"
 
 using namespace cw;
 
@@ -109,190 +112,6 @@ int env_int(const char *name, int dflt) {
     const char *s = getenv(name);
     return s && *s ? atoi(s) : dflt;
 }
-
-// ---- host side of the packed transfer --------------------------------------------------------------------
-// The witness of one instance arrives as the packed record written by witness_pack_kernel.  The expansion to
-// the reference's 32-byte rows is zero-extension only (no field arithmetic on the CPU) and is described once
-// per circuit by segments of consecutive witness entries that come from the same section of the record.
-struct PackSeg {
-    uint32_t kind;   // 0 plane run, 1 bits outside the plane, 2 u64 entries, 3 full entries
-    uint32_t start;  // first witness entry
-    uint32_t count;
-    uint32_t src;    // plane run: word * 32 + first bit; otherwise the index inside the section
-};
-struct PackLayout {
-    std::vector<PackSeg> segs;
-    std::vector<uint32_t> bit_loc, u64_loc, full_loc;  // slot ids of the entries outside the plane, in witness order
-    size_t n_plane_words = 0, n_bit_words = 0, words = 0;  // words: per instance, rounded to 16 bytes
-};
-
-void build_pack_layout(const Tape &t, PackLayout &L) {
-    const size_t W = t.n_witness;
-    L.n_plane_words = t.n_bitwords;
-    for (size_t i = 0; i < W; ++i) {
-        const uint32_t loc = t.witness_slot[i];
-        PackSeg sg;
-        sg.start = (uint32_t)i;
-        sg.count = 1;
-        if (loc & OPERAND_BIT) {
-            sg.kind = 0;
-            sg.src = loc & OPERAND_BITPOS_MASK;
-        } else if (t.wit_class[i] == 0) {
-            sg.kind = 1;
-            sg.src = (uint32_t)L.bit_loc.size();
-            L.bit_loc.push_back(loc);
-        } else if (t.wit_class[i] == 1) {
-            sg.kind = 2;
-            sg.src = (uint32_t)L.u64_loc.size();
-            L.u64_loc.push_back(loc);
-        } else {
-            sg.kind = 3;
-            sg.src = (uint32_t)L.full_loc.size();
-            L.full_loc.push_back(loc);
-        }
-        if (!L.segs.empty()) {
-            PackSeg &p = L.segs.back();
-            // (a plane run stays inside its word)
-            const bool same_word = sg.kind != 0 || ((p.src + p.count) >> 5) == (p.src >> 5);
-            if (p.kind == sg.kind && p.src + p.count == sg.src && same_word) {
-                ++p.count;
-                continue;
-            }
-        }
-        L.segs.push_back(sg);
-    }
-    L.n_bit_words = (L.bit_loc.size() + 31) / 32;
-    L.words = (L.n_plane_words + L.n_bit_words + 2 * L.u64_loc.size() + 8 * L.full_loc.size() + 3) & ~(size_t)3;
-}
-
-// one instance: packed record -> W rows of 32 bytes, written once, front to back, with streaming stores
-void expand_record(const PackLayout &L, const uint32_t *rec, uint64_t *row_out) {
-    const uint32_t *plane = rec, *xb = rec + L.n_plane_words, *pu = xb + L.n_bit_words, *pf = pu + 2 * L.u64_loc.size();
-    const bool aligned = (((uintptr_t)row_out) & 15u) == 0;
-    const __m128i zero = _mm_setzero_si128();
-    auto put = [&](uint64_t *dst, __m128i lo, __m128i hi) {
-        if (aligned) {
-            _mm_stream_si128((__m128i *)dst, lo);
-            _mm_stream_si128((__m128i *)(dst + 2), hi);
-        } else {
-            _mm_storeu_si128((__m128i *)dst, lo);
-            _mm_storeu_si128((__m128i *)(dst + 2), hi);
-        }
-    };
-    for (const PackSeg &sg : L.segs) {
-        uint64_t *dst = row_out + 4 * (size_t)sg.start;
-        switch (sg.kind) {
-            case 0: {
-                uint32_t bits = plane[sg.src >> 5] >> (sg.src & 31u);
-                for (uint32_t j = 0; j < sg.count; ++j, dst += 4, bits >>= 1)
-                    put(dst, _mm_cvtsi64_si128((long long)(bits & 1u)), zero);
-                break;
-            }
-            case 1:
-                for (uint32_t j = 0; j < sg.count; ++j, dst += 4) {
-                    const uint32_t k = sg.src + j;
-                    put(dst, _mm_cvtsi64_si128((long long)((xb[k >> 5] >> (k & 31u)) & 1u)), zero);
-                }
-                break;
-            case 2:
-                for (uint32_t j = 0; j < sg.count; ++j, dst += 4)
-                    put(dst, _mm_loadl_epi64((const __m128i *)(pu + 2 * (size_t)(sg.src + j))), zero);
-                break;
-            default:
-                for (uint32_t j = 0; j < sg.count; ++j, dst += 4) {
-                    const uint32_t *f = pf + 8 * (size_t)(sg.src + j);
-                    put(dst, _mm_loadu_si128((const __m128i *)f), _mm_loadu_si128((const __m128i *)(f + 4)));
-                }
-        }
-    }
-    _mm_sfence();
-}
-
-// persistent worker threads for the host-side expansion (created on first use, shared by all batches of the process)
-class Pool {
-  public:
-    static Pool &get() {
-        static Pool p;
-        return p;
-    }
-    unsigned size() const { return (unsigned)th_.size() + 1; }
-    // runs fn(i) for i in [0, n) on the workers and the calling thread; returns when all are done
-    void parallel_for(size_t n, const std::function<void(size_t)> &fn) {
-        if (n == 0) return;
-        std::unique_lock<std::mutex> lk(mu_);
-        done_cv_.wait(lk, [&] { return !busy_; });  // one parallel_for at a time
-        busy_ = true;
-        fn_ = &fn;
-        n_ = n;
-        next_ = 0;
-        pending_ = n;
-        ++gen_;
-        lk.unlock();
-        cv_.notify_all();
-        work();
-        lk.lock();
-        done_cv_.wait(lk, [&] { return pending_ == 0; });
-        busy_ = false;
-        fn_ = nullptr;
-        lk.unlock();
-        done_cv_.notify_all();
-    }
-
-  private:
-    Pool() {
-        unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        // several ranks of one host share its cores (torchrun sets LOCAL_WORLD_SIZE)
-        unsigned ranks = (unsigned)std::max(1, env_int("LOCAL_WORLD_SIZE", 1));
-        unsigned dflt = std::max(4u, std::min(32u, hw / ranks));
-        unsigned nt = (unsigned)std::max(1, env_int("CW_UNPACK_THREADS", (int)dflt));
-        nt = std::min(nt, hw);
-        for (unsigned i = 1; i < nt; ++i) th_.emplace_back([this] { loop(); });
-    }
-    ~Pool() {
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            stop_ = true;
-        }
-        cv_.notify_all();
-        for (auto &t : th_) t.join();
-    }
-    void work() {
-        for (;;) {
-            size_t i;
-            {
-                std::lock_guard<std::mutex> lk(mu_);
-                if (!fn_ || next_ >= n_) return;
-                i = next_++;
-            }
-            (*fn_)(i);
-            bool last;
-            {
-                std::lock_guard<std::mutex> lk(mu_);
-                last = --pending_ == 0;
-            }
-            if (last) done_cv_.notify_all();
-        }
-    }
-    void loop() {
-        uint64_t seen = 0;
-        for (;;) {
-            {
-                std::unique_lock<std::mutex> lk(mu_);
-                cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
-                if (stop_) return;
-                seen = gen_;
-            }
-            work();
-        }
-    }
-    std::vector<std::thread> th_;
-    std::mutex mu_;
-    std::condition_variable cv_, done_cv_;
-    const std::function<void(size_t)> *fn_ = nullptr;
-    size_t n_ = 0, next_ = 0, pending_ = 0;
-    uint64_t gen_ = 0;
-    bool stop_ = false, busy_ = false;
-};
 
 }  // namespace
 
@@ -482,6 +301,7 @@ int cw_circuit_stats(const cw_circuit *c, cw_stats *o) {
     o->n_slot_operands = t.n_slot_operands;
     o->n_bitwords = t.n_bitwords;
     o->n_resident_slots = t.n_resident;
+    o->n_values = t.n_values;
     return CW_OK;
 }
 
@@ -1096,6 +916,15 @@ int cw_circuit_pack_info(const cw_circuit *c, uint64_t info[5], uint32_t *entry)
     return CW_OK;
 }
 
+// one packed record -> the n_witness canonical 32-byte rows of that instance (host memory; what cw_batch_get_witness
+// does for every instance); `store_bits` 0 = widest vector stores of the CPU, or at most 128 / 256 / 512
+int cw_circuit_expand_record(const cw_circuit *c, const uint32_t *record, uint64_t *rows, int store_bits) {
+    if (!c || !record || !rows) return fail(CW_EINVAL, "null argument");
+    expand_record(c->pack_layout(), record, rows, store_bits);
+    return CW_OK;
+}
+const char *cw_host_expand_isa(void) { return expand_isa(); }
+
 // ---- R1CS -------------------------------------------------------------------------------------
 int cw_r1cs_from_circuit(const cw_circuit *c, cw_r1cs **out) {
     if (!c || !out) return fail(CW_EINVAL, "null argument");
@@ -1485,6 +1314,264 @@ int cw_r1cs_eval_batch(cw_r1cs *r, cw_batch *b, uint32_t first, uint32_t count, 
     eo.c = (uint4 *)c_dev;
     CU(cudaMemsetAsync(b->fb_d, 0xFF, (size_t)b->batch * 8, b->stream));
     return launch_r1cs(all, d, S, b->stream, b->fb_d, &eo);
+}
+
+// ---- lowered circuit as a blob / multi-GPU plumbing -----------------------------------------------------------
+int cw_circuit_serialize(const cw_circuit *c, uint8_t *out, size_t cap, size_t *len) {
+    if (!c || !len) return fail(CW_EINVAL, "null argument");
+    std::vector<uint8_t> blob;
+    serialize_tape(c->tape, blob);
+    *len = blob.size();
+    if (!out) return CW_OK;
+    if (cap < blob.size()) return fail(CW_EINVAL, "buffer too small");
+    memcpy(out, blob.data(), blob.size());
+    return CW_OK;
+}
+
+int cw_circuit_deserialize(const void *data, size_t len, cw_circuit **out) {
+    if (!data || !out) return fail(CW_EINVAL, "null argument");
+    cw_circuit *c = new cw_circuit();
+    try {
+        deserialize_tape((const uint8_t *)data, len, c->tape);
+    } catch (const std::exception &e) {
+        delete c;
+        return fail(CW_EFORMAT, e.what());
+    }
+    *out = c;
+    return CW_OK;
+}
+
+// packed records of instances [first, first + count) into caller-provided DEVICE memory (count * words * 4 bytes),
+// asynchronously on the batch stream: what a gather to another GPU sends
+int cw_batch_pack_device(cw_batch *b, uint32_t first, uint32_t count, uint32_t *dst_device) {
+    if (!b || !dst_device || (uint64_t)first + count > b->batch) return fail(CW_EINVAL, "bad argument");
+    if (!b->ran) return fail(CW_ESTATE, "batch has not been run");
+    CU(cudaSetDevice(b->device));
+    const PackLayout &L = b->c->pack_layout();
+    if (!b->pack_flag_d) CU(cudaMalloc((void **)&b->pack_flag_d, 4));
+    return pack_rows(b, L, first, count, dst_device);
+}
+
+// NCCL is resolved at run time (dlopen): the library loads and every single-GPU entry point works on machines
+// without NCCL, and inside a process that already carries a copy (PyTorch's) that copy is the one used.
+namespace {
+struct NcclApi {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+int load_nccl() {
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.h) return CW_OK;
+    void *h = nullptr;
+    const char *env = getenv("CW_NCCL_LIB");
+    for (const char *name : {env ? env : "libnccl.so.2", "libnccl.so.2", "libnccl.so"}) {
+        h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return fail(CW_ENODEV, "NCCL is not available (libnccl.so.2 could not be loaded)");
+    NcclApi a;
+    a.h = h;
+#define CW_SYM(field, sym)                                             \
+    *(void **)(&a.field) = dlsym(h, sym);                              \
+    if (!a.field) return fail(CW_ENODEV, std::string("NCCL symbol missing: ") + sym)
+    CW_SYM(GetUniqueId, "ncclGetUniqueId");
+    CW_SYM(CommInitRank, "ncclCommInitRank");
+    CW_SYM(CommDestroy, "ncclCommDestroy");
+    CW_SYM(Broadcast, "ncclBroadcast");
+    CW_SYM(AllReduce, "ncclAllReduce");
+    CW_SYM(Send, "ncclSend");
+    CW_SYM(Recv, "ncclRecv");
+    CW_SYM(GroupStart, "ncclGroupStart");
+    CW_SYM(GroupEnd, "ncclGroupEnd");
+    CW_SYM(GetErrorString, "ncclGetErrorString");
+#undef CW_SYM
+    g_nccl = a;
+    return CW_OK;
+}
+#define NC(call)                                                                                           \
+    do {                                                                                                   \
+        ncclResult_t r_ = (call);                                                                          \
+        if (r_ != ncclSuccess) return fail(CW_ECUDA, std::string(#call) + ": " + g_nccl.GetErrorString(r_)); \
+    } while (0)
+}  // namespace
+
+struct cw_comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1, device = 0;
+    bool owned = false;
+    cudaStream_t stream = nullptr;
+    uint64_t bytes_sent = 0, bytes_received = 0;  // payload bytes this rank moved through the data-path collectives
+};
+
+int cw_comm_unique_id(uint8_t id[CW_COMM_ID_BYTES]) {
+    if (!id) return fail(CW_EINVAL, "null argument");
+    int rc = load_nccl();
+    if (rc) return rc;
+    static_assert(sizeof(ncclUniqueId) == CW_COMM_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId u;
+    NC(g_nccl.GetUniqueId(&u));
+    memcpy(id, &u, sizeof(u));
+    return CW_OK;
+}
+
+int cw_comm_init(const uint8_t id[CW_COMM_ID_BYTES], int rank, int world, int device, cw_comm **out) {
+    if (!id || !out || world < 1 || rank < 0 || rank >= world) return fail(CW_EINVAL, "bad argument");
+    int rc = load_nccl();
+    if (rc) return rc;
+    if ((rc = ensure_device(device))) return rc;
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    cw_comm *c = new cw_comm();
+    c->rank = rank;
+    c->world = world;
+    c->device = device;
+    c->owned = true;
+    ncclResult_t r = g_nccl.CommInitRank(&c->comm, world, u, rank);
+    if (r != ncclSuccess) {
+        delete c;
+        return fail(CW_ECUDA, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
+    }
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    *out = c;
+    return CW_OK;
+}
+
+int cw_comm_from_nccl(void *nccl_comm, int rank, int world, int device, cw_comm **out) {
+    if (!nccl_comm || !out || world < 1 || rank < 0 || rank >= world) return fail(CW_EINVAL, "bad argument");
+    int rc = load_nccl();
+    if (rc) return rc;
+    if ((rc = ensure_device(device))) return rc;
+    cw_comm *c = new cw_comm();
+    c->comm = (ncclComm_t)nccl_comm;
+    c->rank = rank;
+    c->world = world;
+    c->device = device;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    *out = c;
+    return CW_OK;
+}
+
+void cw_comm_destroy(cw_comm *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) {
+        cudaStreamSynchronize(c->stream);
+        cudaStreamDestroy(c->stream);
+    }
+    if (c->owned && c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    delete c;
+}
+
+int cw_comm_stats(const cw_comm *c, uint64_t *bytes_sent, uint64_t *bytes_received) {
+    if (!c) return fail(CW_EINVAL, "null argument");
+    if (bytes_sent) *bytes_sent = c->bytes_sent;
+    if (bytes_received) *bytes_received = c->bytes_received;
+    return CW_OK;
+}
+
+// The lowered circuit of `root` (instruction tape, constants, witness maps, function code, input tables, R1CS in
+// CSR form) on every rank: ONE NCCL broadcast of the size and one of the blob; only the root lowers.
+int cw_circuit_broadcast(cw_comm *cm, cw_circuit **c, int root) {
+    if (!cm || !c || root < 0 || root >= cm->world) return fail(CW_EINVAL, "bad argument");
+    if (cm->rank == root && !*c) return fail(CW_EINVAL, "the root must pass its circuit");
+    CU(cudaSetDevice(cm->device));
+    std::vector<uint8_t> blob;
+    if (cm->rank == root) serialize_tape((*c)->tape, blob);
+    unsigned long long n = blob.size(), *n_d = nullptr;
+    CU(cudaMalloc((void **)&n_d, 8));
+    CU(cudaMemcpy(n_d, &n, 8, cudaMemcpyHostToDevice));
+    NC(g_nccl.Broadcast(n_d, n_d, 8, ncclUint8, root, cm->comm, cm->stream));
+    CU(cudaStreamSynchronize(cm->stream));
+    CU(cudaMemcpy(&n, n_d, 8, cudaMemcpyDeviceToHost));
+    cudaFree(n_d);
+    uint8_t *buf_d = nullptr;
+    CU(cudaMalloc((void **)&buf_d, n ? n : 16));
+    if (cm->rank == root) CU(cudaMemcpy(buf_d, blob.data(), n, cudaMemcpyHostToDevice));
+    NC(g_nccl.Broadcast(buf_d, buf_d, n, ncclUint8, root, cm->comm, cm->stream));
+    CU(cudaStreamSynchronize(cm->stream));
+    int rc = CW_OK;
+    if (cm->rank != root) {
+        blob.resize(n);
+        CU(cudaMemcpy(blob.data(), buf_d, n, cudaMemcpyDeviceToHost));
+        rc = cw_circuit_deserialize(blob.data(), blob.size(), c);
+        cm->bytes_received += n;
+    } else cm->bytes_sent += n * (uint64_t)(cm->world - 1);
+    cudaFree(buf_d);
+    return rc;
+}
+
+// Gather of witness vectors: every rank packs instances [first, first + count) of its batch on the device and sends
+// the records to `root` over NVLink (grouped ncclSend / ncclRecv); on the root recv_device[r][count][words] holds
+// rank r's records (its own are packed in place).  Packed records, not 32-byte rows: 30x fewer bytes for circuits
+// of bit decompositions; the root expands what it needs (cw_circuit_pack_info).  ms = device time on the root /
+// sender of pack + transfer.
+int cw_batch_gather_witness_packed(cw_comm *cm, cw_batch *b, uint32_t first, uint32_t count, int root,
+                                   uint32_t *recv_device, uint32_t *send_scratch_device, float *ms) {
+    if (!cm || !b || root < 0 || root >= cm->world || (uint64_t)first + count > b->batch) return fail(CW_EINVAL, "bad argument");
+    if (!b->ran) return fail(CW_ESTATE, "batch has not been run");
+    if (cm->rank == root && !recv_device) return fail(CW_EINVAL, "the root needs a receive buffer");
+    if (cm->rank != root && !send_scratch_device) return fail(CW_EINVAL, "senders need a scratch buffer of count * words * 4 bytes");
+    CU(cudaSetDevice(b->device));
+    const PackLayout &L = b->c->pack_layout();
+    const size_t n = (size_t)count * L.words * 4;  // bytes per rank
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, b->stream));
+    uint32_t *mine = cm->rank == root ? recv_device + (size_t)root * count * L.words : send_scratch_device;
+    int rc = cw_batch_pack_device(b, first, count, mine);
+    if (rc) return rc;
+    NC(g_nccl.GroupStart());
+    if (cm->rank == root) {
+        for (int r = 0; r < cm->world; ++r)
+            if (r != root) NC(g_nccl.Recv(recv_device + (size_t)r * count * L.words, n, ncclUint8, r, cm->comm, b->stream));
+    } else {
+        NC(g_nccl.Send(mine, n, ncclUint8, root, cm->comm, b->stream));
+    }
+    NC(g_nccl.GroupEnd());
+    CU(cudaEventRecord(e1, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    if (ms) CU(cudaEventElapsedTime(ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (cm->rank == root) cm->bytes_received += n * (uint64_t)(cm->world - 1);
+    else cm->bytes_sent += n;
+    return CW_OK;
+}
+
+// all ranks learn whether any instance of any rank failed: out[0] = number of instances with a failed assert,
+// out[1] = number with a runtime error, summed over the communicator (ncclAllReduce of two counters)
+int cw_status_allreduce(cw_comm *cm, cw_batch *b, uint64_t out[2]) {
+    if (!cm || !b || !out) return fail(CW_EINVAL, "null argument");
+    std::vector<int32_t> st(b->batch);
+    int rc = cw_batch_status(b, st.data());
+    if (rc) return rc;
+    unsigned long long h[2] = {0, 0}, *d = nullptr;
+    for (int32_t s : st) {
+        if (s > 0) ++h[0];
+        else if (s < 0) ++h[1];
+    }
+    CU(cudaMalloc((void **)&d, 16));
+    CU(cudaMemcpyAsync(d, h, 16, cudaMemcpyHostToDevice, b->stream));
+    NC(g_nccl.AllReduce(d, d, 2, ncclUint64, ncclSum, cm->comm, b->stream));
+    CU(cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, b->stream));
+    CU(cudaStreamSynchronize(b->stream));
+    cudaFree(d);
+    out[0] = h[0];
+    out[1] = h[1];
+    return CW_OK;
 }
 
 // ---- field batch ops ---------------------------------------------------------------------------

@@ -1264,10 +1264,12 @@ struct Lowerer {
         T.n_resident = n_resident;
         {   // operand statistics
             T.n_slot_operands = 0;
+            T.n_values = 0;
             const size_t n_ops = T.ops.size() / 4;
             for (size_t i = 0; i < n_ops; ++i) {
                 const uint32_t *o = &T.ops[i * 4];
                 const uint32_t opc = o[0] & 0xFFu;
+                if (!is_assert_op(opc)) T.n_values += opc == DOP_BITS ? (o[3] >> 24) + 1u : 1u;
                 if (opc == 45) continue;
                 for (int k = 1; k <= 3; ++k) {
                     if (k == 3 && c_is_immediate(opc)) break;
@@ -1315,6 +1317,131 @@ void lower_circuit(const uint8_t *data, size_t len, uint32_t flags, Tape &out) {
     Lowerer L(out, flags);
     L.parse(data, len);
     L.lower();
+}
+
+}  // namespace cw
+
+// ---- the lowered circuit as one blob ---------------------------------------------------------------------
+// What rank 0 broadcasts to the other GPUs' processes (instruction tape, constants, witness maps, function code,
+// input tables and the R1CS in CSR form): they then skip the lowering.  Also usable as an on-disk cache.  The
+// format is private to one build of the library ("CB2T" + a layout version), not an interchange format.
+namespace cw {
+namespace {
+struct BlobW {
+    std::vector<uint8_t> &o;
+    void raw(const void *p, size_t n) { o.insert(o.end(), (const uint8_t *)p, (const uint8_t *)p + n); }
+    template <class T> void pod(const T &v) { raw(&v, sizeof(T)); }
+    template <class T> void vec(const std::vector<T> &v) {
+        pod<uint64_t>(v.size());
+        if (!v.empty()) raw(v.data(), v.size() * sizeof(T));
+    }
+    void str(const std::string &s) {
+        pod<uint64_t>(s.size());
+        raw(s.data(), s.size());
+    }
+};
+struct BlobR {
+    const uint8_t *p, *end;
+    void raw(void *d, size_t n) {
+        if (n > (size_t)(end - p)) throw std::runtime_error("lowered-circuit blob: truncated");
+        memcpy(d, p, n);
+        p += n;
+    }
+    template <class T> void pod(T &v) { raw(&v, sizeof(T)); }
+    template <class T> void vec(std::vector<T> &v) {
+        uint64_t n;
+        pod(n);
+        if (n > (uint64_t)(end - p) / sizeof(T)) throw std::runtime_error("lowered-circuit blob: bad length");
+        v.resize(n);
+        if (n) raw(v.data(), n * sizeof(T));
+    }
+    void str(std::string &s) {
+        uint64_t n;
+        pod(n);
+        if (n > (uint64_t)(end - p)) throw std::runtime_error("lowered-circuit blob: bad length");
+        s.assign((const char *)p, n);
+        p += n;
+    }
+};
+constexpr uint32_t BLOB_VERSION = 2;
+}  // namespace
+
+void serialize_tape(const Tape &t, std::vector<uint8_t> &out) {
+    BlobW w{out};
+    w.raw("CB2T", 4);
+    w.pod<uint32_t>(BLOB_VERSION);
+    w.pod<int32_t>(t.F.prime_id);
+    w.pod(t.flags);
+    const uint64_t nums[] = {t.n_signals, t.n_witness, t.n_inputs, t.n_outputs, t.n_components, t.n_ir_ops, t.n_mul_ops,
+                             t.n_conv_ops, t.max_level_width, t.n_asserts, t.slot_census[0], t.slot_census[1],
+                             t.slot_census[2], t.slot_census[3], t.n_slot_operands, t.n_values, t.n_resident, t.n_pre,
+                             t.n_slots, t.n_bitwords};
+    w.pod<uint64_t>(sizeof(nums) / 8);
+    w.raw(nums, sizeof(nums));
+    w.vec(t.ops); w.vec(t.level_start); w.vec(t.consts); w.vec(t.witness_slot); w.vec(t.input_slot);
+    w.vec(t.pk_bit_wire); w.vec(t.pk_u64_wire); w.vec(t.pk_full_wire); w.vec(t.wit_class);
+    w.vec(t.fn_code); w.vec(t.fn_info); w.vec(t.call_tab); w.vec(t.witness2signal);
+    w.pod<uint64_t>(t.inputs.size());
+    for (const InputInfo &in : t.inputs) {
+        w.str(in.name);
+        w.pod(in.hash); w.pod(in.signal_id); w.pod(in.size);
+    }
+    w.vec(t.hashmap);
+    const R1csData &r = t.r1cs;
+    w.pod<int32_t>(r.prime_id);
+    w.pod(r.n_wires); w.pod(r.n_constraints);
+    w.vec(r.row_ptr); w.vec(r.col); w.vec(r.coef); w.vec(r.dict);
+    w.pod(r.n_pub_out); w.pod(r.n_pub_in); w.pod(r.n_prv_in);
+}
+
+void deserialize_tape(const uint8_t *data, size_t len, Tape &t) {
+    BlobR r{data, data + len};
+    char magic[4];
+    r.raw(magic, 4);
+    uint32_t ver;
+    r.pod(ver);
+    if (memcmp(magic, "CB2T", 4) || ver != BLOB_VERSION) throw std::runtime_error("lowered-circuit blob: bad magic / version");
+    int32_t prime;
+    r.pod(prime);
+    if (prime < 0 || prime > 1) throw std::runtime_error("lowered-circuit blob: unknown prime");
+    t.F = make_field(prime);
+    r.pod(t.flags);
+    uint64_t n_nums;
+    r.pod(n_nums);
+    uint64_t nums[20];
+    if (n_nums != 20) throw std::runtime_error("lowered-circuit blob: layout mismatch");
+    r.raw(nums, sizeof(nums));
+    t.n_signals = nums[0]; t.n_witness = nums[1]; t.n_inputs = nums[2]; t.n_outputs = nums[3]; t.n_components = nums[4];
+    t.n_ir_ops = nums[5]; t.n_mul_ops = nums[6]; t.n_conv_ops = nums[7]; t.max_level_width = nums[8]; t.n_asserts = nums[9];
+    for (int k = 0; k < 4; ++k) t.slot_census[k] = nums[10 + k];
+    t.n_slot_operands = nums[14]; t.n_values = nums[15]; t.n_resident = (uint32_t)nums[16]; t.n_pre = (uint32_t)nums[17];
+    t.n_slots = (uint32_t)nums[18]; t.n_bitwords = (uint32_t)nums[19];
+    r.vec(t.ops); r.vec(t.level_start); r.vec(t.consts); r.vec(t.witness_slot); r.vec(t.input_slot);
+    r.vec(t.pk_bit_wire); r.vec(t.pk_u64_wire); r.vec(t.pk_full_wire); r.vec(t.wit_class);
+    r.vec(t.fn_code); r.vec(t.fn_info); r.vec(t.call_tab); r.vec(t.witness2signal);
+    uint64_t n_in;
+    r.pod(n_in);
+    if (n_in > len) throw std::runtime_error("lowered-circuit blob: bad length");
+    t.inputs.resize(n_in);
+    for (InputInfo &in : t.inputs) {
+        r.str(in.name);
+        r.pod(in.hash); r.pod(in.signal_id); r.pod(in.size);
+    }
+    r.vec(t.hashmap);
+    R1csData &R = t.r1cs;
+    int32_t rp;
+    r.pod(rp);
+    R.prime_id = rp;
+    r.pod(R.n_wires); r.pod(R.n_constraints);
+    r.vec(R.row_ptr); r.vec(R.col); r.vec(R.coef); r.vec(R.dict);
+    r.pod(R.n_pub_out); r.pod(R.n_pub_in); r.pod(R.n_prv_in);
+    // consistency of what the kernels index with (the blob comes from another rank of the same job, not from a user,
+    // but a short read or a version skew must not turn into out-of-bounds device accesses)
+    if (t.ops.size() % 4 || t.level_start.empty() || t.level_start.back() != t.ops.size() / 4 ||
+        t.witness_slot.size() != t.n_witness || t.input_slot.size() != t.n_inputs || t.wit_class.size() != t.n_witness ||
+        t.witness2signal.size() != t.n_witness || R.row_ptr.size() != 3 * R.n_constraints + 1 || R.col.size() != R.coef.size() ||
+        (R.row_ptr.size() && R.row_ptr.back() != R.col.size()) || t.hashmap.empty())
+        throw std::runtime_error("lowered-circuit blob: inconsistent");
 }
 
 }  // namespace cw

@@ -1,0 +1,49 @@
+// Host side of the packed device->host transfer: the layout of the packed witness records, their expansion to the
+// reference's 32-byte rows (zero-extension only - no field arithmetic happens on the CPU) and the worker threads
+// that run it.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <functional>
+#include <vector>
+
+#include "tape.h"
+
+namespace cw {
+
+// The witness of one instance arrives as the packed record written by witness_pack_kernel.  The expansion is
+// described once per circuit by segments of consecutive witness entries that come from the same section.
+struct PackSeg {
+    uint32_t kind;   // 0 plane run, 1 bits outside the plane, 2 u64 entries, 3 full entries
+    uint32_t start;  // first witness entry
+    uint32_t count;
+    uint32_t src;    // plane run: word * 32 + first bit; otherwise the index inside the section
+};
+struct PackLayout {
+    std::vector<PackSeg> segs;
+    std::vector<uint32_t> bit_loc, u64_loc, full_loc;  // slot ids of the entries outside the plane, in witness order
+    size_t n_plane_words = 0, n_bit_words = 0, words = 0;  // words: per instance, rounded to 16 bytes
+};
+void build_pack_layout(const Tape &t, PackLayout &L);
+
+// one instance: packed record -> W rows of 32 bytes, each written exactly once, front to back, with streaming stores
+// (force_bits: 0 = the widest stores the CPU has, else at most 128 / 256 / 512-bit stores - for tests)
+void expand_record(const PackLayout &L, const uint32_t *rec, uint64_t *row_out, int force_bits = 0);
+const char *expand_isa();  // "avx512" / "avx2" / "sse2": the store width expand_record uses on this CPU
+
+// persistent worker threads (created on first use, shared by all batches of the process)
+class Pool {
+  public:
+    static Pool &get();
+    unsigned size() const;
+    // runs fn(i) for i in [0, n) on the workers and the calling thread; returns when all are done
+    void parallel_for(size_t n, const std::function<void(size_t)> &fn);
+
+  private:
+    Pool();
+    ~Pool();
+    struct Impl;
+    Impl *p_;
+};
+
+}  // namespace cw

@@ -46,6 +46,7 @@ struct Tape {
     uint64_t n_ir_ops = 0, n_mul_ops = 0, n_conv_ops = 0, max_level_width = 0, n_asserts = 0;
     uint64_t slot_census[4] = {0, 0, 0, 0};  // value slots by static width: 1 bit, <= 32, <= 64 bits, wider
     uint64_t n_slot_operands = 0;  // operand reads of slots
+    uint64_t n_values = 0;         // values the tape writes per instance (every destination, each bit of a run)
     uint32_t n_resident = 0;  // slots [0, n_resident) hold witness entries for the whole run; the rest are reused temporaries (CW_FLAG_REUSE)
     uint32_t n_pre = 0;    // slot 0 = constant one, slots 1..n_inputs = main inputs
     uint32_t n_slots = 0;  // witness entries [0, n_witness) then the other values
@@ -73,6 +74,10 @@ struct Tape {
 void lower_circuit(const uint8_t *data, size_t len, uint32_t flags, Tape &out);
 
 uint64_t fnv1a(const char *s, size_t n);
+
+// the lowered circuit as one blob (flatten.cpp): what rank 0 broadcasts, or an on-disk cache
+void serialize_tape(const Tape &t, std::vector<uint8_t> &out);
+void deserialize_tape(const uint8_t *data, size_t len, Tape &t);
 
 // file formats (formats.cpp)
 void write_r1cs(const R1csData &r, const FieldParams &F, const std::string &path);

@@ -26,7 +26,7 @@ class CwStats(ctypes.Structure):
     _fields_ = [(n, c_uint64) for n in (
         "n_signals", "n_witness", "n_inputs", "n_outputs", "n_components", "n_constants", "n_ir_ops",
         "n_tape_ops", "n_slots", "n_levels", "n_constraints", "n_nnz", "n_mul_ops", "n_conv_ops",
-        "max_level_width", "n_slot_operands", "n_bitwords", "n_resident_slots")]
+        "max_level_width", "n_slot_operands", "n_bitwords", "n_resident_slots", "n_values")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -79,6 +79,19 @@ def _load() -> ctypes.CDLL:
         "cw_batch_expand_witness": (c_int, [P, c_uint32, c_uint32, c_void_p]),
         "cw_r1cs_check_batch": (c_int, [P, P, c_void_p, POINTER(c_float)]),
         "cw_r1cs_eval_batch": (c_int, [P, P, c_uint32, c_uint32, c_void_p, c_void_p, c_void_p]),
+        "cw_comm_unique_id": (c_int, [c_void_p]),
+        "cw_comm_init": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(P)]),
+        "cw_comm_from_nccl": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(P)]),
+        "cw_comm_destroy": (None, [P]),
+        "cw_comm_stats": (c_int, [P, POINTER(c_uint64), POINTER(c_uint64)]),
+        "cw_circuit_serialize": (c_int, [P, c_void_p, c_size_t, POINTER(c_size_t)]),
+        "cw_circuit_deserialize": (c_int, [c_void_p, c_size_t, POINTER(P)]),
+        "cw_circuit_broadcast": (c_int, [P, POINTER(P), c_int]),
+        "cw_batch_pack_device": (c_int, [P, c_uint32, c_uint32, c_void_p]),
+        "cw_batch_gather_witness_packed": (c_int, [P, P, c_uint32, c_uint32, c_int, c_void_p, c_void_p, POINTER(c_float)]),
+        "cw_status_allreduce": (c_int, [P, P, POINTER(c_uint64)]),
+        "cw_circuit_expand_record": (c_int, [P, c_void_p, c_void_p, c_int]),
+        "cw_host_expand_isa": (c_char_p, []),
         "cw_batch_witness_device": (c_int, [P, POINTER(c_void_p)]),
         "cw_batch_witness_strided": (c_int, [P, POINTER(c_void_p), POINTER(c_uint64)]),
         "cw_batch_stream": (c_void_p, [P]),

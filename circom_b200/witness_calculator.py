@@ -133,6 +133,32 @@ class Circuit:
             check(lib.cw_circuit_load_mem(buf, len(buf), flags, ctypes.byref(self._h)))
         else:
             check(lib.cw_circuit_load(str(src).encode(), flags, ctypes.byref(self._h)))
+        self._init_from_handle()
+
+    @classmethod
+    def from_handle(cls, handle: ctypes.c_void_p, flags: int = 0) -> "Circuit":
+        """wrap a cw_circuit* produced by the library (cw_circuit_deserialize / cw_circuit_broadcast); takes ownership"""
+        c = cls.__new__(cls)
+        c._h = handle
+        c.flags = flags
+        c._init_from_handle()
+        return c
+
+    @classmethod
+    def deserialize(cls, blob: bytes) -> "Circuit":
+        h = ctypes.c_void_p()
+        check(lib.cw_circuit_deserialize(blob, len(blob), ctypes.byref(h)))
+        return cls.from_handle(h)
+
+    def serialize(self) -> bytes:
+        """the LOWERED circuit as one blob (what rank 0 broadcasts; other ranks skip the lowering)"""
+        n = ctypes.c_size_t()
+        check(lib.cw_circuit_serialize(self._h, None, 0, ctypes.byref(n)))
+        buf = (ctypes.c_uint8 * n.value)()
+        check(lib.cw_circuit_serialize(self._h, buf, n.value, ctypes.byref(n)))
+        return bytes(buf)
+
+    def _init_from_handle(self):
         st = CwStats()
         check(lib.cw_circuit_stats(self._h, ctypes.byref(st)))
         self.stats = st.as_dict()

@@ -82,6 +82,8 @@ typedef struct cw_stats {
     uint64_t n_slot_operands; /* operand reads of value slots in the tape */
     uint64_t n_bitwords;      /* 32-bit words of the per-instance bit plane (CW_FLAG_BITPLANE), else 0 */
     uint64_t n_resident_slots;/* slots holding witness entries; slots beyond are reused temporaries (CW_FLAG_REUSE) */
+    uint64_t n_values;        /* values the tape writes per instance: every destination, each bit of a bit run (the S_w of SURVEY.md 8(d),
+                                 independent of how the values are stored) */
 } cw_stats;
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -155,6 +157,11 @@ int cw_batch_get_witness_packed(cw_batch *b, uint32_t *out_words);
  * entry[n_witness] = (class << 30) | index - class 0: bit `index` of the plane section, 1: bit `index` of the
  * extra-bit section, 2: u64 entry `index`, 3: 32-byte entry `index`; the sections follow each other in that order */
 int cw_circuit_pack_info(const cw_circuit *c, uint64_t info[5], uint32_t *entry);
+/* host side of that layout: one packed record -> the n_witness canonical 32-byte rows of the instance (what
+ * cw_batch_get_witness does per instance; zero-extension only).  store_bits: 0 = the widest vector stores the CPU
+ * has, or at most 128 / 256 / 512.  cw_host_expand_isa names what 0 selects ("avx512" / "avx2" / "sse2"). */
+int cw_circuit_expand_record(const cw_circuit *c, const uint32_t *record, uint64_t *rows, int store_bits);
+const char *cw_host_expand_isa(void);
 /* bytes that crossed PCIe in the last cw_batch_get_witness (entries proven to be bits / 64-bit values travel
  * packed and are zero-extended on the host; CW_PACKED_D2H=0 disables) */
 uint64_t cw_batch_last_d2h_bytes(const cw_batch *b);
@@ -205,6 +212,40 @@ int cw_r1cs_check_batch(cw_r1cs *r, cw_batch *b, int64_t *first_bad, float *kern
  * generation; asynchronous on the batch stream (cw_batch_sync).  One-instance tile layouts only. */
 int cw_r1cs_eval_batch(cw_r1cs *r, cw_batch *b, uint32_t first, uint32_t count, uint64_t *a_dev, uint64_t *b_dev,
                        uint64_t *c_dev);
+
+/* ---- multi-GPU: one process per GPU, independent inputs sharded over the ranks ---------------------------
+ * The reference has no distributed mode (Circom_CalcWit is per-process state, calcwit.cpp:26-45).  Here rank 0
+ * lowers the circuit and broadcasts the lowered form once; every rank runs its shard; witnesses are gathered in
+ * packed form.  NCCL is resolved at run time (dlopen of libnccl.so.2, or CW_NCCL_LIB); without it these entry
+ * points return CW_ENODEV and everything else works. */
+typedef struct cw_comm cw_comm;
+#define CW_COMM_ID_BYTES 128
+/* ncclGetUniqueId: call on one rank, hand the bytes to the others through the host program's own channel */
+int cw_comm_unique_id(uint8_t id[CW_COMM_ID_BYTES]);
+/* ncclCommInitRank (collective over `world` processes); `device` = this rank's CUDA device */
+int cw_comm_init(const uint8_t id[CW_COMM_ID_BYTES], int rank, int world, int device, cw_comm **out);
+/* adopt a communicator the host program already has (ncclComm_t as void*); not destroyed by cw_comm_destroy */
+int cw_comm_from_nccl(void *nccl_comm, int rank, int world, int device, cw_comm **out);
+void cw_comm_destroy(cw_comm *c);
+/* payload bytes this rank sent / received through the collectives below */
+int cw_comm_stats(const cw_comm *c, uint64_t *bytes_sent, uint64_t *bytes_received);
+/* the lowered circuit as a blob (instruction tape, constants, witness maps, function code, input tables, CSR):
+ * cw_circuit_serialize with out = NULL returns the size */
+int cw_circuit_serialize(const cw_circuit *c, uint8_t *out, size_t cap, size_t *len);
+int cw_circuit_deserialize(const void *data, size_t len, cw_circuit **out);
+/* ONE broadcast of the lowered circuit from `root`: *c is the root's circuit on the root and receives a new handle
+ * on the other ranks (which never run the lowering) */
+int cw_circuit_broadcast(cw_comm *cm, cw_circuit **c, int root);
+/* packed records of instances [first, first + count) into caller-provided DEVICE memory (count * words * 4 bytes,
+ * words = cw_circuit_pack_info info[0]); asynchronous on the batch stream */
+int cw_batch_pack_device(cw_batch *b, uint32_t first, uint32_t count, uint32_t *dst_device);
+/* gather of witness vectors on `root`: every rank packs instances [first, first + count) of its batch and sends the
+ * records over NVLink (grouped ncclSend / ncclRecv on the batch stream).  Root: recv_device[world][count][words];
+ * other ranks: send_scratch_device[count][words].  ms = device time of pack + transfer on this rank. */
+int cw_batch_gather_witness_packed(cw_comm *cm, cw_batch *b, uint32_t first, uint32_t count, int root,
+                                   uint32_t *recv_device, uint32_t *send_scratch_device, float *ms);
+/* out[0] = instances with a failed assert, out[1] = instances with a runtime error, summed over all ranks */
+int cw_status_allreduce(cw_comm *cm, cw_batch *b, uint64_t out[2]);
 
 /* ---- field library, batched (parity tests of the device Fr_* equivalents, fr.hpp:28-70) ------ */
 /* r[i] = op(a[i], b[i], c[i]) for i < n on `device`; canonical in / canonical out; b, c may be NULL */

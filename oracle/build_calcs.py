@@ -28,12 +28,13 @@ def circuits():
         "sha256compression": ("bn128", lambda d: C.sha256_compression(d)),
         "sha256_64_bls": ("bls12381", lambda d: C.sha256(d, 64)),
         "ecdsa_scale_8x132": ("bn128", lambda d: C.ecdsa_scale(d, 8, 132)),
+        "sha256_512_bls": ("bls12381", lambda d: C.sha256(d, 512)),   # BASELINE.json configs[4]
     }
 
 
 # calculators whose generated C++ takes g++ -O3 more than ten minutes each: built only when asked for by name
 # (tests/golden/make_golden.py), never by the default build
-SLOW = ("sha256compression", "sha256_64_bls")
+SLOW = ("sha256compression", "sha256_64_bls", "sha256_512_bls")
 
 
 def make_desc(name: str):

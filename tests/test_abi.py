@@ -101,3 +101,50 @@ def test_r1cs_write_read_roundtrip(tmp_path):
     raw = open(p1, "rb").read()
     assert raw[:4] == b"r1cs" and struct.unpack_from("<II", raw, 4) == (1, 3)
     assert struct.unpack_from("<I", raw, 12)[0] == 2   # constraints section comes first (r1cs_porting.rs:19-53)
+
+
+def test_packed_record_layout_and_host_expansion():
+    """cw_circuit_pack_info describes the packed device->host record; cw_circuit_expand_record (the host half of
+    cw_batch_get_witness) turns a record into the reference's 32-byte rows.  A record assembled in Python from an
+    oracle witness must expand to that witness with every store width the CPU has (SSE2 / AVX2 / AVX-512 paths)."""
+    import random
+    from circom_b200.circuits.bigint import ecdsa_scale
+    from oracle.ir_eval import evaluate
+    rng = random.Random(4)
+    for compact in (False, True):
+        d = CircuitDesc("bn128")
+        d.set_main(ecdsa_scale(d, 1, 2))
+        c = Circuit(d, host_only=True, compact=compact)
+        info, ent = c.pack_info()
+        words, n_plane, n_xbits, n_u64, n_full = info
+        assert words * 4 < c.n_witness * 32 // 8 and (words % 4) == 0
+        if compact:
+            assert n_plane == c.stats["n_bitwords"] > 0
+        inp = {"a": [rng.getrandbits(64) for _ in range(4)], "b": [rng.getrandbits(64) for _ in range(4)]}
+        exp = evaluate(d, inp)
+        w2s = c.witness2signal().astype(np.int64)
+        wit = [exp[k] for k in w2s]
+        rec = np.zeros(words, dtype=np.uint32)
+        off = [0, n_plane, n_plane + n_xbits, n_plane + n_xbits + 2 * n_u64]
+        for v, e in zip(wit, ent.tolist()):
+            cls, idx = e >> 30, e & 0x3FFFFFFF
+            if cls <= 1:
+                assert v in (0, 1)
+                rec[off[cls] + (idx >> 5)] |= np.uint32(v << (idx & 31))
+            elif cls == 2:
+                assert v < 2**64
+                rec[off[2] + 2 * idx] = v & 0xFFFFFFFF
+                rec[off[2] + 2 * idx + 1] = v >> 32
+            else:
+                for k in range(8):
+                    rec[off[3] + 8 * idx + k] = (v >> (32 * k)) & 0xFFFFFFFF
+        for bits in (128, 256, 512, 0):
+            for misalign in (0, 1):     # 32-byte aligned rows take the streaming stores, others plain ones
+                buf = np.full(c.n_witness * 4 + 8, 0xDEADBEEFDEADBEEF, dtype=np.uint64)
+                base = (-buf.ctypes.data // 8) % 4 + misalign
+                rows = buf[base:base + c.n_witness * 4]
+                assert native.lib.cw_circuit_expand_record(c._h, rec.ctypes.data, rows.ctypes.data, bits) == 0
+                got = [int.from_bytes(rows[4 * i:4 * i + 4].tobytes(), "little") for i in range(c.n_witness)]
+                assert got == wit, (compact, bits, misalign)
+                assert int(buf[base + c.n_witness * 4]) == 0xDEADBEEFDEADBEEF and (base == 0 or int(buf[base - 1]) == 0xDEADBEEFDEADBEEF)
+    assert native.lib.cw_host_expand_isa() in (b"avx512", b"avx2", b"sse2")

@@ -47,6 +47,13 @@ def _worker(rank, world, port, out_path):
     t = torch.from_numpy(sig.copy())
     dist.broadcast(t, 0)
     assert (t.numpy() == sig).all(), "ranks lowered different tapes"
+    # the LOWERED circuit travels too (what cw_circuit_broadcast sends over NCCL on GPUs): only rank 0 lowered it
+    low = broadcast_blob(c.serialize() if rank == 0 else None, rank, world)
+    c2 = Circuit.deserialize(low)
+    assert c2.stats == c.stats and c2.serialize() == low
+    for x, y in zip(c.tape(), c2.tape()):
+        assert (x == y).all()
+    assert (c2.witness2signal() == c.witness2signal()).all() and c2.input_signal_size("in") == 2
     # the global batch, deterministic on every rank; each rank computes only its shard
     total = 11
     rng = random.Random(42)

@@ -295,6 +295,11 @@ def cpu_reference_run(desc, args, inputs: np.ndarray, seconds: float):
                       % (n, cores, dt, t1)}
 
 
+def native_lib():
+    from circom_b200 import native
+    return native.lib
+
+
 def workload_config(label, desc, batch, world, st=None):
     """the `config` object: the same keys in both arms (our arm adds the lowered-tape figures)"""
     cfg = {"workload": label, "batch_per_gpu": batch, "global_batch": batch * world,
@@ -451,7 +456,9 @@ def run_workload(ctx: Ctx, workload: str, batch: int, steps: int, warmup: int, e
         e2e = {"value": done * world * e2e_steps / e2e_s, "unit": "witnesses/s", "steps": e2e_steps,
                "batch_per_gpu": done, "chunk": chunk, "streams": "2 batches in flight (tape of chunk k+1 under the transfer of chunk k)",
                "h2d_bytes_per_step": int(done * n_in * 32), "d2h_bytes_per_step": int(d2h[0]),
-               "host_witness_bytes_per_step": int(done * W * 32), "s_per_step": e2e_s / e2e_steps}
+               "host_witness_bytes_per_step": int(done * W * 32), "s_per_step": e2e_s / e2e_steps,
+               "host_expansion": native_lib().cw_host_pool_info().decode(),
+               "host_write_GBps": done * world * e2e_steps * W * 32 / e2e_s / 1e9}
         del pair, outs
     torch.cuda.empty_cache()
 

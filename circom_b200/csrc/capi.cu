@@ -671,6 +671,20 @@ int cw_batch_expand_witness(cw_batch *b, uint32_t first, uint32_t count, uint64_
     return expand_rows(b, first, count, (uint4 *)dst_device);
 }
 
+// NUMA node the GPU hangs off (/sys/bus/pci/devices/<bus id>/numa_node), -1 if unknown
+static int device_numa_node(int device) {
+    char id[32] = {0};
+    if (cudaDeviceGetPCIBusId(id, sizeof(id), device) != cudaSuccess) return -1;
+    for (char *p = id; *p; ++p) *p = (char)tolower(*p);
+    std::string path = std::string("/sys/bus/pci/devices/") + id + "/numa_node";
+    FILE *f = fopen(path.c_str(), "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+
 static size_t pack_chunk_instances(const cw_batch *b, const PackLayout &L) {
     size_t mb = (size_t)std::max(8, env_int("CW_PACK_CHUNK_MB", 96));
     size_t n = std::max<size_t>(1, (mb << 20) / (L.words * 4));
@@ -714,11 +728,12 @@ static int get_witness_packed(cw_batch *b, uint64_t *out, bool *done) {
     CU(cudaMemsetAsync(b->pack_flag_d, 0, 4, b->stream));
     const size_t W = t.n_witness, cap = b->packed_cap;
     const size_t n_chunks = (b->batch + cap - 1) / cap;
-    Pool &pool = Pool::get();
+    Pool &pool = Pool::get(device_numa_node(b->device));
     auto expand_chunk = [&](size_t k) {
         const size_t first = k * cap, cnt = std::min(cap, b->batch - first);
         const uint32_t *src = b->packed_h[k & 1];
-        pool.parallel_for(cnt, [&](size_t i) { expand_record(L, src + i * L.words, out + (first + i) * W * 4); });
+        // item key = instance index: the rows of instance i of `out` are always written by the same (pinned) worker
+        pool.parallel_for(cnt, first, [&](size_t i) { expand_record(L, src + i * L.words, out + (first + i) * W * 4); });
     };
     for (size_t k = 0; k < n_chunks; ++k) {
         const size_t first = k * cap, cnt = std::min(cap, b->batch - first);
@@ -924,6 +939,7 @@ int cw_circuit_expand_record(const cw_circuit *c, const uint32_t *record, uint64
     return CW_OK;
 }
 const char *cw_host_expand_isa(void) { return expand_isa(); }
+const char *cw_host_pool_info(void) { return Pool::get().describe(); }
 
 // ---- R1CS -------------------------------------------------------------------------------------
 int cw_r1cs_from_circuit(const cw_circuit *c, cw_r1cs **out) {

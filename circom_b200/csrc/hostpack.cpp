@@ -3,10 +3,15 @@
 
 #include <immintrin.h>
 
+#include <pthread.h>
+#include <sched.h>
+
 #include <algorithm>
 #include <condition_variable>
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <string>
 #include <thread>
 
 namespace cw {
@@ -212,23 +217,65 @@ void expand_record(const PackLayout &L, const uint32_t *rec, uint64_t *row_out, 
 }
 
 // ---- worker pool --------------------------------------------------------------------------------------------------
+namespace {
+// CPUs of every NUMA node, from /sys/devices/system/node/node<k>/cpulist ("0-31,64-95")
+std::vector<std::vector<int>> numa_nodes() {
+    std::vector<std::vector<int>> nodes;
+    for (int k = 0; k < 64; ++k) {
+        char path[96];
+        snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", k);
+        FILE *f = fopen(path, "r");
+        if (!f) break;
+        char buf[4096];
+        std::vector<int> cpus;
+        if (fgets(buf, sizeof(buf), f)) {
+            const char *p = buf;
+            while (*p && *p != '\n') {
+                char *e;
+                long a = strtol(p, &e, 10), b = a;
+                if (e == p) break;
+                p = e;
+                if (*p == '-') {
+                    b = strtol(p + 1, &e, 10);
+                    p = e;
+                }
+                for (long c = a; c <= b; ++c) cpus.push_back((int)c);
+                if (*p == ',') ++p;
+            }
+        }
+        fclose(f);
+        if (!cpus.empty()) nodes.push_back(cpus);
+    }
+    return nodes;
+}
+}  // namespace
+
 struct Pool::Impl {
     std::vector<std::thread> th;
     std::mutex mu;
     std::condition_variable cv, done_cv;
     const std::function<void(size_t)> *fn = nullptr;
-    size_t n = 0, next = 0, pending = 0;
+    size_t n = 0, key0 = 0, pending = 0;
     uint64_t gen = 0;
     bool stop = false, busy = false;
-    void work() {
+    std::string desc;
+    void loop(unsigned me, unsigned nt) {
+        uint64_t seen = 0;
         for (;;) {
-            size_t i;
+            const std::function<void(size_t)> *f;
+            size_t cnt, k0;
             {
-                std::lock_guard<std::mutex> lk(mu);
-                if (!fn || next >= n) return;
-                i = next++;
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return stop || gen != seen; });
+                if (stop) return;
+                seen = gen;
+                f = fn;
+                cnt = n;
+                k0 = key0;
             }
-            (*fn)(i);
+            // my items: i with (k0 + i) % nt == me
+            size_t first = (me + nt - (k0 % nt)) % nt;
+            for (size_t i = first; i < cnt; i += nt) (*f)(i);
             bool last;
             {
                 std::lock_guard<std::mutex> lk(mu);
@@ -237,34 +284,44 @@ struct Pool::Impl {
             if (last) done_cv.notify_all();
         }
     }
-    void loop() {
-        uint64_t seen = 0;
-        for (;;) {
-            {
-                std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return stop || gen != seen; });
-                if (stop) return;
-                seen = gen;
-            }
-            work();
-        }
-    }
 };
 
-Pool &Pool::get() {
-    static Pool p;
+Pool &Pool::get(int node_hint) {
+    static Pool p(node_hint);
     return p;
 }
-unsigned Pool::size() const { return (unsigned)p_->th.size() + 1; }
+unsigned Pool::size() const { return (unsigned)p_->th.size(); }
+const char *Pool::describe() const { return p_->desc.c_str(); }
 
-Pool::Pool() : p_(new Impl()) {
+Pool::Pool(int node_hint) : p_(new Impl()) {
     unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    // several ranks of one host share its cores (torchrun sets LOCAL_WORLD_SIZE)
+    // several ranks of one host share its cores and its memory controllers (torchrun sets LOCAL_WORLD_SIZE)
     unsigned ranks = (unsigned)std::max(1, env_int("LOCAL_WORLD_SIZE", 1));
-    unsigned dflt = std::max(4u, std::min(32u, hw / ranks));
+    std::vector<std::vector<int>> nodes = numa_nodes();
+    const bool pin = env_int("CW_UNPACK_PIN", 1) != 0 && !nodes.empty();
+    std::vector<int> use;  // NUMA nodes the workers live on
+    if (pin) {
+        if (ranks > 1 && node_hint >= 0 && node_hint < (int)nodes.size()) use.push_back(node_hint);
+        else
+            for (size_t k = 0; k < nodes.size(); ++k) use.push_back((int)k);
+    }
+    unsigned dflt = std::max(4u, std::min(32u, hw / 2 / ranks));  // (physical cores: the second hyperthread adds no store bandwidth)
     unsigned nt = (unsigned)std::max(1, env_int("CW_UNPACK_THREADS", (int)dflt));
     nt = std::min(nt, hw);
-    for (unsigned i = 1; i < nt; ++i) p_->th.emplace_back([this] { p_->loop(); });
+    for (unsigned i = 0; i < nt; ++i) {
+        p_->th.emplace_back([this, i, nt] { p_->loop(i, nt); });
+        if (pin) {
+            const std::vector<int> &cpus = nodes[use[i % use.size()]];
+            cpu_set_t set;
+            CPU_ZERO(&set);
+            for (int c : cpus)
+                if (c < CPU_SETSIZE) CPU_SET(c, &set);
+            pthread_setaffinity_np(p_->th.back().native_handle(), sizeof(set), &set);
+        }
+    }
+    p_->desc = std::to_string(nt) + " threads" +
+               (pin ? ", pinned round robin to " + std::to_string(use.size()) + " of " + std::to_string(nodes.size()) + " NUMA nodes" : ", unpinned") +
+               ", static item -> thread map, " + expand_isa() + " stores";
 }
 Pool::~Pool() {
     {
@@ -276,7 +333,7 @@ Pool::~Pool() {
     delete p_;
 }
 
-void Pool::parallel_for(size_t n, const std::function<void(size_t)> &fn) {
+void Pool::parallel_for(size_t n, size_t key0, const std::function<void(size_t)> &fn) {
     if (n == 0) return;
     Impl &I = *p_;
     std::unique_lock<std::mutex> lk(I.mu);
@@ -284,12 +341,11 @@ void Pool::parallel_for(size_t n, const std::function<void(size_t)> &fn) {
     I.busy = true;
     I.fn = &fn;
     I.n = n;
-    I.next = 0;
-    I.pending = n;
+    I.key0 = key0;
+    I.pending = I.th.size();
     ++I.gen;
     lk.unlock();
     I.cv.notify_all();
-    I.work();
     lk.lock();
     I.done_cv.wait(lk, [&] { return I.pending == 0; });
     I.busy = false;

@@ -31,16 +31,23 @@ void build_pack_layout(const Tape &t, PackLayout &L);
 void expand_record(const PackLayout &L, const uint32_t *rec, uint64_t *row_out, int force_bits = 0);
 const char *expand_isa();  // "avx512" / "avx2" / "sse2": the store width expand_record uses on this CPU
 
-// persistent worker threads (created on first use, shared by all batches of the process)
+// Persistent worker threads (created on first use, shared by all batches of the process).  The expansion writes
+// 32 bytes per witness entry - tens of MB per instance - so it runs at the speed of the host's memory system and
+// placement decides that speed on a multi-socket host: the workers are pinned to NUMA nodes (round robin over the
+// nodes in use) and work items are assigned STATICALLY (item key -> worker), so that the rows of instance i of a
+// caller's buffer are always written by the same worker; the first pass places those pages on that worker's node
+// (first touch), every later pass over the same buffer writes node-local memory.
 class Pool {
   public:
-    static Pool &get();
+    // node_hint >= 0 with several ranks on the host (LOCAL_WORLD_SIZE > 1): all workers on that node (the GPU's)
+    static Pool &get(int node_hint = -1);
     unsigned size() const;
-    // runs fn(i) for i in [0, n) on the workers and the calling thread; returns when all are done
-    void parallel_for(size_t n, const std::function<void(size_t)> &fn);
+    // runs fn(i) for i in [0, n) on the workers, item i on worker (key0 + i) % size(); returns when all are done
+    void parallel_for(size_t n, size_t key0, const std::function<void(size_t)> &fn);
+    const char *describe() const;  // e.g. "32 threads over 2 NUMA nodes, static"
 
   private:
-    Pool();
+    explicit Pool(int node_hint);
     ~Pool();
     struct Impl;
     Impl *p_;

@@ -92,6 +92,7 @@ def _load() -> ctypes.CDLL:
         "cw_status_allreduce": (c_int, [P, P, POINTER(c_uint64)]),
         "cw_circuit_expand_record": (c_int, [P, c_void_p, c_void_p, c_int]),
         "cw_host_expand_isa": (c_char_p, []),
+        "cw_host_pool_info": (c_char_p, []),
         "cw_batch_witness_device": (c_int, [P, POINTER(c_void_p)]),
         "cw_batch_witness_strided": (c_int, [P, POINTER(c_void_p), POINTER(c_uint64)]),
         "cw_batch_stream": (c_void_p, [P]),

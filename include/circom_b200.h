@@ -162,6 +162,9 @@ int cw_circuit_pack_info(const cw_circuit *c, uint64_t info[5], uint32_t *entry)
  * has, or at most 128 / 256 / 512.  cw_host_expand_isa names what 0 selects ("avx512" / "avx2" / "sse2"). */
 int cw_circuit_expand_record(const cw_circuit *c, const uint32_t *record, uint64_t *rows, int store_bits);
 const char *cw_host_expand_isa(void);
+/* the worker threads of the expansion: count, NUMA pinning, store width (environment: CW_UNPACK_THREADS,
+ * CW_UNPACK_PIN=0, CW_EXPAND_ISA=128|256|512) */
+const char *cw_host_pool_info(void);
 /* bytes that crossed PCIe in the last cw_batch_get_witness (entries proven to be bits / 64-bit values travel
  * packed and are zero-extended on the host; CW_PACKED_D2H=0 disables) */
 uint64_t cw_batch_last_d2h_bytes(const cw_batch *b);

@@ -305,7 +305,8 @@ def workload_config(label, desc, batch, world, st=None):
     cfg = {"workload": label, "batch_per_gpu": batch, "global_batch": batch * world,
            "n_signals": desc.total_signals, "parallelism": "batch-sharded x%d" % world}
     if st:
-        cfg.update({"n_constraints": st["n_constraints"], "n_tape_ops": st["n_tape_ops"], "n_levels": st["n_levels"]})
+        cfg.update({"n_constraints": st["n_constraints"], "n_tape_ops": st["n_tape_ops"], "n_work_items": st["n_items"],
+                    "n_levels": st["n_levels"]})
     return cfg
 
 
@@ -416,7 +417,8 @@ def run_workload(ctx: Ctx, workload: str, batch: int, steps: int, warmup: int, e
             del b
             torch.cuda.empty_cache()
             pair = [Batch(circuit, chunk, dev), Batch(circuit, chunk, dev)]
-        outs = [np.empty((chunk, W, 4), dtype=np.uint64) for _ in range(2)]   # pageable: first touched by the workers
+        from circom_b200.witness_calculator import aligned_empty
+        outs = [aligned_empty((chunk, W, 4)) for _ in range(2)]   # pageable, 64-byte aligned: first touched by the workers
         pin_np = pin_in.numpy().view(np.uint64)
         n_chunks = (tot + chunk - 1) // chunk
         d2h = [0]
@@ -471,7 +473,7 @@ def run_workload(ctx: Ctx, workload: str, batch: int, steps: int, warmup: int, e
     exec_per_launch_ms = exec_ms / steps
     achieved = batch * b_wit / (exec_per_launch_ms / 1e3) / 1e9
     # bytes the kernel has to move in the layout it runs on: slot + plane writes, slot operand reads, tape words
-    layout_bytes = (32 * (st["n_tape_ops"]) + 4 * st["n_bitwords"]) + 32 * st["n_slot_operands"] + 32 * n_in
+    layout_bytes = (32 * (st["n_stored"]) + 4 * st["n_bitwords"]) + 32 * st["n_slot_operands"] + 32 * n_in
     res = {
         "metric": "witnesses/s", "value": wit_s, "unit": "witnesses/s", "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": exec_ms / steps, "higher_is_better": True, "scaling": "weak",

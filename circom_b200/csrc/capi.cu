@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
 #include <functional>
@@ -84,7 +85,7 @@ int ensure_device(int device) {
 
 struct DevTape {
     uint4 *ops = nullptr;
-    u32 *level_start = nullptr;
+    u32 *items = nullptr, *level_start = nullptr;
     uint4 *consts = nullptr;
     u32 *input_slot = nullptr, *fn_code = nullptr, *fn_info = nullptr, *call_tab = nullptr;
     u32 *wloc = nullptr;  // per witness entry: where its value lives (slot id, or OPD_BIT | plane position)
@@ -205,6 +206,7 @@ static int get_dev_tape(const cw_circuit *c, int device, DevTape &out) {
     DevTape d;
     int rc;
     if ((rc = upload(&d.ops, t.ops.data(), t.ops.size() * 4))) return rc;
+    if ((rc = upload(&d.items, t.items.data(), t.items.size() * 4))) return rc;
     if ((rc = upload(&d.level_start, t.level_start.data(), t.level_start.size() * 4))) return rc;
     if ((rc = upload(&d.consts, t.consts.data(), t.consts.size() * 32))) return rc;
     if ((rc = upload(&d.input_slot, t.input_slot.data(), t.input_slot.size() * 4))) return rc;
@@ -265,6 +267,7 @@ void cw_circuit_destroy(cw_circuit *c) {
     for (auto &kv : c->dev) {
         cudaSetDevice(kv.first);
         cudaFree(kv.second.ops);
+        cudaFree(kv.second.items);
         cudaFree(kv.second.level_start);
         cudaFree(kv.second.consts);
         cudaFree(kv.second.input_slot);
@@ -302,6 +305,8 @@ int cw_circuit_stats(const cw_circuit *c, cw_stats *o) {
     o->n_bitwords = t.n_bitwords;
     o->n_resident_slots = t.n_resident;
     o->n_values = t.n_values;
+    o->n_items = t.n_items();
+    o->n_stored = t.n_stored;
     return CW_OK;
 }
 
@@ -358,6 +363,12 @@ int cw_get_input_signal_id(const cw_circuit *c, uint64_t h, uint64_t *id) {
     return CW_OK;
 }
 
+int cw_circuit_tape_items(const cw_circuit *c, uint32_t *items) {
+    if (!c || !items) return fail(CW_EINVAL, "null argument");
+    memcpy(items, c->tape.items.data(), c->tape.items.size() * 4);
+    return CW_OK;
+}
+
 int cw_circuit_tape(const cw_circuit *c, uint32_t *ops, uint32_t *level_start, uint32_t *witness_slot) {
     const Tape &t = c->tape;
     if (ops) memcpy(ops, t.ops.data(), t.ops.size() * 4);
@@ -403,7 +414,7 @@ int cw_batch_create(const cw_circuit *c, uint32_t batch, int device, cw_batch **
     // along the ops of a level (one-instance tiles).  Tapes with function calls keep one-instance tiles (the
     // interpreter's frame is per thread and lanes diverge inside calls anyway).
     int bt = env_int("CW_BT_LOG2", -1);
-    const uint64_t avg_w = t.n_levels() ? t.n_tape_ops() / t.n_levels() + 1 : 1;
+    const uint64_t avg_w = t.n_levels() ? t.n_items() / t.n_levels() + 1 : 1;
     if (bt < 0) {
         bt = 0;
         if (t.call_tab.empty()) {
@@ -427,10 +438,10 @@ int cw_batch_create(const cw_circuit *c, uint32_t batch, int device, cw_batch **
         u32 tiles = b->batch_padded >> bt;
         u32 per_sm = (tiles + 147) / 148;
         while (th > 64 && (u32)th * per_sm > 1024) th >>= 1;
-        if (tiles < 148u) th = (int)std::min<uint64_t>(1024, std::max<uint64_t>(th, (avg + 31) / 32 * 32));  // few tiles: wide CTAs
+        if (tiles < 148u) th = (int)std::min<uint64_t>(CW_TAPE_LB, std::max<uint64_t>(th, (avg + 31) / 32 * 32));  // few tiles: wide CTAs
     }
     th = (th + 31) / 32 * 32;
-    if (th > 1024) th = 1024;
+    if (th > CW_TAPE_LB) th = CW_TAPE_LB;
     b->threads = (u32)th;
     size_t slot_bytes = (size_t)b->batch_padded * t.n_slots * 32;
     size_t plane_bytes = (size_t)b->batch_padded * t.n_bitwords * 4;
@@ -556,6 +567,7 @@ int cw_batch_run(cw_batch *b) {
     }
     TapeDev tp;
     tp.ops = b->dt.ops;
+    tp.items = b->dt.items;
     tp.level_start = b->dt.level_start;
     tp.consts = b->dt.consts;
     tp.n_levels = (u32)t.n_levels();
@@ -940,6 +952,35 @@ int cw_circuit_expand_record(const cw_circuit *c, const uint32_t *record, uint64
 }
 const char *cw_host_expand_isa(void) { return expand_isa(); }
 const char *cw_host_pool_info(void) { return Pool::get().describe(); }
+
+// Host-side probe (no GPU): the expansion of `n_inst` packed records (all zero) into a freshly allocated row buffer on
+// the worker pool, `reps` passes over the same buffer; mode 0 = expand_record, 1 = plain streaming fill of the same
+// bytes (the memory system's ceiling for this access pattern), 2 = memset.  gbps[r] = bytes of rows written / time.
+int cw_host_expand_bench(const cw_circuit *c, uint32_t n_inst, uint32_t reps, int mode, double *gbps) {
+    if (!c || !gbps || !n_inst || !reps) return fail(CW_EINVAL, "bad argument");
+    const PackLayout &L = c->pack_layout();
+    const size_t W = c->tape.n_witness, row_bytes = W * 32;
+    uint64_t *out = (uint64_t *)aligned_alloc(64, ((size_t)n_inst * row_bytes + 63) & ~(size_t)63);
+    if (!out) return fail(CW_EINVAL, "out of host memory");
+    std::vector<uint32_t> rec(L.words, 0);
+    Pool &pool = Pool::get();
+    for (uint32_t r = 0; r < reps; ++r) {
+        auto t0 = std::chrono::steady_clock::now();
+        pool.parallel_for(n_inst, 0, [&](size_t i) {
+            uint64_t *dst = out + i * W * 4;
+            if (mode == 0) expand_record(L, rec.data(), dst);
+            else if (mode == 1) {
+                const __m128i z = _mm_setzero_si128();
+                for (size_t k = 0; k < W * 2; ++k) _mm_stream_si128((__m128i *)dst + k, z);
+                _mm_sfence();
+            } else memset(dst, 0, row_bytes);
+        });
+        double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        gbps[r] = (double)n_inst * row_bytes / dt / 1e9;
+    }
+    free(out);
+    return CW_OK;
+}
 
 // ---- R1CS -------------------------------------------------------------------------------------
 int cw_r1cs_from_circuit(const cw_circuit *c, cw_r1cs **out) {

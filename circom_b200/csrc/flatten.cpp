@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <stdexcept>
 #include <unordered_map>
 
@@ -121,6 +122,21 @@ inline bool c_is_immediate(uint32_t opcode) {
 }
 inline bool is_assert_op(uint32_t opcode) {
     return opcode == CW_OP_ASSERT || opcode == CW_OP_ASSERT_EQ || opcode == DOP_ASSERT_BOOL || opcode == DOP_ASSERT_FITS;
+}
+
+inline size_t n_live_ops(const std::vector<uint8_t> &live, uint32_t n_pre, size_t n_prov) {
+    size_t n = 0;
+    for (size_t i = 0; i < n_prov; ++i) n += live[n_pre + i];
+    return n;
+}
+// accumulators a fused sub-tree needs while it is evaluated (1: a chain)
+inline int subtree_need(uint32_t i, const std::vector<uint32_t> &kid_a, const std::vector<uint32_t> &kid_b) {
+    const uint32_t a = kid_a[i], b = kid_b[i];
+    if (a == NO_SLOT && b == NO_SLOT) return 1;
+    if (a == NO_SLOT) return subtree_need(b, kid_a, kid_b);
+    if (b == NO_SLOT) return subtree_need(a, kid_a, kid_b);
+    const int na = subtree_need(a, kid_a, kid_b), nb = subtree_need(b, kid_a, kid_b);
+    return std::max(std::max(na, nb), std::min(na, nb) + 1);
 }
 
 struct Lowerer {
@@ -1044,22 +1060,132 @@ struct Lowerer {
                 if (o[k] != NO_SLOT && !(o[k] & OPERAND_CONST)) live[o[k]] = 1;
             }
         }
-        // sort by (level, opcode)
-        uint32_t max_level = 0;
-        size_t n_live = 0;
-        for (size_t i = 0; i < n_prov; ++i)
-            if (live[n_pre + i]) {
-                ++n_live;
-                max_level = std::max(max_level, slot_level[n_pre + i]);
+        // ---- op fusion ---------------------------------------------------------------------------------------
+        // 70 % of the values of circom programs are read exactly once, by the next operation of the same
+        // expression (`acc + a[i]*b[j]`, `(s >> 64) - OFF`, the trees of `+` the DSL builds).  Writing each of them
+        // to the value store and reading it back costs two memory round trips and a level of the DAG per operator.
+        // A value with ONE reader that is not a witness entry is therefore *fused* into its reader: the work item of
+        // the reader first evaluates the producer(s) into one of two accumulator registers.  Trees are evaluated in
+        // post order with at most two live accumulators (deeper sub-tree first; a second fused operand may only be a
+        // chain), at most FUSE_MAX operators per work item.  The DAG gets shallower (levels are recomputed over the
+        // groups) and narrower in memory traffic; each group still writes exactly one value (its root's).
+        constexpr uint32_t FUSE_MAX = 24;
+        std::vector<uint8_t> fusedf(n_prov, 0);          // op is evaluated inside its reader's work item
+        std::vector<uint32_t> kid_a(n_prov, NO_SLOT), kid_b(n_prov, NO_SLOT);  // fused producers of operands a / b (op index)
+        {
+            std::vector<uint32_t> uses(n_pre + n_prov, 0), cons(n_pre + n_prov, NO_SLOT);
+            std::vector<uint8_t> cons_pos(n_pre + n_prov, 0);
+            for (size_t i = 0; i < n_prov; ++i) {
+                if (!live[n_pre + i]) continue;
+                const uint32_t *o = &pops[i * 4];
+                if (o[0] == 45) {
+                    uint32_t n = pcalls[o[1] + 1];
+                    for (uint32_t k = 0; k < n; ++k) {
+                        uint32_t x = pcalls[o[1] + 2 + k];
+                        if (!(x & OPERAND_CONST)) uses[x] += 2;  // call arguments are read through the call table
+                    }
+                    continue;
+                }
+                for (int k = 1; k <= 3; ++k) {
+                    if (k == 3 && c_is_immediate(o[0])) break;
+                    if (o[k] == NO_SLOT || (o[k] & OPERAND_CONST)) continue;
+                    ++uses[o[k]];
+                    cons[o[k]] = (uint32_t)i;
+                    cons_pos[o[k]] = (uint8_t)k;
+                }
             }
+            std::vector<uint8_t> need(n_prov, 1);
+            std::vector<uint32_t> gsize(n_prov, 1);
+            const bool fuse_on = !(flags & (CW_FLAG_NO_FUSE | CW_FLAG_NO_PEEPHOLE));
+            auto candidate = [&](uint32_t slot, size_t reader, int pos) -> bool {
+                if (!fuse_on || slot == NO_SLOT || (slot & OPERAND_CONST) || slot < n_pre) return false;
+                const size_t c = slot - n_pre;
+                const uint32_t opc = pops[c * 4];
+                if (uses[slot] != 1 || cons[slot] != reader || cons_pos[slot] != pos || claimed[slot] >= 0) return false;
+                if (is_assert_op(opc) || opc == 45 || opc == DOP_BITS || opc == CW_OP_COPY) return false;
+                return true;
+            };
+            for (size_t i = 0; i < n_prov; ++i) {
+                if (!live[n_pre + i]) continue;
+                const uint32_t *o = &pops[i * 4];
+                if (o[0] == 45) continue;
+                uint32_t ka = candidate(o[1], i, 1) ? o[1] - n_pre : NO_SLOT;
+                uint32_t kb = candidate(o[2], i, 2) ? o[2] - n_pre : NO_SLOT;
+                if (ka != NO_SLOT && kb != NO_SLOT) {
+                    // two fused operands: the shallower one must be a chain (one accumulator)
+                    uint32_t deep = need[ka] >= need[kb] ? ka : kb, other = deep == ka ? kb : ka;
+                    if (need[other] > 1 || gsize[ka] + gsize[kb] + 1 > FUSE_MAX) {
+                        // keep the larger tree, give the other its own work item
+                        uint32_t drop = gsize[ka] >= gsize[kb] ? kb : ka;
+                        if (need[other] > 1) drop = other;
+                        if (drop == ka) ka = NO_SLOT; else kb = NO_SLOT;
+                    }
+                }
+                if (ka != NO_SLOT && kb == NO_SLOT && gsize[ka] + 1 > FUSE_MAX) ka = NO_SLOT;
+                if (kb != NO_SLOT && ka == NO_SLOT && gsize[kb] + 1 > FUSE_MAX) kb = NO_SLOT;
+                kid_a[i] = ka;
+                kid_b[i] = kb;
+                uint32_t sz = 1;
+                uint8_t nd = 1;
+                if (ka != NO_SLOT && kb != NO_SLOT) {
+                    sz += gsize[ka] + gsize[kb];
+                    nd = (uint8_t)std::max<int>(std::max(need[ka], need[kb]), std::min(need[ka], need[kb]) + 1);
+                } else if (ka != NO_SLOT) { sz += gsize[ka]; nd = need[ka]; }
+                else if (kb != NO_SLOT) { sz += gsize[kb]; nd = need[kb]; }
+                gsize[i] = sz;
+                need[i] = nd;
+                if (ka != NO_SLOT) fusedf[ka] = 1;
+                if (kb != NO_SLOT) fusedf[kb] = 1;
+            }
+        }
+        // levels over the groups (a group reads the external operands of all its operators, writes its root's value)
+        std::vector<uint32_t> glevel(n_pre + n_prov, 0);  // per provisional slot: level of the group that writes it
+        std::vector<uint64_t> gsig(n_prov, 0);            // structure of the group's tree (orders similar work items together)
+        uint32_t max_level = 0;
+        size_t n_roots = 0;
+        {
+            std::vector<uint32_t> ext(n_prov, 0);  // highest level among the external operands of the sub-tree
+            for (size_t i = 0; i < n_prov; ++i) {
+                if (!live[n_pre + i]) continue;
+                const uint32_t *o = &pops[i * 4];
+                uint32_t e = 0;
+                uint64_t sg = 1469598103934665603ull ^ o[0];
+                if (o[0] == 45) {
+                    uint32_t n = pcalls[o[1] + 1];
+                    for (uint32_t k = 0; k < n; ++k) {
+                        uint32_t x = pcalls[o[1] + 2 + k];
+                        if (!(x & OPERAND_CONST)) e = std::max(e, glevel[x]);
+                    }
+                } else {
+                    for (int k = 1; k <= 3; ++k) {
+                        if (k == 3 && c_is_immediate(o[0])) break;
+                        if (o[k] == NO_SLOT || (o[k] & OPERAND_CONST)) continue;
+                        const uint32_t kid = k == 1 ? kid_a[i] : k == 2 ? kid_b[i] : NO_SLOT;
+                        if (kid != NO_SLOT) {
+                            e = std::max(e, ext[kid]);
+                            sg = (sg * 1099511628211ull) ^ gsig[kid] ^ (uint64_t)k;
+                        } else e = std::max(e, glevel[o[k]]);
+                    }
+                }
+                ext[i] = e;
+                gsig[i] = sg * 1099511628211ull;
+                if (!fusedf[i]) {
+                    glevel[n_pre + i] = e + 1;
+                    max_level = std::max(max_level, e + 1);
+                    ++n_roots;
+                }
+            }
+        }
+        // work items = group roots, sorted by (level, root opcode, tree structure)
         std::vector<uint32_t> order;
-        order.reserve(n_live);
+        order.reserve(n_roots);
         for (size_t i = 0; i < n_prov; ++i)
-            if (live[n_pre + i]) order.push_back((uint32_t)i);
+            if (live[n_pre + i] && !fusedf[i]) order.push_back((uint32_t)i);
         std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
-            uint32_t lx = slot_level[n_pre + x], ly = slot_level[n_pre + y];
+            uint32_t lx = glevel[n_pre + x], ly = glevel[n_pre + y];
             if (lx != ly) return lx < ly;
-            return pops[x * 4] < pops[y * 4];
+            if (pops[x * 4] != pops[y * 4]) return pops[x * 4] < pops[y * 4];
+            return gsig[x] < gsig[y];
         });
         // final slots: witness entries first (slot = witness index), other values after them in tape order
         std::vector<uint32_t> remap(n_pre + n_prov, NO_SLOT);
@@ -1073,18 +1199,18 @@ struct Lowerer {
             if (claimed[p] >= 0) remap[p] = (uint32_t)claimed[p];
             else if (!is_assert_op(pops[(size_t)order[r] * 4])) remap[p] = next_tmp++;
         }
-        if (next_tmp >= (1u << 24)) throw std::runtime_error("circuit too large for the packed tape word (2^24 slots)");
+        if (next_tmp >= DST_ACC) throw std::runtime_error("circuit too large for the packed tape word (2^24 slots)");
         T.ops.clear();
-        T.ops.reserve(n_live * 4);
+        T.ops.reserve(n_live_ops(live, n_pre, n_prov) * 4);
+        T.items.clear();
+        T.items.reserve(n_roots + 1);
         T.level_start.assign(max_level + 1, 0);
         T.n_mul_ops = 0;
         uint32_t prev_level = 0;
-        for (size_t r = 0; r < order.size(); ++r) {
-            const uint32_t *o = &pops[(size_t)order[r] * 4];
-            const uint32_t lvl = slot_level[n_pre + order[r]];
-            uint32_t d[4];
-            uint32_t dst = is_assert_op(o[0]) ? 0u : remap[n_pre + order[r]];
-            d[0] = o[0] | (dst << 8);  // opcode in bits 0-7, destination slot in bits 8-31
+        // one operator as a tape word; operands that are fused producers read an accumulator
+        auto word = [&](uint32_t i, uint32_t dstfield, int acc_a, int acc_b, uint32_t d[4]) {
+            const uint32_t *o = &pops[(size_t)i * 4];
+            d[0] = o[0] | (dstfield << 8);  // opcode in bits 0-7, destination in bits 8-31
             if (o[0] == 45) {
                 uint32_t n = pcalls[o[1] + 1];
                 d[1] = (uint32_t)T.call_tab.size();
@@ -1095,33 +1221,81 @@ struct Lowerer {
                     uint32_t a = pcalls[o[1] + 2 + k];
                     T.call_tab.push_back((a & OPERAND_CONST) ? a : remap[a]);
                 }
-            } else {
-                for (int k = 1; k <= 3; ++k) {
-                    if (k == 3 && c_is_immediate(o[0])) d[k] = o[k];  // immediate: IR assert number / bit-field spec
-                    else if (o[k] == NO_SLOT) d[k] = OPERAND_CONST;  // unused operand: constant 0 (never read for its value)
-                    else if (o[k] & OPERAND_CONST) d[k] = o[k];
-                    else d[k] = remap[o[k]];
-                }
+                return;
             }
-            // runs of single-bit extractions of one source into consecutive slots (the bits of a decomposition
-            // are consecutive witness entries) become ONE tape op that writes the whole run: imm bits 24-31 hold
-            // (run length - 1).  One thread fetches the source word once; the run (up to 32 slots) is stored by the whole warp, lane j writing bit j.
-            if (o[0] == DOP_BITS && !(flags & CW_FLAG_NO_PEEPHOLE) && lvl == prev_level && !T.ops.empty()) {
-                uint32_t *p = &T.ops[T.ops.size() - 4];
-                if ((p[0] & 0xFFu) == DOP_BITS && p[1] == d[1] && ((p[3] >> 16) & 0xFFu) == 1u && ((d[3] >> 16) & 0xFFu) == 1u) {
-                    uint32_t cnt = (p[3] >> 24) + 1u, pk = p[3] & 0xFFFFu, pdst = p[0] >> 8;
-                    if (cnt < 32u && (d[3] & 0xFFFFu) == pk + cnt && dst == pdst + cnt) {
-                        p[3] += 1u << 24;
-                        continue;
+            for (int k = 1; k <= 3; ++k) {
+                if (k == 3 && c_is_immediate(o[0])) d[k] = o[k];  // immediate: IR assert number / bit-field spec
+                else if (o[k] == NO_SLOT) d[k] = OPERAND_CONST;  // unused operand: constant 0 (never read for its value)
+                else if (o[k] & OPERAND_CONST) d[k] = o[k];
+                else if (k == 1 && acc_a >= 0) d[k] = OPERAND_ACC | (uint32_t)acc_a;
+                else if (k == 2 && acc_b >= 0) d[k] = OPERAND_ACC | (uint32_t)acc_b;
+                else d[k] = remap[o[k]];
+            }
+        };
+        // post-order emission of a fused sub-tree; its value ends in accumulator `target`
+        std::function<void(uint32_t, int)> emit_sub = [&](uint32_t i, int target) {
+            const uint32_t ka = kid_a[i], kb = kid_b[i];
+            int acc_a = -1, acc_b = -1;
+            if (ka != NO_SLOT && kb != NO_SLOT) {
+                // the deeper sub-tree first (it may use both accumulators), then the chain into the other one
+                const bool a_first = subtree_need(ka, kid_a, kid_b) >= subtree_need(kb, kid_a, kid_b);
+                if (a_first) { emit_sub(ka, target); emit_sub(kb, target ^ 1); }
+                else { emit_sub(kb, target); emit_sub(ka, target ^ 1); }
+                acc_a = a_first ? target : (target ^ 1);
+                acc_b = a_first ? (target ^ 1) : target;
+            } else if (ka != NO_SLOT) { emit_sub(ka, target); acc_a = target; }
+            else if (kb != NO_SLOT) { emit_sub(kb, target); acc_b = target; }
+            uint32_t d[4];
+            word(i, DST_ACC + (uint32_t)target, acc_a, acc_b, d);
+            T.ops.insert(T.ops.end(), d, d + 4);
+            if (pops[(size_t)i * 4] == CW_OP_MUL) ++T.n_mul_ops;
+        };
+        for (size_t r = 0; r < order.size(); ++r) {
+            const uint32_t i = order[r];
+            const uint32_t *o = &pops[(size_t)i * 4];
+            const uint32_t lvl = glevel[n_pre + i];
+            const uint32_t dst = is_assert_op(o[0]) ? 0u : remap[n_pre + i];
+            const uint32_t ka = kid_a[i], kb = kid_b[i];
+            const bool single = ka == NO_SLOT && kb == NO_SLOT;
+            uint32_t d[4];
+            if (single) {
+                word(i, dst, -1, -1, d);
+                // runs of single-bit extractions of one source into consecutive slots (the bits of a decomposition
+                // are consecutive witness entries) become ONE tape op that writes the whole run: imm bits 24-31 hold
+                // (run length - 1).  One thread fetches the source word once.
+                if (o[0] == DOP_BITS && !(flags & CW_FLAG_NO_PEEPHOLE) && lvl == prev_level && !T.ops.empty() &&
+                    T.items.back() == T.ops.size() / 4 - 1) {
+                    uint32_t *p = &T.ops[T.ops.size() - 4];
+                    if ((p[0] & 0xFFu) == DOP_BITS && p[1] == d[1] && ((p[3] >> 16) & 0xFFu) == 1u && ((d[3] >> 16) & 0xFFu) == 1u) {
+                        uint32_t cnt = (p[3] >> 24) + 1u, pk = p[3] & 0xFFFFu, pdst = p[0] >> 8;
+                        if (cnt < 32u && (d[3] & 0xFFFFu) == pk + cnt && dst == pdst + cnt) {
+                            p[3] += 1u << 24;
+                            continue;
+                        }
                     }
                 }
+                T.items.push_back((uint32_t)(T.ops.size() / 4));
+                T.ops.insert(T.ops.end(), d, d + 4);
+            } else {
+                T.items.push_back((uint32_t)(T.ops.size() / 4));
+                int acc_a = -1, acc_b = -1;
+                if (ka != NO_SLOT && kb != NO_SLOT) {
+                    const bool a_first = subtree_need(ka, kid_a, kid_b) >= subtree_need(kb, kid_a, kid_b);
+                    if (a_first) { emit_sub(ka, 0); emit_sub(kb, 1); }
+                    else { emit_sub(kb, 0); emit_sub(ka, 1); }
+                    acc_a = a_first ? 0 : 1;
+                    acc_b = a_first ? 1 : 0;
+                } else if (ka != NO_SLOT) { emit_sub(ka, 0); acc_a = 0; }
+                else { emit_sub(kb, 0); acc_b = 0; }
+                word(i, dst, acc_a, acc_b, d);
+                T.ops.insert(T.ops.end(), d, d + 4);
             }
             prev_level = lvl;
-            T.ops.insert(T.ops.end(), d, d + 4);
             if (o[0] == CW_OP_MUL) ++T.n_mul_ops;
-            T.level_start[lvl]++;  // count per level (levels start at 1)
+            T.level_start[lvl]++;  // work items per level (levels start at 1)
         }
-        // prefix sums: level_start[l-1] = first op of level l
+        T.items.push_back((uint32_t)(T.ops.size() / 4));
+        // prefix sums: level_start[l-1] = first work item of level l
         {
             std::vector<uint32_t> ls(max_level + 1, 0);
             uint32_t acc = 0;
@@ -1170,11 +1344,11 @@ struct Lowerer {
                     uint32_t *o = &T.ops[i * 4];
                     const uint32_t opc = o[0] & 0xFFu;
                     if (opc == DOP_BITS && (o[3] >> 24)) o[0] = opc | (word++ << 8);        // destination = bit-plane word
-                    else if (!is_assert_op(opc)) o[0] = opc | (newid[o[0] >> 8] << 8);
+                    else if (!is_assert_op(opc) && (o[0] >> 8) < DST_ACC) o[0] = opc | (newid[o[0] >> 8] << 8);
                     if (opc == 45) continue;  // operand a is the call-table offset; the table is renumbered below
                     for (int k = 1; k <= 3; ++k) {
                         if (k == 3 && c_is_immediate(opc)) break;
-                        if (!(o[k] & OPERAND_CONST)) o[k] = newid[o[k]];
+                        if (!(o[k] & (OPERAND_CONST | OPERAND_ACC))) o[k] = newid[o[k]];
                     }
                 }
                 for (size_t i = 0; i < T.call_tab.size();) {  // {function, n_args, operands...}
@@ -1201,9 +1375,9 @@ struct Lowerer {
             const size_t n_ops = T.ops.size() / 4;
             const size_t n_lv = T.level_start.size() - 1;
             std::vector<uint32_t> last(next_tmp, 0), phys(next_tmp, NO_SLOT);
-            auto is_tmp = [&](uint32_t o) { return !(o & (OPERAND_CONST | OPERAND_BIT)) && o >= n_resident; };
+            auto is_tmp = [&](uint32_t o) { return !(o & (OPERAND_CONST | OPERAND_BIT | OPERAND_ACC)) && o >= n_resident; };
             for (size_t l = 0; l < n_lv; ++l)
-                for (uint32_t i = T.level_start[l]; i < T.level_start[l + 1]; ++i) {
+                for (uint32_t i = T.items[T.level_start[l]]; i < T.items[T.level_start[l + 1]]; ++i) {
                     const uint32_t *o = &T.ops[(size_t)i * 4];
                     const uint32_t opc = o[0] & 0xFFu;
                     if (opc == 45) {
@@ -1222,10 +1396,10 @@ struct Lowerer {
             uint32_t next_phys = n_resident;
             for (size_t l = 0; l < n_lv; ++l) {
                 for (uint32_t p : release[l]) free_ids.push_back(p);
-                for (uint32_t i = T.level_start[l]; i < T.level_start[l + 1]; ++i) {
+                for (uint32_t i = T.items[T.level_start[l]]; i < T.items[T.level_start[l + 1]]; ++i) {
                     uint32_t *o = &T.ops[(size_t)i * 4];
                     const uint32_t opc = o[0] & 0xFFu, d = o[0] >> 8;
-                    if (is_assert_op(opc)) continue;
+                    if (is_assert_op(opc) || d >= DST_ACC) continue;
                     const uint32_t run = opc == DOP_BITS ? (o[3] >> 24) + 1u : 1u;
                     if (run > 1) {
                         if (T.n_bitwords || d < n_resident) continue;  // a word of the bit plane / witness entries
@@ -1246,7 +1420,8 @@ struct Lowerer {
             for (size_t i = 0; i < n_ops; ++i) {
                 uint32_t *o = &T.ops[i * 4];
                 const uint32_t opc = o[0] & 0xFFu;
-                if (!is_assert_op(opc) && !(opc == DOP_BITS && (o[3] >> 24) && T.n_bitwords) && (o[0] >> 8) >= n_resident)
+                if (!is_assert_op(opc) && !(opc == DOP_BITS && (o[3] >> 24) && T.n_bitwords) && (o[0] >> 8) >= n_resident &&
+                    (o[0] >> 8) < DST_ACC)
                     o[0] = opc | (phys[o[0] >> 8] << 8);
                 if (opc == 45) continue;
                 for (int k = 1; k <= 3; ++k) {
@@ -1265,15 +1440,17 @@ struct Lowerer {
         {   // operand statistics
             T.n_slot_operands = 0;
             T.n_values = 0;
+            T.n_stored = 0;
             const size_t n_ops = T.ops.size() / 4;
             for (size_t i = 0; i < n_ops; ++i) {
                 const uint32_t *o = &T.ops[i * 4];
                 const uint32_t opc = o[0] & 0xFFu;
-                if (!is_assert_op(opc)) T.n_values += opc == DOP_BITS ? (o[3] >> 24) + 1u : 1u;
+                if (!is_assert_op(opc)) T.n_values += opc == DOP_BITS ? (o[3] >> 24) + 1u : 1u;  // (fused values included: S_w of 8(d))
+                if (!is_assert_op(opc) && (o[0] >> 8) < DST_ACC) ++T.n_stored;
                 if (opc == 45) continue;
                 for (int k = 1; k <= 3; ++k) {
                     if (k == 3 && c_is_immediate(opc)) break;
-                    if (!(o[k] & (OPERAND_CONST | OPERAND_BIT))) ++T.n_slot_operands;
+                    if (!(o[k] & (OPERAND_CONST | OPERAND_BIT | OPERAND_ACC))) ++T.n_slot_operands;
                 }
             }
         }
@@ -1363,7 +1540,7 @@ struct BlobR {
         p += n;
     }
 };
-constexpr uint32_t BLOB_VERSION = 2;
+constexpr uint32_t BLOB_VERSION = 3;
 }  // namespace
 
 void serialize_tape(const Tape &t, std::vector<uint8_t> &out) {
@@ -1375,10 +1552,10 @@ void serialize_tape(const Tape &t, std::vector<uint8_t> &out) {
     const uint64_t nums[] = {t.n_signals, t.n_witness, t.n_inputs, t.n_outputs, t.n_components, t.n_ir_ops, t.n_mul_ops,
                              t.n_conv_ops, t.max_level_width, t.n_asserts, t.slot_census[0], t.slot_census[1],
                              t.slot_census[2], t.slot_census[3], t.n_slot_operands, t.n_values, t.n_resident, t.n_pre,
-                             t.n_slots, t.n_bitwords};
+                             t.n_slots, t.n_bitwords, t.n_stored};
     w.pod<uint64_t>(sizeof(nums) / 8);
     w.raw(nums, sizeof(nums));
-    w.vec(t.ops); w.vec(t.level_start); w.vec(t.consts); w.vec(t.witness_slot); w.vec(t.input_slot);
+    w.vec(t.ops); w.vec(t.items); w.vec(t.level_start); w.vec(t.consts); w.vec(t.witness_slot); w.vec(t.input_slot);
     w.vec(t.pk_bit_wire); w.vec(t.pk_u64_wire); w.vec(t.pk_full_wire); w.vec(t.wit_class);
     w.vec(t.fn_code); w.vec(t.fn_info); w.vec(t.call_tab); w.vec(t.witness2signal);
     w.pod<uint64_t>(t.inputs.size());
@@ -1408,15 +1585,15 @@ void deserialize_tape(const uint8_t *data, size_t len, Tape &t) {
     r.pod(t.flags);
     uint64_t n_nums;
     r.pod(n_nums);
-    uint64_t nums[20];
-    if (n_nums != 20) throw std::runtime_error("lowered-circuit blob: layout mismatch");
+    uint64_t nums[21];
+    if (n_nums != 21) throw std::runtime_error("lowered-circuit blob: layout mismatch");
     r.raw(nums, sizeof(nums));
     t.n_signals = nums[0]; t.n_witness = nums[1]; t.n_inputs = nums[2]; t.n_outputs = nums[3]; t.n_components = nums[4];
     t.n_ir_ops = nums[5]; t.n_mul_ops = nums[6]; t.n_conv_ops = nums[7]; t.max_level_width = nums[8]; t.n_asserts = nums[9];
     for (int k = 0; k < 4; ++k) t.slot_census[k] = nums[10 + k];
     t.n_slot_operands = nums[14]; t.n_values = nums[15]; t.n_resident = (uint32_t)nums[16]; t.n_pre = (uint32_t)nums[17];
-    t.n_slots = (uint32_t)nums[18]; t.n_bitwords = (uint32_t)nums[19];
-    r.vec(t.ops); r.vec(t.level_start); r.vec(t.consts); r.vec(t.witness_slot); r.vec(t.input_slot);
+    t.n_slots = (uint32_t)nums[18]; t.n_bitwords = (uint32_t)nums[19]; t.n_stored = nums[20];
+    r.vec(t.ops); r.vec(t.items); r.vec(t.level_start); r.vec(t.consts); r.vec(t.witness_slot); r.vec(t.input_slot);
     r.vec(t.pk_bit_wire); r.vec(t.pk_u64_wire); r.vec(t.pk_full_wire); r.vec(t.wit_class);
     r.vec(t.fn_code); r.vec(t.fn_info); r.vec(t.call_tab); r.vec(t.witness2signal);
     uint64_t n_in;
@@ -1437,7 +1614,8 @@ void deserialize_tape(const uint8_t *data, size_t len, Tape &t) {
     r.pod(R.n_pub_out); r.pod(R.n_pub_in); r.pod(R.n_prv_in);
     // consistency of what the kernels index with (the blob comes from another rank of the same job, not from a user,
     // but a short read or a version skew must not turn into out-of-bounds device accesses)
-    if (t.ops.size() % 4 || t.level_start.empty() || t.level_start.back() != t.ops.size() / 4 ||
+    if (t.ops.size() % 4 || t.level_start.empty() || t.items.empty() || t.level_start.back() != t.items.size() - 1 ||
+        t.items.back() != t.ops.size() / 4 ||
         t.witness_slot.size() != t.n_witness || t.input_slot.size() != t.n_inputs || t.wit_class.size() != t.n_witness ||
         t.witness2signal.size() != t.n_witness || R.row_ptr.size() != 3 * R.n_constraints + 1 || R.col.size() != R.coef.size() ||
         (R.row_ptr.size() && R.row_ptr.back() != R.col.size()) || t.hashmap.empty())

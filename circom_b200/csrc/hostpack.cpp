@@ -211,6 +211,9 @@ void expand_record(const PackLayout &L, const uint32_t *rec, uint64_t *row_out, 
     if (g_isa < 0) g_isa = pick_isa();
     int isa = g_isa;
     if (force_bits) isa = std::min(g_isa, force_bits >= 512 ? 2 : force_bits >= 256 ? 1 : 0);  // never above what the CPU has
+    // streaming (non-temporal) stores need their natural alignment: rows that are 16- but not 32-byte aligned (a
+    // malloc'ed caller buffer) take the 128-bit path, which still streams; unaligned rows fall back to plain stores
+    if ((((uintptr_t)row_out) & 31u) != 0) isa = 0;
     if (isa == 2) expand_avx512(L, rec, row_out);
     else if (isa == 1) expand_avx2(L, rec, row_out);
     else expand_sse2(L, rec, row_out);

@@ -64,7 +64,8 @@ __device__ __forceinline__ void load_const(u32 *v, const uint4 *__restrict__ con
     v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
     v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
 }
-constexpr u32 OPD_CONST = 0x80000000u, OPD_BIT = 0x20000000u, OPD_SLOT = 0x00FFFFFFu, OPD_BITPOS = 0x1FFFFFFFu;
+constexpr u32 OPD_CONST = 0x80000000u, OPD_BIT = 0x20000000u, OPD_ACC = 0x10000000u, OPD_SLOT = 0x00FFFFFFu, OPD_BITPOS = 0x1FFFFFFFu;
+constexpr u32 DST_ACC_DEV = 0x00FFFFFEu;  // destination field: accumulator 0 / 1 of a fused work item (tape.h DST_ACC)
 
 // ---- the bit plane (CW_FLAG_BITPLANE) ----------------------------------------------------------------
 // Bits produced by bit runs (the outputs of Num2Bits-style decompositions: most of the witness of limb
@@ -97,8 +98,9 @@ __device__ __forceinline__ u32 u256_bitlen_dev(const u32 *a) {
 }
 
 struct TapeDev {
-    const uint4 *ops;          // {opcode, a, b, c}
-    const u32 *level_start;    // n_levels + 1
+    const uint4 *ops;          // {opcode | dst << 8, a, b, c}
+    const u32 *items;          // n_items + 1: work item k = tape words [items[k], items[k+1]) evaluated by one thread
+    const u32 *level_start;    // n_levels + 1, indexes work items
     const uint4 *consts;       // 2 per constant
     const u32 *input_slot;     // slot of main input k
     const u32 *fn_code;        // register-machine code of the circuit's functions (5 words per instruction)
@@ -167,7 +169,7 @@ __device__ __noinline__ void exec_call(const TapeDev &tp, u32 call_off, const ui
 // frame); tapes without calls - all circuits whose hints are straight-line - use the lean build.
 // BP: the tape was lowered with a bit plane (bit runs write plane words, operands may be plane bits).
 #ifndef CW_TAPE_LB
-#define CW_TAPE_LB 1024
+#define CW_TAPE_LB 512  // widest CTA of the interpreter (cw_batch_create clamps to it); with MINB it bounds the registers
 #endif
 #ifndef CW_TAPE_MINB
 #define CW_TAPE_MINB 1
@@ -187,10 +189,15 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
     u32 *plane_base = BP ? plane + (((size_t)tile * tp.n_bitwords) << bt_log2) : nullptr;
     u32 lb = tp.level_start[0];
     u32 le = tp.n_levels ? tp.level_start[1] : lb;
-    // the tape word of a thread's first work item of the next level is fetched before the barrier of the
-    // current one, taking one memory round trip off the per-level critical path
+    // the first tape word of a thread's first work item of the next level is fetched before the barrier of the
+    // current one, taking the memory round trips of the item table and the tape off the per-level critical path
     uint4 pre = make_uint4(0, 0, 0, 0);
-    if (threadIdx.x < ((le - lb) << bt_log2)) pre = __ldg(&tp.ops[lb + (threadIdx.x >> bt_log2)]);
+    u32 pre_g0 = 0, pre_g1 = 0;
+    if (threadIdx.x < ((le - lb) << bt_log2)) {
+        pre_g0 = __ldg(&tp.items[lb + (threadIdx.x >> bt_log2)]);
+        pre_g1 = __ldg(&tp.items[lb + (threadIdx.x >> bt_log2) + 1]);
+        pre = __ldg(&tp.ops[pre_g0]);
+    }
     for (u32 l = 0; l < tp.n_levels; ++l) {
         const u32 n = (le - lb) << bt_log2;
         const u32 le_next = (l + 1 < tp.n_levels) ? tp.level_start[l + 2] : le;
@@ -199,21 +206,27 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
         for (u32 w0 = COOP ? (threadIdx.x & ~31u) : threadIdx.x; w0 < n; w0 += blockDim.x) {
             const u32 w = COOP ? w0 + (threadIdx.x & 31u) : w0;
             u32 run_dst = 0, run_n = 0, run_bits = 0;
-            if (!COOP || w < n) do {
-            const u32 oi = lb + (w >> bt_log2);
+            if (!COOP || w < n) {
             const u32 li = w & bt_mask;
-            const uint4 opw = (w == threadIdx.x) ? pre : __ldg(&tp.ops[oi]);
-            const u32 opcode = opw.x & 0xFFu, dst = opw.x >> 8;
             const u32 inst = (tile << bt_log2) + li;
+            const bool first = w == threadIdx.x;
+            const u32 g0 = first ? pre_g0 : __ldg(&tp.items[lb + (w >> bt_log2)]);
+            const u32 g1 = first ? pre_g1 : __ldg(&tp.items[lb + (w >> bt_log2) + 1]);
+            // a fused work item: its words run back to back in this thread, single-use values stay in two
+            // accumulator registers instead of travelling through the value store
+            u32 acc0[8], acc1[8];
+            for (u32 k = g0; k < g1; ++k) do {
+            const uint4 opw = (first && k == g0) ? pre : __ldg(&tp.ops[k]);
+            const u32 opcode = opw.x & 0xFFu, dst = opw.x >> 8;
             u32 r[8];
             if (HAS_CALLS && opcode == OP_CALL) {
                 int e = 0;
                 exec_call<PRIME, BP>(tp, opw.y, base, plane_base, bt_log2, li, r, &e);
                 if (e && inst < batch) err[inst] = 1;
-            } else if (opcode == OP_BITS && ((opw.w >> 16) & 0xFFu) <= 32u && !(opw.y & (OPD_CONST | OPD_BIT))) {
+            } else if (opcode == OP_BITS && ((opw.w >> 16) & 0xFFu) <= 32u && !(opw.y & (OPD_CONST | OPD_BIT | OPD_ACC))) {
                 // narrow bit-field of a slot value: fetch only the one or two 32-bit words that hold it
-                const u32 k = opw.w & 0xFFFFu, m = (opw.w >> 16) & 0xFFu, run = (opw.w >> 24) + 1u;
-                const u32 wd = k >> 5, sh = k & 31u;
+                const u32 kk = opw.w & 0xFFFFu, m = (opw.w >> 16) & 0xFFu, run = (opw.w >> 24) + 1u;
+                const u32 wd = kk >> 5, sh = kk & 31u;
                 const bool two = sh + m + run - 1u > 32u && wd < 7u;
                 u32 lo, hi = 0;
                 {
@@ -240,13 +253,19 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
                             store_slot(r, base, dst + j, bt_log2, li);
                         }
                     }
-                    continue;  // (leaves the do { } while (0) body)
+                    continue;  // (leaves the do { } while (0) body: next word of the item)
                 }
                 r[0] = (u32)window & (m >= 32u ? 0xFFFFFFFFu : ((1u << m) - 1u));
             } else {
                 u32 a[8], b[8];
-                load_operand<BP>(a, opw.y, base, plane_base, tp.consts, bt_log2, li);
-                load_operand<BP>(b, opw.z, base, plane_base, tp.consts, bt_log2, li);
+                if (!(opw.y & OPD_CONST) && (opw.y & OPD_ACC)) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) a[i] = (opw.y & 1u) ? acc1[i] : acc0[i];
+                } else load_operand<BP>(a, opw.y, base, plane_base, tp.consts, bt_log2, li);
+                if (!(opw.z & OPD_CONST) && (opw.z & OPD_ACC)) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) b[i] = (opw.z & 1u) ? acc1[i] : acc0[i];
+                } else load_operand<BP>(b, opw.z, base, plane_base, tp.consts, bt_log2, li);
                 if (opcode == OP_SELECT) {
                     u32 c[8];
                     load_operand<BP>(c, opw.w, base, plane_base, tp.consts, bt_log2, li);
@@ -267,8 +286,15 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
                     if (e && inst < batch) err[inst] = 1;
                 }
             }
-            store_slot(r, base, dst, bt_log2, li);
+            if (dst >= DST_ACC_DEV) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (dst & 1u) acc1[i] = r[i];
+                    else acc0[i] = r[i];
+                }
+            } else store_slot(r, base, dst, bt_log2, li);
             } while (0);
+            }
             if (COOP) {
                 // Bit runs, warp-cooperatively: the slots of a run are consecutive, so lane j stores bit j and one
                 // store instruction covers run * 32 contiguous bytes (whole 128-byte lines) - a lane streaming its
@@ -288,7 +314,11 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
                 }
             }
         }
-        if (threadIdx.x < ((le_next - le) << bt_log2)) pre = __ldg(&tp.ops[le + (threadIdx.x >> bt_log2)]);
+        if (threadIdx.x < ((le_next - le) << bt_log2)) {
+            pre_g0 = __ldg(&tp.items[le + (threadIdx.x >> bt_log2)]);
+            pre_g1 = __ldg(&tp.items[le + (threadIdx.x >> bt_log2) + 1]);
+            pre = __ldg(&tp.ops[pre_g0]);
+        }
         lb = le;
         le = le_next;
         __syncthreads();

@@ -13,6 +13,10 @@ constexpr uint32_t OPERAND_SLOT_MASK = 0x00FFFFFFu;
 // operand bit29 (tapes lowered with CW_FLAG_BITPLANE): the value is one bit of the instance's bit plane,
 // bits 0-28 = word * 32 + bit.  witness_slot[] entries use the same encoding.
 constexpr uint32_t OPERAND_BIT = 0x20000000u, OPERAND_BITPOS_MASK = 0x1FFFFFFFu;
+// Fused work items: a work item is a short sequence of tape words (T.items delimits them) evaluated by one thread;
+// all but the last write one of two accumulator registers instead of a slot (destination field DST_ACC + k) and later
+// words of the same item read them (operand OPERAND_ACC | k).
+constexpr uint32_t OPERAND_ACC = 0x10000000u, DST_ACC = 0x00FFFFFEu;
 constexpr uint32_t WSLOT_MONT = 0x80000000u;     // witness_slot bit31: slot holds the Montgomery image
 constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
 
@@ -46,13 +50,15 @@ struct Tape {
     uint64_t n_ir_ops = 0, n_mul_ops = 0, n_conv_ops = 0, max_level_width = 0, n_asserts = 0;
     uint64_t slot_census[4] = {0, 0, 0, 0};  // value slots by static width: 1 bit, <= 32, <= 64 bits, wider
     uint64_t n_slot_operands = 0;  // operand reads of slots
-    uint64_t n_values = 0;         // values the tape writes per instance (every destination, each bit of a run)
+    uint64_t n_stored = 0;         // values that reach the value store (slots / plane words written): n_values minus the fused ones
+    uint64_t n_values = 0;         // values the tape computes per instance (every destination, each bit of a run)
     uint32_t n_resident = 0;  // slots [0, n_resident) hold witness entries for the whole run; the rest are reused temporaries (CW_FLAG_REUSE)
     uint32_t n_pre = 0;    // slot 0 = constant one, slots 1..n_inputs = main inputs
     uint32_t n_slots = 0;  // witness entries [0, n_witness) then the other values
     uint32_t n_bitwords = 0;  // 32-bit words of the bit plane per instance (0: every value is a 32-byte slot)
     std::vector<uint32_t> ops;          // 4 words per op: opcode | dst << 8, a, b, c
-    std::vector<uint32_t> level_start;  // n_levels + 1
+    std::vector<uint32_t> items;        // n_items + 1: work item k = tape words [items[k], items[k+1])
+    std::vector<uint32_t> level_start;  // n_levels + 1, indexes work items
     std::vector<U256> consts;           // raw limb patterns (already in the form the consumer needs)
     std::vector<uint32_t> witness_slot; // per witness entry (identity: witness entry i lives in slot i)
     std::vector<uint32_t> input_slot;   // slot of main input i
@@ -67,6 +73,7 @@ struct Tape {
     std::vector<HashEntry> hashmap;
     R1csData r1cs;
     size_t n_tape_ops() const { return ops.size() / 4; }
+    size_t n_items() const { return items.empty() ? 0 : items.size() - 1; }
     size_t n_levels() const { return level_start.empty() ? 0 : level_start.size() - 1; }
 };
 

@@ -14,6 +14,7 @@ from . import build as _build
 CW_OK, CW_EINVAL, CW_EIO, CW_EFORMAT, CW_ECUDA, CW_ENOTFOUND, CW_ESTATE, CW_ENODEV = 0, -1, -2, -3, -4, -5, -6, -7
 CW_FLAG_NO_ASSERTS, CW_FLAG_HOST_ONLY, CW_FLAG_O0, CW_FLAG_NO_PEEPHOLE, CW_FLAG_BITPLANE, CW_FLAG_REUSE = 1, 2, 4, 8, 16, 32
 CW_FLAG_COMPACT = CW_FLAG_BITPLANE | CW_FLAG_REUSE
+CW_FLAG_NO_FUSE = 64
 
 
 class CwError(RuntimeError):
@@ -26,14 +27,14 @@ class CwStats(ctypes.Structure):
     _fields_ = [(n, c_uint64) for n in (
         "n_signals", "n_witness", "n_inputs", "n_outputs", "n_components", "n_constants", "n_ir_ops",
         "n_tape_ops", "n_slots", "n_levels", "n_constraints", "n_nnz", "n_mul_ops", "n_conv_ops",
-        "max_level_width", "n_slot_operands", "n_bitwords", "n_resident_slots", "n_values")]
+        "max_level_width", "n_slot_operands", "n_bitwords", "n_resident_slots", "n_items", "n_stored", "n_values")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
 def _load() -> ctypes.CDLL:
-    path = _build.LIB
+    path = os.environ.get("CW_LIB_PATH") or _build.LIB   # (CW_LIB_PATH: an experimental build of the same ABI)
     if not os.path.exists(path):
         _build.build()
     lib = ctypes.CDLL(path)
@@ -58,6 +59,7 @@ def _load() -> ctypes.CDLL:
         "cw_get_input_signal_size": (c_int, [P, c_uint64, POINTER(c_uint64)]),
         "cw_get_input_signal_id": (c_int, [P, c_uint64, POINTER(c_uint64)]),
         "cw_circuit_tape": (c_int, [P, c_void_p, c_void_p, c_void_p]),
+        "cw_circuit_tape_items": (c_int, [P, c_void_p]),
         "cw_circuit_slot_census": (c_int, [P, POINTER(c_uint64)]),
         "cw_circuit_witness2signal": (c_int, [P, c_void_p]),
         "cw_circuit_write_dat": (c_int, [P, c_char_p]),
@@ -93,6 +95,7 @@ def _load() -> ctypes.CDLL:
         "cw_circuit_expand_record": (c_int, [P, c_void_p, c_void_p, c_int]),
         "cw_host_expand_isa": (c_char_p, []),
         "cw_host_pool_info": (c_char_p, []),
+        "cw_host_expand_bench": (c_int, [P, c_uint32, c_uint32, c_int, c_void_p]),
         "cw_batch_witness_device": (c_int, [P, POINTER(c_void_p)]),
         "cw_batch_witness_strided": (c_int, [P, POINTER(c_void_p), POINTER(c_uint64)]),
         "cw_batch_stream": (c_void_p, [P]),

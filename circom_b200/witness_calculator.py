@@ -113,6 +113,15 @@ def limbs_to_ints(a: np.ndarray) -> List[int]:
     return [int.from_bytes(row.tobytes(), "little") for row in a]
 
 
+def aligned_empty(shape, dtype=np.uint64, align: int = 64) -> np.ndarray:
+    """numpy array whose data starts on an `align`-byte boundary: witness rows written into a 64-byte aligned buffer
+    take full-cache-line streaming stores in the host-side expansion (numpy's own allocations are 16-byte aligned)"""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    raw = np.empty(n + align, dtype=np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off:off + n].view(dtype).reshape(shape)
+
+
 class Circuit:
     """A lowered circuit (replaces Circom_Circuit + the compiled <name>.cpp)."""
 
@@ -196,6 +205,12 @@ class Circuit:
         ws = np.zeros(self.n_witness, dtype=np.uint32)
         check(lib.cw_circuit_tape(self._h, ops.ctypes.data, ls.ctypes.data, ws.ctypes.data))
         return ops, ls, ws
+
+    def tape_items(self) -> np.ndarray:
+        """n_items+1 offsets: work item k = tape words [items[k], items[k+1]); level_start indexes work items"""
+        it = np.zeros(self.stats["n_items"] + 1, dtype=np.uint32)
+        check(lib.cw_circuit_tape_items(self._h, it.ctypes.data))
+        return it
 
     def witness2signal(self) -> np.ndarray:
         out = np.zeros(self.n_witness, dtype=np.uint64)
@@ -290,7 +305,7 @@ class Batch:
 
     def witness(self, out: Optional[np.ndarray] = None) -> np.ndarray:
         if out is None:
-            out = np.empty((self.batch, self.circuit.n_witness, 4), dtype=np.uint64)
+            out = aligned_empty((self.batch, self.circuit.n_witness, 4))
         check(lib.cw_batch_get_witness(self._h, out.ctypes.data))
         return out
 

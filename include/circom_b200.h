@@ -45,6 +45,7 @@ extern "C" {
 #define CW_FLAG_NO_PEEPHOLE 8u /* lower IR ops one to one (no bit-field / boolean-assert / shift fusions) */
 #define CW_FLAG_BITPLANE 16u   /* bits written by bit runs live in a packed per-instance bit plane */
 #define CW_FLAG_REUSE 32u      /* values that are not witness entries share slots (allocated like registers) */
+#define CW_FLAG_NO_FUSE 64u    /* one work item per operator: single-use values are stored instead of being fused into their reader */
 #define CW_FLAG_COMPACT (CW_FLAG_BITPLANE | CW_FLAG_REUSE) /* the compact value store: what cw_batch_* runs best on */
 #define CW_FLAG_O0 4u         /* --O0: keep every signal in the witness and every `signal = signal` constraint */
 
@@ -82,7 +83,10 @@ typedef struct cw_stats {
     uint64_t n_slot_operands; /* operand reads of value slots in the tape */
     uint64_t n_bitwords;      /* 32-bit words of the per-instance bit plane (CW_FLAG_BITPLANE), else 0 */
     uint64_t n_resident_slots;/* slots holding witness entries; slots beyond are reused temporaries (CW_FLAG_REUSE) */
-    uint64_t n_values;        /* values the tape writes per instance: every destination, each bit of a bit run (the S_w of SURVEY.md 8(d),
+    uint64_t n_items;         /* work items of the tape: a work item is 1..24 tape words evaluated by one thread (single-use values
+                                 fused into their reader); n_levels are levels of work items */
+    uint64_t n_stored;        /* values that reach the value store per instance (n_values minus the fused ones) */
+    uint64_t n_values;        /* values the tape computes per instance: every destination, each bit of a bit run (the S_w of SURVEY.md 8(d),
                                  independent of how the values are stored) */
 } cw_stats;
 
@@ -113,8 +117,11 @@ int cw_get_input_signal_size(const cw_circuit *c, uint64_t name_hash, uint64_t *
 int cw_get_input_signal_id(const cw_circuit *c, uint64_t name_hash, uint64_t *signal_id);
 /* copies of the lowered tape for inspection / tests (sizes from cw_circuit_stats):
  * ops: n_tape_ops x 4 uint32 {opcode | flags<<8, a, b, c}; operand bit31 = constant-table index;
- * level_start: n_levels+1 uint32; witness_slot: n_witness uint32 (bit31 = value held in Montgomery form) */
+ * level_start: n_levels+1 uint32 (indexes WORK ITEMS, see cw_circuit_tape_items); witness_slot: n_witness uint32 (bit31 = value held in Montgomery form) */
 int cw_circuit_tape(const cw_circuit *c, uint32_t *ops, uint32_t *level_start, uint32_t *witness_slot);
+/* items: n_items+1 uint32 - work item k is the tape words [items[k], items[k+1]); level_start indexes work items.
+ * Inner words of an item write an accumulator (destination field 0xFFFFFE / 0xFFFFFF), operands with bit 28 read one. */
+int cw_circuit_tape_items(const cw_circuit *c, uint32_t *items);
 /* value slots of one instance by the width the lowering's range analysis proves: out[0] one bit, out[1] <= 32 bits,
  * out[2] <= 64 bits, out[3] wider (today every slot is a 32-byte element; the census sizes a narrow-slot layout) */
 int cw_circuit_slot_census(const cw_circuit *c, uint64_t out[4]);
@@ -165,6 +172,9 @@ const char *cw_host_expand_isa(void);
 /* the worker threads of the expansion: count, NUMA pinning, store width (environment: CW_UNPACK_THREADS,
  * CW_UNPACK_PIN=0, CW_EXPAND_ISA=128|256|512) */
 const char *cw_host_pool_info(void);
+/* host-only probe of that expansion (no GPU): `reps` passes over n_inst instances of a fresh buffer; mode 0 = the
+ * expansion itself (all-zero records), 1 = a plain streaming fill of the same bytes, 2 = memset; gbps[reps] */
+int cw_host_expand_bench(const cw_circuit *c, uint32_t n_inst, uint32_t reps, int mode, double *gbps);
 /* bytes that crossed PCIe in the last cw_batch_get_witness (entries proven to be bits / 64-bit values travel
  * packed and are zero-extended on the host; CW_PACKED_D2H=0 disables) */
 uint64_t cw_batch_last_d2h_bytes(const cw_batch *b);

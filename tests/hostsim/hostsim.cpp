@@ -97,15 +97,31 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
         for (size_t l = 0; l < t.n_levels(); ++l) {
             results.clear();
             bit_results.clear();
-            auto put = [&](u32 dst, const u32 *r) {
+            auto put_slot = [&](u32 dst, const u32 *r) {
                 results.push_back(dst);
                 results.insert(results.end(), r, r + 8);
             };
-            for (size_t i = t.level_start[l]; i < t.level_start[l + 1]; ++i) {
+            for (size_t item = t.level_start[l]; item < t.level_start[l + 1]; ++item) {
+              u32 acc[2][8];   // the two accumulator registers of a fused work item
+              bool acc_set[2] = {false, false};
+              auto operand_acc = [&](u32 o, u32 *v) {
+                  if (!(o & OPERAND_CONST) && (o & OPERAND_ACC)) {
+                      if (!acc_set[o & 1u]) bad_read = true;
+                      memcpy(v, acc[o & 1u], 32);
+                      return;
+                  }
+                  operand(o, v);
+              };
+              for (size_t i = t.items[item]; i < t.items[item + 1]; ++i) {
                 const uint32_t *opw = &t.ops[i * 4];
                 const uint32_t op[4] = {opw[0] & 0xFFu, opw[1], opw[2], opw[3]};
                 const uint32_t dst = opw[0] >> 8;
                 u32 a[8], b[8], r[8];
+                auto put = [&](u32 d_, const u32 *r_) {
+                    if (d_ >= DST_ACC) { memcpy(acc[d_ - DST_ACC], r_, 32); acc_set[d_ - DST_ACC] = true; return; }
+                    if (i + 1 != t.items[item + 1]) bad_read = true;   // only the last word of an item writes the store
+                    put_slot(d_, r_);
+                };
                 if (op[0] == OP_CALL) {  // function call: one work item interprets the body
                     const uint32_t *ct = &t.call_tab[op[1]];
                     FnInfo fi{t.fn_info[ct[0] * 4], t.fn_info[ct[0] * 4 + 1], t.fn_info[ct[0] * 4 + 2], t.fn_info[ct[0] * 4 + 3]};
@@ -117,8 +133,8 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
                     put(dst, r);
                     continue;
                 }
-                operand(op[1], a);
-                operand(op[2], b);
+                operand_acc(op[1], a);
+                operand_acc(op[2], b);
                 if (op[0] == OP_BITS && (op[3] >> 24)) {  // run of single-bit extractions into consecutive slots
                     u32 run = (op[3] >> 24) + 1u, k = op[3] & 0xFFFFu;
                     if (t.n_bitwords) {  // the run is one word of the bit plane (dst = word index)
@@ -134,7 +150,7 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
                     }
                     for (u32 j = 0; j < run; ++j) {
                         u256_bits(r, a, (k + j) | (1u << 16));
-                        put(dst + j, r);
+                        put_slot(dst + j, r);
                     }
                     continue;
                 }
@@ -151,6 +167,7 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
                     fr_exec(op[0], r, a, b, op[3], P, err);
                 }
                 put(dst, r);
+              }
             }
             for (size_t k = 0; k < results.size(); k += 9) {
                 if (results[k] >= t.n_slots) { g_err = "destination out of range"; return -5; }
@@ -203,7 +220,11 @@ int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
         g_err = e.what();
         return -1;
     }
-    if (t.n_levels() && t.level_start[t.n_levels()] != t.n_tape_ops()) { g_err = "level table does not cover the tape"; return -2; }
+    if (t.items.empty() || t.items.back() != t.n_tape_ops() || (t.n_levels() && t.level_start[t.n_levels()] != t.n_items())) {
+        g_err = "level / item tables do not cover the tape"; return -2;
+    }
+    for (size_t k = 0; k + 1 < t.items.size(); ++k)
+        if (t.items[k] >= t.items[k + 1]) { g_err = "empty work item"; return -2; }
     const uint32_t n_res = (flags & 32u /* CW_FLAG_REUSE */) ? t.n_resident : t.n_slots;
     std::vector<uint32_t> def(t.n_slots, 0), writes(t.n_slots, 0), read_stamp(t.n_slots, 0), write_stamp(t.n_slots, 0);
     std::vector<uint32_t> bitlvl(t.n_bitwords, 0), bitrun(t.n_bitwords, 0);
@@ -229,6 +250,7 @@ int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
                 }
                 return 0;
             }
+            if (o & OPERAND_ACC) return 0;   // an accumulator of the same work item (checked by the item walk below)
             if (o & ~OPERAND_SLOT_MASK) { g_err = "unknown operand flag"; return -4; }
             if (o >= t.n_slots) { g_err = "slot out of range"; return -4; }
             if (!def[o]) { g_err = "operand not produced in an earlier level"; return -5; }
@@ -236,7 +258,26 @@ int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
             return 0;
         };
         // reads of the level (definitions so far are all from earlier levels)
-        for (uint32_t i = t.level_start[l]; i < t.level_start[l + 1]; ++i) {
+        // accumulator discipline inside a work item: written before read, only the last word writes the store
+        for (uint32_t item = t.level_start[l]; item < t.level_start[l + 1]; ++item) {
+            bool have[2] = {false, false};
+            for (uint32_t i = t.items[item]; i < t.items[item + 1]; ++i) {
+                const uint32_t *opw = &t.ops[(size_t)i * 4];
+                const uint32_t opc = opw[0] & 0xFFu, dst = opw[0] >> 8;
+                const bool last = i + 1 == t.items[item + 1];
+                const bool c_imm = is_assert(opc) || opc == OP_BITS || opc == OP_BITSIP;
+                if (opc != OP_CALL)
+                    for (int k = 1; k <= 3; ++k) {
+                        if (k == 3 && c_imm) break;
+                        if (!(opw[k] & OPERAND_CONST) && (opw[k] & OPERAND_ACC) && !have[opw[k] & 1u]) { g_err = "accumulator read before it is written"; return -16; }
+                    }
+                if (!last) {
+                    if (is_assert(opc) || dst < DST_ACC || opc == OP_CALL) { g_err = "inner word of a work item must write an accumulator"; return -17; }
+                    have[dst - DST_ACC] = true;
+                } else if (!is_assert(opc) && dst >= DST_ACC) { g_err = "last word of a work item writes an accumulator"; return -18; }
+            }
+        }
+        for (uint32_t i = t.items[t.level_start[l]]; i < t.items[t.level_start[l + 1]]; ++i) {
             const uint32_t *opw = &t.ops[(size_t)i * 4];
             const uint32_t opc = opw[0] & 0xFFu;
             int rc;
@@ -253,10 +294,10 @@ int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
             }
         }
         // writes of the level
-        for (uint32_t i = t.level_start[l]; i < t.level_start[l + 1]; ++i) {
+        for (uint32_t i = t.items[t.level_start[l]]; i < t.items[t.level_start[l + 1]]; ++i) {
             const uint32_t *opw = &t.ops[(size_t)i * 4];
             const uint32_t opc = opw[0] & 0xFFu, dst = opw[0] >> 8;
-            if (is_assert(opc)) continue;
+            if (is_assert(opc) || dst >= DST_ACC) continue;
             const uint32_t run = opc == OP_BITS ? (opw[3] >> 24) + 1u : 1u;
             if (t.n_bitwords && run > 1) {  // bit plane: the run is word `dst`
                 if (dst >= t.n_bitwords) { g_err = "bit-plane word out of range"; return -11; }
@@ -273,10 +314,10 @@ int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
                 if (++writes[s] > 1 && s < n_res) { g_err = "slot written twice"; return -7; }
             }
         }
-        for (uint32_t i = t.level_start[l]; i < t.level_start[l + 1]; ++i) {  // ... become visible after the barrier
+        for (uint32_t i = t.items[t.level_start[l]]; i < t.items[t.level_start[l + 1]]; ++i) {  // ... become visible after the barrier
             const uint32_t *opw = &t.ops[(size_t)i * 4];
             const uint32_t opc = opw[0] & 0xFFu, dst = opw[0] >> 8;
-            if (is_assert(opc)) continue;
+            if (is_assert(opc) || dst >= DST_ACC) continue;
             const uint32_t run = opc == OP_BITS ? (opw[3] >> 24) + 1u : 1u;
             if (t.n_bitwords && run > 1) { bitlvl[dst] = L; continue; }
             for (uint32_t j = 0; j < run; ++j) def[dst + j] = L;

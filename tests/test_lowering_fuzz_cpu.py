@@ -119,7 +119,7 @@ def test_random_circuits_match_the_evaluator(prime, seed):
     for e in expected:
         assert check_r1cs(d, e) == 0
     for flags in (0, CW_FLAG_NO_PEEPHOLE, CW_FLAG_O0, CW_FLAG_BITPLANE, CW_FLAG_BITPLANE | CW_FLAG_O0, CW_FLAG_REUSE, CW_FLAG_COMPACT,
-                  CW_FLAG_COMPACT | CW_FLAG_O0, CW_FLAG_REUSE | CW_FLAG_NO_PEEPHOLE):
+                  CW_FLAG_COMPACT | CW_FLAG_O0, CW_FLAG_REUSE | CW_FLAG_NO_PEEPHOLE, 64, 64 | CW_FLAG_COMPACT):
         wit, st, stats, w2s = hostsim_run(d, ins, flags=flags)
         assert not st.any(), (prime, seed, flags, st)
         for i, e in enumerate(expected):

@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=-1, help="timed end-to-end steps (default 1; 0 = skip)")
     ap.add_argument("--e2e-chunk", type=int, default=0, help="instances per streamed chunk of the e2e leg")
     ap.add_argument("--e2e-batch", type=int, default=0, help="instances per e2e step (default: the batch of `value`)")
+    ap.add_argument("--fuse", type=int, default=-1, help="CW_FLAG_FUSE for the workload (default: on for warp-per-op batches)")
     ap.add_argument("--no-configs", action="store_true", help="skip the per-config measurements (C2, C3@8, C4)")
     ap.add_argument("--no-gather", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -348,7 +349,8 @@ def run_workload(ctx: Ctx, workload: str, batch: int, steps: int, warmup: int, e
     rank, world, dev = ctx.rank, ctx.world, ctx.local_rank
     # one-time collective: rank 0's circuit description is broadcast over NCCL (every rank lowers it: 0.2-2.4 s)
     blob = broadcast_blob(desc.to_bytes() if rank == 0 else None, rank, world, device="cuda")
-    circuit = Circuit(blob)
+    fuse = batch >= 9472 if ctx.args.fuse < 0 else bool(ctx.args.fuse)   # measured: pays for warp-per-op batches only
+    circuit = Circuit(blob, fuse=fuse)
     st = circuit.stats
     b = Batch(circuit, batch, dev)
     n_in, W = circuit.n_inputs, circuit.n_witness
@@ -480,7 +482,7 @@ def run_workload(ctx: Ctx, workload: str, batch: int, steps: int, warmup: int, e
         "vs_baseline": None, "dtype": "u256 (8x u32 limbs, Montgomery)", "data": "synthetic",
         "config": dict(workload_config(label, desc, batch, world, st),
                        layout={"instances_per_tile": 1 << bt_log2, "threads_per_cta": threads,
-                               "value_store_bytes_per_instance": bytes_per_inst, "n_slots": st["n_slots"],
+                               "value_store_bytes_per_instance": bytes_per_inst, "n_slots": st["n_slots"], "fused_work_items": fuse,
                                "n_bitwords": st["n_bitwords"]},
                        l2="working set %.1f GB per step >> L2, rewritten every step" % (batch * bytes_per_inst / 1e9)),
         "wall_ms_per_step": wall_ms / steps,

@@ -86,6 +86,7 @@ int ensure_device(int device) {
 struct DevTape {
     uint4 *ops = nullptr;
     u32 *items = nullptr, *level_start = nullptr;
+    uint4 *heads = nullptr;  // first tape word of every work item
     uint4 *consts = nullptr;
     u32 *input_slot = nullptr, *fn_code = nullptr, *fn_info = nullptr, *call_tab = nullptr;
     u32 *wloc = nullptr;  // per witness entry: where its value lives (slot id, or OPD_BIT | plane position)
@@ -207,6 +208,11 @@ static int get_dev_tape(const cw_circuit *c, int device, DevTape &out) {
     int rc;
     if ((rc = upload(&d.ops, t.ops.data(), t.ops.size() * 4))) return rc;
     if ((rc = upload(&d.items, t.items.data(), t.items.size() * 4))) return rc;
+    {
+        std::vector<uint32_t> heads(t.n_items() * 4);
+        for (size_t k = 0; k < t.n_items(); ++k) memcpy(&heads[k * 4], &t.ops[(size_t)t.items[k] * 4], 16);
+        if ((rc = upload(&d.heads, heads.data(), heads.size() * 4))) return rc;
+    }
     if ((rc = upload(&d.level_start, t.level_start.data(), t.level_start.size() * 4))) return rc;
     if ((rc = upload(&d.consts, t.consts.data(), t.consts.size() * 32))) return rc;
     if ((rc = upload(&d.input_slot, t.input_slot.data(), t.input_slot.size() * 4))) return rc;
@@ -220,6 +226,32 @@ static int get_dev_tape(const cw_circuit *c, int device, DevTape &out) {
     c->dev[device] = d;
     out = d;
     return CW_OK;
+}
+
+// builds of the interpreter: function calls (runtime tile size); fused work items (CW_FLAG_FUSE; runtime tile size, or
+// a warp per op); one operator per work item, per bit-plane mode: one instance per tile / a warp per op (tile sizes
+// fixed at compile time) / tile size as an argument
+template <int PR, bool CALLS, bool BP, int BT, bool FU>
+static void launch_tape_k(const TapeDev &tp, cw_batch *b, u32 tiles, u32 th) {
+    tape_exec_kernel<PR, CALLS, BP, BT, FU><<<tiles, th, 0, b->stream>>>(tp, b->slots, b->plane, b->bt_log2, b->first_assert_d,
+                                                                         b->err_d, b->batch);
+}
+template <int PR>
+static void launch_tape(const TapeDev &tp, cw_batch *b, u32 tiles, u32 th, bool calls, bool bp, bool fused) {
+    if (calls) {  // (the lowering does not fuse tapes with function calls)
+        if (bp) launch_tape_k<PR, true, true, -1, false>(tp, b, tiles, th);
+        else launch_tape_k<PR, true, false, -1, false>(tp, b, tiles, th);
+    } else if (fused) {  // (the bit-plane build also runs tapes without a plane: they contain no plane operands)
+        if (b->bt_log2 == 5) launch_tape_k<PR, false, true, 5, true>(tp, b, tiles, th);
+        else launch_tape_k<PR, false, true, -1, true>(tp, b, tiles, th);
+    } else if (bp) {
+        if (b->bt_log2 == 0) launch_tape_k<PR, false, true, 0, false>(tp, b, tiles, th);
+        else if (b->bt_log2 == 5) launch_tape_k<PR, false, true, 5, false>(tp, b, tiles, th);
+        else launch_tape_k<PR, false, true, -1, false>(tp, b, tiles, th);
+    } else {
+        if (b->bt_log2 == 0) launch_tape_k<PR, false, false, 0, false>(tp, b, tiles, th);
+        else launch_tape_k<PR, false, false, -1, false>(tp, b, tiles, th);
+    }
 }
 
 extern "C" {
@@ -268,6 +300,7 @@ void cw_circuit_destroy(cw_circuit *c) {
         cudaSetDevice(kv.first);
         cudaFree(kv.second.ops);
         cudaFree(kv.second.items);
+        cudaFree(kv.second.heads);
         cudaFree(kv.second.level_start);
         cudaFree(kv.second.consts);
         cudaFree(kv.second.input_slot);
@@ -568,6 +601,7 @@ int cw_batch_run(cw_batch *b) {
     TapeDev tp;
     tp.ops = b->dt.ops;
     tp.items = b->dt.items;
+    tp.heads = b->dt.heads;
     tp.level_start = b->dt.level_start;
     tp.consts = b->dt.consts;
     tp.n_levels = (u32)t.n_levels();
@@ -591,29 +625,9 @@ int cw_batch_run(cw_batch *b) {
         const bool calls = !t.call_tab.empty();
         const bool bp = t.n_bitwords != 0;
         const u32 th = calls ? std::min<u32>(b->threads, 256u) : b->threads;  // the interpreter build has a large frame
-#define CW_LAUNCH_TAPE(PR, CALLS, BP_, BT_)                                                                   \
-    tape_exec_kernel<PR, CALLS, BP_, BT_><<<tiles, th, 0, b->stream>>>(tp, b->slots, b->plane, b->bt_log2,     \
-                                                                         b->first_assert_d, b->err_d, b->batch)
-        // builds: calls (runtime tile size), and per bit-plane mode: one instance per tile / a warp per op (tile sizes
-        // fixed at compile time) / tile size as an argument
-#define CW_LAUNCH_PRIME(PR)                                          \
-    do {                                                             \
-        if (calls) {                                                 \
-            if (bp) CW_LAUNCH_TAPE(PR, true, true, -1);              \
-            else CW_LAUNCH_TAPE(PR, true, false, -1);                \
-        } else if (bp) {                                             \
-            if (b->bt_log2 == 0) CW_LAUNCH_TAPE(PR, false, true, 0); \
-            else if (b->bt_log2 == 5) CW_LAUNCH_TAPE(PR, false, true, 5); \
-            else CW_LAUNCH_TAPE(PR, false, true, -1);                \
-        } else {                                                     \
-            if (b->bt_log2 == 0) CW_LAUNCH_TAPE(PR, false, false, 0); \
-            else CW_LAUNCH_TAPE(PR, false, false, -1);               \
-        }                                                            \
-    } while (0)
-        if (t.F.prime_id == 0) CW_LAUNCH_PRIME(0);
-        else CW_LAUNCH_PRIME(1);
-#undef CW_LAUNCH_PRIME
-#undef CW_LAUNCH_TAPE
+        const bool fused = t.n_items() != t.n_tape_ops();
+        if (t.F.prime_id == 0) launch_tape<0>(tp, b, tiles, th, calls, bp, fused);
+        else launch_tape<1>(tp, b, tiles, th, calls, bp, fused);
     }
     CU(cudaEventRecord(b->ev[1], b->stream));
     b->dense_valid = false;

@@ -1096,7 +1096,8 @@ struct Lowerer {
             }
             std::vector<uint8_t> need(n_prov, 1);
             std::vector<uint32_t> gsize(n_prov, 1);
-            const bool fuse_on = !(flags & (CW_FLAG_NO_FUSE | CW_FLAG_NO_PEEPHOLE));
+            // (tapes with function calls keep one operator per work item: the call interpreter's build has no room for it)
+            const bool fuse_on = (flags & CW_FLAG_FUSE) && !(flags & CW_FLAG_NO_PEEPHOLE) && pcalls.empty();
             auto candidate = [&](uint32_t slot, size_t reader, int pos) -> bool {
                 if (!fuse_on || slot == NO_SLOT || (slot & OPERAND_CONST) || slot < n_pre) return false;
                 const size_t c = slot - n_pre;

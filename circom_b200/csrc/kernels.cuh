@@ -100,6 +100,7 @@ __device__ __forceinline__ u32 u256_bitlen_dev(const u32 *a) {
 struct TapeDev {
     const uint4 *ops;          // {opcode | dst << 8, a, b, c}
     const u32 *items;          // n_items + 1: work item k = tape words [items[k], items[k+1]) evaluated by one thread
+    const uint4 *heads;        // n_items: copy of the first tape word of every work item (fetched in parallel with items[])
     const u32 *level_start;    // n_levels + 1, indexes work items
     const uint4 *consts;       // 2 per constant
     const u32 *input_slot;     // slot of main input k
@@ -172,11 +173,13 @@ __device__ __noinline__ void exec_call(const TapeDev &tp, u32 call_off, const ui
 #define CW_TAPE_LB 512  // widest CTA of the interpreter (cw_batch_create clamps to it); with MINB it bounds the registers
 #endif
 #ifndef CW_TAPE_MINB
-#define CW_TAPE_MINB 1
+#define CW_TAPE_MINB 2  // 512 x 2: a 64-register budget (the fused build spills ~100 bytes; measured faster than 84 registers)
 #endif
 // BT >= 0 fixes the tile size at compile time (BT = 0, one instance per CTA: the slot address arithmetic then
 // folds to `base + slot * 32`; BT = 5, a warp per op); BT < 0 takes it from the launch argument.
-template <int PRIME, bool HAS_CALLS, bool BP, int BT>
+// FUSED: the tape has multi-word work items (CW_FLAG_FUSE); otherwise work item k IS tape word k and the item table,
+// the accumulators and the inner loop disappear at compile time.
+template <int PRIME, bool HAS_CALLS, bool BP, int BT, bool FUSED>
 __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
     tape_exec_kernel(TapeDev tp, uint4 *__restrict__ slots, u32 *__restrict__ plane, u32 bt_log2_arg,
                      u32 *__restrict__ first_assert, int *__restrict__ err, u32 batch) {
@@ -194,9 +197,11 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
     uint4 pre = make_uint4(0, 0, 0, 0);
     u32 pre_g0 = 0, pre_g1 = 0;
     if (threadIdx.x < ((le - lb) << bt_log2)) {
-        pre_g0 = __ldg(&tp.items[lb + (threadIdx.x >> bt_log2)]);
-        pre_g1 = __ldg(&tp.items[lb + (threadIdx.x >> bt_log2) + 1]);
-        pre = __ldg(&tp.ops[pre_g0]);
+        if (FUSED) {
+            pre_g0 = __ldg(&tp.items[lb + (threadIdx.x >> bt_log2)]);
+            pre_g1 = __ldg(&tp.items[lb + (threadIdx.x >> bt_log2) + 1]);
+            pre = __ldg(&tp.heads[lb + (threadIdx.x >> bt_log2)]);
+        } else pre = __ldg(&tp.ops[lb + (threadIdx.x >> bt_log2)]);
     }
     for (u32 l = 0; l < tp.n_levels; ++l) {
         const u32 n = (le - lb) << bt_log2;
@@ -210,13 +215,23 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
             const u32 li = w & bt_mask;
             const u32 inst = (tile << bt_log2) + li;
             const bool first = w == threadIdx.x;
-            const u32 g0 = first ? pre_g0 : __ldg(&tp.items[lb + (w >> bt_log2)]);
-            const u32 g1 = first ? pre_g1 : __ldg(&tp.items[lb + (w >> bt_log2) + 1]);
+            u32 g0 = lb + (w >> bt_log2), g1 = g0 + 1u;   // !FUSED: work item k is tape word k
+            if (FUSED) {
+                g0 = first ? pre_g0 : __ldg(&tp.items[lb + (w >> bt_log2)]);
+                g1 = first ? pre_g1 : __ldg(&tp.items[lb + (w >> bt_log2) + 1]);
+            }
             // a fused work item: its words run back to back in this thread, single-use values stay in two
             // accumulator registers instead of travelling through the value store
             u32 acc0[8], acc1[8];
-            for (u32 k = g0; k < g1; ++k) do {
-            const uint4 opw = (first && k == g0) ? pre : __ldg(&tp.ops[k]);
+            uint4 nxt = pre;
+            if (!first) {
+                if (FUSED) nxt = __ldg(&tp.heads[lb + (w >> bt_log2)]);
+                else nxt = __ldg(&tp.ops[g0]);
+            }
+            for (u32 k = g0; k < g1; ++k) {
+            const uint4 opw = nxt;
+            bool has_value = true;   // false: the word stored its results itself / has none (asserts)
+            if (FUSED && k + 1 < g1) nxt = __ldg(&tp.ops[k + 1]);   // the next word of the item travels while this one executes
             const u32 opcode = opw.x & 0xFFu, dst = opw.x >> 8;
             u32 r[8];
             if (HAS_CALLS && opcode == OP_CALL) {
@@ -253,16 +268,15 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
                             store_slot(r, base, dst + j, bt_log2, li);
                         }
                     }
-                    continue;  // (leaves the do { } while (0) body: next word of the item)
-                }
-                r[0] = (u32)window & (m >= 32u ? 0xFFFFFFFFu : ((1u << m) - 1u));
+                    has_value = false;
+                } else r[0] = (u32)window & (m >= 32u ? 0xFFFFFFFFu : ((1u << m) - 1u));
             } else {
                 u32 a[8], b[8];
-                if (!(opw.y & OPD_CONST) && (opw.y & OPD_ACC)) {
+                if (FUSED && !(opw.y & OPD_CONST) && (opw.y & OPD_ACC)) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) a[i] = (opw.y & 1u) ? acc1[i] : acc0[i];
                 } else load_operand<BP>(a, opw.y, base, plane_base, tp.consts, bt_log2, li);
-                if (!(opw.z & OPD_CONST) && (opw.z & OPD_ACC)) {
+                if (FUSED && !(opw.z & OPD_CONST) && (opw.z & OPD_ACC)) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) b[i] = (opw.z & 1u) ? acc1[i] : acc0[i];
                 } else load_operand<BP>(b, opw.z, base, plane_base, tp.consts, bt_log2, li);
@@ -279,21 +293,23 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
                               : opcode == OP_ASSERT_BOOL ? (u256_is_zero(a) || u256_eq(a, b))
                                                          : (u256_bitlen_dev(a) <= b[0]);
                     if (!ok && inst < batch) atomicMin(&first_assert[inst], opw.w);
-                    continue;  // asserts have no destination value
+                    has_value = false;  // asserts have no destination value
                 } else {
                     int e = 0;
                     fr_exec(opcode, r, a, b, opw.w, P, e);
                     if (e && inst < batch) err[inst] = 1;
                 }
             }
-            if (dst >= DST_ACC_DEV) {
+            if (has_value) {
+                if (FUSED && dst >= DST_ACC_DEV) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (dst & 1u) acc1[i] = r[i];
-                    else acc0[i] = r[i];
-                }
-            } else store_slot(r, base, dst, bt_log2, li);
-            } while (0);
+                    for (int i = 0; i < 8; ++i) {
+                        if (dst & 1u) acc1[i] = r[i];
+                        else acc0[i] = r[i];
+                    }
+                } else store_slot(r, base, dst, bt_log2, li);
+            }
+            }
             }
             if (COOP) {
                 // Bit runs, warp-cooperatively: the slots of a run are consecutive, so lane j stores bit j and one
@@ -315,9 +331,11 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
             }
         }
         if (threadIdx.x < ((le_next - le) << bt_log2)) {
-            pre_g0 = __ldg(&tp.items[le + (threadIdx.x >> bt_log2)]);
-            pre_g1 = __ldg(&tp.items[le + (threadIdx.x >> bt_log2) + 1]);
-            pre = __ldg(&tp.ops[pre_g0]);
+            if (FUSED) {   // three independent loads: one round trip
+                pre_g0 = __ldg(&tp.items[le + (threadIdx.x >> bt_log2)]);
+                pre_g1 = __ldg(&tp.items[le + (threadIdx.x >> bt_log2) + 1]);
+                pre = __ldg(&tp.heads[le + (threadIdx.x >> bt_log2)]);
+            } else pre = __ldg(&tp.ops[le + (threadIdx.x >> bt_log2)]);
         }
         lb = le;
         le = le_next;

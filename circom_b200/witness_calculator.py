@@ -126,11 +126,14 @@ class Circuit:
     """A lowered circuit (replaces Circom_Circuit + the compiled <name>.cpp)."""
 
     def __init__(self, src: Union[CircuitDesc, bytes, str], sanity_check: bool = True, host_only: bool = False,
-                 o0: bool = False, flags: int = 0, compact: Optional[bool] = None):
+                 o0: bool = False, flags: int = 0, compact: Optional[bool] = None, fuse: bool = False):
         """compact (default on; environment CW_COMPACT=0 turns it off): lower for the compact value store - bit runs in
         a per-instance bit plane, temporaries sharing slots (CW_FLAG_COMPACT) - instead of one 32-byte slot per value"""
         if compact is None:
             compact = os.environ.get("CW_COMPACT", "1") != "0" and not (flags & native.CW_FLAG_COMPACT)
+        flags |= int(os.environ.get("CW_FLAGS_EXTRA", "0"))   # (experiments)
+        if fuse:   # single-use values stay in registers of their reader's work item: pays for large batches only
+            flags |= native.CW_FLAG_FUSE
         flags |= (0 if sanity_check else native.CW_FLAG_NO_ASSERTS) | (native.CW_FLAG_HOST_ONLY if host_only else 0) | \
             (native.CW_FLAG_O0 if o0 else 0) | (native.CW_FLAG_COMPACT if compact else 0)
         self.flags = flags

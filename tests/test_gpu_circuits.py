@@ -88,6 +88,37 @@ def test_compact_store_matches_plain_store(bt, monkeypatch):
     assert not st.any() and (ow[:, w2s] == wit1[:8]).all()
 
 
+@pytest.mark.parametrize("bt", ["0", "3", "5"])
+def test_fused_work_items_match(bt, monkeypatch):
+    """CW_FLAG_FUSE: single-use values evaluated inside their reader's work item (accumulator registers) - same
+    witnesses as one operator per work item, half the levels"""
+    monkeypatch.setenv("CW_BT_LOG2", bt)
+    for mk, gen in ((lambda d: C.ecdsa_scale(d, 2, 5),
+                     lambda rng: {"a": [int(x) for x in rng.integers(0, 2**63, 8)], "b": [int(x) for x in rng.integers(0, 2**63, 8)]}),
+                    (lambda d: C.sha256(d, 64), lambda rng: {"in": [int(x) for x in rng.integers(0, 2, 64)]})):
+        d = CircuitDesc("bn128")
+        d.set_main(mk(d))
+        rng = np.random.default_rng(11)
+        ins = [gen(rng) for _ in range(40)]
+        arr = flat_inputs(d, ins)
+        wits = []
+        for fuse in (False, True):
+            c = Circuit(d, fuse=fuse)
+            b = Batch(c, len(ins))
+            b.set_inputs(arr)
+            b.run()
+            assert not b.status().any()
+            wits.append((c, b.witness()))
+            fb, _ = R1cs(c).check_batch(b)
+            assert (fb == -1).all()
+        assert (wits[0][1] == wits[1][1]).all()
+        assert wits[1][0].stats["n_levels"] * 3 < wits[0][0].stats["n_levels"] * 2
+        assert wits[1][0].stats["n_items"] < wits[1][0].stats["n_tape_ops"] == wits[0][0].stats["n_items"]
+        ow, st = COracle(d.to_bytes()).run(arr[:4])
+        w2s = wits[1][0].witness2signal().astype(np.int64)
+        assert (ow[:, w2s] == wits[1][1][:4]).all()
+
+
 def test_overlapped_transfers_of_two_batches():
     """cw_batch_get_witness_async: the witnesses of batch A are packed, copied and expanded on a helper thread while
     batch B executes; both results equal the synchronous transfer"""

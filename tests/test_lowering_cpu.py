@@ -38,7 +38,7 @@ def test_tape_matches_oracle(prime, name):
     import zlib
     rng = random.Random(zlib.crc32((prime + name).encode()))
     ins = [gen(rng, d.q) for _ in range(24)]
-    for flags in (0, 4, 16, 32, 48, 52, 64, 112):  # default, O0, BITPLANE, REUSE, both (COMPACT), COMPACT + O0, NO_FUSE, COMPACT + NO_FUSE
+    for flags in (0, 4, 16, 32, 48, 52, 64, 112):  # default, O0, BITPLANE, REUSE, both (COMPACT), COMPACT + O0, FUSE, COMPACT + FUSE
         wit, st, stats, w2s = hostsim_run(d, ins, flags=flags)
         if flags == 4:
             assert w2s.tolist() == list(range(d.total_signals))

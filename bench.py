@@ -411,14 +411,15 @@ def run_workload(ctx: Ctx, workload: str, batch: int, steps: int, warmup: int, e
     e2e = None
     if e2e_steps > 0:
         tot = e2e_batch or batch
-        chunk = e2e_chunk or max(1, min(tot, int(max(64, min(1024, (6e9 / max(1, world)) // (W * 32))))))
+        chunk = e2e_chunk or max(1, min(tot, int(max(64, min(1024, (24e9 / max(1, world)) // (W * 32))))))
         chunk = min(chunk, tot)
         if chunk == batch and tot == batch:
             pair = [b, Batch(circuit, chunk, dev)]
         else:
             del b
             torch.cuda.empty_cache()
-            pair = [Batch(circuit, chunk, dev), Batch(circuit, chunk, dev)]
+            ecirc = Circuit(blob, fuse=False) if fuse and chunk < 9472 else circuit   # small chunks: one operator per work item
+            pair = [Batch(ecirc, chunk, dev), Batch(ecirc, chunk, dev)]
         from circom_b200.witness_calculator import aligned_empty
         outs = [aligned_empty((chunk, W, 4)) for _ in range(2)]   # pageable, 64-byte aligned: first touched by the workers
         pin_np = pin_in.numpy().view(np.uint64)

@@ -471,7 +471,7 @@ int cw_batch_create(const cw_circuit *c, uint32_t batch, int device, cw_batch **
         u32 tiles = b->batch_padded >> bt;
         u32 per_sm = (tiles + 147) / 148;
         while (th > 64 && (u32)th * per_sm > 1024) th >>= 1;
-        if (tiles < 148u) th = (int)std::min<uint64_t>(CW_TAPE_LB, std::max<uint64_t>(th, (avg + 31) / 32 * 32));  // few tiles: wide CTAs
+        if (tiles < 148u) th = CW_TAPE_LB;  // fewer tiles than SMs: the widest CTA (wide levels finish in one pass; measured 6.5 vs 7.6 ms at 8 instances)
     }
     th = (th + 31) / 32 * 32;
     if (th > CW_TAPE_LB) th = CW_TAPE_LB;

@@ -486,11 +486,31 @@ struct R1csDev {
     u32 n_rows;  // rows in perm
 };
 
+// Lazy reduction: most terms of circom constraints are bits / small values times +-1 or +-2^k (boolean logic, the
+// recomposition sums of range checks, carries).  Such a term is an integer below 2^112; the terms of one linear
+// combination are summed as plain 128-bit integers (positive and negative coefficients apart) and enter the modular
+// accumulator ONCE, instead of one 256-bit modular addition per term.
+__device__ __forceinline__ void acc128_add(unsigned long long &lo, unsigned long long &hi, u32 v, u32 sh) {
+    // (lo, hi) += v << sh, 0 <= sh <= 80
+    unsigned long long l, h;
+    if (sh < 64u) {
+        l = (unsigned long long)v << sh;
+        h = sh > 32u ? ((unsigned long long)v >> (64u - sh)) : 0ull;
+    } else {
+        l = 0ull;
+        h = (unsigned long long)v << (sh - 64u);
+    }
+    lo += l;
+    hi += h + (lo < l ? 1ull : 0ull);
+}
+
 template <int PRIME>
 __device__ __forceinline__ void r1cs_lc(u32 *acc, const R1csDev &R, unsigned long long b, unsigned long long e,
                                         const StoreDev &S, const uint4 *__restrict__ tb, const u32 *__restrict__ pb,
                                         u32 li, const FrParams &P, unsigned long long *__restrict__ first_bad_inst) {
     u256_set_u32(acc, 0);
+    unsigned long long plo = 0, phi = 0, nlo = 0, nhi = 0;
+    const bool lazy = e - b < 65536ull;   // 2^16 terms below 2^112 cannot overflow 128 bits
     for (unsigned long long k = b; k < e; ++k) {
         const uint4 term = __ldg(&R.terms[k]);
         const u32 loc = term.x, ci = term.y, kw = term.z, brow = term.w;
@@ -501,6 +521,11 @@ __device__ __forceinline__ void r1cs_lc(u32 *acc, const R1csDev &R, unsigned lon
             // run of plane bits times consecutive powers of two: an integer below 2^(sh + count) < q
             const u32 first = (kw >> 16) & 31u, cnt = ((kw >> 21) & 31u) + 1u;
             const u32 word = (__ldg(&pb[((size_t)loc << S.bt_log2) + li]) >> first) & (cnt >= 32u ? 0xFFFFFFFFu : ((1u << cnt) - 1u));
+            if (lazy && sh <= 80u) {
+                if (neg) acc128_add(nlo, nhi, word, sh);
+                else acc128_add(plo, phi, word, sh);
+                continue;
+            }
             const u32 wd = sh >> 5, s = sh & 31u;
             const u32 l = word << s, h = s ? (word >> (32u - s)) : 0u;
 #pragma unroll
@@ -510,6 +535,11 @@ __device__ __forceinline__ void r1cs_lc(u32 *acc, const R1csDev &R, unsigned lon
             const u32 upper = x[1] | x[2] | x[3] | x[4] | x[5] | x[6] | x[7];
             // the boolean constraint x*(x-1) = 0 of this wire is checked here, while its value is in registers
             if (brow != 0xFFFFFFFFu && (upper || x[0] > 1u)) atomicMin(first_bad_inst, (unsigned long long)brow);
+            if (lazy && !upper && kd >= 1u && (kd <= 2u || sh <= 80u)) {   // a 32-bit value times +-1 / +-2^sh
+                if (neg) acc128_add(nlo, nhi, x[0], kd <= 2u ? 0u : sh);
+                else acc128_add(plo, phi, x[0], kd <= 2u ? 0u : sh);
+                continue;
+            }
             if (kd >= 3) {
                 if (!upper && sh + 32u < P.qbits) {  // x < 2^32: x * 2^sh < 2^(qbits-1) < q, placed without a reduction
                     const u32 wd = sh >> 5, s = sh & 31u;
@@ -536,6 +566,16 @@ __device__ __forceinline__ void r1cs_lc(u32 *acc, const R1csDev &R, unsigned lon
         }
         if (neg) fr_sub(t, acc, x, P);
         else fr_add(t, acc, x, P);
+        u256_set(acc, t);
+    }
+    if (plo | phi) {
+        u32 v[8] = {(u32)plo, (u32)(plo >> 32), (u32)phi, (u32)(phi >> 32), 0u, 0u, 0u, 0u}, t[8];
+        fr_add(t, acc, v, P);
+        u256_set(acc, t);
+    }
+    if (nlo | nhi) {
+        u32 v[8] = {(u32)nlo, (u32)(nlo >> 32), (u32)nhi, (u32)(nhi >> 32), 0u, 0u, 0u, 0u}, t[8];
+        fr_sub(t, acc, v, P);
         u256_set(acc, t);
     }
 }

@@ -1387,6 +1387,49 @@ int cw_r1cs_eval_batch(cw_r1cs *r, cw_batch *b, uint32_t first, uint32_t count, 
     return launch_r1cs(all, d, S, b->stream, b->fb_d, &eo);
 }
 
+// readWitness side of the file boundary: the 32-byte entries of a .wtns (written by this library, the reference
+// calculator or snarkjs); out = NULL returns the count only
+int cw_wtns_read(const char *path, int *prime_id, uint64_t *n_witness, uint64_t *out, size_t cap_entries) {
+    if (!path || !n_witness) return fail(CW_EINVAL, "null argument");
+    std::vector<uint64_t> w;
+    int pid = 0;
+    try {
+        read_wtns(path, pid, w);
+    } catch (const std::exception &e) {
+        return fail(CW_EFORMAT, e.what());
+    }
+    if (prime_id) *prime_id = pid;
+    *n_witness = w.size() / 4;
+    if (!out) return CW_OK;
+    if (cap_entries < w.size() / 4) return fail(CW_EINVAL, "buffer too small");
+    memcpy(out, w.data(), w.size() * 8);
+    return CW_OK;
+}
+
+// A.w o B.w == C.w for a .wtns file against a .r1cs file (what `snarkjs wtns check` does): first_bad = -1 if every
+// constraint holds, else the smallest violated row
+int cw_r1cs_check_files(const char *r1cs_path, const char *wtns_path, int device, int64_t *first_bad) {
+    if (!r1cs_path || !wtns_path || !first_bad) return fail(CW_EINVAL, "null argument");
+    cw_r1cs *r = nullptr;
+    int rc = cw_r1cs_load(r1cs_path, &r);
+    if (rc) return rc;
+    std::vector<uint64_t> w;
+    int pid = 0;
+    try {
+        read_wtns(wtns_path, pid, w);
+    } catch (const std::exception &e) {
+        cw_r1cs_destroy(r);
+        return fail(CW_EFORMAT, e.what());
+    }
+    if (pid != r->data.prime_id || w.size() / 4 != r->data.n_wires) {
+        cw_r1cs_destroy(r);
+        return fail(CW_EINVAL, "the witness and the constraint system do not match (prime or number of wires)");
+    }
+    rc = cw_r1cs_check(r, w.data(), 0, 1, device, first_bad, nullptr);
+    cw_r1cs_destroy(r);
+    return rc;
+}
+
 // ---- lowered circuit as a blob / multi-GPU plumbing -----------------------------------------------------------
 int cw_circuit_serialize(const cw_circuit *c, uint8_t *out, size_t cap, size_t *len) {
     if (!c || !len) return fail(CW_EINVAL, "null argument");

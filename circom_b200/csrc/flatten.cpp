@@ -1462,6 +1462,7 @@ struct Lowerer {
         if (remap[0] != 0) throw std::runtime_error("lowering: constant-one signal is not witness entry 0");
         T.consts = consts;
         if (T.consts.empty()) T.consts.push_back(u256_from_u64(0));
+        T.dat_consts = ir_consts;
         // census of the value slots by static width (what narrow slots would store in 4 / 8 bytes)
         for (int k = 0; k < 4; ++k) T.slot_census[k] = 0;
         for (size_t i = 0; i < n_pre + n_prov; ++i) {
@@ -1541,7 +1542,7 @@ struct BlobR {
         p += n;
     }
 };
-constexpr uint32_t BLOB_VERSION = 3;
+constexpr uint32_t BLOB_VERSION = 4;
 }  // namespace
 
 void serialize_tape(const Tape &t, std::vector<uint8_t> &out) {
@@ -1556,7 +1557,7 @@ void serialize_tape(const Tape &t, std::vector<uint8_t> &out) {
                              t.n_slots, t.n_bitwords, t.n_stored};
     w.pod<uint64_t>(sizeof(nums) / 8);
     w.raw(nums, sizeof(nums));
-    w.vec(t.ops); w.vec(t.items); w.vec(t.level_start); w.vec(t.consts); w.vec(t.witness_slot); w.vec(t.input_slot);
+    w.vec(t.ops); w.vec(t.items); w.vec(t.level_start); w.vec(t.consts); w.vec(t.dat_consts); w.vec(t.witness_slot); w.vec(t.input_slot);
     w.vec(t.pk_bit_wire); w.vec(t.pk_u64_wire); w.vec(t.pk_full_wire); w.vec(t.wit_class);
     w.vec(t.fn_code); w.vec(t.fn_info); w.vec(t.call_tab); w.vec(t.witness2signal);
     w.pod<uint64_t>(t.inputs.size());
@@ -1594,7 +1595,7 @@ void deserialize_tape(const uint8_t *data, size_t len, Tape &t) {
     for (int k = 0; k < 4; ++k) t.slot_census[k] = nums[10 + k];
     t.n_slot_operands = nums[14]; t.n_values = nums[15]; t.n_resident = (uint32_t)nums[16]; t.n_pre = (uint32_t)nums[17];
     t.n_slots = (uint32_t)nums[18]; t.n_bitwords = (uint32_t)nums[19]; t.n_stored = nums[20];
-    r.vec(t.ops); r.vec(t.items); r.vec(t.level_start); r.vec(t.consts); r.vec(t.witness_slot); r.vec(t.input_slot);
+    r.vec(t.ops); r.vec(t.items); r.vec(t.level_start); r.vec(t.consts); r.vec(t.dat_consts); r.vec(t.witness_slot); r.vec(t.input_slot);
     r.vec(t.pk_bit_wire); r.vec(t.pk_u64_wire); r.vec(t.pk_full_wire); r.vec(t.wit_class);
     r.vec(t.fn_code); r.vec(t.fn_info); r.vec(t.call_tab); r.vec(t.witness2signal);
     uint64_t n_in;

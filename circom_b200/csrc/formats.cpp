@@ -46,7 +46,7 @@ void write_r1cs(const R1csData &r, const FieldParams &F, const std::string &path
     File f(path, "wb");
     f.w("r1cs", 4);
     f.put<uint32_t>(1);
-    f.put<uint32_t>(3);
+    f.put<uint32_t>(r.has_custom_gates ? 5 : 3);
     // constraints section first
     uint64_t nnz = r.col.size();
     uint64_t m = r.n_constraints;
@@ -80,6 +80,31 @@ void write_r1cs(const R1csData &r, const FieldParams &F, const std::string &path
     f.put<uint32_t>(3);
     f.put<uint64_t>(8 * r.n_wires);
     for (uint64_t i = 0; i < r.n_wires; ++i) f.put<uint64_t>(i);
+    if (r.has_custom_gates) {
+        // custom gates used (r1cs_writer.rs:356-392): u32 count; per gate: NUL-terminated name, u32 #parameters, field elements
+        uint64_t sz = 4;
+        for (auto &g : r.gates_used) sz += g.first.size() + 1 + 4 + 32 * g.second.size();
+        f.put<uint32_t>(4);
+        f.put<uint64_t>(sz);
+        f.put<uint32_t>((uint32_t)r.gates_used.size());
+        for (auto &g : r.gates_used) {
+            f.w(g.first.data(), g.first.size());
+            f.put<uint8_t>(0);
+            f.put<uint32_t>((uint32_t)g.second.size());
+            for (const U256 &p : g.second) f.w(p.v, 32);
+        }
+        // custom gates applied (r1cs_writer.rs:408-440): u32 count; per application: u32 gate index, u32 #wires, u64 wires
+        sz = 4;
+        for (auto &a : r.gates_applied) sz += 8 + 8 * a.second.size();
+        f.put<uint32_t>(5);
+        f.put<uint64_t>(sz);
+        f.put<uint32_t>((uint32_t)r.gates_applied.size());
+        for (auto &a : r.gates_applied) {
+            f.put<uint32_t>(a.first);
+            f.put<uint32_t>((uint32_t)a.second.size());
+            for (uint64_t w : a.second) f.put<uint64_t>(w);
+        }
+    }
 }
 
 void read_r1cs(const std::string &path, R1csData &out) {
@@ -98,7 +123,7 @@ void read_r1cs(const std::string &path, R1csData &out) {
     if (memcmp(buf.data(), "r1cs", 4)) throw std::runtime_error("r1cs: bad magic");
     if (u32(4) != 1) throw std::runtime_error("r1cs: unsupported version");
     uint32_t nsec = u32(8);
-    size_t pos = 12, hdr = 0, cons = 0, hdr_len = 0, cons_len = 0;
+    size_t pos = 12, hdr = 0, cons = 0, hdr_len = 0, cons_len = 0, cgu = 0, cgu_len = 0, cga = 0, cga_len = 0;
     for (uint32_t s = 0; s < nsec; ++s) {
         uint32_t ty = u32(pos);
         uint64_t len = u64(pos + 4);
@@ -106,6 +131,8 @@ void read_r1cs(const std::string &path, R1csData &out) {
         need(pos, len);
         if (ty == 1) { hdr = pos; hdr_len = len; }
         if (ty == 2) { cons = pos; cons_len = len; }
+        if (ty == 4) { cgu = pos; cgu_len = len; }
+        if (ty == 5) { cga = pos; cga_len = len; }
         pos += len;
     }
     if (!hdr || !cons) throw std::runtime_error("r1cs: missing header or constraint section");
@@ -164,6 +191,92 @@ void read_r1cs(const std::string &path, R1csData &out) {
         out.row_ptr.push_back(out.col.size());
     }
     if (out.dict.empty()) out.dict.push_back(u256_from_u64(0));
+    // custom-gate sections (r1cs_reader.rs:343-419): kept verbatim for the writer; the evaluator does not interpret them
+    out.has_custom_gates = cgu != 0 || cga != 0;
+    out.gates_used.clear();
+    out.gates_applied.clear();
+    if (cgu) {
+        size_t q0 = cgu, qe = cgu + cgu_len;
+        if (cgu_len < 4) throw std::runtime_error("r1cs: custom-gate section too short");
+        uint32_t n = u32(q0);
+        q0 += 4;
+        for (uint32_t i = 0; i < n; ++i) {
+            size_t z = q0;
+            while (z < qe && buf[z]) ++z;
+            if (z >= qe) throw std::runtime_error("r1cs: unterminated custom-gate name");
+            std::string name((const char *)&buf[q0], z - q0);
+            q0 = z + 1;
+            if (q0 + 4 > qe) throw std::runtime_error("r1cs: custom-gate section too short");
+            uint32_t np = u32(q0);
+            q0 += 4;
+            if ((uint64_t)np * 32 > qe - q0) throw std::runtime_error("r1cs: custom-gate section too short");
+            std::vector<U256> ps(np);
+            for (uint32_t k = 0; k < np; ++k, q0 += 32) memcpy(ps[k].v, &buf[q0], 32);
+            out.gates_used.emplace_back(std::move(name), std::move(ps));
+        }
+    }
+    if (cga) {
+        size_t q0 = cga, qe = cga + cga_len;
+        if (cga_len < 4) throw std::runtime_error("r1cs: custom-gate section too short");
+        uint32_t n = u32(q0);
+        q0 += 4;
+        for (uint32_t i = 0; i < n; ++i) {
+            if (q0 + 8 > qe) throw std::runtime_error("r1cs: custom-gate section too short");
+            uint32_t gi = u32(q0), ns = u32(q0 + 4);
+            q0 += 8;
+            if ((uint64_t)ns * 8 > qe - q0) throw std::runtime_error("r1cs: custom-gate section too short");
+            if (gi >= out.gates_used.size()) throw std::runtime_error("r1cs: custom-gate application names an unknown gate");
+            std::vector<uint64_t> ws(ns);
+            for (uint32_t k = 0; k < ns; ++k, q0 += 8) ws[k] = u64(q0);
+            out.gates_applied.emplace_back(gi, std::move(ws));
+        }
+    }
+}
+
+// .wtns: "wtns", u32 version 2, u32 2 sections; section 1 = {u32 n8 = 32, prime, u32 nVars}; section 2 = nVars x 32 bytes
+void read_wtns(const std::string &path, int &prime_id, std::vector<uint64_t> &witness) {
+    File f(path, "rb");
+    fseek(f.f, 0, SEEK_END);
+    long sz = ftell(f.f);
+    fseek(f.f, 0, SEEK_SET);
+    std::vector<uint8_t> buf(sz);
+    if (sz && fread(buf.data(), 1, sz, f.f) != (size_t)sz) throw std::runtime_error("wtns: read failed");
+    auto need = [&](size_t off, size_t n) {
+        if (n > buf.size() || off > buf.size() - n) throw std::runtime_error("wtns: truncated file");
+    };
+    auto u32 = [&](size_t off) { need(off, 4); uint32_t v; memcpy(&v, &buf[off], 4); return v; };
+    auto u64 = [&](size_t off) { need(off, 8); uint64_t v; memcpy(&v, &buf[off], 8); return v; };
+    need(0, 12);
+    if (memcmp(buf.data(), "wtns", 4)) throw std::runtime_error("wtns: bad magic");
+    if (u32(4) != 2) throw std::runtime_error("wtns: unsupported version");
+    uint32_t nsec = u32(8);
+    size_t pos = 12, s1 = 0, s1_len = 0, s2 = 0, s2_len = 0;
+    for (uint32_t s = 0; s < nsec; ++s) {
+        uint32_t ty = u32(pos);
+        uint64_t len = u64(pos + 4);
+        pos += 12;
+        need(pos, len);
+        if (ty == 1) { s1 = pos; s1_len = len; }
+        if (ty == 2) { s2 = pos; s2_len = len; }
+        pos += len;
+    }
+    if (!s1 || !s2 || s1_len < 4 + 32 + 4) throw std::runtime_error("wtns: missing section");
+    if (u32(s1) != 32) throw std::runtime_error("wtns: only 32-byte fields are supported");
+    U256 q;
+    memcpy(q.v, &buf[s1 + 4], 32);
+    if (q == make_field(0).q) prime_id = 0;
+    else if (q == make_field(1).q) prime_id = 1;
+    else throw std::runtime_error("wtns: unsupported prime");
+    uint32_t n = u32(s1 + 36);
+    if ((uint64_t)n * 32 != s2_len) throw std::runtime_error("wtns: witness section has the wrong size");
+    witness.resize((size_t)n * 4);
+    memcpy(witness.data(), &buf[s2], (size_t)n * 32);
+    FieldParams F = make_field(prime_id);
+    for (uint32_t i = 0; i < n; ++i) {
+        U256 v;
+        memcpy(v.v, &witness[(size_t)i * 4], 32);
+        if (!(v < F.q)) throw std::runtime_error("wtns: value not reduced modulo the prime");
+    }
 }
 
 // writeBinWitness (c_elements/common/main.cpp:288-334)
@@ -198,6 +311,27 @@ void write_dat(const Tape &t, const std::string &path) {
         f.put<uint64_t>(e.signalsize);
     }
     for (uint64_t i = 0; i < t.n_witness; ++i) f.put<uint64_t>(t.witness2signal[i]);
+    // circuitConstants (generate_dat_constant_list, c_code_generator.rs:616-679): 40 bytes per constant -
+    // {i32 shortVal, u32 type, n * R mod q}: values inside the signed 32-bit range carry shortVal and type
+    // 0x40000000 (short + Montgomery), all others 0 and 0xC0000000 (long Montgomery)
+    for (const U256 &c : t.dat_consts) {
+        U256 neg;
+        u256_sub(neg, t.F.q, c);
+        const bool is_neg = t.F.half < c;  // the signed view of generic/fr.cpp:1184-1218
+        const U256 &mag = is_neg ? neg : c;
+        const bool small = !(mag.v[1] | mag.v[2] | mag.v[3]) && (is_neg ? mag.v[0] <= 2147483648ull : mag.v[0] <= 2147483647ull);
+        if (small) {
+            f.put<int32_t>(is_neg ? (int32_t)(0 - (int64_t)mag.v[0]) : (int32_t)mag.v[0]);
+            f.put<uint32_t>(0x40000000u);
+        } else {
+            f.put<int32_t>(0);
+            f.put<uint32_t>(0xC0000000u);
+        }
+        U256 m = t.F.to_mont(c);
+        f.w(m.v, 32);
+    }
+    // (templateInsId2IOSignalInfo, c_code_generator.rs:681-794: empty - circuits with run-time component
+    // indexing are outside what the lowering accepts)
 }
 
 }  // namespace cw

@@ -41,6 +41,10 @@ struct R1csData {
     std::vector<uint32_t> coef;     // index into dict
     std::vector<U256> dict;         // distinct coefficients, canonical
     uint32_t n_pub_out = 0, n_pub_in = 0, n_prv_in = 0;
+    // custom-gate sections 4 / 5 of a PLONK-style .r1cs (r1cs_writer.rs:356-454): carried through read -> write unchanged
+    bool has_custom_gates = false;
+    std::vector<std::pair<std::string, std::vector<U256>>> gates_used;        // (template name, parameters)
+    std::vector<std::pair<uint32_t, std::vector<uint64_t>>> gates_applied;   // (index into gates_used, wires)
 };
 
 struct Tape {
@@ -60,6 +64,7 @@ struct Tape {
     std::vector<uint32_t> items;        // n_items + 1: work item k = tape words [items[k], items[k+1])
     std::vector<uint32_t> level_start;  // n_levels + 1, indexes work items
     std::vector<U256> consts;           // raw limb patterns (already in the form the consumer needs)
+    std::vector<U256> dat_consts;       // the circuit's constant list as the .dat carries it (canonical; c_code_generator.rs:616-679)
     std::vector<uint32_t> witness_slot; // per witness entry (identity: witness entry i lives in slot i)
     std::vector<uint32_t> input_slot;   // slot of main input i
     // witness entries by static size class, for the packed device->host transfer
@@ -91,5 +96,7 @@ void write_r1cs(const R1csData &r, const FieldParams &F, const std::string &path
 void read_r1cs(const std::string &path, R1csData &out);
 std::vector<uint8_t> wtns_bytes(const FieldParams &F, const uint64_t *witness, uint64_t n_witness);
 void write_dat(const Tape &t, const std::string &path);
+// .wtns (main.cpp:288-334 / witness_calculator.js:212-276): returns the witness as 4 x u64 limbs per entry
+void read_wtns(const std::string &path, int &prime_id, std::vector<uint64_t> &witness);
 
 }  // namespace cw

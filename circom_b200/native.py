@@ -96,6 +96,8 @@ def _load() -> ctypes.CDLL:
         "cw_host_expand_isa": (c_char_p, []),
         "cw_host_pool_info": (c_char_p, []),
         "cw_host_expand_bench": (c_int, [P, c_uint32, c_uint32, c_int, c_void_p]),
+        "cw_wtns_read": (c_int, [c_char_p, POINTER(c_int), POINTER(c_uint64), c_void_p, c_size_t]),
+        "cw_r1cs_check_files": (c_int, [c_char_p, c_char_p, c_int, POINTER(c_int64)]),
         "cw_batch_witness_device": (c_int, [P, POINTER(c_void_p)]),
         "cw_batch_witness_strided": (c_int, [P, POINTER(c_void_p), POINTER(c_uint64)]),
         "cw_batch_stream": (c_void_p, [P]),

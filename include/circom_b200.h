@@ -129,8 +129,8 @@ int cw_circuit_tape_items(const cw_circuit *c, uint32_t *items);
 int cw_circuit_slot_census(const cw_circuit *c, uint64_t out[4]);
 /* witness2SignalList (calcwit.hpp:54-56, c_code_generator.rs:605-614): n_witness entries */
 int cw_circuit_witness2signal(const cw_circuit *c, uint64_t *out);
-/* save / load the reference's .dat layout for the input hash map + witness2signal list
- * (c_code_generator.rs:575-603,605-614,818-865) */
+/* the reference's .dat (generate_dat_file, c_code_generator.rs:818-865): input hash map (:575-603), witness2signal list
+ * (:605-614), circuit constants in the 40-byte tagged Montgomery form (:616-679); the io-map section is empty */
 int cw_circuit_write_dat(const cw_circuit *c, const char *path);
 
 /* ---- batch: Circom_CalcWit for `batch` independent inputs on one GPU ------------------------ */
@@ -261,6 +261,12 @@ int cw_batch_gather_witness_packed(cw_comm *cm, cw_batch *b, uint32_t first, uin
                                    uint32_t *recv_device, uint32_t *send_scratch_device, float *ms);
 /* out[0] = instances with a failed assert, out[1] = instances with a runtime error, summed over all ranks */
 int cw_status_allreduce(cw_comm *cm, cw_batch *b, uint64_t out[2]);
+
+/* ---- file boundary (the consumers of these files: snarkjs, rapidsnark) ---------------------------------- */
+/* the entries of a .wtns (layout main.cpp:288-334): out[n_witness][4] canonical limbs; out = NULL returns the count */
+int cw_wtns_read(const char *path, int *prime_id, uint64_t *n_witness, uint64_t *out, size_t cap_entries);
+/* A.w o B.w == C.w for a .wtns file against a .r1cs file: *first_bad = -1 or the smallest violated row */
+int cw_r1cs_check_files(const char *r1cs_path, const char *wtns_path, int device, int64_t *first_bad);
 
 /* ---- field library, batched (parity tests of the device Fr_* equivalents, fr.hpp:28-70) ------ */
 /* r[i] = op(a[i], b[i], c[i]) for i < n on `device`; canonical in / canonical out; b, c may be NULL */

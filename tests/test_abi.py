@@ -64,7 +64,7 @@ def test_dat_layout(tmp_path):
     p = str(tmp_path / "m.dat")
     c.write_dat(p)
     raw = open(p, "rb").read()
-    assert len(raw) == 256 * 24 + 4 * 8
+    assert len(raw) == 256 * 24 + 4 * 8 + 40 * len(d.consts)
     ent = {}
     for i in range(256):
         h, sid, sz = struct.unpack_from("<QQQ", raw, i * 24)
@@ -148,3 +148,23 @@ def test_packed_record_layout_and_host_expansion():
                 assert got == wit, (compact, bits, misalign)
                 assert int(buf[base + c.n_witness * 4]) == 0xDEADBEEFDEADBEEF and (base == 0 or int(buf[base - 1]) == 0xDEADBEEFDEADBEEF)
     assert native.lib.cw_host_expand_isa() in (b"avx512", b"avx2", b"sse2")
+
+
+@pytest.mark.parametrize("prime", ["bn128", "bls12381"])
+def test_dat_equals_the_file_the_reference_runtime_loads(prime, tmp_path):
+    """cw_circuit_write_dat (--O0 witness list) == the .dat the reference calculators of oracle/_ref are linked with
+    (oracle/emit_ref_cpp.dat_bytes, consumed by the reference's loadCircuit, main.cpp:22-124): hash map, witness list
+    and the constants in their 40-byte tagged Montgomery form (short constants incl. negative ones, long ones)"""
+    from oracle.emit_ref_cpp import dat_bytes
+    for mk in (lambda d: C.all_ops(d), lambda d: C.poseidon(d, 2), lambda d: C.int_div(d, 32), lambda d: C.less_than(d, 8)):
+        d = CircuitDesc(prime)
+        d.set_main(mk(d))
+        d.const_id(-5)
+        d.const_id(2**31 - 1)
+        d.const_id(-2**31)
+        d.const_id(2**31)
+        d.const_id(-2**31 - 1)
+        c = Circuit(d, host_only=True, o0=True)
+        p = str(tmp_path / "c.dat")
+        c.write_dat(p)
+        assert open(p, "rb").read() == dat_bytes(d)

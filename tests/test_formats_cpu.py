@@ -1,6 +1,7 @@
 """File formats checked with an independent python reader: the `.r1cs` the back end writes is parsed here
 from the format definition (constraint_writers/src/r1cs_writer.rs:6-14,49-72,246-269,328-341) and its
 constraints are evaluated with python integers on oracle witnesses; plus lowering edge cases."""
+import os
 import struct
 
 import numpy as np
@@ -209,3 +210,59 @@ def test_r1cs_with_custom_gate_sections_loads(tmp_path):
     open(p2, "wb").write(raw)
     r = R1cs(p2)
     assert r.n_constraints == c.stats["n_constraints"] and r.n_wires == c.n_witness
+
+
+def test_custom_gate_sections_round_trip(tmp_path):
+    """sections 4 / 5 (custom gates used: NUL-terminated template name + field-element parameters; custom gates applied:
+    gate index + wire list - constraint_writers/src/r1cs_writer.rs:356-454, read back by r1cs_reader.rs:343-419) survive
+    load -> write byte for byte, in the reference's section order (constraints, header, wire map, gates used, applied)"""
+    d = CircuitDesc("bn128")
+    d.set_main(C.less_than(d, 8))
+    c = Circuit(d, host_only=True)
+    p = str(tmp_path / "a.r1cs")
+    R1cs(c).write(p)
+    raw = bytearray(open(p, "rb").read())
+    raw[8:12] = struct.pack("<I", 5)
+    used = struct.pack("<I", 2)
+    used += b"Poseidon\0" + struct.pack("<I", 2) + (3).to_bytes(32, "little") + (d.q - 1).to_bytes(32, "little")
+    used += b"EmptyGate\0" + struct.pack("<I", 0)
+    applied = struct.pack("<I", 3)
+    applied += struct.pack("<II", 0, 3) + struct.pack("<3Q", 1, 2, 5)
+    applied += struct.pack("<II", 1, 0)
+    applied += struct.pack("<II", 0, 1) + struct.pack("<Q", 7)
+    raw += struct.pack("<IQ", 4, len(used)) + used + struct.pack("<IQ", 5, len(applied)) + applied
+    p2 = str(tmp_path / "b.r1cs")
+    open(p2, "wb").write(raw)
+    r = R1cs(p2)
+    assert r.n_constraints == c.stats["n_constraints"]
+    p3 = str(tmp_path / "c.r1cs")
+    r.write(p3)
+    assert open(p3, "rb").read() == bytes(raw)
+    # an application that names a gate which is not in the list is refused
+    bad = bytearray(raw)
+    off = len(raw) - len(applied) + 4
+    bad[off:off + 4] = struct.pack("<I", 9)
+    open(p2, "wb").write(bad)
+    with pytest.raises(Exception):
+        R1cs(p2)
+
+
+def test_wtns_reader_round_trip(tmp_path):
+    """cw_wtns_read parses what writeBinWitness writes (main.cpp:288-334; golden fixture bytes from the reference
+    calculator) and refuses damaged files"""
+    import ctypes
+    import zlib
+    from circom_b200 import native
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    raw = zlib.decompress(open(os.path.join(here, "poseidon2_0.wtns.z"), "rb").read())
+    p = str(tmp_path / "p.wtns")
+    open(p, "wb").write(raw)
+    pid, n = ctypes.c_int(), ctypes.c_uint64()
+    assert native.lib.cw_wtns_read(p.encode(), ctypes.byref(pid), ctypes.byref(n), None, 0) == 0
+    assert pid.value == 0 and n.value * 32 + 76 == len(raw)
+    out = np.zeros((n.value, 4), dtype=np.uint64)
+    assert native.lib.cw_wtns_read(p.encode(), ctypes.byref(pid), ctypes.byref(n), out.ctypes.data, n.value) == 0
+    assert out.tobytes() == raw[76:]
+    for damaged in (raw[:100], raw[:4] + b"\x03" + raw[5:], b"wtnz" + raw[4:], raw[:76] + b"\xff" * 32 + raw[108:]):
+        open(p, "wb").write(damaged)
+        assert native.lib.cw_wtns_read(p.encode(), ctypes.byref(pid), ctypes.byref(n), None, 0) == native.CW_EFORMAT

@@ -375,3 +375,26 @@ def test_packed_device_to_host_transfer_equals_plain_copy(monkeypatch):
     w2s = c.witness2signal().astype(np.int64)
     exp = evaluate(d, ins[5])
     assert limbs_to_ints(packed[5]) == [exp[k] for k in w2s]
+
+
+def test_r1cs_check_of_files(tmp_path):
+    """cw_r1cs_check_files: a .wtns (ours, or the reference calculator's golden fixture) against a .r1cs file"""
+    import zlib, os, json
+    d = CircuitDesc("bn128")
+    d.set_main(C.poseidon(d, 2))
+    c = Circuit(d, o0=True)                    # the reference calculators write every signal (--O0 witness list)
+    rp = str(tmp_path / "p.r1cs")
+    R1cs(c).write(rp)
+    wc = WitnessCalculator(c)
+    wp = str(tmp_path / "p.wtns")
+    open(wp, "wb").write(wc.calculateWTNSBin({"inputs": ["1", "2"]}))
+    fb = ctypes.c_int64(7)
+    assert native.lib.cw_r1cs_check_files(rp.encode(), wp.encode(), 0, ctypes.byref(fb)) == 0 and fb.value == -1
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    raw = zlib.decompress(open(os.path.join(here, "poseidon2_0.wtns.z"), "rb").read())
+    open(wp, "wb").write(raw)                  # bytes written by the reference calculator
+    assert native.lib.cw_r1cs_check_files(rp.encode(), wp.encode(), 0, ctypes.byref(fb)) == 0 and fb.value == -1
+    bad = bytearray(raw)
+    bad[76 + 32 * 5] ^= 1                      # one witness entry off by one
+    open(wp, "wb").write(bad)
+    assert native.lib.cw_r1cs_check_files(rp.encode(), wp.encode(), 0, ctypes.byref(fb)) == 0 and fb.value >= 0

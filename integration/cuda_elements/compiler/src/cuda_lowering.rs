@@ -1,0 +1,318 @@
+// compiler/src/cuda_lowering.rs  (new; `mod cuda_lowering;` in compiler/src/lib.rs, `WriteCuda` re-exported from
+// translating_traits/mod.rs beside WriteC / WriteWasm, mod.rs:5-29)
+//
+// produce_c (template.rs:281-472 + the bucket emitters) prints C++ that RE-EXECUTES circom's compile-time control flow
+// at run time: loops over `lvar` counters, index arithmetic, sub-component bookkeeping.  The CUDA producer executes
+// that part HERE, once, by partial evaluation of the IR: every variable slot is either Known(BigInt) - evaluated with
+// circom_algebra::modular_arithmetic, exactly what the C++ would compute - or Dynamic(Ref), a value that depends on
+// signals and therefore becomes a .cb2c operation.  Template bodies come out as straight-line op lists; function bodies
+// (whose control flow may depend on run-time values) keep their loops as register code with jumps.
+//
+// Written against circom 2.2.3, not compiled in circom_b200's build image.  `Err(())` marks what format version 1
+// does not express (docs/CB2C.md, last section).
+use crate::circuit_design::{function::FunctionCodeInfo, template::TemplateCodeInfo};
+use crate::intermediate_representation::ir_interface::*;
+use circom_algebra::modular_arithmetic as ma;
+use code_producers::cuda_elements::*;
+use num_bigint_dig::BigInt;
+
+#[derive(Clone)]
+pub enum Val { Known(BigInt), Dynamic(Ref) }
+
+pub struct TemplateCtx<'a> {
+    pub producer: &'a CUDAProducer,
+    pub file: &'a mut Cb2cFile,
+    pub q: BigInt,
+    pub rec: TemplateRecord,
+    pub vars: Vec<Val>,                 // lvar[]: template.rs:288
+    pub sub_of_cmp: Vec<u32>,           // component slot -> index into rec.subs (CreateCmpBucket order)
+    pub n_out: usize, pub n_in: usize,
+}
+
+pub trait WriteCuda {
+    /// evaluates the instruction; a value-producing instruction returns where its value is
+    fn produce_cuda(&self, cx: &mut TemplateCtx) -> Result<Option<Val>, ()>;
+}
+
+impl<'a> TemplateCtx<'a> {
+    fn tmp(&mut self) -> Ref { self.rec.n_tmp += 1; Ref::Tmp(self.rec.n_tmp - 1) }
+    fn emit(&mut self, op: Op, a: Ref, b: Ref, c: Ref) -> Ref {
+        let d = self.tmp();
+        self.rec.ops.push(OpRec { op, d, a, b, c });
+        d
+    }
+    fn as_ref(&mut self, v: &Val) -> Ref {
+        match v {
+            Val::Known(k) => { let q = self.q.clone(); Ref::Const(self.file.const_id(k, &q)) }
+            Val::Dynamic(r) => *r,
+        }
+    }
+    /// `Fr_toInt` of an address expression: addresses inside templates are compile-time values
+    fn address(&mut self, i: &InstructionPointer) -> Result<usize, ()> {
+        match i.produce_cuda(self)? {
+            Some(Val::Known(k)) => k.to_u64_digits().1.first().map(|x| *x as usize).or(Some(0)).ok_or(()),
+            _ => Err(()), // run-time addressing (ToAddress of a signal-dependent value): not in version 1
+        }
+    }
+    /// signal index inside this template -> reference (outputs, inputs, intermediates: executed_template.rs:442-552)
+    fn own(&self, idx: usize) -> Ref { Ref::Own(idx as u32) }
+}
+
+fn operator_code(op: &OperatorType) -> Result<Op, ()> {
+    use OperatorType::*;
+    Ok(match op {
+        Mul => Op::MUL, Div => Op::DIV, Add => Op::ADD, Sub => Op::SUB, Pow => Op::POW, IntDiv => Op::IDIV, Mod => Op::MOD,
+        ShiftL => Op::SHL, ShiftR => Op::SHR, LesserEq => Op::LEQ, GreaterEq => Op::GEQ, Lesser => Op::LT, Greater => Op::GT,
+        Eq(SizeOption::Single(1)) => Op::EQ, NotEq => Op::NEQ, BoolOr => Op::LOR, BoolAnd => Op::LAND, BoolNot => Op::LNOT,
+        BitOr => Op::BOR, BitAnd => Op::BAND, BitXor => Op::BXOR, Complement => Op::BNOT, PrefixSub => Op::NEG,
+        Eq(_) => return Err(()),               // array equality: expand element-wise upstream
+        ToAddress | MulAddress | AddAddress => unreachable!("address arithmetic is evaluated, never emitted"),
+    })
+}
+
+fn eval_known(op: &OperatorType, a: &BigInt, b: Option<&BigInt>, q: &BigInt) -> Result<BigInt, ()> {
+    use OperatorType::*;
+    let b0 = BigInt::from(0);
+    let b = b.unwrap_or(&b0);
+    Ok(match op {
+        Mul | MulAddress => ma::mul(a, b, q), Add | AddAddress => ma::add(a, b, q), Sub => ma::sub(a, b, q),
+        Div => ma::div(a, b, q).map_err(|_| {})?, IntDiv => ma::idiv(a, b, q).map_err(|_| {})?,
+        Mod => ma::mod_op(a, b, q).map_err(|_| {})?, Pow => ma::pow(a, b, q),
+        ShiftL => ma::shift_l(a, b, q).map_err(|_| {})?, ShiftR => ma::shift_r(a, b, q).map_err(|_| {})?,
+        LesserEq => ma::lesser_eq(a, b, q), GreaterEq => ma::greater_eq(a, b, q), Lesser => ma::lesser(a, b, q),
+        Greater => ma::greater(a, b, q), Eq(_) => ma::eq(a, b, q), NotEq => ma::not_eq(a, b, q),
+        BoolOr => ma::bool_or(a, b, q), BoolAnd => ma::bool_and(a, b, q), BoolNot => ma::not(a, q),
+        BitOr => ma::bit_or(a, b, q), BitAnd => ma::bit_and(a, b, q), BitXor => ma::bit_xor(a, b, q),
+        Complement => ma::complement_256(a, q), PrefixSub => ma::prefix_sub(a, q), ToAddress => a.clone(),
+    })
+}
+
+impl WriteCuda for Instruction {
+    fn produce_cuda(&self, cx: &mut TemplateCtx) -> Result<Option<Val>, ()> {
+        use Instruction::*;
+        match self {
+            Value(v) => v.produce_cuda(cx), Load(v) => v.produce_cuda(cx), Store(v) => v.produce_cuda(cx),
+            Compute(v) => v.produce_cuda(cx), Call(v) => v.produce_cuda(cx), Branch(v) => v.produce_cuda(cx),
+            Return(_) => Err(()),                 // only inside functions (FunctionCtx below)
+            Assert(v) => v.produce_cuda(cx), Log(_) => Ok(None), // log(): no effect on the witness (log_bucket.rs:105-135)
+            Loop(v) => v.produce_cuda(cx), CreateCmp(v) => v.produce_cuda(cx),
+        }
+    }
+}
+
+impl WriteCuda for ValueBucket {   // value_bucket.rs:81-87
+    fn produce_cuda(&self, cx: &mut TemplateCtx) -> Result<Option<Val>, ()> {
+        Ok(Some(Val::Known(match self.parse_as {
+            ValueType::U32 => BigInt::from(self.value),
+            ValueType::BigInt => cx.producer.field_tracking[self.value].parse::<BigInt>().map_err(|_| {})?,
+        })))
+    }
+}
+
+impl WriteCuda for ComputeBucket { // compute_bucket.rs:276-400
+    fn produce_cuda(&self, cx: &mut TemplateCtx) -> Result<Option<Val>, ()> {
+        let mut args = vec![];
+        for a in &self.stack { args.push(a.produce_cuda(cx)?.ok_or(())?); }
+        if let (Some(Val::Known(a)), b) = (args.get(0), args.get(1)) {
+            let kb = match b { Some(Val::Known(k)) => Some(Some(k)), None => Some(None), _ => None };
+            if let Some(kb) = kb { let q = cx.q.clone(); return Ok(Some(Val::Known(eval_known(&self.op, a, kb, &q)?))); }
+        }
+        let ra = cx.as_ref(&args[0]);
+        let rb = if args.len() > 1 { cx.as_ref(&args[1]) } else { Ref::None };
+        Ok(Some(Val::Dynamic(cx.emit(operator_code(&self.op)?, ra, rb, Ref::None))))
+    }
+}
+
+impl WriteCuda for LoadBucket {    // load_bucket.rs:325-447
+    fn produce_cuda(&self, cx: &mut TemplateCtx) -> Result<Option<Val>, ()> {
+        let idx = match &self.src {
+            LocationRule::Indexed { location, .. } => cx.address(location)?,
+            LocationRule::Mapped { .. } => return Err(()), // templateInsId2IOSignalInfo lookups: not in version 1
+        };
+        Ok(Some(match &self.address_type {
+            AddressType::Variable => cx.vars[idx].clone(),
+            AddressType::Signal => Val::Dynamic(cx.own(idx)),
+            AddressType::SubcmpSignal { cmp_address, .. } => {
+                let cmp = cx.address(cmp_address)?;
+                Val::Dynamic(Ref::Sub { sub: cx.sub_of_cmp[cmp], idx: idx as u32 })
+            }
+        }))
+    }
+}
+
+impl WriteCuda for StoreBucket {   // store_bucket.rs:607-834
+    fn produce_cuda(&self, cx: &mut TemplateCtx) -> Result<Option<Val>, ()> {
+        if self.context.size != SizeOption::Single(1) { return Err(()); } // array copies: expanded by the caller per element
+        let v = self.src.produce_cuda(cx)?.ok_or(())?;
+        let idx = match &self.dest {
+            LocationRule::Indexed { location, .. } => cx.address(location)?,
+            LocationRule::Mapped { .. } => return Err(()),
+        };
+        match &self.dest_address_type {
+            AddressType::Variable => { cx.vars[idx] = v; }
+            AddressType::Signal => { let a = cx.as_ref(&v); let d = cx.own(idx); cx.rec.ops.push(OpRec { op: Op::COPY, d, a, b: Ref::None, c: Ref::None }); }
+            AddressType::SubcmpSignal { cmp_address, input_information, .. } => {
+                // the trigger (inputCounter, StatusInput::Last / NoLast, store_bucket.rs:660-734) is re-derived by the
+                // lowering from the order of the stores; a trigger that depends on run-time values is not expressible
+                if let InputInformation::Input { status: StatusInput::Unknown, .. } = input_information {
+                    // still fine when all stores of this component are compile-time ordered (the common case);
+                    // the lowering reports "never received all its inputs" otherwise
+                }
+                let cmp = cx.address(cmp_address)?;
+                let a = cx.as_ref(&v);
+                cx.rec.ops.push(OpRec { op: Op::COPY, d: Ref::Sub { sub: cx.sub_of_cmp[cmp], idx: idx as u32 }, a, b: Ref::None, c: Ref::None });
+            }
+        }
+        Ok(None)
+    }
+}
+
+impl WriteCuda for LoopBucket {    // loop_bucket.rs:76-91: unrolled - the condition must be compile-time
+    fn produce_cuda(&self, cx: &mut TemplateCtx) -> Result<Option<Val>, ()> {
+        loop {
+            match self.continue_condition.produce_cuda(cx)? {
+                Some(Val::Known(c)) => { if c == BigInt::from(0) { return Ok(None); } }
+                _ => return Err(()), // a template loop on a signal-dependent condition cannot generate constraints either
+            }
+            for i in &self.body { i.produce_cuda(cx)?; }
+        }
+    }
+}
+
+impl WriteCuda for BranchBucket {  // branch_bucket.rs:100-122
+    fn produce_cuda(&self, cx: &mut TemplateCtx) -> Result<Option<Val>, ()> {
+        match self.cond.produce_cuda(cx)? {
+            Some(Val::Known(c)) => {
+                for i in if c != BigInt::from(0) { &self.if_branch } else { &self.else_branch } { i.produce_cuda(cx)?; }
+                Ok(None)
+            }
+            Some(Val::Dynamic(c)) => {
+                // `var v = cond ? a : b` / if-else over variables with a run-time condition: both arms are evaluated on
+                // copies of the variable state and merged with SELECT (total: x/0 = 0).  Arms that store signals or
+                // create components under a run-time condition are refused.
+                let before = cx.vars.clone();
+                let n_ops = cx.rec.ops.len();
+                for i in &self.if_branch { i.produce_cuda(cx)?; }
+                let then_vars = std::mem::replace(&mut cx.vars, before);
+                for i in &self.else_branch { i.produce_cuda(cx)?; }
+                if cx.rec.ops[n_ops..].iter().any(|o| !matches!(o.d, Ref::Tmp(_))) { return Err(()); }
+                for k in 0..cx.vars.len() {
+                    let (t, e) = (then_vars[k].clone(), cx.vars[k].clone());
+                    let same = match (&t, &e) { (Val::Known(x), Val::Known(y)) => x == y, (Val::Dynamic(x), Val::Dynamic(y)) => x == y, _ => false };
+                    if !same {
+                        let (rt, re) = (cx.as_ref(&t), cx.as_ref(&e));
+                        cx.vars[k] = Val::Dynamic(cx.emit(Op::SELECT, rt, re, c));
+                    }
+                }
+                Ok(None)
+            }
+            None => Err(()),
+        }
+    }
+}
+
+impl WriteCuda for AssertBucket {  // assert_bucket.rs:70-88
+    fn produce_cuda(&self, cx: &mut TemplateCtx) -> Result<Option<Val>, ()> {
+        if self.is_constraint_equality && cx.producer.sanity_check_style == 0 { return Ok(None); }
+        // `a === b` arrives as Compute(Eq, [a, b]): keep the two sides so that the lowering can compare representations
+        if let Instruction::Compute(c) = self.evaluate.as_ref() {
+            if let OperatorType::Eq(SizeOption::Single(1)) = c.op {
+                let a = c.stack[0].produce_cuda(cx)?.ok_or(())?;
+                let b = c.stack[1].produce_cuda(cx)?.ok_or(())?;
+                let (ra, rb) = (cx.as_ref(&a), cx.as_ref(&b));
+                cx.rec.ops.push(OpRec { op: Op::ASSERT_EQ, d: Ref::None, a: ra, b: rb, c: Ref::None });
+                return Ok(None);
+            }
+        }
+        let v = self.evaluate.produce_cuda(cx)?.ok_or(())?;
+        let a = cx.as_ref(&v);
+        cx.rec.ops.push(OpRec { op: Op::ASSERT, d: Ref::None, a, b: Ref::None, c: Ref::None });
+        Ok(None)
+    }
+}
+
+impl WriteCuda for CreateCmpBucket { // create_component_bucket.rs:204-352
+    fn produce_cuda(&self, cx: &mut TemplateCtx) -> Result<Option<Val>, ()> {
+        if self.is_part_mixed_array_not_uniform_parallel || self.has_inputs == false && false { return Err(()); }
+        let first = cx.address(&self.sub_cmp_id)?;
+        for (k, _parallel) in &self.defined_positions {            // `parallel` is ignored: every component is data-parallel here
+            let slot = first + *k;
+            if cx.sub_of_cmp.len() <= slot { cx.sub_of_cmp.resize(slot + 1, u32::MAX); }
+            cx.sub_of_cmp[slot] = cx.rec.subs.len() as u32;
+            cx.rec.subs.push(self.template_id as u32);             // template ids = order of Circuit::templates
+        }
+        Ok(None)
+    }
+}
+
+impl WriteCuda for CallBucket {    // call_bucket.rs:466-533
+    fn produce_cuda(&self, cx: &mut TemplateCtx) -> Result<Option<Val>, ()> {
+        if self.argument_types.iter().any(|t| t.size != SizeOption::Single(1)) { return Err(()); } // array arguments: one ARG per element upstream
+        let fid = cx.producer_function_id(&self.symbol)?;
+        for a in &self.arguments {
+            let v = a.produce_cuda(cx)?.ok_or(())?;
+            let r = cx.as_ref(&v);
+            cx.rec.ops.push(OpRec { op: Op::ARG, d: Ref::None, a: r, b: Ref::None, c: Ref::None });
+        }
+        let d = cx.tmp();
+        cx.rec.ops.push(OpRec { op: Op::CALL, d, a: Ref::Imm(fid), b: Ref::Imm(self.arguments.len() as u32), c: Ref::None });
+        match &self.return_info {
+            ReturnType::Intermediate { .. } => Ok(Some(Val::Dynamic(d))),
+            ReturnType::Final(f) => {                               // `x <-- f(...)`: the store is part of the bucket
+                if f.context.size != SizeOption::Single(1) { return Err(()); } // array results: one call per element
+                let idx = match &f.dest { LocationRule::Indexed { location, .. } => cx.address(location)?, _ => return Err(()) };
+                match &f.dest_address_type {
+                    AddressType::Variable => cx.vars[idx] = Val::Dynamic(d),
+                    AddressType::Signal => { let o = cx.own(idx); cx.rec.ops.push(OpRec { op: Op::COPY, d: o, a: d, b: Ref::None, c: Ref::None }); }
+                    AddressType::SubcmpSignal { cmp_address, .. } => {
+                        let cmp = cx.address(cmp_address)?;
+                        cx.rec.ops.push(OpRec { op: Op::COPY, d: Ref::Sub { sub: cx.sub_of_cmp[cmp], idx: idx as u32 }, a: d, b: Ref::None, c: Ref::None });
+                    }
+                }
+                Ok(None)
+            }
+        }
+    }
+}
+
+// Function bodies keep their control flow: registers = the function's variable slots (FunctionCodeInfo::
+// max_number_of_vars) + expression temporaries; LoopBucket -> JZ / JMP, BranchBucket -> JZ / JMP, ReturnBucket -> RET,
+// Load/Store of `Variable` with a run-time index -> LOADX / STOREX (compute_bucket.rs:361-363 ToAddress = Fr_toInt).
+// The walk is the same as above with `Val::Dynamic(Ref::Tmp(reg))` everywhere; see docs/CB2C.md "function".
+pub fn lower_function(f: &FunctionCodeInfo, producer: &CUDAProducer, file: &mut Cb2cFile) -> Result<FunctionRecord, ()> {
+    let mut rec = FunctionRecord { name: f.header.clone(), n_params: f.params.iter().map(|p| p.length.iter().product::<usize>().max(1)).sum::<usize>() as u32,
+                                   n_regs: f.max_number_of_vars as u32, code: vec![] };
+    if rec.n_regs > 192 { return Err(()); }
+    function_body(&f.body, producer, file, &mut rec)?;
+    Ok(rec)
+}
+
+/// Circuit::produce_cuda: the counterpart of Circuit::produce_c (circuit.rs:596-612)
+pub fn produce_cb2c(templates: &[Box<TemplateCodeInfo>], functions: &[Box<FunctionCodeInfo>], producer: &CUDAProducer,
+                    constraints_of: &dyn Fn(usize) -> Vec<[Vec<(Ref, BigInt)>; 3]>) -> Result<Cb2cFile, ()> {
+    let q = producer.prime_str.parse::<BigInt>().map_err(|_| {})?;
+    let mut file = Cb2cFile::default();
+    file.prime = producer.prime_id()?;
+    for f in functions { let r = lower_function(f, producer, &mut file)?; file.functions.push(r); }
+    for t in templates {
+        if t.is_extern_c { return Err(()); }
+        let mut cx = TemplateCtx { producer, file: &mut file, q: q.clone(), rec: TemplateRecord::default(),
+                                   vars: vec![Val::Known(BigInt::from(0)); t.var_stack_depth], sub_of_cmp: vec![],
+                                   n_out: t.number_of_outputs, n_in: t.number_of_inputs };
+        cx.rec.name = t.header.clone();
+        cx.rec.n_out = t.number_of_outputs as u32;
+        cx.rec.n_in = t.number_of_inputs as u32;
+        cx.rec.n_inter = t.number_of_intermediates as u32;
+        for i in &t.body { i.produce_cuda(&mut cx)?; }
+        let mut rec = cx.rec;
+        for con in constraints_of(t.id) {                            // ConstraintExporter view of this template instance
+            let mut row: [Vec<(Ref, u32)>; 3] = Default::default();
+            for (k, lc) in con.iter().enumerate() { for (r, c) in lc { row[k].push((*r, file.const_id(c, &q))); } }
+            rec.constraints.push(row);
+        }
+        file.templates.push(rec);
+    }
+    file.main = (templates.len() - 1) as u32;                        // the main template is instantiated last
+    for info in &producer.main_input_list { file.names.push((info.name.clone(), info.start as u32, info.size as u32)); }
+    Ok(file)
+}

@@ -21,6 +21,7 @@ pub struct CUDAProducer {
     pub main_input_list: InputList,    // (name, start, size): the source of the .dat hash map, mod.rs:17
     pub field_tracking: Vec<String>,   // the constant table the IR's ValueBucket{BigInt} indexes, mod.rs:27
     pub sanity_check_style: usize,     // 0: drop `===` asserts (assert_bucket.rs:73)
+    pub function_ids: HashMap<String, u32>, // function header -> index in Cb2cFile::functions (Circuit::functions order)
 }
 
 impl CUDAProducer {

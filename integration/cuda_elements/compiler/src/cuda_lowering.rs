@@ -233,7 +233,7 @@ impl WriteCuda for AssertBucket {  // assert_bucket.rs:70-88
 
 impl WriteCuda for CreateCmpBucket { // create_component_bucket.rs:204-352
     fn produce_cuda(&self, cx: &mut TemplateCtx) -> Result<Option<Val>, ()> {
-        if self.is_part_mixed_array_not_uniform_parallel || self.has_inputs == false && false { return Err(()); }
+        if self.is_part_mixed_array_not_uniform_parallel { return Err(()); }   // mixed-template arrays: templateInsId2IOSignalInfo
         let first = cx.address(&self.sub_cmp_id)?;
         for (k, _parallel) in &self.defined_positions {            // `parallel` is ignored: every component is data-parallel here
             let slot = first + *k;
@@ -248,7 +248,7 @@ impl WriteCuda for CreateCmpBucket { // create_component_bucket.rs:204-352
 impl WriteCuda for CallBucket {    // call_bucket.rs:466-533
     fn produce_cuda(&self, cx: &mut TemplateCtx) -> Result<Option<Val>, ()> {
         if self.argument_types.iter().any(|t| t.size != SizeOption::Single(1)) { return Err(()); } // array arguments: one ARG per element upstream
-        let fid = cx.producer_function_id(&self.symbol)?;
+        let fid = *cx.producer.function_ids.get(&self.symbol).ok_or(())?;
         for a in &self.arguments {
             let v = a.produce_cuda(cx)?.ok_or(())?;
             let r = cx.as_ref(&v);
@@ -279,6 +279,93 @@ impl WriteCuda for CallBucket {    // call_bucket.rs:466-533
 // max_number_of_vars) + expression temporaries; LoopBucket -> JZ / JMP, BranchBucket -> JZ / JMP, ReturnBucket -> RET,
 // Load/Store of `Variable` with a run-time index -> LOADX / STOREX (compute_bucket.rs:361-363 ToAddress = Fr_toInt).
 // The walk is the same as above with `Val::Dynamic(Ref::Tmp(reg))` everywhere; see docs/CB2C.md "function".
+// One pass over a function body.  `regs` = variable slots first (LoadBucket / StoreBucket with AddressType::Variable
+// address them; a compile-time address is the register itself, a run-time one goes through LOADX / STOREX with base 0),
+// expression temporaries after them.
+struct FunctionCtx<'a> { producer: &'a CUDAProducer, file: &'a mut Cb2cFile, q: BigInt, rec: &'a mut FunctionRecord }
+impl<'a> FunctionCtx<'a> {
+    fn reg(&mut self) -> Ref { self.rec.n_regs += 1; Ref::Tmp(self.rec.n_regs - 1) }
+    fn push(&mut self, op: Op, d: Ref, a: Ref, b: Ref, c: Ref) -> usize { self.rec.code.push(OpRec { op, d, a, b, c }); self.rec.code.len() - 1 }
+    fn value(&mut self, i: &InstructionPointer) -> Result<Ref, ()> {
+        Ok(match i.as_ref() {
+            Instruction::Value(v) => {
+                let k = match v.parse_as { ValueType::U32 => BigInt::from(v.value),
+                                           ValueType::BigInt => self.producer.field_tracking[v.value].parse::<BigInt>().map_err(|_| {})? };
+                let q = self.q.clone();
+                Ref::Const(self.file.const_id(&k, &q))
+            }
+            Instruction::Compute(c) => {
+                // address arithmetic (ToAddress / MulAddress / AddAddress) is ordinary arithmetic on registers here
+                let a = self.value(&c.stack[0])?;
+                let b = if c.stack.len() > 1 { self.value(&c.stack[1])? } else { Ref::None };
+                let op = match c.op { OperatorType::ToAddress => return Ok(a), OperatorType::MulAddress => Op::MUL,
+                                      OperatorType::AddAddress => Op::ADD, _ => operator_code(&c.op)? };
+                let d = self.reg();
+                self.push(op, d, a, b, Ref::None);
+                d
+            }
+            Instruction::Load(l) => match (&l.address_type, &l.src) {
+                (AddressType::Variable, LocationRule::Indexed { location, .. }) => match location.as_ref() {
+                    Instruction::Value(v) => Ref::Tmp(v.value as u32),
+                    _ => { let idx = self.value(location)?; let d = self.reg(); self.push(Op::LOADX, d, Ref::Imm(0), idx, Ref::None); d }
+                },
+                _ => return Err(()),   // functions only see variables (call_bucket.rs: arguments are copied in)
+            },
+            Instruction::Call(c) => {
+                let fid = *self.producer.function_ids.get(&c.symbol).ok_or(())?;
+                let _ = fid; return Err(());   // nested calls: inline upstream or extend the VM with a call stack (not in version 1)
+            }
+            _ => return Err(()),
+        })
+    }
+    fn stmt(&mut self, i: &InstructionPointer) -> Result<(), ()> {
+        match i.as_ref() {
+            Instruction::Store(s) => {
+                let v = self.value(&s.src)?;
+                match (&s.dest_address_type, &s.dest) {
+                    (AddressType::Variable, LocationRule::Indexed { location, .. }) => match location.as_ref() {
+                        Instruction::Value(a) => { self.push(Op::COPY, Ref::Tmp(a.value as u32), v, Ref::None, Ref::None); }
+                        _ => { let idx = self.value(location)?; self.push(Op::STOREX, Ref::None, Ref::Imm(0), idx, v); }
+                    },
+                    _ => return Err(()),
+                }
+            }
+            Instruction::Loop(l) => {                      // loop_bucket.rs:76-91: while (Fr_isTrue(cond)) body
+                let head = self.rec.code.len();
+                let c = self.value(&l.continue_condition)?;
+                let jz = self.push(Op::JZ, Ref::None, c, Ref::Imm(0), Ref::None);
+                for b in &l.body { self.stmt(b)?; }
+                self.push(Op::JMP, Ref::None, Ref::Imm(head as u32), Ref::None, Ref::None);
+                let end = self.rec.code.len() as u32;
+                self.rec.code[jz].b = Ref::Imm(end);
+            }
+            Instruction::Branch(b) => {                    // branch_bucket.rs:100-122
+                let c = self.value(&b.cond)?;
+                let jz = self.push(Op::JZ, Ref::None, c, Ref::Imm(0), Ref::None);
+                for x in &b.if_branch { self.stmt(x)?; }
+                let jmp = self.push(Op::JMP, Ref::None, Ref::Imm(0), Ref::None, Ref::None);
+                self.rec.code[jz].b = Ref::Imm(self.rec.code.len() as u32);
+                for x in &b.else_branch { self.stmt(x)?; }
+                self.rec.code[jmp].a = Ref::Imm(self.rec.code.len() as u32);
+            }
+            Instruction::Return(r) => {                    // return_bucket.rs:70-120
+                if r.with_size != 1 { return Err(()); }    // array results: one call per element (extra index parameter)
+                let v = self.value(&r.value)?;
+                self.push(Op::RET, Ref::None, v, Ref::None, Ref::None);
+            }
+            Instruction::Assert(_) | Instruction::Log(_) => {}   // asserts inside functions abort the C++ run; here: status, see DESIGN
+            _ => return Err(()),
+        }
+        Ok(())
+    }
+}
+fn function_body(body: &InstructionList, producer: &CUDAProducer, file: &mut Cb2cFile, rec: &mut FunctionRecord) -> Result<(), ()> {
+    let q = producer.prime_str.parse::<BigInt>().map_err(|_| {})?;
+    let mut cx = FunctionCtx { producer, file, q, rec };
+    for i in body { cx.stmt(i)?; }
+    Ok(())
+}
+
 pub fn lower_function(f: &FunctionCodeInfo, producer: &CUDAProducer, file: &mut Cb2cFile) -> Result<FunctionRecord, ()> {
     let mut rec = FunctionRecord { name: f.header.clone(), n_params: f.params.iter().map(|p| p.length.iter().product::<usize>().max(1)).sum::<usize>() as u32,
                                    n_regs: f.max_number_of_vars as u32, code: vec![] };

@@ -27,8 +27,14 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple, Union
 PRIMES = {
     "bn128": 21888242871839275222246405745257275088548364400416034343698204186575808495617,
     "bls12381": 52435875175126190479447740508185965837690552500527637822603658699938581184513,
+    "grumpkin": 21888242871839275222246405745257275088696311157297823662689037894645226208583,
+    "pallas": 28948022309329048855892746252171976963363056481941560715954676764349967630337,
+    "vesta": 28948022309329048855892746252171976963363056481941647379679742748393362948097,
+    "secq256r1": 115792089210356248762697446949407573530086143415290314195533631308867097853951,
+    "bls12377": 8444461749428370424248824938781546531375899335154063827935233455917409239041,
 }
-PRIME_IDS = {"bn128": 0, "bls12381": 1}
+# the 256-bit primes of program_structure/src/utils/constants.rs:3-13 (goldilocks, a 64-bit field, is not a 256-bit element path)
+PRIME_IDS = {"bn128": 0, "bls12381": 1, "grumpkin": 2, "pallas": 3, "vesta": 4, "secq256r1": 5, "bls12377": 6}
 
 # OperatorType (compiler/src/intermediate_representation/compute_bucket.rs:7-34) + moves
 OPS = {

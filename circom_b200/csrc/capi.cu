@@ -76,7 +76,9 @@ int ensure_device(int device) {
     CU(cudaSetDevice(device));
     std::lock_guard<std::mutex> lk(g_dev_mutex);
     if (!g_dev_ready[device]) {
-        FrParams h[2] = {make_dev_params(make_field(0)), make_dev_params(make_field(1))};
+        FrParams h[N_PRIMES_DEV];
+        static_assert(N_PRIMES_DEV == CW_N_PRIMES, "prime tables");
+        for (int k = 0; k < N_PRIMES_DEV; ++k) h[k] = make_dev_params(make_field(k));
         CU(cudaMemcpyToSymbol(c_fr, h, sizeof(h)));
         g_dev_ready[device] = true;
     }
@@ -612,6 +614,7 @@ int cw_batch_run(cw_batch *b) {
     tp.call_tab = b->dt.call_tab;
     tp.n_inputs = (u32)t.n_inputs;
     tp.n_bitwords = t.n_bitwords;
+    tp.prime = (u32)t.F.prime_id;
     CU(cudaMemsetAsync(b->first_assert_d, 0xFF, (size_t)b->batch * 4, b->stream));
     CU(cudaMemsetAsync(b->err_d, 0, (size_t)b->batch * 4, b->stream));
     CU(cudaEventRecord(b->ev[0], b->stream));
@@ -627,7 +630,12 @@ int cw_batch_run(cw_batch *b) {
         const u32 th = calls ? std::min<u32>(b->threads, 256u) : b->threads;  // the interpreter build has a large frame
         const bool fused = t.n_items() != t.n_tape_ops();
         if (t.F.prime_id == 0) launch_tape<0>(tp, b, tiles, th, calls, bp, fused);
-        else launch_tape<1>(tp, b, tiles, th, calls, bp, fused);
+        else if (t.F.prime_id == 1) launch_tape<1>(tp, b, tiles, th, calls, bp, fused);
+        else {  // the other 256-bit primes: one build (bit-plane capable, runtime tile size), prime index from tp.prime
+            if (fused) return fail(CW_ESTATE, "CW_FLAG_FUSE is available for bn128 and bls12381");
+            if (calls) launch_tape_k<-1, true, true, -1, false>(tp, b, tiles, th);
+            else launch_tape_k<-1, false, true, -1, false>(tp, b, tiles, th);
+        }
     }
     CU(cudaEventRecord(b->ev[1], b->stream));
     b->dense_valid = false;
@@ -1231,6 +1239,7 @@ static int launch_r1cs(cw_r1cs *r, const DevR1cs &d, const StoreDev &S, cudaStre
     rd.dictM = d.dictM;
     rd.perm = d.perm;
     rd.n_rows = d.n_general;
+    rd.prime = (u32)R.prime_id;
     const u32 n_tiles = (S.batch + (1u << S.bt_log2) - 1) >> S.bt_log2;
     if (d.n_general) {
         const uint64_t items = (uint64_t)d.n_general << S.bt_log2;
@@ -1246,7 +1255,9 @@ static int launch_r1cs(cw_r1cs *r, const DevR1cs &d, const StoreDev &S, cudaStre
         else r1cs_check_kernel<PR, 3, false><<<grid, 256, 0, stream>>>(rd, S, fb_d, eo);                 \
     } while (0)
         if (R.prime_id == 0) CW_LAUNCH_R1CS(0);
-        else CW_LAUNCH_R1CS(1);
+        else if (R.prime_id == 1) CW_LAUNCH_R1CS(1);
+        else if (eval) r1cs_check_kernel<-1, 3, true><<<grid, 256, 0, stream>>>(rd, S, fb_d, eo);
+        else r1cs_check_kernel<-1, 3, false><<<grid, 256, 0, stream>>>(rd, S, fb_d, eo);
 #undef CW_LAUNCH_R1CS
     }
     if (d.n_bool && !eval) {
@@ -1691,7 +1702,7 @@ int cw_status_allreduce(cw_comm *cm, cw_batch *b, uint64_t out[2]) {
 // ---- field batch ops ---------------------------------------------------------------------------
 int cw_fr_batch_op(int prime_id, int op, const uint64_t *a, const uint64_t *b, const uint64_t *c, uint64_t *r,
                    size_t n, int device) {
-    if (!a || !r || prime_id < 0 || prime_id > 1) return fail(CW_EINVAL, "bad argument");
+    if (!a || !r || prime_id < 0 || prime_id >= CW_N_PRIMES) return fail(CW_EINVAL, "bad argument");
     int rc = ensure_device(device);
     if (rc) return rc;
     uint4 *A = nullptr, *B = nullptr, *C = nullptr, *Rr = nullptr;
@@ -1704,8 +1715,9 @@ int cw_fr_batch_op(int prime_id, int op, const uint64_t *a, const uint64_t *b, c
     CU(cudaMemset(err, 0, 4));
     u32 grid = (u32)std::min<size_t>((n + 127) / 128, 148 * 16);
     if (!grid) grid = 1;
-    if (prime_id == 0) fr_batch_op_kernel<0><<<grid, 128>>>(op, A, B, C, Rr, n, err);
-    else fr_batch_op_kernel<1><<<grid, 128>>>(op, A, B, C, Rr, n, err);
+    if (prime_id == 0) fr_batch_op_kernel<0><<<grid, 128>>>(op, A, B, C, Rr, n, err, 0u);
+    else if (prime_id == 1) fr_batch_op_kernel<1><<<grid, 128>>>(op, A, B, C, Rr, n, err, 1u);
+    else fr_batch_op_kernel<-1><<<grid, 128>>>(op, A, B, C, Rr, n, err, (u32)prime_id);
     CU(cudaGetLastError());
     CU(cudaMemcpy(r, Rr, n * 32, cudaMemcpyDeviceToHost));
     int herr = 0;
@@ -1719,6 +1731,7 @@ int cw_fr_batch_op(int prime_id, int op, const uint64_t *a, const uint64_t *b, c
 }
 
 int cw_fr_mul_bench(int prime_id, size_t n, int iters, int device, float *ms) {
+    if (prime_id < 0 || prime_id > 1 || !ms) return fail(CW_EINVAL, "the throughput probe is built for bn128 and bls12381");
     int rc = ensure_device(device);
     if (rc) return rc;
     std::vector<uint64_t> h(n * 4);

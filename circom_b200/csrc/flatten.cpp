@@ -748,7 +748,7 @@ struct Lowerer {
         main_tid = r.get<uint32_t>();
         uint32_t n_names = r.get<uint32_t>();
         uint32_t n_funcs = r.get<uint32_t>();
-        if (prime > 1) throw std::runtime_error("cb2c: unknown prime");
+        if (prime >= (uint32_t)CW_N_PRIMES) throw std::runtime_error("cb2c: unknown prime");
         T.F = make_field((int)prime);
         r.expect(n_consts, 32);
         r.expect(n_tm, 36);
@@ -1582,7 +1582,7 @@ void deserialize_tape(const uint8_t *data, size_t len, Tape &t) {
     if (memcmp(magic, "CB2T", 4) || ver != BLOB_VERSION) throw std::runtime_error("lowered-circuit blob: bad magic / version");
     int32_t prime;
     r.pod(prime);
-    if (prime < 0 || prime > 1) throw std::runtime_error("lowered-circuit blob: unknown prime");
+    if (prime < 0 || prime >= CW_N_PRIMES) throw std::runtime_error("lowered-circuit blob: unknown prime");
     t.F = make_field(prime);
     r.pod(t.flags);
     uint64_t n_nums;

@@ -141,10 +141,8 @@ void read_r1cs(const std::string &path, R1csData &out) {
     if (fs != 32 || hdr_len < 4 + 32 + 28) throw std::runtime_error("r1cs: only 32-byte fields are supported");
     U256 q;
     memcpy(q.v, &buf[hdr + 4], 32);
-    FieldParams f0 = make_field(0), f1 = make_field(1);
-    if (q == f0.q) out.prime_id = 0;
-    else if (q == f1.q) out.prime_id = 1;
-    else throw std::runtime_error("r1cs: unsupported prime");
+    out.prime_id = prime_id_of(q);
+    if (out.prime_id < 0) throw std::runtime_error("r1cs: unsupported prime");
     size_t h = hdr + 4 + 32;
     out.n_wires = u32(h);
     out.n_pub_out = u32(h + 4);
@@ -264,9 +262,8 @@ void read_wtns(const std::string &path, int &prime_id, std::vector<uint64_t> &wi
     if (u32(s1) != 32) throw std::runtime_error("wtns: only 32-byte fields are supported");
     U256 q;
     memcpy(q.v, &buf[s1 + 4], 32);
-    if (q == make_field(0).q) prime_id = 0;
-    else if (q == make_field(1).q) prime_id = 1;
-    else throw std::runtime_error("wtns: unsupported prime");
+    prime_id = prime_id_of(q);
+    if (prime_id < 0) throw std::runtime_error("wtns: unsupported prime");
     uint32_t n = u32(s1 + 36);
     if ((uint64_t)n * 32 != s2_len) throw std::runtime_error("wtns: witness section has the wrong size");
     witness.resize((size_t)n * 4);

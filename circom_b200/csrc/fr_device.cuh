@@ -177,11 +177,13 @@ CW_HD void fr_mont_mul_c(u32 *r, const u32 *a, const u32 *b, const FrParams &P) 
         t[7] = (u32)c;
         t[8] = t9 + (u32)(c >> 32);
     }
-    // both moduli are < 2^255, so the CIOS result is < 2q < 2^256 and t[8] == 0
+    // the CIOS result is < 2q: for the 254 / 255-bit moduli it fits 256 bits (t[8] == 0); for a 256-bit modulus
+    // (secq256r1) the ninth limb can be 1, and then the subtraction is due whatever its borrow says
     u32 d[8];
     u32 br = u256_sub(d, t, P.q);
+    const bool sub = t[8] != 0u || !br;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) r[i] = br ? t[i] : d[i];
+    for (int i = 0; i < 8; ++i) r[i] = sub ? d[i] : t[i];
 }
 
 #if defined(__CUDA_ARCH__)
@@ -251,9 +253,10 @@ __device__ __forceinline__ void fr_mont_mul_ptx(u32 *r, const u32 *a, const u32 
 #pragma unroll
     for (int i = 0; i < 8; ++i) fr_mont_step(t, a, b[i], P);
     u32 d[8];
-    u32 br = u256_sub(d, t, P.q);  // result < 2q < 2^256 (t[8] == 0)
+    u32 br = u256_sub(d, t, P.q);  // result < 2q; t[8] is 0 unless the modulus has 256 bits
+    const bool sub = t[8] != 0u || !br;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) r[i] = br ? t[i] : d[i];
+    for (int i = 0; i < 8; ++i) r[i] = sub ? d[i] : t[i];
 }
 #endif
 
@@ -454,15 +457,16 @@ CW_HD bool u256_divmod(u32 *quo, u32 *rem, const u32 *a, const u32 *b) {
 #pragma unroll
         for (int j = 7; j > 0; --j) n[j] = (n[j] << 1) | (n[j - 1] >> 31);
         n[0] <<= 1;
+        const u32 rtop = r[7] >> 31;  // r < b: with a 256-bit divisor 2r + carry can leave 256 bits - then it exceeds b for sure
 #pragma unroll
         for (int j = 7; j > 0; --j) r[j] = (r[j] << 1) | (r[j - 1] >> 31);
-        r[0] = (r[0] << 1) | carry;  // r < b < 2^255 before the shift: no overflow
+        r[0] = (r[0] << 1) | carry;
         u32 t[8];
-        u32 br = u256_sub(t, r, b);
+        u32 br = u256_sub(t, r, b);   // (mod 2^256: the right difference also when the shift overflowed)
 #pragma unroll
         for (int j = 7; j > 0; --j) q[j] = (q[j] << 1) | (q[j - 1] >> 31);
         q[0] <<= 1;
-        if (!br) {
+        if (rtop || !br) {
             u256_set(r, t);
             q[0] |= 1;
         }

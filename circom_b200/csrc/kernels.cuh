@@ -9,7 +9,11 @@ namespace cw {
 
 // Per-prime parameters live in constant memory so that modulus limbs are read as c[bank][imm]
 // instruction operands (no registers, no loads).
-__constant__ FrParams c_fr[2];
+// bn128 and bls12381 have kernel builds of their own (template PRIME = 0 / 1: the table index folds into the
+// instruction); the other 256-bit primes share one build (PRIME = -1) that takes the index from its arguments.
+constexpr int N_PRIMES_DEV = 7;
+__constant__ FrParams c_fr[N_PRIMES_DEV];
+#define CW_FR(PRIME, rt) c_fr[(PRIME) >= 0 ? (PRIME) : (int)(rt)]
 
 // ---- value-slot storage ---------------------------------------------------------------------
 // One instance tile holds BT = 1 << bt_log2 instances.  A slot (256-bit value) of a tile is two
@@ -111,6 +115,7 @@ struct TapeDev {
     u32 n_slots;
     u32 n_inputs;
     u32 n_bitwords;            // words of the bit plane per instance (0: no bit plane)
+    u32 prime;                 // index into c_fr (read by the PRIME = -1 builds)
 };
 
 // ---- inputs: inputs[batch][n_inputs][8 u32] canonical -> slots 1..n_inputs, slot 0 = 1 ----------
@@ -146,7 +151,7 @@ __global__ void stage_inputs_kernel(TapeDev tp, const uint4 *__restrict__ inputs
 template <int PRIME, bool BP>
 __device__ __noinline__ void exec_call(const TapeDev &tp, u32 call_off, const uint4 *base, const u32 *plane_base,
                                        u32 bt_log2, u32 li, u32 *r, int *err) {
-    const FrParams &P = c_fr[PRIME];
+    const FrParams &P = CW_FR(PRIME, tp.prime);
     const u32 *ct = tp.call_tab + call_off;
     const u32 f = __ldg(&ct[0]), n_args = __ldg(&ct[1]);
     FnInfo fi;
@@ -183,7 +188,7 @@ template <int PRIME, bool HAS_CALLS, bool BP, int BT, bool FUSED>
 __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
     tape_exec_kernel(TapeDev tp, uint4 *__restrict__ slots, u32 *__restrict__ plane, u32 bt_log2_arg,
                      u32 *__restrict__ first_assert, int *__restrict__ err, u32 batch) {
-    const FrParams &P = c_fr[PRIME];
+    const FrParams &P = CW_FR(PRIME, tp.prime);
     const u32 bt_log2 = BT >= 0 ? (u32)BT : bt_log2_arg;
     constexpr bool COOP = BT == 0 && !HAS_CALLS && !BP;  // warp-cooperative bit-run stores (needs blockDim % 32 == 0)
     const u32 tile = blockIdx.x;
@@ -484,6 +489,7 @@ struct R1csDev {
     const uint4 *dictM;
     const u32 *perm;
     u32 n_rows;  // rows in perm
+    u32 prime;   // index into c_fr (PRIME = -1 build)
 };
 
 // Lazy reduction: most terms of circom constraints are bits / small values times +-1 or +-2^k (boolean logic, the
@@ -615,7 +621,7 @@ struct EvalOut {
 template <int PRIME, int MINB, bool EVAL>
 __global__ void __launch_bounds__(256, MINB) r1cs_check_kernel(R1csDev R, StoreDev S, unsigned long long *__restrict__ first_bad,
                                                          EvalOut out) {
-    const FrParams &P = c_fr[PRIME];
+    const FrParams &P = CW_FR(PRIME, R.prime);
     const u32 bt_mask = (1u << S.bt_log2) - 1u;
     const u32 n_tiles = (S.batch + bt_mask) >> S.bt_log2;
     const unsigned long long n_items = (unsigned long long)R.n_rows << S.bt_log2;
@@ -672,8 +678,8 @@ __global__ void __launch_bounds__(256) r1cs_bool_kernel(const u32 *__restrict__ 
 template <int PRIME>
 __global__ void fr_batch_op_kernel(int op, const uint4 *__restrict__ A, const uint4 *__restrict__ B,
                                    const uint4 *__restrict__ C, uint4 *__restrict__ Rr, size_t n,
-                                   int *__restrict__ err) {
-    const FrParams &P = c_fr[PRIME];
+                                   int *__restrict__ err, u32 prime_rt) {
+    const FrParams &P = CW_FR(PRIME, prime_rt);
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         u32 a[8], b[8] = {0, 0, 0, 0, 0, 0, 0, 0}, c[8] = {0, 0, 0, 0, 0, 0, 0, 0}, r[8];
         load_const(a, A, (u32)i);

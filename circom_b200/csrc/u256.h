@@ -41,6 +41,10 @@ inline uint64_t u256_sub(U256 &r, const U256 &a, const U256 &b) {
     return (uint64_t)br;
 }
 
+constexpr int CW_N_PRIMES = 7;  // bn128, bls12381, grumpkin, pallas, vesta, secq256r1, bls12377
+// id of the prime with modulus q, or -1
+int prime_id_of(const struct U256 &q);
+
 // Field constants for one prime.  q from program_structure/src/utils/constants.rs:3-6;
 // derived values as the reference compiler derives them (c_code_generator.rs:1086-1099).
 struct FieldParams {
@@ -101,13 +105,17 @@ struct FieldParams {
 inline FieldParams make_field(int prime_id) {
     FieldParams f;
     f.prime_id = prime_id;
-    if (prime_id == 0) {
-        // 21888242871839275222246405745257275088548364400416034343698204186575808495617
-        f.q = U256{{0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL}};
-    } else {
-        // 52435875175126190479447740508185965837690552500527637822603658699938581184513
-        f.q = U256{{0xffffffff00000001ULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL, 0x73eda753299d7d48ULL}};
-    }
+    // program_structure/src/utils/constants.rs:3-13 (goldilocks, 64 bits, has no 256-bit element path)
+    static const uint64_t Q[CW_N_PRIMES][4] = {
+        {0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL},  // bn128
+        {0xffffffff00000001ULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL, 0x73eda753299d7d48ULL},  // bls12381
+        {0x3c208c16d87cfd47ULL, 0x97816a916871ca8dULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL},  // grumpkin
+        {0x992d30ed00000001ULL, 0x224698fc094cf91bULL, 0x0000000000000000ULL, 0x4000000000000000ULL},  // pallas
+        {0x8c46eb2100000001ULL, 0x224698fc0994a8ddULL, 0x0000000000000000ULL, 0x4000000000000000ULL},  // vesta
+        {0xffffffffffffffffULL, 0x00000000ffffffffULL, 0x0000000000000000ULL, 0xffffffff00000001ULL},  // secq256r1
+        {0x0a11800000000001ULL, 0x59aa76fed0000001ULL, 0x60b44d1e5c37b001ULL, 0x12ab655e9a2ca556ULL},  // bls12377
+    };
+    memcpy(f.q.v, Q[prime_id >= 0 && prime_id < CW_N_PRIMES ? prime_id : 0], 32);
     for (int i = 0; i < 4; ++i) f.half.v[i] = (f.q.v[i] >> 1) | (i < 3 ? (f.q.v[i + 1] << 63) : 0);
     // Newton iteration for q^-1 mod 2^64
     uint64_t inv = 1;
@@ -127,6 +135,12 @@ inline FieldParams make_field(int prime_id) {
     }
     f.r2 = x;
     return f;
+}
+
+inline int prime_id_of(const U256 &q) {
+    for (int i = 0; i < CW_N_PRIMES; ++i)
+        if (make_field(i).q == q) return i;
+    return -1;
 }
 
 }  // namespace cw

@@ -38,6 +38,13 @@ extern "C" {
 /* primes (program_structure/src/utils/constants.rs:3-6) */
 #define CW_PRIME_BN128 0
 #define CW_PRIME_BLS12381 1
+/* the other 256-bit primes of constants.rs:7-13 (one shared kernel build; goldilocks - a 64-bit field with its own
+ * element layout, c_elements/goldilocks/fr.hpp:10-60 - is not supported) */
+#define CW_PRIME_GRUMPKIN 2
+#define CW_PRIME_PALLAS 3
+#define CW_PRIME_VESTA 4
+#define CW_PRIME_SECQ256R1 5
+#define CW_PRIME_BLS12377 6
 
 /* cw_circuit_load flags */
 #define CW_FLAG_NO_ASSERTS 1u /* --sanity_check 0: drop `===` asserts (assert_bucket.rs:73) */

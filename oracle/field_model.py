@@ -18,6 +18,11 @@ from __future__ import annotations
 PRIMES = {
     "bn128": 21888242871839275222246405745257275088548364400416034343698204186575808495617,
     "bls12381": 52435875175126190479447740508185965837690552500527637822603658699938581184513,
+    "grumpkin": 21888242871839275222246405745257275088696311157297823662689037894645226208583,
+    "pallas": 28948022309329048855892746252171976963363056481941560715954676764349967630337,
+    "vesta": 28948022309329048855892746252171976963363056481941647379679742748393362948097,
+    "secq256r1": 115792089210356248762697446949407573530086143415290314195533631308867097853951,
+    "bls12377": 8444461749428370424248824938781546531375899335154063827935233455917409239041,
 }
 
 # IR opcodes: OperatorType of compiler/src/intermediate_representation/compute_bucket.rs:7-34

@@ -19,14 +19,14 @@ from tests.test_lowering_cpu import CIRCUITS
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("prime", [0, 1])
+@pytest.mark.parametrize("prime", range(7))
 def test_device_field_ops(prime):
-    """device Fr_* equivalents (fr.hpp:28-70) over all operators, random + edge operands"""
-    F = Field(["bn128", "bls12381"][prime])
+    """device Fr_* equivalents (fr.hpp:28-70) over all operators, random + edge operands, all seven 256-bit primes"""
+    F = Field(["bn128", "bls12381", "grumpkin", "pallas", "vesta", "secq256r1", "bls12377"][prime])
     q = F.q
     rng = random.Random(991 + prime)
     edges = edge_values(q)
-    n = 20000
+    n = 20000 if prime < 2 else 6000
     A = [rand_operand(rng, q, edges) for _ in range(n)]
     B = [rand_operand(rng, q, edges) if rng.random() > 0.25 else rng.randrange(300) for _ in range(n)]
     Cc = [rng.choice([0, 1, rng.randrange(q)]) for _ in range(n)]
@@ -398,3 +398,27 @@ def test_r1cs_check_of_files(tmp_path):
     bad[76 + 32 * 5] ^= 1                      # one witness entry off by one
     open(wp, "wb").write(bad)
     assert native.lib.cw_r1cs_check_files(rp.encode(), wp.encode(), 0, ctypes.byref(fb)) == 0 and fb.value >= 0
+
+
+@pytest.mark.parametrize("prime", ["grumpkin", "pallas", "vesta", "secq256r1", "bls12377"])
+def test_other_primes_run_circuits(prime):
+    """the remaining 256-bit primes of constants.rs:7-13 through the shared kernel build: every operator (AllOps),
+    function calls (int_div) and a Poseidon-shaped tape of products, against the evaluator; R1CS check on the result"""
+    for name in ("all_ops", "int_div32", "multiplier_n6"):
+        mk, gen = CIRCUITS[name]
+        d = CircuitDesc(prime)
+        d.set_main(mk(d))
+        rng = random.Random(zlib.crc32((prime + name).encode()))
+        ins = [gen(rng, d.q) for _ in range(33)]
+        for compact in (False, True):
+            c = Circuit(d, compact=compact)
+            b = Batch(c, len(ins))
+            b.set_inputs(flat_inputs(d, ins))
+            b.run()
+            assert not b.status().any()
+            wit = b.witness()
+            w2s = c.witness2signal().astype(np.int64)
+            for i, inp in enumerate(ins):
+                exp = evaluate(d, inp)
+                assert limbs_to_ints(wit[i]) == [exp[k] for k in w2s], (prime, name, compact, i)
+            assert (R1cs(c).check_batch(b)[0] == -1).all() and (R1cs(c).check(wit)[0] == -1).all()

@@ -260,7 +260,8 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
 #pragma unroll
                 for (int i = 1; i < 8; ++i) r[i] = 0;
                 if (run > 1u) {
-                    if (BP) {  // the run is ONE word of the bit plane (dst = word index): a single 4-byte store
+                    if (BP && tp.n_bitwords) {  // the run is ONE word of the bit plane (dst = word index): a single 4-byte store
+                        // (a BP build may be handed a tape without a plane: then runs are slots, below)
                         plane_base[((size_t)dst << bt_log2) + li] =
                             (u32)window & (run >= 32u ? 0xFFFFFFFFu : ((1u << run) - 1u));
                     } else if (COOP) {  // `run` (<= 32) consecutive slots, one bit each: stored by the whole warp after the body

@@ -102,8 +102,8 @@ def test_fused_work_items_match(bt, monkeypatch):
         ins = [gen(rng) for _ in range(40)]
         arr = flat_inputs(d, ins)
         wits = []
-        for fuse in (False, True):
-            c = Circuit(d, fuse=fuse)
+        for fuse, compact in ((False, True), (True, True), (True, False)):
+            c = Circuit(d, fuse=fuse, compact=compact)
             b = Batch(c, len(ins))
             b.set_inputs(arr)
             b.run()
@@ -111,7 +111,7 @@ def test_fused_work_items_match(bt, monkeypatch):
             wits.append((c, b.witness()))
             fb, _ = R1cs(c).check_batch(b)
             assert (fb == -1).all()
-        assert (wits[0][1] == wits[1][1]).all()
+        assert (wits[0][1] == wits[1][1]).all() and (wits[0][1] == wits[2][1]).all()
         assert wits[1][0].stats["n_levels"] * 3 < wits[0][0].stats["n_levels"] * 2
         assert wits[1][0].stats["n_items"] < wits[1][0].stats["n_tape_ops"] == wits[0][0].stats["n_items"]
         ow, st = COracle(d.to_bytes()).run(arr[:4])

@@ -1243,13 +1243,7 @@ static int launch_r1cs(cw_r1cs *r, const DevR1cs &d, const StoreDev &S, cudaStre
     const u32 n_tiles = (S.batch + (1u << S.bt_log2) - 1) >> S.bt_log2;
     if (d.n_general) {
         const uint64_t items = (uint64_t)d.n_general << S.bt_log2;
-        // grid.x covers the rows, grid.y the tiles; a thread re-walks its row for the tiles y, y + grid.y, ... (term records
-        // from L1): as many tiles per thread (up to 8) as still leave ~16 CTAs per SM
-        const u32 gx = (u32)std::max<uint64_t>(1, std::min<uint64_t>((items + 255) / 256, 148 * 8));
-        u32 tiles_per_thread = 1;
-        while (tiles_per_thread < 8 && (uint64_t)gx * (n_tiles / (2 * tiles_per_thread)) >= 148ull * 16) tiles_per_thread *= 2;
-        tiles_per_thread = (u32)std::max(1, env_int("CW_R1CS_IPB", (int)tiles_per_thread));
-        dim3 grid(gx, std::min<u32>(std::max<u32>(1, (n_tiles + tiles_per_thread - 1) / tiles_per_thread), 65535u));
+        dim3 grid((u32)std::max<uint64_t>(1, std::min<uint64_t>((items + 255) / 256, 148 * 8)), std::min<u32>(n_tiles, 65535u));
         // long rows: many resident warps (48 registers); short rows: the unspilled build
         const bool lean = env_int("CW_R1CS_LEAN", d.mean_row_terms >= 12 ? 1 : 0) != 0;
         EvalOut eo;

@@ -626,19 +626,16 @@ __global__ void __launch_bounds__(256, MINB) r1cs_check_kernel(R1csDev R, StoreD
     const u32 bt_mask = (1u << S.bt_log2) - 1u;
     const u32 n_tiles = (S.batch + bt_mask) >> S.bt_log2;
     const unsigned long long n_items = (unsigned long long)R.n_rows << S.bt_log2;
-    // a thread keeps its row and walks the tiles blockIdx.y, blockIdx.y + gridDim.y, ...: the row's pointers stay in
-    // registers and its term records come from L1 after the first tile (the host sizes gridDim.y for ~8 tiles per thread)
-    for (unsigned long long w = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; w < n_items;
-         w += (unsigned long long)gridDim.x * blockDim.x) {
-        const u32 li = (u32)w & bt_mask;
-        const u32 row = __ldg(&R.perm[w >> S.bt_log2]);
-        const unsigned long long p0 = __ldg(&R.row_ptr[3 * (size_t)row]), p1 = __ldg(&R.row_ptr[3 * (size_t)row + 1]),
-                                 p2 = __ldg(&R.row_ptr[3 * (size_t)row + 2]), p3 = __ldg(&R.row_ptr[3 * (size_t)row + 3]);
-        for (u32 tile = blockIdx.y; tile < n_tiles; tile += gridDim.y) {
-            const u32 inst = (tile << S.bt_log2) + li;
+    for (u32 tile = blockIdx.y; tile < n_tiles; tile += gridDim.y) {
+        const uint4 *tb = store_tile(S, tile);
+        const u32 *pb = store_plane(S, tile);
+        for (unsigned long long w = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; w < n_items;
+             w += (unsigned long long)gridDim.x * blockDim.x) {
+            const u32 li = (u32)w & bt_mask, inst = (tile << S.bt_log2) + li;
             if (inst >= S.batch) continue;
-            const uint4 *tb = store_tile(S, tile);
-            const u32 *pb = store_plane(S, tile);
+            const u32 row = __ldg(&R.perm[w >> S.bt_log2]);
+            const unsigned long long p0 = __ldg(&R.row_ptr[3 * (size_t)row]), p1 = __ldg(&R.row_ptr[3 * (size_t)row + 1]),
+                                     p2 = __ldg(&R.row_ptr[3 * (size_t)row + 2]), p3 = __ldg(&R.row_ptr[3 * (size_t)row + 3]);
             u32 a[8], b[8], c[8];
             r1cs_lc<PRIME>(a, R, p0, p1, S, tb, pb, li, P, &first_bad[inst]);
             r1cs_lc<PRIME>(b, R, p1, p2, S, tb, pb, li, P, &first_bad[inst]);

@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-WORKLOADS = ["ecdsa_scale", "sha256compression", "poseidon2", "sha256_512_bls"]
+WORKLOADS = ["ecdsa_scale", "sha256compression", "poseidon2", "sha256_512_bls", "ecdsa_scale_calls"]
 
 
 def parse_args():
@@ -71,6 +71,12 @@ def make_workload(args):
         d.set_main(C.ecdsa_scale(d, args.lanes, args.chain), "ecdsa_scale_%dx%d" % (args.lanes, args.chain))
         label = "ecdsa-scale synthetic (secp256k1 BigMultModP chains %dx%d, 4x64-bit limbs), BN254" % (args.lanes, args.chain)
         # 18,944 = 148 SMs x 4 CTAs x 32 instances: one full wave of warp-per-op tiles; 2.2 MB of value store each
+        batch = args.batch_per_gpu or 18944
+    elif args.workload == "ecdsa_scale_calls":
+        d.set_main(C.ecdsa_scale(d, args.lanes, args.chain, hints="functions"),
+                   "ecdsa_scale_calls_%dx%d" % (args.lanes, args.chain))
+        label = ("ecdsa-scale synthetic with function-computed hints (one long_div-style call per quotient / remainder "
+                 "limb: 9 calls per BigMultModP), %dx%d, BN254" % (args.lanes, args.chain))
         batch = args.batch_per_gpu or 18944
     elif args.workload == "sha256compression":
         d.set_main(C.sha256_compression(d), "sha256compression")
@@ -560,7 +566,8 @@ def main():
         # every BASELINE.json config at its stated per-GPU batch, each parity-gated against the reference calculator
         cfgs = []
         plan = [("C2", "sha256compression", 1024, True, 4), ("C3", "ecdsa_scale", 8, True, 2),
-                ("C4", "sha256_512_bls", 1024, True, 4)]
+                ("C4", "sha256_512_bls", 1024, True, 4),
+                ("C3-calls: the headline circuit with its hints computed by circom-style functions", "ecdsa_scale_calls", 18944, False, 2)]
         for tag, wl, bsz, r1, ps in plan:
             res, d2, in2 = run_workload(ctx, wl, bsz, max(3, min(args.steps, 5)), 3, 1, r1, parity_samples=ps,
                                         lanes=args.lanes, chain=args.chain)

@@ -30,8 +30,111 @@ def _split(t: Template, x):
     return x & M64, x >> N
 
 
-def big_mult_mod_p(d: CircuitDesc) -> Template:
-    """out = a*b mod p for 4x64-bit limb operands (limbs of a, b must be < 2^64)."""
+def fn_modp_limb(d: CircuitDesc):
+    """function modp_limb(X[8], sel): quotient and remainder of the 512-bit X (eight 64-bit limbs) by the secp256k1
+    prime, returned one limb per call (sel 0..4: quotient limb, 5..8: remainder limb) - the job of circom-ecdsa's
+    `long_div` hint (bigint_func.circom), written like it: `var` arrays indexed by run-time loop counters, a folding
+    loop whose trip count depends on the data, a limb-wise comparison with early exit, a conditional subtraction."""
+    from ..circuit import Function
+    delta = (1 << 32) + 977
+    p_l = _limbs(SECP256K1_P)
+
+    def build(f: Function):
+        X = f.array(2 * KL)
+        for i in range(2 * KL):
+            f.store(X, f.var(i), f.param(i))
+        sel = f.param(2 * KL)
+        R = f.array(KL)
+        Q = f.array(KL + 1)
+        Pp = f.array(KL)
+        for i in range(KL):
+            f.store(Pp, f.var(i), p_l[i])
+        four = KL
+        # Q = X_hi ; R = X_lo + X_hi * delta (with carries), h = carry out
+        i = f.var(0)
+        c = f.var(0)
+        f.loop_begin()
+        f.loop_break_if_zero(i.lt(four))
+        hi = f.load(X, i + four)
+        f.store(Q, i, hi)
+        s = f.load(X, i) + hi * delta + c
+        f.store(R, i, s & M64)
+        f.set(c, s >> N)
+        f.set(i, i + 1)
+        f.loop_end()
+        f.store(Q, f.var(four), 0)
+        h = f.var(c)
+        # while (h != 0): R += h * delta, Q += h   (X = Q*p + R is kept; at most three rounds)
+        f.loop_begin()
+        f.loop_break_if_zero(h.neq(0))
+        f.set(c, h * delta)
+        qc = f.var(h)
+        f.set(i, 0)
+        f.loop_begin()
+        f.loop_break_if_zero(i.lt(four))
+        s2 = f.load(R, i) + c
+        f.store(R, i, s2 & M64)
+        f.set(c, s2 >> N)
+        f.set(i, i + 1)
+        f.loop_end()
+        f.set(h, c)
+        f.set(i, 0)
+        f.loop_begin()                                  # Q += qc with carries
+        f.loop_break_if_zero(i.leq(four))
+        s3 = f.load(Q, i) + qc
+        f.store(Q, i, s3 & M64)
+        f.set(qc, s3 >> N)
+        f.set(i, i + 1)
+        f.loop_end()
+        f.loop_end()
+        # R >= p ?  compare from the top limb down, leave at the first difference
+        ge = f.var(1)
+        j = f.var(four)
+        f.loop_begin()
+        f.loop_break_if_zero(j.neq(0))
+        f.set(j, j - 1)
+        rj = f.load(R, j)
+        pj = f.load(Pp, j)
+        f.if_begin(rj.neq(pj))
+        f.set(ge, rj.gt(pj))
+        f.set(j, 0)
+        f.if_end()
+        f.loop_end()
+        f.if_begin(ge)
+        b = f.var(0)                                    # R -= p
+        f.set(i, 0)
+        f.loop_begin()
+        f.loop_break_if_zero(i.lt(four))
+        s4 = f.load(R, i) + (1 << N) - f.load(Pp, i) - b
+        f.store(R, i, s4 & M64)
+        f.set(b, 1 - (s4 >> N))
+        f.set(i, i + 1)
+        f.loop_end()
+        one = f.var(1)                                  # Q += 1
+        f.set(i, 0)
+        f.loop_begin()
+        f.loop_break_if_zero(i.leq(four))
+        s5 = f.load(Q, i) + one
+        f.store(Q, i, s5 & M64)
+        f.set(one, s5 >> N)
+        f.set(i, i + 1)
+        f.loop_end()
+        f.if_end()
+        res = f.var(0)
+        f.if_begin(sel.leq(four))
+        f.set(res, f.load(Q, sel))
+        f.if_else()
+        f.set(res, f.load(R, sel - (four + 1)))
+        f.if_end()
+        f.ret(res)
+    return d.function("modp_limb", 2 * KL + 1, build)
+
+
+def big_mult_mod_p(d: CircuitDesc, hints: str = "inline") -> Template:
+    """out = a*b mod p for 4x64-bit limb operands (limbs of a, b must be < 2^64).  hints = "inline": quotient and
+    remainder hints as straight-line shifts and masks; "functions": one call of `modp_limb` per hint limb (the
+    circom-ecdsa style: hints computed by functions with data-dependent control flow)."""
+    fmod = fn_modp_limb(d) if hints == "functions" else None
     n2b64 = num2bits(d, N)
     n2b_carry = num2bits(d, 72)
     p_l = _limbs(SECP256K1_P)
@@ -76,6 +179,11 @@ def big_mult_mod_p(d: CircuitDesc) -> Template:
             lo, c = _split(t, s)
             P.append(lo)
         P.append(c)                                # limb 7 (< 2^64)
+        if fmod is not None:
+            for i in range(KL):
+                t.assign(out[i], t.call(fmod, P + [KL + 1 + i]))
+            for i in range(KL + 1):
+                t.assign(quo[i], t.call(fmod, P + [i]))
         # first fold: R1 = Xlo + Xhi*delta (5 limbs), Q1 = Xhi
         R = []
         c = t.const(0)
@@ -122,10 +230,11 @@ def big_mult_mod_p(d: CircuitDesc) -> Template:
             s = Q[i] + c
             lo, c = _split(t, s)
             Qf.append(lo)
-        for i in range(KL):
-            t.assign(out[i], rem[i])
-        for i in range(KL + 1):
-            t.assign(quo[i], Qf[i])
+        if fmod is None:
+            for i in range(KL):
+                t.assign(out[i], rem[i])
+            for i in range(KL + 1):
+                t.assign(quo[i], Qf[i])
 
         # ---- range checks: limbs of out and q are 64-bit (Num2Bits) --------------------------
         for i in range(KL):
@@ -161,14 +270,14 @@ def big_mult_mod_p(d: CircuitDesc) -> Template:
                 prev = carry[m]
             else:
                 t.constrain(lhs, 0)
-    return d.template("BigMultModP", (N, KL), build)
+    return d.template("BigMultModP" if fmod is None else "BigMultModPfn", (N, KL), build)
 
 
-def ecdsa_scale(d: CircuitDesc, lanes: int = 8, steps: int = 132) -> Template:
+def ecdsa_scale(d: CircuitDesc, lanes: int = 8, steps: int = 132, hints: str = "inline") -> Template:
     """`lanes` independent chains of `steps` modular multiplications over the secp256k1 base field
     (alternating squarings and multiplications, like the field operations of a double-and-add
     ladder).  8 x 132 gives ~1.0M R1CS constraints."""
-    mm = big_mult_mod_p(d)
+    mm = big_mult_mod_p(d, hints)
     n2b64 = num2bits(d, N)
 
     def build(t: Template):
@@ -192,7 +301,7 @@ def ecdsa_scale(d: CircuitDesc, lanes: int = 8, steps: int = 132) -> Template:
                 x = [c["out", i] for i in range(KL)]
             for i in range(KL):
                 t.assign_constrained(out[l * KL + i], x[i])
-    return d.template("EcdsaScale", (lanes, steps), build)
+    return d.template("EcdsaScale" if hints == "inline" else "EcdsaScaleFn", (lanes, steps), build)
 
 
 def ecdsa_scale_expected(a_vals, b_vals, lanes: int = 8, steps: int = 132):

@@ -446,17 +446,14 @@ int cw_batch_create(const cw_circuit *c, uint32_t batch, int device, cw_batch **
     b->batch = batch;
     // Tile size (instances side by side in the slot store).  Lanes along instances (32-instance tiles: a warp is one
     // op, every access coalesced, no divergence) need enough tiles to fill the GPU with CTAs; below that, lanes run
-    // along the ops of a level (one-instance tiles).  Tapes with function calls keep one-instance tiles (the
-    // interpreter's frame is per thread and lanes diverge inside calls anyway).
+    // along the ops of a level (one-instance tiles).
     int bt = env_int("CW_BT_LOG2", -1);
     const uint64_t avg_w = t.n_levels() ? t.n_items() / t.n_levels() + 1 : 1;
     if (bt < 0) {
         bt = 0;
-        if (t.call_tab.empty()) {
-            if (batch >= 32u * 148u * 2u) bt = 5;
-            else
-                while (bt < 5 && (avg_w << bt) < 64 && (batch >> (bt + 1)) >= 296u) ++bt;  // very narrow tapes (Poseidon)
-        }
+        if (batch >= 32u * 148u * 2u) bt = 5;   // (also with function calls: the 32 lanes run the same function body)
+        else if (t.call_tab.empty())
+            while (bt < 5 && (avg_w << bt) < 64 && (batch >> (bt + 1)) >= 296u) ++bt;  // very narrow tapes (Poseidon)
     }
     if (bt > 5) bt = 5;
     b->bt_log2 = (u32)bt;

@@ -601,9 +601,15 @@ CW_HD void fr_exec(u32 opcode, u32 *r, const u32 *a, const u32 *b, u32 imm, cons
 // inferred statically)
 CW_HD void fr_apply_canonical(u32 op, u32 *r, const u32 *a, const u32 *b, const u32 *c, const FrParams &P, int &err) {
     if (op == OP_MUL) {
-        u32 am[8];
-        fr_to_mont(am, a, P);
-        fr_mont_mul(r, am, b, P);
+        // limb arithmetic inside hint functions multiplies small values: when the integer product provably stays
+        // below 2^(qbits-1) < q it IS the field product (36 limb products instead of two Montgomery products)
+        if (u256_bitlen(a) + u256_bitlen(b) < P.qbits) {
+            u256_mul_lo(r, a, b);
+        } else {
+            u32 am[8];
+            fr_to_mont(am, a, P);
+            fr_mont_mul(r, am, b, P);
+        }
     } else if (op == 2 /* DIV */) {
         u32 bm[8], im[8];
         fr_to_mont(bm, b, P);

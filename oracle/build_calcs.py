@@ -29,6 +29,8 @@ def circuits():
         "sha256_64_bls": ("bls12381", lambda d: C.sha256(d, 64)),
         "ecdsa_scale_8x132": ("bn128", lambda d: C.ecdsa_scale(d, 8, 132)),
         "sha256_512_bls": ("bls12381", lambda d: C.sha256(d, 512)),   # BASELINE.json configs[4]
+        # the bench circuit with function-computed hints (circom-ecdsa style)
+        "ecdsa_scale_calls_8x132": ("bn128", lambda d: C.ecdsa_scale(d, 8, 132, hints="functions")),
     }
 
 

@@ -26,6 +26,10 @@ CIRCUITS = {
     "int_div32": (lambda d: C.int_div(d, 32),
                   lambda r, q: {"a": r.choice([0, 1, 2**32 - 1, r.randrange(2**32)]),
                                 "b": r.choice([1, 2**32 - 1, r.randrange(1, 2**r.randrange(1, 33))])}),
+    # the bench circuit's BigMultModP with its quotient / remainder hints computed by a long_div-style function
+    "ecdsa_calls_1x2": (lambda d: C.ecdsa_scale(d, 1, 2, hints="functions"),
+                        lambda r, q: {"a": [r.choice([2**64 - 1, r.getrandbits(64)]) for _ in range(4)],
+                                      "b": [r.choice([2**64 - 1, 0, r.getrandbits(64)]) for _ in range(4)]}),
 }
 
 

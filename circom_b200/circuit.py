@@ -328,6 +328,17 @@ class Template:
         self.ops.append((OPS["CALL"], dst, (K_NONE, 0, fn.id), (K_NONE, 0, len(exprs)), NONE_REF))
         return Expr(self, dst)
 
+    def call_array(self, fn: "Function", args: Sequence, n: int) -> List[Expr]:
+        """`var r[n] = f(args...)`: ONE call whose n results land in n consecutive temporaries (the reference's
+        CallBucket with a destination of size n, call_bucket.rs:466-533)"""
+        assert len(args) == fn.n_params and 1 <= n <= fn.n_results, "bad array call of %s" % fn.name
+        exprs = [a if isinstance(a, Expr) else self.const(a) for a in args]
+        for e in exprs:
+            self.ops.append((OPS["ARG"], NONE_REF, e.ref, NONE_REF, NONE_REF))
+        dsts = [self._tmp() for _ in range(n)]
+        self.ops.append((OPS["CALL"], dsts[0], (K_NONE, 0, fn.id), (K_NONE, 0, len(exprs)), (K_NONE, 0, n)))
+        return [Expr(self, d) for d in dsts]
+
     # -- statements -------------------------------------------------------------------
     def assign(self, dst: Expr, src) -> None:
         """`dst <-- src` (StoreBucket, store_bucket.rs:607-646)."""
@@ -451,6 +462,7 @@ class Function:
     def __init__(self, desc: "CircuitDesc", name: str, n_params: int):
         self.desc, self.name, self.n_params = desc, name, n_params
         self.n_regs = n_params
+        self.n_results = 1
         self.code: List[Tuple[int, Ref, Ref, Ref, Ref]] = []
         self._loops: List[Tuple[int, List[int]]] = []
         self._ifs: List[List[int]] = []
@@ -537,6 +549,13 @@ class Function:
 
     def ret(self, value) -> None:
         self.code.append((OPS["RET"], NONE_REF, self._operand(value), NONE_REF, NONE_REF))
+
+    def ret_array(self, base: int, n: int) -> None:
+        """`return arr;` for a `var arr[n]` (ReturnBucket with_size = n, return_bucket.rs:70-120: the reference copies n
+        elements into the caller's destination): registers base .. base+n-1 are the results of a `call_array`"""
+        assert 1 <= n and base + n <= self.n_regs
+        self.n_results = max(self.n_results, n)
+        self.code.append((OPS["RET"], NONE_REF, (K_TMP, 0, base), (K_NONE, 0, n), NONE_REF))
 
     def finalize(self) -> "Function":
         assert not self._loops and not self._ifs and self.code and self.code[-1][0] == OPS["RET"]

@@ -31,10 +31,10 @@ def _split(t: Template, x):
 
 
 def fn_modp_limb(d: CircuitDesc):
-    """function modp_limb(X[8], sel): quotient and remainder of the 512-bit X (eight 64-bit limbs) by the secp256k1
-    prime, returned one limb per call (sel 0..4: quotient limb, 5..8: remainder limb) - the job of circom-ecdsa's
-    `long_div` hint (bigint_func.circom), written like it: `var` arrays indexed by run-time loop counters, a folding
-    loop whose trip count depends on the data, a limb-wise comparison with early exit, a conditional subtraction."""
+    """function long_div_p(X[8]) -> var out[9]: quotient (5 limbs) and remainder (4 limbs) of the 512-bit X (eight
+    64-bit limbs) by the secp256k1 prime, returned as ONE array - the job of circom-ecdsa's `long_div` hint
+    (bigint_func.circom), written like it: `var` arrays indexed by run-time loop counters, a folding loop whose trip
+    count depends on the data, a limb-wise comparison with early exit, a conditional subtraction."""
     from ..circuit import Function
     delta = (1 << 32) + 977
     p_l = _limbs(SECP256K1_P)
@@ -43,9 +43,8 @@ def fn_modp_limb(d: CircuitDesc):
         X = f.array(2 * KL)
         for i in range(2 * KL):
             f.store(X, f.var(i), f.param(i))
-        sel = f.param(2 * KL)
-        R = f.array(KL)
-        Q = f.array(KL + 1)
+        Q = f.array(2 * KL + 1)          # out[0..4] = quotient, out[5..8] = remainder: one contiguous `var out[9]`
+        R = Q + KL + 1
         Pp = f.array(KL)
         for i in range(KL):
             f.store(Pp, f.var(i), p_l[i])
@@ -120,20 +119,14 @@ def fn_modp_limb(d: CircuitDesc):
         f.set(i, i + 1)
         f.loop_end()
         f.if_end()
-        res = f.var(0)
-        f.if_begin(sel.leq(four))
-        f.set(res, f.load(Q, sel))
-        f.if_else()
-        f.set(res, f.load(R, sel - (four + 1)))
-        f.if_end()
-        f.ret(res)
-    return d.function("modp_limb", 2 * KL + 1, build)
+        f.ret_array(Q, 2 * KL + 1)
+    return d.function("long_div_p", 2 * KL, build)
 
 
 def big_mult_mod_p(d: CircuitDesc, hints: str = "inline") -> Template:
     """out = a*b mod p for 4x64-bit limb operands (limbs of a, b must be < 2^64).  hints = "inline": quotient and
-    remainder hints as straight-line shifts and masks; "functions": one call of `modp_limb` per hint limb (the
-    circom-ecdsa style: hints computed by functions with data-dependent control flow)."""
+    remainder hints as straight-line shifts and masks; "functions": `var qr[9] = long_div_p(P)`, one array-valued
+    call (the circom-ecdsa style: hints computed by functions with data-dependent control flow)."""
     fmod = fn_modp_limb(d) if hints == "functions" else None
     n2b64 = num2bits(d, N)
     n2b_carry = num2bits(d, 72)
@@ -180,10 +173,11 @@ def big_mult_mod_p(d: CircuitDesc, hints: str = "inline") -> Template:
             P.append(lo)
         P.append(c)                                # limb 7 (< 2^64)
         if fmod is not None:
+            qr = t.call_array(fmod, P, 2 * KL + 1)     # var qr[9] = long_div_p(P): ONE call
             for i in range(KL):
-                t.assign(out[i], t.call(fmod, P + [KL + 1 + i]))
+                t.assign(out[i], qr[KL + 1 + i])
             for i in range(KL + 1):
-                t.assign(quo[i], t.call(fmod, P + [i]))
+                t.assign(quo[i], qr[i])
         # first fold: R1 = Xlo + Xhi*delta (5 limbs), Q1 = Xhi
         R = []
         c = t.const(0)

@@ -88,3 +88,83 @@ def int_div(d: CircuitDesc, nbits: int = 32) -> Template:
         t.assign_constrained(c["in", 1], b)
         t.constrain(c["out"], 1)
     return d.template("IntDiv", (nbits,), build)
+
+
+def fn_divmod_array(d: CircuitDesc, nbits: int = 64) -> Function:
+    """function divmod_arr(a, b) { var out[3]; ... return out; }: quotient, remainder and bit length of `a` from ONE
+    call (`var qr[3] = divmod_arr(a, b);`).  An early `return out;` for b == 0 makes it a function with two RETs."""
+    def build(f: Function):
+        a, b = f.param(0), f.param(1)
+        out = f.array(3)
+        bits = f.array(nbits)
+        i = f.var(0)
+        t = f.var(a)
+        f.loop_begin()
+        f.loop_break_if_zero(t.neq(0))
+        f.store(bits, i, t & 1)
+        f.set(t, t >> 1)
+        f.set(i, i + 1)
+        f.loop_end()
+        two = f.var(2)
+        f.store(out, two, i)
+        f.if_begin(b.eq(0))
+        f.ret_array(out, 3)
+        f.if_end()
+        q = f.var(0)
+        r = f.var(0)
+        f.loop_begin()
+        f.loop_break_if_zero(i.neq(0))
+        f.set(i, i - 1)
+        f.set(r, r * 2 + f.load(bits, i))
+        f.set(q, q * 2)
+        f.if_begin(r.geq(b))
+        f.set(r, r - b)
+        f.set(q, q + 1)
+        f.if_end()
+        f.loop_end()
+        zero = f.var(0)
+        one = f.var(1)
+        f.store(out, zero, q)
+        f.store(out, one, r)
+        f.ret_array(out, 3)
+    return d.function("divmod_arr%d" % nbits, 2, build)
+
+
+def int_div_array(d: CircuitDesc, nbits: int = 32, use: str = "all") -> Template:
+    """IntDiv with its three hints from one array-returning call.  use = "all": q, r, nbits are outputs;
+    "tail": only r and nbits are read (the first result of the call is dead); "head": only q (the others are dead)."""
+    fdiv = fn_divmod_array(d, 64)
+    n2b = num2bits(d, nbits)
+
+    def build(t: Template):
+        a = t.input("a")
+        b = t.input("b")
+        if use == "head":
+            q = t.output("q")
+            res = t.call_array(fdiv, [a, b], 3)
+            t.assign(q, res[0])
+            cq = t.component("rq", n2b)
+            t.assign_constrained(cq["in"], q)
+            return
+        if use == "tail":
+            r = t.output("r")
+            nb = t.output("nbits")
+            res = t.call_array(fdiv, [a, b], 3)
+            t.assign(r, res[1])
+            t.assign(nb, res[2])
+            cr = t.component("rr", n2b)
+            t.assign_constrained(cr["in"], r)
+            return
+        q = t.output("q")
+        r = t.output("r")
+        nb = t.output("nbits")
+        res = t.call_array(fdiv, [a, b], 2)            # fewer results than the function returns: the first two
+        t.assign(q, res[0])
+        t.assign(r, res[1] + 0 * res[0])
+        t.assign(nb, t.call_array(fdiv, [a, b], 3)[2])
+        t.constrain(q * b + r, a)
+        cq = t.component("rq", n2b)
+        t.assign_constrained(cq["in"], q)
+        cr = t.component("rr", n2b)
+        t.assign_constrained(cr["in"], r)
+    return d.template("IntDivArr_" + use, (nbits,), build)

@@ -149,7 +149,8 @@ struct Lowerer {
     std::vector<int32_t> sig_vid;
     // provisional tape
     std::vector<uint32_t> pops;  // 4 words per op
-    std::vector<uint32_t> pcalls;  // provisional call table: {function, n_args, arg operands...}
+    std::vector<uint32_t> pcalls;  // provisional call table: {function, n_args, arg operands..., n_extra, provisional slots of results 1..}
+    std::vector<uint32_t> fn_min_ret;  // per function: the fewest values any of its RETs returns
     std::vector<uint32_t> plevel;
     std::vector<uint32_t> slot_level;  // per provisional slot
     // constant table (raw patterns)
@@ -564,11 +565,22 @@ struct Lowerer {
                     lvl = std::max(lvl, operand_level(opnd));
                 }
                 argstack.resize(argstack.size() - n);
+                // `var r[k] = f(..)`: ONE call, k results.  Result 0 is the CALL's own value; every further result is a
+                // pseudo-op (47) that owns a slot but no tape word - the call stores it through the call table
+                const uint32_t n_res = rk(o.c) == K_NONE && ridx(o.c) > 1 ? ridx(o.c) : 1;
+                if (rk(o.d) != K_TMP || (uint64_t)ridx(o.d) + n_res > tmp.size() || n_res > fn_min_ret[fid])
+                    throw std::runtime_error("lowering: bad call destination in " + t.name);
                 uint32_t slot = emit(45, NO_SLOT, NO_SLOT, NO_SLOT, true);
                 pops[pops.size() - 3] = off;  // operand `a` is the call-table offset, not a slot
                 slot_level.back() = lvl + 1;
-                if (rk(o.d) != K_TMP) throw std::runtime_error("lowering: bad call destination");
                 tmp[ridx(o.d)] = new_val(slot, FC);
+                pcalls.push_back(n_res - 1);
+                for (uint32_t k = 1; k < n_res; ++k) {
+                    uint32_t s = emit(47, slot);
+                    slot_level.back() = lvl + 1;   // written by the call itself
+                    pcalls.push_back(s);
+                    tmp[ridx(o.d) + k] = new_val(s, FC);
+                }
                 continue;
             }
             if (o.op == CW_OP_ASSERT_EQ || o.op == CW_OP_ASSERT) {
@@ -823,6 +835,8 @@ struct Lowerer {
                 } else if (o.op == 45 /* CALL */) {
                     if (rk(o.d) != K_TMP) throw std::runtime_error("cb2c: bad call destination in template " + t.name);
                     check_ref(o.d, false, true);
+                    if (rk(o.c) == K_NONE && ridx(o.c) > 1 && (ridx(o.c) > 64 || (uint64_t)ridx(o.d) + ridx(o.c) > t.n_tmp))
+                        throw std::runtime_error("cb2c: bad result count of a call in template " + t.name);
                 } else {
                     if (o.op < CW_OP_MUL || o.op > CW_OP_INV) throw std::runtime_error("cb2c: unknown opcode in template " + t.name);
                     const bool is_assert = o.op == CW_OP_ASSERT || o.op == CW_OP_ASSERT_EQ;
@@ -907,6 +921,7 @@ struct Lowerer {
             T.fn_info.push_back(n_instr);
             T.fn_info.push_back(n_regs);
             T.fn_info.push_back(n_params);
+            uint32_t min_ret = 0xFFFFFFFFu;
             auto bad = [&](const char *what) { throw std::runtime_error(std::string("cb2c: function body: ") + what); };
             auto reg = [&](uint64_t w) -> uint32_t {   // a register
                 if (rk(w) != K_TMP || ridx(w) >= n_regs) bad("bad register");
@@ -933,7 +948,14 @@ struct Lowerer {
                 switch (op) {
                     case 40 /* JMP */: e[1] = imm(w[2], n_instr); break;
                     case 41 /* JZ */: e[1] = val(w[2], false); e[2] = imm(w[3], n_instr); break;
-                    case 42 /* RET */: e[1] = val(w[2], false); break;
+                    case 42 /* RET: a value, or (operand b = count > 1) `count` consecutive registers from register a */: {
+                        e[1] = val(w[2], false);
+                        const uint32_t cnt = rk(w[3]) == K_NONE && ridx(w[3]) > 1 ? ridx(w[3]) : 1;
+                        if (cnt > 1 && (rk(w[2]) != K_TMP || cnt > 64 || (uint64_t)ridx(w[2]) + cnt > n_regs)) bad("bad array return");
+                        e[2] = 0x40000000u | cnt;
+                        min_ret = std::min(min_ret, cnt);
+                        break;
+                    }
                     case 43 /* LOADX: d = regs[base + b] */:
                         e[0] = reg(w[1]); e[1] = imm(w[2], n_regs); e[2] = val(w[3], false);
                         break;
@@ -950,6 +972,7 @@ struct Lowerer {
                 T.fn_code.push_back(op);
                 for (uint32_t x : e) T.fn_code.push_back(x);
             }
+            fn_min_ret.push_back(min_ret == 0xFFFFFFFFu ? 1 : min_ret);
         }
     }
     uint32_t main_tid = 0;
@@ -1103,13 +1126,13 @@ struct Lowerer {
                 const size_t c = slot - n_pre;
                 const uint32_t opc = pops[c * 4];
                 if (uses[slot] != 1 || cons[slot] != reader || cons_pos[slot] != pos || claimed[slot] >= 0) return false;
-                if (is_assert_op(opc) || opc == 45 || opc == DOP_BITS || opc == CW_OP_COPY) return false;
+                if (is_assert_op(opc) || opc == 45 || opc == 47 || opc == DOP_BITS || opc == CW_OP_COPY) return false;
                 return true;
             };
             for (size_t i = 0; i < n_prov; ++i) {
                 if (!live[n_pre + i]) continue;
                 const uint32_t *o = &pops[i * 4];
-                if (o[0] == 45) continue;
+                if (o[0] == 45 || o[0] == 47) continue;
                 uint32_t ka = candidate(o[1], i, 1) ? o[1] - n_pre : NO_SLOT;
                 uint32_t kb = candidate(o[2], i, 2) ? o[2] - n_pre : NO_SLOT;
                 if (ka != NO_SLOT && kb != NO_SLOT) {
@@ -1151,6 +1174,10 @@ struct Lowerer {
                 const uint32_t *o = &pops[i * 4];
                 uint32_t e = 0;
                 uint64_t sg = 1469598103934665603ull ^ o[0];
+                if (o[0] == 47) {  // a further result of a call: written by the call's work item
+                    glevel[n_pre + i] = glevel[o[1]];
+                    continue;
+                }
                 if (o[0] == 45) {
                     uint32_t n = pcalls[o[1] + 1];
                     for (uint32_t k = 0; k < n; ++k) {
@@ -1181,7 +1208,7 @@ struct Lowerer {
         std::vector<uint32_t> order;
         order.reserve(n_roots);
         for (size_t i = 0; i < n_prov; ++i)
-            if (live[n_pre + i] && !fusedf[i]) order.push_back((uint32_t)i);
+            if (live[n_pre + i] && !fusedf[i] && pops[i * 4] != 47) order.push_back((uint32_t)i);
         std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
             uint32_t lx = glevel[n_pre + x], ly = glevel[n_pre + y];
             if (lx != ly) return lx < ly;
@@ -1199,6 +1226,15 @@ struct Lowerer {
             uint32_t p = n_pre + order[r];
             if (claimed[p] >= 0) remap[p] = (uint32_t)claimed[p];
             else if (!is_assert_op(pops[(size_t)order[r] * 4])) remap[p] = next_tmp++;
+            if (pops[(size_t)order[r] * 4] == 45) {  // the further results of a call follow its first one
+                const uint32_t *ct = &pcalls[pops[(size_t)order[r] * 4 + 1]];
+                const uint32_t *ex = ct + 2 + ct[1];
+                for (uint32_t k = 0; k < ex[0]; ++k) {
+                    const uint32_t s = ex[1 + k];
+                    if (!live[s]) continue;
+                    remap[s] = claimed[s] >= 0 ? (uint32_t)claimed[s] : next_tmp++;
+                }
+            }
         }
         if (next_tmp >= DST_ACC) throw std::runtime_error("circuit too large for the packed tape word (2^24 slots)");
         T.ops.clear();
@@ -1222,6 +1258,9 @@ struct Lowerer {
                     uint32_t a = pcalls[o[1] + 2 + k];
                     T.call_tab.push_back((a & OPERAND_CONST) ? a : remap[a]);
                 }
+                const uint32_t *ex = &pcalls[o[1] + 2 + n];
+                T.call_tab.push_back(ex[0]);
+                for (uint32_t k = 0; k < ex[0]; ++k) T.call_tab.push_back(live[ex[1 + k]] ? remap[ex[1 + k]] : NO_SLOT);
                 return;
             }
             for (int k = 1; k <= 3; ++k) {
@@ -1352,11 +1391,14 @@ struct Lowerer {
                         if (!(o[k] & (OPERAND_CONST | OPERAND_ACC))) o[k] = newid[o[k]];
                     }
                 }
-                for (size_t i = 0; i < T.call_tab.size();) {  // {function, n_args, operands...}
-                    const uint32_t n = T.call_tab[i + 1];
-                    for (uint32_t k = 0; k < n; ++k)
-                        if (!(T.call_tab[i + 2 + k] & OPERAND_CONST)) T.call_tab[i + 2 + k] = newid[T.call_tab[i + 2 + k]];
-                    i += 2 + n;
+                for (size_t i = 0; i < T.call_tab.size();) {  // {function, n_args, operands..., n_extra, destinations...}
+                    const uint32_t n = T.call_tab[i + 1], nx = T.call_tab[i + 2 + n];
+                    for (uint32_t k = 0; k < n + 1 + nx; ++k) {
+                        if (k == n) continue;
+                        uint32_t &e = T.call_tab[i + 2 + k];
+                        if (!(e & OPERAND_CONST)) e = newid[e];   // (NO_SLOT, a dead result, has the constant bit)
+                    }
+                    i += 3 + n + nx;
                 }
                 T.n_bitwords = n_words;
                 next_tmp = nw;
@@ -1407,14 +1449,22 @@ struct Lowerer {
                         for (uint32_t j = 0; j < run; ++j) phys[d + j] = next_phys++;  // consecutive, never released
                         continue;
                     }
-                    if (d < n_resident) continue;
-                    uint32_t p;
-                    if (!free_ids.empty()) { p = free_ids.back(); free_ids.pop_back(); }
-                    else p = next_phys++;
-                    phys[d] = p;
-                    // readers are in levels (l, last[d]]; a value nobody reads (cannot happen after the dead-value
-                    // sweep) would be released at once
-                    release[std::min<size_t>(std::max<size_t>(last[d], l) + 1, n_lv)].push_back(p);
+                    auto alloc = [&](uint32_t d) {
+                        if (d < n_resident) return;
+                        uint32_t p;
+                        if (!free_ids.empty()) { p = free_ids.back(); free_ids.pop_back(); }
+                        else p = next_phys++;
+                        phys[d] = p;
+                        // readers are in levels (l, last[d]]; a value nobody reads (the first result of a call whose
+                        // other results are used) is released at once
+                        release[std::min<size_t>(std::max<size_t>(last[d], l) + 1, n_lv)].push_back(p);
+                    };
+                    alloc(d);
+                    if (opc == 45) {  // the further results of a call
+                        const uint32_t *ex = &T.call_tab[o[1] + 2 + T.call_tab[o[1] + 1]];
+                        for (uint32_t k = 0; k < ex[0]; ++k)
+                            if (ex[1 + k] != NO_SLOT) alloc(ex[1 + k]);
+                    }
                 }
             }
             auto map = [&](uint32_t o) { return is_tmp(o) ? phys[o] : o; };
@@ -1431,9 +1481,10 @@ struct Lowerer {
                 }
             }
             for (size_t i = 0; i < T.call_tab.size();) {
-                const uint32_t n = T.call_tab[i + 1];
-                for (uint32_t k = 0; k < n; ++k) T.call_tab[i + 2 + k] = map(T.call_tab[i + 2 + k]);
-                i += 2 + n;
+                const uint32_t n = T.call_tab[i + 1], nx = T.call_tab[i + 2 + n];
+                for (uint32_t k = 0; k < n + 1 + nx; ++k)
+                    if (k != n) T.call_tab[i + 2 + k] = map(T.call_tab[i + 2 + k]);
+                i += 3 + n + nx;
             }
             next_tmp = next_phys;
         }
@@ -1448,7 +1499,12 @@ struct Lowerer {
                 const uint32_t opc = o[0] & 0xFFu;
                 if (!is_assert_op(opc)) T.n_values += opc == DOP_BITS ? (o[3] >> 24) + 1u : 1u;  // (fused values included: S_w of 8(d))
                 if (!is_assert_op(opc) && (o[0] >> 8) < DST_ACC) ++T.n_stored;
-                if (opc == 45) continue;
+                if (opc == 45) {
+                    const uint32_t *ex = &T.call_tab[o[1] + 2 + T.call_tab[o[1] + 1]];
+                    for (uint32_t k = 0; k < ex[0]; ++k)
+                        if (ex[1 + k] != NO_SLOT) { ++T.n_values; ++T.n_stored; }
+                    continue;
+                }
                 for (int k = 1; k <= 3; ++k) {
                     if (k == 3 && c_is_immediate(opc)) break;
                     if (!(o[k] & (OPERAND_CONST | OPERAND_BIT | OPERAND_ACC))) ++T.n_slot_operands;
@@ -1542,7 +1598,7 @@ struct BlobR {
         p += n;
     }
 };
-constexpr uint32_t BLOB_VERSION = 4;
+constexpr uint32_t BLOB_VERSION = 5;
 }  // namespace
 
 void serialize_tape(const Tape &t, std::vector<uint8_t> &out) {

@@ -659,14 +659,19 @@ CW_HD int vm_index(const u32 *v, u32 base, u32 n_regs) {
     return (int)(v[0] + base);
 }
 // regs: n_regs * 8 words, parameters already stored in registers 0..n_params-1.  err: 1 division by zero,
-// 2 bad index / runaway loop.
+// 2 bad index / runaway loop.  `result` is the (first) returned value; a `RET` with a count c > 1 returns the c
+// consecutive registers ret_base .. ret_base + c - 1 (`return arr;`, return_bucket.rs:70-120), the caller copies
+// those it wants out of `regs`.
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-inline void vm_run(const u32 *code, FnInfo fi, u32 *regs, const u32 *consts32, u32 *result, const FrParams &P, int &err) {
+inline void vm_run(const u32 *code, FnInfo fi, u32 *regs, const u32 *consts32, u32 *result, const FrParams &P, int &err,
+                   u32 &ret_base, u32 &ret_cnt) {
     const u32 *ins = code + 5 * (size_t)fi.code_off;
     u32 pc = 0;
     u256_set_u32(result, 0);
+    ret_base = 0;
+    ret_cnt = 0;
     for (u32 step = 0; step < (u32)VM_MAX_STEPS; ++step) {
         if (pc >= fi.n_instr) { err = 2; return; }
         const u32 op = ins[5 * pc], d = ins[5 * pc + 1], a = ins[5 * pc + 2], b = ins[5 * pc + 3], c = ins[5 * pc + 4];
@@ -675,7 +680,12 @@ inline void vm_run(const u32 *code, FnInfo fi, u32 *regs, const u32 *consts32, u
         if (op == FOP_JMP) { pc = a & 0x3FFFFFFFu; continue; }
         vm_operand(va, a, regs, consts32);
         if (op == FOP_JZ) { if (u256_is_zero(va)) pc = b & 0x3FFFFFFFu; continue; }
-        if (op == FOP_RET) { u256_set(result, va); return; }
+        if (op == FOP_RET) {
+            u256_set(result, va);
+            ret_cnt = b & 0x3FFFFFFFu;
+            if (ret_cnt > 1) ret_base = a;   // (the lowering checked: a register, a + count <= n_regs)
+            return;
+        }
         vm_operand(vb, b, regs, consts32);
         if (op == FOP_LOADX) {
             int i = vm_index(vb, a & 0x3FFFFFFFu, fi.n_regs);
@@ -696,6 +706,40 @@ inline void vm_run(const u32 *code, FnInfo fi, u32 *regs, const u32 *consts32, u
         for (int k = 0; k < 8; ++k) regs[8 * (size_t)d + k] = r[k];
     }
     err = 2;
+}
+
+// ---- R1CS rows of small integers ------------------------------------------------------------------------------
+// A linear combination whose terms are all "small" (32-bit witness values times +-1 / +-2^k, the lazy sums of
+// kernels.cuh: r1cs_lc) is known as two plain integers, the sum of its positive and of its negative terms.  When the
+// sums of A and B fit 64 bits and those of C 128 bits,
+//      a = pa - na,  b = pb - nb  in (-2^64, 2^64),   c = pc - nc  in (-2^128, 2^128),
+// a*b - c lies in (-2^129, 2^129); every supported prime is above 2^250, so a*b = c (mod q) holds exactly when it
+// holds over the integers: no modular reduction, no Montgomery product.
+CW_HD void mul64wide(u64 a, u64 b, u64 &lo, u64 &hi) {
+#if defined(__CUDA_ARCH__)
+    lo = a * b;
+    hi = __umul64hi(a, b);
+#else
+    unsigned __int128 p = (unsigned __int128)a * b;
+    lo = (u64)p;
+    hi = (u64)(p >> 64);
+#endif
+}
+CW_HD bool small_row_holds(u64 pa, u64 na, u64 pb, u64 nb, u64 pc_lo, u64 pc_hi, u64 nc_lo, u64 nc_hi) {
+    const bool nega = pa < na, negb = pb < nb;
+    const u64 ma = nega ? na - pa : pa - na, mb = negb ? nb - pb : pb - nb;
+    u64 lo, hi;
+    mul64wide(ma, mb, lo, hi);
+    const bool neg = nega != negb;           // (a zero product has either sign)
+    // a*b = c   <=>   |ab| + nc = pc   (ab >= 0)      or      |ab| + pc = nc   (ab <= 0)
+    const u64 x_lo = neg ? pc_lo : nc_lo, x_hi = neg ? pc_hi : nc_hi;
+    const u64 y_lo = neg ? nc_lo : pc_lo, y_hi = neg ? nc_hi : pc_hi;
+    const u64 s_lo = lo + x_lo;
+    const u64 c0 = s_lo < lo ? 1u : 0u;
+    const u64 t = hi + x_hi;
+    const u64 s_hi = t + c0;
+    const bool carry = t < hi || s_hi < t;   // the sum left 128 bits: it cannot equal a 128-bit value
+    return !carry && s_lo == y_lo && s_hi == y_hi;
 }
 
 }  // namespace cw

@@ -110,7 +110,7 @@ struct TapeDev {
     const u32 *input_slot;     // slot of main input k
     const u32 *fn_code;        // register-machine code of the circuit's functions (5 words per instruction)
     const u32 *fn_info;        // per function {code offset, n_instr, n_regs, n_params}
-    const u32 *call_tab;       // per call {function, n_args, arg operands...}
+    const u32 *call_tab;       // per call {function, n_args, arg operands..., n_extra, slots of results 1..n_extra}
     u32 n_levels;
     u32 n_slots;
     u32 n_inputs;
@@ -149,7 +149,7 @@ __global__ void stage_inputs_kernel(TapeDev tp, const uint4 *__restrict__ inputs
 // A function call (circom `function` with run-time loops / branches): the thread copies the arguments into
 // the callee's registers (local memory: they are indexed dynamically) and interprets the body.
 template <int PRIME, bool BP>
-__device__ __noinline__ void exec_call(const TapeDev &tp, u32 call_off, const uint4 *base, const u32 *plane_base,
+__device__ __noinline__ void exec_call(const TapeDev &tp, u32 call_off, uint4 *base, const u32 *plane_base,
                                        u32 bt_log2, u32 li, u32 *r, int *err) {
     const FrParams &P = CW_FR(PRIME, tp.prime);
     const u32 *ct = tp.call_tab + call_off;
@@ -167,7 +167,16 @@ __device__ __noinline__ void exec_call(const TapeDev &tp, u32 call_off, const ui
         for (int j = 0; j < 8; ++j) regs[8 * k + j] = v[j];
     }
     int e = 0;
-    vm_run(tp.fn_code, fi, regs, reinterpret_cast<const u32 *>(tp.consts), r, P, e);
+    u32 ret_base, ret_cnt;
+    vm_run(tp.fn_code, fi, regs, reinterpret_cast<const u32 *>(tp.consts), r, P, e, ret_base, ret_cnt);
+    // `var q[k] = f(..)`: results 1 .. k-1 go straight from the callee's registers to their slots (result 0 is `r`)
+    const u32 n_extra = __ldg(&ct[2 + n_args]);
+    for (u32 k = 0; k < n_extra; ++k) {
+        const u32 d = __ldg(&ct[3 + n_args + k]);
+        if (d == 0xFFFFFFFFu) continue;   // a result nobody reads
+        if (k + 1 >= ret_cnt) { e = 2; continue; }
+        store_slot(&regs[8 * (ret_base + k + 1)], base, d, bt_log2, li);
+    }
     *err = e;
 }
 
@@ -511,12 +520,19 @@ __device__ __forceinline__ void acc128_add(unsigned long long &lo, unsigned long
     hi += h + (lo < l ? 1ull : 0ull);
 }
 
+// A linear combination in two parts: the lazy integer sums of its small terms (positive / negative coefficients) and
+// the modular accumulator `acc` of the others; `general` tells whether acc was used at all.
+struct LcSum {
+    unsigned long long plo, phi, nlo, nhi;
+    bool general;
+};
 template <int PRIME>
-__device__ __forceinline__ void r1cs_lc(u32 *acc, const R1csDev &R, unsigned long long b, unsigned long long e,
+__device__ __forceinline__ void r1cs_lc(u32 *acc, LcSum &sum, const R1csDev &R, unsigned long long b, unsigned long long e,
                                         const StoreDev &S, const uint4 *__restrict__ tb, const u32 *__restrict__ pb,
                                         u32 li, const FrParams &P, unsigned long long *__restrict__ first_bad_inst) {
     u256_set_u32(acc, 0);
     unsigned long long plo = 0, phi = 0, nlo = 0, nhi = 0;
+    bool general = false;
     const bool lazy = e - b < 65536ull;   // 2^16 terms below 2^112 cannot overflow 128 bits
     for (unsigned long long k = b; k < e; ++k) {
         const uint4 term = __ldg(&R.terms[k]);
@@ -574,14 +590,20 @@ __device__ __forceinline__ void r1cs_lc(u32 *acc, const R1csDev &R, unsigned lon
         if (neg) fr_sub(t, acc, x, P);
         else fr_add(t, acc, x, P);
         u256_set(acc, t);
+        general = true;
     }
-    if (plo | phi) {
-        u32 v[8] = {(u32)plo, (u32)(plo >> 32), (u32)phi, (u32)(phi >> 32), 0u, 0u, 0u, 0u}, t[8];
+    sum.plo = plo; sum.phi = phi; sum.nlo = nlo; sum.nhi = nhi;
+    sum.general = general;
+}
+// the value of the linear combination as a canonical field element: the lazy sums enter the accumulator once
+__device__ __forceinline__ void r1cs_lc_finish(u32 *acc, const LcSum &s, const FrParams &P) {
+    if (s.plo | s.phi) {
+        u32 v[8] = {(u32)s.plo, (u32)(s.plo >> 32), (u32)s.phi, (u32)(s.phi >> 32), 0u, 0u, 0u, 0u}, t[8];
         fr_add(t, acc, v, P);
         u256_set(acc, t);
     }
-    if (nlo | nhi) {
-        u32 v[8] = {(u32)nlo, (u32)(nlo >> 32), (u32)nhi, (u32)(nhi >> 32), 0u, 0u, 0u, 0u}, t[8];
+    if (s.nlo | s.nhi) {
+        u32 v[8] = {(u32)s.nlo, (u32)(s.nlo >> 32), (u32)s.nhi, (u32)(s.nhi >> 32), 0u, 0u, 0u, 0u}, t[8];
         fr_sub(t, acc, v, P);
         u256_set(acc, t);
     }
@@ -637,16 +659,28 @@ __global__ void __launch_bounds__(256, MINB) r1cs_check_kernel(R1csDev R, StoreD
             const unsigned long long p0 = __ldg(&R.row_ptr[3 * (size_t)row]), p1 = __ldg(&R.row_ptr[3 * (size_t)row + 1]),
                                      p2 = __ldg(&R.row_ptr[3 * (size_t)row + 2]), p3 = __ldg(&R.row_ptr[3 * (size_t)row + 3]);
             u32 a[8], b[8], c[8];
-            r1cs_lc<PRIME>(a, R, p0, p1, S, tb, pb, li, P, &first_bad[inst]);
-            r1cs_lc<PRIME>(b, R, p1, p2, S, tb, pb, li, P, &first_bad[inst]);
-            r1cs_lc<PRIME>(c, R, p2, p3, S, tb, pb, li, P, &first_bad[inst]);
-            if (EVAL) {
-                const size_t o = ((size_t)inst * out.m + row) * 2;
-                stg256(out.a + o, a);
-                stg256(out.b + o, b);
-                stg256(out.c + o, c);
+            LcSum sa, sb, sc;
+            r1cs_lc<PRIME>(a, sa, R, p0, p1, S, tb, pb, li, P, &first_bad[inst]);
+            r1cs_lc<PRIME>(b, sb, R, p1, p2, S, tb, pb, li, P, &first_bad[inst]);
+            r1cs_lc<PRIME>(c, sc, R, p2, p3, S, tb, pb, li, P, &first_bad[inst]);
+            // rows of small integers (boolean logic, carries, recomposition sums: the bulk of circom constraints) are
+            // decided over the integers, without a reduction (fr_device.cuh: small_row_holds)
+            bool ok;
+            if (!EVAL && !(sa.general | sb.general | sc.general) && !(sa.phi | sa.nhi | sb.phi | sb.nhi)) {
+                ok = small_row_holds(sa.plo, sa.nlo, sb.plo, sb.nlo, sc.plo, sc.phi, sc.nlo, sc.nhi);
+            } else {
+                r1cs_lc_finish(a, sa, P);
+                r1cs_lc_finish(b, sb, P);
+                r1cs_lc_finish(c, sc, P);
+                if (EVAL) {
+                    const size_t o = ((size_t)inst * out.m + row) * 2;
+                    stg256(out.a + o, a);
+                    stg256(out.b + o, b);
+                    stg256(out.c + o, c);
+                }
+                ok = r1cs_row_holds(a, b, c, P);
             }
-            if (!r1cs_row_holds(a, b, c, P)) atomicMin(&first_bad[inst], (unsigned long long)row);
+            if (!ok) atomicMin(&first_bad[inst], (unsigned long long)row);
         }
     }
 }

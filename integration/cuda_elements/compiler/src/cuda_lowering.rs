@@ -254,12 +254,35 @@ impl WriteCuda for CallBucket {    // call_bucket.rs:466-533
             let r = cx.as_ref(&v);
             cx.rec.ops.push(OpRec { op: Op::ARG, d: Ref::None, a: r, b: Ref::None, c: Ref::None });
         }
+        // `var r[n] = f(..)`: ONE call, its n results in n consecutive temporaries (CALL operand c = n, docs/CB2C.md)
+        let n_res = match &self.return_info {
+            ReturnType::Final(f) => match f.context.size { SizeOption::Single(n) => n, _ => return Err(()) },
+            _ => 1,
+        };
+        if n_res == 0 || n_res > 64 { return Err(()); }
         let d = cx.tmp();
-        cx.rec.ops.push(OpRec { op: Op::CALL, d, a: Ref::Imm(fid), b: Ref::Imm(self.arguments.len() as u32), c: Ref::None });
+        let d0 = match d { Ref::Tmp(i) => i, _ => return Err(()) };
+        for _ in 1..n_res { cx.tmp(); }
+        cx.rec.ops.push(OpRec { op: Op::CALL, d, a: Ref::Imm(fid), b: Ref::Imm(self.arguments.len() as u32),
+                                c: if n_res > 1 { Ref::Imm(n_res as u32) } else { Ref::None } });
         match &self.return_info {
             ReturnType::Intermediate { .. } => Ok(Some(Val::Dynamic(d))),
+            ReturnType::Final(f) if n_res > 1 => {                  // array destination: variables only (signals: per-element COPY)
+                let idx = match &f.dest { LocationRule::Indexed { location, .. } => cx.address(location)?, _ => return Err(()) };
+                for k in 0..n_res {
+                    let r = Ref::Tmp(d0 + k as u32);
+                    match &f.dest_address_type {
+                        AddressType::Variable => cx.vars[idx + k] = Val::Dynamic(r),
+                        AddressType::Signal => { let o = cx.own(idx + k); cx.rec.ops.push(OpRec { op: Op::COPY, d: o, a: r, b: Ref::None, c: Ref::None }); }
+                        AddressType::SubcmpSignal { cmp_address, .. } => {
+                            let cmp = cx.address(cmp_address)?;
+                            cx.rec.ops.push(OpRec { op: Op::COPY, d: Ref::Sub { sub: cx.sub_of_cmp[cmp], idx: (idx + k) as u32 }, a: r, b: Ref::None, c: Ref::None });
+                        }
+                    }
+                }
+                Ok(None)
+            }
             ReturnType::Final(f) => {                               // `x <-- f(...)`: the store is part of the bucket
-                if f.context.size != SizeOption::Single(1) { return Err(()); } // array results: one call per element
                 let idx = match &f.dest { LocationRule::Indexed { location, .. } => cx.address(location)?, _ => return Err(()) };
                 match &f.dest_address_type {
                     AddressType::Variable => cx.vars[idx] = Val::Dynamic(d),
@@ -349,9 +372,23 @@ impl<'a> FunctionCtx<'a> {
                 self.rec.code[jmp].a = Ref::Imm(self.rec.code.len() as u32);
             }
             Instruction::Return(r) => {                    // return_bucket.rs:70-120
-                if r.with_size != 1 { return Err(()); }    // array results: one call per element (extra index parameter)
-                let v = self.value(&r.value)?;
-                self.push(Op::RET, Ref::None, v, Ref::None, Ref::None);
+                if r.with_size > 1 {                       // `return arr;`: with_size consecutive variable slots, returned in place
+                    if r.with_size > 64 { return Err(()); }
+                    let base = match r.value.as_ref() {
+                        Instruction::Load(l) => match (&l.address_type, &l.src) {
+                            (AddressType::Variable, LocationRule::Indexed { location, .. }) => match location.as_ref() {
+                                Instruction::Value(v) => v.value as u32,
+                                _ => return Err(()),
+                            },
+                            _ => return Err(()),
+                        },
+                        _ => return Err(()),
+                    };
+                    self.push(Op::RET, Ref::None, Ref::Tmp(base), Ref::Imm(r.with_size as u32), Ref::None);
+                } else {
+                    let v = self.value(&r.value)?;
+                    self.push(Op::RET, Ref::None, v, Ref::None, Ref::None);
+                }
             }
             Instruction::Assert(_) | Instruction::Log(_) => {}   // asserts inside functions abort the C++ run; here: status, see DESIGN
             _ => return Err(()),

@@ -24,6 +24,8 @@ def circuits():
         "less_than8": ("bn128", lambda d: C.less_than(d, 8)),
         "poseidon2": ("bn128", lambda d: C.poseidon(d, 2)),
         "int_div32": ("bn128", lambda d: C.int_div(d, 32)),
+        "int_div_arr32": ("bn128", lambda d: C.int_div_array(d, 32, "all")),     # `var qr[3] = f(a, b);`: one call, three results
+        "ecdsa_calls_2x5": ("bn128", lambda d: C.ecdsa_scale(d, 2, 5, hints="functions")),
         "ecdsa_scale_2x5": ("bn128", lambda d: C.ecdsa_scale(d, 2, 5)),
         "sha256compression": ("bn128", lambda d: C.sha256_compression(d)),
         "sha256_64_bls": ("bls12381", lambda d: C.sha256(d, 64)),
@@ -67,4 +69,4 @@ def build(names=None, force: bool = False):
 
 
 if __name__ == "__main__":
-    print("built:", build(sys.argv[1:] or None, force="--force" in sys.argv))
+    print("built:", build([a for a in sys.argv[1:] if a != "--force"] or None, force="--force" in sys.argv))

@@ -327,7 +327,9 @@ typedef struct {
 /* one function call: variables are registers, loops / branches test Fr_isTrue (loop_bucket.rs:76-91,
  * branch_bucket.rs:100-122), array variables are indexed through Fr_toInt (compute_bucket.rs:361-363).
  * returns 0 ok, -1 division by zero, -2 bad index / runaway */
-static int run_func(const circuit *c, const func *f, const fe *args, fe *result) {
+#define MAX_RESULTS 64
+/* result[0 .. *n_res): RET with a count in operand b returns that many consecutive registers (return_bucket.rs with_size) */
+static int run_func(const circuit *c, const func *f, const fe *args, fe *result, u32 *n_res) {
     fe *regs = (fe *)calloc(f->n_regs ? f->n_regs : 1, sizeof(fe));
     for (u32 i = 0; i < f->n_params; ++i) regs[i] = args[i];
     fe zero = fe_u64(0);
@@ -343,7 +345,16 @@ static int run_func(const circuit *c, const func *f, const fe *args, fe *result)
         }
         if (o->op == 40) { pc = RIDX(o->a); continue; }                          /* JMP */
         if (o->op == 41) { if (is_zero4(arg[0])) pc = RIDX(o->b); continue; }      /* JZ */
-        if (o->op == 42) { *result = *arg[0]; rc = 0; break; }                     /* RET */
+        if (o->op == 42) {                                                         /* RET */
+            u32 cnt = RK(o->b) == 0 ? RIDX(o->b) : 0;
+            if (cnt > 1) {
+                if (RK(o->a) != K_TMP || RIDX(o->a) + cnt > f->n_regs || cnt > MAX_RESULTS) break;
+                for (u32 k = 0; k < cnt; ++k) result[k] = regs[RIDX(o->a) + k];
+                *n_res = cnt;
+            } else { result[0] = *arg[0]; *n_res = 1; }
+            rc = 0;
+            break;
+        }
         if (o->op == 43 || o->op == 44) {                                          /* LOADX / STOREX */
             const fe *ix = arg[1];
             if (ix->v[1] | ix->v[2] | ix->v[3] || ix->v[0] + RIDX(o->a) >= f->n_regs) break;
@@ -394,12 +405,14 @@ static void run_comp(ctx_t *x, comp *me) {
         if (o->op == 46) { if (n_args < 64) argstack[n_args++] = *arg[0]; continue; }     /* ARG */
         if (o->op == 45) {                                                              /* CALL */
             u32 fid = RIDX(o->a), n = RIDX(o->b);
-            fe res = fe_u64(0);
+            fe res[MAX_RESULTS];
+            u32 got = 0, want = RK(o->c) == 0 && RIDX(o->c) > 1 ? RIDX(o->c) : 1;
             if (fid >= c->n_funcs || n > n_args) { x->status = -2; break; }
-            int rc = run_func(c, &c->fn[fid], &argstack[n_args - n], &res);
+            int rc = run_func(c, &c->fn[fid], &argstack[n_args - n], res, &got);
             n_args -= n;
             if (rc) { x->status = rc; break; }
-            tmp[RIDX(o->d)] = res;
+            if (got < want || RIDX(o->d) + want > t->n_tmp) { x->status = -2; break; }
+            for (u32 k = 0; k < want; ++k) tmp[RIDX(o->d) + k] = res[k];   /* n results in consecutive temporaries */
             continue;
         }
         if (o->op == OP_ASSERT_EQ || o->op == OP_ASSERT) {

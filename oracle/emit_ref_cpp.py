@@ -117,7 +117,10 @@ def _emit_function(w, f) -> None:
         elif op == 41:
             w("if (!Fr_isTrue(%s)) goto L%d;" % (addr(a), b[2]))
         elif op == 42:
-            w("Fr_copy(destination,%s); return;" % addr(a))
+            if b[0] == 0 and b[2] > 1:     # array return (return_bucket.rs:70-120: Fr_copyn of destination_size elements)
+                w("Fr_copyn(destination,&lvar[%d],destination_size); return;" % a[2])
+            else:
+                w("Fr_copy(destination,%s); return;" % addr(a))
         elif op == 43:
             w("Fr_copy(&lvar[%d],&lvar[%d + Fr_toInt(%s)]);" % (d[2], a[2], addr(b)))
         elif op == 44:
@@ -209,7 +212,7 @@ def _emit_template(w, t) -> None:
             w("FrElement lvarcall[%d];" % fn.n_regs)
             for k, r in enumerate(args):
                 w("Fr_copy(&lvarcall[%d],%s);" % (k, addr(r)))
-            w("%s_%d(ctx,lvarcall,myId,%s,1);" % (fn.name, fn.id, addr(d)))
+            w("%s_%d(ctx,lvarcall,myId,%s,%d);" % (fn.name, fn.id, addr(d), c[2] if c[0] == 0 and c[2] > 1 else 1))
             w("}")
             continue
         if op == 27:  # ASSERT_EQ

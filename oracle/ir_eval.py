@@ -56,6 +56,9 @@ def run_function(desc, F, fn, args):
             if val(a) == 0:
                 pc = b[2]
         elif op == OPS["RET"]:
+            n = b[2] if b[0] == 0 else 0          # array return: registers a .. a+n-1 (return_bucket.rs with_size)
+            if n > 1:
+                return [regs[a[2] + k] for k in range(n)]
             return val(a)
         elif op == OPS["LOADX"]:
             i = a[2] + to_int(val(b))
@@ -120,7 +123,14 @@ def evaluate(desc, inputs: Dict[str, Sequence[int]], check_asserts: bool = True)
                 n = b[2]
                 args = argstack[len(argstack) - n:]
                 del argstack[len(argstack) - n:]
-                tmp[d[2]] = run_function(desc, F, desc.functions[a[2]], args)
+                res = run_function(desc, F, desc.functions[a[2]], args)
+                n_res = cc[2] if cc[0] == 0 else 0
+                if n_res > 1:                      # one call, n_res results in consecutive temporaries
+                    assert isinstance(res, list) and len(res) >= n_res
+                    for k in range(n_res):
+                        tmp[d[2] + k] = res[k]
+                else:
+                    tmp[d[2]] = res[0] if isinstance(res, list) else res
                 continue
             if op == OPS["ASSERT_EQ"]:
                 if check_asserts and load(a) != load(b):

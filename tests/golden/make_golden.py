@@ -28,7 +28,8 @@ sys.path.insert(0, ROOT)
 
 from oracle import build_calcs  # noqa: E402
 
-NAMES = ["multiplier2", "all_ops", "all_ops_bls", "less_than8", "poseidon2", "int_div32", "ecdsa_scale_2x5",
+NAMES = ["multiplier2", "all_ops", "all_ops_bls", "less_than8", "poseidon2", "int_div32", "int_div_arr32", "ecdsa_scale_2x5",
+         "ecdsa_calls_2x5",
          "sha256compression", "sha256_64_bls",   # the two SHA calculators take ~11 min of g++ each
          "ecdsa_scale_8x132"]                    # the bench circuit (1.2 M constraints): one case, 38 MB -> 1 MB
 
@@ -47,7 +48,7 @@ def gen_inputs(name: str, d, rng: random.Random):
         return [{"in": [str(a), str(b)]} for a, b in [(0, 0), (255, 0), (0, 255), (17, 17), (200, 201), (201, 200)]]
     if name == "poseidon2":
         return [{"inputs": ["1", "2"]}] + [{"inputs": [str(rng.randrange(q)), str(rng.randrange(q))]} for _ in range(2)]
-    if name == "int_div32":
+    if name in ("int_div32", "int_div_arr32"):
         return [{"a": str(a), "b": str(b)} for a, b in
                 [(0, 1), (2**32 - 1, 1), (2**32 - 1, 2**32 - 1), (12345678, 1000), (rng.randrange(2**32), rng.randrange(1, 2**16))]]
     if name == "sha256compression":   # config C2: hin = SHA-256 IV, inp = one padded block (known answer: hashlib)
@@ -63,7 +64,7 @@ def gen_inputs(name: str, d, rng: random.Random):
     if name == "ecdsa_scale_8x132":
         n = d.main.n_in // 2
         return [{"a": [str(rng.getrandbits(64)) for _ in range(n)], "b": [str(rng.getrandbits(64)) for _ in range(n)]}]
-    if name.startswith("ecdsa_scale"):
+    if name.startswith("ecdsa_scale") or name.startswith("ecdsa_calls"):
         n = d.main.n_in // 2
         return [{"a": [str(rng.getrandbits(64)) for _ in range(n)], "b": [str(rng.getrandbits(64)) for _ in range(n)]}
                 for _ in range(2)] + [{"a": [str(2**64 - 1)] * n, "b": [str(2**64 - 1)] * n}]
@@ -71,8 +72,9 @@ def gen_inputs(name: str, d, rng: random.Random):
 
 
 def main():
-    build_calcs.build(NAMES)
-    for name in NAMES:
+    names = sys.argv[1:] or NAMES          # `make_golden.py <name>...`: only these fixtures
+    build_calcs.build(names)
+    for name in names:
         calc = build_calcs.calc_path(name)
         assert os.path.exists(calc) and os.path.exists(calc + ".dat"), "reference calculator %s not built" % name
         d = build_calcs.make_desc(name)

@@ -128,7 +128,14 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
                     std::vector<u32> regs((size_t)fi.n_regs * 8, 0);
                     for (uint32_t k = 0; k < ct[1]; ++k) operand(ct[2 + k], &regs[(size_t)k * 8]);
                     int e = 0;
-                    vm_run(t.fn_code.data(), fi, regs.data(), (const u32 *)t.consts.data(), r, P, e);
+                    u32 ret_base, ret_cnt;
+                    vm_run(t.fn_code.data(), fi, regs.data(), (const u32 *)t.consts.data(), r, P, e, ret_base, ret_cnt);
+                    const uint32_t *ex = ct + 2 + ct[1];
+                    for (uint32_t k = 0; k < ex[0]; ++k) {   // results 1.. of `var q[k] = f(..)`
+                        if (ex[1 + k] == 0xFFFFFFFFu) continue;
+                        if (k + 1 >= ret_cnt) { e = 2; continue; }
+                        put_slot(ex[1 + k], &regs[(size_t)8 * (ret_base + k + 1)]);
+                    }
                     if (e) err = 1;
                     put(dst, r);
                     continue;
@@ -305,13 +312,21 @@ int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
                 bitrun[dst] = run;
                 continue;
             }
-            for (uint32_t j = 0; j < run; ++j) {
-                const uint32_t s = dst + j;
+            auto write_one = [&](uint32_t s) -> int {
                 if (s >= t.n_slots) { g_err = "destination out of range"; return -6; }
                 if (read_stamp[s] == L) { g_err = "a level writes a slot that the same level reads"; return -14; }
                 if (write_stamp[s] == L) { g_err = "a level writes a slot twice"; return -15; }
                 write_stamp[s] = L;
                 if (++writes[s] > 1 && s < n_res) { g_err = "slot written twice"; return -7; }
+                return 0;
+            };
+            int rc;
+            for (uint32_t j = 0; j < run; ++j)
+                if ((rc = write_one(dst + j))) return rc;
+            if (opc == OP_CALL) {  // the further results of the call
+                const uint32_t *ex = &t.call_tab[opw[1]] + 2 + t.call_tab[opw[1] + 1];
+                for (uint32_t k = 0; k < ex[0]; ++k)
+                    if (ex[1 + k] != 0xFFFFFFFFu && (rc = write_one(ex[1 + k]))) return rc;
             }
         }
         for (uint32_t i = t.items[t.level_start[l]]; i < t.items[t.level_start[l + 1]]; ++i) {  // ... become visible after the barrier
@@ -321,6 +336,11 @@ int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
             const uint32_t run = opc == OP_BITS ? (opw[3] >> 24) + 1u : 1u;
             if (t.n_bitwords && run > 1) { bitlvl[dst] = L; continue; }
             for (uint32_t j = 0; j < run; ++j) def[dst + j] = L;
+            if (opc == OP_CALL) {
+                const uint32_t *ex = &t.call_tab[opw[1]] + 2 + t.call_tab[opw[1] + 1];
+                for (uint32_t k = 0; k < ex[0]; ++k)
+                    if (ex[1 + k] != 0xFFFFFFFFu) def[ex[1 + k]] = L;
+            }
         }
     }
     {   // every witness entry is produced exactly once, in a resident place, and no two entries share a place
@@ -379,6 +399,14 @@ int hs_fr_op(int prime, int op, const uint64_t *A, const uint64_t *B, const uint
         memcpy(R + 4 * i, r, 32);
     }
     return any_err;
+}
+
+// the integer test of small R1CS rows (fr_device.cuh: small_row_holds); v = n x {pa, na, pb, nb, pc_lo, pc_hi, nc_lo, nc_hi}
+void hs_small_rows(const uint64_t *v, uint8_t *ok, size_t n) {
+    for (size_t i = 0; i < n; ++i) {
+        const uint64_t *r = v + 8 * i;
+        ok[i] = small_row_holds(r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]) ? 1 : 0;
+    }
 }
 
 // R1CS check with the kernel's arithmetic (Montgomery coefficient dictionary)

@@ -26,6 +26,14 @@ CIRCUITS = {
     "int_div32": (lambda d: C.int_div(d, 32),
                   lambda r, q: {"a": r.choice([0, 1, 2**32 - 1, r.randrange(2**32)]),
                                 "b": r.choice([1, 2**32 - 1, r.randrange(1, 2**r.randrange(1, 33))])}),
+    # one call, several results (`var qr[3] = f(a, b);`): all used / first result dead / only the first used
+    "int_div_arr_all": (lambda d: C.int_div_array(d, 32, "all"),
+                        lambda r, q: {"a": r.choice([0, 1, 2**32 - 1, r.randrange(2**32)]),
+                                      "b": r.choice([1, 2**32 - 1, r.randrange(1, 2**r.randrange(1, 33))])}),
+    "int_div_arr_tail": (lambda d: C.int_div_array(d, 32, "tail"),
+                         lambda r, q: {"a": r.randrange(2**32), "b": r.choice([0, 1, r.randrange(1, 2**32)])}),
+    "int_div_arr_head": (lambda d: C.int_div_array(d, 32, "head"),
+                         lambda r, q: {"a": r.randrange(2**32), "b": r.choice([0, 1, r.randrange(1, 2**32)])}),
     # the bench circuit's BigMultModP with its quotient / remainder hints computed by a long_div-style function
     "ecdsa_calls_1x2": (lambda d: C.ecdsa_scale(d, 1, 2, hints="functions"),
                         lambda r, q: {"a": [r.choice([2**64 - 1, r.getrandbits(64)]) for _ in range(4)],
@@ -167,3 +175,50 @@ def test_r1cs_check_arithmetic_and_violation_detection():
     assert hs.hs_r1cs_check(blob, ctypes.c_size_t(len(blob)), bad.ctypes.data_as(ctypes.c_void_p), len(ins),
                             fb.ctypes.data_as(ctypes.c_void_p)) == 0
     assert fb[2] >= 0 and (np.delete(fb, 2) == -1).all()
+
+
+def test_small_row_integer_check():
+    """fr_device.cuh small_row_holds: a*b == c decided over the integers for a = pa - na, b = pb - nb (64-bit sums) and
+    c = pc - nc (128-bit sums) - the fast path of the R1CS kernel for rows of small terms - against python ints"""
+    hs = hostsim()
+    rng = random.Random(11)
+    M64, M128 = 2**64 - 1, 2**128 - 1
+    rows, exp = [], []
+
+    def add(pa, na, pb, nb, pc, nc):
+        rows.append([pa, na, pb, nb, pc & M64, pc >> 64, nc & M64, nc >> 64])
+        exp.append(1 if (pa - na) * (pb - nb) == pc - nc else 0)
+
+    def small(bits):
+        return rng.choice([0, 1, 2, M64, rng.getrandbits(rng.randrange(1, bits + 1))])
+
+    for _ in range(20000):
+        pa, na, pb, nb = small(64), small(64), small(64), small(64)
+        prod = (pa - na) * (pb - nb)
+        nc = rng.choice([0, 0, rng.getrandbits(rng.randrange(1, 128))])
+        mode = rng.randrange(5)
+        if mode < 3:                         # a satisfied row (when its parts fit 128 bits)
+            pc = prod + nc
+            if pc < 0:
+                pc, nc = 0, -prod
+                if rng.random() < 0.5 and nc + 5 <= M128:
+                    pc, nc = 5, nc + 5
+            if pc > M128 or nc > M128:
+                continue
+            add(pa, na, pb, nb, pc, nc)
+        elif mode == 3:                      # off by a little / by a multiple of 2^64 or 2^128 (wrap-arounds)
+            pc = (prod + nc + rng.choice([1, -1, 2**64, -2**64, 2**128, -2**128])) % (2**128)
+            add(pa, na, pb, nb, pc, nc)
+        else:
+            add(pa, na, pb, nb, rng.getrandbits(128), nc)
+    # edges: the sum |ab| + x leaves 128 bits
+    add(M64, 0, M64, 0, (M64 * M64 + 5) & M128, 5)
+    add(M64, 0, M64, 0, 0, M128)
+    add(0, M64, M64, 0, M128, (M64 * M64 + M128) & M128)
+    add(0, M64, 0, M64, M64 * M64, 0)
+    add(0, 0, M64, 3, 0, 0)
+    v = np.array(rows, dtype=np.uint64)
+    ok = np.zeros(len(rows), dtype=np.uint8)
+    hs.hs_small_rows(v.ctypes.data_as(ctypes.c_void_p), ok.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(rows)))
+    assert ok.tolist() == exp
+    assert 0.2 < sum(exp) / len(exp) < 0.8

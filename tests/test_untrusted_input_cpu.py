@@ -50,6 +50,7 @@ def mutate(rng, src: bytes) -> bytes:
 def descriptions():
     out = []
     for mk in (lambda d: C.multiplier2(d), lambda d: C.less_than(d, 8), lambda d: C.int_div(d, 32),
+               lambda d: C.int_div_array(d, 16, "all"),
                lambda d: C.num2bits(d, 16), lambda d: C.is_zero(d), lambda d: C.all_ops(d)):
         d = CircuitDesc("bn128")
         d.set_main(mk(d))
@@ -192,6 +193,47 @@ def test_hostile_input_name_table_and_function_bodies():
     assert rejected > 5 * n_instr
     # truncated in the middle of the code
     assert try_load(good[:code + 40 * (n_instr // 2) + 3]) == native.CW_EFORMAT
+
+
+def test_hostile_array_calls():
+    """`var r[n] = f(..)`: the result count of a CALL and the (base, count) of an array RET come from the file; the callee's
+    registers are copied to the caller's slots by index, so every count is checked against the function and the template"""
+    from circom_b200.circuit import OPS, K_NONE, K_TMP
+
+    def variant(edit):
+        d = CircuitDesc("bn128")
+        d.set_main(C.int_div_array(d, 16, "all"))
+        edit(d)
+        return try_load(d.to_bytes())
+
+    def ret_edit(b_ref=None, a_ref=None):
+        def edit(d):
+            f = d.functions[0]
+            k = max(i for i, c in enumerate(f.code) if c[0] == OPS["RET"])
+            op, dd, a, b, c = f.code[k]
+            f.code[k] = (op, dd, a_ref or a, b_ref or b, c)
+        return edit
+
+    def call_edit(n):
+        def edit(d):
+            t = d.main
+            k = next(i for i, o in enumerate(t.ops) if o[0] == OPS["CALL"])
+            op, dd, a, b, c = t.ops[k]
+            t.ops[k] = (op, dd, a, b, (K_NONE, 0, n))
+        return edit
+
+    assert variant(lambda d: None) == 0
+    assert variant(ret_edit(b_ref=(K_NONE, 0, 2))) == native.CW_EFORMAT    # the second call wants 3, one RET now returns 2
+    assert variant(ret_edit(b_ref=(K_NONE, 0, 65))) == native.CW_EFORMAT   # more than 64 results
+    def past_end(d):
+        ret_edit(a_ref=(K_TMP, 0, d.functions[0].n_regs - 2))(d)
+    assert variant(past_end) == native.CW_EFORMAT                          # three registers from n_regs - 2
+    assert variant(ret_edit(a_ref=(K_TMP, 0, 191))) == native.CW_EFORMAT   # base register out of range
+    assert variant(ret_edit(b_ref=(K_NONE, 0, 1))) == native.CW_EFORMAT    # a scalar return under a call that wants 2 / 3
+    assert variant(call_edit(3)) == 0                                     # (first call asks for 2 of the 3)
+    assert variant(call_edit(4)) == native.CW_EFORMAT                      # more than the function returns
+    assert variant(call_edit(65)) == native.CW_EFORMAT
+    assert variant(call_edit(0x3FFFFFFF)) == native.CW_EFORMAT
 
 
 def test_set_input_outside_main_inputs_is_refused():

@@ -75,8 +75,8 @@ def make_workload(args):
     elif args.workload == "ecdsa_scale_calls":
         d.set_main(C.ecdsa_scale(d, args.lanes, args.chain, hints="functions"),
                    "ecdsa_scale_calls_%dx%d" % (args.lanes, args.chain))
-        label = ("ecdsa-scale synthetic with function-computed hints (one long_div-style call per quotient / remainder "
-                 "limb: 9 calls per BigMultModP), %dx%d, BN254" % (args.lanes, args.chain))
+        label = ("ecdsa-scale synthetic with function-computed hints (one long_div-style call per BigMultModP returns "
+                 "quotient and remainder as `var out[9]`), %dx%d, BN254" % (args.lanes, args.chain))
         batch = args.batch_per_gpu or 18944
     elif args.workload == "sha256compression":
         d.set_main(C.sha256_compression(d), "sha256compression")

@@ -27,11 +27,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = os.environ.get("CW_NVCC_EXTRA", "").split()
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
+    tmp = LIB + ".building"     # (a reader - another process, a snapshot of the tree - never sees a half-written library)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
+        if os.path.exists(tmp):
+            os.unlink(tmp)
         raise RuntimeError("nvcc failed:\n" + r.stdout[-3000:] + r.stderr[-6000:])
+    os.replace(tmp, LIB)
     if verbose:
         print(r.stderr)
     # command-line calculator (client of the C ABI only)

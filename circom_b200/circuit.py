@@ -463,6 +463,7 @@ class Function:
         self.desc, self.name, self.n_params = desc, name, n_params
         self.n_regs = n_params
         self.n_results = 1
+        self._arrays: List[Tuple[int, int]] = []          # (first register, length) of every `var` / parameter array
         self.code: List[Tuple[int, Ref, Ref, Ref, Ref]] = []
         self._loops: List[Tuple[int, List[int]]] = []
         self._ifs: List[List[int]] = []
@@ -483,9 +484,24 @@ class Function:
         """n consecutive registers; returns the index of the first (for load/store with a run-time index)"""
         base = self.n_regs
         self.n_regs += n
+        self._arrays.append((base, n))
         for k in range(n):
             self.set(FReg(self, base + k), init)
         return base
+
+    def param_array(self, first: int, n: int) -> int:
+        """parameters first .. first+n-1 as one array (`function f(x[n])`: array parameters are consecutive variables and
+        are indexed in place); returns the base for load / store"""
+        assert 0 <= first and first + n <= self.n_params
+        self._arrays.append((first, n))
+        return first
+
+    def _extent(self, base: int) -> int:
+        """registers from `base` to the end of the array that contains it (0: not inside a declared array)"""
+        for start, n in self._arrays:
+            if start <= base < start + n:
+                return start + n - base
+        return 0
 
     def _operand(self, o) -> Ref:
         if isinstance(o, FReg):
@@ -506,11 +522,13 @@ class Function:
     def load(self, base: int, idx: FReg) -> FReg:
         r = FReg(self, self.n_regs)
         self.n_regs += 1
-        self.code.append((OPS["LOADX"], (K_TMP, 0, r.idx), (K_NONE, 0, base), (K_TMP, 0, idx.idx), NONE_REF))
+        # operand c = (NONE, extent): the index must stay below it (0 = unknown: up to the last register)
+        self.code.append((OPS["LOADX"], (K_TMP, 0, r.idx), (K_NONE, 0, base), (K_TMP, 0, idx.idx), (K_NONE, 0, self._extent(base))))
         return r
 
     def store(self, base: int, idx: FReg, src) -> None:
-        self.code.append((OPS["STOREX"], NONE_REF, (K_NONE, 0, base), (K_TMP, 0, idx.idx), self._operand(src)))
+        self.code.append((OPS["STOREX"], (K_NONE, 0, self._extent(base)), (K_NONE, 0, base), (K_TMP, 0, idx.idx),
+                          self._operand(src)))
 
     def loop_begin(self) -> None:
         self._loops.append((len(self.code), []))
@@ -673,7 +691,17 @@ class CircuitDesc:
         return path
 
     # -- serialisation -------------------------------------------------------------------
-    def to_bytes(self) -> bytes:
+    def symbol_names(self, t: "Template") -> Tuple[List[str], List[str]]:
+        """(names of the own signals in numbering order, array elements spelled out; names of the sub-components):
+        the content of the symbols section, what `--sym` prints per component (dag/src/sym_porting.rs:16-33)"""
+        own = []
+        for cat in ("out", "in", "inter"):
+            for name, n in t.sigs[cat]:
+                own += ["%s[%d]" % (name, j) for j in range(n)] if t.sig_is_array[name] else [name]
+        return own, [s.name for s in t.subs]
+
+    def to_bytes(self, symbols: bool = False) -> bytes:
+        """the `.cb2c` file (docs/CB2C.md); symbols=True appends the optional symbols section (`cw_circuit_write_sym`)"""
         import numpy as np
         assert self.main is not None
         # constraint coefficients go through the constant table as well
@@ -714,7 +742,16 @@ class CircuitDesc:
         head = b"CB2C" + struct.pack("<7I", 1, PRIME_IDS[self.prime], len(self.consts), len(self.templates),
                                      self.main.id, len(ins), len(self.functions))
         consts = b"".join(int(c).to_bytes(32, "little") for c in self.consts)
-        return head + consts + b"".join(blobs) + names + funcs
+        syms = b""
+        if symbols:
+            def pstr(x: str) -> bytes:
+                nb = x.encode()
+                return struct.pack("<I", len(nb)) + nb + b"\0" * ((-len(nb)) % 4)
+            syms = b"SYMS"
+            for t in self.templates:
+                own, subs = self.symbol_names(t)
+                syms += b"".join(pstr(x) for x in own) + b"".join(pstr(x) for x in subs)
+        return head + consts + b"".join(blobs) + names + funcs + syms
 
     def save(self, path: str) -> str:
         with open(path, "wb") as f:

@@ -40,9 +40,7 @@ def fn_modp_limb(d: CircuitDesc):
     p_l = _limbs(SECP256K1_P)
 
     def build(f: Function):
-        X = f.array(2 * KL)
-        for i in range(2 * KL):
-            f.store(X, f.var(i), f.param(i))
+        X = f.param_array(0, 2 * KL)     # `function long_div_p(X[8])`: the parameter array is indexed in place
         Q = f.array(2 * KL + 1)          # out[0..4] = quotient, out[5..8] = remainder: one contiguous `var out[9]`
         R = Q + KL + 1
         Pp = f.array(KL)

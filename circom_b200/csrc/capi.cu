@@ -433,6 +433,24 @@ int cw_circuit_write_dat(const cw_circuit *c, const char *path) {
     return CW_OK;
 }
 
+int cw_circuit_functions(const cw_circuit *c, uint32_t *n, uint32_t *info) {
+    if (!c || !n) return fail(CW_EINVAL, "null argument");
+    *n = (uint32_t)(c->tape.fn_info.size() / 4);
+    if (info) memcpy(info, c->tape.fn_info.data(), c->tape.fn_info.size() * 4);
+    return CW_OK;
+}
+
+int cw_circuit_write_sym(const cw_circuit *c, const char *path) {
+    if (!c || !path) return fail(CW_EINVAL, "null argument");
+    if (c->tape.sym.empty()) return fail(CW_ESTATE, "the circuit description carries no symbols section");
+    try {
+        write_sym(c->tape, path);
+    } catch (const std::exception &e) {
+        return fail(CW_EIO, e.what());
+    }
+    return CW_OK;
+}
+
 // ---- batch ------------------------------------------------------------------------------------
 int cw_batch_create(const cw_circuit *c, uint32_t batch, int device, cw_batch **out) {
     if (!c || !out || batch == 0) return fail(CW_EINVAL, "bad argument");
@@ -612,6 +630,7 @@ int cw_batch_run(cw_batch *b) {
     tp.n_inputs = (u32)t.n_inputs;
     tp.n_bitwords = t.n_bitwords;
     tp.prime = (u32)t.F.prime_id;
+    tp.vm_wide = env_int("CW_VM_WIDE", 0) ? 1u : 0u;
     CU(cudaMemsetAsync(b->first_assert_d, 0xFF, (size_t)b->batch * 4, b->stream));
     CU(cudaMemsetAsync(b->err_d, 0, (size_t)b->batch * 4, b->stream));
     CU(cudaEventRecord(b->ev[0], b->stream));

@@ -19,6 +19,7 @@
 //      (level, opcode) and slots renumbered so that the destination of tape
 //      op i is slot n_pre + i.
 #include <algorithm>
+#include <bitset>
 #include <cstdio>
 #include <cstring>
 #include <functional>
@@ -137,6 +138,136 @@ inline int subtree_need(uint32_t i, const std::vector<uint32_t> &kid_a, const st
     if (b == NO_SLOT) return subtree_need(a, kid_a, kid_b);
     const int na = subtree_need(a, kid_a, kid_b), nb = subtree_need(b, kid_a, kid_b);
     return std::max(std::max(na, nb), std::min(na, nb) + 1);
+}
+
+// ---- register allocation for function bodies ---------------------------------------------------------------------
+// A compiler-written function body gives every expression temporary its own register (the `expaux` of the C++ producer) and
+// every variable its own slot; the interpreter keeps the registers of a call in the thread's local memory (32 bytes each,
+// dynamically indexed), so the frame size is what a call costs: hundreds of concurrent calls per SM each touching a 3 KB frame
+// live in L2 / DRAM instead of L1.  Scalars are therefore packed: liveness over the control-flow graph, interference, greedy
+// colouring.  Registers that can be reached through a run-time index (LOADX / STOREX ranges [base, limit), array returns)
+// are never shared: a range that contains parameters stays where it is, the others move behind the scalars as blocks.
+// Parameters keep their registers (the caller stores the arguments there); a dead parameter's register is reused.
+// Registers read before they are written rely on the zero-initialised frame: they stay live from the entry and may not
+// share a register with a parameter.
+static void allocate_function_registers(uint32_t *code, uint32_t n_instr, uint32_t n_params, uint32_t &n_regs) {
+    constexpr uint32_t MAXR = 192;
+    if (n_regs > MAXR || n_regs == 0 || n_instr == 0) return;
+    using Set = std::bitset<MAXR>;
+    auto is_reg = [](uint32_t o) { return !(o & 0xC0000000u); };
+    enum { JMP = 40, JZ = 41, RET = 42, LOADX = 43, STOREX = 44 };
+    // registers reachable through a run-time index
+    Set pinned;
+    for (uint32_t i = 0; i < n_instr; ++i) {
+        const uint32_t *w = &code[5 * (size_t)i];
+        uint32_t lo = 0, hi = 0;
+        if (w[0] == LOADX) { lo = w[2] & 0x3FFFFFFFu; hi = w[4] & 0x3FFFFFFFu; }
+        else if (w[0] == STOREX) { lo = w[2] & 0x3FFFFFFFu; hi = w[1] & 0x3FFFFFFFu; }
+        else if (w[0] == RET && (w[3] & 0x3FFFFFFFu) > 1) { lo = w[2]; hi = lo + (w[3] & 0x3FFFFFFFu); }
+        for (uint32_t r = lo; r < hi && r < n_regs; ++r) pinned.set(r);
+    }
+    // per instruction: registers read / the register written, scalars only
+    std::vector<Set> use(n_instr), live_in(n_instr), live_out(n_instr);
+    std::vector<int> def(n_instr, -1);
+    auto add_use = [&](uint32_t i, uint32_t o) { if (is_reg(o) && o < n_regs && !pinned.test(o)) use[i].set(o); };
+    for (uint32_t i = 0; i < n_instr; ++i) {
+        const uint32_t *w = &code[5 * (size_t)i];
+        switch (w[0]) {
+            case JMP: break;
+            case JZ: add_use(i, w[2]); break;
+            case RET: if ((w[3] & 0x3FFFFFFFu) <= 1) add_use(i, w[2]); break;
+            case LOADX: add_use(i, w[3]); if (!pinned.test(w[1])) def[i] = (int)w[1]; break;
+            case STOREX: add_use(i, w[3]); add_use(i, w[4]); break;
+            default: add_use(i, w[2]); add_use(i, w[3]); add_use(i, w[4]); if (!pinned.test(w[1])) def[i] = (int)w[1];
+        }
+    }
+    for (bool changed = true; changed;) {
+        changed = false;
+        for (uint32_t i = n_instr; i-- > 0;) {
+            const uint32_t *w = &code[5 * (size_t)i];
+            Set out;
+            if (w[0] == JMP) { out = live_in[w[2] & 0x3FFFFFFFu]; }
+            else if (w[0] == RET) {}
+            else {
+                if (i + 1 < n_instr) out = live_in[i + 1];
+                if (w[0] == JZ) out |= live_in[w[3] & 0x3FFFFFFFu];
+            }
+            Set in = out;
+            if (def[i] >= 0) in.reset((size_t)def[i]);
+            in |= use[i];
+            if (in != live_in[i] || out != live_out[i]) { live_in[i] = in; live_out[i] = out; changed = true; }
+        }
+    }
+    // interference
+    std::vector<Set> edge(n_regs);
+    auto connect = [&](uint32_t a, uint32_t b) { if (a != b) { edge[a].set(b); edge[b].set(a); } };
+    for (uint32_t i = 0; i < n_instr; ++i)
+        if (def[i] >= 0)
+            for (uint32_t r = 0; r < n_regs; ++r)
+                if (live_out[i].test(r)) connect((uint32_t)def[i], r);
+    for (uint32_t p = 0; p < n_params; ++p)   // the arguments are all written before the first instruction
+        for (uint32_t r = 0; r < n_regs; ++r)
+            if (!pinned.test(p) && !pinned.test(r) && (r < n_params || live_in[0].test(r))) connect(p, r);
+    // which scalars exist at all (a register no instruction names needs no place)
+    Set named;
+    for (uint32_t i = 0; i < n_instr; ++i) { named |= use[i]; if (def[i] >= 0) named.set((size_t)def[i]); }
+    // pinned ranges (maximal runs); a run that reaches into the parameters stays in place
+    struct Run { uint32_t lo, hi; bool fixed; };
+    std::vector<Run> runs;
+    for (uint32_t r = 0; r < n_regs;) {
+        if (!pinned.test(r)) { ++r; continue; }
+        uint32_t e = r;
+        while (e < n_regs && pinned.test(e)) ++e;
+        runs.push_back({r, e, r < n_params});
+        r = e;
+    }
+    std::vector<uint32_t> map(n_regs, 0xFFFFFFFFu);
+    Set taken;   // places no scalar may use
+    for (const Run &ru : runs)
+        if (ru.fixed)
+            for (uint32_t r = ru.lo; r < ru.hi; ++r) { map[r] = r; taken.set(r); }
+    for (uint32_t p = 0; p < n_params; ++p)
+        if (map[p] == 0xFFFFFFFFu) map[p] = p;
+    uint32_t top = n_params;
+    for (const Run &ru : runs)
+        if (ru.fixed) top = std::max(top, ru.hi);
+    for (uint32_t r = n_params; r < n_regs; ++r) {
+        if (pinned.test(r) || !named.test(r)) continue;
+        Set busy = taken;
+        for (uint32_t o = 0; o < n_regs; ++o)
+            if (edge[r].test(o) && map[o] != 0xFFFFFFFFu && !pinned.test(o)) busy.set(map[o]);
+        uint32_t c = 0;
+        while (c < MAXR && busy.test(c)) ++c;
+        if (c >= MAXR) return;   // (cannot happen: the identity is a valid colouring)
+        map[r] = c;
+        top = std::max(top, c + 1);
+    }
+    for (const Run &ru : runs) {
+        if (ru.fixed) continue;
+        for (uint32_t r = ru.lo; r < ru.hi; ++r) map[r] = top + (r - ru.lo);
+        top += ru.hi - ru.lo;
+    }
+    if (top > n_regs) return;    // (no gain; keep the original numbering)
+    auto m = [&](uint32_t o) { return is_reg(o) && o < n_regs && map[o] != 0xFFFFFFFFu ? map[o] : o; };
+    for (uint32_t i = 0; i < n_instr; ++i) {
+        uint32_t *w = &code[5 * (size_t)i];
+        switch (w[0]) {
+            case JMP: break;
+            case JZ: w[2] = m(w[2]); break;
+            case RET: w[2] = m(w[2]); break;   // (an array return names its first register: pinned, mapped like the others)
+            case LOADX: case STOREX: {
+                const uint32_t base = w[2] & 0x3FFFFFFFu, lim = (w[0] == LOADX ? w[4] : w[1]) & 0x3FFFFFFFu;
+                // base == limit (an empty range) names no register: any in-frame value will do
+                const uint32_t nb = base < lim && base < n_regs ? map[base] : 0, nl = nb + (lim > base ? lim - base : 0);
+                w[2] = 0x40000000u | nb;
+                if (w[0] == LOADX) { w[1] = m(w[1]); w[3] = m(w[3]); w[4] = 0x40000000u | nl; }
+                else { w[3] = m(w[3]); w[4] = m(w[4]); w[1] = 0x40000000u | nl; }
+                break;
+            }
+            default: w[1] = m(w[1]); w[2] = m(w[2]); w[3] = m(w[3]); w[4] = m(w[4]);
+        }
+    }
+    n_regs = std::max<uint32_t>(top, 1);
 }
 
 struct Lowerer {
@@ -956,12 +1087,23 @@ struct Lowerer {
                         min_ret = std::min(min_ret, cnt);
                         break;
                     }
-                    case 43 /* LOADX: d = regs[base + b] */:
+                    // run-time indexed `var` arrays.  The producer may state the extent of the array behind the base (LOADX:
+                    // operand c, STOREX: operand d; 0 / NONE = unknown, then up to the last register); the encoded word is the
+                    // exclusive upper limit of the register index, checked by the interpreter at run time.
+                    case 43 /* LOADX: d = regs[base + b] */: {
                         e[0] = reg(w[1]); e[1] = imm(w[2], n_regs); e[2] = val(w[3], false);
+                        const uint32_t base = ridx(w[2]), ext = rk(w[4]) == K_NONE ? ridx(w[4]) : 0;
+                        if (rk(w[4]) != K_NONE || (uint64_t)base + ext > n_regs) bad("bad array extent");
+                        e[3] = 0x40000000u | (ext ? base + ext : n_regs);
                         break;
-                    case 44 /* STOREX: regs[base + b] = c */:
+                    }
+                    case 44 /* STOREX: regs[base + b] = c */: {
                         e[1] = imm(w[2], n_regs); e[2] = val(w[3], false); e[3] = val(w[4], false);
+                        const uint32_t base = ridx(w[2]), ext = rk(w[1]) == K_NONE ? ridx(w[1]) : 0;
+                        if (rk(w[1]) != K_NONE || (uint64_t)base + ext > n_regs) bad("bad array extent");
+                        e[0] = 0x40000000u | (ext ? base + ext : n_regs);
                         break;
+                    }
                     default:
                         if (op < CW_OP_MUL || op > CW_OP_INV || op == CW_OP_ASSERT || op == CW_OP_ASSERT_EQ) bad("unknown opcode");
                         e[0] = reg(w[1]);
@@ -973,6 +1115,37 @@ struct Lowerer {
                 for (uint32_t x : e) T.fn_code.push_back(x);
             }
             fn_min_ret.push_back(min_ret == 0xFFFFFFFFu ? 1 : min_ret);
+            if (!(flags & CW_FLAG_NO_PEEPHOLE)) {
+                uint32_t packed = n_regs;
+                allocate_function_registers(&T.fn_code[5 * (size_t)T.fn_info[4 * (size_t)i]], n_instr, n_params, packed);
+                T.fn_info[4 * (size_t)i + 2] = packed;
+            }
+        }
+        // optional symbols section: "SYMS", then per template the names of its own signals and of its sub-components
+        // (what the reference keeps in the DAG for sym_porting.rs).  Anything else after the functions is refused.
+        if (r.left()) {
+            if (r.left() < 4 || memcmp(r.bytes(4), "SYMS", 4)) throw std::runtime_error("cb2c: unknown section after the functions");
+            T.sym.resize(n_tm);
+            auto name = [&]() {
+                std::string s = r.str();
+                if (s.empty() || s.size() > 4096) throw std::runtime_error("cb2c: bad symbol name");
+                for (unsigned char ch : s)
+                    if (ch < 0x21 || ch == ',' || ch == 0x7F) throw std::runtime_error("cb2c: bad character in a symbol name");
+                return s;
+            };
+            for (uint32_t i = 0; i < n_tm; ++i) {
+                Tape::SymTemplate &st = T.sym[i];
+                st.n_own = tm[i].n_own;
+                st.total_signals = tm[i].total_signals;
+                st.subs = tm[i].subs;
+                r.expect((uint64_t)st.n_own + st.subs.size(), 4);
+                st.own.resize(st.n_own);
+                for (auto &n : st.own) n = name();
+                st.sub.resize(st.subs.size());
+                for (auto &n : st.sub) n = name();
+            }
+            if (r.left()) throw std::runtime_error("cb2c: bytes after the symbols section");
+            T.sym_main = main_tid;
         }
     }
     uint32_t main_tid = 0;

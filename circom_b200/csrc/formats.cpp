@@ -331,4 +331,68 @@ void write_dat(const Tape &t, const std::string &path) {
     // indexing are outside what the lowering accepts)
 }
 
+// .sym: one line per signal, `signal id,witness index (-1: eliminated),node id,qualified name`, a component's own signals
+// first, then its sub-components in creation order (visit_tree, dag/src/sym_porting.rs:16-33; the witness column as
+// constraint_list/src/sym_porting.rs:24-31).  The node id is the DAG node of the component's template instance: the
+// reference numbers nodes when their first instance finishes executing, children before parents - the post-order of
+// first visits from main (the template order of a compiler-written description already is that order).  Signal 0, the
+// constant one, has no line.
+void write_sym(const Tape &t, const std::string &path) {
+    if (t.sym.empty()) throw std::runtime_error("the circuit description carries no symbols section");
+    std::vector<int64_t> wit(t.n_signals, -1);
+    for (uint64_t i = 0; i < t.n_witness; ++i)
+        if (t.witness2signal[i] < t.n_signals) wit[t.witness2signal[i]] = (int64_t)i;
+    std::vector<int64_t> node(t.sym.size(), -1);
+    {
+        int64_t next = 0;
+        std::vector<std::pair<uint32_t, size_t>> st;   // (template, next child)
+        st.push_back({t.sym_main, 0});
+        std::vector<uint8_t> open(t.sym.size(), 0);
+        open[t.sym_main] = 1;
+        while (!st.empty()) {
+            auto &top = st.back();
+            const Tape::SymTemplate &tt = t.sym[top.first];
+            if (top.second < tt.subs.size()) {
+                const uint32_t ch = tt.subs[top.second++];
+                if (node[ch] < 0 && !open[ch]) { open[ch] = 1; st.push_back({ch, 0}); }
+            } else {
+                node[top.first] = next++;
+                st.pop_back();
+            }
+        }
+    }
+    File f(path, "wb");
+    std::string buf;
+    buf.reserve(1u << 20);
+    struct Frame { uint32_t tid; uint64_t start; std::string path; };
+    std::vector<Frame> stack;
+    stack.push_back({t.sym_main, 1, "main"});
+    while (!stack.empty()) {
+        Frame fr = std::move(stack.back());
+        stack.pop_back();
+        const Tape::SymTemplate &st = t.sym[fr.tid];
+        if (fr.start + st.total_signals > t.n_signals) throw std::runtime_error("symbols do not match the circuit");
+        for (uint32_t i = 0; i < st.n_own; ++i) {
+            const uint64_t sig = fr.start + i;
+            buf += std::to_string(sig);
+            buf += ',';
+            buf += std::to_string(wit[sig]);
+            buf += ',';
+            buf += std::to_string(node[fr.tid]);
+            buf += ',';
+            buf += fr.path;
+            buf += '.';
+            buf += st.own[i];
+            buf += '\n';
+            if (buf.size() > (1u << 20) - 8192) { f.w(buf.data(), buf.size()); buf.clear(); }
+        }
+        // children are visited in creation order: push them in reverse
+        std::vector<uint64_t> starts(st.subs.size());
+        uint64_t off = fr.start + st.n_own;
+        for (size_t k = 0; k < st.subs.size(); ++k) { starts[k] = off; off += t.sym[st.subs[k]].total_signals; }
+        for (size_t k = st.subs.size(); k-- > 0;) stack.push_back({st.subs[k], starts[k], fr.path + "." + st.sub[k]});
+    }
+    f.w(buf.data(), buf.size());
+}
+
 }  // namespace cw

@@ -652,10 +652,11 @@ CW_HD void vm_operand(u32 *v, u32 o, const u32 *regs, const u32 *consts32) {
         for (int k = 0; k < 8; ++k) v[k] = p[k];
     }
 }
-// index operand -> int through the signed view (Fr_toInt, generic/fr.cpp:1146); -1 if out of range
-CW_HD int vm_index(const u32 *v, u32 base, u32 n_regs) {
+// index operand -> int through the signed view (Fr_toInt, generic/fr.cpp:1146); -1 if out of range.  `limit`: the end of
+// the array behind `base` (the lowering checked limit <= n_regs; without a declared extent it is n_regs)
+CW_HD int vm_index(const u32 *v, u32 base, u32 limit) {
     u32 hi = v[1] | v[2] | v[3] | v[4] | v[5] | v[6] | v[7];
-    if (hi || (u64)v[0] + base >= n_regs) return -1;
+    if (hi || (u64)v[0] + base >= limit) return -1;
     return (int)(v[0] + base);
 }
 // regs: n_regs * 8 words, parameters already stored in registers 0..n_params-1.  err: 1 division by zero,
@@ -688,14 +689,14 @@ inline void vm_run(const u32 *code, FnInfo fi, u32 *regs, const u32 *consts32, u
         }
         vm_operand(vb, b, regs, consts32);
         if (op == FOP_LOADX) {
-            int i = vm_index(vb, a & 0x3FFFFFFFu, fi.n_regs);
+            int i = vm_index(vb, a & 0x3FFFFFFFu, c & 0x3FFFFFFFu);
             if (i < 0) { err = 2; return; }
             for (int k = 0; k < 8; ++k) regs[8 * (size_t)d + k] = regs[8 * (size_t)i + k];
             continue;
         }
         vm_operand(vc, c, regs, consts32);
         if (op == FOP_STOREX) {
-            int i = vm_index(vb, a & 0x3FFFFFFFu, fi.n_regs);
+            int i = vm_index(vb, a & 0x3FFFFFFFu, d & 0x3FFFFFFFu);
             if (i < 0) { err = 2; return; }
             for (int k = 0; k < 8; ++k) regs[8 * (size_t)i + k] = vc[k];
             continue;
@@ -708,14 +709,20 @@ inline void vm_run(const u32 *code, FnInfo fi, u32 *regs, const u32 *consts32, u
     err = 2;
 }
 
-// ---- R1CS rows of small integers ------------------------------------------------------------------------------
-// A linear combination whose terms are all "small" (32-bit witness values times +-1 / +-2^k, the lazy sums of
-// kernels.cuh: r1cs_lc) is known as two plain integers, the sum of its positive and of its negative terms.  When the
-// sums of A and B fit 64 bits and those of C 128 bits,
-//      a = pa - na,  b = pb - nb  in (-2^64, 2^64),   c = pc - nc  in (-2^128, 2^128),
-// a*b - c lies in (-2^129, 2^129); every supported prime is above 2^250, so a*b = c (mod q) holds exactly when it
-// holds over the integers: no modular reduction, no Montgomery product.
-CW_HD void mul64wide(u64 a, u64 b, u64 &lo, u64 &hi) {
+// ---- the narrow register machine -------------------------------------------------------------------------------
+// Hint functions are limb arithmetic: their values are 64-bit limbs, carries, products of two limbs, loop counters.  A
+// call frame of 32-byte registers in local memory is what a call costs (hundreds of concurrent calls per SM), so a
+// call first runs on a machine whose registers are 128-bit integers (16 bytes, half the frame and half the traffic per
+// instruction; plain integer add / multiply / compare instead of modular ones).  A value below 2^128 is its own
+// canonical form and is non-negative in the signed view of every supported prime (all above 2^250), so the integer
+// result IS the field result as long as it stays below 2^128.  Anything else - a wider argument or constant, a sum or
+// product that leaves 128 bits, a difference below zero, an operator the narrow machine does not have (field division,
+// powers, bit complement) - abandons the run: the caller repeats the call on the full-width machine (functions are pure,
+// nothing was stored).  Errors (bad index, runaway loop) are reported as on the full-width machine.
+struct N128 {
+    u64 lo, hi;
+};
+CW_HD void mul64wide_vm(u64 a, u64 b, u64 &lo, u64 &hi) {
 #if defined(__CUDA_ARCH__)
     lo = a * b;
     hi = __umul64hi(a, b);
@@ -725,21 +732,162 @@ CW_HD void mul64wide(u64 a, u64 b, u64 &lo, u64 &hi) {
     hi = (u64)(p >> 64);
 #endif
 }
-CW_HD bool small_row_holds(u64 pa, u64 na, u64 pb, u64 nb, u64 pc_lo, u64 pc_hi, u64 nc_lo, u64 nc_hi) {
-    const bool nega = pa < na, negb = pb < nb;
-    const u64 ma = nega ? na - pa : pa - na, mb = negb ? nb - pb : pb - nb;
-    u64 lo, hi;
-    mul64wide(ma, mb, lo, hi);
-    const bool neg = nega != negb;           // (a zero product has either sign)
-    // a*b = c   <=>   |ab| + nc = pc   (ab >= 0)      or      |ab| + pc = nc   (ab <= 0)
-    const u64 x_lo = neg ? pc_lo : nc_lo, x_hi = neg ? pc_hi : nc_hi;
-    const u64 y_lo = neg ? nc_lo : pc_lo, y_hi = neg ? nc_hi : pc_hi;
-    const u64 s_lo = lo + x_lo;
-    const u64 c0 = s_lo < lo ? 1u : 0u;
-    const u64 t = hi + x_hi;
-    const u64 s_hi = t + c0;
-    const bool carry = t < hi || s_hi < t;   // the sum left 128 bits: it cannot equal a 128-bit value
-    return !carry && s_lo == y_lo && s_hi == y_hi;
+CW_HD bool vmn_operand(N128 &v, u32 o, const u32 *regs, const u32 *consts32) {
+    if (o & 0x80000000u) {
+        const u32 *p = consts32 + 8 * (size_t)(o & 0x3FFFFFFFu);
+        if (p[4] | p[5] | p[6] | p[7]) return false;
+        v.lo = p[0] | ((u64)p[1] << 32);
+        v.hi = p[2] | ((u64)p[3] << 32);
+    } else if (o & 0x40000000u) {
+        v.lo = o & 0x3FFFFFFFu;
+        v.hi = 0;
+    } else {
+        const u32 *p = regs + 4 * (size_t)o;
+        v.lo = p[0] | ((u64)p[1] << 32);
+        v.hi = p[2] | ((u64)p[3] << 32);
+    }
+    return true;
+}
+CW_HD void vmn_store(u32 *regs, u32 d, const N128 &v) {
+    u32 *p = regs + 4 * (size_t)d;
+    p[0] = (u32)v.lo; p[1] = (u32)(v.lo >> 32); p[2] = (u32)v.hi; p[3] = (u32)(v.hi >> 32);
+}
+CW_HD bool n128_lt(const N128 &a, const N128 &b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
+CW_HD bool n128_eq(const N128 &a, const N128 &b) { return a.hi == b.hi && a.lo == b.lo; }
+// one value operator on 128-bit integers; false: the result (or the operator) needs the full-width machine
+CW_HD bool vmn_apply(u32 op, N128 &r, const N128 &a, const N128 &b, const N128 &c) {
+    switch (op) {
+        case OP_ADD: {
+            r.lo = a.lo + b.lo;
+            const u64 cy = r.lo < a.lo ? 1u : 0u;
+            const u64 t = a.hi + b.hi;
+            r.hi = t + cy;
+            return !(t < a.hi || r.hi < t);
+        }
+        case OP_SUB: {
+            if (n128_lt(a, b)) return false;   // negative: q - (b - a)
+            r.lo = a.lo - b.lo;
+            r.hi = a.hi - b.hi - (a.lo < b.lo ? 1u : 0u);
+            return true;
+        }
+        case OP_MUL: {
+            if (a.hi && b.hi) return false;
+            const N128 &x = a.hi ? a : b, &y = a.hi ? b : a;   // y.hi == 0
+            u64 lo, hi, clo, chi;
+            mul64wide_vm(x.lo, y.lo, lo, hi);
+            mul64wide_vm(x.hi, y.lo, clo, chi);
+            if (chi) return false;
+            r.lo = lo;
+            r.hi = hi + clo;
+            return r.hi >= hi;
+        }
+        case OP_IDIV: case OP_MOD:
+            if (a.hi | b.hi || !b.lo) return false;   // (division by zero: reported by the full-width machine)
+            r.lo = op == OP_IDIV ? a.lo / b.lo : a.lo % b.lo;
+            r.hi = 0;
+            return true;
+        case OP_SHR: {
+            if (b.hi || b.lo >= 128u) return false;
+            const u32 k = (u32)b.lo;
+            if (k == 0) r = a;
+            else if (k < 64u) { r.lo = (a.lo >> k) | (a.hi << (64u - k)); r.hi = a.hi >> k; }
+            else { r.lo = a.hi >> (k - 64u); r.hi = 0; }
+            return true;
+        }
+        case OP_SHL: {
+            if (b.hi || b.lo >= 128u) return false;
+            const u32 k = (u32)b.lo;
+            if (k == 0) { r = a; return true; }
+            if (k < 64u) {
+                if (a.hi >> (64u - k)) return false;
+                r.hi = (a.hi << k) | (a.lo >> (64u - k));
+                r.lo = a.lo << k;
+            } else {
+                if (a.hi || (k > 64u && (a.lo >> (128u - k)))) return false;
+                r.hi = a.lo << (k - 64u);
+                r.lo = 0;
+            }
+            return true;
+        }
+        case OP_LEQ: r.lo = !n128_lt(b, a); r.hi = 0; return true;
+        case OP_GEQ: r.lo = !n128_lt(a, b); r.hi = 0; return true;
+        case OP_LT: r.lo = n128_lt(a, b); r.hi = 0; return true;
+        case OP_GT: r.lo = n128_lt(b, a); r.hi = 0; return true;
+        case OP_EQ: r.lo = n128_eq(a, b); r.hi = 0; return true;
+        case OP_NEQ: r.lo = !n128_eq(a, b); r.hi = 0; return true;
+        case OP_LOR: r.lo = ((a.lo | a.hi) || (b.lo | b.hi)) ? 1u : 0u; r.hi = 0; return true;
+        case OP_LAND: r.lo = ((a.lo | a.hi) && (b.lo | b.hi)) ? 1u : 0u; r.hi = 0; return true;
+        case OP_LNOT: r.lo = (a.lo | a.hi) ? 0u : 1u; r.hi = 0; return true;
+        case OP_BOR: r.lo = a.lo | b.lo; r.hi = a.hi | b.hi; return true;
+        case OP_BAND: r.lo = a.lo & b.lo; r.hi = a.hi & b.hi; return true;
+        case OP_BXOR: r.lo = a.lo ^ b.lo; r.hi = a.hi ^ b.hi; return true;
+        case OP_NEG: if (a.lo | a.hi) return false; r = a; return true;
+        case OP_COPY: r = a; return true;
+        case OP_SELECT: r = (c.lo | c.hi) ? a : b; return true;
+        default: return false;
+    }
+}
+// regs: the arguments in the full-width layout (8 words per register, as the caller loads them); they are repacked to 4
+// words in place.  Returns false when the call has to be repeated on the full-width machine (regs are garbage then).
+// On success: err / result / ret_base / ret_cnt as vm_run; returned registers are 4 words each (vmn_result).
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline bool vm_run_narrow(const u32 *code, FnInfo fi, u32 *regs, const u32 *consts32, u32 *result, int &err, u32 &ret_base,
+                          u32 &ret_cnt) {
+    for (u32 k = 0; k < fi.n_params; ++k) {
+        const u32 *p = regs + 8 * (size_t)k;
+        if (p[4] | p[5] | p[6] | p[7]) return false;
+    }
+    for (u32 k = 0; k < fi.n_params; ++k)
+        for (int j = 0; j < 4; ++j) regs[4 * (size_t)k + j] = regs[8 * (size_t)k + j];
+    for (u32 k = 4 * fi.n_params; k < 4 * fi.n_regs; ++k) regs[k] = 0;
+    const u32 *ins = code + 5 * (size_t)fi.code_off;
+    u32 pc = 0;
+    u256_set_u32(result, 0);
+    ret_base = 0;
+    ret_cnt = 0;
+    for (u32 step = 0; step < (u32)VM_MAX_STEPS; ++step) {
+        if (pc >= fi.n_instr) { err = 2; return true; }
+        const u32 op = ins[5 * pc], d = ins[5 * pc + 1], a = ins[5 * pc + 2], b = ins[5 * pc + 3], c = ins[5 * pc + 4];
+        ++pc;
+        if (op == FOP_JMP) { pc = a & 0x3FFFFFFFu; continue; }
+        N128 va, vb, vc, r;
+        if (!vmn_operand(va, a, regs, consts32)) return false;
+        if (op == FOP_JZ) { if (!(va.lo | va.hi)) pc = b & 0x3FFFFFFFu; continue; }
+        if (op == FOP_RET) {
+            result[0] = (u32)va.lo; result[1] = (u32)(va.lo >> 32); result[2] = (u32)va.hi; result[3] = (u32)(va.hi >> 32);
+            ret_cnt = b & 0x3FFFFFFFu;
+            if (ret_cnt > 1) ret_base = a;
+            return true;
+        }
+        if (!vmn_operand(vb, b, regs, consts32)) return false;
+        if (op == FOP_LOADX || op == FOP_STOREX) {
+            const u32 base = a & 0x3FFFFFFFu, limit = (op == FOP_LOADX ? c : d) & 0x3FFFFFFFu;
+            if (vb.hi || (vb.lo >> 32) || vb.lo + base >= limit) { err = 2; return true; }
+            const u32 i = (u32)vb.lo + base;
+            if (op == FOP_LOADX) {
+                for (int k = 0; k < 4; ++k) regs[4 * (size_t)d + k] = regs[4 * (size_t)i + k];
+            } else {
+                if (!vmn_operand(vc, c, regs, consts32)) return false;
+                vmn_store(regs, i, vc);
+            }
+            continue;
+        }
+        if (!vmn_operand(vc, c, regs, consts32)) return false;
+        if (!vmn_apply(op, r, va, vb, vc)) return false;
+        vmn_store(regs, d, r);
+    }
+    err = 2;
+    return true;
+}
+// register `reg` of a finished call as a canonical element (narrow: 4 stored words, the upper half is zero)
+CW_HD void vm_result(u32 *out, const u32 *regs, u32 reg, bool narrow) {
+    if (narrow) {
+        for (int k = 0; k < 4; ++k) { out[k] = regs[4 * (size_t)reg + k]; out[4 + k] = 0; }
+    } else {
+        for (int k = 0; k < 8; ++k) out[k] = regs[8 * (size_t)reg + k];
+    }
 }
 
 }  // namespace cw

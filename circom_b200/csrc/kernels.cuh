@@ -116,6 +116,7 @@ struct TapeDev {
     u32 n_inputs;
     u32 n_bitwords;            // words of the bit plane per instance (0: no bit plane)
     u32 prime;                 // index into c_fr (read by the PRIME = -1 builds)
+    u32 vm_wide;               // 1: calls skip the 128-bit register machine (CW_VM_WIDE=1, for measurements)
 };
 
 // ---- inputs: inputs[batch][n_inputs][8 u32] canonical -> slots 1..n_inputs, slot 0 = 1 ----------
@@ -160,7 +161,6 @@ __device__ __noinline__ void exec_call(const TapeDev &tp, u32 call_off, uint4 *b
     fi.n_regs = __ldg(&tp.fn_info[4 * f + 2]);
     fi.n_params = __ldg(&tp.fn_info[4 * f + 3]);
     u32 regs[VM_MAX_REGS * 8];
-    for (u32 k = 0; k < fi.n_regs * 8; ++k) regs[k] = 0;
     for (u32 k = 0; k < n_args; ++k) {
         u32 v[8];
         load_operand<BP>(v, __ldg(&ct[2 + k]), base, plane_base, tp.consts, bt_log2, li);
@@ -168,14 +168,29 @@ __device__ __noinline__ void exec_call(const TapeDev &tp, u32 call_off, uint4 *b
     }
     int e = 0;
     u32 ret_base, ret_cnt;
-    vm_run(tp.fn_code, fi, regs, reinterpret_cast<const u32 *>(tp.consts), r, P, e, ret_base, ret_cnt);
+    // first on the 128-bit machine (fr_device.cuh: half the frame, integer arithmetic); a value that leaves 128 bits
+    // abandons that run and the call is repeated at full width
+    const bool narrow = !tp.vm_wide && vm_run_narrow(tp.fn_code, fi, regs, reinterpret_cast<const u32 *>(tp.consts), r, e,
+                                                     ret_base, ret_cnt);
+    if (!narrow) {
+        for (u32 k = 0; k < fi.n_regs * 8; ++k) regs[k] = 0;
+        for (u32 k = 0; k < n_args; ++k) {
+            u32 v[8];
+            load_operand<BP>(v, __ldg(&ct[2 + k]), base, plane_base, tp.consts, bt_log2, li);
+            for (int j = 0; j < 8; ++j) regs[8 * k + j] = v[j];
+        }
+        e = 0;
+        vm_run(tp.fn_code, fi, regs, reinterpret_cast<const u32 *>(tp.consts), r, P, e, ret_base, ret_cnt);
+    }
     // `var q[k] = f(..)`: results 1 .. k-1 go straight from the callee's registers to their slots (result 0 is `r`)
     const u32 n_extra = __ldg(&ct[2 + n_args]);
     for (u32 k = 0; k < n_extra; ++k) {
         const u32 d = __ldg(&ct[3 + n_args + k]);
         if (d == 0xFFFFFFFFu) continue;   // a result nobody reads
         if (k + 1 >= ret_cnt) { e = 2; continue; }
-        store_slot(&regs[8 * (ret_base + k + 1)], base, d, bt_log2, li);
+        u32 v[8];
+        vm_result(v, regs, ret_base + k + 1, narrow);
+        store_slot(v, base, d, bt_log2, li);
     }
     *err = e;
 }
@@ -520,19 +535,12 @@ __device__ __forceinline__ void acc128_add(unsigned long long &lo, unsigned long
     hi += h + (lo < l ? 1ull : 0ull);
 }
 
-// A linear combination in two parts: the lazy integer sums of its small terms (positive / negative coefficients) and
-// the modular accumulator `acc` of the others; `general` tells whether acc was used at all.
-struct LcSum {
-    unsigned long long plo, phi, nlo, nhi;
-    bool general;
-};
 template <int PRIME>
-__device__ __forceinline__ void r1cs_lc(u32 *acc, LcSum &sum, const R1csDev &R, unsigned long long b, unsigned long long e,
+__device__ __forceinline__ void r1cs_lc(u32 *acc, const R1csDev &R, unsigned long long b, unsigned long long e,
                                         const StoreDev &S, const uint4 *__restrict__ tb, const u32 *__restrict__ pb,
                                         u32 li, const FrParams &P, unsigned long long *__restrict__ first_bad_inst) {
     u256_set_u32(acc, 0);
     unsigned long long plo = 0, phi = 0, nlo = 0, nhi = 0;
-    bool general = false;
     const bool lazy = e - b < 65536ull;   // 2^16 terms below 2^112 cannot overflow 128 bits
     for (unsigned long long k = b; k < e; ++k) {
         const uint4 term = __ldg(&R.terms[k]);
@@ -590,20 +598,14 @@ __device__ __forceinline__ void r1cs_lc(u32 *acc, LcSum &sum, const R1csDev &R, 
         if (neg) fr_sub(t, acc, x, P);
         else fr_add(t, acc, x, P);
         u256_set(acc, t);
-        general = true;
     }
-    sum.plo = plo; sum.phi = phi; sum.nlo = nlo; sum.nhi = nhi;
-    sum.general = general;
-}
-// the value of the linear combination as a canonical field element: the lazy sums enter the accumulator once
-__device__ __forceinline__ void r1cs_lc_finish(u32 *acc, const LcSum &s, const FrParams &P) {
-    if (s.plo | s.phi) {
-        u32 v[8] = {(u32)s.plo, (u32)(s.plo >> 32), (u32)s.phi, (u32)(s.phi >> 32), 0u, 0u, 0u, 0u}, t[8];
+    if (plo | phi) {
+        u32 v[8] = {(u32)plo, (u32)(plo >> 32), (u32)phi, (u32)(phi >> 32), 0u, 0u, 0u, 0u}, t[8];
         fr_add(t, acc, v, P);
         u256_set(acc, t);
     }
-    if (s.nlo | s.nhi) {
-        u32 v[8] = {(u32)s.nlo, (u32)(s.nlo >> 32), (u32)s.nhi, (u32)(s.nhi >> 32), 0u, 0u, 0u, 0u}, t[8];
+    if (nlo | nhi) {
+        u32 v[8] = {(u32)nlo, (u32)(nlo >> 32), (u32)nhi, (u32)(nhi >> 32), 0u, 0u, 0u, 0u}, t[8];
         fr_sub(t, acc, v, P);
         u256_set(acc, t);
     }
@@ -659,28 +661,16 @@ __global__ void __launch_bounds__(256, MINB) r1cs_check_kernel(R1csDev R, StoreD
             const unsigned long long p0 = __ldg(&R.row_ptr[3 * (size_t)row]), p1 = __ldg(&R.row_ptr[3 * (size_t)row + 1]),
                                      p2 = __ldg(&R.row_ptr[3 * (size_t)row + 2]), p3 = __ldg(&R.row_ptr[3 * (size_t)row + 3]);
             u32 a[8], b[8], c[8];
-            LcSum sa, sb, sc;
-            r1cs_lc<PRIME>(a, sa, R, p0, p1, S, tb, pb, li, P, &first_bad[inst]);
-            r1cs_lc<PRIME>(b, sb, R, p1, p2, S, tb, pb, li, P, &first_bad[inst]);
-            r1cs_lc<PRIME>(c, sc, R, p2, p3, S, tb, pb, li, P, &first_bad[inst]);
-            // rows of small integers (boolean logic, carries, recomposition sums: the bulk of circom constraints) are
-            // decided over the integers, without a reduction (fr_device.cuh: small_row_holds)
-            bool ok;
-            if (!EVAL && !(sa.general | sb.general | sc.general) && !(sa.phi | sa.nhi | sb.phi | sb.nhi)) {
-                ok = small_row_holds(sa.plo, sa.nlo, sb.plo, sb.nlo, sc.plo, sc.phi, sc.nlo, sc.nhi);
-            } else {
-                r1cs_lc_finish(a, sa, P);
-                r1cs_lc_finish(b, sb, P);
-                r1cs_lc_finish(c, sc, P);
-                if (EVAL) {
-                    const size_t o = ((size_t)inst * out.m + row) * 2;
-                    stg256(out.a + o, a);
-                    stg256(out.b + o, b);
-                    stg256(out.c + o, c);
-                }
-                ok = r1cs_row_holds(a, b, c, P);
+            r1cs_lc<PRIME>(a, R, p0, p1, S, tb, pb, li, P, &first_bad[inst]);
+            r1cs_lc<PRIME>(b, R, p1, p2, S, tb, pb, li, P, &first_bad[inst]);
+            r1cs_lc<PRIME>(c, R, p2, p3, S, tb, pb, li, P, &first_bad[inst]);
+            if (EVAL) {
+                const size_t o = ((size_t)inst * out.m + row) * 2;
+                stg256(out.a + o, a);
+                stg256(out.b + o, b);
+                stg256(out.c + o, c);
             }
-            if (!ok) atomicMin(&first_bad[inst], (unsigned long long)row);
+            if (!r1cs_row_holds(a, b, c, P)) atomicMin(&first_bad[inst], (unsigned long long)row);
         }
     }
 }

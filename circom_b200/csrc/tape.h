@@ -77,6 +77,16 @@ struct Tape {
     std::vector<InputInfo> inputs;
     std::vector<HashEntry> hashmap;
     R1csData r1cs;
+    // names of signals and components per template, when the description carries a symbols section (docs/CB2C.md):
+    // the source of `.sym` (dag/src/sym_porting.rs).  Not part of the lowered-circuit blob.
+    struct SymTemplate {
+        uint32_t n_own = 0;
+        uint64_t total_signals = 0;
+        std::vector<uint32_t> subs;          // template of each sub-component
+        std::vector<std::string> own, sub;   // names of the own signals / of the sub-components
+    };
+    std::vector<SymTemplate> sym;            // empty: no symbols
+    uint32_t sym_main = 0;
     size_t n_tape_ops() const { return ops.size() / 4; }
     size_t n_items() const { return items.empty() ? 0 : items.size() - 1; }
     size_t n_levels() const { return level_start.empty() ? 0 : level_start.size() - 1; }
@@ -98,5 +108,8 @@ std::vector<uint8_t> wtns_bytes(const FieldParams &F, const uint64_t *witness, u
 void write_dat(const Tape &t, const std::string &path);
 // .wtns (main.cpp:288-334 / witness_calculator.js:212-276): returns the witness as 4 x u64 limbs per entry
 void read_wtns(const std::string &path, int &prime_id, std::vector<uint64_t> &witness);
+// .sym (constraint_writers/src/sym_writer.rs:4-38, dag/src/sym_porting.rs:16-33): one line per signal,
+// `signal id,witness index or -1,node id,qualified name`.  Throws when the circuit carries no symbols.
+void write_sym(const Tape &t, const std::string &path);
 
 }  // namespace cw

@@ -63,6 +63,8 @@ def _load() -> ctypes.CDLL:
         "cw_circuit_slot_census": (c_int, [P, POINTER(c_uint64)]),
         "cw_circuit_witness2signal": (c_int, [P, c_void_p]),
         "cw_circuit_write_dat": (c_int, [P, c_char_p]),
+        "cw_circuit_write_sym": (c_int, [P, c_char_p]),
+        "cw_circuit_functions": (c_int, [P, POINTER(c_uint32), POINTER(c_uint32)]),
         "cw_batch_create": (c_int, [P, c_uint32, c_int, POINTER(P)]),
         "cw_batch_destroy": (None, [P]),
         "cw_batch_set_input": (c_int, [P, c_uint32, c_uint64, c_uint32, POINTER(c_uint64)]),

@@ -126,7 +126,8 @@ class Circuit:
     """A lowered circuit (replaces Circom_Circuit + the compiled <name>.cpp)."""
 
     def __init__(self, src: Union[CircuitDesc, bytes, str], sanity_check: bool = True, host_only: bool = False,
-                 o0: bool = False, flags: int = 0, compact: Optional[bool] = None, fuse: bool = False):
+                 o0: bool = False, flags: int = 0, compact: Optional[bool] = None, fuse: bool = False,
+                 symbols: bool = False):
         """compact (default on; environment CW_COMPACT=0 turns it off): lower for the compact value store - bit runs in
         a per-instance bit plane, temporaries sharing slots (CW_FLAG_COMPACT) - instead of one 32-byte slot per value"""
         if compact is None:
@@ -139,7 +140,7 @@ class Circuit:
         self.flags = flags
         self._h = ctypes.c_void_p()
         if isinstance(src, CircuitDesc):
-            src = src.to_bytes()
+            src = src.to_bytes(symbols=symbols)   # (symbols: signal / component names for write_sym)
         if isinstance(src, (bytes, bytearray)):
             buf = bytes(src)
             check(lib.cw_circuit_load_mem(buf, len(buf), flags, ctypes.byref(self._h)))
@@ -230,6 +231,20 @@ class Circuit:
 
     def write_dat(self, path: str) -> None:
         check(lib.cw_circuit_write_dat(self._h, path.encode()))
+
+    def functions(self) -> List[dict]:
+        """the lowered functions: instructions and registers of a call frame (after the lowering's register allocation)"""
+        n = ctypes.c_uint32()
+        check(lib.cw_circuit_functions(self._h, ctypes.byref(n), None))
+        info = (ctypes.c_uint32 * (4 * max(1, n.value)))()
+        check(lib.cw_circuit_functions(self._h, ctypes.byref(n), info))
+        return [{"n_instr": int(info[4 * i + 1]), "n_regs": int(info[4 * i + 2]), "n_params": int(info[4 * i + 3])}
+                for i in range(n.value)]
+
+    def write_sym(self, path: str) -> None:
+        """the compiler's `.sym` (`signal id,witness index or -1,node id,main.path.name` per signal); the description must
+        carry the symbols section (Circuit(desc, symbols=True) / a producer that writes it)"""
+        check(lib.cw_circuit_write_sym(self._h, path.encode()))
 
     def flatten_inputs(self, inp: dict) -> List[int]:
         """One instance's inputs in main-input signal order, with the reference's checks."""

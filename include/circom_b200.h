@@ -134,11 +134,18 @@ int cw_circuit_tape_items(const cw_circuit *c, uint32_t *items);
 /* value slots of one instance by the width the lowering's range analysis proves: out[0] one bit, out[1] <= 32 bits,
  * out[2] <= 64 bits, out[3] wider (today every slot is a 32-byte element; the census sizes a narrow-slot layout) */
 int cw_circuit_slot_census(const cw_circuit *c, uint64_t out[4]);
+/* the circuit's functions (FunctionCodeInfo, function.rs:9-20) as lowered: *n = their number; info (may be NULL) receives 4
+ * words per function: {code offset, instructions, registers of a call frame after register allocation, parameters} */
+int cw_circuit_functions(const cw_circuit *c, uint32_t *n, uint32_t *info);
 /* witness2SignalList (calcwit.hpp:54-56, c_code_generator.rs:605-614): n_witness entries */
 int cw_circuit_witness2signal(const cw_circuit *c, uint64_t *out);
 /* the reference's .dat (generate_dat_file, c_code_generator.rs:818-865): input hash map (:575-603), witness2signal list
  * (:605-614), circuit constants in the 40-byte tagged Montgomery form (:616-679); the io-map section is empty */
 int cw_circuit_write_dat(const cw_circuit *c, const char *path);
+/* the compiler's .sym (constraint_writers/src/sym_writer.rs:4-38, dag/src/sym_porting.rs:16-33): one line per signal,
+ * `signal id,witness index or -1,node id,main.<path>.<name>`.  Needs a description with a symbols section (docs/CB2C.md);
+ * CW_ESTATE otherwise (also for circuits restored with cw_circuit_deserialize: the blob carries no names). */
+int cw_circuit_write_sym(const cw_circuit *c, const char *path);
 
 /* ---- batch: Circom_CalcWit for `batch` independent inputs on one GPU ------------------------ */
 int cw_batch_create(const cw_circuit *c, uint32_t batch, int device, cw_batch **out);

@@ -80,6 +80,11 @@ pub struct TemplateRecord {
     pub subs: Vec<u32>,                                   // template index per sub-component, creation order
     pub ops: Vec<OpRec>,
     pub constraints: Vec<[Vec<(Ref, u32)>; 3]>,           // A, B, C: (signal reference, constant id)
+    // symbols section (docs/CB2C.md): names of the own signals in numbering order (array elements spelled out, as
+    // TemplateInstance::signals / dag::Node::signal_correspondence give them) and of the sub-components (the `symbol`
+    // of each CreateCmpBucket, with its indices for component arrays) - what `--sym` prints (dag/src/sym_porting.rs)
+    pub signal_names: Vec<String>,
+    pub sub_names: Vec<String>,
 }
 #[derive(Default)]
 pub struct FunctionRecord { pub name: String, pub n_params: u32, pub n_regs: u32, pub code: Vec<OpRec> }
@@ -152,6 +157,15 @@ impl Cb2cFile {
             Self::w_str(w, &f.name)?;
             for v in [f.n_params, f.n_regs, f.code.len() as u32] { Self::w_u32(w, v)?; }
             Self::w_ops(w, &f.code)?;
+        }
+        // optional symbols section: only when every template carries a complete set of names
+        if self.templates.iter().all(|t| t.signal_names.len() as u32 == t.n_out + t.n_in + t.n_inter
+                                          && t.sub_names.len() == t.subs.len()) {
+            w.write_all(b"SYMS").map_err(|_| {})?;
+            for t in &self.templates {
+                for n in &t.signal_names { Self::w_str(w, n)?; }
+                for n in &t.sub_names { Self::w_str(w, n)?; }
+            }
         }
         Ok(())
     }

@@ -240,6 +240,13 @@ impl WriteCuda for CreateCmpBucket { // create_component_bucket.rs:204-352
             if cx.sub_of_cmp.len() <= slot { cx.sub_of_cmp.resize(slot + 1, u32::MAX); }
             cx.sub_of_cmp[slot] = cx.rec.subs.len() as u32;
             cx.rec.subs.push(self.template_id as u32);             // template ids = order of Circuit::templates
+            // symbols: `name_subcomponent` plus the indices of position k inside `dimensions` (row-major), e.g. `bits[2]`
+            let mut name = self.name_subcomponent.clone();
+            let mut rest = *k;
+            let mut idx = vec![0usize; self.dimensions.len()];
+            for (d, dim) in self.dimensions.iter().enumerate().rev() { idx[d] = rest % dim; rest /= dim; }
+            for i in idx { name.push_str(&format!("[{}]", i)); }
+            cx.rec.sub_names.push(name);
         }
         Ok(None)
     }
@@ -412,8 +419,11 @@ pub fn lower_function(f: &FunctionCodeInfo, producer: &CUDAProducer, file: &mut 
 }
 
 /// Circuit::produce_cuda: the counterpart of Circuit::produce_c (circuit.rs:596-612)
+/// `signal_names_of(template id)`: the names of the instance's signals in numbering order, array elements spelled out
+/// (from the VCP: TemplateInstance::signals, the same list `--sym` walks) - empty to omit the symbols section.
 pub fn produce_cb2c(templates: &[Box<TemplateCodeInfo>], functions: &[Box<FunctionCodeInfo>], producer: &CUDAProducer,
-                    constraints_of: &dyn Fn(usize) -> Vec<[Vec<(Ref, BigInt)>; 3]>) -> Result<Cb2cFile, ()> {
+                    constraints_of: &dyn Fn(usize) -> Vec<[Vec<(Ref, BigInt)>; 3]>,
+                    signal_names_of: &dyn Fn(usize) -> Vec<String>) -> Result<Cb2cFile, ()> {
     let q = producer.prime_str.parse::<BigInt>().map_err(|_| {})?;
     let mut file = Cb2cFile::default();
     file.prime = producer.prime_id()?;
@@ -434,6 +444,7 @@ pub fn produce_cb2c(templates: &[Box<TemplateCodeInfo>], functions: &[Box<Functi
             for (k, lc) in con.iter().enumerate() { for (r, c) in lc { row[k].push((*r, file.const_id(c, &q))); } }
             rec.constraints.push(row);
         }
+        rec.signal_names = signal_names_of(t.id);
         file.templates.push(rec);
     }
     file.main = (templates.len() - 1) as u32;                        // the main template is instantiated last

@@ -357,7 +357,10 @@ static int run_func(const circuit *c, const func *f, const fe *args, fe *result,
         }
         if (o->op == 43 || o->op == 44) {                                          /* LOADX / STOREX */
             const fe *ix = arg[1];
-            if (ix->v[1] | ix->v[2] | ix->v[3] || ix->v[0] + RIDX(o->a) >= f->n_regs) break;
+            /* the extent of the array, when the producer wrote it (LOADX: operand c, STOREX: operand d; docs/CB2C.md) */
+            const u64 ext = o->op == 43 ? (RK(o->c) == 0 ? RIDX(o->c) : 0) : (RK(o->d) == 0 ? RIDX(o->d) : 0);
+            const u64 lim = ext && RIDX(o->a) + ext <= f->n_regs ? RIDX(o->a) + ext : f->n_regs;
+            if (ix->v[1] | ix->v[2] | ix->v[3] || ix->v[0] + RIDX(o->a) >= lim) break;
             u32 i = (u32)ix->v[0] + RIDX(o->a);
             if (o->op == 43) regs[RIDX(o->d)] = regs[i]; else regs[i] = *arg[2];
             continue;

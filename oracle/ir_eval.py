@@ -62,11 +62,11 @@ def run_function(desc, F, fn, args):
             return val(a)
         elif op == OPS["LOADX"]:
             i = a[2] + to_int(val(b))
-            assert 0 <= i < fn.n_regs
+            assert 0 <= i < (a[2] + c[2] if c[0] == 0 and c[2] else fn.n_regs)   # operand c: extent of the array
             regs[d[2]] = regs[i]
         elif op == OPS["STOREX"]:
             i = a[2] + to_int(val(b))
-            assert 0 <= i < fn.n_regs
+            assert 0 <= i < (a[2] + d[2] if d[0] == 0 and d[2] else fn.n_regs)      # operand d: extent of the array
             regs[i] = val(c)
         else:
             regs[d[2]] = F.apply(op, val(a), val(b), val(c))

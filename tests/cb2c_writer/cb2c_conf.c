@@ -7,7 +7,7 @@
  *         component m = Multiplier2(); m.a <== x; m.b <== y; p <== m.c + 1; }
  *
  * tests/test_cb2c_spec_cpu.py checks that the bytes equal what the DSL writes for the same circuit and that the file
- * loads, lowers and computes the expected witness.   usage: cb2c_conf out.cb2c */
+ * loads, lowers and computes the expected witness.   usage: cb2c_conf out.cb2c [sym]   (sym: with the symbols section) */
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -83,6 +83,12 @@ int main(int argc, char **argv) {
     /* ---- main-input names: global ids (one = 0, outputs 1..3, inputs 4, 5) ---- */
     str("x"); u32(4); u32(1);
     str("y"); u32(5); u32(1);
+    /* ---- no functions; optional symbols section: per template the own signals in numbering order, then the sub-components ---- */
+    if (argc > 2 && !strcmp(argv[2], "sym")) {
+        fwrite("SYMS", 1, 4, f);
+        str("c"); str("a"); str("b");                                       /* Multiplier2 */
+        str("bits[0]"); str("bits[1]"); str("p"); str("x"); str("y"); str("m");  /* Conf: 5 signals, 1 sub-component */
+    }
     fclose(f);
     return 0;
 }

@@ -37,7 +37,16 @@ static FrParams dev_params(const FieldParams &F) {
 
 static std::string g_err;
 
+static unsigned long long g_narrow_calls = 0, g_wide_calls = 0;   // calls finished on the 128-bit / the full-width machine
+
 extern "C" {
+// counters of the two register machines since the last call (tests: the narrow one must actually run)
+void hs_vm_counters(unsigned long long *narrow, unsigned long long *wide) {
+    *narrow = g_narrow_calls;
+    *wide = g_wide_calls;
+    g_narrow_calls = g_wide_calls = 0;
+}
+
 
 const char *hs_last_error() { return g_err.c_str(); }
 
@@ -129,12 +138,25 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
                     for (uint32_t k = 0; k < ct[1]; ++k) operand(ct[2 + k], &regs[(size_t)k * 8]);
                     int e = 0;
                     u32 ret_base, ret_cnt;
-                    vm_run(t.fn_code.data(), fi, regs.data(), (const u32 *)t.consts.data(), r, P, e, ret_base, ret_cnt);
+                    // as kernels.cuh exec_call: the 128-bit machine first, the full-width one when it gives up
+                    static const bool vm_wide = getenv("CW_VM_WIDE") && atoi(getenv("CW_VM_WIDE"));
+                    const bool narrow = !vm_wide && vm_run_narrow(t.fn_code.data(), fi, regs.data(), (const u32 *)t.consts.data(),
+                                                                  r, e, ret_base, ret_cnt);
+                    g_narrow_calls += narrow;
+                    g_wide_calls += !narrow;
+                    if (!narrow) {
+                        std::fill(regs.begin(), regs.end(), 0u);
+                        for (uint32_t k = 0; k < ct[1]; ++k) operand(ct[2 + k], &regs[(size_t)k * 8]);
+                        e = 0;
+                        vm_run(t.fn_code.data(), fi, regs.data(), (const u32 *)t.consts.data(), r, P, e, ret_base, ret_cnt);
+                    }
                     const uint32_t *ex = ct + 2 + ct[1];
                     for (uint32_t k = 0; k < ex[0]; ++k) {   // results 1.. of `var q[k] = f(..)`
                         if (ex[1 + k] == 0xFFFFFFFFu) continue;
                         if (k + 1 >= ret_cnt) { e = 2; continue; }
-                        put_slot(ex[1 + k], &regs[(size_t)8 * (ret_base + k + 1)]);
+                        u32 v[8];
+                        vm_result(v, regs.data(), ret_base + k + 1, narrow);
+                        put_slot(ex[1 + k], v);
                     }
                     if (e) err = 1;
                     put(dst, r);
@@ -401,11 +423,14 @@ int hs_fr_op(int prime, int op, const uint64_t *A, const uint64_t *B, const uint
     return any_err;
 }
 
-// the integer test of small R1CS rows (fr_device.cuh: small_row_holds); v = n x {pa, na, pb, nb, pc_lo, pc_hi, nc_lo, nc_hi}
-void hs_small_rows(const uint64_t *v, uint8_t *ok, size_t n) {
+// one operator of the 128-bit register machine (fr_device.cuh: vmn_apply); v = n x {a_lo, a_hi, b_lo, b_hi, c_lo, c_hi},
+// out = n x {r_lo, r_hi}, ok[i] = 0 when the operator hands the call to the full-width machine
+void hs_vmn_apply(int op, const uint64_t *v, uint64_t *out, uint8_t *ok, size_t n) {
     for (size_t i = 0; i < n; ++i) {
-        const uint64_t *r = v + 8 * i;
-        ok[i] = small_row_holds(r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]) ? 1 : 0;
+        N128 a{v[6 * i], v[6 * i + 1]}, b{v[6 * i + 2], v[6 * i + 3]}, c{v[6 * i + 4], v[6 * i + 5]}, r{0, 0};
+        ok[i] = vmn_apply((u32)op, r, a, b, c) ? 1 : 0;
+        out[2 * i] = r.lo;
+        out[2 * i + 1] = r.hi;
     }
 }
 

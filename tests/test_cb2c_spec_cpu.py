@@ -63,3 +63,48 @@ def test_c_writer_from_the_spec_matches_the_dsl_and_runs(tmp_path):
     assert not ost.any() and (ow[:, w2s] == wit).all()
     for i, (x, y) in enumerate(((3, 11), (2, 5), (1, 2**63))):
         assert limbs_to_ints(wit[i]) == [1, x & 1, (x >> 1) & 1, x * y + 1, x, y, x * y]
+
+
+def test_symbols_section_and_sym_file(tmp_path):
+    """The optional symbols section, written from the spec by the C writer, equals the DSL's; `cw_circuit_write_sym` prints the
+    reference's `.sym` lines (sym_writer.rs:10-14: `signal,witness,node,name`; order of dag/src/sym_porting.rs:16-33: a
+    component's signals, then its sub-components; witness = -1 for a signal that the signal merging removed)."""
+    exe, out = str(tmp_path / "cb2c_conf"), str(tmp_path / "conf_sym.cb2c")
+    subprocess.check_call(["gcc", "-O1", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "cb2c_writer", "cb2c_conf.c")])
+    subprocess.check_call([exe, out, "sym"])
+    blob = open(out, "rb").read()
+    d = dsl_conf()
+    assert blob == d.to_bytes(symbols=True) and blob.startswith(d.to_bytes()) and blob[len(d.to_bytes()):][:4] == b"SYMS"
+    c = Circuit(blob, host_only=True)
+    assert c.stats == Circuit(d, host_only=True).stats      # names change nothing of the lowering
+    sym = str(tmp_path / "conf.sym")
+    c.write_sym(sym)
+    assert open(sym).read() == ("1,1,1,main.bits[0]\n2,2,1,main.bits[1]\n3,3,1,main.p\n4,4,1,main.x\n5,5,1,main.y\n"
+                                "6,6,0,main.m.c\n7,-1,0,main.m.a\n8,-1,0,main.m.b\n")
+    # --O0 keeps every signal in the witness
+    Circuit(blob, host_only=True, o0=True).write_sym(sym)
+    assert [ln.split(",")[1] for ln in open(sym).read().split()] == [str(i) for i in range(1, 9)]
+    # a description without the section: refused, not guessed
+    import pytest
+    with pytest.raises(Exception, match="no symbols"):
+        Circuit(d, host_only=True).write_sym(sym)
+    # a bigger tree: one line per signal but the constant one, ids ascending, the witness column is the inverse of
+    # witness2signal, paths follow the component tree
+    d2 = CircuitDesc("bn128")
+    d2.set_main(C.ecdsa_scale(d2, 1, 2))
+    c2 = Circuit(d2, host_only=True, symbols=True)
+    c2.write_sym(sym)
+    lines = [ln.split(",") for ln in open(sym).read().split()]
+    assert [int(x[0]) for x in lines] == list(range(1, d2.total_signals))
+    w2s = c2.witness2signal().tolist()
+    inv = {s: i for i, s in enumerate(w2s)}
+    assert all(int(x[1]) == inv.get(int(x[0]), -1) for x in lines)
+    assert lines[0][3].startswith("main.") and any(x[3].count(".") >= 3 for x in lines)
+    assert len({x[3] for x in lines}) == len(lines)         # qualified names are unique
+    assert open(sym).read() == "".join(x + "\n" for x in d2.sym_lines(w2s))   # = the Python writer, node ids included
+    for mk in (lambda dd: C.int_div(dd, 8), lambda dd: C.sha256(dd, 8), lambda dd: C.poseidon(dd, 2)):
+        d3 = CircuitDesc("bn128")
+        d3.set_main(mk(d3))
+        c3 = Circuit(d3, host_only=True, symbols=True)
+        c3.write_sym(sym)
+        assert open(sym).read() == "".join(x + "\n" for x in d3.sym_lines(c3.witness2signal()))

@@ -119,10 +119,13 @@ def test_r1cs_of_the_documented_basic_circuit(tmp_path):
     for o0, symfile in ((False, symfile_o1), (True, symfile_o0)):
         d = CircuitDesc("bn128")
         d.set_main(_basic_circom(d))
-        c = Circuit(d, host_only=True, o0=o0)
+        c = Circuit(d, host_only=True, o0=o0, symbols=True)
         assert d.sym_lines(c.witness2signal()) == symfile
         p = d.write_sym(str(tmp_path / "basic.sym"), c.witness2signal())
         assert open(p).read() == "".join(x + "\n" for x in symfile)
+        # the C library's writer (cw_circuit_write_sym, names from the symbols section of the description)
+        c.write_sym(str(tmp_path / "basic_c.sym"))
+        assert open(str(tmp_path / "basic_c.sym")).read() == "".join(x + "\n" for x in symfile)
     for o0, doc, sym in ((False, doc_o1, sym_o1), (True, doc_o0, list(range(7)))):
         d = CircuitDesc("bn128")
         assert d.q == q

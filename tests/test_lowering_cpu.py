@@ -177,48 +177,101 @@ def test_r1cs_check_arithmetic_and_violation_detection():
     assert fb[2] >= 0 and (np.delete(fb, 2) == -1).all()
 
 
-def test_small_row_integer_check():
-    """fr_device.cuh small_row_holds: a*b == c decided over the integers for a = pa - na, b = pb - nb (64-bit sums) and
-    c = pc - nc (128-bit sums) - the fast path of the R1CS kernel for rows of small terms - against python ints"""
+
+def test_narrow_register_machine_ops():
+    """fr_device.cuh vmn_apply (the 128-bit machine hint functions run on first): whenever it produces a result it is the
+    field result of the python model; it gives up exactly when the result leaves 128 bits / the operator is not an
+    integer one, and it must not give up on the common cases (that is its point)"""
     hs = hostsim()
-    rng = random.Random(11)
-    M64, M128 = 2**64 - 1, 2**128 - 1
-    rows, exp = [], []
+    rng = random.Random(5)
+    M = 2**128
 
-    def add(pa, na, pb, nb, pc, nc):
-        rows.append([pa, na, pb, nb, pc & M64, pc >> 64, nc & M64, nc >> 64])
-        exp.append(1 if (pa - na) * (pb - nb) == pc - nc else 0)
+    def small():
+        return rng.choice([0, 1, 2, 2**64 - 1, 2**64, 2**127, M - 1, rng.getrandbits(rng.randrange(1, 129)),
+                           rng.getrandbits(rng.randrange(1, 65)), rng.randrange(140)])
+    for prime in ("bn128", "secq256r1"):
+        F = Field(prime)
+        for op in list(range(1, 26)) + [28]:
+            n = 4000
+            A = [small() for _ in range(n)]
+            B = [small() for _ in range(n)]
+            Cc = [rng.choice([0, 1, small()]) for _ in range(n)]
+            v = np.array([[a & (2**64 - 1), a >> 64, b & (2**64 - 1), b >> 64, c & (2**64 - 1), c >> 64]
+                          for a, b, c in zip(A, B, Cc)], dtype=np.uint64)
+            out = np.zeros((n, 2), dtype=np.uint64)
+            ok = np.zeros(n, dtype=np.uint8)
+            hs.hs_vmn_apply(op, v.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p),
+                            ok.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(n))
+            n_ok = 0
+            for i in range(n):
+                try:
+                    exp = F.apply(op, A[i], B[i], Cc[i]) if op != 28 else F.inv(A[i])
+                except DivisionByZero:
+                    assert not ok[i]          # the full-width machine reports it
+                    continue
+                if ok[i]:
+                    n_ok += 1
+                    assert int(out[i, 0]) | (int(out[i, 1]) << 64) == exp, (OP_NAMES.get(op, op), hex(A[i]), hex(B[i]))
+                else:
+                    # giving up is only allowed when the narrow machine has no answer
+                    fits = exp < M
+                    name = OP_NAMES.get(op, str(op))
+                    if name in ("ADD", "SUB", "LT", "GT", "LEQ", "GEQ", "EQ", "NEQ", "LOR", "LAND", "LNOT", "BOR", "BAND",
+                                "BXOR", "COPY", "SELECT"):
+                        assert not fits or name == "SUB" and A[i] < B[i], (name, hex(A[i]), hex(B[i]))
+                    if name == "MUL" and A[i] < 2**64 and B[i] < 2**64:
+                        raise AssertionError("64 x 64 product refused")
+                    if name in ("SHR", "SHL") and B[i] < 128 and fits and name == "SHR":
+                        raise AssertionError("shift refused")
+            name = OP_NAMES.get(op, str(op))
+            if name in ("DIV", "POW", "BNOT", "INV") or op == 28:
+                assert n_ok == 0
+            elif name not in ("NEG", "IDIV", "MOD"):
+                assert n_ok > n // 4, name
 
-    def small(bits):
-        return rng.choice([0, 1, 2, M64, rng.getrandbits(rng.randrange(1, bits + 1))])
 
-    for _ in range(20000):
-        pa, na, pb, nb = small(64), small(64), small(64), small(64)
-        prod = (pa - na) * (pb - nb)
-        nc = rng.choice([0, 0, rng.getrandbits(rng.randrange(1, 128))])
-        mode = rng.randrange(5)
-        if mode < 3:                         # a satisfied row (when its parts fit 128 bits)
-            pc = prod + nc
-            if pc < 0:
-                pc, nc = 0, -prod
-                if rng.random() < 0.5 and nc + 5 <= M128:
-                    pc, nc = 5, nc + 5
-            if pc > M128 or nc > M128:
-                continue
-            add(pa, na, pb, nb, pc, nc)
-        elif mode == 3:                      # off by a little / by a multiple of 2^64 or 2^128 (wrap-arounds)
-            pc = (prod + nc + rng.choice([1, -1, 2**64, -2**64, 2**128, -2**128])) % (2**128)
-            add(pa, na, pb, nb, pc, nc)
-        else:
-            add(pa, na, pb, nb, rng.getrandbits(128), nc)
-    # edges: the sum |ab| + x leaves 128 bits
-    add(M64, 0, M64, 0, (M64 * M64 + 5) & M128, 5)
-    add(M64, 0, M64, 0, 0, M128)
-    add(0, M64, M64, 0, M128, (M64 * M64 + M128) & M128)
-    add(0, M64, 0, M64, M64 * M64, 0)
-    add(0, 0, M64, 3, 0, 0)
-    v = np.array(rows, dtype=np.uint64)
-    ok = np.zeros(len(rows), dtype=np.uint8)
-    hs.hs_small_rows(v.ctypes.data_as(ctypes.c_void_p), ok.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(rows)))
-    assert ok.tolist() == exp
-    assert 0.2 < sum(exp) / len(exp) < 0.8
+def test_calls_run_on_the_narrow_machine_and_fall_back():
+    """calls of limb-arithmetic functions finish on the 128-bit machine; a call whose values leave 128 bits (a negative
+    difference, a field division, a wide argument) is repeated at full width - same witness either way"""
+    hs = hostsim()
+    na, wi = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+    rng = random.Random(9)
+    d = CircuitDesc("bn128")
+    d.set_main(C.ecdsa_scale(d, 1, 2, hints="functions"))
+    ins = [{"a": [rng.getrandbits(64) for _ in range(4)], "b": [rng.getrandbits(64) for _ in range(4)]} for _ in range(6)]
+    hs.hs_vm_counters(ctypes.byref(na), ctypes.byref(wi))
+    wit, st, _, w2s = hostsim_run(d, ins)
+    hs.hs_vm_counters(ctypes.byref(na), ctypes.byref(wi))
+    assert not st.any() and na.value == 6 * 2 and wi.value == 0
+    for i, inp in enumerate(ins):
+        exp = evaluate(d, inp)
+        assert limbs_to_ints(wit[i]) == [exp[k] for k in w2s]
+
+    # a function that leaves the integers depending on its arguments
+    d = CircuitDesc("bn128")
+
+    def body(f):
+        a, b = f.param(0), f.param(1)
+        x = f.var(a - b)                  # negative when a < b
+        f.if_begin(b.gt(1000))
+        f.set(x, x + a / b)               # field division
+        f.if_end()
+        f.ret(x * 3)
+    fn = d.function("mix", 2, body)
+
+    def build(t):
+        a, b = t.input("a"), t.input("b")
+        o = t.output("o")
+        t.assign(o, t.call(fn, [a, b]))
+    d.set_main(d.template("Mix", (), build))
+    q = d.q
+    ins = [{"a": 7, "b": 5}, {"a": 5, "b": 7}, {"a": 2**70, "b": 2**69}, {"a": 9, "b": 2000}, {"a": q - 1, "b": 1},
+           {"a": 2**128, "b": 1}, {"a": 2**127, "b": 3}, {"a": 2**70, "b": 999}, {"a": 2**100, "b": 1}]
+    # narrow: (7, 5), (2^70, 999), (2^100, 1); wide: a < b, the two field divisions (b > 1000), the two wide arguments,
+    # (2^127 - 3) * 3 >= 2^128
+    wit, st, _, w2s = hostsim_run(d, ins)
+    hs.hs_vm_counters(ctypes.byref(na), ctypes.byref(wi))
+    assert not st.any() and na.value == 3 and wi.value == 6
+    for i, inp in enumerate(ins):
+        exp = evaluate(d, inp)
+        assert limbs_to_ints(wit[i]) == [exp[k] for k in w2s], i

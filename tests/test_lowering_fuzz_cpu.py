@@ -11,6 +11,7 @@ import pytest
 from circom_b200.circuit import CircuitDesc
 from circom_b200 import circuits as C
 from oracle.ir_eval import evaluate, check_r1cs
+from oracle.field_model import DivisionByZero
 from tests.util import hostsim_run, limbs_to_ints, edge_values
 
 CW_FLAG_O0, CW_FLAG_NO_PEEPHOLE, CW_FLAG_BITPLANE, CW_FLAG_REUSE, CW_FLAG_COMPACT = 4, 8, 16, 32, 48
@@ -153,3 +154,128 @@ def test_shift_by_negative_signal_amount_is_not_treated_as_narrow(prime):
         assert not st.any()
         for i, e in enumerate(expected):
             assert limbs_to_ints(wit[i]) == [e[k] for k in w2s], (prime, flags, ins[i])
+
+
+def random_function(d, rng, n_params):
+    """a random structured function body: scalars, `var` arrays with run-time indices (kept in range by masking), nested
+    if / else and counted loops, values that are reused long after their definition, registers read before they are
+    written (the frame is zero-initialised), scalar or array return.  Exercises the lowering's register allocation
+    (liveness over loops and branches) and both register machines (values leave 128 bits now and then)."""
+    from circom_b200.circuit import FReg
+
+    def build(f):
+        scalars = [f.param(i) for i in range(n_params)]
+        arrays = []
+        if n_params >= 4 and rng.random() < 0.5:
+            arrays.append((f.param_array(0, 4), 4))
+            scalars = scalars[4:] or [f.var(3)]
+        for _ in range(rng.randrange(0, 3)):
+            n = rng.choice([2, 4, 8])
+            arrays.append((f.array(n, rng.randrange(5)), n))
+        for _ in range(rng.randrange(1, 4)):
+            scalars.append(f.var(rng.choice([0, 1, 7, rng.getrandbits(64)])))
+        for _ in range(rng.randrange(0, 2)):           # never initialised: reads the zero of the fresh frame
+            r = FReg(f, f.n_regs)
+            f.n_regs += 1
+            scalars.append(r)
+
+        def operand():
+            return rng.choice(scalars) if rng.random() < 0.8 else rng.choice([0, 1, 2, 3, 255, 2**32, 2**64 - 1, d.q - 1])
+
+        def expr(depth=0):
+            a = rng.choice(scalars)
+            k = rng.random()
+            if k < 0.45:
+                op = rng.choice(["__add__", "__mul__", "__and__", "__or__", "__xor__", "lt", "gt", "eq", "neq", "leq", "geq"])
+                return getattr(a, op)(operand() if depth or rng.random() < 0.6 else expr(1))
+            if k < 0.6:
+                return a - operand()
+            if k < 0.75:
+                return a >> rng.randrange(0, 70)
+            if k < 0.85:
+                return a << rng.randrange(0, 40)
+            if k < 0.92 and arrays:
+                base, n = rng.choice(arrays)
+                return f.load(base, a & (n - 1))
+            if k < 0.96:
+                return a // (operand() if rng.random() < 0.5 else 3)
+            return a / 7 if rng.random() < 0.5 else -a
+
+        def block(depth, budget):
+            for _ in range(rng.randrange(1, budget)):
+                k = rng.random()
+                if k < 0.5 or depth >= 3:
+                    tgt = rng.choice(scalars[n_params if not arrays or arrays[0][0] else 0:] or scalars)
+                    if tgt.idx < n_params and arrays and arrays[0][0] == 0:
+                        continue
+                    f.set(tgt, expr())
+                elif k < 0.65 and arrays:
+                    base, n = rng.choice(arrays)
+                    f.store(base, rng.choice(scalars) & (n - 1), expr())
+                elif k < 0.85:
+                    f.if_begin(expr())
+                    block(depth + 1, 4)
+                    if rng.random() < 0.5:
+                        f.if_else()
+                        block(depth + 1, 4)
+                    f.if_end()
+                else:
+                    i = f.var(0)
+                    n = rng.randrange(1, 5)
+                    f.loop_begin()
+                    f.loop_break_if_zero(i.lt(n))
+                    block(depth + 1, 4)
+                    f.set(i, i + 1)
+                    f.loop_end()
+                    scalars.append(i)
+        block(0, 8)
+        outs = [a for a in arrays if a[0] >= n_params]
+        if outs and rng.random() < 0.5:
+            base, n = rng.choice(outs)
+            f.ret_array(base, n)
+        else:
+            f.ret(expr())
+    return d.function("fz", n_params, build)
+
+
+@pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("CW_FUZZ_FUNCS", "150"))))
+def test_random_function_bodies_match_the_evaluator(seed):
+    import ctypes
+    from tests.util import hostsim
+    rng = random.Random(1000 + seed)
+    prime = rng.choice(["bn128", "bls12381", "secq256r1"])
+    d = CircuitDesc(prime)
+    n_params = rng.randrange(1, 6)
+    fn = random_function(d, rng, n_params)
+    n_res = fn.n_results
+
+    def build(t):
+        ins = t.input("x", n_params)
+        outs = t.output("o", n_res)
+        res = t.call_array(fn, ins, n_res) if n_res > 1 else [t.call(fn, ins)]
+        for k in range(n_res):
+            t.assign(outs[k], res[k])
+    d.set_main(d.template("Fz", (), build))
+    q = d.q
+    ins = [{"x": [rng.choice([0, 1, 2, rng.getrandbits(64), rng.getrandbits(32), rng.getrandbits(120), q - 1, rng.randrange(q)])
+                  for _ in range(n_params)]} for _ in range(12)]
+    ok_ins, exps = [], []
+    for inp in ins:
+        try:
+            exps.append(evaluate(d, inp))
+            ok_ins.append(inp)
+        except (DivisionByZero, AssertionError, RuntimeError):
+            pass          # division by zero / a runaway loop: error statuses are covered elsewhere
+    if not ok_ins:
+        return
+    hs = hostsim()
+    na, wi = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+    hs.hs_vm_counters(ctypes.byref(na), ctypes.byref(wi))
+    for flags in (0, 48):
+        wit, st, _, w2s = hostsim_run(d, ok_ins, flags=flags)
+        assert not st.any()
+        for i, exp in enumerate(exps):
+            assert limbs_to_ints(wit[i]) == [exp[k] for k in w2s], (seed, i)
+    # the packed frame never exceeds the declared one
+    from circom_b200.witness_calculator import Circuit
+    assert Circuit(d, host_only=True).functions()[0]["n_regs"] <= fn.n_regs

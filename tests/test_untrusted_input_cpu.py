@@ -236,6 +236,27 @@ def test_hostile_array_calls():
     assert variant(call_edit(0x3FFFFFFF)) == native.CW_EFORMAT
 
 
+def test_hostile_symbols_section():
+    """names end up in a text file, one line per signal: control characters, separators, empty and oversized names, short
+    or overlong sections are refused at load time"""
+    d = CircuitDesc("bn128")
+    d.set_main(C.less_than(d, 4))
+    plain, good = d.to_bytes(), d.to_bytes(symbols=True)
+    assert try_load(good) == 0
+    body = good[len(plain) + 4:]
+    assert try_load(plain + b"SYMX" + body) == native.CW_EFORMAT           # unknown section
+    assert try_load(plain + b"SY") == native.CW_EFORMAT
+    assert try_load(good + b"\0\0\0\0") == native.CW_EFORMAT               # bytes after the section
+    assert try_load(good[:-8]) == native.CW_EFORMAT                        # a name is missing
+    first = struct.unpack_from("<I", body, 0)[0]
+    assert body[4:4 + first] == b"out[0]" and body[10:12] == b"\0\0"      # (the first template is the Num2Bits)
+    for bad in (b"o,t[0]", b"o\nt[0]", b"o t[0]", b"\x7fut[0]", b"out[0\0"):
+        assert try_load(plain + b"SYMS" + body[:4] + bad + body[10:]) == native.CW_EFORMAT, bad
+    assert try_load(plain + b"SYMS" + struct.pack("<I", 0) + body[12:]) == native.CW_EFORMAT         # empty name
+    assert try_load(plain + b"SYMS" + struct.pack("<I", 0xFFFFFFFF) + body[4:]) == native.CW_EFORMAT  # length past the file
+    assert try_load(plain + b"SYMS" + struct.pack("<I", 5000) + b"a" * 5000 + body[12:]) == native.CW_EFORMAT
+
+
 def test_set_input_outside_main_inputs_is_refused():
     """cw_batch_set_input indexes host arrays with (signal id - first input): a hash-map entry pointing elsewhere must
     not be followed (defence in depth behind the parser's check) - exercised through the Python twin of the lookup"""

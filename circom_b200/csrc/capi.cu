@@ -22,6 +22,7 @@
 
 #include "../../include/circom_b200.h"
 #include "kernels.cuh"
+#include "tape_calls.h"
 #include "tape.h"
 #include "hostpack.h"
 
@@ -80,6 +81,7 @@ int ensure_device(int device) {
         static_assert(N_PRIMES_DEV == CW_N_PRIMES, "prime tables");
         for (int k = 0; k < N_PRIMES_DEV; ++k) h[k] = make_dev_params(make_field(k));
         CU(cudaMemcpyToSymbol(c_fr, h, sizeof(h)));
+        CU(tape_calls_set_params(h, sizeof(h)));
         g_dev_ready[device] = true;
     }
     return CW_OK;
@@ -240,9 +242,9 @@ static void launch_tape_k(const TapeDev &tp, cw_batch *b, u32 tiles, u32 th) {
 }
 template <int PR>
 static void launch_tape(const TapeDev &tp, cw_batch *b, u32 tiles, u32 th, bool calls, bool bp, bool fused) {
-    if (calls) {  // (the lowering does not fuse tapes with function calls)
-        if (bp) launch_tape_k<PR, true, true, -1, false>(tp, b, tiles, th);
-        else launch_tape_k<PR, true, false, -1, false>(tp, b, tiles, th);
+    if (calls) {  // the builds with the function machine: tape_calls.cu
+        launch_tape_calls(PR, tp, b->slots, b->plane, b->bt_log2, b->first_assert_d, b->err_d, b->batch, tiles, th, bp, fused,
+                          b->stream);
     } else if (fused) {  // (the bit-plane build also runs tapes without a plane: they contain no plane operands)
         if (b->bt_log2 == 5) launch_tape_k<PR, false, true, 5, true>(tp, b, tiles, th);
         else launch_tape_k<PR, false, true, -1, true>(tp, b, tiles, th);
@@ -649,7 +651,8 @@ int cw_batch_run(cw_batch *b) {
         else if (t.F.prime_id == 1) launch_tape<1>(tp, b, tiles, th, calls, bp, fused);
         else {  // the other 256-bit primes: one build (bit-plane capable, runtime tile size), prime index from tp.prime
             if (fused) return fail(CW_ESTATE, "CW_FLAG_FUSE is available for bn128 and bls12381");
-            if (calls) launch_tape_k<-1, true, true, -1, false>(tp, b, tiles, th);
+            if (calls) launch_tape_calls(-1, tp, b->slots, b->plane, b->bt_log2, b->first_assert_d, b->err_d, b->batch, tiles, th,
+                                         true, false, b->stream);
             else launch_tape_k<-1, false, true, -1, false>(tp, b, tiles, th);
         }
     }

@@ -1292,8 +1292,8 @@ struct Lowerer {
             }
             std::vector<uint8_t> need(n_prov, 1);
             std::vector<uint32_t> gsize(n_prov, 1);
-            // (tapes with function calls keep one operator per work item: the call interpreter's build has no room for it)
-            const bool fuse_on = (flags & CW_FLAG_FUSE) && !(flags & CW_FLAG_NO_PEEPHOLE) && pcalls.empty();
+            // (a call is always a work item of its own: never a fused producer, never a reader with fused operands)
+            const bool fuse_on = (flags & CW_FLAG_FUSE) && !(flags & CW_FLAG_NO_PEEPHOLE);
             auto candidate = [&](uint32_t slot, size_t reader, int pos) -> bool {
                 if (!fuse_on || slot == NO_SLOT || (slot & OPERAND_CONST) || slot < n_pre) return false;
                 const size_t c = slot - n_pre;

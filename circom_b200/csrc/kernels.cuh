@@ -119,6 +119,9 @@ struct TapeDev {
     u32 vm_wide;               // 1: calls skip the 128-bit register machine (CW_VM_WIDE=1, for measurements)
 };
 
+// (tape_calls.cu compiles only the interpreter builds with the function machine - ptxas gives up on one module with all
+// builds - and defines CW_KERNELS_TAPE_ONLY: the non-template kernels must exist in one translation unit only)
+#ifndef CW_KERNELS_TAPE_ONLY
 // ---- inputs: inputs[batch][n_inputs][8 u32] canonical -> slots 1..n_inputs, slot 0 = 1 ----------
 __global__ void stage_inputs_kernel(TapeDev tp, const uint4 *__restrict__ inputs, uint4 *__restrict__ slots,
                                     u32 batch, u32 batch_padded, u32 bt_log2) {
@@ -140,6 +143,8 @@ __global__ void stage_inputs_kernel(TapeDev tp, const uint4 *__restrict__ inputs
     }
 }
 
+#endif  // CW_KERNELS_TAPE_ONLY
+
 // ---- the tape interpreter ---------------------------------------------------------------------
 // One CTA owns one tile of BT instances and walks the levels of the tape; within a level the work
 // items (op, instance) are spread over the CTA's threads, instance fastest.  Values produced in
@@ -149,7 +154,8 @@ __global__ void stage_inputs_kernel(TapeDev tp, const uint4 *__restrict__ inputs
 // is a broadcast; with BT = 1 a warp is 32 ops of one instance (small batches: lanes along ops).
 // A function call (circom `function` with run-time loops / branches): the thread copies the arguments into
 // the callee's registers (local memory: they are indexed dynamically) and interprets the body.
-template <int PRIME, bool BP>
+// (TAG: one copy of the function per interpreter build - ptxas 12.9 crashes on a module in which several kernels share it)
+template <int PRIME, bool BP, int TAG>
 __device__ __noinline__ void exec_call(const TapeDev &tp, u32 call_off, uint4 *base, const u32 *plane_base,
                                        u32 bt_log2, u32 li, u32 *r, int *err) {
     const FrParams &P = CW_FR(PRIME, tp.prime);
@@ -265,7 +271,7 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
             u32 r[8];
             if (HAS_CALLS && opcode == OP_CALL) {
                 int e = 0;
-                exec_call<PRIME, BP>(tp, opw.y, base, plane_base, bt_log2, li, r, &e);
+                exec_call<PRIME, BP, BT * 2 + (FUSED ? 1 : 0)>(tp, opw.y, base, plane_base, bt_log2, li, r, &e);
                 if (e && inst < batch) err[inst] = 1;
             } else if (opcode == OP_BITS && ((opw.w >> 16) & 0xFFu) <= 32u && !(opw.y & (OPD_CONST | OPD_BIT | OPD_ACC))) {
                 // narrow bit-field of a slot value: fetch only the one or two 32-bit words that hold it
@@ -373,6 +379,7 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
     }
 }
 
+#ifndef CW_KERNELS_TAPE_ONLY
 // ---- where the values of an instance live --------------------------------------------------------------
 // The tape's value store (tile layout, optional bit plane) or - for witnesses handed in by a caller - a dense
 // array of 32-byte rows (bt_log2 = 0, n_bitwords = 0, n_slots = row stride, location = wire id).
@@ -761,5 +768,7 @@ __global__ void fr_mul_bench_kernel(uint4 *__restrict__ data, size_t n, int iter
     data[2 * i] = make_uint4(x[0], x[1], x[2], x[3]);
     data[2 * i + 1] = make_uint4(x[4], x[5], x[6], x[7]);
 }
+
+#endif  // CW_KERNELS_TAPE_ONLY
 
 }  // namespace cw

@@ -271,7 +271,7 @@ def test_random_function_bodies_match_the_evaluator(seed):
     hs = hostsim()
     na, wi = ctypes.c_ulonglong(), ctypes.c_ulonglong()
     hs.hs_vm_counters(ctypes.byref(na), ctypes.byref(wi))
-    for flags in (0, 48):
+    for flags in (0, 48, 112):      # plain, compact store, compact + fused work items (calls stay items of their own)
         wit, st, _, w2s = hostsim_run(d, ok_ins, flags=flags)
         assert not st.any()
         for i, exp in enumerate(exps):

@@ -89,7 +89,7 @@ int ensure_device(int device) {
 
 struct DevTape {
     uint4 *ops = nullptr;
-    u32 *items = nullptr, *level_start = nullptr;
+    u32 *items = nullptr, *level_start = nullptr, *level_calls = nullptr;
     uint4 *heads = nullptr;  // first tape word of every work item
     uint4 *consts = nullptr;
     u32 *input_slot = nullptr, *fn_code = nullptr, *fn_info = nullptr, *call_tab = nullptr;
@@ -218,6 +218,21 @@ static int get_dev_tape(const cw_circuit *c, int device, DevTape &out) {
         if ((rc = upload(&d.heads, heads.data(), heads.size() * 4))) return rc;
     }
     if ((rc = upload(&d.level_start, t.level_start.data(), t.level_start.size() * 4))) return rc;
+    if (!t.call_tab.empty()) {
+        // calls close their level (the lowering sorts the items of a level by opcode, CALL is the largest): the kernel runs
+        // them after the other items
+        std::vector<uint32_t> lc(t.n_levels(), 0);
+        for (size_t l = 0; l < t.n_levels(); ++l) {
+            bool tail = true;
+            for (uint32_t k = t.level_start[l + 1]; k-- > t.level_start[l];) {
+                const bool is_call = (t.ops[(size_t)t.items[k] * 4] & 0xFFu) == 45u && t.items[k + 1] - t.items[k] == 1;
+                if (is_call && !tail) return fail(CW_ESTATE, "internal: a call is not at the end of its level");
+                if (is_call) ++lc[l];
+                else tail = false;
+            }
+        }
+        if ((rc = upload(&d.level_calls, lc.data(), lc.size() * 4))) return rc;
+    }
     if ((rc = upload(&d.consts, t.consts.data(), t.consts.size() * 32))) return rc;
     if ((rc = upload(&d.input_slot, t.input_slot.data(), t.input_slot.size() * 4))) return rc;
     if ((rc = upload(&d.fn_code, t.fn_code.data(), t.fn_code.size() * 4))) return rc;
@@ -306,6 +321,7 @@ void cw_circuit_destroy(cw_circuit *c) {
         cudaFree(kv.second.items);
         cudaFree(kv.second.heads);
         cudaFree(kv.second.level_start);
+        cudaFree(kv.second.level_calls);
         cudaFree(kv.second.consts);
         cudaFree(kv.second.input_slot);
         cudaFree(kv.second.fn_code);
@@ -622,6 +638,7 @@ int cw_batch_run(cw_batch *b) {
     tp.items = b->dt.items;
     tp.heads = b->dt.heads;
     tp.level_start = b->dt.level_start;
+    tp.level_calls = b->dt.level_calls;
     tp.consts = b->dt.consts;
     tp.n_levels = (u32)t.n_levels();
     tp.n_slots = t.n_slots;

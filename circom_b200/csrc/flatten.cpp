@@ -140,6 +140,85 @@ inline int subtree_need(uint32_t i, const std::vector<uint32_t> &kid_a, const st
     return std::max(std::max(na, nb), std::min(na, nb) + 1);
 }
 
+// ---- copy coalescing in function bodies ---------------------------------------------------------------------------
+// The producers write `x = e` as the expression into a temporary followed by a copy (the C++ producer's
+// `Fr_add(&expaux[0], ..); Fr_copy(&lvar[x], &expaux[0]);`): a quarter of the instructions an interpreted call executes.
+// When the temporary is written by the instruction just before the copy, dies with it, and no jump lands on the copy, the
+// expression writes its destination directly and the copy disappears.  Returns the new instruction count.
+static uint32_t coalesce_function_copies(uint32_t *code, uint32_t n_instr, uint32_t n_regs) {
+    constexpr uint32_t MAXR = 192;
+    if (n_regs > MAXR || n_instr < 2) return n_instr;
+    using Set = std::bitset<MAXR>;
+    enum { JMP = 40, JZ = 41, RET = 42, LOADX = 43, STOREX = 44, COPY = 24 };
+    auto is_reg = [&](uint32_t o) { return !(o & 0xC0000000u) && o < n_regs; };
+    Set pinned;
+    std::vector<uint8_t> target(n_instr + 1, 0);
+    for (uint32_t i = 0; i < n_instr; ++i) {
+        const uint32_t *w = &code[5 * (size_t)i];
+        uint32_t lo = 0, hi = 0;
+        if (w[0] == LOADX) { lo = w[2] & 0x3FFFFFFFu; hi = w[4] & 0x3FFFFFFFu; }
+        else if (w[0] == STOREX) { lo = w[2] & 0x3FFFFFFFu; hi = w[1] & 0x3FFFFFFFu; }
+        else if (w[0] == RET && (w[3] & 0x3FFFFFFFu) > 1) { lo = w[2]; hi = lo + (w[3] & 0x3FFFFFFFu); }
+        for (uint32_t r = lo; r < hi && r < n_regs; ++r) pinned.set(r);
+        if (w[0] == JMP) target[std::min(w[2] & 0x3FFFFFFFu, n_instr)] = 1;
+        if (w[0] == JZ) target[std::min(w[3] & 0x3FFFFFFFu, n_instr)] = 1;
+    }
+    // liveness of the scalars (as in allocate_function_registers)
+    std::vector<Set> use(n_instr), live_in(n_instr), live_out(n_instr);
+    std::vector<int> def(n_instr, -1);
+    auto add_use = [&](uint32_t i, uint32_t o) { if (is_reg(o) && !pinned.test(o)) use[i].set(o); };
+    for (uint32_t i = 0; i < n_instr; ++i) {
+        const uint32_t *w = &code[5 * (size_t)i];
+        switch (w[0]) {
+            case JMP: break;
+            case JZ: add_use(i, w[2]); break;
+            case RET: if ((w[3] & 0x3FFFFFFFu) <= 1) add_use(i, w[2]); break;
+            case LOADX: add_use(i, w[3]); if (!pinned.test(w[1])) def[i] = (int)w[1]; break;
+            case STOREX: add_use(i, w[3]); add_use(i, w[4]); break;
+            default: add_use(i, w[2]); add_use(i, w[3]); add_use(i, w[4]); if (!pinned.test(w[1])) def[i] = (int)w[1];
+        }
+    }
+    for (bool changed = true; changed;) {
+        changed = false;
+        for (uint32_t i = n_instr; i-- > 0;) {
+            const uint32_t *w = &code[5 * (size_t)i];
+            Set out;
+            if (w[0] == JMP) out = live_in[w[2] & 0x3FFFFFFFu];
+            else if (w[0] != RET) {
+                if (i + 1 < n_instr) out = live_in[i + 1];
+                if (w[0] == JZ) out |= live_in[w[3] & 0x3FFFFFFFu];
+            }
+            Set in = out;
+            if (def[i] >= 0) in.reset((size_t)def[i]);
+            in |= use[i];
+            if (in != live_in[i] || out != live_out[i]) { live_in[i] = in; live_out[i] = out; changed = true; }
+        }
+    }
+    std::vector<uint8_t> dead(n_instr, 0);
+    for (uint32_t i = 1; i < n_instr; ++i) {
+        uint32_t *c = &code[5 * (size_t)i], *p = &code[5 * (size_t)(i - 1)];
+        if (c[0] != COPY || target[i] || dead[i - 1]) continue;
+        const uint32_t t = c[2], d = c[1];
+        if (!is_reg(t) || pinned.test(t) || t == d || def[i - 1] != (int)t || live_out[i].test(t)) continue;
+        if (p[0] == JMP || p[0] == JZ || p[0] == RET || p[0] == STOREX) continue;   // (def[] is -1 for these anyway)
+        p[1] = d;      // the producer writes the destination of the copy
+        dead[i] = 1;
+    }
+    std::vector<uint32_t> newidx(n_instr + 1, 0);
+    uint32_t n = 0;
+    for (uint32_t i = 0; i < n_instr; ++i) { newidx[i] = n; n += !dead[i]; }
+    newidx[n_instr] = n;
+    if (n == n_instr) return n_instr;
+    for (uint32_t i = 0; i < n_instr; ++i) {
+        uint32_t *w = &code[5 * (size_t)i];
+        if (w[0] == JMP) w[2] = 0x40000000u | newidx[w[2] & 0x3FFFFFFFu];
+        if (w[0] == JZ) w[3] = 0x40000000u | newidx[w[3] & 0x3FFFFFFFu];
+    }
+    for (uint32_t i = 0; i < n_instr; ++i)
+        if (!dead[i] && newidx[i] != i) memmove(&code[5 * (size_t)newidx[i]], &code[5 * (size_t)i], 20);
+    return n;
+}
+
 // ---- register allocation for function bodies ---------------------------------------------------------------------
 // A compiler-written function body gives every expression temporary its own register (the `expaux` of the C++ producer) and
 // every variable its own slot; the interpreter keeps the registers of a call in the thread's local memory (32 bytes each,
@@ -1116,8 +1195,12 @@ struct Lowerer {
             }
             fn_min_ret.push_back(min_ret == 0xFFFFFFFFu ? 1 : min_ret);
             if (!(flags & CW_FLAG_NO_PEEPHOLE)) {
+                uint32_t *body = &T.fn_code[5 * (size_t)T.fn_info[4 * (size_t)i]];
+                const uint32_t kept = coalesce_function_copies(body, n_instr, n_regs);
+                T.fn_code.resize(5 * ((size_t)T.fn_info[4 * (size_t)i] + kept));   // (this function's code is the tail of fn_code)
+                T.fn_info[4 * (size_t)i + 1] = kept;
                 uint32_t packed = n_regs;
-                allocate_function_registers(&T.fn_code[5 * (size_t)T.fn_info[4 * (size_t)i]], n_instr, n_params, packed);
+                allocate_function_registers(&T.fn_code[5 * (size_t)T.fn_info[4 * (size_t)i]], kept, n_params, packed);
                 T.fn_info[4 * (size_t)i + 2] = packed;
             }
         }
@@ -1292,8 +1375,10 @@ struct Lowerer {
             }
             std::vector<uint8_t> need(n_prov, 1);
             std::vector<uint32_t> gsize(n_prov, 1);
-            // (a call is always a work item of its own: never a fused producer, never a reader with fused operands)
-            const bool fuse_on = (flags & CW_FLAG_FUSE) && !(flags & CW_FLAG_NO_PEEPHOLE);
+            // (tapes with function calls keep one operator per work item: with the function machine in the build the fused
+            // interpreter spills - measured 169.7 ms against 153.6 ms per 18,944 instances of the bench circuit with hints
+            // computed by functions)
+            const bool fuse_on = (flags & CW_FLAG_FUSE) && !(flags & CW_FLAG_NO_PEEPHOLE) && pcalls.empty();
             auto candidate = [&](uint32_t slot, size_t reader, int pos) -> bool {
                 if (!fuse_on || slot == NO_SLOT || (slot & OPERAND_CONST) || slot < n_pre) return false;
                 const size_t c = slot - n_pre;

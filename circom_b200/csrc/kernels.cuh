@@ -111,6 +111,7 @@ struct TapeDev {
     const u32 *fn_code;        // register-machine code of the circuit's functions (5 words per instruction)
     const u32 *fn_info;        // per function {code offset, n_instr, n_regs, n_params}
     const u32 *call_tab;       // per call {function, n_args, arg operands..., n_extra, slots of results 1..n_extra}
+    const u32 *level_calls;    // per level: how many of its LAST work items are calls (tapes with calls; else null)
     u32 n_levels;
     u32 n_slots;
     u32 n_inputs;
@@ -239,7 +240,11 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
         } else pre = __ldg(&tp.ops[lb + (threadIdx.x >> bt_log2)]);
     }
     for (u32 l = 0; l < tp.n_levels; ++l) {
-        const u32 n = (le - lb) << bt_log2;
+        // Calls are the last work items of their level (the items of a level are sorted by opcode, CALL is the largest) and
+        // run in a loop of their own after the others: the call site - an ABI call with a 6 KB frame - then does not sit
+        // in the hot loop, whose values would otherwise have to survive it in memory.
+        const u32 n_calls = HAS_CALLS ? __ldg(&tp.level_calls[l]) : 0u;
+        const u32 n = (le - lb - n_calls) << bt_log2;
         const u32 le_next = (l + 1 < tp.n_levels) ? tp.level_start[l + 2] : le;
         // COOP (one instance per CTA): the warp walks the level together - lanes beyond the level's end idle in
         // the body - so that the bit runs of its lanes can be stored cooperatively afterwards
@@ -269,11 +274,7 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
             if (FUSED && k + 1 < g1) nxt = __ldg(&tp.ops[k + 1]);   // the next word of the item travels while this one executes
             const u32 opcode = opw.x & 0xFFu, dst = opw.x >> 8;
             u32 r[8];
-            if (HAS_CALLS && opcode == OP_CALL) {
-                int e = 0;
-                exec_call<PRIME, BP, BT * 2 + (FUSED ? 1 : 0)>(tp, opw.y, base, plane_base, bt_log2, li, r, &e);
-                if (e && inst < batch) err[inst] = 1;
-            } else if (opcode == OP_BITS && ((opw.w >> 16) & 0xFFu) <= 32u && !(opw.y & (OPD_CONST | OPD_BIT | OPD_ACC))) {
+            if (opcode == OP_BITS && ((opw.w >> 16) & 0xFFu) <= 32u && !(opw.y & (OPD_CONST | OPD_BIT | OPD_ACC))) {
                 // narrow bit-field of a slot value: fetch only the one or two 32-bit words that hold it
                 const u32 kk = opw.w & 0xFFFFu, m = (opw.w >> 16) & 0xFFu, run = (opw.w >> 24) + 1u;
                 const u32 wd = kk >> 5, sh = kk & 31u;
@@ -364,6 +365,19 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
                         stg256(base + ((size_t)(d + lane) << 1), r);
                     }
                 }
+            }
+        }
+        if (HAS_CALLS && n_calls) {
+            const u32 cb = le - n_calls;   // (a call is a work item of one word: item k is tape word items[k])
+            for (u32 w = threadIdx.x; w < (n_calls << bt_log2); w += blockDim.x) {
+                const u32 li = w & bt_mask;
+                const u32 inst = (tile << bt_log2) + li;
+                const uint4 opw = __ldg(&tp.ops[FUSED ? __ldg(&tp.items[cb + (w >> bt_log2)]) : cb + (w >> bt_log2)]);
+                u32 r[8];
+                int e = 0;
+                exec_call<PRIME, BP, BT * 2 + (FUSED ? 1 : 0)>(tp, opw.y, base, plane_base, bt_log2, li, r, &e);
+                if (e && inst < batch) err[inst] = 1;
+                store_slot(r, base, opw.x >> 8, bt_log2, li);
             }
         }
         if (threadIdx.x < ((le_next - le) << bt_log2)) {

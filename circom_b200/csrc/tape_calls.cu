@@ -12,16 +12,14 @@ static void launch_k(const TapeDev &tp, uint4 *slots, u32 *plane, u32 bt_log2, u
     tape_exec_kernel<PR, true, BP, BT, FU><<<tiles, threads, 0, stream>>>(tp, slots, plane, bt_log2, first_assert, err, batch);
 }
 
-// warp-per-op tiles with a bit plane - the large-batch layout - get the specialised builds (tile size at compile time,
-// fused work items) also with calls; everything else runs the builds that take the tile size as an argument
+// warp-per-op tiles with a bit plane - the large-batch layout - get the build with the tile size fixed at compile time also
+// with calls; everything else runs the builds that take the tile size as an argument
 template <int PR>
 static void launch_pr(const TapeDev &tp, uint4 *slots, u32 *plane, u32 bt_log2, u32 *first_assert, int *err, u32 batch,
                       u32 tiles, u32 threads, bool bp, bool fused, cudaStream_t stream) {
 #define CW_ARGS tp, slots, plane, bt_log2, first_assert, err, batch, tiles, threads, stream
-    if (fused) {
-        if (bt_log2 == 5) launch_k<PR, true, 5, true>(CW_ARGS);
-        else launch_k<PR, true, -1, true>(CW_ARGS);
-    } else if (bp) {
+    (void)fused;   // (the lowering does not fuse tapes with calls: measured slower, flatten.cpp)
+    if (bp) {
         if (bt_log2 == 5) launch_k<PR, true, 5, false>(CW_ARGS);
         else launch_k<PR, true, -1, false>(CW_ARGS);
     } else launch_k<PR, false, -1, false>(CW_ARGS);

@@ -286,6 +286,16 @@ int hs_check_levels(const uint8_t *cb2c, size_t len, uint32_t flags) {
             read_stamp[o] = L;
             return 0;
         };
+        // calls close their level (the kernel runs them in a loop of their own after the other work items)
+        {
+            bool seen_call = false;
+            for (uint32_t item = t.level_start[l]; item < t.level_start[l + 1]; ++item) {
+                const bool is_call = (t.ops[(size_t)t.items[item] * 4] & 0xFFu) == OP_CALL;
+                if (is_call && t.items[item + 1] - t.items[item] != 1) { g_err = "a call shares its work item"; return -19; }
+                if (!is_call && seen_call) { g_err = "a call is not at the end of its level"; return -19; }
+                seen_call |= is_call;
+            }
+        }
         // reads of the level (definitions so far are all from earlier levels)
         // accumulator discipline inside a work item: written before read, only the last word writes the store
         for (uint32_t item = t.level_start[l]; item < t.level_start[l + 1]; ++item) {

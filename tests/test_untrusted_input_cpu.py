@@ -272,7 +272,8 @@ def test_lowered_blob_roundtrip_and_damage():
     """the lowered-circuit blob (cw_circuit_serialize / _deserialize: what one rank broadcasts to the others): exact
     round trip; truncated or corrupted blobs are refused or load consistently, never crash"""
     rng = random.Random(99)
-    for mk in (lambda d: C.int_div(d, 32), lambda d: C.num2bits(d, 40), lambda d: C.all_ops(d)):
+    for mk in (lambda d: C.int_div(d, 32), lambda d: C.num2bits(d, 40), lambda d: C.all_ops(d),
+               lambda d: C.int_div_array(d, 16, "all")):       # (a call with several results: destinations in the call table)
         d = CircuitDesc("bn128")
         d.set_main(mk(d))
         c = Circuit(d, host_only=True)

@@ -113,12 +113,26 @@ def limbs_to_ints(a: np.ndarray) -> List[int]:
     return [int.from_bytes(row.tobytes(), "little") for row in a]
 
 
-def aligned_empty(shape, dtype=np.uint64, align: int = 64) -> np.ndarray:
+def aligned_empty(shape, dtype=np.uint64, align: int = 64, hugepages: Optional[bool] = None) -> np.ndarray:
     """numpy array whose data starts on an `align`-byte boundary: witness rows written into a 64-byte aligned buffer
-    take full-cache-line streaming stores in the host-side expansion (numpy's own allocations are 16-byte aligned)"""
+    take full-cache-line streaming stores in the host-side expansion (numpy's own allocations are 16-byte aligned).
+    hugepages (or CW_HUGEPAGES=1): align to 2 MB and advise the kernel to back the buffer with huge pages before its first
+    touch.  Measured on the bench (24 GB row buffers, 16 expansion threads): 6.68 / 6.70 k witnesses/s with, 6.94 / 6.47 k
+    without - no effect, the streaming stores are bandwidth-bound, so it stays opt-in."""
     n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    if hugepages is None:
+        hugepages = n >= (64 << 20) and os.environ.get("CW_HUGEPAGES", "0") == "1"
+    if hugepages:
+        align = max(align, 2 << 20)
     raw = np.empty(n + align, dtype=np.uint8)
     off = (-raw.ctypes.data) % align
+    if hugepages:
+        try:
+            libc = ctypes.CDLL(None, use_errno=True)
+            libc.madvise.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+            libc.madvise(ctypes.c_void_p(raw.ctypes.data + off), ctypes.c_size_t(n & ~((2 << 20) - 1)), 14)   # MADV_HUGEPAGE
+        except (OSError, AttributeError):
+            pass      # advice only
     return raw[off:off + n].view(dtype).reshape(shape)
 
 

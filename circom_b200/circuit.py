@@ -565,6 +565,24 @@ class Function:
             op, d, _a, b, c = self.code[pcs[1]]
             self.code[pcs[1]] = (op, d, (K_NONE, 0, len(self.code)), b, c)
 
+    def call(self, fn: "Function", args: Sequence) -> FReg:
+        """`x = g(args...)` inside a function body: g must be an earlier (finalized) function"""
+        return self.call_array(fn, args, 1)[0]
+
+    def call_array(self, fn: "Function", args: Sequence, n: int) -> List[FReg]:
+        """`var r[n] = g(args...)`: the arguments are copied into consecutive fresh registers (the callee's parameters, as the
+        C++ producer fills `lvarcall`), the n results land in n consecutive registers"""
+        assert fn.id >= 0 and len(args) == fn.n_params and 1 <= n <= fn.n_results, "bad call of %s" % fn.name
+        base = self.n_regs
+        self.n_regs += fn.n_params
+        for k, a in enumerate(args):
+            self.set(FReg(self, base + k), a)
+        d = self.n_regs
+        self.n_regs += n
+        self.code.append((OPS["CALL"], (K_TMP, 0, d), (K_NONE, 0, fn.id), (K_TMP, 0, base) if fn.n_params else NONE_REF,
+                          (K_NONE, 0, n if n > 1 else 0)))
+        return [FReg(self, d + k) for k in range(n)]
+
     def ret(self, value) -> None:
         self.code.append((OPS["RET"], NONE_REF, self._operand(value), NONE_REF, NONE_REF))
 

@@ -168,3 +168,46 @@ def int_div_array(d: CircuitDesc, nbits: int = 32, use: str = "all") -> Template
         cr = t.component("rr", n2b)
         t.assign_constrained(cr["in"], r)
     return d.template("IntDivArr_" + use, (nbits,), build)
+
+
+def fn_gcd(d: CircuitDesc) -> Function:
+    """function gcd(a, b) { while (b != 0) { var qr[3] = divmod_arr(a, b); a = b; b = qr[1]; } return a; } - a function
+    that calls another one (with an array result) inside a loop whose trip count depends on the data, the way
+    circom-ecdsa's bigint functions are built from `long_div` / `short_div` / `long_sub`"""
+    fdiv = fn_divmod_array(d, 64)
+    fbl = fn_bit_length(d)
+
+    def build(f: Function):
+        a = f.var(f.param(0))
+        b = f.var(f.param(1))
+        steps = f.var(0)
+        f.loop_begin()
+        f.loop_break_if_zero(b.neq(0))
+        qr = f.call_array(fdiv, [a, b], 3)
+        f.set(a, b)
+        f.set(b, qr[1])
+        f.set(steps, steps + f.call(fbl, [qr[0]]))      # a second callee, scalar result
+        f.loop_end()
+        out = f.array(2)
+        f.store(out, f.var(0), a)
+        f.store(out, f.var(1), steps)
+        f.ret_array(out, 2)
+    return d.function("gcd", 2, build)
+
+
+def gcd_circuit(d: CircuitDesc, nbits: int = 32) -> Template:
+    """g = gcd(a, b) as a hint (two levels of function calls), constrained only by range checks: a test of the call path"""
+    fg = fn_gcd(d)
+    n2b = num2bits(d, nbits)
+
+    def build(t: Template):
+        a = t.input("a")
+        b = t.input("b")
+        g = t.output("g")
+        s = t.output("steps")
+        res = t.call_array(fg, [a, b], 2)
+        t.assign(g, res[0])
+        t.assign(s, res[1])
+        c = t.component("rg", n2b)
+        t.assign_constrained(c["in"], g)
+    return d.template("Gcd", (nbits,), build)

@@ -145,11 +145,11 @@ inline int subtree_need(uint32_t i, const std::vector<uint32_t> &kid_a, const st
 // `Fr_add(&expaux[0], ..); Fr_copy(&lvar[x], &expaux[0]);`): a quarter of the instructions an interpreted call executes.
 // When the temporary is written by the instruction just before the copy, dies with it, and no jump lands on the copy, the
 // expression writes its destination directly and the copy disappears.  Returns the new instruction count.
-static uint32_t coalesce_function_copies(uint32_t *code, uint32_t n_instr, uint32_t n_regs) {
+static uint32_t coalesce_function_copies(uint32_t *code, uint32_t n_instr, uint32_t n_regs, const std::vector<uint32_t> &fn_params) {
     constexpr uint32_t MAXR = 192;
     if (n_regs > MAXR || n_instr < 2) return n_instr;
     using Set = std::bitset<MAXR>;
-    enum { JMP = 40, JZ = 41, RET = 42, LOADX = 43, STOREX = 44, COPY = 24 };
+    enum { JMP = 40, JZ = 41, RET = 42, LOADX = 43, STOREX = 44, CALLF = 45, COPY = 24 };
     auto is_reg = [&](uint32_t o) { return !(o & 0xC0000000u) && o < n_regs; };
     Set pinned;
     std::vector<uint8_t> target(n_instr + 1, 0);
@@ -159,6 +159,10 @@ static uint32_t coalesce_function_copies(uint32_t *code, uint32_t n_instr, uint3
         if (w[0] == LOADX) { lo = w[2] & 0x3FFFFFFFu; hi = w[4] & 0x3FFFFFFFu; }
         else if (w[0] == STOREX) { lo = w[2] & 0x3FFFFFFFu; hi = w[1] & 0x3FFFFFFFu; }
         else if (w[0] == RET && (w[3] & 0x3FFFFFFFu) > 1) { lo = w[2]; hi = lo + (w[3] & 0x3FFFFFFFu); }
+        else if (w[0] == CALLF) {   // the argument registers are one block; several results too
+            for (uint32_t r = w[3]; r < w[3] + fn_params[w[2] & 0x3FFFFFFFu] && r < n_regs; ++r) pinned.set(r);
+            if ((w[4] & 0x3FFFFFFFu) > 1) { lo = w[1]; hi = lo + (w[4] & 0x3FFFFFFFu); }
+        }
         for (uint32_t r = lo; r < hi && r < n_regs; ++r) pinned.set(r);
         if (w[0] == JMP) target[std::min(w[2] & 0x3FFFFFFFu, n_instr)] = 1;
         if (w[0] == JZ) target[std::min(w[3] & 0x3FFFFFFFu, n_instr)] = 1;
@@ -175,6 +179,7 @@ static uint32_t coalesce_function_copies(uint32_t *code, uint32_t n_instr, uint3
             case RET: if ((w[3] & 0x3FFFFFFFu) <= 1) add_use(i, w[2]); break;
             case LOADX: add_use(i, w[3]); if (!pinned.test(w[1])) def[i] = (int)w[1]; break;
             case STOREX: add_use(i, w[3]); add_use(i, w[4]); break;
+            case CALLF: if (!pinned.test(w[1])) def[i] = (int)w[1]; break;   // (arguments: pinned registers)
             default: add_use(i, w[2]); add_use(i, w[3]); add_use(i, w[4]); if (!pinned.test(w[1])) def[i] = (int)w[1];
         }
     }
@@ -229,12 +234,13 @@ static uint32_t coalesce_function_copies(uint32_t *code, uint32_t n_instr, uint3
 // Parameters keep their registers (the caller stores the arguments there); a dead parameter's register is reused.
 // Registers read before they are written rely on the zero-initialised frame: they stay live from the entry and may not
 // share a register with a parameter.
-static void allocate_function_registers(uint32_t *code, uint32_t n_instr, uint32_t n_params, uint32_t &n_regs) {
+static void allocate_function_registers(uint32_t *code, uint32_t n_instr, uint32_t n_params, uint32_t &n_regs,
+                                        const std::vector<uint32_t> &fn_params) {
     constexpr uint32_t MAXR = 192;
     if (n_regs > MAXR || n_regs == 0 || n_instr == 0) return;
     using Set = std::bitset<MAXR>;
     auto is_reg = [](uint32_t o) { return !(o & 0xC0000000u); };
-    enum { JMP = 40, JZ = 41, RET = 42, LOADX = 43, STOREX = 44 };
+    enum { JMP = 40, JZ = 41, RET = 42, LOADX = 43, STOREX = 44, CALLF = 45 };
     // registers reachable through a run-time index
     Set pinned;
     for (uint32_t i = 0; i < n_instr; ++i) {
@@ -243,6 +249,10 @@ static void allocate_function_registers(uint32_t *code, uint32_t n_instr, uint32
         if (w[0] == LOADX) { lo = w[2] & 0x3FFFFFFFu; hi = w[4] & 0x3FFFFFFFu; }
         else if (w[0] == STOREX) { lo = w[2] & 0x3FFFFFFFu; hi = w[1] & 0x3FFFFFFFu; }
         else if (w[0] == RET && (w[3] & 0x3FFFFFFFu) > 1) { lo = w[2]; hi = lo + (w[3] & 0x3FFFFFFFu); }
+        else if (w[0] == CALLF) {   // the argument registers are one block; several results too
+            for (uint32_t r = w[3]; r < w[3] + fn_params[w[2] & 0x3FFFFFFFu] && r < n_regs; ++r) pinned.set(r);
+            if ((w[4] & 0x3FFFFFFFu) > 1) { lo = w[1]; hi = lo + (w[4] & 0x3FFFFFFFu); }
+        }
         for (uint32_t r = lo; r < hi && r < n_regs; ++r) pinned.set(r);
     }
     // per instruction: registers read / the register written, scalars only
@@ -257,6 +267,7 @@ static void allocate_function_registers(uint32_t *code, uint32_t n_instr, uint32
             case RET: if ((w[3] & 0x3FFFFFFFu) <= 1) add_use(i, w[2]); break;
             case LOADX: add_use(i, w[3]); if (!pinned.test(w[1])) def[i] = (int)w[1]; break;
             case STOREX: add_use(i, w[3]); add_use(i, w[4]); break;
+            case CALLF: if (!pinned.test(w[1])) def[i] = (int)w[1]; break;   // (arguments: pinned registers)
             default: add_use(i, w[2]); add_use(i, w[3]); add_use(i, w[4]); if (!pinned.test(w[1])) def[i] = (int)w[1];
         }
     }
@@ -343,6 +354,7 @@ static void allocate_function_registers(uint32_t *code, uint32_t n_instr, uint32
                 else { w[3] = m(w[3]); w[4] = m(w[4]); w[1] = 0x40000000u | nl; }
                 break;
             }
+            case CALLF: w[1] = m(w[1]); if (fn_params[w[2] & 0x3FFFFFFFu]) w[3] = m(w[3]); break;
             default: w[1] = m(w[1]); w[2] = m(w[2]); w[3] = m(w[3]); w[4] = m(w[4]);
         }
     }
@@ -361,6 +373,7 @@ struct Lowerer {
     std::vector<uint32_t> pops;  // 4 words per op
     std::vector<uint32_t> pcalls;  // provisional call table: {function, n_args, arg operands..., n_extra, provisional slots of results 1..}
     std::vector<uint32_t> fn_min_ret;  // per function: the fewest values any of its RETs returns
+    std::vector<uint32_t> fn_stack_regs, fn_stack_depth;  // per function: registers / frames of its deepest chain of calls
     std::vector<uint32_t> plevel;
     std::vector<uint32_t> slot_level;  // per provisional slot
     // constant table (raw patterns)
@@ -1132,6 +1145,7 @@ struct Lowerer {
             T.fn_info.push_back(n_regs);
             T.fn_info.push_back(n_params);
             uint32_t min_ret = 0xFFFFFFFFu;
+            std::vector<uint32_t> callees;
             auto bad = [&](const char *what) { throw std::runtime_error(std::string("cb2c: function body: ") + what); };
             auto reg = [&](uint64_t w) -> uint32_t {   // a register
                 if (rk(w) != K_TMP || ridx(w) >= n_regs) bad("bad register");
@@ -1183,6 +1197,22 @@ struct Lowerer {
                         e[0] = 0x40000000u | (ext ? base + ext : n_regs);
                         break;
                     }
+                    case 45 /* CALL of an earlier function: d <- f(registers b .. b + n_params - 1); c = result count */: {
+                        if (rk(w[2]) != K_NONE || ridx(w[2]) >= i) bad("a function may only call functions with a smaller index");
+                        const uint32_t f = ridx(w[2]), np = T.fn_info[4 * (size_t)f + 3];
+                        const uint32_t want = rk(w[4]) == K_NONE && ridx(w[4]) > 1 ? ridx(w[4]) : 1;
+                        if (rk(w[4]) != K_NONE || want > 64 || want > fn_min_ret[f]) bad("bad result count of a call");
+                        e[0] = reg(w[1]);
+                        if ((uint64_t)e[0] + want > n_regs) bad("call results run past the registers");
+                        if (np) {
+                            if (rk(w[3]) != K_TMP || (uint64_t)ridx(w[3]) + np > n_regs) bad("bad argument registers of a call");
+                            e[2] = ridx(w[3]);
+                        } else e[2] = 0;
+                        e[1] = 0x40000000u | f;
+                        e[3] = 0x40000000u | want;
+                        callees.push_back(f);
+                        break;
+                    }
                     default:
                         if (op < CW_OP_MUL || op > CW_OP_INV || op == CW_OP_ASSERT || op == CW_OP_ASSERT_EQ) bad("unknown opcode");
                         e[0] = reg(w[1]);
@@ -1196,13 +1226,25 @@ struct Lowerer {
             fn_min_ret.push_back(min_ret == 0xFFFFFFFFu ? 1 : min_ret);
             if (!(flags & CW_FLAG_NO_PEEPHOLE)) {
                 uint32_t *body = &T.fn_code[5 * (size_t)T.fn_info[4 * (size_t)i]];
-                const uint32_t kept = coalesce_function_copies(body, n_instr, n_regs);
+                std::vector<uint32_t> fn_params;   // parameters of the functions defined so far (callees)
+                for (size_t f = 0; f + 1 <= (size_t)i; ++f) fn_params.push_back(T.fn_info[4 * f + 3]);
+                const uint32_t kept = coalesce_function_copies(body, n_instr, n_regs, fn_params);
                 T.fn_code.resize(5 * ((size_t)T.fn_info[4 * (size_t)i] + kept));   // (this function's code is the tail of fn_code)
                 T.fn_info[4 * (size_t)i + 1] = kept;
                 uint32_t packed = n_regs;
-                allocate_function_registers(&T.fn_code[5 * (size_t)T.fn_info[4 * (size_t)i]], kept, n_params, packed);
+                allocate_function_registers(&T.fn_code[5 * (size_t)T.fn_info[4 * (size_t)i]], kept, n_params, packed, fn_params);
                 T.fn_info[4 * (size_t)i + 2] = packed;
             }
+            // the deepest chain of nested calls below this function: registers and frames the interpreter needs
+            uint32_t below_regs = 0, below_depth = 0;
+            for (uint32_t f : callees) {
+                below_regs = std::max(below_regs, fn_stack_regs[f]);
+                below_depth = std::max(below_depth, fn_stack_depth[f]);
+            }
+            fn_stack_regs.push_back(T.fn_info[4 * (size_t)i + 2] + below_regs);
+            fn_stack_depth.push_back(1 + below_depth);
+            if (fn_stack_regs.back() > 192 || fn_stack_depth.back() > 9)   // (VM_MAX_REGS, VM_MAX_DEPTH + 1 of fr_device.cuh)
+                throw std::runtime_error("cb2c: nested function calls need too many registers / frames");
         }
         // optional symbols section: "SYMS", then per template the names of its own signals and of its sub-components
         // (what the reference keeps in the DAG for sym_porting.rs).  Anything else after the functions is refused.

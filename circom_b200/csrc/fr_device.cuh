@@ -636,9 +636,25 @@ CW_HD void fr_apply_canonical(u32 op, u32 *r, const u32 *a, const u32 *b, const 
 // whose thread interprets the body over private registers.  Instruction = 5 words {op, d, a, b, c};
 // operand: bit31 = constant-table index, bit30 = immediate, else register index.
 enum { FOP_JMP = 40, FOP_JZ = 41, FOP_RET = 42, FOP_LOADX = 43, FOP_STOREX = 44, OP_CALL = 45 };
-enum { VM_MAX_REGS = 192, VM_MAX_STEPS = 1 << 22 };
+enum { VM_MAX_REGS = 192, VM_MAX_STEPS = 1 << 22, VM_MAX_DEPTH = 8 };
 struct FnInfo {
     u32 code_off, n_instr, n_regs, n_params;
+};
+CW_HD FnInfo vm_fn(const u32 *fn_info, u32 f) {
+    FnInfo fi;
+    fi.code_off = fn_info[4 * (size_t)f];
+    fi.n_instr = fn_info[4 * (size_t)f + 1];
+    fi.n_regs = fn_info[4 * (size_t)f + 2];
+    fi.n_params = fn_info[4 * (size_t)f + 3];
+    return fi;
+}
+// A function may call functions with a smaller index (`CALL` inside a body: {45, d, function, first argument register,
+// result count}; the callee's parameters are the caller's registers b .. b + n_params - 1, as the C++ producer fills
+// `lvarcall`, call_bucket.rs:466-533).  Frames are stacked in the one register array of the call: the callee's frame
+// starts behind the caller's.  The lowering checked at load time that the deepest chain of calls needs at most
+// VM_MAX_REGS registers and VM_MAX_DEPTH frames (callee index < caller index: no recursion), so nothing is checked here.
+struct VmFrame {
+    u32 fn, pc, base, dst, want;
 };
 
 CW_HD void vm_operand(u32 *v, u32 o, const u32 *regs, const u32 *consts32) {
@@ -666,9 +682,13 @@ CW_HD int vm_index(const u32 *v, u32 base, u32 limit) {
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-inline void vm_run(const u32 *code, FnInfo fi, u32 *regs, const u32 *consts32, u32 *result, const FrParams &P, int &err,
-                   u32 &ret_base, u32 &ret_cnt) {
+inline void vm_run(const u32 *code, const u32 *fn_info, u32 fn, u32 *regs, const u32 *consts32, u32 *result, const FrParams &P,
+                   int &err, u32 &ret_base, u32 &ret_cnt) {
+    FnInfo fi = vm_fn(fn_info, fn);
     const u32 *ins = code + 5 * (size_t)fi.code_off;
+    u32 *fr = regs;          // registers of the running frame
+    u32 base = 0, depth = 0;
+    VmFrame stack[VM_MAX_DEPTH];
     u32 pc = 0;
     u256_set_u32(result, 0);
     ret_base = 0;
@@ -679,32 +699,61 @@ inline void vm_run(const u32 *code, FnInfo fi, u32 *regs, const u32 *consts32, u
         ++pc;
         u32 va[8], vb[8], vc[8], r[8];
         if (op == FOP_JMP) { pc = a & 0x3FFFFFFFu; continue; }
-        vm_operand(va, a, regs, consts32);
+        if (op == OP_CALL) {   // a nested call: new frame behind this one, arguments copied, the rest zero
+            const u32 f = a & 0x3FFFFFFFu;
+            const FnInfo callee = vm_fn(fn_info, f);
+            const u32 nb = base + fi.n_regs;
+            if (depth >= (u32)VM_MAX_DEPTH || nb + callee.n_regs > (u32)VM_MAX_REGS) { err = 2; return; }
+            u32 *nf = regs + 8 * (size_t)nb;
+            for (u32 k = 0; k < callee.n_params * 8; ++k) nf[k] = fr[8 * (size_t)b + k];
+            for (u32 k = callee.n_params * 8; k < callee.n_regs * 8; ++k) nf[k] = 0;
+            stack[depth].fn = fn; stack[depth].pc = pc; stack[depth].base = base; stack[depth].dst = d;
+            stack[depth].want = c & 0x3FFFFFFFu;
+            ++depth;
+            fn = f; fi = callee; ins = code + 5 * (size_t)fi.code_off; base = nb; fr = nf; pc = 0;
+            continue;
+        }
+        vm_operand(va, a, fr, consts32);
         if (op == FOP_JZ) { if (u256_is_zero(va)) pc = b & 0x3FFFFFFFu; continue; }
         if (op == FOP_RET) {
-            u256_set(result, va);
-            ret_cnt = b & 0x3FFFFFFFu;
-            if (ret_cnt > 1) ret_base = a;   // (the lowering checked: a register, a + count <= n_regs)
-            return;
+            const u32 cnt = b & 0x3FFFFFFFu;
+            if (depth == 0) {
+                u256_set(result, va);
+                ret_cnt = cnt;
+                if (ret_cnt > 1) ret_base = a;   // (the lowering checked: a register, a + count <= n_regs)
+                return;
+            }
+            --depth;
+            const VmFrame &top = stack[depth];
+            u32 *cf = regs + 8 * (size_t)top.base;   // the caller's registers
+            const u32 want = top.want > 1 ? top.want : 1u;
+            if (want > 1 && cnt < want) { err = 2; return; }
+            if (cnt > 1) {
+                for (u32 k = 0; k < want * 8; ++k) cf[8 * (size_t)top.dst + k] = fr[8 * (size_t)a + k];
+            } else {
+                for (int k = 0; k < 8; ++k) cf[8 * (size_t)top.dst + k] = va[k];
+            }
+            fn = top.fn; fi = vm_fn(fn_info, fn); ins = code + 5 * (size_t)fi.code_off; base = top.base; fr = cf; pc = top.pc;
+            continue;
         }
-        vm_operand(vb, b, regs, consts32);
+        vm_operand(vb, b, fr, consts32);
         if (op == FOP_LOADX) {
             int i = vm_index(vb, a & 0x3FFFFFFFu, c & 0x3FFFFFFFu);
             if (i < 0) { err = 2; return; }
-            for (int k = 0; k < 8; ++k) regs[8 * (size_t)d + k] = regs[8 * (size_t)i + k];
+            for (int k = 0; k < 8; ++k) fr[8 * (size_t)d + k] = fr[8 * (size_t)i + k];
             continue;
         }
-        vm_operand(vc, c, regs, consts32);
+        vm_operand(vc, c, fr, consts32);
         if (op == FOP_STOREX) {
             int i = vm_index(vb, a & 0x3FFFFFFFu, d & 0x3FFFFFFFu);
             if (i < 0) { err = 2; return; }
-            for (int k = 0; k < 8; ++k) regs[8 * (size_t)i + k] = vc[k];
+            for (int k = 0; k < 8; ++k) fr[8 * (size_t)i + k] = vc[k];
             continue;
         }
         int e = 0;
         fr_apply_canonical(op, r, va, vb, vc, P, e);
         if (e) err = 1;
-        for (int k = 0; k < 8; ++k) regs[8 * (size_t)d + k] = r[k];
+        for (int k = 0; k < 8; ++k) fr[8 * (size_t)d + k] = r[k];
     }
     err = 2;
 }
@@ -833,8 +882,9 @@ CW_HD bool vmn_apply(u32 op, N128 &r, const N128 &a, const N128 &b, const N128 &
 #if defined(__CUDACC__)
 __host__ __device__
 #endif
-inline bool vm_run_narrow(const u32 *code, FnInfo fi, u32 *regs, const u32 *consts32, u32 *result, int &err, u32 &ret_base,
-                          u32 &ret_cnt) {
+inline bool vm_run_narrow(const u32 *code, const u32 *fn_info, u32 fn, u32 *regs, const u32 *consts32, u32 *result, int &err,
+                          u32 &ret_base, u32 &ret_cnt) {
+    FnInfo fi = vm_fn(fn_info, fn);
     for (u32 k = 0; k < fi.n_params; ++k) {
         const u32 *p = regs + 8 * (size_t)k;
         if (p[4] | p[5] | p[6] | p[7]) return false;
@@ -843,6 +893,9 @@ inline bool vm_run_narrow(const u32 *code, FnInfo fi, u32 *regs, const u32 *cons
         for (int j = 0; j < 4; ++j) regs[4 * (size_t)k + j] = regs[8 * (size_t)k + j];
     for (u32 k = 4 * fi.n_params; k < 4 * fi.n_regs; ++k) regs[k] = 0;
     const u32 *ins = code + 5 * (size_t)fi.code_off;
+    u32 *fr = regs;
+    u32 base = 0, depth = 0;
+    VmFrame stack[VM_MAX_DEPTH];
     u32 pc = 0;
     u256_set_u32(result, 0);
     ret_base = 0;
@@ -852,31 +905,58 @@ inline bool vm_run_narrow(const u32 *code, FnInfo fi, u32 *regs, const u32 *cons
         const u32 op = ins[5 * pc], d = ins[5 * pc + 1], a = ins[5 * pc + 2], b = ins[5 * pc + 3], c = ins[5 * pc + 4];
         ++pc;
         if (op == FOP_JMP) { pc = a & 0x3FFFFFFFu; continue; }
+        if (op == OP_CALL) {
+            const u32 f = a & 0x3FFFFFFFu;
+            const FnInfo callee = vm_fn(fn_info, f);
+            const u32 nb = base + fi.n_regs;
+            if (depth >= (u32)VM_MAX_DEPTH || nb + callee.n_regs > (u32)VM_MAX_REGS) { err = 2; return true; }
+            u32 *nf = regs + 4 * (size_t)nb;
+            for (u32 k = 0; k < callee.n_params * 4; ++k) nf[k] = fr[4 * (size_t)b + k];
+            for (u32 k = callee.n_params * 4; k < callee.n_regs * 4; ++k) nf[k] = 0;
+            stack[depth].fn = fn; stack[depth].pc = pc; stack[depth].base = base; stack[depth].dst = d;
+            stack[depth].want = c & 0x3FFFFFFFu;
+            ++depth;
+            fn = f; fi = callee; ins = code + 5 * (size_t)fi.code_off; base = nb; fr = nf; pc = 0;
+            continue;
+        }
         N128 va, vb, vc, r;
-        if (!vmn_operand(va, a, regs, consts32)) return false;
+        if (!vmn_operand(va, a, fr, consts32)) return false;
         if (op == FOP_JZ) { if (!(va.lo | va.hi)) pc = b & 0x3FFFFFFFu; continue; }
         if (op == FOP_RET) {
-            result[0] = (u32)va.lo; result[1] = (u32)(va.lo >> 32); result[2] = (u32)va.hi; result[3] = (u32)(va.hi >> 32);
-            ret_cnt = b & 0x3FFFFFFFu;
-            if (ret_cnt > 1) ret_base = a;
-            return true;
+            const u32 cnt = b & 0x3FFFFFFFu;
+            if (depth == 0) {
+                result[0] = (u32)va.lo; result[1] = (u32)(va.lo >> 32); result[2] = (u32)va.hi; result[3] = (u32)(va.hi >> 32);
+                ret_cnt = cnt;
+                if (ret_cnt > 1) ret_base = a;
+                return true;
+            }
+            --depth;
+            const VmFrame &top = stack[depth];
+            u32 *cf = regs + 4 * (size_t)top.base;
+            const u32 want = top.want > 1 ? top.want : 1u;
+            if (want > 1 && cnt < want) { err = 2; return true; }
+            if (cnt > 1) {
+                for (u32 k = 0; k < want * 4; ++k) cf[4 * (size_t)top.dst + k] = fr[4 * (size_t)a + k];
+            } else vmn_store(cf, top.dst, va);
+            fn = top.fn; fi = vm_fn(fn_info, fn); ins = code + 5 * (size_t)fi.code_off; base = top.base; fr = cf; pc = top.pc;
+            continue;
         }
-        if (!vmn_operand(vb, b, regs, consts32)) return false;
+        if (!vmn_operand(vb, b, fr, consts32)) return false;
         if (op == FOP_LOADX || op == FOP_STOREX) {
-            const u32 base = a & 0x3FFFFFFFu, limit = (op == FOP_LOADX ? c : d) & 0x3FFFFFFFu;
-            if (vb.hi || (vb.lo >> 32) || vb.lo + base >= limit) { err = 2; return true; }
-            const u32 i = (u32)vb.lo + base;
+            const u32 ab = a & 0x3FFFFFFFu, limit = (op == FOP_LOADX ? c : d) & 0x3FFFFFFFu;
+            if (vb.hi || (vb.lo >> 32) || vb.lo + ab >= limit) { err = 2; return true; }
+            const u32 i = (u32)vb.lo + ab;
             if (op == FOP_LOADX) {
-                for (int k = 0; k < 4; ++k) regs[4 * (size_t)d + k] = regs[4 * (size_t)i + k];
+                for (int k = 0; k < 4; ++k) fr[4 * (size_t)d + k] = fr[4 * (size_t)i + k];
             } else {
-                if (!vmn_operand(vc, c, regs, consts32)) return false;
-                vmn_store(regs, i, vc);
+                if (!vmn_operand(vc, c, fr, consts32)) return false;
+                vmn_store(fr, i, vc);
             }
             continue;
         }
-        if (!vmn_operand(vc, c, regs, consts32)) return false;
+        if (!vmn_operand(vc, c, fr, consts32)) return false;
         if (!vmn_apply(op, r, va, vb, vc)) return false;
-        vmn_store(regs, d, r);
+        vmn_store(fr, d, r);
     }
     err = 2;
     return true;

@@ -177,8 +177,8 @@ __device__ __noinline__ void exec_call(const TapeDev &tp, u32 call_off, uint4 *b
     u32 ret_base, ret_cnt;
     // first on the 128-bit machine (fr_device.cuh: half the frame, integer arithmetic); a value that leaves 128 bits
     // abandons that run and the call is repeated at full width
-    const bool narrow = !tp.vm_wide && vm_run_narrow(tp.fn_code, fi, regs, reinterpret_cast<const u32 *>(tp.consts), r, e,
-                                                     ret_base, ret_cnt);
+    const bool narrow = !tp.vm_wide && vm_run_narrow(tp.fn_code, tp.fn_info, f, regs, reinterpret_cast<const u32 *>(tp.consts), r,
+                                                     e, ret_base, ret_cnt);
     if (!narrow) {
         for (u32 k = 0; k < fi.n_regs * 8; ++k) regs[k] = 0;
         for (u32 k = 0; k < n_args; ++k) {
@@ -187,7 +187,7 @@ __device__ __noinline__ void exec_call(const TapeDev &tp, u32 call_off, uint4 *b
             for (int j = 0; j < 8; ++j) regs[8 * k + j] = v[j];
         }
         e = 0;
-        vm_run(tp.fn_code, fi, regs, reinterpret_cast<const u32 *>(tp.consts), r, P, e, ret_base, ret_cnt);
+        vm_run(tp.fn_code, tp.fn_info, f, regs, reinterpret_cast<const u32 *>(tp.consts), r, P, e, ret_base, ret_cnt);
     }
     // `var q[k] = f(..)`: results 1 .. k-1 go straight from the callee's registers to their slots (result 0 is `r`)
     const u32 n_extra = __ldg(&ct[2 + n_args]);

@@ -342,8 +342,33 @@ impl<'a> FunctionCtx<'a> {
                 _ => return Err(()),   // functions only see variables (call_bucket.rs: arguments are copied in)
             },
             Instruction::Call(c) => {
+                // a call inside a function body (call_bucket.rs:466-533): the arguments go to consecutive fresh registers
+                // (the callee's parameters; array arguments element by element), CALL {d, function, first argument register,
+                // result count}.  The callee must already be lowered: `produce_cb2c` walks the functions callee first.
                 let fid = *self.producer.function_ids.get(&c.symbol).ok_or(())?;
-                let _ = fid; return Err(());   // nested calls: inline upstream or extend the VM with a call stack (not in version 1)
+                if fid >= self.file.functions.len() as u32 { return Err(()); }      // recursion / not yet lowered
+                let mut vals = Vec::new();
+                for a in &c.arguments { vals.push(self.value(a)?); }
+                let base = self.rec.n_regs;
+                for v in vals { let r = self.reg(); self.push(Op::COPY, r, v, Ref::None, Ref::None); }
+                let n_res = match &c.return_info {
+                    ReturnType::Final(f) => match f.context.size { SizeOption::Single(n) => n, _ => return Err(()) },
+                    _ => 1,
+                };
+                if n_res == 0 || n_res > 64 { return Err(()); }
+                let d = self.reg();
+                for _ in 1..n_res { self.reg(); }
+                self.push(Op::CALL, d, Ref::Imm(fid), if c.arguments.is_empty() { Ref::None } else { Ref::Tmp(base) },
+                          if n_res > 1 { Ref::Imm(n_res as u32) } else { Ref::None });
+                if let ReturnType::Final(f) = &c.return_info {      // `x = g(..)` / `var r[n] = g(..)`: store into the variable slots
+                    let d0 = match d { Ref::Tmp(i) => i, _ => return Err(()) };
+                    if let (AddressType::Variable, LocationRule::Indexed { location, .. }) = (&f.dest_address_type, &f.dest) {
+                        if let Instruction::Value(v) = location.as_ref() {
+                            for k in 0..n_res { self.push(Op::COPY, Ref::Tmp(v.value as u32 + k as u32), Ref::Tmp(d0 + k as u32), Ref::None, Ref::None); }
+                        } else { return Err(()); }
+                    } else { return Err(()); }
+                }
+                d
             }
             _ => return Err(()),
         })
@@ -427,7 +452,12 @@ pub fn produce_cb2c(templates: &[Box<TemplateCodeInfo>], functions: &[Box<Functi
     let q = producer.prime_str.parse::<BigInt>().map_err(|_| {})?;
     let mut file = Cb2cFile::default();
     file.prime = producer.prime_id()?;
-    for f in functions { let r = lower_function(f, producer, &mut file)?; file.functions.push(r); }
+    // callee first: `producer.function_ids` numbers the functions in a topological order of the call graph (computed by
+    // `Circuit::cuda_producer`; a cycle - a recursive function - has no such order and is refused there), and `functions`
+    // is walked in that order so that a body only names functions that are already in `file.functions`
+    let mut order: Vec<&Box<FunctionCodeInfo>> = functions.iter().collect();
+    order.sort_by_key(|f| producer.function_ids.get(&f.header).copied().unwrap_or(u32::MAX));
+    for f in order { let r = lower_function(f, producer, &mut file)?; file.functions.push(r); }
     for t in templates {
         if t.is_extern_c { return Err(()); }
         let mut cx = TemplateCtx { producer, file: &mut file, q: q.clone(), rec: TemplateRecord::default(),

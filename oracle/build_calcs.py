@@ -26,6 +26,7 @@ def circuits():
         "int_div32": ("bn128", lambda d: C.int_div(d, 32)),
         "int_div_arr32": ("bn128", lambda d: C.int_div_array(d, 32, "all")),     # `var qr[3] = f(a, b);`: one call, three results
         "ecdsa_calls_2x5": ("bn128", lambda d: C.ecdsa_scale(d, 2, 5, hints="functions")),
+        "gcd32": ("bn128", lambda d: C.gcd_circuit(d, 32)),                        # functions calling functions
         "ecdsa_scale_2x5": ("bn128", lambda d: C.ecdsa_scale(d, 2, 5)),
         "sha256compression": ("bn128", lambda d: C.sha256_compression(d)),
         "sha256_64_bls": ("bls12381", lambda d: C.sha256(d, 64)),

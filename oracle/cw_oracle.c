@@ -355,6 +355,18 @@ static int run_func(const circuit *c, const func *f, const fe *args, fe *result,
             rc = 0;
             break;
         }
+        if (o->op == 45) {                                                         /* nested CALL of an earlier function */
+            u32 fid = RIDX(o->a), want = RK(o->c) == 0 && RIDX(o->c) > 1 ? RIDX(o->c) : 1, got = 0;
+            if (fid >= c->n_funcs || &c->fn[fid] >= f) break;
+            const func *g = &c->fn[fid];
+            if (RIDX(o->b) + g->n_params > f->n_regs || RIDX(o->d) + want > f->n_regs) break;
+            fe res[MAX_RESULTS];
+            int rc2 = run_func(c, g, &regs[RIDX(o->b)], res, &got);
+            if (rc2) { rc = rc2; break; }
+            if (got < want) break;
+            for (u32 k = 0; k < want; ++k) regs[RIDX(o->d) + k] = res[k];
+            continue;
+        }
         if (o->op == 43 || o->op == 44) {                                          /* LOADX / STOREX */
             const fe *ix = arg[1];
             /* the extent of the array, when the producer wrote it (LOADX: operand c, STOREX: operand d; docs/CB2C.md) */

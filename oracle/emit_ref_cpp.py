@@ -125,6 +125,14 @@ def _emit_function(w, f) -> None:
             w("Fr_copy(&lvar[%d],&lvar[%d + Fr_toInt(%s)]);" % (d[2], a[2], addr(b)))
         elif op == 44:
             w("Fr_copy(&lvar[%d + Fr_toInt(%s)],%s);" % (a[2], addr(b), addr(c)))
+        elif op == 45:     # a nested call (call_bucket.rs:466-533): the callee's lvar array is filled with the arguments
+            fn = f.desc.functions[a[2]]
+            w("{")
+            w("FrElement lvarcall[%d];" % fn.n_regs)
+            for k in range(fn.n_params):
+                w("Fr_copy(&lvarcall[%d],&lvar[%d]);" % (k, b[2] + k))
+            w("%s_%d(ctx,lvarcall,componentFather,%s,%d);" % (fn.name, fn.id, addr(d), c[2] if c[0] == 0 and c[2] > 1 else 1))
+            w("}")
         elif op == 24:
             w("Fr_copy(%s,%s);" % (addr(d), addr(a)))
         elif op in _FN:

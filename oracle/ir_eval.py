@@ -60,6 +60,17 @@ def run_function(desc, F, fn, args):
             if n > 1:
                 return [regs[a[2] + k] for k in range(n)]
             return val(a)
+        elif op == OPS["CALL"]:                  # nested call: the callee's parameters are the registers b .. b+n_params-1
+            callee = desc.functions[a[2]]
+            assert callee.id < fn.id, "a function may only call earlier functions"
+            res = run_function(desc, F, callee, [regs[b[2] + k] for k in range(callee.n_params)])
+            n_res = c[2] if c[0] == 0 else 0
+            if n_res > 1:
+                assert isinstance(res, list) and len(res) >= n_res
+                for k in range(n_res):
+                    regs[d[2] + k] = res[k]
+            else:
+                regs[d[2]] = res[0] if isinstance(res, list) else res
         elif op == OPS["LOADX"]:
             i = a[2] + to_int(val(b))
             assert 0 <= i < (a[2] + c[2] if c[0] == 0 and c[2] else fn.n_regs)   # operand c: extent of the array

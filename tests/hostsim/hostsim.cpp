@@ -134,21 +134,22 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
                 if (op[0] == OP_CALL) {  // function call: one work item interprets the body
                     const uint32_t *ct = &t.call_tab[op[1]];
                     FnInfo fi{t.fn_info[ct[0] * 4], t.fn_info[ct[0] * 4 + 1], t.fn_info[ct[0] * 4 + 2], t.fn_info[ct[0] * 4 + 3]};
-                    std::vector<u32> regs((size_t)fi.n_regs * 8, 0);
+                    std::vector<u32> regs((size_t)VM_MAX_REGS * 8, 0);   // (frames of nested calls are stacked behind the first)
                     for (uint32_t k = 0; k < ct[1]; ++k) operand(ct[2 + k], &regs[(size_t)k * 8]);
                     int e = 0;
                     u32 ret_base, ret_cnt;
                     // as kernels.cuh exec_call: the 128-bit machine first, the full-width one when it gives up
                     static const bool vm_wide = getenv("CW_VM_WIDE") && atoi(getenv("CW_VM_WIDE"));
-                    const bool narrow = !vm_wide && vm_run_narrow(t.fn_code.data(), fi, regs.data(), (const u32 *)t.consts.data(),
-                                                                  r, e, ret_base, ret_cnt);
+                    const bool narrow = !vm_wide && vm_run_narrow(t.fn_code.data(), t.fn_info.data(), ct[0], regs.data(),
+                                                                  (const u32 *)t.consts.data(), r, e, ret_base, ret_cnt);
                     g_narrow_calls += narrow;
                     g_wide_calls += !narrow;
                     if (!narrow) {
                         std::fill(regs.begin(), regs.end(), 0u);
                         for (uint32_t k = 0; k < ct[1]; ++k) operand(ct[2 + k], &regs[(size_t)k * 8]);
                         e = 0;
-                        vm_run(t.fn_code.data(), fi, regs.data(), (const u32 *)t.consts.data(), r, P, e, ret_base, ret_cnt);
+                        vm_run(t.fn_code.data(), t.fn_info.data(), ct[0], regs.data(), (const u32 *)t.consts.data(), r, P, e, ret_base,
+                               ret_cnt);
                     }
                     const uint32_t *ex = ct + 2 + ct[1];
                     for (uint32_t k = 0; k < ex[0]; ++k) {   // results 1.. of `var q[k] = f(..)`

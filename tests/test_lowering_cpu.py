@@ -34,6 +34,10 @@ CIRCUITS = {
                          lambda r, q: {"a": r.randrange(2**32), "b": r.choice([0, 1, r.randrange(1, 2**32)])}),
     "int_div_arr_head": (lambda d: C.int_div_array(d, 32, "head"),
                          lambda r, q: {"a": r.randrange(2**32), "b": r.choice([0, 1, r.randrange(1, 2**32)])}),
+    # a function that calls two other functions inside a data-dependent loop (nested frames in the interpreter)
+    "gcd32": (lambda d: C.gcd_circuit(d, 32),
+              lambda r, q: {"a": r.choice([0, 1, 2**32 - 1, r.randrange(2**32), 2 * 3 * 5 * 7 * 11 * 13 * r.randrange(1, 1000)]),
+                            "b": r.choice([0, 1, r.randrange(1, 2**32), 2 * 3 * 5 * 7 * r.randrange(1, 100000)])}),
     # the bench circuit's BigMultModP with its quotient / remainder hints computed by a long_div-style function
     "ecdsa_calls_1x2": (lambda d: C.ecdsa_scale(d, 1, 2, hints="functions"),
                         lambda r, q: {"a": [r.choice([2**64 - 1, r.getrandbits(64)]) for _ in range(4)],

@@ -156,7 +156,7 @@ def test_shift_by_negative_signal_amount_is_not_treated_as_narrow(prime):
             assert limbs_to_ints(wit[i]) == [e[k] for k in w2s], (prime, flags, ins[i])
 
 
-def random_function(d, rng, n_params):
+def random_function(d, rng, n_params, callees=(), name="fz"):
     """a random structured function body: scalars, `var` arrays with run-time indices (kept in range by masking), nested
     if / else and counted loops, values that are reused long after their definition, registers read before they are
     written (the frame is zero-initialised), scalar or array return.  Exercises the lowering's register allocation
@@ -184,6 +184,11 @@ def random_function(d, rng, n_params):
 
         def expr(depth=0):
             a = rng.choice(scalars)
+            if callees and rng.random() < 0.12:       # a nested call (the callee may itself call an earlier function)
+                g = rng.choice(callees)
+                n = rng.randrange(1, g.n_results + 1)
+                res = f.call_array(g, [operand() for _ in range(g.n_params)], n)
+                return res[rng.randrange(n)] + 0
             k = rng.random()
             if k < 0.45:
                 op = rng.choice(["__add__", "__mul__", "__and__", "__or__", "__xor__", "lt", "gt", "eq", "neq", "leq", "geq"])
@@ -235,7 +240,7 @@ def random_function(d, rng, n_params):
             f.ret_array(base, n)
         else:
             f.ret(expr())
-    return d.function("fz", n_params, build)
+    return d.function(name, n_params, build)
 
 
 @pytest.mark.parametrize("seed", range(int(__import__("os").environ.get("CW_FUZZ_FUNCS", "150"))))
@@ -246,7 +251,11 @@ def test_random_function_bodies_match_the_evaluator(seed):
     prime = rng.choice(["bn128", "bls12381", "secq256r1"])
     d = CircuitDesc(prime)
     n_params = rng.randrange(1, 6)
-    fn = random_function(d, rng, n_params)
+    callees = []
+    if seed % 3 == 0:        # every third circuit: one or two helper functions, the second may call the first
+        for k in range(rng.randrange(1, 3)):
+            callees.append(random_function(d, rng, rng.randrange(1, 4), tuple(callees), "helper%d" % k))
+    fn = random_function(d, rng, n_params, tuple(callees))
     n_res = fn.n_results
 
     def build(t):
@@ -278,4 +287,4 @@ def test_random_function_bodies_match_the_evaluator(seed):
             assert limbs_to_ints(wit[i]) == [exp[k] for k in w2s], (seed, i)
     # the packed frame never exceeds the declared one
     from circom_b200.witness_calculator import Circuit
-    assert Circuit(d, host_only=True).functions()[0]["n_regs"] <= fn.n_regs
+    assert Circuit(d, host_only=True).functions()[-1]["n_regs"] <= fn.n_regs

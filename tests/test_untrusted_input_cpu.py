@@ -50,7 +50,7 @@ def mutate(rng, src: bytes) -> bytes:
 def descriptions():
     out = []
     for mk in (lambda d: C.multiplier2(d), lambda d: C.less_than(d, 8), lambda d: C.int_div(d, 32),
-               lambda d: C.int_div_array(d, 16, "all"),
+               lambda d: C.int_div_array(d, 16, "all"), lambda d: C.gcd_circuit(d, 16),
                lambda d: C.num2bits(d, 16), lambda d: C.is_zero(d), lambda d: C.all_ops(d)):
         d = CircuitDesc("bn128")
         d.set_main(mk(d))
@@ -234,6 +234,62 @@ def test_hostile_array_calls():
     assert variant(call_edit(4)) == native.CW_EFORMAT                      # more than the function returns
     assert variant(call_edit(65)) == native.CW_EFORMAT
     assert variant(call_edit(0x3FFFFFFF)) == native.CW_EFORMAT
+
+
+def test_hostile_nested_calls():
+    """a CALL inside a function body names its callee, its argument registers and its result count: all from the file.  The
+    callee must be an earlier function (no recursion: the deepest chain of frames is known at load time and must fit the
+    interpreter's register array)"""
+    from circom_b200.circuit import OPS, K_NONE, K_TMP
+
+    def variant(edit):
+        d = CircuitDesc("bn128")
+        d.set_main(C.gcd_circuit(d, 16))
+        edit(d)
+        return try_load(d.to_bytes())
+
+    def call_edit(**kw):
+        def edit(d):
+            f = d.functions[-1]                       # gcd: calls divmod_arr (3 results) and bit_length
+            k = next(i for i, c in enumerate(f.code) if c[0] == OPS["CALL"])
+            op, dd, a, b, c = f.code[k]
+            f.code[k] = (op, kw.get("d", dd), kw.get("a", a), kw.get("b", b), kw.get("c", c))
+        return edit
+
+    assert variant(lambda d: None) == 0
+    me = 2                                            # index of gcd itself
+    assert variant(call_edit(a=(K_NONE, 0, me))) == native.CW_EFORMAT         # calls itself
+    assert variant(call_edit(a=(K_NONE, 0, 7))) == native.CW_EFORMAT          # no such function
+    assert variant(call_edit(a=(K_TMP, 0, 0))) == native.CW_EFORMAT
+    assert variant(call_edit(c=(K_NONE, 0, 4))) == native.CW_EFORMAT          # more results than divmod_arr returns
+    assert variant(call_edit(c=(K_NONE, 0, 65))) == native.CW_EFORMAT
+    assert variant(call_edit(c=(K_TMP, 0, 1))) == native.CW_EFORMAT
+
+    def past(d):
+        call_edit(b=(K_TMP, 0, d.functions[-1].n_regs - 1))(d)               # two arguments from the last register
+    assert variant(past) == native.CW_EFORMAT
+    assert variant(call_edit(b=(K_NONE, 0, 3))) == native.CW_EFORMAT          # argument base must be a register
+
+    def dest_past(d):
+        call_edit(d=(K_TMP, 0, d.functions[-1].n_regs - 2))(d)               # three results from n_regs - 2
+    assert variant(dest_past) == native.CW_EFORMAT
+
+    # a chain of calls whose frames do not fit the interpreter's 192 registers is refused at load time
+    d = CircuitDesc("bn128")
+    prev = None
+    for k in range(4):
+        def body(f, prev=prev):
+            arr = f.array(60)                          # 60 registers reachable by index: cannot be packed
+            i = f.var(1)
+            f.store(arr, i, f.param(0))
+            x = f.load(arr, i)
+            f.ret(f.call(prev, [x]) + 1 if prev is not None else x + 1)
+        prev = d.function("deep%d" % k, 1, body)
+
+    def build(t):
+        t.assign(t.output("o"), t.call(prev, [t.input("a")]))
+    d.set_main(d.template("Deep", (), build))
+    assert try_load(d.to_bytes()) == native.CW_EFORMAT and b"too many registers" in lib.cw_last_error()
 
 
 def test_hostile_symbols_section():

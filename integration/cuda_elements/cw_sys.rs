@@ -17,6 +17,8 @@ extern "C" {
     pub fn cw_get_size_of_witness(c: *const cw_circuit) -> u32;
     pub fn cw_get_main_input_signal_no(c: *const cw_circuit) -> u32;
     pub fn cw_fnv1a(name: *const c_char) -> u64;
+    pub fn cw_circuit_write_dat(c: *const cw_circuit, path: *const c_char) -> c_int;
+    pub fn cw_circuit_write_sym(c: *const cw_circuit, path: *const c_char) -> c_int;   // needs the symbols section of the .cb2c
     pub fn cw_batch_create(c: *const cw_circuit, batch: u32, device: c_int, out: *mut *mut cw_batch) -> c_int;
     pub fn cw_batch_destroy(b: *mut cw_batch);
     pub fn cw_batch_set_input(b: *mut cw_batch, instance: u32, name_hash: u64, idx: u32, limbs: *const u64) -> c_int;

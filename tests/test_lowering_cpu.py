@@ -279,3 +279,37 @@ def test_calls_run_on_the_narrow_machine_and_fall_back():
     for i, inp in enumerate(ins):
         exp = evaluate(d, inp)
         assert limbs_to_ints(wit[i]) == [exp[k] for k in w2s], i
+
+
+@pytest.mark.parametrize("prime", range(7))
+def test_modular_inverse_by_division_steps(prime):
+    """fr_device.cuh fr_modinv / fr_inv_mont (safegcd, 600 division steps on 30-bit limbs) against python's pow(x, -1, q) for
+    every prime: edge values (0 -> 0 as the reference, 1, q-1, powers of two, values around the limb boundaries) and
+    random ones; field division through the same path"""
+    name = ["bn128", "bls12381", "grumpkin", "pallas", "vesta", "secq256r1", "bls12377"][prime]
+    F = Field(name)
+    q = F.q
+    rng = random.Random(400 + prime)
+    hs = hostsim()
+    vals = [0, 1, 2, 3, q - 1, q - 2, (q - 1) // 2, (q + 1) // 2] + [2**k for k in range(1, 253, 7)] + \
+           [2**(30 * k) - 1 for k in range(1, 9)] + [2**(30 * k) for k in range(1, 9)] + [2**(30 * k) + 1 for k in range(1, 9)] + \
+           [q - 2**k for k in range(1, 250, 11)]
+    vals = [v % q for v in vals]
+    vals += [rng.randrange(q) for _ in range(3000 - len(vals))]
+    A = vals
+    B = [rng.choice([1, rng.randrange(q)]) for _ in A]
+    a, b = ints_to_limbs(A), ints_to_limbs(B)
+    c = np.zeros_like(a)
+    r = np.zeros((len(A), 4), dtype=np.uint64)
+    hs.hs_fr_op(prime, 28, a.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p), c.ctypes.data_as(ctypes.c_void_p),
+                r.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(A)))
+    got = limbs_to_ints(r)
+    for x, g in zip(A, got):
+        assert g == F.inv(x), hex(x)
+        assert x == 0 or g * x % q == 1
+    # b / a (DIV = 2) goes through the same inverse
+    hs.hs_fr_op(prime, OPS["DIV"], b.ctypes.data_as(ctypes.c_void_p), a.ctypes.data_as(ctypes.c_void_p),
+                c.ctypes.data_as(ctypes.c_void_p), r.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(A)))
+    got = limbs_to_ints(r)
+    for x, y, g in zip(A, B, got):
+        assert g == F.div(y, x), (hex(y), hex(x))

@@ -19,7 +19,7 @@ def main(n=512, batch=18944):
         x = t.input("x", n)
         y = t.output("y", n)
         for i in range(n):
-            t.assign(y[i], 1 / x[i])
+            t.assign(y[i], t.const(1) / x[i])
             t.constrain(y[i] * x[i], 1)
     d.set_main(d.template("Inverses", (n,), build))
     c = Circuit(d)

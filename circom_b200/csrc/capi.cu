@@ -14,6 +14,7 @@
 #include <cstring>
 #include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <stdexcept>
@@ -121,9 +122,25 @@ int env_int(const char *name, int dflt) {
 
 }  // namespace
 
+// Packed-transfer layout from the classes the witness values were SEEN to have (narrower than the proven ones; kernels.cuh:
+// witness_observe_kernel), with the device copies of its location lists.  One per circuit and device, replaced (never
+// edited) when a batch shows a wider value; transfers hold a reference while they use it.
+struct NarrowPack {
+    PackLayout L;
+    std::vector<uint8_t> cls;
+    u32 *pk_bit = nullptr, *pk_u64 = nullptr, *pk_full = nullptr;
+    ~NarrowPack() {
+        cudaFree(pk_bit);
+        cudaFree(pk_u64);
+        cudaFree(pk_full);
+    }
+};
+
 struct cw_circuit {
     Tape tape;
     mutable std::mutex mu;
+    mutable std::mutex narrow_mu;   // serialises the (rare) observation passes
+    mutable std::map<int, std::shared_ptr<NarrowPack>> narrow;   // guarded by mu
     mutable std::map<int, DevTape> dev;
     mutable PackLayout pack;
     mutable bool pack_ready = false;
@@ -773,14 +790,69 @@ static int ensure_pack_buffers(cw_batch *b, const PackLayout &L) {
     return CW_OK;
 }
 
-// packed records of instances [first, first + count) into `dst_d` (device), on the batch stream
-static int pack_rows(cw_batch *b, const PackLayout &L, u32 first, u32 count, u32 *dst_d) {
+// packed records of instances [first, first + count) into `dst_d` (device), on the batch stream; np: the layout of observed
+// classes (else the proven one, whose location lists are part of the device tape)
+static int pack_rows(cw_batch *b, const PackLayout &L, u32 first, u32 count, u32 *dst_d, const NarrowPack *np = nullptr) {
     const size_t items = L.n_plane_words + L.n_bit_words + L.u64_loc.size() + L.full_loc.size();
     dim3 grid((u32)std::max<size_t>(1, std::min<size_t>((items + 255) / 256, 148 * 4)), std::min<u32>(count, 65535u));
-    witness_pack_kernel<<<grid, 256, 0, b->stream>>>(b->store(), b->dt.pk_bit, (u32)L.bit_loc.size(), b->dt.pk_u64,
-                                                     (u32)L.u64_loc.size(), b->dt.pk_full, (u32)L.full_loc.size(), dst_d,
-                                                     L.words, first, count, b->pack_flag_d);
+    witness_pack_kernel<<<grid, 256, 0, b->stream>>>(b->store(), np ? np->pk_bit : b->dt.pk_bit, (u32)L.bit_loc.size(),
+                                                     np ? np->pk_u64 : b->dt.pk_u64, (u32)L.u64_loc.size(),
+                                                     np ? np->pk_full : b->dt.pk_full, (u32)L.full_loc.size(), dst_d, L.words,
+                                                     first, count, b->pack_flag_d);
     CU(cudaGetLastError());
+    return CW_OK;
+}
+
+// Looks at the values of a finished batch and (re)builds the circuit's layout of observed classes for the batch's device:
+// class = max(what earlier batches showed, what this one shows), never wider than the proven class.
+static int observe_classes(cw_batch *b, std::shared_ptr<NarrowPack> prev, std::shared_ptr<NarrowPack> &out) {
+    const cw_circuit *c = b->c;
+    const Tape &t = c->tape;
+    const size_t W = t.n_witness;
+    std::lock_guard<std::mutex> guard(c->narrow_mu);
+    {   // another transfer may have observed meanwhile: start from the newest
+        std::lock_guard<std::mutex> lk(c->mu);
+        auto it = c->narrow.find(b->device);
+        if (it != c->narrow.end() && it->second != prev) prev = it->second;
+    }
+    // the entries worth looking at: outside the bit plane, proven class above "bit"
+    std::vector<u32> loc, wit;
+    for (size_t i = 0; i < W; ++i)
+        if (!(t.witness_slot[i] & OPERAND_BIT) && t.wit_class[i] > 0) {
+            loc.push_back(t.witness_slot[i]);
+            wit.push_back((u32)i);
+        }
+    auto np = std::make_shared<NarrowPack>();
+    np->cls.assign(t.wit_class.begin(), t.wit_class.end());
+    if (!loc.empty()) {
+        std::vector<u32> cls(loc.size(), 0);
+        if (prev)
+            for (size_t k = 0; k < loc.size(); ++k) cls[k] = prev->cls[wit[k]];
+        u32 *loc_d = nullptr, *cls_d = nullptr;
+        int rc;
+        if ((rc = upload(&loc_d, loc.data(), loc.size() * 4))) return rc;
+        if ((rc = upload(&cls_d, cls.data(), cls.size() * 4))) { cudaFree(loc_d); return rc; }
+        const u32 n_tiles = (b->batch + (1u << b->bt_log2) - 1) >> b->bt_log2;
+        const uint64_t items = (uint64_t)loc.size() << b->bt_log2;
+        dim3 grid((u32)std::max<uint64_t>(1, std::min<uint64_t>((items + 255) / 256, 148 * 8)), std::min<u32>(n_tiles, 65535u));
+        witness_observe_kernel<<<grid, 256, 0, b->stream>>>(b->store(), loc_d, (u32)loc.size(), cls_d);
+        cudaError_t e = cudaMemcpyAsync(cls.data(), cls_d, cls.size() * 4, cudaMemcpyDeviceToHost, b->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+        cudaFree(loc_d);
+        cudaFree(cls_d);
+        if (e != cudaSuccess) return fail(CW_ECUDA, cudaGetErrorString(e));
+        for (size_t k = 0; k < loc.size(); ++k) np->cls[wit[k]] = (uint8_t)std::min<u32>(cls[k], t.wit_class[wit[k]]);
+    }
+    build_pack_layout(t, np->L, np->cls.data());
+    int rc;
+    if ((rc = upload(&np->pk_bit, np->L.bit_loc.data(), np->L.bit_loc.size() * 4))) return rc;
+    if ((rc = upload(&np->pk_u64, np->L.u64_loc.data(), np->L.u64_loc.size() * 4))) return rc;
+    if ((rc = upload(&np->pk_full, np->L.full_loc.data(), np->L.full_loc.size() * 4))) return rc;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        c->narrow[b->device] = np;
+    }
+    out = np;
     return CW_OK;
 }
 
@@ -788,12 +860,47 @@ static int pack_rows(cw_batch *b, const PackLayout &L, u32 first, u32 count, u32
 // them to the canonical 32-byte rows (zero-extension only - no field arithmetic happens on the CPU).  The batch
 // moves in chunks through two staging buffers: while the worker threads expand chunk k, the pack kernel and the
 // copy of chunk k + 1 run on the GPU / the copy engine.  CW_PACKED_D2H=0 forces the dense copy.
+static int get_witness_packed_with(cw_batch *b, uint64_t *out, const PackLayout &L, const PackLayout &Lstatic,
+                                   const NarrowPack *np, bool *flagged);
 static int get_witness_packed(cw_batch *b, uint64_t *out, bool *done) {
     const Tape &t = b->c->tape;
-    const PackLayout &L = b->c->pack_layout();
+    const PackLayout &Lstatic = b->c->pack_layout();
     *done = false;
-    if (env_int("CW_PACKED_D2H", 1) == 0 || L.words * 4 * 2 > (size_t)t.n_witness * 32) return CW_OK;
-    int rc = ensure_pack_buffers(b, L);
+    if (env_int("CW_PACKED_D2H", 1) == 0) return CW_OK;
+    int rc;
+    // Classes observed at run time (CW_PACK_OBSERVE=0: proven classes only).  Values that are bits or limbs without the
+    // lowering being able to prove it - every xor of a hash circuit - then cross PCIe as bits / 8 bytes.  The first
+    // transfer of a circuit looks at its batch; the pack kernel re-checks every value, a batch that shows a wider value
+    // widens the layout and is sent again.
+    std::shared_ptr<NarrowPack> np;
+    if (env_int("CW_PACK_OBSERVE", 1) != 0 && (!Lstatic.u64_loc.empty() || !Lstatic.full_loc.empty())) {
+        {
+            std::lock_guard<std::mutex> lk(b->c->mu);
+            auto it = b->c->narrow.find(b->device);
+            if (it != b->c->narrow.end()) np = it->second;
+        }
+        if (!np && (rc = observe_classes(b, nullptr, np))) return rc;
+    }
+    for (int attempt = 0;; ++attempt) {
+        const PackLayout &L = np ? np->L : Lstatic;
+        if (L.words * 4 * 2 > (size_t)t.n_witness * 32) return CW_OK;   // not worth it: dense copy
+        bool flagged = false;
+        if ((rc = get_witness_packed_with(b, out, L, Lstatic, np.get(), &flagged))) return rc;
+        if (!flagged) break;
+        if (!np || attempt > 0) return CW_OK;   // a value exceeded its PROVEN class (never expected): dense copy
+        std::shared_ptr<NarrowPack> wider;
+        if ((rc = observe_classes(b, np, wider))) return rc;
+        np = wider;
+    }
+    *done = true;
+    return CW_OK;
+}
+
+// one pass of the packed transfer with layout L (staging buffers are sized for the proven layout, the widest)
+static int get_witness_packed_with(cw_batch *b, uint64_t *out, const PackLayout &L, const PackLayout &Lstatic,
+                                   const NarrowPack *np, bool *flagged) {
+    const Tape &t = b->c->tape;
+    int rc = ensure_pack_buffers(b, Lstatic);
     if (rc) return rc;
     CU(cudaMemsetAsync(b->pack_flag_d, 0, 4, b->stream));
     const size_t W = t.n_witness, cap = b->packed_cap;
@@ -808,7 +915,7 @@ static int get_witness_packed(cw_batch *b, uint64_t *out, bool *done) {
     for (size_t k = 0; k < n_chunks; ++k) {
         const size_t first = k * cap, cnt = std::min(cap, b->batch - first);
         // staging buffer k & 1 was consumed by the expansion of chunk k - 2, which finished before chunk k - 1 was waited for
-        if ((rc = pack_rows(b, L, (u32)first, (u32)cnt, b->packed_d[k & 1]))) return rc;
+        if ((rc = pack_rows(b, L, (u32)first, (u32)cnt, b->packed_d[k & 1], np))) return rc;
         CU(cudaMemcpyAsync(b->packed_h[k & 1], b->packed_d[k & 1], cnt * L.words * 4, cudaMemcpyDeviceToHost, b->stream));
         CU(cudaEventRecord(b->pack_ev[k & 1], b->stream));
         if (k > 0) {
@@ -819,10 +926,12 @@ static int get_witness_packed(cw_batch *b, uint64_t *out, bool *done) {
     int flag = 0;
     CU(cudaMemcpyAsync(&flag, b->pack_flag_d, 4, cudaMemcpyDeviceToHost, b->stream));
     CU(cudaStreamSynchronize(b->stream));
-    if (flag) return CW_OK;  // a value exceeded its static class (never expected): the caller does the dense copy
+    if (flag) {   // a value exceeded its class: the rows written so far are overwritten by the next attempt
+        *flagged = true;
+        return CW_OK;
+    }
     expand_chunk(n_chunks - 1);
     b->last_d2h_bytes = (uint64_t)b->batch * L.words * 4;
-    *done = true;
     return CW_OK;
 }
 

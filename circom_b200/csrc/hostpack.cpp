@@ -16,8 +16,10 @@
 
 namespace cw {
 
-void build_pack_layout(const Tape &t, PackLayout &L) {
+void build_pack_layout(const Tape &t, PackLayout &L, const uint8_t *cls) {
     const size_t W = t.n_witness;
+    if (!cls) cls = t.wit_class.data();
+    L = PackLayout();
     L.n_plane_words = t.n_bitwords;
     for (size_t i = 0; i < W; ++i) {
         const uint32_t loc = t.witness_slot[i];
@@ -27,11 +29,11 @@ void build_pack_layout(const Tape &t, PackLayout &L) {
         if (loc & OPERAND_BIT) {
             sg.kind = 0;
             sg.src = loc & OPERAND_BITPOS_MASK;
-        } else if (t.wit_class[i] == 0) {
+        } else if (cls[i] == 0) {
             sg.kind = 1;
             sg.src = (uint32_t)L.bit_loc.size();
             L.bit_loc.push_back(loc);
-        } else if (t.wit_class[i] == 1) {
+        } else if (cls[i] == 1) {
             sg.kind = 2;
             sg.src = (uint32_t)L.u64_loc.size();
             L.u64_loc.push_back(loc);

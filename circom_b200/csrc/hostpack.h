@@ -24,7 +24,8 @@ struct PackLayout {
     std::vector<uint32_t> bit_loc, u64_loc, full_loc;  // slot ids of the entries outside the plane, in witness order
     size_t n_plane_words = 0, n_bit_words = 0, words = 0;  // words: per instance, rounded to 16 bytes
 };
-void build_pack_layout(const Tape &t, PackLayout &L);
+// cls: per witness entry 0 bit / 1 <= 64 bits / 2 full; nullptr: the classes the lowering proved (t.wit_class)
+void build_pack_layout(const Tape &t, PackLayout &L, const uint8_t *cls = nullptr);
 
 // one instance: packed record -> W rows of 32 bytes, each written exactly once, front to back, with streaming stores
 // (force_bits: 0 = the widest stores the CPU has, else at most 128 / 256 / 512-bit stores - for tests)

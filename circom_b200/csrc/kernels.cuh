@@ -451,6 +451,29 @@ __global__ void witness_expand_kernel(StoreDev S, const u32 *__restrict__ wloc, 
     }
 }
 
+// ---- classes of the witness values as they ARE in a batch -----------------------------------------------------
+// cls[k] = max over the instances of {0: the value of entry loc[k] is 0 or 1, 1: below 2^64, 2: wider} (merged into what
+// cls already holds).  The packed transfer uses observed classes where they are narrower than the proven ones - the
+// xor / majority outputs of hash circuits are bits that no range analysis proves - and re-checks every value it packs.
+__global__ void __launch_bounds__(256) witness_observe_kernel(StoreDev S, const u32 *__restrict__ loc, u32 n, u32 *__restrict__ cls) {
+    const u32 bt_mask = (1u << S.bt_log2) - 1u;
+    const u32 n_tiles = (S.batch + bt_mask) >> S.bt_log2;
+    const unsigned long long n_items = (unsigned long long)n << S.bt_log2;
+    for (u32 tile = blockIdx.y; tile < n_tiles; tile += gridDim.y) {
+        const uint4 *tb = store_tile(S, tile);
+        for (unsigned long long w = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; w < n_items;
+             w += (unsigned long long)gridDim.x * blockDim.x) {
+            const u32 li = (u32)w & bt_mask, inst = (tile << S.bt_log2) + li;
+            if (inst >= S.batch) continue;
+            const u32 k = (u32)(w >> S.bt_log2);
+            u32 x[8];
+            load_slot_nc(x, tb, __ldg(&loc[k]), S.bt_log2, li);
+            const u32 c = (x[2] | x[3] | x[4] | x[5] | x[6] | x[7]) ? 2u : ((x[1] | (x[0] & ~1u)) ? 1u : 0u);
+            if (c > cls[k]) atomicMax(&cls[k], c);
+        }
+    }
+}
+
 // ---- packed witness for the device->host transfer -------------------------------------------------------
 // Most witness entries of real circuits are bits or 64-bit limbs.  The lowering knows an upper bound of every
 // entry's bit length (range analysis); entries proven to be one bit travel as one bit, entries proven <= 64 bits

@@ -273,3 +273,45 @@ def test_function_hints_large_batch_and_runtime_errors():
         assert limbs_to_ints(wit[i][1:4]) == [inp["a"] // inp["b"], inp["a"] % inp["b"], inp["a"].bit_length()]
     ow, st = COracle(d.to_bytes()).run(arr[:64])
     assert not st.any() and (ow[:, w2s] == wit[:64]).all()
+
+
+def test_packed_transfer_with_observed_classes(monkeypatch):
+    """The xor / majority outputs of a hash circuit are bits that no range analysis proves: the first transfer of a circuit
+    looks at the values of its batch and packs by the classes it saw (re-checked by the pack kernel for every value it
+    sends).  Same rows as the dense copy; far fewer bytes; a later batch with wider values (inputs that are not bits)
+    widens the layout and is sent again - still the dense rows; then bits again."""
+    d = CircuitDesc("bn128")
+    d.set_main(C.sha256(d, 64))
+    rng = random.Random(21)
+    n = 40
+    bits = [{"in": [rng.getrandbits(1) for _ in range(64)]} for _ in range(n)]
+    wide = [{"in": [rng.choice([0, 1, 2, 5, rng.randrange(d.q)]) for _ in range(64)]} for _ in range(n)]
+
+    def fetch(c, ins, env):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        b = Batch(c, len(ins))
+        b.set_inputs(flat_inputs(d, ins))
+        b.run()
+        w = b.witness()
+        nbytes = b.last_d2h_bytes()
+        for k in env:
+            monkeypatch.delenv(k)
+        return w, nbytes, b.status()
+
+    c = Circuit(d, sanity_check=False)        # (non-bit inputs violate the circuit's own asserts: not the point here)
+    W = c.n_witness
+    dense_bits, nd, _ = fetch(c, bits, {"CW_PACKED_D2H": "0"})
+    dense_wide, _, _ = fetch(c, wide, {"CW_PACKED_D2H": "0"})
+    assert nd == n * W * 32
+    proven, n_proven, _ = fetch(Circuit(d, sanity_check=False), bits, {"CW_PACK_OBSERVE": "0"})
+    assert (proven == dense_bits).all()
+    w1, n1, _ = fetch(c, bits, {})                       # first transfer: observes, packs narrow
+    assert (w1 == dense_bits).all() and n1 * 8 < n_proven and n1 * 20 < nd
+    w2, n2, _ = fetch(c, wide, {})                       # values outside the observed classes: widened, sent again
+    assert (w2 == dense_wide).all() and n2 > n1
+    w3, n3, _ = fetch(c, bits, {})                       # the layout stays widened; rows unchanged
+    assert (w3 == dense_bits).all() and n3 == n2
+    ow, st = COracle(d.to_bytes()).run(flat_inputs(d, bits)[:4])
+    w2s = c.witness2signal().astype(np.int64)
+    assert (ow[:, w2s] == w1[:4]).all()

@@ -90,7 +90,8 @@ int ensure_device(int device) {
 
 struct DevTape {
     uint4 *ops = nullptr;
-    u32 *items = nullptr, *level_start = nullptr, *level_calls = nullptr;
+    u32 *items = nullptr, *level_start = nullptr, *level_info = nullptr;
+    bool has_slow = false;
     uint4 *heads = nullptr;  // first tape word of every work item
     uint4 *consts = nullptr;
     u32 *input_slot = nullptr, *fn_code = nullptr, *fn_info = nullptr, *call_tab = nullptr;
@@ -235,20 +236,30 @@ static int get_dev_tape(const cw_circuit *c, int device, DevTape &out) {
         if ((rc = upload(&d.heads, heads.data(), heads.size() * 4))) return rc;
     }
     if ((rc = upload(&d.level_start, t.level_start.data(), t.level_start.size() * 4))) return rc;
-    if (!t.call_tab.empty()) {
-        // calls close their level (the lowering sorts the items of a level by opcode, CALL is the largest): the kernel runs
-        // them after the other items
-        std::vector<uint32_t> lc(t.n_levels(), 0);
+    {
+        // per level: how many calls close it (the lowering sorts the items of a level by opcode, CALL is the largest: the
+        // kernel runs them after the other items) and whether it has INV / POW items (run in a pass of their own)
+        std::vector<uint32_t> info(t.n_levels(), 0);
         for (size_t l = 0; l < t.n_levels(); ++l) {
             bool tail = true;
             for (uint32_t k = t.level_start[l + 1]; k-- > t.level_start[l];) {
-                const bool is_call = (t.ops[(size_t)t.items[k] * 4] & 0xFFu) == 45u && t.items[k + 1] - t.items[k] == 1;
-                if (is_call && !tail) return fail(CW_ESTATE, "internal: a call is not at the end of its level");
-                if (is_call) ++lc[l];
+                const uint32_t opc = t.ops[(size_t)t.items[k] * 4] & 0xFFu;
+                const bool single = t.items[k + 1] - t.items[k] == 1;
+                const bool is_call = opc == 45u && single;
+                if (opc == 45u && !(single && tail)) return fail(CW_ESTATE, "internal: a call is not at the end of its level");
+                if (is_call) ++info[l];
                 else tail = false;
+                for (uint32_t w = t.items[k]; w < t.items[k + 1]; ++w) {
+                    const uint32_t o = t.ops[(size_t)w * 4] & 0xFFu;
+                    if (o == 28u || o == 5u) {   // INV, POW
+                        if (!single) return fail(CW_ESTATE, "internal: a fused work item contains INV / POW");
+                        info[l] |= 0x80000000u;
+                        d.has_slow = true;
+                    }
+                }
             }
         }
-        if ((rc = upload(&d.level_calls, lc.data(), lc.size() * 4))) return rc;
+        if ((rc = upload(&d.level_info, info.data(), info.size() * 4))) return rc;
     }
     if ((rc = upload(&d.consts, t.consts.data(), t.consts.size() * 32))) return rc;
     if ((rc = upload(&d.input_slot, t.input_slot.data(), t.input_slot.size() * 4))) return rc;
@@ -338,7 +349,7 @@ void cw_circuit_destroy(cw_circuit *c) {
         cudaFree(kv.second.items);
         cudaFree(kv.second.heads);
         cudaFree(kv.second.level_start);
-        cudaFree(kv.second.level_calls);
+        cudaFree(kv.second.level_info);
         cudaFree(kv.second.consts);
         cudaFree(kv.second.input_slot);
         cudaFree(kv.second.fn_code);
@@ -655,7 +666,8 @@ int cw_batch_run(cw_batch *b) {
     tp.items = b->dt.items;
     tp.heads = b->dt.heads;
     tp.level_start = b->dt.level_start;
-    tp.level_calls = b->dt.level_calls;
+    tp.level_info = b->dt.level_info;
+    tp.has_slow = b->dt.has_slow ? 1u : 0u;
     tp.consts = b->dt.consts;
     tp.n_levels = (u32)t.n_levels();
     tp.n_slots = t.n_slots;

@@ -1427,12 +1427,13 @@ struct Lowerer {
                 const uint32_t opc = pops[c * 4];
                 if (uses[slot] != 1 || cons[slot] != reader || cons_pos[slot] != pos || claimed[slot] >= 0) return false;
                 if (is_assert_op(opc) || opc == 45 || opc == 47 || opc == DOP_BITS || opc == CW_OP_COPY) return false;
+                if (opc == CW_OP_INV || opc == CW_OP_POW) return false;   // (run in a pass of their own: items of one word)
                 return true;
             };
             for (size_t i = 0; i < n_prov; ++i) {
                 if (!live[n_pre + i]) continue;
                 const uint32_t *o = &pops[i * 4];
-                if (o[0] == 45 || o[0] == 47) continue;
+                if (o[0] == 45 || o[0] == 47 || o[0] == CW_OP_INV || o[0] == CW_OP_POW) continue;
                 uint32_t ka = candidate(o[1], i, 1) ? o[1] - n_pre : NO_SLOT;
                 uint32_t kb = candidate(o[2], i, 2) ? o[2] - n_pre : NO_SLOT;
                 if (ka != NO_SLOT && kb != NO_SLOT) {

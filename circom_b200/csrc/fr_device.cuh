@@ -433,7 +433,8 @@ CW_HD void inv30_normalize(Inv30 &r, int32_t sign, const Inv30 &m) {
         r.v[i] &= 0x3FFFFFFF;
     }
 }
-// canonical x < q  ->  x^-1 mod q (canonical), 0 -> 0
+// canonical x < q  ->  x^-1 mod q (canonical), 0 -> 0.  (Five 9-limb numbers: inlined into the interpreter's hot loop it
+// cost 16 % of the headline throughput in spills - the interpreter runs INV / POW in a pass of their own, kernels.cuh.)
 CW_HD void fr_modinv(u32 *out, const u32 *x, const FrParams &P) {
     Inv30 m, f, g, d, e;
     inv30_from_u256(m, P.q);
@@ -701,7 +702,10 @@ CW_HD u32 u256_bitlen(const u32 *a) {
     return n;
 }
 
-CW_HD void fr_exec(u32 opcode, u32 *r, const u32 *a, const u32 *b, u32 imm, const FrParams &P, int &err) {
+// SLOW = false leaves out the two operators that are loops of hundreds of steps (INV, POW): the interpreter runs them
+// in a pass of their own so that their code and registers stay out of its hot loop (kernels.cuh)
+template <bool SLOW>
+CW_HD void fr_exec_t(u32 opcode, u32 *r, const u32 *a, const u32 *b, u32 imm, const FrParams &P, int &err) {
     switch (opcode) {
         case OP_BITSIP: u256_bits_in_place(r, a, imm); break;
         case OP_BITS: u256_bits(r, a, imm); break;
@@ -710,8 +714,8 @@ CW_HD void fr_exec(u32 opcode, u32 *r, const u32 *a, const u32 *b, u32 imm, cons
         case OP_ADD: fr_add(r, a, b, P); break;
         case OP_SUB: fr_sub(r, a, b, P); break;
         case OP_NEG: fr_neg(r, a, P); break;
-        case OP_INV: fr_inv_mont(r, a, P); break;
-        case OP_POW: fr_pow_mont(r, a, b, P); break;
+        case OP_INV: if (SLOW) fr_inv_mont(r, a, P); break;
+        case OP_POW: if (SLOW) fr_pow_mont(r, a, b, P); break;
         case OP_IDIV: { u32 rem[8]; if (!u256_divmod(r, rem, a, b)) err = 1; break; }
         case OP_MOD: { u32 quo[8]; if (!u256_divmod(quo, r, a, b)) err = 1; break; }
         case OP_SHL: fr_shl(r, a, b, P); break;
@@ -748,6 +752,9 @@ CW_HD void fr_exec(u32 opcode, u32 *r, const u32 *a, const u32 *b, u32 imm, cons
         case OP_COPY: u256_set(r, a); break;
         default: u256_set_u32(r, 0); break;
     }
+}
+CW_HD void fr_exec(u32 opcode, u32 *r, const u32 *a, const u32 *b, u32 imm, const FrParams &P, int &err) {
+    fr_exec_t<true>(opcode, r, a, b, imm, P, err);
 }
 
 // ---- canonical-in / canonical-out application of one IR operator ---------------------------------------

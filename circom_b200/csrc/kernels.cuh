@@ -111,13 +111,14 @@ struct TapeDev {
     const u32 *fn_code;        // register-machine code of the circuit's functions (5 words per instruction)
     const u32 *fn_info;        // per function {code offset, n_instr, n_regs, n_params}
     const u32 *call_tab;       // per call {function, n_args, arg operands..., n_extra, slots of results 1..n_extra}
-    const u32 *level_calls;    // per level: how many of its LAST work items are calls (tapes with calls; else null)
+    const u32 *level_info;     // per level: bits 0-30 how many of its LAST work items are calls, bit 31: it has INV / POW items
     u32 n_levels;
     u32 n_slots;
     u32 n_inputs;
     u32 n_bitwords;            // words of the bit plane per instance (0: no bit plane)
     u32 prime;                 // index into c_fr (read by the PRIME = -1 builds)
     u32 vm_wide;               // 1: calls skip the 128-bit register machine (CW_VM_WIDE=1, for measurements)
+    u32 has_slow;              // the tape has INV / POW items at all
 };
 
 // (tape_calls.cu compiles only the interpreter builds with the function machine - ptxas gives up on one module with all
@@ -156,6 +157,15 @@ __global__ void stage_inputs_kernel(TapeDev tp, const uint4 *__restrict__ inputs
 // A function call (circom `function` with run-time loops / branches): the thread copies the arguments into
 // the callee's registers (local memory: they are indexed dynamically) and interprets the body.
 // (TAG: one copy of the function per interpreter build - ptxas 12.9 crashes on a module in which several kernels share it)
+// INV (600 division steps) and POW (a square-and-multiply ladder) are loops of hundreds of steps over many registers; the
+// interpreter skips them in its hot loop and runs them afterwards, per level, through this function (one copy per build, TAG)
+template <int PRIME, int TAG>
+__device__ __noinline__ void exec_slow_op(u32 opcode, u32 *r, const u32 *a, const u32 *b, u32 prime_rt) {
+    const FrParams &P = CW_FR(PRIME, prime_rt);
+    if (opcode == OP_INV) fr_inv_mont(r, a, P);
+    else fr_pow_mont(r, a, b, P);
+}
+
 template <int PRIME, bool BP, int TAG>
 __device__ __noinline__ void exec_call(const TapeDev &tp, u32 call_off, uint4 *base, const u32 *plane_base,
                                        u32 bt_log2, u32 li, u32 *r, int *err) {
@@ -243,7 +253,8 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
         // Calls are the last work items of their level (the items of a level are sorted by opcode, CALL is the largest) and
         // run in a loop of their own after the others: the call site - an ABI call with a 6 KB frame - then does not sit
         // in the hot loop, whose values would otherwise have to survive it in memory.
-        const u32 n_calls = HAS_CALLS ? __ldg(&tp.level_calls[l]) : 0u;
+        const u32 info = (HAS_CALLS || tp.has_slow) ? __ldg(&tp.level_info[l]) : 0u;
+        const u32 n_calls = HAS_CALLS ? (info & 0x7FFFFFFFu) : 0u;
         const u32 n = (le - lb - n_calls) << bt_log2;
         const u32 le_next = (l + 1 < tp.n_levels) ? tp.level_start[l + 2] : le;
         // COOP (one instance per CTA): the warp walks the level together - lanes beyond the level's end idle in
@@ -331,9 +342,11 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
                                                          : (u256_bitlen_dev(a) <= b[0]);
                     if (!ok && inst < batch) atomicMin(&first_assert[inst], opw.w);
                     has_value = false;  // asserts have no destination value
+                } else if (opcode == OP_INV || opcode == OP_POW) {
+                    has_value = false;   // the slow operators of the level run after the others (below); never fused
                 } else {
                     int e = 0;
-                    fr_exec(opcode, r, a, b, opw.w, P, e);
+                    fr_exec_t<false>(opcode, r, a, b, opw.w, P, e);
                     if (e && inst < batch) err[inst] = 1;
                 }
             }
@@ -365,6 +378,19 @@ __global__ void __launch_bounds__(CW_TAPE_LB, CW_TAPE_MINB)
                         stg256(base + ((size_t)(d + lane) << 1), r);
                     }
                 }
+            }
+        }
+        if (info >> 31) {   // INV / POW items of this level (work items of one word)
+            for (u32 w = threadIdx.x; w < n; w += blockDim.x) {
+                const u32 li = w & bt_mask;
+                const uint4 opw = __ldg(&tp.ops[FUSED ? __ldg(&tp.items[lb + (w >> bt_log2)]) : lb + (w >> bt_log2)]);
+                const u32 opcode = opw.x & 0xFFu;
+                if (opcode != OP_INV && opcode != OP_POW) continue;
+                u32 a[8], b[8], r[8];
+                load_operand<BP>(a, opw.y, base, plane_base, tp.consts, bt_log2, li);
+                load_operand<BP>(b, opw.z, base, plane_base, tp.consts, bt_log2, li);
+                exec_slow_op<PRIME, (HAS_CALLS ? 64 : 0) + (BP ? 32 : 0) + (BT + 1) * 2 + (FUSED ? 1 : 0)>(opcode, r, a, b, tp.prime);
+                store_slot(r, base, opw.x >> 8, bt_log2, li);
             }
         }
         if (HAS_CALLS && n_calls) {

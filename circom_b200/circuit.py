@@ -32,9 +32,10 @@ PRIMES = {
     "vesta": 28948022309329048855892746252171976963363056481941647379679742748393362948097,
     "secq256r1": 115792089210356248762697446949407573530086143415290314195533631308867097853951,
     "bls12377": 8444461749428370424248824938781546531375899335154063827935233455917409239041,
+    "goldilocks": 18446744069414584321,
 }
-# the 256-bit primes of program_structure/src/utils/constants.rs:3-13 (goldilocks, a 64-bit field, is not a 256-bit element path)
-PRIME_IDS = {"bn128": 0, "bls12381": 1, "grumpkin": 2, "pallas": 3, "vesta": 4, "secq256r1": 5, "bls12377": 6}
+# the primes of program_structure/src/utils/constants.rs:3-13 (goldilocks: 64-bit values in the same 32-byte elements)
+PRIME_IDS = {"bn128": 0, "bls12381": 1, "grumpkin": 2, "pallas": 3, "vesta": 4, "secq256r1": 5, "bls12377": 6, "goldilocks": 7}
 
 # OperatorType (compiler/src/intermediate_representation/compute_bucket.rs:7-34) + moves
 OPS = {

@@ -61,7 +61,8 @@ FrParams make_dev_params(const FieldParams &F) {
     split(p.qm2, qm2);
     p.np32 = F.np32;
     p.qbits = F.qbits;
-    p.top_mask = (F.qbits - 224 >= 32) ? 0xFFFFFFFFu : ((1u << (F.qbits - 224)) - 1u);
+    // lboMask of the limb that holds the top bit; fr_mask_wrap clears the limbs above it (goldilocks: limb 1, all ones)
+    p.top_mask = (F.qbits % 32 == 0) ? 0xFFFFFFFFu : ((1u << (F.qbits % 32)) - 1u);
     return p;
 }
 
@@ -1069,7 +1070,8 @@ int cw_batch_wtns_bytes(cw_batch *b, uint32_t inst, uint8_t *out, size_t cap, si
     if (!b || inst >= b->batch) return fail(CW_EINVAL, "bad instance");
     if (!b->ran) return fail(CW_ESTATE, "batch has not been run");
     const Tape &t = b->c->tape;
-    size_t need = 76 + 32 * (size_t)t.n_witness;
+    const size_t n8 = field_bytes(t.F);
+    size_t need = 44 + n8 + n8 * (size_t)t.n_witness;
     if (len) *len = need;
     if (!out) return CW_OK;
     if (cap < need) return fail(CW_EINVAL, "buffer too small");

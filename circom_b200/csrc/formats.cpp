@@ -40,6 +40,10 @@ inline bool wire_less(uint32_t a, uint32_t b) {
 }
 }  // namespace
 
+// bytes of one field element in files: whole 64-bit words of the prime (constraint_list/src/r1cs_porting.rs:6-10;
+// 32 for the 256-bit primes, 8 for goldilocks - n8 of c_elements/common64/main.cpp:327)
+size_t field_bytes(const FieldParams &F) { return (size_t)((F.qbits + 63) / 64) * 8; }
+
 // Section order and header layout follow constraint_list/src/r1cs_porting.rs:19-53 and
 // constraint_writers/src/r1cs_writer.rs:6-14,49-72,93-101,246-269,328-341.
 void write_r1cs(const R1csData &r, const FieldParams &F, const std::string &path) {
@@ -50,7 +54,8 @@ void write_r1cs(const R1csData &r, const FieldParams &F, const std::string &path
     // constraints section first
     uint64_t nnz = r.col.size();
     uint64_t m = r.n_constraints;
-    uint64_t csize = 3 * m * 4 + nnz * (4 + 32);
+    const size_t fb = field_bytes(F);
+    uint64_t csize = 3 * m * 4 + nnz * (4 + fb);
     f.put<uint32_t>(2);
     f.put<uint64_t>(csize);
     std::vector<uint32_t> order;
@@ -62,14 +67,14 @@ void write_r1cs(const R1csData &r, const FieldParams &F, const std::string &path
         std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return wire_less(r.col[x], r.col[y]); });
         for (uint32_t i : order) {
             f.put<uint32_t>(r.col[i]);
-            f.w(r.dict[r.coef[i]].v, 32);
+            f.w(r.dict[r.coef[i]].v, fb);
         }
     }
     // header
     f.put<uint32_t>(1);
-    f.put<uint64_t>(4 + 32 + 4 * 4 + 8 + 4);
-    f.put<uint32_t>(32);
-    f.w(F.q.v, 32);
+    f.put<uint64_t>(4 + fb + 4 * 4 + 8 + 4);
+    f.put<uint32_t>((uint32_t)fb);
+    f.w(F.q.v, fb);
     f.put<uint32_t>((uint32_t)r.n_wires);
     f.put<uint32_t>(r.n_pub_out);
     f.put<uint32_t>(r.n_pub_in);
@@ -83,7 +88,7 @@ void write_r1cs(const R1csData &r, const FieldParams &F, const std::string &path
     if (r.has_custom_gates) {
         // custom gates used (r1cs_writer.rs:356-392): u32 count; per gate: NUL-terminated name, u32 #parameters, field elements
         uint64_t sz = 4;
-        for (auto &g : r.gates_used) sz += g.first.size() + 1 + 4 + 32 * g.second.size();
+        for (auto &g : r.gates_used) sz += g.first.size() + 1 + 4 + fb * g.second.size();
         f.put<uint32_t>(4);
         f.put<uint64_t>(sz);
         f.put<uint32_t>((uint32_t)r.gates_used.size());
@@ -91,7 +96,7 @@ void write_r1cs(const R1csData &r, const FieldParams &F, const std::string &path
             f.w(g.first.data(), g.first.size());
             f.put<uint8_t>(0);
             f.put<uint32_t>((uint32_t)g.second.size());
-            for (const U256 &p : g.second) f.w(p.v, 32);
+            for (const U256 &p : g.second) f.w(p.v, fb);
         }
         // custom gates applied (r1cs_writer.rs:408-440): u32 count; per application: u32 gate index, u32 #wires, u64 wires
         sz = 4;
@@ -136,14 +141,15 @@ void read_r1cs(const std::string &path, R1csData &out) {
         pos += len;
     }
     if (!hdr || !cons) throw std::runtime_error("r1cs: missing header or constraint section");
-    need(hdr, 4 + 32 + 28);
-    uint32_t fs = u32(hdr);
-    if (fs != 32 || hdr_len < 4 + 32 + 28) throw std::runtime_error("r1cs: only 32-byte fields are supported");
-    U256 q;
-    memcpy(q.v, &buf[hdr + 4], 32);
+    need(hdr, 4);
+    const uint32_t fs = u32(hdr);
+    if ((fs != 32 && fs != 8) || hdr_len < 4 + (size_t)fs + 28) throw std::runtime_error("r1cs: only 32-byte and 8-byte fields are supported");
+    need(hdr, 4 + (size_t)fs + 28);
+    U256 q = u256_from_u64(0);
+    memcpy(q.v, &buf[hdr + 4], fs);
     out.prime_id = prime_id_of(q);
-    if (out.prime_id < 0) throw std::runtime_error("r1cs: unsupported prime");
-    size_t h = hdr + 4 + 32;
+    if (out.prime_id < 0 || field_bytes(make_field(out.prime_id)) != fs) throw std::runtime_error("r1cs: unsupported prime");
+    size_t h = hdr + 4 + fs;
     out.n_wires = u32(h);
     out.n_pub_out = u32(h + 4);
     out.n_pub_in = u32(h + 8);
@@ -159,24 +165,24 @@ void read_r1cs(const std::string &path, R1csData &out) {
         if (p + 4 > end) throw std::runtime_error("r1cs: constraint section too short");
         uint32_t n = u32(p);
         p += 4;
-        if (p + (size_t)n * 36 > end) throw std::runtime_error("r1cs: constraint section too short");
+        if ((uint64_t)n * (4 + fs) > end - p) throw std::runtime_error("r1cs: constraint section too short");
         size_t first = out.col.size();
         for (uint32_t j = 0; j < n; ++j) {
             uint32_t w = u32(p);
             if (w >= out.n_wires) throw std::runtime_error("r1cs: wire id out of range");
-            std::string key((const char *)&buf[p + 4], 32);
+            std::string key((const char *)&buf[p + 4], fs);
             auto it = idx.find(key);
             uint32_t id;
             if (it == idx.end()) {
-                U256 c;
-                memcpy(c.v, key.data(), 32);
+                U256 c = u256_from_u64(0);
+                memcpy(c.v, key.data(), fs);
                 id = (uint32_t)out.dict.size();
                 out.dict.push_back(c);
                 idx.emplace(std::move(key), id);
             } else id = it->second;
             out.col.push_back(w);
             out.coef.push_back(id);
-            p += 36;
+            p += 4 + fs;
         }
         // numeric order inside the CSR row (files carry the byte-string order)
         std::vector<std::pair<uint32_t, uint32_t>> tmp;
@@ -207,9 +213,9 @@ void read_r1cs(const std::string &path, R1csData &out) {
             if (q0 + 4 > qe) throw std::runtime_error("r1cs: custom-gate section too short");
             uint32_t np = u32(q0);
             q0 += 4;
-            if ((uint64_t)np * 32 > qe - q0) throw std::runtime_error("r1cs: custom-gate section too short");
-            std::vector<U256> ps(np);
-            for (uint32_t k = 0; k < np; ++k, q0 += 32) memcpy(ps[k].v, &buf[q0], 32);
+            if ((uint64_t)np * fs > qe - q0) throw std::runtime_error("r1cs: custom-gate section too short");
+            std::vector<U256> ps(np, u256_from_u64(0));
+            for (uint32_t k = 0; k < np; ++k, q0 += fs) memcpy(ps[k].v, &buf[q0], fs);
             out.gates_used.emplace_back(std::move(name), std::move(ps));
         }
     }
@@ -258,16 +264,17 @@ void read_wtns(const std::string &path, int &prime_id, std::vector<uint64_t> &wi
         if (ty == 2) { s2 = pos; s2_len = len; }
         pos += len;
     }
-    if (!s1 || !s2 || s1_len < 4 + 32 + 4) throw std::runtime_error("wtns: missing section");
-    if (u32(s1) != 32) throw std::runtime_error("wtns: only 32-byte fields are supported");
-    U256 q;
-    memcpy(q.v, &buf[s1 + 4], 32);
+    if (!s1 || !s2 || s1_len < 4 + 8 + 4) throw std::runtime_error("wtns: missing section");
+    const uint32_t n8 = u32(s1);
+    if ((n8 != 32 && n8 != 8) || s1_len < 4 + (size_t)n8 + 4) throw std::runtime_error("wtns: only 32-byte and 8-byte fields are supported");
+    U256 q = u256_from_u64(0);
+    memcpy(q.v, &buf[s1 + 4], n8);
     prime_id = prime_id_of(q);
-    if (prime_id < 0) throw std::runtime_error("wtns: unsupported prime");
-    uint32_t n = u32(s1 + 36);
-    if ((uint64_t)n * 32 != s2_len) throw std::runtime_error("wtns: witness section has the wrong size");
-    witness.resize((size_t)n * 4);
-    memcpy(witness.data(), &buf[s2], (size_t)n * 32);
+    if (prime_id < 0 || field_bytes(make_field(prime_id)) != n8) throw std::runtime_error("wtns: unsupported prime");
+    uint32_t n = u32(s1 + 4 + n8);
+    if ((uint64_t)n * n8 != s2_len) throw std::runtime_error("wtns: witness section has the wrong size");
+    witness.assign((size_t)n * 4, 0);   // always 4 x u64 per value in memory
+    for (uint32_t i = 0; i < n; ++i) memcpy(&witness[(size_t)i * 4], &buf[s2 + (size_t)i * n8], n8);
     FieldParams F = make_field(prime_id);
     for (uint32_t i = 0; i < n; ++i) {
         U256 v;
@@ -278,7 +285,8 @@ void read_wtns(const std::string &path, int &prime_id, std::vector<uint64_t> &wi
 
 // writeBinWitness (c_elements/common/main.cpp:288-334)
 std::vector<uint8_t> wtns_bytes(const FieldParams &F, const uint64_t *witness, uint64_t n_witness) {
-    std::vector<uint8_t> o(76 + 32 * n_witness);
+    const size_t n8 = field_bytes(F);
+    std::vector<uint8_t> o(44 + n8 + n8 * n_witness);
     uint8_t *p = o.data();
     auto put32 = [&](uint32_t v) { memcpy(p, &v, 4); p += 4; };
     auto put64 = [&](uint64_t v) { memcpy(p, &v, 8); p += 8; };
@@ -287,14 +295,15 @@ std::vector<uint8_t> wtns_bytes(const FieldParams &F, const uint64_t *witness, u
     put32(2);
     put32(2);
     put32(1);
-    put64(8 + 32);
-    put32(32);
-    memcpy(p, F.q.v, 32);
-    p += 32;
+    put64(8 + n8);
+    put32((uint32_t)n8);
+    memcpy(p, F.q.v, n8);
+    p += n8;
     put32((uint32_t)n_witness);
     put32(2);
-    put64(32ull * n_witness);
-    memcpy(p, witness, 32 * n_witness);
+    put64((uint64_t)n8 * n_witness);
+    if (n8 == 32) memcpy(p, witness, 32 * n_witness);
+    else for (uint64_t i = 0; i < n_witness; ++i) memcpy(p + i * n8, witness + 4 * i, n8);   // low words of the 4 x u64 values
     return o;
 }
 
@@ -310,7 +319,9 @@ void write_dat(const Tape &t, const std::string &path) {
     for (uint64_t i = 0; i < t.n_witness; ++i) f.put<uint64_t>(t.witness2signal[i]);
     // circuitConstants (generate_dat_constant_list, c_code_generator.rs:616-679): 40 bytes per constant -
     // {i32 shortVal, u32 type, n * R mod q}: values inside the signed 32-bit range carry shortVal and type
-    // 0x40000000 (short + Montgomery), all others 0 and 0xC0000000 (long Montgomery)
+    // 0x40000000 (short + Montgomery), all others 0 and 0xC0000000 (long Montgomery).  The goldilocks runtime keeps its
+    // constants as literals in the generated code: no constant list in its .dat (generate_dat_file, :838-841)
+    if (field_bytes(t.F) == 8) return;
     for (const U256 &c : t.dat_consts) {
         U256 neg;
         u256_sub(neg, t.F.q, c);

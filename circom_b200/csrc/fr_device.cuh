@@ -27,8 +27,8 @@ struct FrParams {
     u32 r2[8];    // 2^512 mod q
     u32 qm2[8];   // q - 2 (Fermat exponent)
     u32 np32;     // -q^-1 mod 2^32
-    u32 qbits;    // 254 / 255
-    u32 top_mask; // lboMask on limb 7 (generic/fr.cpp:16)
+    u32 qbits;    // 254 / 255 / 256; 64 for goldilocks
+    u32 top_mask; // lboMask on the limb of the top bit (generic/fr.cpp:16)
     u32 pad;
 };
 
@@ -517,7 +517,12 @@ CW_HD void u256_shr(u32 *r, const u32 *a, u32 k) {
     u256_set(r, t);
 }
 CW_HD void fr_mask_wrap(u32 *r, const FrParams &P) {  // top-limb mask then one conditional subtraction
-    r[7] &= P.top_mask;
+    if (P.qbits > 224u) r[7] &= P.top_mask;   // every 256-bit prime
+    else {                                    // goldilocks (c_elements/goldilocks/fr.hpp:177-181,255-270): 64-bit words
+        const u32 top = (P.qbits - 1u) >> 5;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r[i] = (u32)i < top ? r[i] : ((u32)i == top ? (r[i] & P.top_mask) : 0u);
+    }
     fr_cond_sub(r, P);
 }
 // decode the shift amount: returns 0 = plain by k, 1 = opposite direction by k, 2 = result is zero

@@ -11,7 +11,7 @@ namespace cw {
 // instruction operands (no registers, no loads).
 // bn128 and bls12381 have kernel builds of their own (template PRIME = 0 / 1: the table index folds into the
 // instruction); the other 256-bit primes share one build (PRIME = -1) that takes the index from its arguments.
-constexpr int N_PRIMES_DEV = 7;
+constexpr int N_PRIMES_DEV = 8;
 __constant__ FrParams c_fr[N_PRIMES_DEV];
 #define CW_FR(PRIME, rt) c_fr[(PRIME) >= 0 ? (PRIME) : (int)(rt)]
 
@@ -611,7 +611,9 @@ __device__ __forceinline__ void r1cs_lc(u32 *acc, const R1csDev &R, unsigned lon
                                         u32 li, const FrParams &P, unsigned long long *__restrict__ first_bad_inst) {
     u256_set_u32(acc, 0);
     unsigned long long plo = 0, phi = 0, nlo = 0, nhi = 0;
-    const bool lazy = e - b < 65536ull;   // 2^16 terms below 2^112 cannot overflow 128 bits
+    // 2^16 terms below 2^112 cannot overflow 128 bits; the sum enters the accumulator unreduced, so it must stay below q
+    // (every 256-bit prime; not goldilocks, whose terms take the modular path)
+    const bool lazy = e - b < 65536ull && P.qbits > 130u;
     for (unsigned long long k = b; k < e; ++k) {
         const uint4 term = __ldg(&R.terms[k]);
         const u32 loc = term.x, ci = term.y, kw = term.z, brow = term.w;

@@ -105,6 +105,7 @@ void deserialize_tape(const uint8_t *data, size_t len, Tape &t);
 void write_r1cs(const R1csData &r, const FieldParams &F, const std::string &path);
 void read_r1cs(const std::string &path, R1csData &out);
 std::vector<uint8_t> wtns_bytes(const FieldParams &F, const uint64_t *witness, uint64_t n_witness);
+size_t field_bytes(const FieldParams &F);   // element size in .r1cs / .wtns files: 32, or 8 for goldilocks
 void write_dat(const Tape &t, const std::string &path);
 // .wtns (main.cpp:288-334 / witness_calculator.js:212-276): returns the witness as 4 x u64 limbs per entry
 void read_wtns(const std::string &path, int &prime_id, std::vector<uint64_t> &witness);

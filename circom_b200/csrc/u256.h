@@ -41,7 +41,7 @@ inline uint64_t u256_sub(U256 &r, const U256 &a, const U256 &b) {
     return (uint64_t)br;
 }
 
-constexpr int CW_N_PRIMES = 7;  // bn128, bls12381, grumpkin, pallas, vesta, secq256r1, bls12377
+constexpr int CW_N_PRIMES = 8;  // bn128, bls12381, grumpkin, pallas, vesta, secq256r1, bls12377, goldilocks
 // id of the prime with modulus q, or -1
 int prime_id_of(const struct U256 &q);
 
@@ -105,7 +105,8 @@ struct FieldParams {
 inline FieldParams make_field(int prime_id) {
     FieldParams f;
     f.prime_id = prime_id;
-    // program_structure/src/utils/constants.rs:3-13 (goldilocks, 64 bits, has no 256-bit element path)
+    // program_structure/src/utils/constants.rs:3-13.  goldilocks (2^64 - 2^32 + 1, c_elements/goldilocks/fr.hpp:11) runs in
+    // the same 32-byte elements with six zero limbs: R = 2^256 Montgomery arithmetic holds for any odd modulus
     static const uint64_t Q[CW_N_PRIMES][4] = {
         {0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL},  // bn128
         {0xffffffff00000001ULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL, 0x73eda753299d7d48ULL},  // bls12381
@@ -114,6 +115,7 @@ inline FieldParams make_field(int prime_id) {
         {0x8c46eb2100000001ULL, 0x224698fc0994a8ddULL, 0x0000000000000000ULL, 0x4000000000000000ULL},  // vesta
         {0xffffffffffffffffULL, 0x00000000ffffffffULL, 0x0000000000000000ULL, 0xffffffff00000001ULL},  // secq256r1
         {0x0a11800000000001ULL, 0x59aa76fed0000001ULL, 0x60b44d1e5c37b001ULL, 0x12ab655e9a2ca556ULL},  // bls12377
+        {0xffffffff00000001ULL, 0x0000000000000000ULL, 0x0000000000000000ULL, 0x0000000000000000ULL},  // goldilocks
     };
     memcpy(f.q.v, Q[prime_id >= 0 && prime_id < CW_N_PRIMES ? prime_id : 0], 32);
     for (int i = 0; i < 4; ++i) f.half.v[i] = (f.q.v[i] >> 1) | (i < 3 ? (f.q.v[i + 1] << 63) : 0);

@@ -38,13 +38,15 @@ extern "C" {
 /* primes (program_structure/src/utils/constants.rs:3-6) */
 #define CW_PRIME_BN128 0
 #define CW_PRIME_BLS12381 1
-/* the other 256-bit primes of constants.rs:7-13 (one shared kernel build; goldilocks - a 64-bit field with its own
- * element layout, c_elements/goldilocks/fr.hpp:10-60 - is not supported) */
+/* the other primes of constants.rs:7-13 (one shared kernel build).  goldilocks (c_elements/goldilocks/fr.hpp:10-60) runs
+ * in the same 32-byte elements with its upper 24 bytes zero; its .wtns / .r1cs files carry 8-byte elements
+ * (c_elements/common64/main.cpp:327, constraint_list/src/r1cs_porting.rs:6-10) */
 #define CW_PRIME_GRUMPKIN 2
 #define CW_PRIME_PALLAS 3
 #define CW_PRIME_VESTA 4
 #define CW_PRIME_SECQ256R1 5
 #define CW_PRIME_BLS12377 6
+#define CW_PRIME_GOLDILOCKS 7
 
 /* cw_circuit_load flags */
 #define CW_FLAG_NO_ASSERTS 1u /* --sanity_check 0: drop `===` asserts (assert_bucket.rs:73) */

@@ -261,10 +261,27 @@ def build_calculator(prime: str, circuit_cpp: str, out_bin: str, opt: str = "-O3
     return out_bin
 
 
+def build_goldilocks(force: bool = False) -> str:
+    """The reference's goldilocks field library is one header (c_elements/goldilocks/fr.hpp) of inline functions on
+    uint64_t: compile it, where it lies, behind the C entry point of oracle/goldilocks_wrap.cpp."""
+    so = os.path.join(OUT, "libfr_goldilocks.so")
+    if not have_reference():
+        if os.path.exists(so):
+            return so
+        raise RuntimeError("reference tree absent and oracle/_ref not prebuilt")
+    if not force and os.path.exists(so):
+        return so
+    os.makedirs(OUT, exist_ok=True)
+    _run(["g++"] + CXXFLAGS + ["-I", os.path.join(REF, "goldilocks"), "-I", os.path.join(HERE, "gmp_shim"), "-shared",
+                               "-o", so, os.path.join(HERE, "goldilocks_wrap.cpp"), GMP_SO])
+    return so
+
+
 def build_all(force: bool = False):
     os.makedirs(OUT, exist_ok=True)
     for p in PRIMES:
         build_prime(p, force)
+    build_goldilocks(force)
 
 
 if __name__ == "__main__":

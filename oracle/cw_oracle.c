@@ -135,8 +135,11 @@ static void shr4(fe *r, const fe *a, unsigned k) {
     *r = o;
 }
 static void wrap_bits(const field_t *F, fe *r) {                          /* lboMask + one conditional -q :293-303 */
-    u64 mask = F->qbits >= 256 ? ~0ull : ((1ull << (F->qbits - 192)) - 1);
-    r->v[3] &= mask;
+    /* whole 64-bit words of the prime: 4 for the 256-bit primes, 1 for goldilocks (goldilocks/fr.hpp:177-181,255-270) */
+    const unsigned top = (F->qbits - 1) / 64;
+    u64 mask = F->qbits % 64 == 0 ? ~0ull : ((1ull << (F->qbits % 64)) - 1);
+    r->v[top] &= mask;
+    for (unsigned i = top + 1; i < 4; ++i) r->v[i] = 0;
     if (cmp4(r, &F->q) >= 0) sub4(r, r, &F->q);
 }
 static int shift_kind(const field_t *F, const fe *b, unsigned *k) {      /* :1995-2027,2157-2307 */
@@ -236,8 +239,8 @@ typedef struct {
 #define RIDX(r) ((u32)(r))
 
 static void field_init(field_t *F, u32 prime) {
-    /* program_structure/src/utils/constants.rs:3-13: bn128, bls12381, grumpkin, pallas, vesta, secq256r1, bls12377 */
-    static const u64 Q[7][4] = {
+    /* program_structure/src/utils/constants.rs:3-13: bn128, bls12381, grumpkin, pallas, vesta, secq256r1, bls12377, goldilocks */
+    static const u64 Q[8][4] = {
         {0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL},
         {0xffffffff00000001ULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL, 0x73eda753299d7d48ULL},
         {0x3c208c16d87cfd47ULL, 0x97816a916871ca8dULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL},
@@ -245,8 +248,9 @@ static void field_init(field_t *F, u32 prime) {
         {0x8c46eb2100000001ULL, 0x224698fc0994a8ddULL, 0x0000000000000000ULL, 0x4000000000000000ULL},
         {0xffffffffffffffffULL, 0x00000000ffffffffULL, 0x0000000000000000ULL, 0xffffffff00000001ULL},
         {0x0a11800000000001ULL, 0x59aa76fed0000001ULL, 0x60b44d1e5c37b001ULL, 0x12ab655e9a2ca556ULL},
+        {0xffffffff00000001ULL, 0, 0, 0},
     };
-    memcpy(F->q.v, Q[prime < 7 ? prime : 0], 32);
+    memcpy(F->q.v, Q[prime < 8 ? prime : 0], 32);
     for (int i = 0; i < 4; ++i) F->half.v[i] = (F->q.v[i] >> 1) | (i < 3 ? F->q.v[i + 1] << 63 : 0);
     u64 inv = 1;
     for (int i = 0; i < 6; ++i) inv *= 2 - F->q.v[0] * inv;
@@ -513,8 +517,8 @@ int64_t orc_r1cs_check(const circuit *c, const u64 *witness) {
 
 /* single operator, canonical in/out (for pinning against the reference library); 0 on div by zero */
 int orc_apply(u32 prime, u32 op, const u64 *a, const u64 *b, const u64 *c3, u64 *r) {
-    static field_t F[7]; static int init[7] = {0, 0, 0, 0, 0, 0, 0};
-    if (prime >= 7) return -1;
+    static field_t F[8]; static int init[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (prime >= 8) return -1;
     if (!init[prime]) { field_init(&F[prime], prime); init[prime] = 1; }
     fe z = fe_u64(0);
     return f_apply(&F[prime], op, (fe *)r, (const fe *)a, b ? (const fe *)b : &z, c3 ? (const fe *)c3 : &z);

@@ -23,6 +23,7 @@ PRIMES = {
     "vesta": 28948022309329048855892746252171976963363056481941647379679742748393362948097,
     "secq256r1": 115792089210356248762697446949407573530086143415290314195533631308867097853951,
     "bls12377": 8444461749428370424248824938781546531375899335154063827935233455917409239041,
+    "goldilocks": 18446744069414584321,
 }
 
 # IR opcodes: OperatorType of compiler/src/intermediate_representation/compute_bucket.rs:7-34

@@ -88,6 +88,10 @@ mp_limb_t __gmpn_rshift(mp_ptr, mp_srcptr, mp_size_t, unsigned int);
 #define mpz_get_str __gmpz_get_str
 #define mpz_powm __gmpz_powm
 #define mpz_invert __gmpz_invert
+/* used by c_elements/goldilocks/fr.hpp:84-106 */
+#define mpz_add_ui __gmpz_add_ui
+#define mpz_get_ui __gmpz_get_ui
+#define mpz_tdiv_q_2exp __gmpz_tdiv_q_2exp
 
 void __gmpz_init(mpz_ptr);
 void __gmpz_clear(mpz_ptr);
@@ -109,6 +113,9 @@ void __gmpz_fdiv_q(mpz_ptr, mpz_srcptr, mpz_srcptr);
 char *__gmpz_get_str(char *, int, mpz_srcptr);
 void __gmpz_powm(mpz_ptr, mpz_srcptr, mpz_srcptr, mpz_srcptr);
 int __gmpz_invert(mpz_ptr, mpz_srcptr, mpz_srcptr);
+void __gmpz_add_ui(mpz_ptr, mpz_srcptr, unsigned long);
+unsigned long __gmpz_get_ui(mpz_srcptr);
+void __gmpz_tdiv_q_2exp(mpz_ptr, mpz_srcptr, mp_bitcnt_t);
 
 #ifdef __cplusplus
 }

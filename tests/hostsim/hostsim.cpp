@@ -31,7 +31,7 @@ static FrParams dev_params(const FieldParams &F) {
     split(p.qm2, qm2);
     p.np32 = F.np32;
     p.qbits = F.qbits;
-    p.top_mask = (F.qbits - 224 >= 32) ? 0xFFFFFFFFu : ((1u << (F.qbits - 224)) - 1u);
+    p.top_mask = (F.qbits % 32 == 0) ? 0xFFFFFFFFu : ((1u << (F.qbits % 32)) - 1u);
     return p;
 }
 

@@ -269,3 +269,51 @@ def test_wtns_reader_round_trip(tmp_path):
     for damaged in (raw[:100], raw[:4] + b"\x03" + raw[5:], b"wtnz" + raw[4:], raw[:76] + b"\xff" * 32 + raw[108:]):
         open(p, "wb").write(damaged)
         assert native.lib.cw_wtns_read(p.encode(), ctypes.byref(pid), ctypes.byref(n), None, 0) == native.CW_EFORMAT
+
+
+def test_goldilocks_files_carry_8_byte_elements(tmp_path):
+    """goldilocks: field size 8 in `.r1cs` (constraint_list/src/r1cs_porting.rs:6-10: whole 64-bit words of the prime)
+    and n8 = 8 in `.wtns` (c_elements/common64/main.cpp:312-353); in memory a value stays 4 x u64 with zero upper words"""
+    import ctypes
+    from circom_b200 import native
+    d = CircuitDesc("goldilocks")
+    d.set_main(C.less_than(d, 12))
+    c = Circuit(d, host_only=True)
+    p = str(tmp_path / "g.r1cs")
+    R1cs(c).write(p, d.main.n_out, 0, d.main.n_in)
+    raw = open(p, "rb").read()
+    r = parse_r1cs(raw)
+    h = raw.index(struct.pack("<IQ", 1, 4 + 8 + 28)) + 12      # header section: 4 + field size + 28 bytes
+    assert struct.unpack_from("<I", raw, h)[0] == 8 and r["q"] == d.q == 2**64 - 2**32 + 1
+    sig = evaluate(d, {"in": [77, 3000]})
+    w = [sig[k] for k in c.witness2signal().astype(np.int64)]
+    assert len(r["cons"]) == c.stats["n_constraints"] > 0
+    for A, B, Cc in r["cons"]:
+        a, b, cc = (sum(v * w[k] for k, v in X.items()) % d.q for X in (A, B, Cc))
+        assert (a * b - cc) % d.q == 0
+    # read -> write reproduces the file
+    r2 = R1cs(p)
+    p2 = str(tmp_path / "g2.r1cs")
+    r2.write(p2)
+    assert open(p2, "rb").read() == raw
+    # .wtns as the reference's goldilocks runtime writes it
+    n = len(w)
+    wt = b"wtns" + struct.pack("<II", 2, 2) + struct.pack("<IQ", 1, 8 + 8) + struct.pack("<IQI", 8, d.q, n) + \
+        struct.pack("<IQ", 2, 8 * n) + b"".join(struct.pack("<Q", v) for v in w)
+    wp = str(tmp_path / "g.wtns")
+    open(wp, "wb").write(wt)
+    pid, cnt = ctypes.c_int(), ctypes.c_uint64()
+    out = np.zeros((n, 4), dtype=np.uint64)
+    assert native.lib.cw_wtns_read(wp.encode(), ctypes.byref(pid), ctypes.byref(cnt), out.ctypes.data, n) == 0
+    assert pid.value == 7 and cnt.value == n and limbs_of(out) == w
+    # a 32-byte-element file that names the goldilocks prime is malformed; so is a value that is not reduced
+    bad = b"wtns" + struct.pack("<II", 2, 2) + struct.pack("<IQ", 1, 8 + 32) + struct.pack("<I", 32) + d.q.to_bytes(32, "little") + \
+        struct.pack("<I", 1) + struct.pack("<IQ", 2, 32) + (1).to_bytes(32, "little")
+    open(wp, "wb").write(bad)
+    assert native.lib.cw_wtns_read(wp.encode(), ctypes.byref(pid), ctypes.byref(cnt), None, 0) == native.CW_EFORMAT
+    open(wp, "wb").write(wt[:-8] + struct.pack("<Q", d.q))
+    assert native.lib.cw_wtns_read(wp.encode(), ctypes.byref(pid), ctypes.byref(cnt), None, 0) == native.CW_EFORMAT
+
+
+def limbs_of(a):
+    return [int.from_bytes(r.tobytes(), "little") for r in np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)]

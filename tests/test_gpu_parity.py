@@ -13,16 +13,16 @@ from circom_b200 import circuits as C
 from circom_b200.witness_calculator import Circuit, Batch, R1cs, WitnessCalculator, builder
 from oracle.field_model import Field, OP_NAMES
 from oracle.ir_eval import evaluate, check_r1cs
-from tests.util import ints_to_limbs, limbs_to_ints, edge_values, rand_operand, flat_inputs
+from tests.util import ints_to_limbs, limbs_to_ints, edge_values, rand_operand, flat_inputs, PRIME_NAMES
 from tests.test_lowering_cpu import CIRCUITS
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("prime", range(7))
+@pytest.mark.parametrize("prime", range(8))
 def test_device_field_ops(prime):
-    """device Fr_* equivalents (fr.hpp:28-70) over all operators, random + edge operands, all seven 256-bit primes"""
-    F = Field(["bn128", "bls12381", "grumpkin", "pallas", "vesta", "secq256r1", "bls12377"][prime])
+    """device Fr_* equivalents (fr.hpp:28-70; goldilocks/fr.hpp) over all operators, random + edge operands, all eight primes"""
+    F = Field(PRIME_NAMES[prime])
     q = F.q
     rng = random.Random(991 + prime)
     edges = edge_values(q)
@@ -400,9 +400,9 @@ def test_r1cs_check_of_files(tmp_path):
     assert native.lib.cw_r1cs_check_files(rp.encode(), wp.encode(), 0, ctypes.byref(fb)) == 0 and fb.value >= 0
 
 
-@pytest.mark.parametrize("prime", ["grumpkin", "pallas", "vesta", "secq256r1", "bls12377"])
+@pytest.mark.parametrize("prime", ["grumpkin", "pallas", "vesta", "secq256r1", "bls12377", "goldilocks"])
 def test_other_primes_run_circuits(prime):
-    """the remaining 256-bit primes of constants.rs:7-13 through the shared kernel build: every operator (AllOps),
+    """the remaining primes of constants.rs:7-13 (goldilocks: 64-bit values in the same elements) through the shared kernel build: every operator (AllOps),
     function calls (int_div) and a Poseidon-shaped tape of products, against the evaluator; R1CS check on the result"""
     for name in ("all_ops", "int_div32", "multiplier_n6"):
         mk, gen = CIRCUITS[name]

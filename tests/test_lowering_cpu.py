@@ -11,7 +11,7 @@ from circom_b200.circuit import CircuitDesc, OPS
 from circom_b200 import circuits as C
 from oracle.field_model import Field, OP_NAMES, DivisionByZero
 from oracle.ir_eval import evaluate, check_r1cs
-from tests.util import hostsim, hostsim_run, ints_to_limbs, limbs_to_ints, edge_values, rand_operand
+from tests.util import hostsim, hostsim_run, ints_to_limbs, limbs_to_ints, edge_values, rand_operand, PRIME_NAMES
 
 CIRCUITS = {
     "multiplier2": (lambda d: C.multiplier2(d), lambda r, q: {"a": r.randrange(q), "b": r.randrange(q)}),
@@ -45,9 +45,11 @@ CIRCUITS = {
 }
 
 
-@pytest.mark.parametrize("prime", ["bn128", "bls12381", "grumpkin", "pallas", "vesta", "secq256r1", "bls12377"])
+@pytest.mark.parametrize("prime", ["bn128", "bls12381", "grumpkin", "pallas", "vesta", "secq256r1", "bls12377", "goldilocks"])
 @pytest.mark.parametrize("name", sorted(CIRCUITS))
 def test_tape_matches_oracle(prime, name):
+    if prime == "goldilocks" and name == "ecdsa_calls_1x2":
+        pytest.skip("products of 64-bit limbs need a field above 2^130")
     mk, gen = CIRCUITS[name]
     d = CircuitDesc(prime)
     d.set_main(mk(d))
@@ -131,11 +133,11 @@ def test_assert_failure_is_reported():
     assert st.tolist() == [0]
 
 
-@pytest.mark.parametrize("prime", range(7))
+@pytest.mark.parametrize("prime", range(8))
 def test_device_field_source_vs_model(prime):
     """every operator of fr_device.cuh (compiled for the host) against the python model, for all seven 256-bit primes
     (secq256r1 is a full 256-bit modulus: the ninth limb of the Montgomery product and of the division matter)"""
-    F = Field(["bn128", "bls12381", "grumpkin", "pallas", "vesta", "secq256r1", "bls12377"][prime])
+    F = Field(PRIME_NAMES[prime])
     q = F.q
     rng = random.Random(77 + prime)
     edges = edge_values(q)
@@ -281,12 +283,12 @@ def test_calls_run_on_the_narrow_machine_and_fall_back():
         assert limbs_to_ints(wit[i]) == [exp[k] for k in w2s], i
 
 
-@pytest.mark.parametrize("prime", range(7))
+@pytest.mark.parametrize("prime", range(8))
 def test_modular_inverse_by_division_steps(prime):
     """fr_device.cuh fr_modinv / fr_inv_mont (safegcd, 600 division steps on 30-bit limbs) against python's pow(x, -1, q) for
     every prime: edge values (0 -> 0 as the reference, 1, q-1, powers of two, values around the limb boundaries) and
     random ones; field division through the same path"""
-    name = ["bn128", "bls12381", "grumpkin", "pallas", "vesta", "secq256r1", "bls12377"][prime]
+    name = PRIME_NAMES[prime]
     F = Field(name)
     q = F.q
     rng = random.Random(400 + prime)

@@ -107,7 +107,7 @@ def rand_input(rng, q, edges):
     return rng.randrange(q)
 
 
-@pytest.mark.parametrize("prime", ["bn128", "bls12381"])
+@pytest.mark.parametrize("prime", ["bn128", "bls12381", "goldilocks"])
 @pytest.mark.parametrize("seed", range(40))
 def test_random_circuits_match_the_evaluator(prime, seed):
     rng = random.Random(1000 * seed + (7 if prime == "bn128" else 13))
@@ -131,7 +131,7 @@ def test_random_circuits_match_the_evaluator(prime, seed):
                 raise AssertionError("prime %s seed %d flags %d input %d: witness entries %s differ" % (prime, seed, flags, i, bad))
 
 
-@pytest.mark.parametrize("prime", ["bn128", "bls12381"])
+@pytest.mark.parametrize("prime", ["bn128", "bls12381", "goldilocks"])
 def test_shift_by_negative_signal_amount_is_not_treated_as_narrow(prime):
     """r = (x & 0xFF) >> y with y = q - 200 is a LEFT shift by 200 (Fr_shr, generic/fr.cpp:2189-2263): r is ~208 bits
     wide, and r * 2^100 must be reduced modulo q - the range analysis once took r for an 8-bit value"""

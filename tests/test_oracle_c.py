@@ -13,7 +13,7 @@ import pytest
 from oracle import build_calcs, c_oracle
 from oracle.field_model import Field, OPS
 from oracle.ir_eval import evaluate
-from tests.util import edge_values, flat_inputs, limbs_to_ints, rand_operand
+from tests.util import edge_values, flat_inputs, limbs_to_ints, rand_operand, PRIME_NAMES
 from tests.test_lowering_cpu import CIRCUITS
 from circom_b200.circuit import CircuitDesc
 
@@ -34,9 +34,9 @@ def input_json(desc, arr_row) -> dict:
     return obj
 
 
-@pytest.mark.parametrize("prime_id", [0, 1])
+@pytest.mark.parametrize("prime_id", [0, 1, 7])
 def test_c_oracle_ops_vs_model(prime_id):
-    F = Field(["bn128", "bls12381"][prime_id])
+    F = Field(PRIME_NAMES[prime_id])
     rng = random.Random(31 + prime_id)
     edges = edge_values(F.q)
     for it in range(600):

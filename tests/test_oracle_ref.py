@@ -51,6 +51,45 @@ def test_model_matches_reference_fr(prime):
 
 
 @needs_ref
+def test_model_matches_reference_goldilocks():
+    """goldilocks has a field library of its own in the reference (c_elements/goldilocks/fr.hpp: plain uint64_t values,
+    no Montgomery form, no short / long tags); the same python model with q = 2^64 - 2^32 + 1 must describe it, value
+    for value: shifts with their 64-bit truncation (:166-195), the bit operators with one conditional subtraction
+    (:255-270), comparisons on the signed view (:197-239), inv(0) = 0 (:84-106), Fr_toInt (:23-26)."""
+    import ctypes
+    from oracle import build_ref
+    lib = ctypes.CDLL(build_ref.build_goldilocks())
+    lib.gl_apply.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]
+    lib.gl_is_true.argtypes = [ctypes.c_uint64]
+    F = Field("goldilocks")
+    q = F.q
+    assert q == 2**64 - 2**32 + 1 and F.qbits == 64 and F.mask == 2**64 - 1
+    rng = random.Random(4321)
+    edges = edge_values(q) + [q - 63, q - 65, 2**63, 2**63 + 1, 2**32 * (2**32 - 1), 0xFFFFFFFF, 0xFFFFFFFF00000000 % q]
+    n = 0
+    for it in range(6000):
+        a, b = rand_operand(rng, q, edges), rand_operand(rng, q, edges)
+        if rng.random() < 0.3:
+            b = rng.randrange(300)
+        for op in list(range(1, 24)) + [28]:
+            r = ctypes.c_uint64(0)
+            rc = lib.gl_apply(op, a, b, ctypes.byref(r))
+            if op in (OPS["IDIV"], OPS["MOD"]) and b == 0:
+                assert rc == 1          # the reference process dies of SIGFPE there; the model raises
+                continue
+            assert rc == 0
+            exp = F.inv(a) if op == 28 else F.apply(op, a, b)
+            n += 1
+            assert r.value == exp, (OP_NAMES.get(op, op), hex(a), hex(b), hex(r.value), hex(exp))
+        assert lib.gl_is_true(a) == int(a != 0)
+    assert n > 100000
+    # Fr_toInt: the signed view, truncated to int (goldilocks/fr.hpp:23-26)
+    lib.gl_to_int.argtypes = [ctypes.c_uint64]
+    for v in (0, 1, 5, 2**31 - 1, q - 1, q - 7, q - 2**31):
+        assert lib.gl_to_int(v) == (v if v <= F.half else v - q)
+
+
+@needs_ref
 def test_reference_division_by_zero_is_zero():
     """Fr_inv ignores mpz_invert's failure (generic/fr.cpp:2895-2906): x/0 == 0 with GMP 6.3."""
     from oracle.ref_fr import RefFr

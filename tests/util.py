@@ -11,6 +11,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOSTSIM_DIR = os.path.join(ROOT, "tests", "hostsim")
 HOSTSIM_SO = os.path.join(HOSTSIM_DIR, "libhostsim.so")
+# prime ids of include/circom_b200.h (program_structure/src/utils/constants.rs:3-13)
+PRIME_NAMES = ["bn128", "bls12381", "grumpkin", "pallas", "vesta", "secq256r1", "bls12377", "goldilocks"]
 
 
 def ints_to_limbs(vals):

@@ -8,9 +8,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcircom_b200.so")
 CLI = os.path.join(HERE, "circom_cuda_witness")
-SOURCES = ["capi.cu", "tape_calls.cu", "flatten.cpp", "formats.cpp", "hostpack.cpp"]
+SOURCES = ["capi.cu", "tape_calls.cu", "flatten.cpp", "formats.cpp", "hostpack.cpp", "r1cs_compile.cpp"]
 CLI_SOURCES = ["cli.cpp"]
-HEADERS = ["kernels.cuh", "fr_device.cuh", "tape.h", "tape_calls.h", "u256.h", "hostpack.h", os.path.join("..", "..", "include", "circom_b200.h")]
+HEADERS = ["kernels.cuh", "fr_device.cuh", "tape.h", "tape_calls.h", "u256.h", "hostpack.h", "r1cs_small.h", os.path.join("..", "..", "include", "circom_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared", "-ldl"]
 

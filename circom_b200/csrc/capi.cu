@@ -105,7 +105,8 @@ struct DevR1cs {
     uint4 *terms = nullptr;  // per term {location, dictionary index, kind word, absorbed boolean row}
     uint4 *dictM = nullptr;
     u32 *perm = nullptr, *bool_loc = nullptr, *bool_row = nullptr;
-    u32 n_general = 0, n_bool = 0;
+    u32 *perm_small = nullptr;   // rows small by shape: decided over the integers (r1cs_small.h)
+    u32 n_general = 0, n_bool = 0, n_small = 0;
     u32 mean_row_terms = 0;  // compiled terms per general row
     uint64_t n_terms = 0;
 };
@@ -180,6 +181,8 @@ struct cw_batch {
     u32 *first_assert_d = nullptr;
     int *err_d = nullptr;
     unsigned long long *fb_d = nullptr;  // per-instance result of the R1CS check
+    u32 *r1cs_wide_d = nullptr;          // bitmap of the integer rows handed to the general kernel (launch_r1cs)
+    u32 r1cs_wide_rows = 0;
     DevTape dt;
     std::vector<uint64_t> host_inputs;  // [batch][n_inputs][4]
     std::vector<uint8_t> assigned;      // [batch][n_inputs]
@@ -590,6 +593,7 @@ void cw_batch_destroy(cw_batch *b) {
     cudaFree(b->first_assert_d);
     cudaFree(b->err_d);
     cudaFree(b->fb_d);
+    cudaFree(b->r1cs_wide_d);
     for (auto &e : b->ev)
         if (e) cudaEventDestroy(e);
     if (b->stream) cudaStreamDestroy(b->stream);
@@ -1215,157 +1219,36 @@ void cw_r1cs_destroy(cw_r1cs *r) {
         cudaFree(kv.second.terms);
         cudaFree(kv.second.dictM);
         cudaFree(kv.second.perm);
+        cudaFree(kv.second.perm_small);
         cudaFree(kv.second.bool_loc);
         cudaFree(kv.second.bool_row);
     }
     delete r;
 }
 
-// Compile the CSR for one value layout: wire ids become locations (slot / plane bit; identity for dense witness
-// rows), runs of plane bits with consecutive power-of-two coefficients become one term, boolean rows are absorbed
-// or dropped where the storage makes them tautologies, rows are sorted by structure.
+// The CSR compiled for one value layout (r1cs_compile.cpp), uploaded.
 static int compile_r1cs(cw_r1cs *r, int device, const cw_circuit *layout, DevR1cs &d) {
-    const R1csData &R = r->data;
-    const Tape *T = layout ? &layout->tape : nullptr;
-    if (T && T->n_witness != R.n_wires) return fail(CW_EINVAL, "the R1CS and the batch's circuit have different numbers of wires");
-    auto loc_of = [&](u32 wire) -> u32 { return T ? T->witness_slot[wire] : wire; };
+    R1csCompiled h;
+    try {
+        compile_r1cs_host(r->data, r->F, layout ? &layout->tape : nullptr, r->no_bool_rows,
+                          !r->no_bool_rows && env_int("CW_R1CS_SMALL", 1) != 0, h);
+    } catch (const std::exception &e) {
+        return fail(CW_EINVAL, e.what());
+    }
     int rc;
-    std::vector<U256> dm(R.dict.size());
-    std::vector<unsigned short> kind(R.dict.size());
-    auto pow2_exp = [](const U256 &v) -> int {  // k if v == 2^k, else -1
-        int k = -1;
-        for (int i = 0; i < 256; ++i)
-            if ((v.v[i >> 6] >> (i & 63)) & 1) {
-                if (k >= 0) return -1;
-                k = i;
-            }
-        return k;
-    };
-    for (size_t i = 0; i < R.dict.size(); ++i) {
-        dm[i] = r->F.to_mont(R.dict[i]);
-        U256 negv;
-        u256_sub(negv, r->F.q, R.dict[i]);
-        int kp = pow2_exp(R.dict[i]), kn = R.dict[i].is_zero() ? -1 : pow2_exp(negv);
-        if (kp == 0) kind[i] = 1;
-        else if (kn == 0) kind[i] = 2;
-        else if (kp > 0 && kp < 250) kind[i] = (unsigned short)(3 | (kp << 8));
-        else if (kn > 0 && kn < 250) kind[i] = (unsigned short)(4 | (kn << 8));
-        else kind[i] = 0;
-    }
-    const size_t m = R.n_constraints;
-    // boolean rows  x * (x - 1) = 0  (A = {x:1}, B = {x:1, one:-1}, C = {} or A/B swapped): they only need
-    // `w[x] in {0,1}`.  A wire stored as one bit of the bit plane satisfies it by construction (the row is dropped);
-    // otherwise the check rides on a term of a general row that reads the wire anyway, or goes to r1cs_bool_kernel.
-    std::vector<u32> general, bool_wire, bool_row;
-    auto is_unit = [&](uint64_t k, int want) { return (kind[R.coef[k]] & 0xFF) == want && (kind[R.coef[k]] >> 8) == 0; };
-    for (size_t row = 0; row < m; ++row) {
-        uint64_t p0 = R.row_ptr[3 * row], p1 = R.row_ptr[3 * row + 1], p2 = R.row_ptr[3 * row + 2], p3 = R.row_ptr[3 * row + 3];
-        bool is_bool = false;
-        u32 wire = 0;
-        if (p3 == p2 && (p1 - p0) + (p2 - p1) == 3) {
-            uint64_t s0 = (p1 - p0 == 1) ? p0 : p1, l0 = (p1 - p0 == 1) ? p1 : p0;  // single-term block / two-term block
-            // two-term block is sorted by wire: {one: -1, x: +1}
-            if (is_unit(s0, 1) && R.col[s0] != 0 && R.col[l0] == 0 && is_unit(l0, 2) && R.col[l0 + 1] == R.col[s0] && is_unit(l0 + 1, 1)) {
-                is_bool = true;
-                wire = R.col[s0];
-            }
-        }
-        if (is_bool && !r->no_bool_rows) {
-            if (loc_of(wire) & OPERAND_BIT) continue;  // a stored bit is 0 or 1
-            bool_wire.push_back(wire);
-            bool_row.push_back((u32)row);
-        } else general.push_back((u32)row);
-    }
-    // compiled terms of the general rows
-    std::vector<unsigned long long> row_ptr(3 * m + 1, 0);
-    std::vector<uint4> terms;
-    terms.reserve(R.col.size());
-    std::vector<uint64_t> sig(m, 0);
-    std::vector<u32> wire2bool(R.n_wires, 0xFFFFFFFFu);
-    for (size_t i = 0; i < bool_wire.size(); ++i)
-        if (wire2bool[bool_wire[i]] == 0xFFFFFFFFu) wire2bool[bool_wire[i]] = (u32)i;
-    std::vector<uint8_t> absorbed(bool_wire.size(), 0);
-    const uint32_t qbits = r->F.qbits;
-    uint64_t terms_general = 0;
-    {
-        size_t gi = 0;
-        for (size_t row = 0; row < m; ++row) {
-            const bool is_general = gi < general.size() && general[gi] == row;
-            if (is_general) ++gi;
-            uint64_t h = 1469598103934665603ull, cnt[3] = {0, 0, 0};
-            for (int blk = 0; blk < 3; ++blk) {
-                row_ptr[3 * row + blk] = terms.size();
-                if (!is_general) continue;
-                uint64_t k = R.row_ptr[3 * row + blk];
-                const uint64_t e = R.row_ptr[3 * row + blk + 1];
-                while (k < e) {
-                    const u32 loc = loc_of(R.col[k]);
-                    const unsigned short kd = kind[R.coef[k]];
-                    const int kk = kd & 0xFF;
-                    // a run: plane bits at consecutive positions of one word, coefficients +-2^(s), +-2^(s+1), ...
-                    if ((loc & OPERAND_BIT) && kk >= 1 && kk <= 4) {
-                        const bool negc = kk == 2 || kk == 4;
-                        const u32 s0 = kk <= 2 ? 0u : (u32)(kd >> 8), pos0 = loc & OPERAND_BITPOS_MASK;
-                        uint64_t j = k + 1;
-                        while (j < e) {
-                            const u32 lj = loc_of(R.col[j]);
-                            const unsigned short kj = kind[R.coef[j]];
-                            const int kkj = kj & 0xFF;
-                            if (!(lj & OPERAND_BIT) || kkj < 1 || kkj > 4 || (kkj == 2 || kkj == 4) != negc) break;
-                            const u32 sj = kkj <= 2 ? 0u : (u32)(kj >> 8), pj = lj & OPERAND_BITPOS_MASK;
-                            if (pj != pos0 + (u32)(j - k) || (pj >> 5) != (pos0 >> 5) || sj != s0 + (u32)(j - k)) break;
-                            ++j;
-                        }
-                        const u32 n = (u32)(j - k);
-                        if (s0 + n < qbits && s0 < 256) {  // the run's value is below 2^(s0 + n) <= 2^(qbits-1) < q
-                            terms.push_back(make_uint4(pos0 >> 5, 0u,
-                                                       (negc ? 6u : 5u) | (s0 << 8) | ((pos0 & 31u) << 16) | ((n - 1u) << 21),
-                                                       0xFFFFFFFFu));
-                            h = (h ^ (negc ? 6u : 5u)) * 1099511628211ull;
-                            ++cnt[blk];
-                            k = j;
-                            continue;
-                        }
-                    }
-                    u32 brow = 0xFFFFFFFFu;
-                    const u32 bi = wire2bool[R.col[k]];
-                    if (bi != 0xFFFFFFFFu && !absorbed[bi]) {
-                        absorbed[bi] = 1;
-                        brow = bool_row[bi];
-                    }
-                    terms.push_back(make_uint4(loc, R.coef[k], kd, brow));
-                    h = (h ^ (u32)kk) * 1099511628211ull;
-                    ++cnt[blk];
-                    ++k;
-                }
-            }
-            if (is_general) {
-                const uint64_t total = std::min<uint64_t>(cnt[0] + cnt[1] + cnt[2], 0xFFFF);
-                terms_general += cnt[0] + cnt[1] + cnt[2];
-                sig[row] = (total << 48) | ((std::min<uint64_t>(cnt[0], 255)) << 40) | ((std::min<uint64_t>(cnt[1], 255)) << 32) | (h & 0xFFFFFFFFull);
-            }
-        }
-        row_ptr[3 * m] = terms.size();
-    }
-    // rows sorted by structure so that neighbouring work items have equal length and branch alike
-    std::stable_sort(general.begin(), general.end(), [&](u32 x, u32 y) { return sig[x] > sig[y]; });
-    {
-        size_t o = 0;
-        for (size_t i = 0; i < bool_wire.size(); ++i)
-            if (!absorbed[i]) { bool_wire[o] = loc_of(bool_wire[i]); bool_row[o] = bool_row[i]; ++o; }
-        bool_wire.resize(o);
-        bool_row.resize(o);
-    }
-    d.n_general = (u32)general.size();
-    d.n_bool = (u32)bool_wire.size();
-    d.n_terms = terms.size();
-    d.mean_row_terms = general.empty() ? 0 : (u32)(terms_general / general.size());
-    if ((rc = upload(&d.terms, terms.data(), terms.size() * sizeof(uint4)))) return rc;
-    if ((rc = upload(&d.bool_loc, bool_wire.data(), bool_wire.size() * 4))) return rc;
-    if ((rc = upload(&d.bool_row, bool_row.data(), bool_row.size() * 4))) return rc;
-    if ((rc = upload(&d.row_ptr, row_ptr.data(), row_ptr.size() * 8))) return rc;
-    if ((rc = upload(&d.dictM, dm.data(), dm.size() * 32))) return rc;
-    if ((rc = upload(&d.perm, general.data(), general.size() * 4))) return rc;
+    static_assert(sizeof(R1csTerm) == sizeof(uint4), "term records are read as uint4");
+    d.n_general = (u32)h.perm.size();
+    d.n_small = (u32)h.perm_small.size();
+    d.n_bool = (u32)h.bool_loc.size();
+    d.n_terms = h.n_terms;
+    d.mean_row_terms = h.mean_row_terms;
+    if ((rc = upload(&d.terms, h.terms.data(), h.terms.size() * sizeof(uint4)))) return rc;
+    if ((rc = upload(&d.bool_loc, h.bool_loc.data(), h.bool_loc.size() * 4))) return rc;
+    if ((rc = upload(&d.bool_row, h.bool_row.data(), h.bool_row.size() * 4))) return rc;
+    if ((rc = upload(&d.row_ptr, h.row_ptr.data(), h.row_ptr.size() * 8))) return rc;
+    if ((rc = upload(&d.dictM, h.dictM.data(), h.dictM.size() * 32))) return rc;
+    if ((rc = upload(&d.perm, h.perm.data(), h.perm.size() * 4))) return rc;
+    if ((rc = upload(&d.perm_small, h.perm_small.data(), h.perm_small.size() * 4))) return rc;
     (void)device;
     return CW_OK;
 }
@@ -1388,9 +1271,10 @@ struct R1csOut {
     uint4 *a = nullptr, *b = nullptr, *c = nullptr;
 };
 
-// launches on `stream`; fb_d[batch] must hold ~0 on entry
+// launches on `stream`; fb_d[batch] must hold ~0 on entry; `wide` = (n_small + 31) / 32 words of scratch for the rows the
+// integer-row kernel hands to the general one
 static int launch_r1cs(cw_r1cs *r, const DevR1cs &d, const StoreDev &S, cudaStream_t stream, unsigned long long *fb_d,
-                       const R1csOut *eval) {
+                       const R1csOut *eval, u32 *wide) {
     const R1csData &R = r->data;
     R1csDev rd;
     rd.row_ptr = d.row_ptr;
@@ -1409,15 +1293,30 @@ static int launch_r1cs(cw_r1cs *r, const DevR1cs &d, const StoreDev &S, cudaStre
         if (eval) { eo.a = eval->a; eo.b = eval->b; eo.c = eval->c; eo.m = R.n_constraints; }
 #define CW_LAUNCH_R1CS(PR)                                                                              \
     do {                                                                                                \
-        if (eval) r1cs_check_kernel<PR, 3, true><<<grid, 256, 0, stream>>>(rd, S, fb_d, eo);             \
-        else if (lean) r1cs_check_kernel<PR, 5, false><<<grid, 256, 0, stream>>>(rd, S, fb_d, eo);       \
-        else r1cs_check_kernel<PR, 3, false><<<grid, 256, 0, stream>>>(rd, S, fb_d, eo);                 \
+        if (eval) r1cs_check_kernel<PR, 3, true, false><<<grid, 256, 0, stream>>>(rd, S, fb_d, eo, nullptr);       \
+        else if (lean) r1cs_check_kernel<PR, 5, false, false><<<grid, 256, 0, stream>>>(rd, S, fb_d, eo, nullptr); \
+        else r1cs_check_kernel<PR, 3, false, false><<<grid, 256, 0, stream>>>(rd, S, fb_d, eo, nullptr);           \
     } while (0)
         if (R.prime_id == 0) CW_LAUNCH_R1CS(0);
         else if (R.prime_id == 1) CW_LAUNCH_R1CS(1);
-        else if (eval) r1cs_check_kernel<-1, 3, true><<<grid, 256, 0, stream>>>(rd, S, fb_d, eo);
-        else r1cs_check_kernel<-1, 3, false><<<grid, 256, 0, stream>>>(rd, S, fb_d, eo);
+        else if (eval) r1cs_check_kernel<-1, 3, true, false><<<grid, 256, 0, stream>>>(rd, S, fb_d, eo, nullptr);
+        else r1cs_check_kernel<-1, 3, false, false><<<grid, 256, 0, stream>>>(rd, S, fb_d, eo, nullptr);
 #undef CW_LAUNCH_R1CS
+    }
+    if (d.n_small) {
+        // rows that are small by shape: over the integers first; the rows in which a value turned out wide (bitmap) go
+        // through the general kernel afterwards
+        if (!wide || eval) return fail(CW_ESTATE, "integer rows need their scratch bitmap");
+        CU(cudaMemsetAsync(wide, 0, ((size_t)d.n_small + 31) / 32 * 4, stream));
+        rd.perm = d.perm_small;
+        rd.n_rows = d.n_small;
+        const uint64_t items = (uint64_t)d.n_small << S.bt_log2;
+        dim3 grid((u32)std::max<uint64_t>(1, std::min<uint64_t>((items + 255) / 256, 148 * 8)), std::min<u32>(n_tiles, 65535u));
+        r1cs_small_kernel<<<grid, 256, 0, stream>>>(rd, S, fb_d, wide);
+        EvalOut eo;
+        if (R.prime_id == 0) r1cs_check_kernel<0, 3, false, true><<<grid, 256, 0, stream>>>(rd, S, fb_d, eo, wide);
+        else if (R.prime_id == 1) r1cs_check_kernel<1, 3, false, true><<<grid, 256, 0, stream>>>(rd, S, fb_d, eo, wide);
+        else r1cs_check_kernel<-1, 3, false, true><<<grid, 256, 0, stream>>>(rd, S, fb_d, eo, wide);
     }
     if (d.n_bool && !eval) {
         const uint64_t items = (uint64_t)d.n_bool << S.bt_log2;
@@ -1465,11 +1364,13 @@ int cw_r1cs_check_strided(cw_r1cs *r, const uint64_t *witness, uint64_t stride_e
     S.n_bitwords = 0;
     S.bt_log2 = 0;
     S.batch = batch;
+    u32 *wide_d = nullptr;
+    if (d.n_small) CU(cudaMalloc((void **)&wide_d, ((size_t)d.n_small + 31) / 32 * 4));
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0));
-    rc = launch_r1cs(r, d, S, nullptr, fb_d, nullptr);
+    rc = launch_r1cs(r, d, S, nullptr, fb_d, nullptr, wide_d);
     CU(cudaEventRecord(e1));
     if (!rc) {
         std::vector<unsigned long long> fb(batch);
@@ -1482,6 +1383,7 @@ int cw_r1cs_check_strided(cw_r1cs *r, const uint64_t *witness, uint64_t stride_e
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(fb_d);
+    if (wide_d) cudaFree(wide_d);
     if (tmp) cudaFree(tmp);
     return rc;
 }
@@ -1501,8 +1403,16 @@ int cw_r1cs_check_batch(cw_r1cs *r, cw_batch *b, int64_t *first_bad, float *kern
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
     CU(cudaMemsetAsync(b->fb_d, 0xFF, (size_t)b->batch * 8, b->stream));
+    if (d.n_small > b->r1cs_wide_rows) {   // scratch of the integer rows: grows with the largest R1CS this batch has checked
+        CU(cudaStreamSynchronize(b->stream));
+        cudaFree(b->r1cs_wide_d);
+        b->r1cs_wide_d = nullptr;
+        b->r1cs_wide_rows = 0;
+        CU(cudaMalloc((void **)&b->r1cs_wide_d, ((size_t)d.n_small + 31) / 32 * 4));
+        b->r1cs_wide_rows = d.n_small;
+    }
     CU(cudaEventRecord(e0, b->stream));
-    rc = launch_r1cs(r, d, b->store(), b->stream, b->fb_d, nullptr);
+    rc = launch_r1cs(r, d, b->store(), b->stream, b->fb_d, nullptr, b->r1cs_wide_d);
     CU(cudaEventRecord(e1, b->stream));
     if (!rc) {
         std::vector<unsigned long long> fb(b->batch);
@@ -1516,6 +1426,20 @@ int cw_r1cs_check_batch(cw_r1cs *r, cw_batch *b, int64_t *first_bad, float *kern
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return rc;
+}
+
+int cw_r1cs_compiled_info(cw_r1cs *r, cw_batch *b, int device, uint64_t info[4]) {
+    if (!r || !info) return fail(CW_EINVAL, "null argument");
+    int rc = b ? CW_OK : ensure_device(device);
+    if (rc) return rc;
+    if (b) CU(cudaSetDevice(b->device));
+    DevR1cs d;
+    if ((rc = get_dev_r1cs(r, b ? b->device : device, b ? b->c : nullptr, d))) return rc;
+    info[0] = d.n_general;
+    info[1] = d.n_small;
+    info[2] = d.n_bool;
+    info[3] = d.n_terms;
+    return CW_OK;
 }
 
 // A.w, B.w, C.w of every constraint for instances [first, first + count) of a batch, left in device memory for a
@@ -1554,7 +1478,7 @@ int cw_r1cs_eval_batch(cw_r1cs *r, cw_batch *b, uint32_t first, uint32_t count, 
     eo.b = (uint4 *)b_dev;
     eo.c = (uint4 *)c_dev;
     CU(cudaMemsetAsync(b->fb_d, 0xFF, (size_t)b->batch * 8, b->stream));
-    return launch_r1cs(all, d, S, b->stream, b->fb_d, &eo);
+    return launch_r1cs(all, d, S, b->stream, b->fb_d, &eo, nullptr);
 }
 
 // readWitness side of the file boundary: the 32-byte entries of a .wtns (written by this library, the reference

@@ -121,15 +121,14 @@ cw::U256 parse_number(const std::string &text_in, bool is_string, const cw::Fiel
         else if (c == 'b') { base = 2; t = t.substr(2); }
         else if (c == 'o') { base = 8; t = t.substr(2); }
     }
-    if (!is_string) {  // JSON number: integers only (the reference prints the double with %.0f)
-        size_t dot = t.find_first_of(".eE");
-        if (dot != std::string::npos) {
-            std::ostringstream o;
-            o.setf(std::ios::fixed);
-            o.precision(0);
-            o << atof(t.c_str());
-            t = o.str();
-        }
+    bool negative = false;
+    if (!is_string) {
+        // a JSON number of any spelling goes through a double and is printed with fixed precision 0 (main.cpp:170-175):
+        // 3.7 is 4, 2^53 + 1 is 2^53, -5 is q - 5 (mpz_init_set_str reads the sign, mpz_fdiv_r folds it, fr.cpp:2805-2811)
+        char buf[400];
+        snprintf(buf, sizeof(buf), "%.0f", strtod(t.c_str(), nullptr));
+        t = buf;
+        if (!t.empty() && t[0] == '-') { negative = true; t = t.substr(1); }
     }
     if (t.empty()) throw std::runtime_error("Invalid number in JSON input: " + text_in);
     cw::U256 acc = cw::u256_from_u64(0), b = cw::u256_from_u64(base);
@@ -138,6 +137,7 @@ cw::U256 parse_number(const std::string &text_in, bool is_string, const cw::Fiel
         if (d >= (int)base) throw std::runtime_error("Invalid number in JSON input: " + text_in);
         acc = F.addm(F.mulm(acc, b), cw::u256_from_u64((uint64_t)d));
     }
+    if (negative) acc = F.subm(cw::u256_from_u64(0), acc);
     return acc;
 }
 

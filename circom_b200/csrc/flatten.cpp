@@ -1346,6 +1346,7 @@ struct Lowerer {
             // static size class of the entry (range analysis): 1 bit / <= 64 bits / full.  Used only to pack
             // the device->host transfer of witnesses; the pack kernel re-checks every value at run time.
             uint32_t wb = vbits(v);
+            T.wit_bits.push_back((uint16_t)std::min<uint32_t>(wb, 256));
             if (wb <= 1) { T.pk_bit_wire.push_back((uint32_t)i); T.wit_class.push_back(0); }
             else if (wb <= 64) { T.pk_u64_wire.push_back((uint32_t)i); T.wit_class.push_back(1); }
             else { T.pk_full_wire.push_back((uint32_t)i); T.wit_class.push_back(2); }
@@ -1899,7 +1900,7 @@ struct BlobR {
         p += n;
     }
 };
-constexpr uint32_t BLOB_VERSION = 5;
+constexpr uint32_t BLOB_VERSION = 6;
 }  // namespace
 
 void serialize_tape(const Tape &t, std::vector<uint8_t> &out) {
@@ -1915,7 +1916,7 @@ void serialize_tape(const Tape &t, std::vector<uint8_t> &out) {
     w.pod<uint64_t>(sizeof(nums) / 8);
     w.raw(nums, sizeof(nums));
     w.vec(t.ops); w.vec(t.items); w.vec(t.level_start); w.vec(t.consts); w.vec(t.dat_consts); w.vec(t.witness_slot); w.vec(t.input_slot);
-    w.vec(t.pk_bit_wire); w.vec(t.pk_u64_wire); w.vec(t.pk_full_wire); w.vec(t.wit_class);
+    w.vec(t.pk_bit_wire); w.vec(t.pk_u64_wire); w.vec(t.pk_full_wire); w.vec(t.wit_class); w.vec(t.wit_bits);
     w.vec(t.fn_code); w.vec(t.fn_info); w.vec(t.call_tab); w.vec(t.witness2signal);
     w.pod<uint64_t>(t.inputs.size());
     for (const InputInfo &in : t.inputs) {
@@ -1953,7 +1954,7 @@ void deserialize_tape(const uint8_t *data, size_t len, Tape &t) {
     t.n_slot_operands = nums[14]; t.n_values = nums[15]; t.n_resident = (uint32_t)nums[16]; t.n_pre = (uint32_t)nums[17];
     t.n_slots = (uint32_t)nums[18]; t.n_bitwords = (uint32_t)nums[19]; t.n_stored = nums[20];
     r.vec(t.ops); r.vec(t.items); r.vec(t.level_start); r.vec(t.consts); r.vec(t.dat_consts); r.vec(t.witness_slot); r.vec(t.input_slot);
-    r.vec(t.pk_bit_wire); r.vec(t.pk_u64_wire); r.vec(t.pk_full_wire); r.vec(t.wit_class);
+    r.vec(t.pk_bit_wire); r.vec(t.pk_u64_wire); r.vec(t.pk_full_wire); r.vec(t.wit_class); r.vec(t.wit_bits);
     r.vec(t.fn_code); r.vec(t.fn_info); r.vec(t.call_tab); r.vec(t.witness2signal);
     uint64_t n_in;
     r.pod(n_in);
@@ -1975,7 +1976,7 @@ void deserialize_tape(const uint8_t *data, size_t len, Tape &t) {
     // but a short read or a version skew must not turn into out-of-bounds device accesses)
     if (t.ops.size() % 4 || t.level_start.empty() || t.items.empty() || t.level_start.back() != t.items.size() - 1 ||
         t.items.back() != t.ops.size() / 4 ||
-        t.witness_slot.size() != t.n_witness || t.input_slot.size() != t.n_inputs || t.wit_class.size() != t.n_witness ||
+        t.witness_slot.size() != t.n_witness || t.input_slot.size() != t.n_inputs || t.wit_class.size() != t.n_witness || t.wit_bits.size() != t.n_witness ||
         t.witness2signal.size() != t.n_witness || R.row_ptr.size() != 3 * R.n_constraints + 1 || R.col.size() != R.coef.size() ||
         (R.row_ptr.size() && R.row_ptr.back() != R.col.size()) || t.hashmap.empty())
         throw std::runtime_error("lowered-circuit blob: inconsistent");

@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include "fr_device.cuh"
+#include "r1cs_small.h"
 
 namespace cw {
 
@@ -715,9 +716,10 @@ struct EvalOut {
     uint4 *a = nullptr, *b = nullptr, *c = nullptr;
     unsigned long long m = 0;  // rows per instance
 };
-template <int PRIME, int MINB, bool EVAL>
+// FILTER: the rows of R.perm are the integer rows (r1cs_small_kernel below); only those it marked in `filter` are decided
+template <int PRIME, int MINB, bool EVAL, bool FILTER>
 __global__ void __launch_bounds__(256, MINB) r1cs_check_kernel(R1csDev R, StoreDev S, unsigned long long *__restrict__ first_bad,
-                                                         EvalOut out) {
+                                                         EvalOut out, const u32 *__restrict__ filter) {
     const FrParams &P = CW_FR(PRIME, R.prime);
     const u32 bt_mask = (1u << S.bt_log2) - 1u;
     const u32 n_tiles = (S.batch + bt_mask) >> S.bt_log2;
@@ -729,6 +731,10 @@ __global__ void __launch_bounds__(256, MINB) r1cs_check_kernel(R1csDev R, StoreD
              w += (unsigned long long)gridDim.x * blockDim.x) {
             const u32 li = (u32)w & bt_mask, inst = (tile << S.bt_log2) + li;
             if (inst >= S.batch) continue;
+            if (FILTER) {
+                const u32 k = (u32)(w >> S.bt_log2);
+                if (!((filter[k >> 5] >> (k & 31u)) & 1u)) continue;   // (written by the kernel before this one: plain load)
+            }
             const u32 row = __ldg(&R.perm[w >> S.bt_log2]);
             const unsigned long long p0 = __ldg(&R.row_ptr[3 * (size_t)row]), p1 = __ldg(&R.row_ptr[3 * (size_t)row + 1]),
                                      p2 = __ldg(&R.row_ptr[3 * (size_t)row + 2]), p3 = __ldg(&R.row_ptr[3 * (size_t)row + 3]);
@@ -743,6 +749,56 @@ __global__ void __launch_bounds__(256, MINB) r1cs_check_kernel(R1csDev R, StoreD
                 stg256(out.c + o, c);
             }
             if (!r1cs_row_holds(a, b, c, P)) atomicMin(&first_bad[inst], (unsigned long long)row);
+        }
+    }
+}
+
+// ---- integer rows (r1cs_small.h): rows that are small by shape, decided over the integers ----------------------
+// Same work decomposition as r1cs_check_kernel over R.perm = the small rows.  Per term: the 16-byte record, the value
+// (32 bytes, or a plane word), a shift and a 64-bit add - no field arithmetic, three 64-bit accumulators instead of
+// three 8-limb ones.  A value of 2^16 or more marks the row in `wide` (one bit per row of R.perm, any instance) and
+// the general kernel decides it afterwards.
+__global__ void __launch_bounds__(256, 6) r1cs_small_kernel(R1csDev R, StoreDev S, unsigned long long *__restrict__ first_bad,
+                                                            u32 *__restrict__ wide) {
+    const u32 bt_mask = (1u << S.bt_log2) - 1u;
+    const u32 n_tiles = (S.batch + bt_mask) >> S.bt_log2;
+    const unsigned long long n_items = (unsigned long long)R.n_rows << S.bt_log2;
+    for (u32 tile = blockIdx.y; tile < n_tiles; tile += gridDim.y) {
+        const uint4 *tb = store_tile(S, tile);
+        const u32 *pb = store_plane(S, tile);
+        for (unsigned long long w = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; w < n_items;
+             w += (unsigned long long)gridDim.x * blockDim.x) {
+            const u32 li = (u32)w & bt_mask, inst = (tile << S.bt_log2) + li;
+            if (inst >= S.batch) continue;
+            const u32 k = (u32)(w >> S.bt_log2);
+            const u32 row = __ldg(&R.perm[k]);
+            unsigned long long p = __ldg(&R.row_ptr[3 * (size_t)row]);
+            long long v[3];
+            u32 is_wide = 0u;
+#pragma unroll
+            for (int blk = 0; blk < 3; ++blk) {
+                const unsigned long long e = __ldg(&R.row_ptr[3 * (size_t)row + blk + 1]);
+                long long acc = 0;
+                for (; p < e; ++p) {
+                    const uint4 term = __ldg(&R.terms[p]);
+                    if ((term.z & 0xFFu) >= 5u) {
+                        r1cs_small_run(acc, term.z, __ldg(&pb[((size_t)term.x << S.bt_log2) + li]));
+                    } else if (term.x & OPD_BIT) {
+                        const u32 pos = term.x & OPD_BITPOS;
+                        r1cs_small_term(acc, is_wide, term.z, (__ldg(&pb[((size_t)(pos >> 5) << S.bt_log2) + li]) >> (pos & 31u)) & 1u, 0u);
+                    } else {
+                        u32 x[8];
+                        load_slot_nc(x, tb, term.x, S.bt_log2, li);
+                        const u32 upper = x[1] | x[2] | x[3] | x[4] | x[5] | x[6] | x[7];
+                        // the boolean constraint x*(x-1) = 0 of this wire rides on the term, as in the general kernel
+                        if (term.w != 0xFFFFFFFFu && (upper || x[0] > 1u)) atomicMin(&first_bad[inst], (unsigned long long)term.w);
+                        r1cs_small_term(acc, is_wide, term.z, x[0], upper);
+                    }
+                }
+                v[blk] = acc;
+            }
+            if (is_wide) atomicOr(&wide[k >> 5], 1u << (k & 31u));
+            else if (!r1cs_small_holds(v[0], v[1], v[2])) atomicMin(&first_bad[inst], (unsigned long long)row);
         }
     }
 }

@@ -70,6 +70,7 @@ struct Tape {
     // witness entries by static size class, for the packed device->host transfer
     std::vector<uint32_t> pk_bit_wire, pk_u64_wire, pk_full_wire;
     std::vector<uint8_t> wit_class;  // per witness entry: 0 bit, 1 <= 64 bits, 2 full
+    std::vector<uint16_t> wit_bits;  // per witness entry: the canonical value is below 2^wit_bits (256: nothing known)
     // circom functions (data-dependent control flow): register-machine code, per-function
     // {code offset, n_instr, n_regs, n_params}, and the per-call tables {function, n_args, arg operands...}
     std::vector<uint32_t> fn_code, fn_info, call_tab;
@@ -91,6 +92,27 @@ struct Tape {
     size_t n_items() const { return items.empty() ? 0 : items.size() - 1; }
     size_t n_levels() const { return level_start.empty() ? 0 : level_start.size() - 1; }
 };
+
+// The CSR of an R1CS compiled for one value layout (r1cs_compile.cpp): what the check kernels read.
+struct R1csTerm {   // 16 bytes, read as one uint4 on the device
+    uint32_t loc;    // location of the wire's value (slot id, or OPERAND_BIT | plane position; a plane word index for runs)
+    uint32_t coef;   // coefficient dictionary index
+    uint32_t kind;   // kind word (kernels.cuh: 0 general, 1/2 +-1, 3/4 +-2^k, 5/6 +- run of plane bits)
+    uint32_t brow;   // boolean row x*(x-1) = 0 of this wire checked along with the term, or ~0
+};
+struct R1csCompiled {
+    std::vector<unsigned long long> row_ptr;   // 3m + 1, into terms
+    std::vector<R1csTerm> terms;
+    std::vector<U256> dictM;                   // coefficient dictionary, Montgomery form
+    std::vector<uint32_t> perm;                // general rows, sorted by structure
+    std::vector<uint32_t> perm_small;          // rows small by shape (r1cs_small.h), sorted by structure
+    std::vector<uint32_t> bool_loc, bool_row;  // boolean rows no general row absorbs
+    uint32_t mean_row_terms = 0;               // compiled terms per row of perm
+    uint64_t n_terms = 0;
+};
+// T = the circuit whose value store the check reads (nullptr: dense witness rows, location = wire id).  Throws.
+void compile_r1cs_host(const R1csData &R, const FieldParams &F, const Tape *T, bool no_bool_rows, bool want_small,
+                       R1csCompiled &out);
 
 // Parse a .cb2c description and lower it.  Throws std::runtime_error.
 void lower_circuit(const uint8_t *data, size_t len, uint32_t flags, Tape &out);

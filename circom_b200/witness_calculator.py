@@ -421,6 +421,12 @@ class R1cs:
         check(lib.cw_r1cs_check_batch(self._h, b._h, fb.ctypes.data, ctypes.byref(ms)))
         return fb, ms.value
 
+    def compiled_info(self, b: Optional["Batch"] = None, device: int = 0) -> dict:
+        """rows by the kernel that decides them, for the value layout of batch b (None: dense witness rows)"""
+        info = (ctypes.c_uint64 * 4)()
+        check(lib.cw_r1cs_compiled_info(self._h, b._h if b is not None else None, device, info))
+        return {"general_rows": info[0], "integer_rows": info[1], "boolean_rows": info[2], "terms": info[3]}
+
     def eval_batch(self, b: "Batch", first: int, count: int, a_ptr: int, b_ptr: int, c_ptr: int) -> None:
         """A.w, B.w, C.w of instances [first, first+count) into device arrays [count][n_constraints][4] uint64"""
         check(lib.cw_r1cs_eval_batch(self._h, b._h, first, count, ctypes.c_void_p(a_ptr), ctypes.c_void_p(b_ptr),

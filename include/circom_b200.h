@@ -238,6 +238,10 @@ int cw_r1cs_check_strided(cw_r1cs *r, const uint64_t *witness, uint64_t stride_e
 /* the witnesses of a batch where the tape left them (any tile layout, bit plane, reused temporaries): nothing is
  * copied or expanded, plane bits are read as bits, recomposition sums as words.  Runs on the batch's stream. */
 int cw_r1cs_check_batch(cw_r1cs *r, cw_batch *b, int64_t *first_bad, float *kernel_ms);
+/* how the check reads the constraints for one value layout (b: that batch's store; NULL: dense witness rows on `device`):
+ * info = {general rows, integer rows - rows of small +-2^k terms decided over the integers unless a value they meet is
+ * wide (csrc/r1cs_small.h; CW_R1CS_SMALL=0 turns them off) -, boolean rows checked on their own, compiled terms} */
+int cw_r1cs_compiled_info(cw_r1cs *r, cw_batch *b, int device, uint64_t info[4]);
 /* A.w, B.w, C.w of every constraint for instances [first, first + count) of a batch, left in device memory
  * ([count][n_constraints][4] uint64 each, canonical, 32-byte aligned) for the prover stage that follows witness
  * generation; asynchronous on the batch stream (cw_batch_sync).  One-instance tile layouts only. */

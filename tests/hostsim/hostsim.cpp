@@ -10,6 +10,9 @@
 
 #include "../../circom_b200/csrc/fr_device.cuh"
 #include "../../circom_b200/csrc/tape.h"
+#include "../../circom_b200/csrc/r1cs_small.h"
+#include <algorithm>
+#include <stdexcept>
 
 using namespace cw;
 
@@ -49,6 +52,118 @@ void hs_vm_counters(unsigned long long *narrow, unsigned long long *wide) {
 
 
 const char *hs_last_error() { return g_err.c_str(); }
+
+// ---- the compiled R1CS on the value store of an instance (emulation of r1cs_small_kernel + r1cs_check_kernel) ----
+// Set up by hs_run_r1cs; called by hs_run when an instance has finished, with its slots and bit plane.
+struct R1csHook {
+    bool on = false;
+    bool compiled = false;
+    R1csCompiled C;
+    int64_t tamper_wire = -1;       // this witness entry is overwritten in the store before the check
+    U256 tamper_value;
+    int64_t *first_bad_compiled = nullptr, *first_bad_plain = nullptr;   // per instance
+    uint64_t n_small_rows = 0, n_wide_marks = 0, n_general_rows = 0;
+};
+static R1csHook g_hook;
+
+static void r1cs_hook_instance(const Tape &t, std::vector<u32> &slots, std::vector<u32> &bitplane, uint32_t inst) {
+    R1csHook &H = g_hook;
+    const FieldParams &F = t.F;
+    if (!H.compiled) {
+        compile_r1cs_host(t.r1cs, F, &t, false, true, H.C);
+        H.compiled = true;
+        H.n_small_rows = H.C.perm_small.size();
+        H.n_general_rows = H.C.perm.size();
+    }
+    auto value_at = [&](u32 loc) -> U256 {
+        U256 v = u256_from_u64(0);
+        if (loc & OPERAND_BIT) {
+            const u32 pos = loc & OPERAND_BITPOS_MASK;
+            v.v[0] = (bitplane[pos >> 5] >> (pos & 31u)) & 1u;
+        } else memcpy(v.v, &slots[(size_t)loc * 8], 32);
+        return v;
+    };
+    if (H.tamper_wire >= 0) {
+        const u32 loc = t.witness_slot[(size_t)H.tamper_wire];
+        if (loc & OPERAND_BIT) {
+            const u32 pos = loc & OPERAND_BITPOS_MASK;
+            bitplane[pos >> 5] = (bitplane[pos >> 5] & ~(1u << (pos & 31u))) | ((u32)(H.tamper_value.v[0] & 1u) << (pos & 31u));
+        } else memcpy(&slots[(size_t)loc * 8], H.tamper_value.v, 32);
+    }
+    const R1csData &R = t.r1cs;
+    // plain check on the dense witness row (the definition)
+    int64_t plain = -1;
+    {
+        std::vector<U256> w(R.n_wires);
+        for (uint64_t i = 0; i < R.n_wires; ++i) w[i] = value_at(t.witness_slot[i]);
+        for (uint64_t row = 0; row < R.n_constraints && plain < 0; ++row) {
+            U256 acc[3];
+            for (int m = 0; m < 3; ++m) {
+                acc[m] = u256_from_u64(0);
+                for (uint64_t k = R.row_ptr[3 * row + m]; k < R.row_ptr[3 * row + m + 1]; ++k)
+                    acc[m] = F.addm(acc[m], F.mulm(R.dict[R.coef[k]], w[R.col[k]]));
+            }
+            if (!(F.mulm(acc[0], acc[1]) == acc[2])) plain = (int64_t)row;
+        }
+    }
+    // the compiled form
+    uint64_t fb = ~0ull;
+    auto general_row = [&](u32 row) {
+        U256 acc[3];
+        for (int m = 0; m < 3; ++m) {
+            acc[m] = u256_from_u64(0);
+            for (unsigned long long k = H.C.row_ptr[3 * (size_t)row + m]; k < H.C.row_ptr[3 * (size_t)row + m + 1]; ++k) {
+                const R1csTerm &tm = H.C.terms[k];
+                const u32 kd = tm.kind & 0xFFu, sh = (tm.kind >> 8) & 0xFFu;
+                U256 x;
+                bool neg = kd == 2 || kd == 4 || kd == 6;
+                if (kd >= 5) {
+                    const u32 first = (tm.kind >> 16) & 31u, cnt = ((tm.kind >> 21) & 31u) + 1u;
+                    const u32 word = (bitplane[tm.loc] >> first) & (cnt >= 32u ? 0xFFFFFFFFu : ((1u << cnt) - 1u));
+                    x = u256_from_u64(word);
+                    for (u32 j = 0; j < sh; ++j) x = F.addm(x, x);
+                } else {
+                    x = value_at(tm.loc);
+                    if (tm.brow != 0xFFFFFFFFu && !(x == u256_from_u64(0)) && !(x == u256_from_u64(1))) fb = std::min<uint64_t>(fb, tm.brow);
+                    if (kd == 0) { x = F.mulm(R.dict[tm.coef], x); }
+                    else if (kd >= 3) for (u32 j = 0; j < sh; ++j) x = F.addm(x, x);
+                }
+                acc[m] = neg ? F.subm(acc[m], x) : F.addm(acc[m], x);
+            }
+        }
+        if (!(F.mulm(acc[0], acc[1]) == acc[2])) fb = std::min<uint64_t>(fb, row);
+    };
+    for (u32 row : H.C.perm) general_row(row);
+    for (u32 row : H.C.perm_small) {
+        long long v[3];
+        u32 wide = 0;
+        unsigned long long p = H.C.row_ptr[3 * (size_t)row];
+        for (int m = 0; m < 3; ++m) {
+            long long acc = 0;
+            for (; p < H.C.row_ptr[3 * (size_t)row + m + 1]; ++p) {
+                const R1csTerm &tm = H.C.terms[p];
+                if ((tm.kind & 0xFFu) >= 5u) r1cs_small_run(acc, tm.kind, bitplane[tm.loc]);
+                else {
+                    U256 x = value_at(tm.loc);
+                    const u32 upper = (u32)(x.v[0] >> 32) | (u32)x.v[1] | (u32)(x.v[1] >> 32) | (u32)x.v[2] | (u32)(x.v[2] >> 32) |
+                                      (u32)x.v[3] | (u32)(x.v[3] >> 32);
+                    if (tm.brow != 0xFFFFFFFFu && (upper || (u32)x.v[0] > 1u)) fb = std::min<uint64_t>(fb, tm.brow);
+                    r1cs_small_term(acc, wide, tm.kind, (u32)x.v[0], upper);
+                }
+            }
+            v[m] = acc;
+        }
+        if (wide) { ++H.n_wide_marks; general_row(row); }
+        else if (!r1cs_small_holds(v[0], v[1], v[2])) fb = std::min<uint64_t>(fb, row);
+    }
+    for (size_t i = 0; i < H.C.bool_loc.size(); ++i) {
+        U256 x = value_at(H.C.bool_loc[i]);
+        if (!(x == u256_from_u64(0)) && !(x == u256_from_u64(1))) fb = std::min<uint64_t>(fb, H.C.bool_row[i]);
+    }
+    H.first_bad_compiled[inst] = fb == ~0ull ? -1 : (int64_t)fb;
+    H.first_bad_plain[inst] = plain;
+}
+
 
 // returns 0 on success; witness[batch][W][4 u64]; status[batch] like cw_batch_status
 // Model of the device interpreter: all ops of a level read first, then all results of the level are written
@@ -217,9 +332,45 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
             memcpy(witness + ((size_t)inst * t.n_witness + w) * 4, v, 32);
         }
         if (bad_read) { g_err = "a slot or a bit of the bit plane was read before it was written (or is out of range)"; return -6; }
+        if (g_hook.on) {
+            try {
+                r1cs_hook_instance(t, slots, bitplane, inst);
+            } catch (const std::exception &e) {
+                g_err = e.what();
+                return -30;
+            }
+        }
         status[inst] = err ? -1 : (first_assert == 0xFFFFFFFFu ? 0 : (int32_t)(first_assert + 1));
     }
     return 0;
+}
+
+// hs_run + the compiled R1CS check on the value store each instance leaves (see r1cs_hook_instance).  tamper_wire >= 0:
+// that witness entry is overwritten with tamper_value (4 x u64) before the check.  counters = {rows in perm_small, rows
+// marked wide over all instances, rows in perm}.
+int hs_run_r1cs(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inputs, uint32_t batch, int64_t tamper_wire,
+                const uint64_t *tamper_value, int64_t *first_bad_compiled, int64_t *first_bad_plain, uint64_t *counters) {
+    Tape probe;
+    try {
+        lower_circuit(cb2c, len, flags, probe);
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return -1;
+    }
+    std::vector<uint64_t> wit((size_t)batch * probe.n_witness * 4);
+    std::vector<int32_t> st(batch);
+    g_hook = R1csHook();
+    g_hook.on = true;
+    g_hook.tamper_wire = tamper_wire;
+    if (tamper_value) memcpy(g_hook.tamper_value.v, tamper_value, 32);
+    g_hook.first_bad_compiled = first_bad_compiled;
+    g_hook.first_bad_plain = first_bad_plain;
+    int rc = hs_run(cb2c, len, flags, inputs, batch, wit.data(), st.data(), nullptr);
+    counters[0] = g_hook.n_small_rows;
+    counters[1] = g_hook.n_wide_marks;
+    counters[2] = g_hook.n_general_rows;
+    g_hook = R1csHook();
+    return rc;
 }
 
 // witness2SignalList of the lowered circuit; returns n_witness (or <0)

@@ -239,7 +239,10 @@ def test_cli_matches_reference_calculator(tmp_path):
     d = build_calcs.make_desc("all_ops")
     cb = str(tmp_path / "all_ops.cb2c")
     d.save(cb)
-    ins = [{"a": "0x1234567890abcdef1234", "b": "77"}, {"a": "5", "b": "0b101"}, {"a": 123456789, "b": "0o17"}]
+    ins = [{"a": "0x1234567890abcdef1234", "b": "77"}, {"a": "5", "b": "0b101"}, {"a": 123456789, "b": "0o17"},
+           # JSON numbers go through a double in the reference (main.cpp:170-175): 2^53 + 1 loses its last bit, 1e20 and
+           # 2^64 + 1 print their exact double, 3.7 rounds to 4, -5 is q - 5
+           {"a": 9007199254740993, "b": 1e20}, {"a": -5, "b": 3.7}, {"a": 18446744073709551617, "b": 255}]
     env = dict(os.environ, CW_O0="1")
     jp = str(tmp_path / "batch.json")
     json.dump(ins, open(jp, "w"))
@@ -315,3 +318,66 @@ def test_packed_transfer_with_observed_classes(monkeypatch):
     ow, st = COracle(d.to_bytes()).run(flat_inputs(d, bits)[:4])
     w2s = c.witness2signal().astype(np.int64)
     assert (ow[:, w2s] == w1[:4]).all()
+
+
+@pytest.mark.parametrize("bt", ["0", "3"])
+def test_integer_rows_of_the_r1cs_check_on_the_device(bt, monkeypatch, tmp_path):
+    """r1cs_small_kernel (rows of small +-2^k terms decided over the integers, csrc/r1cs_small.h) against the general
+    kernel alone (CW_R1CS_SMALL=0) and against the definition evaluated with python ints from the written .r1cs: a SHA-256
+    compression on the batch's value store and on dense rows; valid witnesses, witnesses with overwritten entries, and
+    inputs that are not bits (rows handed over through the bitmap)."""
+    from tests.test_formats_cpu import parse_r1cs
+    monkeypatch.setenv("CW_BT_LOG2", bt)
+    d = CircuitDesc("bn128")
+    d.set_main(C.sha256_compression(d))
+    rng = random.Random(77)
+    names = [(n, sz) for n, _g, sz in d.main_inputs()]
+    n = 24
+    ins = [{nm: [rng.randrange(2) for _ in range(sz)] for nm, sz in names} for _ in range(n)]
+    ins[-1] = {nm: [rng.choice([0, 1, 1, 70000, 1 << 16, d.q - 1, rng.randrange(d.q)]) for _ in range(sz)] for nm, sz in names}
+    c = Circuit(d)
+    b = Batch(c, n)
+    b.set_inputs(flat_inputs(d, ins))
+    b.run()
+    wit = b.witness()
+    monkeypatch.setenv("CW_R1CS_SMALL", "0")
+    r_off = R1cs(c)
+    fb_off, _ = r_off.check_batch(b)
+    fbd_off, _ = r_off.check(wit)
+    assert r_off.compiled_info(b)["integer_rows"] == 0 and r_off.compiled_info()["integer_rows"] == 0
+    monkeypatch.setenv("CW_R1CS_SMALL", "1")
+    r_on = R1cs(c)
+    info = r_on.compiled_info(b)
+    assert info["integer_rows"] > 20000 and info["integer_rows"] > 10 * info["general_rows"]
+    assert r_on.compiled_info()["integer_rows"] > 20000
+    fb_on, _ = r_on.check_batch(b)
+    fbd_on, _ = r_on.check(wit)
+    assert (fb_on == fb_off).all() and (fbd_on == fb_off).all() and (fbd_off == fb_off).all()
+    assert (fb_on[:-1] == -1).all()
+    # the definition, from the file
+    p = str(tmp_path / "c.r1cs")
+    r_on.write(p, d.main.n_out, 0, d.main.n_in)
+    cons = parse_r1cs(open(p, "rb").read())["cons"]
+
+    def first_bad(w):
+        for k, (A, B, Cc) in enumerate(cons):
+            a = sum(v * w[j] for j, v in A.items()) % d.q
+            bb = sum(v * w[j] for j, v in B.items()) % d.q
+            cc = sum(v * w[j] for j, v in Cc.items()) % d.q
+            if (a * bb - cc) % d.q:
+                return k
+        return -1
+    assert first_bad(limbs_to_ints(wit[-1])) == fb_on[-1]
+    # overwritten entries, dense rows
+    W = c.n_witness
+    w2 = wit.copy()
+    vals = [0, 1, 1, 0, 2, 255, 1 << 16, (1 << 16) - 1, 1 << 40, d.q - 1, d.q >> 1]
+    for i in range(n - 1):
+        wire = rng.randrange(1, W)
+        v = vals[i % len(vals)]
+        w2[i, wire] = np.frombuffer(int(v).to_bytes(32, "little"), dtype=np.uint64)
+    a_on, _ = r_on.check(w2)
+    a_off, _ = r_off.check(w2)
+    assert (a_on == a_off).all() and (a_on[:-1] >= 0).sum() >= 8
+    for i in (0, 5, 6, 9):
+        assert first_bad(limbs_to_ints(w2[i])) == a_on[i]

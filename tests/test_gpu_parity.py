@@ -422,3 +422,10 @@ def test_other_primes_run_circuits(prime):
                 exp = evaluate(d, inp)
                 assert limbs_to_ints(wit[i]) == [exp[k] for k in w2s], (prime, name, compact, i)
             assert (R1cs(c).check_batch(b)[0] == -1).all() and (R1cs(c).check(wit)[0] == -1).all()
+            if prime == "goldilocks":   # the .wtns of the reference's goldilocks runtime: n8 = 8 (common64/main.cpp:312-353)
+                import struct
+                raw = b.wtns_bytes(0)
+                W = c.n_witness
+                assert raw[:12] == b"wtns" + struct.pack("<II", 2, 2) and struct.unpack_from("<IQIQI", raw, 12) == (1, 16, 8, d.q, W)
+                assert struct.unpack_from("<IQ", raw, 40) == (2, 8 * W) and len(raw) == 52 + 8 * W
+                assert list(struct.unpack_from("<%dQ" % W, raw, 52)) == limbs_to_ints(wit[0])

@@ -11,7 +11,7 @@ from circom_b200.circuit import CircuitDesc, OPS
 from circom_b200 import circuits as C
 from oracle.field_model import Field, OP_NAMES, DivisionByZero
 from oracle.ir_eval import evaluate, check_r1cs
-from tests.util import hostsim, hostsim_run, ints_to_limbs, limbs_to_ints, edge_values, rand_operand, PRIME_NAMES
+from tests.util import hostsim, hostsim_run, hostsim_run_r1cs, ints_to_limbs, limbs_to_ints, edge_values, rand_operand, PRIME_NAMES
 
 CIRCUITS = {
     "multiplier2": (lambda d: C.multiplier2(d), lambda r, q: {"a": r.randrange(q), "b": r.randrange(q)}),
@@ -315,3 +315,47 @@ def test_modular_inverse_by_division_steps(prime):
     got = limbs_to_ints(r)
     for x, y, g in zip(A, B, got):
         assert g == F.div(y, x), (hex(y), hex(x))
+
+
+@pytest.mark.parametrize("flags", [0, 48])
+def test_integer_rows_of_the_r1cs_check(flags):
+    """The compiled R1CS (r1cs_compile.cpp) with its integer rows (r1cs_small.h: the functions r1cs_small_kernel runs) on the
+    value store the tape leaves, against the definition A.w * B.w = C.w evaluated in the field: a SHA-256 compression
+    (almost every row is small by shape; with bit inputs no value is wide), the same witness with one entry overwritten
+    (0 <-> 1, a byte, a 17-bit value, a field-sized value), and inputs that are not bits (rows marked wide go through
+    the general path and must give the same answer)."""
+    d = CircuitDesc("bn128")
+    d.set_main(C.sha256_compression(d))
+    rng = random.Random(50 + flags)
+    names = [(n, sz) for n, _g, sz in d.main_inputs()]
+    ins = [{n: [rng.randrange(2) for _ in range(sz)] for n, sz in names} for _ in range(2)]
+    fc, fp, cnt = hostsim_run_r1cs(d, ins, flags)
+    assert fc.tolist() == fp.tolist() == [-1, -1]
+    assert cnt[0] > 20000 and cnt[0] > 10 * cnt[2] and cnt[1] == 0
+    W = len(hostsim_run(d, ins[:1], flags)[3])
+    hits = 0
+    for trial in range(24):
+        wire = rng.randrange(1, W)
+        val = [0, 1, 1, 0, 2, 255, 1 << 16, (1 << 16) - 1, 1 << 40, d.q - 1, d.q >> 1][trial % 11]
+        fc, fp, cnt = hostsim_run_r1cs(d, ins[:1], flags, tamper=(wire, val))
+        assert fc.tolist() == fp.tolist(), (wire, val)
+        hits += fp[0] >= 0
+    assert hits >= 8
+    # inputs that are not bits: the integer rows that meet them are handed over, the answer stays the definition's
+    wild = {n: [rng.choice([0, 1, 1, 1 << 16, 70000, d.q - 1, rng.randrange(d.q)]) for _ in range(sz)] for n, sz in names}
+    fc, fp, cnt = hostsim_run_r1cs(d, [wild, ins[0]], flags)
+    assert fc.tolist() == fp.tolist() and fc[1] == -1 and cnt[1] > 0
+
+
+def test_integer_rows_are_left_alone_where_they_do_not_pay():
+    """rows of limbs (the big-integer circuit) and small fields (goldilocks: |a*b - c| is not below q) keep the general path"""
+    d = CircuitDesc("bn128")
+    d.set_main(C.ecdsa_scale(d, 2, 5))
+    rng = random.Random(9)
+    ins = [{n: [rng.getrandbits(64) for _ in range(sz)] for n, _g, sz in d.main_inputs()}]
+    fc, fp, cnt = hostsim_run_r1cs(d, ins, 48)
+    assert fc.tolist() == fp.tolist() == [-1] and cnt[0] == 0 and cnt[2] > 0
+    g = CircuitDesc("goldilocks")
+    g.set_main(C.less_than(g, 12))
+    fc, fp, cnt = hostsim_run_r1cs(g, [{"in": [77, 3000]}], 48)
+    assert fc.tolist() == fp.tolist() == [-1] and cnt[0] == 0

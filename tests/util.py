@@ -32,8 +32,9 @@ def limbs_to_ints(a):
 def build_hostsim() -> str:
     srcs = [os.path.join(HOSTSIM_DIR, "hostsim.cpp"),
             os.path.join(ROOT, "circom_b200", "csrc", "flatten.cpp"),
-            os.path.join(ROOT, "circom_b200", "csrc", "formats.cpp")]
-    deps = srcs + [os.path.join(ROOT, "circom_b200", "csrc", f) for f in ("fr_device.cuh", "tape.h", "u256.h")]
+            os.path.join(ROOT, "circom_b200", "csrc", "formats.cpp"),
+            os.path.join(ROOT, "circom_b200", "csrc", "r1cs_compile.cpp")]
+    deps = srcs + [os.path.join(ROOT, "circom_b200", "csrc", f) for f in ("fr_device.cuh", "tape.h", "u256.h", "r1cs_small.h")]
     if os.path.exists(HOSTSIM_SO) and all(os.path.getmtime(d) <= os.path.getmtime(HOSTSIM_SO) for d in deps):
         return HOSTSIM_SO
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", HOSTSIM_SO] + srcs)
@@ -100,3 +101,22 @@ def rand_operand(rng: random.Random, q: int, edges):
     if r < 0.5:
         return rng.randrange(1 << rng.randrange(1, 255)) % q
     return rng.randrange(q)
+
+
+def hostsim_run_r1cs(desc, inputs_list, flags=0, tamper=None):
+    """hs_run + the compiled R1CS (r1cs_compile.cpp; emulation of r1cs_small_kernel / r1cs_check_kernel on the value store the
+    tape leaves).  tamper = (witness index, value).  Returns (first_bad compiled, first_bad plain definition, counters
+    {small rows, wide marks over the batch, general rows})."""
+    hs = hostsim()
+    blob = desc.to_bytes()
+    B = len(inputs_list)
+    inp = flat_inputs(desc, inputs_list)
+    fc = np.zeros(B, dtype=np.int64)
+    fp = np.zeros(B, dtype=np.int64)
+    cnt = np.zeros(3, dtype=np.uint64)
+    tv = ints_to_limbs([tamper[1] % desc.q]) if tamper else None
+    rc = hs.hs_run_r1cs(blob, ctypes.c_size_t(len(blob)), flags, inp.ctypes.data_as(ctypes.c_void_p), B,
+                        ctypes.c_int64(tamper[0] if tamper else -1), tv.ctypes.data_as(ctypes.c_void_p) if tamper else None,
+                        fc.ctypes.data_as(ctypes.c_void_p), fp.ctypes.data_as(ctypes.c_void_p), cnt.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0, (rc, hs.hs_last_error())
+    return fc, fp, [int(x) for x in cnt]

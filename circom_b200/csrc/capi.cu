@@ -106,6 +106,8 @@ struct DevR1cs {
     uint4 *dictM = nullptr;
     u32 *perm = nullptr, *bool_loc = nullptr, *bool_row = nullptr;
     u32 *perm_small = nullptr;   // rows small by shape: decided over the integers (r1cs_small.h)
+    uint2 *sgroups = nullptr, *srecs = nullptr;   // ... from a term list of their own
+    u32 *sbrow = nullptr;
     u32 n_general = 0, n_bool = 0, n_small = 0;
     u32 mean_row_terms = 0;  // compiled terms per general row
     uint64_t n_terms = 0;
@@ -1220,6 +1222,9 @@ void cw_r1cs_destroy(cw_r1cs *r) {
         cudaFree(kv.second.dictM);
         cudaFree(kv.second.perm);
         cudaFree(kv.second.perm_small);
+        cudaFree(kv.second.sgroups);
+        cudaFree(kv.second.srecs);
+        cudaFree(kv.second.sbrow);
         cudaFree(kv.second.bool_loc);
         cudaFree(kv.second.bool_row);
     }
@@ -1249,6 +1254,10 @@ static int compile_r1cs(cw_r1cs *r, int device, const cw_circuit *layout, DevR1c
     if ((rc = upload(&d.dictM, h.dictM.data(), h.dictM.size() * 32))) return rc;
     if ((rc = upload(&d.perm, h.perm.data(), h.perm.size() * 4))) return rc;
     if ((rc = upload(&d.perm_small, h.perm_small.data(), h.perm_small.size() * 4))) return rc;
+    static_assert(sizeof(R1csSmallRec) == sizeof(uint2), "integer-row records are read as uint2");
+    if ((rc = upload(&d.sgroups, h.sgroups.data(), h.sgroups.size() * 4))) return rc;
+    if ((rc = upload(&d.srecs, h.srecs.data(), h.srecs.size() * sizeof(uint2)))) return rc;
+    if ((rc = upload(&d.sbrow, h.sbrow.data(), h.sbrow.size() * 4))) return rc;
     (void)device;
     return CW_OK;
 }
@@ -1271,7 +1280,7 @@ struct R1csOut {
     uint4 *a = nullptr, *b = nullptr, *c = nullptr;
 };
 
-// launches on `stream`; fb_d[batch] must hold ~0 on entry; `wide` = (n_small + 31) / 32 words of scratch for the rows the
+// launches on `stream`; fb_d[batch] must hold ~0 on entry; `wide` = (n_small + 31) / 32 + 1 words of scratch for the rows the
 // integer-row kernel hands to the general one
 static int launch_r1cs(cw_r1cs *r, const DevR1cs &d, const StoreDev &S, cudaStream_t stream, unsigned long long *fb_d,
                        const R1csOut *eval, u32 *wide) {
@@ -1307,12 +1316,17 @@ static int launch_r1cs(cw_r1cs *r, const DevR1cs &d, const StoreDev &S, cudaStre
         // rows that are small by shape: over the integers first; the rows in which a value turned out wide (bitmap) go
         // through the general kernel afterwards
         if (!wide || eval) return fail(CW_ESTATE, "integer rows need their scratch bitmap");
-        CU(cudaMemsetAsync(wide, 0, ((size_t)d.n_small + 31) / 32 * 4, stream));
+        CU(cudaMemsetAsync(wide, 0, (((size_t)d.n_small + 31) / 32 + 1) * 4, stream));
         rd.perm = d.perm_small;
         rd.n_rows = d.n_small;
         const uint64_t items = (uint64_t)d.n_small << S.bt_log2;
         dim3 grid((u32)std::max<uint64_t>(1, std::min<uint64_t>((items + 255) / 256, 148 * 8)), std::min<u32>(n_tiles, 65535u));
-        r1cs_small_kernel<<<grid, 256, 0, stream>>>(rd, S, fb_d, wide);
+        R1csSmallDev sg;
+        sg.groups = d.sgroups;
+        sg.recs = d.srecs;
+        sg.brow = d.sbrow;
+        if (S.bt_log2 == 0) r1cs_small_kernel<true><<<grid, 256, 0, stream>>>(rd, sg, S, fb_d, wide);
+        else r1cs_small_kernel<false><<<grid, 256, 0, stream>>>(rd, sg, S, fb_d, wide);
         EvalOut eo;
         if (R.prime_id == 0) r1cs_check_kernel<0, 3, false, true><<<grid, 256, 0, stream>>>(rd, S, fb_d, eo, wide);
         else if (R.prime_id == 1) r1cs_check_kernel<1, 3, false, true><<<grid, 256, 0, stream>>>(rd, S, fb_d, eo, wide);
@@ -1365,7 +1379,7 @@ int cw_r1cs_check_strided(cw_r1cs *r, const uint64_t *witness, uint64_t stride_e
     S.bt_log2 = 0;
     S.batch = batch;
     u32 *wide_d = nullptr;
-    if (d.n_small) CU(cudaMalloc((void **)&wide_d, ((size_t)d.n_small + 31) / 32 * 4));
+    if (d.n_small) CU(cudaMalloc((void **)&wide_d, (((size_t)d.n_small + 31) / 32 + 1) * 4));
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
@@ -1408,7 +1422,7 @@ int cw_r1cs_check_batch(cw_r1cs *r, cw_batch *b, int64_t *first_bad, float *kern
         cudaFree(b->r1cs_wide_d);
         b->r1cs_wide_d = nullptr;
         b->r1cs_wide_rows = 0;
-        CU(cudaMalloc((void **)&b->r1cs_wide_d, ((size_t)d.n_small + 31) / 32 * 4));
+        CU(cudaMalloc((void **)&b->r1cs_wide_d, (((size_t)d.n_small + 31) / 32 + 1) * 4));
         b->r1cs_wide_rows = d.n_small;
     }
     CU(cudaEventRecord(e0, b->stream));

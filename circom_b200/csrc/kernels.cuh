@@ -732,6 +732,7 @@ __global__ void __launch_bounds__(256, MINB) r1cs_check_kernel(R1csDev R, StoreD
             const u32 li = (u32)w & bt_mask, inst = (tile << S.bt_log2) + li;
             if (inst >= S.batch) continue;
             if (FILTER) {
+                if (!filter[(R.n_rows + 31u) >> 5]) return;   // the word after the bitmap: no row was marked at all
                 const u32 k = (u32)(w >> S.bt_log2);
                 if (!((filter[k >> 5] >> (k & 31u)) & 1u)) continue;   // (written by the kernel before this one: plain load)
             }
@@ -754,51 +755,64 @@ __global__ void __launch_bounds__(256, MINB) r1cs_check_kernel(R1csDev R, StoreD
 }
 
 // ---- integer rows (r1cs_small.h): rows that are small by shape, decided over the integers ----------------------
-// Same work decomposition as r1cs_check_kernel over R.perm = the small rows.  Per term: the 16-byte record, the value
-// (32 bytes, or a plane word), a shift and a 64-bit add - no field arithmetic, three 64-bit accumulators instead of
-// three 8-limb ones.  A value of 2^16 or more marks the row in `wide` (one bit per row of R.perm, any instance) and
-// the general kernel decides it afterwards.
-__global__ void __launch_bounds__(256, 6) r1cs_small_kernel(R1csDev R, StoreDev S, unsigned long long *__restrict__ first_bad,
+// Work item = (row of R.perm = the small rows, instance), as in r1cs_check_kernel; the rows are read from their own term
+// list: groups of 32 rows with uniform term counts, 8-byte records interleaved inside a group (one-instance tiles: a warp
+// is a group, a record load is one 256-byte line, the loops do not diverge; 32-instance tiles: a warp is one row).  Per
+// term: the record, the value (32 bytes, or a plane word), a shift and a 64-bit add - no field arithmetic, six
+// 64-bit accumulators instead of three 8-limb ones.  A value of 2^16 or more marks the row in `wide` (one bit per row of
+// R.perm, whichever instance) and the general kernel decides it afterwards.
+struct R1csSmallDev {
+    const uint2 *groups;   // {first record, n0 | n1 << 8 | n2 << 16}
+    const uint2 *recs;     // R1csSmallRec
+    const u32 *brow;       // boolean row of a record with SM_BROW
+};
+template <bool BT0>
+__global__ void __launch_bounds__(256, 6) r1cs_small_kernel(R1csDev R, R1csSmallDev G, StoreDev S, unsigned long long *__restrict__ first_bad,
                                                             u32 *__restrict__ wide) {
-    const u32 bt_mask = (1u << S.bt_log2) - 1u;
-    const u32 n_tiles = (S.batch + bt_mask) >> S.bt_log2;
-    const unsigned long long n_items = (unsigned long long)R.n_rows << S.bt_log2;
+    const u32 bt_log2 = BT0 ? 0u : S.bt_log2;
+    const u32 bt_mask = (1u << bt_log2) - 1u;
+    const u32 n_tiles = (S.batch + bt_mask) >> bt_log2;
+    const unsigned long long n_items = (unsigned long long)R.n_rows << bt_log2;
     for (u32 tile = blockIdx.y; tile < n_tiles; tile += gridDim.y) {
         const uint4 *tb = store_tile(S, tile);
         const u32 *pb = store_plane(S, tile);
         for (unsigned long long w = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; w < n_items;
              w += (unsigned long long)gridDim.x * blockDim.x) {
-            const u32 li = (u32)w & bt_mask, inst = (tile << S.bt_log2) + li;
+            const u32 li = (u32)w & bt_mask, inst = (tile << bt_log2) + li;
             if (inst >= S.batch) continue;
-            const u32 k = (u32)(w >> S.bt_log2);
-            const u32 row = __ldg(&R.perm[k]);
-            unsigned long long p = __ldg(&R.row_ptr[3 * (size_t)row]);
+            const u32 k = (u32)(w >> bt_log2);
+            const uint2 hdr = __ldg(&G.groups[k >> 5]);
+            u32 at = hdr.x + (k & 31u);
             long long v[3];
             u32 is_wide = 0u;
 #pragma unroll
             for (int blk = 0; blk < 3; ++blk) {
-                const unsigned long long e = __ldg(&R.row_ptr[3 * (size_t)row + blk + 1]);
-                long long acc = 0;
-                for (; p < e; ++p) {
-                    const uint4 term = __ldg(&R.terms[p]);
-                    if ((term.z & 0xFFu) >= 5u) {
-                        r1cs_small_run(acc, term.z, __ldg(&pb[((size_t)term.x << S.bt_log2) + li]));
-                    } else if (term.x & OPD_BIT) {
-                        const u32 pos = term.x & OPD_BITPOS;
-                        r1cs_small_term(acc, is_wide, term.z, (__ldg(&pb[((size_t)(pos >> 5) << S.bt_log2) + li]) >> (pos & 31u)) & 1u, 0u);
+                const u32 n = (hdr.y >> (8 * blk)) & 0xFFu;
+                unsigned long long pos = 0ull, neg = 0ull;
+                for (u32 t = 0; t < n; ++t, at += 32u) {
+                    const uint2 rec = __ldg(&G.recs[at]);
+                    if (rec.x & (SM_RUN | SM_BIT)) {
+                        if (rec.x & SM_RUN) {
+                            r1cs_small_acc_run(pos, neg, rec.x, rec.y, __ldg(&pb[((size_t)(rec.x & SM_LOC) << bt_log2) + li]));
+                        } else {
+                            const u32 p = rec.x & SM_BITPOS;
+                            r1cs_small_acc(pos, neg, is_wide, rec.x, rec.y, (__ldg(&pb[((size_t)(p >> 5) << bt_log2) + li]) >> (p & 31u)) & 1u, 0u);
+                        }
                     } else {
                         u32 x[8];
-                        load_slot_nc(x, tb, term.x, S.bt_log2, li);
+                        load_slot_nc(x, tb, rec.x & OPD_SLOT, bt_log2, li);
                         const u32 upper = x[1] | x[2] | x[3] | x[4] | x[5] | x[6] | x[7];
                         // the boolean constraint x*(x-1) = 0 of this wire rides on the term, as in the general kernel
-                        if (term.w != 0xFFFFFFFFu && (upper || x[0] > 1u)) atomicMin(&first_bad[inst], (unsigned long long)term.w);
-                        r1cs_small_term(acc, is_wide, term.z, x[0], upper);
+                        if ((rec.x & SM_BROW) && (upper || x[0] > 1u)) atomicMin(&first_bad[inst], (unsigned long long)__ldg(&G.brow[at]));
+                        r1cs_small_acc(pos, neg, is_wide, rec.x, rec.y, x[0], upper);
                     }
                 }
-                v[blk] = acc;
+                v[blk] = (long long)(pos - neg);
             }
-            if (is_wide) atomicOr(&wide[k >> 5], 1u << (k & 31u));
-            else if (!r1cs_small_holds(v[0], v[1], v[2])) atomicMin(&first_bad[inst], (unsigned long long)row);
+            if (is_wide) {
+                atomicOr(&wide[k >> 5], 1u << (k & 31u));
+                wide[(R.n_rows + 31u) >> 5] = 1u;   // "some row is marked" (every writer stores the same value)
+            } else if (!r1cs_small_holds(v[0], v[1], v[2])) atomicMin(&first_bad[inst], (unsigned long long)__ldg(&R.perm[k]));
         }
     }
 }

@@ -22,7 +22,7 @@ void compile_r1cs_host(const R1csData &R, const FieldParams &F, const Tape *T, b
     if (T && T->n_witness != R.n_wires) throw std::runtime_error("the R1CS and the batch's circuit have different numbers of wires");
     auto loc_of = [&](u32 wire) -> u32 { return T ? T->witness_slot[wire] : wire; };
     // |a*b - c| must stay below q for the integer decision: every 256-bit prime, not goldilocks
-    want_small = want_small && F.qbits > 130;
+    want_small = want_small && F.qbits > 130 && (T || R.n_wires <= OPERAND_SLOT_MASK);   // (locations of 24 bits in the records)
     std::vector<U256> &dm = out.dictM;
     dm.assign(R.dict.size(), u256_from_u64(0));
     std::vector<unsigned short> kind(R.dict.size());
@@ -91,6 +91,7 @@ void compile_r1cs_host(const R1csData &R, const FieldParams &F, const Tape *T, b
             if (is_general) ++gi;
             uint64_t h = 1469598103934665603ull, cnt[3] = {0, 0, 0};
             bool small_shape = true;
+            unsigned __int128 bound[3] = {0, 0, 0};   // of |sum| if every value met is below 2^16
             for (int blk = 0; blk < 3; ++blk) {
                 row_ptr[3 * row + blk] = terms.size();
                 if (!is_general) continue;
@@ -120,6 +121,7 @@ void compile_r1cs_host(const R1csData &R, const FieldParams &F, const Tape *T, b
                                                      (negc ? 6u : 5u) | (s0 << 8) | ((pos0 & 31u) << 16) | ((n - 1u) << 21),
                                                      0xFFFFFFFFu});
                             if (s0 + n > R1CS_SMALL_MAX_BITS) small_shape = false;
+                            else bound[blk] += (unsigned __int128)1 << (s0 + n);
                             h = (h ^ (negc ? 6u : 5u)) * 1099511628211ull;
                             ++cnt[blk];
                             k = j;
@@ -138,6 +140,7 @@ void compile_r1cs_host(const R1csData &R, const FieldParams &F, const Tape *T, b
                     // a wire it knows nothing about is decided by the run)
                     const bool limb = T && T->wit_bits[R.col[k]] > 16 && T->wit_bits[R.col[k]] <= 128;   // (a bound near the field size is no bound)
                     if (kk < 1 || kk > 4 || (u32)(kd >> 8) > R1CS_SMALL_MAX_SHIFT || limb) small_shape = false;
+                    else bound[blk] += (unsigned __int128)1 << (16 + (kk <= 2 ? 0u : (u32)(kd >> 8)));
                     h = (h ^ (u32)kk) * 1099511628211ull;
                     ++cnt[blk];
                     ++k;
@@ -147,8 +150,9 @@ void compile_r1cs_host(const R1csData &R, const FieldParams &F, const Tape *T, b
                 const uint64_t total = std::min<uint64_t>(cnt[0] + cnt[1] + cnt[2], 0xFFFF);
                 terms_general += cnt[0] + cnt[1] + cnt[2];
                 sig[row] = (total << 48) | ((std::min<uint64_t>(cnt[0], 255)) << 40) | ((std::min<uint64_t>(cnt[1], 255)) << 32) | (h & 0xFFFFFFFFull);
+                const unsigned __int128 lim = (unsigned __int128)1 << R1CS_SMALL_SUM_BITS;
                 is_small[row] = want_small && small_shape && cnt[0] <= R1CS_SMALL_MAX_TERMS && cnt[1] <= R1CS_SMALL_MAX_TERMS &&
-                                cnt[2] <= R1CS_SMALL_MAX_TERMS;
+                                cnt[2] <= R1CS_SMALL_MAX_TERMS && bound[0] < lim && bound[1] < lim && bound[2] < lim;
             }
         }
         row_ptr[3 * m] = terms.size();
@@ -176,6 +180,58 @@ void compile_r1cs_host(const R1csData &R, const FieldParams &F, const Tape *T, b
             if (!absorbed[i]) { bool_wire[o] = loc_of(bool_wire[i]); bool_row[o] = bool_row[i]; ++o; }
         bool_wire.resize(o);
         bool_row.resize(o);
+    }
+    // the integer rows' own term list (r1cs_small.h): groups of 32 rows, interleaved 8-byte records, uniform counts per group
+    out.srecs.clear();
+    out.sbrow.clear();
+    out.sgroups.clear();
+    {
+        const size_t ns = out.perm_small.size();
+        const u32 pad_loc = loc_of(0) & (SM_BIT | SM_BITPOS);   // the constant one: a value that is never wide; coefficient 0
+        bool any_brow = false;
+        for (size_t g0 = 0; g0 < ns; g0 += 32) {
+            const size_t gn = std::min<size_t>(32, ns - g0);
+            u32 n[3] = {0, 0, 0};
+            for (size_t r = 0; r < gn; ++r)
+                for (int blk = 0; blk < 3; ++blk)
+                    n[blk] = std::max<u32>(n[blk], (u32)(row_ptr[3 * (size_t)out.perm_small[g0 + r] + blk + 1] -
+                                                         row_ptr[3 * (size_t)out.perm_small[g0 + r] + blk]));
+            const size_t base = out.srecs.size();
+            if (base + (size_t)(n[0] + n[1] + n[2]) * 32 > 0xFFFFFFFFull) throw std::runtime_error("R1CS too large for the integer-row term list");
+            out.sgroups.push_back((u32)base);
+            out.sgroups.push_back(n[0] | (n[1] << 8) | (n[2] << 16));
+            out.srecs.resize(base + (size_t)(n[0] + n[1] + n[2]) * 32, R1csSmallRec{pad_loc, SM_PAD});
+            out.sbrow.resize(out.srecs.size(), 0xFFFFFFFFu);
+            u32 t0 = 0;
+            for (int blk = 0; blk < 3; ++blk) {
+                for (size_t r = 0; r < gn; ++r) {
+                    const u32 row = out.perm_small[g0 + r];
+                    const unsigned long long b = row_ptr[3 * (size_t)row + blk], e = row_ptr[3 * (size_t)row + blk + 1];
+                    for (unsigned long long k = b; k < e; ++k) {
+                        const R1csTerm &tm = terms[k];
+                        const u32 kd = tm.kind & 0xFFu, sh = (tm.kind >> 8) & 0xFFu;
+                        R1csSmallRec rec;
+                        if (kd >= 5u) {
+                            rec.loc = (tm.loc & SM_LOC) | SM_RUN | (kd == 6u ? SM_NEG : 0u);
+                            rec.mag = ((tm.kind >> 16) & 31u) | (((tm.kind >> 21) & 31u) << 5) | (sh << 10);
+                        } else {
+                            rec.loc = (tm.loc & (SM_BIT | SM_BITPOS)) | ((kd == 2u || kd == 4u) ? SM_NEG : 0u);   // (slot ids have 24 bits)
+                            rec.mag = kd <= 2u ? 0u : sh;
+                            if (tm.brow != 0xFFFFFFFFu) {
+                                if (tm.loc & OPERAND_BIT) throw std::runtime_error("boolean row on a plane bit");
+                                rec.loc |= SM_BROW;
+                                any_brow = true;
+                            }
+                        }
+                        const size_t at = base + ((size_t)t0 + (size_t)(k - b)) * 32 + r;
+                        out.srecs[at] = rec;
+                        out.sbrow[at] = tm.brow;
+                    }
+                }
+                t0 += n[blk];
+            }
+        }
+        if (!any_brow) out.sbrow.clear();
     }
     out.bool_loc = bool_wire;
     out.bool_row = bool_row;

@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "u256.h"
+#include "r1cs_small.h"
 
 namespace cw {
 
@@ -106,6 +107,11 @@ struct R1csCompiled {
     std::vector<U256> dictM;                   // coefficient dictionary, Montgomery form
     std::vector<uint32_t> perm;                // general rows, sorted by structure
     std::vector<uint32_t> perm_small;          // rows small by shape (r1cs_small.h), sorted by structure
+    // ... and their own term list: per group of 32 rows {first record, counts n0 | n1 << 8 | n2 << 16}; record t of row r of
+    // group g at sgroups[2g] + t * 32 + r; sbrow (empty: no term carries one): the boolean row checked along with a record
+    std::vector<uint32_t> sgroups;
+    std::vector<struct R1csSmallRec> srecs;
+    std::vector<uint32_t> sbrow;
     std::vector<uint32_t> bool_loc, bool_row;  // boolean rows no general row absorbs
     uint32_t mean_row_terms = 0;               // compiled terms per row of perm
     uint64_t n_terms = 0;

@@ -22,7 +22,10 @@ CONFIGS = [
     ("C4 Sha256(512) bls12381, 32 per tile", "bls12381", lambda d: C.sha256(d, 512), 1024, "5"),
     ("Poseidon(2) bn128", "bn128", lambda d: C.poseidon(d, 2), 4096, None),
 ]
+only = os.environ.get("PROBE_ONLY")
 for name, prime, mk, batch, bt in CONFIGS:
+    if only and only not in name:
+        continue
     if bt is None:
         os.environ.pop("CW_BT_LOG2", None)
     else:

@@ -134,24 +134,30 @@ static void r1cs_hook_instance(const Tape &t, std::vector<u32> &slots, std::vect
         if (!(F.mulm(acc[0], acc[1]) == acc[2])) fb = std::min<uint64_t>(fb, row);
     };
     for (u32 row : H.C.perm) general_row(row);
-    for (u32 row : H.C.perm_small) {
+    for (size_t k = 0; k < H.C.perm_small.size(); ++k) {     // as r1cs_small_kernel reads them: the grouped record list
+        const u32 row = H.C.perm_small[k];
+        const u32 base = H.C.sgroups[2 * (k >> 5)], counts = H.C.sgroups[2 * (k >> 5) + 1];
+        size_t at = (size_t)base + (k & 31u);
         long long v[3];
         u32 wide = 0;
-        unsigned long long p = H.C.row_ptr[3 * (size_t)row];
         for (int m = 0; m < 3; ++m) {
-            long long acc = 0;
-            for (; p < H.C.row_ptr[3 * (size_t)row + m + 1]; ++p) {
-                const R1csTerm &tm = H.C.terms[p];
-                if ((tm.kind & 0xFFu) >= 5u) r1cs_small_run(acc, tm.kind, bitplane[tm.loc]);
-                else {
-                    U256 x = value_at(tm.loc);
+            const u32 n = (counts >> (8 * m)) & 0xFFu;
+            unsigned long long pos = 0, neg = 0;
+            for (u32 tt = 0; tt < n; ++tt, at += 32) {
+                const R1csSmallRec rec = H.C.srecs[at];
+                if (rec.loc & SM_RUN) r1cs_small_acc_run(pos, neg, rec.loc, rec.mag, bitplane[rec.loc & SM_LOC]);
+                else if (rec.loc & SM_BIT) {
+                    const u32 p = rec.loc & SM_BITPOS;
+                    r1cs_small_acc(pos, neg, wide, rec.loc, rec.mag, (bitplane[p >> 5] >> (p & 31u)) & 1u, 0u);
+                } else {
+                    U256 x = value_at(rec.loc & OPERAND_SLOT_MASK);
                     const u32 upper = (u32)(x.v[0] >> 32) | (u32)x.v[1] | (u32)(x.v[1] >> 32) | (u32)x.v[2] | (u32)(x.v[2] >> 32) |
                                       (u32)x.v[3] | (u32)(x.v[3] >> 32);
-                    if (tm.brow != 0xFFFFFFFFu && (upper || (u32)x.v[0] > 1u)) fb = std::min<uint64_t>(fb, tm.brow);
-                    r1cs_small_term(acc, wide, tm.kind, (u32)x.v[0], upper);
+                    if ((rec.loc & SM_BROW) && (upper || (u32)x.v[0] > 1u)) fb = std::min<uint64_t>(fb, H.C.sbrow[at]);
+                    r1cs_small_acc(pos, neg, wide, rec.loc, rec.mag, (u32)x.v[0], upper);
                 }
             }
-            v[m] = acc;
+            v[m] = (long long)(pos - neg);
         }
         if (wide) { ++H.n_wide_marks; general_row(row); }
         else if (!r1cs_small_holds(v[0], v[1], v[2])) fb = std::min<uint64_t>(fb, row);

@@ -397,12 +397,17 @@ def run_workload(ctx: Ctx, workload: str, batch: int, steps: int, warmup: int, e
 
     # ---- R1CS check on the device-resident witnesses ---------------------------------------------
     r1cs_ms = None
+    r1cs_rows = None
     if r1cs:
         r = R1cs(circuit)
         fb, _ = r.check_batch(b)
         assert (fb == -1).all(), "R1CS check failed on generated witnesses"
         ms = [r.check_batch(b)[1] for _ in range(max(2, steps))]
         r1cs_ms = ctx.max_over_ranks([float(np.mean(ms))])[0]
+        try:   # which kernel decides the rows (integer rows: csrc/r1cs_small.h)
+            r1cs_rows = r.compiled_info(b)
+        except Exception:
+            r1cs_rows = None
         del r
 
     # ---- gather leg: the packed witnesses of every rank on rank 0 (NCCL) ---------------------------
@@ -512,11 +517,14 @@ def run_workload(ctx: Ctx, workload: str, batch: int, steps: int, warmup: int, e
     if r1cs_ms is not None:
         nnz, m = st["n_nnz"], st["n_constraints"]
         b_r1cs = nnz * 8 + 3 * (m + 1) * 8 + 32 * st["n_constants"] + batch * (32 * W + 8)
-        res["r1cs"] = {"mconstraints_per_s": total_batch * m / (r1cs_ms / 1e3) / 1e6, "ms": r1cs_ms,
-                       "roofline": {"kernel": "r1cs_check_kernel", "bound": "hbm",
+        r1cs_kernel = "r1cs_check_kernel"
+        if r1cs_rows and r1cs_rows.get("integer_rows", 0) > r1cs_rows.get("general_rows", 0):
+            r1cs_kernel = "r1cs_small_kernel"
+        res["r1cs"] = {"mconstraints_per_s": total_batch * m / (r1cs_ms / 1e3) / 1e6, "ms": r1cs_ms, "rows": r1cs_rows,
+                       "roofline": {"kernel": r1cs_kernel, "bound": "hbm",
                                     "achieved": b_r1cs / (r1cs_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                                     "frac": b_r1cs / (r1cs_ms / 1e3) / 1e9 / peak,
-                                    "traffic": ncu_traffic(desc.name, batch, "r1cs_check_kernel"),
+                                    "traffic": ncu_traffic(desc.name, batch, r1cs_kernel),
                                     "basis": "SURVEY 8(d): 32 B per wire and instance; the check reads the compact store "
                                              "(bits as bits, recomposition runs as words), so it moves far fewer bytes "
                                              "than that and is bound by integer issue",

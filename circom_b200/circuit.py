@@ -612,6 +612,7 @@ class CircuitDesc:
         self._cache: Dict[tuple, Template] = {}
         self.main: Optional[Template] = None
         self.name = "circuit"
+        self.io_map_templates: set = set()   # template ids that sit in component arrays of mixed templates (mark_mixed_array)
 
     def const_id(self, v: int) -> int:
         v %= self.q
@@ -770,7 +771,36 @@ class CircuitDesc:
             for t in self.templates:
                 own, subs = self.symbol_names(t)
                 syms += b"".join(pstr(x) for x in own) + b"".join(pstr(x) for x in subs)
-        return head + consts + b"".join(blobs) + names + funcs + syms
+        iomp = b""
+        if self.io_map_templates:
+            # the compiler's TemplateInstanceIOMap for the template instances that sit in component arrays of mixed
+            # templates (build_input_output_list, compiler/src/circuit_design/build.rs:498-520): docs/CB2C.md, IOMP
+            iomp = b"IOMP" + struct.pack("<I", len(self.io_map_templates))
+            for tid in sorted(self.io_map_templates):
+                defs = self.io_defs(self.templates[tid])
+                iomp += struct.pack("<II", tid, len(defs))
+                for off, lengths, size, bus in defs:
+                    iomp += struct.pack("<II", off, len(lengths)) + b"".join(struct.pack("<I", x) for x in lengths)
+                    iomp += struct.pack("<II", size, bus)
+        return head + consts + b"".join(blobs) + names + funcs + iomp + syms
+
+    @staticmethod
+    def io_defs(t: "Template"):
+        """IODef list of a template instance: (offset = local id of element 0, dimensions, element size, bus id) per output
+        and input signal, in declaration order = signal code order (build.rs:498-520)"""
+        defs, off = [], 0
+        for cat in ("out", "in"):
+            for name, n in t.sigs[cat]:
+                defs.append((off, [n] if t.sig_is_array[name] else [], 1, 0))
+                off += n
+        return defs
+
+    def mark_mixed_array(self, *templates: "Template") -> None:
+        """declare that these template instances occur together in one component array (`component ops[2]; ops[0] = A();
+        ops[1] = B();`): the reference compiler then addresses their signals through the io map (`LocationRule::Mapped`,
+        store_bucket.rs:498-566) and ships the map in the `.dat`"""
+        for t in templates:
+            self.io_map_templates.add(t.id)
 
     def save(self, path: str) -> str:
         with open(path, "wb") as f:

@@ -113,3 +113,56 @@ def all_ops(d: CircuitDesc) -> Template:
         t.assign_constrained(outs[25], z["out"])
         t.assign_constrained(outs[26], a * b + a)
     return d.template("AllOps", (), build)
+
+
+def mixed_array(d: CircuitDesc) -> Template:
+    """A component array whose elements are instances of DIFFERENT templates -
+
+        template Acc(n) { signal input in[n]; signal input k; signal output out; ... }
+        component ops[3];  ops[0] = Acc(2);  ops[1] = Acc(3);  ops[2] = Scale();
+
+    - the case in which the reference compiler cannot know a sub-component signal's offset statically (the inputs of
+    Acc(2) and Acc(3) start at the same place but `k` does not) and emits `LocationRule::Mapped` accesses that look the
+    offset up in templateInsId2IOSignalInfo at run time (store_bucket.rs:498-566, load_bucket.rs:264-322).  A producer that
+    unrolls the loops knows every element's template: the description below is what it writes, and the io map travels
+    to the `.dat` (CircuitDesc.mark_mixed_array)."""
+    def acc(n):
+        def build(t: Template):
+            xs = t.input("in", n)
+            k = t.input("k")
+            out = t.output("out")
+            s = xs[0]
+            for x in xs[1:]:
+                s = s + x
+            t.assign_constrained(out, s * k)
+        return d.template("Acc", (n,), build)
+
+    def scale(t: Template):
+        out = t.output("out", 2)
+        x = t.input("x")
+        y = t.input("y")
+        t.assign_constrained(out[0], x * y)
+        t.assign_constrained(out[1], x * x)
+    a2, a3, sc = acc(2), acc(3), d.template("Scale", (), scale)
+    d.mark_mixed_array(a2, a3, sc)
+
+    def build(t: Template):
+        a = t.input("a", 3)
+        b = t.input("b")
+        out = t.output("out", 4)
+        o0 = t.component("ops[0]", a2)
+        o1 = t.component("ops[1]", a3)
+        o2 = t.component("ops[2]", sc)
+        t.assign_constrained(o0.sig("in", 0), a[0])
+        t.assign_constrained(o0.sig("in", 1), a[1])
+        t.assign_constrained(o0.sig("k"), b)
+        for j in range(3):
+            t.assign_constrained(o1.sig("in", j), a[j])
+        t.assign_constrained(o1.sig("k"), o0.sig("out"))
+        t.assign_constrained(o2.sig("x"), o1.sig("out"))
+        t.assign_constrained(o2.sig("y"), b)
+        t.assign_constrained(out[0], o0.sig("out"))
+        t.assign_constrained(out[1], o1.sig("out"))
+        t.assign_constrained(out[2], o2.sig("out", 0))
+        t.assign_constrained(out[3], o2.sig("out", 1))
+    return d.template("MixedArray", (), build)

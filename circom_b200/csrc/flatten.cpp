@@ -1248,6 +1248,41 @@ struct Lowerer {
         }
         // optional symbols section: "SYMS", then per template the names of its own signals and of its sub-components
         // (what the reference keeps in the DAG for sym_porting.rs).  Anything else after the functions is refused.
+        // optional io-map section: "IOMP" - the compiler's TemplateInstanceIOMap (code_producers/src/components/mod.rs:4-10,47:
+        // per template instance that sits in a component array of mixed templates, the list of its input / output
+        // signals with offset, dimensions, element size, bus id).  The reference's generated code resolves `Mapped`
+        // locations through it at run time (load_bucket.rs:264-322); here a producer has resolved them already, the map is
+        // carried for the `.dat` only (c_code_generator.rs:681-735).
+        if (r.left() >= 4 && !memcmp(r.p, "IOMP", 4)) {
+            r.bytes(4);
+            const uint32_t n_e = r.get<uint32_t>();
+            if (n_e > n_tm) throw std::runtime_error("cb2c: io map names more templates than the file has");
+            int64_t prev = -1;
+            for (uint32_t e = 0; e < n_e; ++e) {
+                const uint32_t tid = r.get<uint32_t>(), n_defs = r.get<uint32_t>();
+                if (tid >= n_tm || (int64_t)tid <= prev) throw std::runtime_error("cb2c: io map entries must name templates in ascending order");
+                prev = tid;
+                const uint64_t n_io = (uint64_t)tm[tid].n_out + tm[tid].n_in;
+                if (n_defs > n_io) throw std::runtime_error("cb2c: io map lists more signals than the template has inputs and outputs");
+                std::vector<Tape::IoDef> defs(n_defs);
+                for (Tape::IoDef &d : defs) {
+                    d.offset = r.get<uint32_t>();
+                    const uint32_t nl = r.get<uint32_t>();
+                    if (nl > 32) throw std::runtime_error("cb2c: io map signal with more than 32 dimensions");
+                    r.expect(nl, 4);
+                    uint64_t elems = 1;
+                    for (uint32_t k = 0; k < nl; ++k) {
+                        d.lengths.push_back(r.get<uint32_t>());
+                        elems *= d.lengths.back();
+                        if (elems > n_io) throw std::runtime_error("cb2c: io map signal larger than its template");
+                    }
+                    d.size = r.get<uint32_t>();
+                    d.bus_id = r.get<uint32_t>();
+                    if (d.size < 1 || (uint64_t)d.offset + elems * d.size > n_io) throw std::runtime_error("cb2c: io map signal outside its template's inputs and outputs");
+                }
+                T.io_map.emplace_back(tid, std::move(defs));
+            }
+        }
         if (r.left()) {
             if (r.left() < 4 || memcmp(r.bytes(4), "SYMS", 4)) throw std::runtime_error("cb2c: unknown section after the functions");
             T.sym.resize(n_tm);

@@ -338,8 +338,21 @@ void write_dat(const Tape &t, const std::string &path) {
         U256 m = t.F.to_mont(c);
         f.w(m.v, 32);
     }
-    // (templateInsId2IOSignalInfo, c_code_generator.rs:681-794: empty - circuits with run-time component
-    // indexing are outside what the lowering accepts)
+    // templateInsId2IOSignalInfo (generate_dat_io_signals_info, c_code_generator.rs:681-735; read back by loadCircuit,
+    // main.cpp:57-93): the template ids, then per template {#signals, per signal: offset, #dimensions - 1, the dimensions
+    // but the first, element size, bus id}, all u32.  The bus field map that follows (:737-794) has no entries: buses are
+    // flattened by the producer.
+    for (const auto &e : t.io_map) f.put<uint32_t>(e.first);
+    for (const auto &e : t.io_map) {
+        f.put<uint32_t>((uint32_t)e.second.size());
+        for (const Tape::IoDef &d : e.second) {
+            f.put<uint32_t>(d.offset);
+            f.put<uint32_t>(d.lengths.empty() ? 0u : (uint32_t)d.lengths.size() - 1u);
+            for (size_t i = 1; i < d.lengths.size(); ++i) f.put<uint32_t>(d.lengths[i]);
+            f.put<uint32_t>(d.size);
+            f.put<uint32_t>(d.bus_id);
+        }
+    }
 }
 
 // .sym: one line per signal, `signal id,witness index (-1: eliminated),node id,qualified name`, a component's own signals

@@ -88,6 +88,13 @@ struct Tape {
         std::vector<std::string> own, sub;   // names of the own signals / of the sub-components
     };
     std::vector<SymTemplate> sym;            // empty: no symbols
+    // the compiler's io map (docs/CB2C.md, IOMP section), written into the `.dat` where the reference runtime looks for it
+    // (c_code_generator.rs:681-735, main.cpp:57-93).  Not part of the lowered-circuit blob.
+    struct IoDef {
+        uint32_t offset = 0, size = 1, bus_id = 0;
+        std::vector<uint32_t> lengths;
+    };
+    std::vector<std::pair<uint32_t, std::vector<IoDef>>> io_map;   // (template instance id, its signals), ascending ids
     uint32_t sym_main = 0;
     size_t n_tape_ops() const { return ops.size() / 4; }
     size_t n_items() const { return items.empty() ? 0 : items.size() - 1; }

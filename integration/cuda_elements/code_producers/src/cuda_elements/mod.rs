@@ -4,6 +4,7 @@
 // libcircom_b200.so lowers to an instruction tape.  Written against circom 2.2.3; NOT compiled in the build image of
 // circom_b200 (no Rust toolchain there) - the byte layout is pinned by tests/test_cb2c_spec_cpu.py through an
 // independent C writer, the semantics by the Python DSL that emits the same records.
+use crate::components::{FieldMap, TemplateInstanceIOMap};
 use num_bigint_dig::BigInt;
 use std::collections::HashMap;
 use std::io::Write;
@@ -12,7 +13,7 @@ pub use crate::components::*; // InputList, TemplateInstanceIOMap, ... (as c_ele
 
 /// What `CProducer` (c_elements/mod.rs:6-39) carries, reduced to what a .cb2c needs.
 pub struct CUDAProducer {
-    pub prime: String,                 // "--prime" value: bn128 | bls12381 (others: Err at `prime_id`)
+    pub prime: String,                 // "--prime" value (program_structure/src/utils/constants.rs:3-13); unknown names: Err at `prime_id`
     pub prime_str: String,             // decimal modulus, as CProducer::get_prime()
     pub main_header: String,
     pub main_signal_offset: usize,     // = 1 (signal 0 is the constant one), c_elements/mod.rs:52
@@ -22,6 +23,8 @@ pub struct CUDAProducer {
     pub field_tracking: Vec<String>,   // the constant table the IR's ValueBucket{BigInt} indexes, mod.rs:27
     pub sanity_check_style: usize,     // 0: drop `===` asserts (assert_bucket.rs:73)
     pub function_ids: HashMap<String, u32>, // function header -> index in Cb2cFile::functions (Circuit::functions order)
+    pub io_map: TemplateInstanceIOMap,      // as CProducer::io_map (c_elements/mod.rs:24): resolves LocationRule::Mapped now, travels to the .dat
+    pub busid_field_info: FieldMap,         // as CProducer::busid_field_info: the fields of each bus (flattened by the producer)
 }
 
 impl CUDAProducer {
@@ -29,7 +32,13 @@ impl CUDAProducer {
         match self.prime.as_str() {
             "bn128" => Ok(0),
             "bls12381" => Ok(1),
-            _ => Err(()), // Goldilocks and the other 256-bit primes: not in format version 1
+            "grumpkin" => Ok(2),
+            "pallas" => Ok(3),
+            "vesta" => Ok(4),
+            "secq256r1" => Ok(5),
+            "bls12377" => Ok(6),
+            "goldilocks" => Ok(7),   // 64-bit values in the same 32-byte constants / elements
+            _ => Err(()),
         }
     }
 }
@@ -98,6 +107,7 @@ pub struct Cb2cFile {
     pub main: u32,
     pub names: Vec<(String, u32, u32)>,                   // (qualified name, global signal id, size)
     pub functions: Vec<FunctionRecord>,
+    pub io_map: TemplateInstanceIOMap,                    // copied from the producer by produce_cb2c: the IOMP section
 }
 
 impl Cb2cFile {
@@ -157,6 +167,22 @@ impl Cb2cFile {
             Self::w_str(w, &f.name)?;
             for v in [f.n_params, f.n_regs, f.code.len() as u32] { Self::w_u32(w, v)?; }
             Self::w_ops(w, &f.code)?;
+        }
+        // optional io-map section (docs/CB2C.md): what generate_dat_io_signals_info puts into the .dat, handed to the library
+        if !self.io_map.is_empty() {
+            w.write_all(b"IOMP").map_err(|_| {})?;
+            Self::w_u32(w, self.io_map.len() as u32)?;
+            for (template_id, defs) in &self.io_map {              // BTreeMap: ascending template ids
+                Self::w_u32(w, *template_id as u32)?;
+                Self::w_u32(w, defs.len() as u32)?;
+                for d in defs {
+                    Self::w_u32(w, d.offset as u32)?;
+                    Self::w_u32(w, d.lengths.len() as u32)?;
+                    for l in &d.lengths { Self::w_u32(w, *l as u32)?; }
+                    Self::w_u32(w, d.size as u32)?;
+                    Self::w_u32(w, d.bus_id.unwrap_or(0) as u32)?;
+                }
+            }
         }
         // optional symbols section: only when every template carries a complete set of names
         if self.templates.iter().all(|t| t.signal_names.len() as u32 == t.n_out + t.n_in + t.n_inter

@@ -13,6 +13,7 @@
 use crate::circuit_design::{function::FunctionCodeInfo, template::TemplateCodeInfo};
 use crate::intermediate_representation::ir_interface::*;
 use circom_algebra::modular_arithmetic as ma;
+use code_producers::components::IODef;
 use code_producers::cuda_elements::*;
 use num_bigint_dig::BigInt;
 
@@ -56,6 +57,38 @@ impl<'a> TemplateCtx<'a> {
     }
     /// signal index inside this template -> reference (outputs, inputs, intermediates: executed_template.rs:442-552)
     fn own(&self, idx: usize) -> Ref { Ref::Own(idx as u32) }
+    /// `LocationRule::Mapped` (store_bucket.rs:498-566, load_bucket.rs:264-322): a signal of an element of a component
+    /// array of mixed templates.  The C++ looks the offset up at run time in templateInsId2IOSignalInfo[templateId of the
+    /// element]; here the element (cmp) is a compile-time value, so its template instance is known and the very same
+    /// arithmetic runs now: defs[signal_code].offset + ((i0 * lengths[1] + i1) * lengths[2] + ...) * size, missing trailing
+    /// indexes multiplied through.  Bus fields (AccessType::Qualified -> busInsId2FieldInfo) are flattened the same way
+    /// from producer.busid_field_info.
+    fn mapped_address(&mut self, cmp: usize, signal_code: usize, indexes: &[AccessType]) -> Result<usize, ()> {
+        let template_id = self.rec.subs[self.sub_of_cmp[cmp] as usize] as usize;
+        let defs = self.producer.io_map.get(&template_id).ok_or(())?;
+        let mut cur = defs.iter().find(|d| d.code == signal_code).ok_or(())?.clone();
+        let mut offset = cur.offset;
+        for (pos, access) in indexes.iter().enumerate() {
+            match access {
+                AccessType::Indexed(info) => {
+                    let mut idx = self.address(&info.indexes[0])?;
+                    for i in 1..info.indexes.len() { idx = idx * cur.lengths[i] + self.address(&info.indexes[i])?; }
+                    if info.indexes.len() < info.symbol_dim {
+                        if pos + 1 != indexes.len() { return Err(()); }             // must be the last access (load_bucket.rs:297)
+                        for i in info.indexes.len()..info.symbol_dim { idx *= cur.lengths[i]; }
+                    }
+                    offset += idx * cur.size;
+                }
+                AccessType::Qualified(field_no) => {
+                    let bus = cur.bus_id.ok_or(())?;
+                    let f = self.producer.busid_field_info.get(bus).and_then(|fs| fs.get(*field_no)).ok_or(())?;
+                    offset += f.offset;
+                    cur = IODef { code: *field_no, offset: f.offset, lengths: f.dimensions.clone(), size: f.size, bus_id: f.bus_id };
+                }
+            }
+        }
+        Ok(offset)
+    }
 }
 
 fn operator_code(op: &OperatorType) -> Result<Op, ()> {
@@ -125,9 +158,13 @@ impl WriteCuda for ComputeBucket { // compute_bucket.rs:276-400
 
 impl WriteCuda for LoadBucket {    // load_bucket.rs:325-447
     fn produce_cuda(&self, cx: &mut TemplateCtx) -> Result<Option<Val>, ()> {
-        let idx = match &self.src {
-            LocationRule::Indexed { location, .. } => cx.address(location)?,
-            LocationRule::Mapped { .. } => return Err(()), // templateInsId2IOSignalInfo lookups: not in version 1
+        let idx = match (&self.src, &self.address_type) {
+            (LocationRule::Indexed { location, .. }, _) => cx.address(location)?,
+            (LocationRule::Mapped { signal_code, indexes }, AddressType::SubcmpSignal { cmp_address, .. }) => {
+                let cmp = cx.address(cmp_address)?;
+                cx.mapped_address(cmp, *signal_code, indexes)?
+            }
+            _ => return Err(()),                       // Mapped is only ever produced for sub-component signals
         };
         Ok(Some(match &self.address_type {
             AddressType::Variable => cx.vars[idx].clone(),
@@ -144,9 +181,13 @@ impl WriteCuda for StoreBucket {   // store_bucket.rs:607-834
     fn produce_cuda(&self, cx: &mut TemplateCtx) -> Result<Option<Val>, ()> {
         if self.context.size != SizeOption::Single(1) { return Err(()); } // array copies: expanded by the caller per element
         let v = self.src.produce_cuda(cx)?.ok_or(())?;
-        let idx = match &self.dest {
-            LocationRule::Indexed { location, .. } => cx.address(location)?,
-            LocationRule::Mapped { .. } => return Err(()),
+        let idx = match (&self.dest, &self.dest_address_type) {
+            (LocationRule::Indexed { location, .. }, _) => cx.address(location)?,
+            (LocationRule::Mapped { signal_code, indexes }, AddressType::SubcmpSignal { cmp_address, .. }) => {
+                let cmp = cx.address(cmp_address)?;
+                cx.mapped_address(cmp, *signal_code, indexes)?
+            }
+            _ => return Err(()),
         };
         match &self.dest_address_type {
             AddressType::Variable => { cx.vars[idx] = v; }

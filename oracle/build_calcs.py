@@ -22,6 +22,8 @@ def circuits():
         "all_ops": ("bn128", lambda d: C.all_ops(d)),
         "all_ops_bls": ("bls12381", lambda d: C.all_ops(d)),
         "less_than8": ("bn128", lambda d: C.less_than(d, 8)),
+        # a component array of mixed templates: the calculator reads sub-component signals through the io map of its .dat
+        "mixed_array": ("bn128", lambda d: C.mixed_array(d)),
         "poseidon2": ("bn128", lambda d: C.poseidon(d, 2)),
         "int_div32": ("bn128", lambda d: C.int_div(d, 32)),
         "int_div_arr32": ("bn128", lambda d: C.int_div_array(d, 32, "all")),     # `var qr[3] = f(a, b);`: one call, three results

@@ -70,7 +70,7 @@ def emit_cpp(desc) -> str:
     w("uint get_size_of_input_hashmap() {return %d;}\n" % hashmap_size(desc))
     w("uint get_size_of_witness() {return %d;}\n" % desc.total_signals)
     w("uint get_size_of_constants() {return %d;}\n" % len(desc.consts))
-    w("uint get_size_of_io_map() {return 0;}\n")
+    w("uint get_size_of_io_map() {return %d;}\n" % len(getattr(desc, "io_map_templates", ())))
     w("uint get_size_of_bus_field_map() {return 0;}\n")
     w("void release_memory_component(Circom_CalcWit* ctx, uint pos) {{\n"
       "if (pos != 0){{\n"
@@ -196,6 +196,16 @@ def _emit_template(w, t) -> None:
         if k == K_OWN:
             return "&signalValues[mySignalStart + %d]" % r[2]
         if k == K_SUB:
+            st = t.subs[r[1]].tmpl
+            if st.id in getattr(t.desc, "io_map_templates", ()):
+                # LocationRule::Mapped (load_bucket.rs:264-322, store_bucket.rs:498-566): the element of a component array of
+                # mixed templates - the signal's offset comes from templateInsId2IOSignalInfo at run time
+                code, idx, is_array = _io_code(st, r[2])
+                d0 = "ctx->templateInsId2IOSignalInfo[ctx->componentMemory[mySubcomponents[%d]].templateId].defs[%d]" % (r[1], code)
+                acc = "%s.offset" % d0
+                if is_array:
+                    acc = "%s+(%d)*%s.size" % (acc, idx, d0)
+                return "&ctx->signalValues[ctx->componentMemory[mySubcomponents[%d]].signalStart + %s]" % (r[1], acc)
             return "&ctx->signalValues[ctx->componentMemory[mySubcomponents[%d]].signalStart + %d]" % (r[1], r[2])
         if k == K_CONST:
             return "&circuitConstants[%d]" % r[2]
@@ -262,6 +272,36 @@ def _emit_template(w, t) -> None:
     w("}\n")
 
 
+def _io_code(st, local_id: int):
+    """(signal code, element index, is array) of input / output signal `local_id` of template instance st: codes number the
+    declared outputs then inputs (TemplateDB::get_signal_id order = IODef order, build.rs:498-520)"""
+    code, off = 0, 0
+    for cat in ("out", "in"):
+        for name, n in st.sigs[cat]:
+            if off <= local_id < off + n:
+                return code, local_id - off, st.sig_is_array[name]
+            off += n
+            code += 1
+    raise ValueError("signal %d of %s is not an input or output" % (local_id, st.name))
+
+
+def io_map_bytes(desc) -> bytes:
+    """generate_dat_io_signals_info (c_code_generator.rs:681-735): the template ids, then per template the number of signals
+    and per signal offset, #dimensions - 1, the dimensions but the first, element size, bus id - u32 little endian (the Rust
+    writes to_be_bytes reversed).  generate_dat_bus_field_info (:737-794) adds nothing without buses."""
+    from circom_b200.circuit import CircuitDesc
+    tids = sorted(getattr(desc, "io_map_templates", ()))
+    out = b"".join(struct.pack("<I", t) for t in tids)
+    for t in tids:
+        defs = CircuitDesc.io_defs(desc.templates[t])
+        out += struct.pack("<I", len(defs))
+        for off, lengths, size, bus in defs:
+            out += struct.pack("<II", off, len(lengths) - 1 if lengths else 0)
+            out += b"".join(struct.pack("<I", x) for x in lengths[1:])
+            out += struct.pack("<II", size, bus)
+    return out
+
+
 def hashmap_size(desc) -> int:
     n = len(desc.main_inputs())
     s = 256
@@ -291,7 +331,7 @@ def dat_bytes(desc) -> bytes:
         else:
             out += struct.pack("<iI", 0, 0xC0000000)
         out += ((n * R) % q).to_bytes(32, "little")
-    return out
+    return out + io_map_bytes(desc)
 
 
 def build_reference_calculator(desc, out_dir: str, name: str | None = None, opt: str = "-O3") -> str:

@@ -154,9 +154,12 @@ def test_packed_record_layout_and_host_expansion():
 def test_dat_equals_the_file_the_reference_runtime_loads(prime, tmp_path):
     """cw_circuit_write_dat (--O0 witness list) == the .dat the reference calculators of oracle/_ref are linked with
     (oracle/emit_ref_cpp.dat_bytes, consumed by the reference's loadCircuit, main.cpp:22-124): hash map, witness list
-    and the constants in their 40-byte tagged Montgomery form (short constants incl. negative ones, long ones)"""
-    from oracle.emit_ref_cpp import dat_bytes
-    for mk in (lambda d: C.all_ops(d), lambda d: C.poseidon(d, 2), lambda d: C.int_div(d, 32), lambda d: C.less_than(d, 8)):
+    and the constants in their 40-byte tagged Montgomery form (short constants incl. negative ones, long ones); for a
+    component array of mixed templates also templateInsId2IOSignalInfo (c_code_generator.rs:681-735) - the reference
+    calculator of that circuit (oracle/_ref/calc/mixed_array) reads its sub-component signals through it"""
+    from oracle.emit_ref_cpp import dat_bytes, io_map_bytes
+    for mk in (lambda d: C.all_ops(d), lambda d: C.poseidon(d, 2), lambda d: C.int_div(d, 32), lambda d: C.less_than(d, 8),
+               lambda d: C.mixed_array(d)):
         d = CircuitDesc(prime)
         d.set_main(mk(d))
         d.const_id(-5)
@@ -168,3 +171,4 @@ def test_dat_equals_the_file_the_reference_runtime_loads(prime, tmp_path):
         p = str(tmp_path / "c.dat")
         c.write_dat(p)
         assert open(p, "rb").read() == dat_bytes(d)
+    assert len(io_map_bytes(d)) == 4 * (3 + 3 + 3 * 3 * 4) and open(p, "rb").read().endswith(io_map_bytes(d))

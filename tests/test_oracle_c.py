@@ -66,7 +66,7 @@ def test_c_oracle_circuits_vs_python_evaluator(name):
 
 
 REF_NAMES = ["multiplier2", "all_ops", "all_ops_bls", "less_than8", "poseidon2", "int_div32", "ecdsa_scale_2x5",
-             "ecdsa_scale_8x132"]
+             "ecdsa_scale_8x132", "mixed_array"]
 
 
 @pytest.mark.parametrize("name", REF_NAMES)

@@ -313,6 +313,34 @@ def test_hostile_symbols_section():
     assert try_load(plain + b"SYMS" + struct.pack("<I", 5000) + b"a" * 5000 + body[12:]) == native.CW_EFORMAT
 
 
+def test_hostile_io_map_section():
+    """the IOMP section (docs/CB2C.md) ends up in the `.dat` a reference runtime indexes with: entries must name existing
+    templates in ascending order and signals inside their inputs and outputs; truncated or oversized counts are refused"""
+    d = CircuitDesc("bn128")
+    d.set_main(C.mixed_array(d))
+    good = d.to_bytes()
+    at = good.index(b"IOMP")
+    plain, sec = good[:at], good[at:]
+    assert try_load(good) == 0 and try_load(good + d.to_bytes(symbols=True)[len(good):]) == 0      # IOMP, then SYMS
+    u = lambda *xs: struct.pack("<%dI" % len(xs), *xs)
+    entry = lambda tid, defs: u(tid, len(defs)) + b"".join(u(o, len(ls)) + u(*ls) + u(sz, bus) for o, ls, sz, bus in defs)
+    ok = [(0, [], 1, 0), (1, [2], 1, 0), (3, [], 1, 0)]           # template 0 = Acc(2): out, in[2], k
+    assert try_load(plain + b"IOMP" + u(1) + entry(0, ok)) == 0
+    for bad in (b"IOMP" + u(1) + entry(9, ok),                                          # no such template
+                b"IOMP" + u(2) + entry(1, ok[:1]) + entry(0, ok[:1]),                    # not ascending
+                b"IOMP" + u(2) + entry(0, ok[:1]) + entry(0, ok[:1]),                    # twice
+                b"IOMP" + u(1) + entry(0, [(3, [2], 1, 0)]),                             # runs past the template's signals
+                b"IOMP" + u(1) + entry(0, [(0, [3, 2], 1, 0)]),
+                b"IOMP" + u(1) + entry(0, [(0, [], 0, 0)]),                              # element size 0
+                b"IOMP" + u(1) + entry(0, ok + ok),                                      # more signals than inputs + outputs
+                b"IOMP" + u(1) + u(0, 1) + u(0, 33) + u(*([1] * 33)) + u(1, 0),          # 33 dimensions
+                b"IOMP" + u(1) + u(0, 1) + u(0, 0xFFFFFFFF),                             # dimension count past the file
+                b"IOMP" + u(0xFFFFFFFF),
+                b"IOMP" + u(1) + entry(0, ok)[:-4],
+                sec + b"\0\0\0\0", b"IOMQ" + sec[4:]):
+        assert try_load(plain + bad) == native.CW_EFORMAT, bad[:24]
+
+
 def test_set_input_outside_main_inputs_is_refused():
     """cw_batch_set_input indexes host arrays with (signal id - first input): a hash-map entry pointing elsewhere must
     not be followed (defence in depth behind the parser's check) - exercised through the Python twin of the lookup"""

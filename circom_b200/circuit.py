@@ -43,6 +43,8 @@ OPS = {
     "SHL": 8, "SHR": 9, "LEQ": 10, "GEQ": 11, "LT": 12, "GT": 13, "EQ": 14, "NEQ": 15,
     "LOR": 16, "LAND": 17, "LNOT": 18, "BOR": 19, "BAND": 20, "BXOR": 21, "BNOT": 22,
     "NEG": 23, "COPY": 24, "SELECT": 25, "ASSERT": 26, "ASSERT_EQ": 27,
+    # producer-level only (never in a .cb2c): d <- own signal array element a[toInt(b)], c = (NONE, extent) - Template.load_indexed
+    "LOADSIG": 48,
     # function bodies (FunctionCodeInfo, compiler/src/circuit_design/function.rs) and their call sites
     "JMP": 40, "JZ": 41, "RET": 42, "LOADX": 43, "STOREX": 44, "CALL": 45, "ARG": 46,
 }
@@ -316,6 +318,64 @@ class Template:
         a = a if isinstance(a, Expr) else self.const(a)
         b = b if isinstance(b, Expr) else self.const(b)
         return Expr(self, self._emit("SELECT", a, b, cond))
+
+    def load_indexed(self, arr: Sequence[Expr], idx: Expr) -> Expr:
+        """`arr[idx]` in a `<--` expression with a SIGNAL-dependent index - the reference compiler prints a load whose address
+        is computed at run time, `&signalValues[mySignalStart + base + Fr_toInt(idx)]` (LoadBucket with an Indexed location
+        over ToAddress, load_bucket.rs:325-447, compute_bucket.rs:361-363).  Tape operands are static, so a producer for this
+        back end expands the access over the array's extent: n comparisons, n selections, two adder trees, and an assert that
+        the index hit an element (the reference reads whatever lies beside the array there).  `arr` is a declared signal array
+        of this template.  The expansion is written at serialisation (Template.expanded_ops); evaluators of the description
+        and the reference-calculator emitter see the access itself."""
+        assert arr and all(e._ref is not None and e._ref[0] == K_OWN for e in arr), "load_indexed: an own signal array"
+        name = arr[0]._ref[2][1]
+        assert [e._ref[2] for e in arr] == [("name", name, j) for j in range(len(arr))] and self.sig_info[name][1] == len(arr)
+        dst = self._tmp()
+        self.ops.append((OPS["LOADSIG"], dst, arr[0].ref, idx.ref, (K_NONE, 0, len(arr))))
+        return Expr(self, dst)
+
+    def expanded_ops(self):
+        """(ops as a `.cb2c` carries them, n_tmp): LOADSIG replaced by primitive operations on fresh temporaries"""
+        if not any(op == OPS["LOADSIG"] for op, *_ in self.ops):
+            return self.ops, self.n_tmp
+        out, n_tmp = [], self.n_tmp
+        cref = lambda v: (K_CONST, 0, self.desc.const_id(v))
+
+        def tmp():
+            nonlocal n_tmp
+            n_tmp += 1
+            return (K_TMP, 0, n_tmp - 1)
+
+        def tree(refs, last=None):
+            refs = list(refs)
+            while len(refs) > 1:
+                nxt = []
+                for i in range(0, len(refs) - 1, 2):
+                    d = last if (last is not None and len(refs) == 2) else tmp()
+                    out.append((OPS["ADD"], d, refs[i], refs[i + 1], NONE_REF))
+                    nxt.append(d)
+                if len(refs) & 1:
+                    nxt.append(refs[-1])
+                refs = nxt
+            return refs[0]
+        for op, d, a, b, c in self.ops:
+            if op != OPS["LOADSIG"]:
+                out.append((op, d, a, b, c))
+                continue
+            n, base = c[2], a[2]
+            eqs, sels = [], []
+            for i in range(n):
+                e = tmp()
+                out.append((OPS["EQ"], e, b, cref(i), NONE_REF))
+                eqs.append(e)
+            for i in range(n):
+                sl = d if n == 1 else tmp()
+                out.append((OPS["SELECT"], sl, (K_OWN, 0, base + i), cref(0), eqs[i]))
+                sels.append(sl)
+            if n > 1:
+                tree(sels, last=d)
+            out.append((OPS["ASSERT"], NONE_REF, tree(eqs), NONE_REF, NONE_REF))
+        return out, n_tmp
 
     def call(self, fn: "Function", args: Sequence) -> Expr:
         """`f(args...)` inside an expression (CallBucket, call_bucket.rs:466-533): the arguments are copied to
@@ -726,6 +786,7 @@ class CircuitDesc:
         assert self.main is not None
         # constraint coefficients go through the constant table as well
         blobs = []
+        expanded = {t.id: t.expanded_ops() for t in self.templates}   # (first: the expansions add constants)
         for t in self.templates:
             nb = t.name.encode()
             nb += b"\0" * ((-len(nb)) % 4)
@@ -739,11 +800,12 @@ class CircuitDesc:
                         cons_words.append(self.const_id(lc[k]))
                         nterms += 1
             hdr = struct.pack("<I", len(t.name.encode())) + nb
-            hdr += struct.pack("<8I", t.n_out, t.n_in, t.n_inter, len(t.subs), t.n_tmp, len(t.ops),
+            t_ops, t_n_tmp = expanded[t.id]
+            hdr += struct.pack("<8I", t.n_out, t.n_in, t.n_inter, len(t.subs), t_n_tmp, len(t_ops),
                                len(t.constraints), nterms)
             subs = np.array([s.tmpl.id for s in t.subs], dtype="<u4").tobytes()
             ops = np.array([[op, pack_ref(d), pack_ref(a), pack_ref(b), pack_ref(c)]
-                            for op, d, a, b, c in t.ops], dtype="<u8").reshape(-1, 5).tobytes()
+                            for op, d, a, b, c in t_ops], dtype="<u8").reshape(-1, 5).tobytes()
             cons = np.array(cons_words, dtype="<u8").tobytes()
             blobs.append(hdr + subs + ops + cons)
         names = b""

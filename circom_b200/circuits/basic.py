@@ -166,3 +166,28 @@ def mixed_array(d: CircuitDesc) -> Template:
         t.assign_constrained(out[2], o2.sig("out", 0))
         t.assign_constrained(out[3], o2.sig("out", 1))
     return d.template("MixedArray", (), build)
+
+
+def table_lookup(d: CircuitDesc, n: int = 8) -> Template:
+    """`out <-- table[sel]` with a signal index - a witness hint the reference compiles to a load at a run-time address
+    (Template.load_indexed) - constrained the circomlib way: a one-hot decomposition of sel (IsEqual per position via the
+    inverse trick is overkill here: eq[i] * (sel - i) === 0, sum eq[i] === 1) and out === sum eq[i] * table[i]."""
+    def build(t: Template):
+        table = t.input("table", n)
+        sel = t.input("sel")
+        out = t.output("out")
+        picked = t.signal("picked")
+        t.assign(picked, t.load_indexed(table, sel))          # <-- table[sel]
+        eq = t.signal("eq", n)
+        prod = t.signal("prod", n)
+        acc_e, acc_p = None, None
+        for i in range(n):
+            t.assign(eq[i], sel.eq(i))
+            t.constrain(eq[i] * (sel - i), t.const(0))
+            t.assign_constrained(prod[i], eq[i] * table[i])
+            acc_e = eq[i] if acc_e is None else acc_e + eq[i]
+            acc_p = prod[i] if acc_p is None else acc_p + prod[i]
+        t.constrain(acc_e, t.const(1))
+        t.constrain(picked, acc_p)
+        t.assign_constrained(out, picked * picked)
+    return d.template("TableLookup", (n,), build)

@@ -28,6 +28,7 @@ pub struct TemplateCtx<'a> {
     pub vars: Vec<Val>,                 // lvar[]: template.rs:288
     pub sub_of_cmp: Vec<u32>,           // component slot -> index into rec.subs (CreateCmpBucket order)
     pub n_out: usize, pub n_in: usize,
+    pub signal_extents: &'a [(usize, usize)],   // (first local id, total size) of every declared signal (array) of the template
 }
 
 pub trait WriteCuda {
@@ -57,6 +58,73 @@ impl<'a> TemplateCtx<'a> {
     }
     /// signal index inside this template -> reference (outputs, inputs, intermediates: executed_template.rs:442-552)
     fn own(&self, idx: usize) -> Ref { Ref::Own(idx as u32) }
+    /// number of `stride`-sized elements from own signal `base` to the end of the array that contains it
+    fn signal_extent(&self, base: usize, stride: usize) -> Result<usize, ()> {
+        let (first, len) = self.signal_extents.iter().find(|(f, l)| *f <= base && base < f + l).ok_or(())?;
+        if stride == 0 || (first + len - base) % stride != 0 { return Err(()); }
+        Ok((first + len - base) / stride)
+    }
+    /// A load address that depends on a signal (`out <-- table[sel]`): the location is address arithmetic over one
+    /// `ToAddress(value)` (compute_bucket.rs:361-363: Fr_toInt) - base + toInt(value) * stride.  Returns (base, value, stride).
+    fn dynamic_address(&mut self, i: &InstructionPointer) -> Result<(usize, Ref, usize), ()> {
+        if let Instruction::Compute(c) = &**i {
+            use OperatorType::*;
+            match c.op {
+                ToAddress => {
+                    let v = c.stack[0].produce_cuda(self)?.ok_or(())?;
+                    return Ok((0, self.as_ref(&v), 1));
+                }
+                AddAddress => {
+                    let (k, d) = match (self.address(&c.stack[0]), self.address(&c.stack[1])) {
+                        (Ok(k), Err(())) => (k, &c.stack[1]),
+                        (Err(()), Ok(k)) => (k, &c.stack[0]),
+                        _ => return Err(()),                              // two run-time parts: not expanded
+                    };
+                    let (base, v, stride) = self.dynamic_address(d)?;
+                    return Ok((base + k, v, stride));
+                }
+                MulAddress => {
+                    let (k, d) = match (self.address(&c.stack[0]), self.address(&c.stack[1])) {
+                        (Ok(k), Err(())) => (k, &c.stack[1]),
+                        (Err(()), Ok(k)) => (k, &c.stack[0]),
+                        _ => return Err(()),
+                    };
+                    let (base, v, stride) = self.dynamic_address(d)?;
+                    return Ok((base * k, v, stride * k));
+                }
+                _ => {}
+            }
+        }
+        Err(())
+    }
+    /// The expansion of such a load over the array it indexes (docs/CB2C.md, "run-time addresses"; the Python DSL's
+    /// Template.expanded_ops writes the same ops): EQ(value, i), SELECT(eq_i ? signal[base + i * stride] : 0), two adder trees,
+    /// ASSERT(sum of the eq_i).  `extent` = elements from `base` to the end of the indexed array:
+    /// TemplateCodeInfo::signal_extents (added by circom/src/patch.md from TemplateInstance::wires, the source of
+    /// build_input_output_list, build.rs:498-520).
+    fn indexed_signal_load(&mut self, base: usize, value: Ref, stride: usize, extent: usize) -> Ref {
+        let q = self.q.clone();
+        let zero = Ref::Const(self.file.const_id(&BigInt::from(0), &q));
+        let mut eqs = vec![];
+        let mut sels = vec![];
+        for i in 0..extent {
+            let ci = Ref::Const(self.file.const_id(&BigInt::from(i), &q));
+            let e = self.emit(Op::EQ, value, ci, Ref::None);
+            eqs.push(e);
+            sels.push(self.emit(Op::SELECT, self.own(base + i * stride), zero, e));
+        }
+        let tree = |cx: &mut Self, mut xs: Vec<Ref>| -> Ref {
+            while xs.len() > 1 {
+                let mut nxt = vec![];
+                for p in xs.chunks(2) { nxt.push(if p.len() == 2 { cx.emit(Op::ADD, p[0], p[1], Ref::None) } else { p[0] }); }
+                xs = nxt;
+            }
+            xs[0]
+        };
+        let hit = tree(self, eqs);
+        self.rec.ops.push(OpRec { op: Op::ASSERT, d: Ref::None, a: hit, b: Ref::None, c: Ref::None });
+        tree(self, sels)
+    }
     /// `LocationRule::Mapped` (store_bucket.rs:498-566, load_bucket.rs:264-322): a signal of an element of a component
     /// array of mixed templates.  The C++ looks the offset up at run time in templateInsId2IOSignalInfo[templateId of the
     /// element]; here the element (cmp) is a compile-time value, so its template instance is known and the very same
@@ -159,6 +227,14 @@ impl WriteCuda for ComputeBucket { // compute_bucket.rs:276-400
 impl WriteCuda for LoadBucket {    // load_bucket.rs:325-447
     fn produce_cuda(&self, cx: &mut TemplateCtx) -> Result<Option<Val>, ()> {
         let idx = match (&self.src, &self.address_type) {
+            (LocationRule::Indexed { location, .. }, AddressType::Signal) => match cx.address(location) {
+                Ok(k) => k,
+                Err(()) => {                           // a signal array indexed by a signal: expanded over the array
+                    let (base, value, stride) = cx.dynamic_address(location)?;
+                    let extent = cx.signal_extent(base, stride)?;
+                    return Ok(Some(Val::Dynamic(cx.indexed_signal_load(base, value, stride, extent))));
+                }
+            },
             (LocationRule::Indexed { location, .. }, _) => cx.address(location)?,
             (LocationRule::Mapped { signal_code, indexes }, AddressType::SubcmpSignal { cmp_address, .. }) => {
                 let cmp = cx.address(cmp_address)?;

@@ -24,6 +24,8 @@ def circuits():
         "less_than8": ("bn128", lambda d: C.less_than(d, 8)),
         # a component array of mixed templates: the calculator reads sub-component signals through the io map of its .dat
         "mixed_array": ("bn128", lambda d: C.mixed_array(d)),
+        # `out <-- table[sel]`: the calculator loads at a run-time address, the description carries the expansion
+        "table_lookup8": ("bn128", lambda d: C.table_lookup(d, 8)),
         "poseidon2": ("bn128", lambda d: C.poseidon(d, 2)),
         "int_div32": ("bn128", lambda d: C.int_div(d, 32)),
         "int_div_arr32": ("bn128", lambda d: C.int_div_array(d, 32, "all")),     # `var qr[3] = f(a, b);`: one call, three results

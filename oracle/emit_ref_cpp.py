@@ -243,6 +243,12 @@ def _emit_template(w, t) -> None:
         if op == 26:  # ASSERT
             w("assert(Fr_isTrue(%s));" % addr(a))
             continue
+        if op == 48:  # LOADSIG: a load whose Indexed location is computed at run time (load_bucket.rs:325-447 with
+            #           ComputeBucket ToAddress = Fr_toInt, compute_bucket.rs:361-363)
+            w("{")
+            w("Fr_copy(%s,&signalValues[mySignalStart + (%d + Fr_toInt(%s))]);" % (addr(d), a[2], addr(b)))
+            w("}")
+            continue
         dst = addr(d)
         w("{")
         if op == 24:

@@ -151,6 +151,14 @@ def evaluate(desc, inputs: Dict[str, Sequence[int]], check_asserts: bool = True)
                 if check_asserts and load(a) == 0:
                     raise AssertFailed(t.name)
                 continue
+            if op == 48:   # LOADSIG (producer level, circuit.py: Template.load_indexed): own signal array a[toInt(b)], extent cc
+                iv = load(b)
+                iv = iv - F.q if iv > F.half else iv           # Fr_toInt on the signed view (generic/fr.cpp:2766-2803)
+                if not 0 <= iv < cc[2]:
+                    raise AssertFailed(t.name)                 # the reference reads beside the array here
+                tmp[d[2]] = sig[c.start + a[2] + iv]
+                assert tmp[d[2]] is not None, "indexed load of a signal that is not assigned yet"
+                continue
             v = F.apply(op, load(a), load(b), load(cc))
             if d[0] == K_TMP:
                 tmp[d[2]] = v

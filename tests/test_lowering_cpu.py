@@ -38,6 +38,10 @@ CIRCUITS = {
     "gcd32": (lambda d: C.gcd_circuit(d, 32),
               lambda r, q: {"a": r.choice([0, 1, 2**32 - 1, r.randrange(2**32), 2 * 3 * 5 * 7 * 11 * 13 * r.randrange(1, 1000)]),
                             "b": r.choice([0, 1, r.randrange(1, 2**32), 2 * 3 * 5 * 7 * r.randrange(1, 100000)])}),
+    # a component array of mixed templates (io map in the description) and a load at a run-time address (expanded by the producer)
+    "mixed_array": (lambda d: C.mixed_array(d), lambda r, q: {"a": [r.randrange(q) for _ in range(3)], "b": r.choice([0, 1, r.randrange(q)])}),
+    "table_lookup8": (lambda d: C.table_lookup(d, 8), lambda r, q: {"table": [r.choice([0, 1, q - 1, r.randrange(q)]) for _ in range(8)],
+                                                                     "sel": r.randrange(8)}),
     # the bench circuit's BigMultModP with its quotient / remainder hints computed by a long_div-style function
     "ecdsa_calls_1x2": (lambda d: C.ecdsa_scale(d, 1, 2, hints="functions"),
                         lambda r, q: {"a": [r.choice([2**64 - 1, r.getrandbits(64)]) for _ in range(4)],
@@ -359,3 +363,27 @@ def test_integer_rows_are_left_alone_where_they_do_not_pay():
     g.set_main(C.less_than(g, 12))
     fc, fp, cnt = hostsim_run_r1cs(g, [{"in": [77, 3000]}], 48)
     assert fc.tolist() == fp.tolist() == [-1] and cnt[0] == 0
+
+
+def test_indexed_load_expansion_and_its_range_assert():
+    """`out <-- table[sel]` (Template.load_indexed): the description carries the expansion (EQ / SELECT per element, adder
+    trees, an assert that the index hit), the evaluator indexes directly; an index outside the array - where the reference
+    reads whatever lies beside it - gives a non-zero status instead of a witness"""
+    d = CircuitDesc("bn128")
+    d.set_main(C.table_lookup(d, 5))
+    t = d.main
+    ops, n_tmp = t.expanded_ops()
+    assert any(op == OPS["LOADSIG"] for op, *_ in t.ops) and not any(op == OPS["LOADSIG"] for op, *_ in ops)
+    assert len(ops) == len(t.ops) - 1 + 5 + 5 + 4 + 4 + 1 and n_tmp > t.n_tmp
+    ins = [{"table": [10, 20, 30, 40, 50], "sel": k} for k in range(5)]
+    for flags in (0, 4, 48, 112):
+        wit, st, _, w2s = hostsim_run(d, ins, flags=flags)
+        assert not st.any()
+        for k in range(5):
+            assert limbs_to_ints(wit[k])[1] == (10 * (k + 1)) ** 2
+    bad = [{"table": [1, 2, 3, 4, 5], "sel": 5}, {"table": [1, 2, 3, 4, 5], "sel": d.q - 1}, {"table": [1, 2, 3, 4, 5], "sel": 2**40}]
+    _, st, _, _ = hostsim_run(d, bad, flags=48)
+    assert (st != 0).all()
+    for b in bad:
+        with pytest.raises(Exception):
+            evaluate(d, b)

@@ -66,7 +66,7 @@ def test_c_oracle_circuits_vs_python_evaluator(name):
 
 
 REF_NAMES = ["multiplier2", "all_ops", "all_ops_bls", "less_than8", "poseidon2", "int_div32", "ecdsa_scale_2x5",
-             "ecdsa_scale_8x132", "mixed_array"]
+             "ecdsa_scale_8x132", "mixed_array", "table_lookup8"]
 
 
 @pytest.mark.parametrize("name", REF_NAMES)
@@ -82,6 +82,11 @@ def test_reference_runtime_wtns_equals_oracle(name, tmp_path):
         arr[:, :, 0] = rng.integers(0, 2**64, size=(2, n_in), dtype=np.uint64)
     elif name.startswith("less_than"):
         arr[:, :, 0] = rng.integers(0, 256, size=(2, n_in), dtype=np.uint64)
+    elif name.startswith("table_lookup"):
+        arr[:, :, :] = rng.integers(0, 2**64, size=(2, n_in, 4), dtype=np.uint64)
+        arr[:, :, 3] &= np.uint64(0x0FFFFFFFFFFFFFFF)
+        arr[:, n_in - 1, :] = 0
+        arr[:, n_in - 1, 0] = rng.integers(0, n_in - 1, size=2, dtype=np.uint64)   # sel: a position of the table
     elif name.startswith("int_div"):
         arr[:, 0, 0] = rng.integers(0, 2**32, size=2, dtype=np.uint64)
         arr[:, 1, 0] = rng.integers(1, 2**20, size=2, dtype=np.uint64)

@@ -288,3 +288,81 @@ def test_random_function_bodies_match_the_evaluator(seed):
     # the packed frame never exceeds the declared one
     from circom_b200.witness_calculator import Circuit
     assert Circuit(d, host_only=True).functions()[-1]["n_regs"] <= fn.n_regs
+
+
+def bit_logic_template(d, rng, n_in):
+    """random circuits of the kind the integer rows are for: range checks (boolean rows, recomposition sums that become runs
+    of plane bits), and / xor / majority-style products of bits, linear forms with +-2^k coefficients up to 2^44, a few
+    field-sized coefficients and long sums in between"""
+    widths = [rng.choice([3, 8, 16, 33]) for _ in range(n_in)]
+
+    def build(t):
+        xs = t.input("x", n_in)
+        out = t.output("out")
+        vals = []
+        for i, x in enumerate(xs):
+            b = t.signal("b%d" % i, widths[i])
+            acc = t.const(0)
+            for k in range(widths[i]):
+                t.assign(b[k], (x >> k) & 1)
+                t.constrain(b[k] * (b[k] - 1), 0)
+                acc = acc + b[k] * (1 << k)
+            if rng.random() < 0.8:
+                t.constrain(acc, x)
+            vals += b
+        for j in range(rng.randrange(12, 40)):
+            a, b2, c = rng.choice(vals), rng.choice(vals), rng.choice(vals)
+            s = t.signal("v%d" % j)
+            kind = rng.choice(["and", "xor", "lin", "lin", "big", "sum"])
+            if kind == "and":
+                t.assign_constrained(s, a * b2)
+            elif kind == "xor":
+                t.assign_constrained(s, a + b2 - 2 * a * b2)
+            elif kind == "lin":
+                k1, k2 = rng.randrange(0, 31), rng.randrange(0, 46)
+                t.assign_constrained(s, (a * (1 << k1) - b2 + c * (1 << k2)) * rng.choice(vals))
+            elif kind == "big":
+                t.assign_constrained(s, (a * rng.randrange(d.q) + b2) * c)
+            else:
+                e = t.const(0)
+                for _ in range(rng.randrange(30, 70)):
+                    e = e + rng.choice(vals) * (1 << rng.randrange(0, 20)) * rng.choice([1, -1])
+                t.assign_constrained(s, e * a)
+            vals.append(s)
+        t.assign_constrained(out, vals[-1] * vals[-2])
+    return d.template("BitLogic%d" % rng.randrange(1 << 30), (), build)
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_compiled_r1cs_with_integer_rows_on_random_circuits(seed, monkeypatch):
+    """the compiled R1CS (general rows, integer rows with their grouped records, absorbed and free-standing boolean rows,
+    runs of plane bits) on the value store of random circuits, with the integer rows forced on however few they are:
+    equal to the definition on valid witnesses and on witnesses with one entry overwritten"""
+    from tests.util import hostsim_run_r1cs
+    monkeypatch.setenv("CW_R1CS_SMALL_ALWAYS", "1")
+    rng = random.Random(31337 + seed)
+    d = CircuitDesc("bn128" if seed % 3 else "bls12381")
+    n_in = rng.randrange(2, 5)
+    if seed % 2:
+        d.set_main(random_template(d, rng, n_in, n_vals=rng.randrange(20, 70), with_components=seed % 4 == 1))
+    else:
+        d.set_main(bit_logic_template(d, rng, n_in))
+    edges = edge_values(d.q)
+    small = lambda: rng.choice([0, 1, 1, 2, 3, 255, 65535, 65536, rng.randrange(1 << 16), rng.randrange(1 << 33)])
+    ins = [{"x": [small() if rng.random() < 0.7 else rand_input(rng, d.q, edges) for _ in range(n_in)]} for _ in range(6)]
+    n_small = n_wide = 0
+    for flags in (0, CW_FLAG_COMPACT):
+        fc, fp, cnt = hostsim_run_r1cs(d, ins, flags)
+        assert fc.tolist() == fp.tolist(), (seed, flags)
+        if seed % 2:
+            assert fc.tolist() == [-1] * len(ins)
+        n_small += cnt[0]
+        n_wide += cnt[1]
+        W = len(hostsim_run(d, ins[:1], flags)[3])
+        for trial in range(8):
+            wire = rng.randrange(1, W)
+            val = rng.choice([0, 1, 2, 65535, 65536, 1 << 40, d.q - 1, rng.randrange(d.q)])
+            fc, fp, _ = hostsim_run_r1cs(d, ins[:2], flags, tamper=(wire, val))
+            assert fc.tolist() == fp.tolist(), (seed, flags, wire, val)
+    if seed % 2 == 0:
+        assert n_small >= 8

@@ -466,7 +466,7 @@ class WitnessCalculator:
         self.device = device
         self.prime = self.circuit.prime
         self.witnessSize = self.circuit.n_witness
-        self.n32 = 8
+        self.n32 = 2 * ((self.prime.bit_length() + 63) // 64)   # getFieldNumLen32 (wasm_code_generator.rs:655-674): 8; goldilocks 2
         self._batches: Dict[int, Batch] = {}
 
     def circom_version(self) -> int:
@@ -501,7 +501,9 @@ class WitnessCalculator:
         return limbs_to_ints(self._run([input]).witness()[0])
 
     def calculateBinWitness(self, input: dict, sanityCheck: bool = True) -> bytes:
-        return self._run([input]).witness()[0].tobytes()
+        """witnessSize x n32 32-bit words (witness_calculator.js:194-210)"""
+        w = self._run([input]).witness()[0]
+        return np.ascontiguousarray(w[:, :self.n32 // 2]).tobytes()
 
     def calculateWTNSBin(self, input: dict, sanityCheck: bool = True) -> bytes:
         return self._run([input]).wtns_bytes(0)

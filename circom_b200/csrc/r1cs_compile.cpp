@@ -15,8 +15,9 @@ typedef uint32_t u32;
 // Compile the CSR for one value layout: wire ids become locations (slot / plane bit; identity for dense witness
 // rows), runs of plane bits with consecutive power-of-two coefficients become one term, boolean rows are absorbed
 // or dropped where the storage makes them tautologies, rows are sorted by structure.  With `want_small`, rows whose
-// terms are all small by shape (coefficients +-2^k with small k, few terms) are listed apart (perm_small): the
-// integer-row kernel decides them over the integers when the values it meets are small too (r1cs_small.h).
+// terms are all small by shape (coefficients +-2^k, the bound of each of the three sums below 2^61 when every value is
+// below 2^16) are listed apart (perm_small) with a term list of their own: the integer-row kernel decides them over the
+// integers when the values it meets are small too (r1cs_small.h).
 void compile_r1cs_host(const R1csData &R, const FieldParams &F, const Tape *T, bool no_bool_rows, bool want_small,
                        R1csCompiled &out) {
     if (T && T->n_witness != R.n_wires) throw std::runtime_error("the R1CS and the batch's circuit have different numbers of wires");

@@ -108,3 +108,33 @@ def test_symbols_section_and_sym_file(tmp_path):
         c3 = Circuit(d3, host_only=True, symbols=True)
         c3.write_sym(sym)
         assert open(sym).read() == "".join(x + "\n" for x in d3.sym_lines(c3.witness2signal()))
+
+
+def test_rust_producer_numbers_match_the_format():
+    """integration/cuda_elements is not compiled in this image; what can be pinned is that the numbers it writes are the
+    format's: the opcode enum against circuit.py's OPS (= what flatten.cpp::parse accepts), the reference kinds, the prime
+    ids, the section tags and the order of the header words"""
+    import os
+    import re
+    from circom_b200.circuit import OPS, PRIME_IDS
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "integration", "cuda_elements")
+    src = open(os.path.join(root, "code_producers", "src", "cuda_elements", "mod.rs")).read()
+    body = re.search(r"pub enum Op \{(.*?)\}", src, re.S).group(1)
+    val, ops = 0, {}
+    for item in [x.strip() for x in body.replace("\n", " ").split(",") if x.strip()]:
+        m = re.match(r"(\w+)(?:\s*=\s*(\d+))?$", item)
+        val = int(m.group(2)) if m.group(2) else val + 1
+        ops[m.group(1)] = val
+    assert ops and all(OPS[k] == v for k, v in ops.items() if k != "INV") and ops["INV"] == 28
+    assert {"MUL", "SELECT", "ASSERT_EQ", "CALL", "ARG", "LOADX", "STOREX", "RET", "JZ", "JMP"} <= set(ops)
+    for name, pid in PRIME_IDS.items():
+        assert re.search(r'"%s" => Ok\(%d\)' % (name, pid), src), name
+    kinds = re.search(r"let \(k, s, i\).*?match self \{(.*?)\};", src, re.S).group(1)
+    for variant, k in (("None", 0), ("Own", 1), ("Sub", 2), ("Const", 3), ("Tmp", 4), ("One", 5)):
+        assert re.search(r"Ref::%s\b[^=]*=> \(%d," % (variant, k), kinds), variant
+    assert src.index('b"CB2C"') < src.index('b"IOMP"') < src.index('b"SYMS"')
+    head = re.search(r"for v in \[1u32, self\.prime, (.*?)\]", src, re.S).group(1)
+    assert [w.strip().split(".")[1].split(" ")[0] for w in head.split(",")][:3] == ["consts", "templates", "main"]
+    low = open(os.path.join(root, "compiler", "src", "cuda_lowering.rs")).read()
+    for fn in ("mapped_address", "dynamic_address", "indexed_signal_load", "produce_cb2c"):
+        assert "fn %s" % fn in low

@@ -7,7 +7,8 @@
  *         component m = Multiplier2(); m.a <== x; m.b <== y; p <== m.c + 1; }
  *
  * tests/test_cb2c_spec_cpu.py checks that the bytes equal what the DSL writes for the same circuit and that the file
- * loads, lowers and computes the expected witness.   usage: cb2c_conf out.cb2c [sym]   (sym: with the symbols section) */
+ * loads, lowers and computes the expected witness.   usage: cb2c_conf out.cb2c [sym|iomap|iomap+sym]   (sym: with the symbols
+ * section; iomap: with the io-map section, as if both templates sat in a component array of mixed templates) */
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -84,7 +85,21 @@ int main(int argc, char **argv) {
     str("x"); u32(4); u32(1);
     str("y"); u32(5); u32(1);
     /* ---- no functions; optional symbols section: per template the own signals in numbering order, then the sub-components ---- */
-    if (argc > 2 && !strcmp(argv[2], "sym")) {
+    if (argc > 2 && strstr(argv[2], "iomap")) {
+        /* optional io-map section: entries in ascending template order; per signal {offset, #dims, dims.., element size, bus id} */
+        fwrite("IOMP", 1, 4, f);
+        u32(2);
+        u32(0); u32(3);                       /* Multiplier2: c, a, b */
+        u32(0); u32(0); u32(1); u32(0);
+        u32(1); u32(0); u32(1); u32(0);
+        u32(2); u32(0); u32(1); u32(0);
+        u32(1); u32(4);                       /* Conf: bits[2], p, x, y */
+        u32(0); u32(1); u32(2); u32(1); u32(0);
+        u32(2); u32(0); u32(1); u32(0);
+        u32(3); u32(0); u32(1); u32(0);
+        u32(4); u32(0); u32(1); u32(0);
+    }
+    if (argc > 2 && strstr(argv[2], "sym")) {
         fwrite("SYMS", 1, 4, f);
         str("c"); str("a"); str("b");                                       /* Multiplier2 */
         str("bits[0]"); str("bits[1]"); str("p"); str("x"); str("y"); str("m");  /* Conf: 5 signals, 1 sub-component */

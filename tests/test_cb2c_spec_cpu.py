@@ -110,6 +110,28 @@ def test_symbols_section_and_sym_file(tmp_path):
         assert open(sym).read() == "".join(x + "\n" for x in d3.sym_lines(c3.witness2signal()))
 
 
+def test_io_map_section_from_the_spec(tmp_path):
+    """The optional io-map section, written from the spec by the C writer, equals the DSL's (alone and followed by the
+    symbols); the library copies it into the `.dat` in the layout the reference's loadCircuit reads (main.cpp:57-93)"""
+    from oracle.emit_ref_cpp import dat_bytes, io_map_bytes
+    exe = str(tmp_path / "cb2c_conf")
+    subprocess.check_call(["gcc", "-O1", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "cb2c_writer", "cb2c_conf.c")])
+    d = dsl_conf()
+    d.mark_mixed_array(*d.templates)
+    for mode, sym in (("iomap", False), ("iomap+sym", True)):
+        out = str(tmp_path / ("conf_%s.cb2c" % mode))
+        subprocess.check_call([exe, out, mode])
+        blob = open(out, "rb").read()
+        assert blob == d.to_bytes(symbols=sym) and b"IOMP" in blob
+        c = Circuit(blob, host_only=True, o0=True)
+        p = str(tmp_path / "conf.dat")
+        c.write_dat(p)
+        assert open(p, "rb").read() == dat_bytes(d) and dat_bytes(d).endswith(io_map_bytes(d))
+    # template ids, then per template: #signals, {offset, #dims - 1, dims but the first, size, bus}
+    assert io_map_bytes(d) == np.array([0, 1, 3, 0, 0, 1, 0, 1, 0, 1, 0, 2, 0, 1, 0,
+                                        4, 0, 0, 1, 0, 2, 0, 1, 0, 3, 0, 1, 0, 4, 0, 1, 0], dtype="<u4").tobytes()
+
+
 def test_rust_producer_numbers_match_the_format():
     """integration/cuda_elements is not compiled in this image; what can be pinned is that the numbers it writes are the
     format's: the opcode enum against circuit.py's OPS (= what flatten.cpp::parse accepts), the reference kinds, the prime

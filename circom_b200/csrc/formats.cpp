@@ -321,8 +321,8 @@ void write_dat(const Tape &t, const std::string &path) {
     // {i32 shortVal, u32 type, n * R mod q}: values inside the signed 32-bit range carry shortVal and type
     // 0x40000000 (short + Montgomery), all others 0 and 0xC0000000 (long Montgomery).  The goldilocks runtime keeps its
     // constants as literals in the generated code: no constant list in its .dat (generate_dat_file, :838-841)
-    if (field_bytes(t.F) == 8) return;
     for (const U256 &c : t.dat_consts) {
+        if (field_bytes(t.F) == 8) break;
         U256 neg;
         u256_sub(neg, t.F.q, c);
         const bool is_neg = t.F.half < c;  // the signed view of generic/fr.cpp:1184-1218

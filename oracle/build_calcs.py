@@ -22,6 +22,10 @@ def circuits():
         "all_ops": ("bn128", lambda d: C.all_ops(d)),
         "all_ops_bls": ("bls12381", lambda d: C.all_ops(d)),
         "less_than8": ("bn128", lambda d: C.less_than(d, 8)),
+        # goldilocks: the reference's other runtime (c_elements/common64 + goldilocks/fr.hpp), u64 values, operators as expressions
+        "all_ops_gl": ("goldilocks", lambda d: C.all_ops(d)),
+        "less_than8_gl": ("goldilocks", lambda d: C.less_than(d, 8)),
+        "mixed_array_gl": ("goldilocks", lambda d: C.mixed_array(d)),
         # a component array of mixed templates: the calculator reads sub-component signals through the io map of its .dat
         "mixed_array": ("bn128", lambda d: C.mixed_array(d)),
         # `out <-- table[sel]`: the calculator loads at a run-time address, the description carries the expansion

@@ -243,9 +243,40 @@ def build_prime(prime: str, force: bool = False) -> str:
     return so
 
 
+def build_goldilocks_runtime(force: bool = False):
+    """The goldilocks runtime shell: c_elements/common64/main.cpp is a handlebars template over the prime
+    (generate_main_cpp_file, c_code_generator.rs:945-962): rendered into oracle/_ref/goldilocks/main.cpp; calcwit.cpp compiled
+    where it lies.  Returns the two objects."""
+    gdir = os.path.join(OUT, "goldilocks")
+    main_o, calc_o = os.path.join(OUT, "rt_goldilocks_main.o"), os.path.join(OUT, "rt_goldilocks_calcwit.o")
+    if not force and os.path.exists(main_o) and os.path.exists(calc_o):
+        return main_o, calc_o
+    if not have_reference():
+        raise RuntimeError("reference tree absent and oracle/_ref not prebuilt")
+    os.makedirs(gdir, exist_ok=True)
+    with open(os.path.join(REF, "common64", "main.cpp")) as f:
+        text = f.read()
+    with open(os.path.join(gdir, "main.cpp"), "w") as f:
+        f.write(text.replace("{{prime}}", "18446744069414584321ull"))
+    inc = ["-I", os.path.join(REF, "common64"), "-I", os.path.join(REF, "goldilocks"), "-I", os.path.join(HERE, "gmp_shim"),
+           "-I", json_include_dir()]
+    _run(["g++"] + CXXFLAGS + inc + ["-c", os.path.join(gdir, "main.cpp"), "-o", main_o])
+    _run(["g++"] + CXXFLAGS + inc + ["-c", os.path.join(REF, "common64", "calcwit.cpp"), "-o", calc_o])
+    return main_o, calc_o
+
+
 def build_calculator(prime: str, circuit_cpp: str, out_bin: str, opt: str = "-O3") -> str:
     """Link a hand-lowered <circuit>.cpp with the reference runtime shell into
     `out_bin` (usage: out_bin input.json out.wtns; reads out_bin + '.dat')."""
+    if prime == "goldilocks":
+        main_o, calc_o = build_goldilocks_runtime()
+        inc = ["-I", os.path.join(REF, "common64"), "-I", os.path.join(REF, "goldilocks"), "-I", os.path.join(HERE, "gmp_shim"),
+               "-I", json_include_dir()]
+        obj = out_bin + ".o"
+        _run(["g++"] + [f if f != "-O3" else opt for f in CXXFLAGS] + inc + ["-c", circuit_cpp, "-o", obj])
+        _run(["g++", "-o", out_bin, obj, main_o, calc_o, GMP_SO])
+        os.remove(obj)
+        return out_bin
     build_prime(prime)
     pdir = os.path.join(OUT, prime)
     inc = ["-I", pdir, "-I", os.path.join(HERE, "gmp_shim"), "-I", json_include_dir(),

@@ -48,6 +48,8 @@ def _header(t) -> str:
 
 
 def emit_cpp(desc) -> str:
+    if desc.prime == "goldilocks":
+        return emit_cpp_goldilocks(desc)
     out: List[str] = []
     w = out.append
     main = desc.main
@@ -329,7 +331,7 @@ def dat_bytes(desc) -> bytes:
     out += b"".join(struct.pack("<Q", i) for i in range(desc.total_signals))
     q = desc.q
     R = 1 << (((q.bit_length() + 63) // 64) * 64)
-    for v in desc.consts:
+    for v in (() if desc.prime == "goldilocks" else desc.consts):   # (goldilocks: literals in the code, c_code_generator.rs:838-841)
         n = v % q
         nn = n - q if n > q // 2 else n
         if -2147483648 <= nn <= 2147483647:
@@ -338,6 +340,135 @@ def dat_bytes(desc) -> bytes:
             out += struct.pack("<iI", 0, 0xC0000000)
         out += ((n * R) % q).to_bytes(32, "little")
     return out + io_map_bytes(desc)
+
+
+def emit_cpp_goldilocks(desc) -> str:
+    """The goldilocks flavour of the generated code (every `prime_str != "goldilocks"` branch of the emitters taken the other
+    way): values are plain `u64`, operators are expressions - `dest = Fr_mul(a, b);` (compute_bucket.rs:425-460,
+    store_bucket.rs:641-645) -, constants are literals (`<n>ull`, value_bucket.rs:82-86), there is no constant table, the
+    runtime is c_elements/common64/{main,calcwit}.cpp with c_elements/goldilocks/fr.hpp.  Component machinery as in the
+    256-bit flavour (template.rs:177-472)."""
+    if getattr(desc, "functions", []):
+        raise ValueError("the goldilocks emitter covers templates only")
+    out: List[str] = []
+    w = out.append
+    main = desc.main
+    for inc in ("<stdio.h>", "<iostream>", "<assert.h>", '"circom.hpp"', '"calcwit.hpp"', '"fr.hpp"'):
+        w("#include %s" % inc)
+    for t in desc.templates:
+        w("void %s_create(uint soffset,uint coffset,Circom_CalcWit* ctx,std::string componentName,uint componentFather);" % _header(t))
+        w("void %s_run(uint ctx_index,Circom_CalcWit* ctx);" % _header(t))
+    w("Circom_TemplateFunction _functionTable[%d] = { %s };" % (
+        len(desc.templates), ",".join("%s_run" % _header(t) for t in desc.templates)))
+    w("Circom_TemplateFunction _functionTableParallel[%d] = { %s };" % (
+        len(desc.templates), ",".join("NULL" for _ in desc.templates)))
+    w("uint get_main_input_signal_start() {return %d;}\n" % (main.n_out + 1))
+    w("uint get_main_input_signal_no() {return %d;}\n" % main.n_in)
+    w("uint get_total_signal_no() {return %d;}\n" % desc.total_signals)
+    w("uint get_number_of_components() {return %d;}\n" % main.total_components)
+    w("uint get_size_of_input_hashmap() {return %d;}\n" % hashmap_size(desc))
+    w("uint get_size_of_witness() {return %d;}\n" % desc.total_signals)
+    w("uint get_size_of_io_map() {return %d;}\n" % len(getattr(desc, "io_map_templates", ())))
+    w("uint get_size_of_bus_field_map() {return 0;}\n")
+    w("void release_memory_component(Circom_CalcWit* ctx, uint pos) {{\n"
+      "if (pos != 0){{\n"
+      "if(ctx->componentMemory[pos].subcomponents)delete []ctx->componentMemory[pos].subcomponents;\n"
+      "}}\n}}\n")
+    for t in desc.templates:
+        H = _header(t)
+        w("void %s_create(uint soffset,uint coffset,Circom_CalcWit* ctx,std::string componentName,uint componentFather){" % H)
+        w("ctx->componentMemory[coffset].templateId = %d;" % t.id)
+        w('ctx->componentMemory[coffset].templateName = "%s";' % t.name)
+        w("ctx->componentMemory[coffset].signalStart = soffset;")
+        w("ctx->componentMemory[coffset].inputCounter = %d;" % t.n_in)
+        w("ctx->componentMemory[coffset].componentName = componentName;")
+        w("ctx->componentMemory[coffset].idFather = componentFather;")
+        w("ctx->componentMemory[coffset].subcomponents = new uint[%d]{0};" % max(len(t.subs), 1))
+        if t.n_in == 0:
+            w("%s_run(coffset,ctx);" % H)
+        w("}\n")
+        w("void %s_run(uint ctx_index,Circom_CalcWit* ctx){" % H)
+        w("u64* signalValues = ctx->signalValues;")
+        w("u64 expaux[%d];" % (t.n_tmp + 1))
+        w("u64 lvar[1];")
+        w("u64 mySignalStart = ctx->componentMemory[ctx_index].signalStart;")
+        w("std::string myTemplateName = ctx->componentMemory[ctx_index].templateName;")
+        w("u64 myId = ctx_index;")
+        w("u32* mySubcomponents = ctx->componentMemory[ctx_index].subcomponents;")
+        soff, coff = t.n_own, 0
+        for i, sb in enumerate(t.subs):
+            w("{")
+            w('std::string new_cmp_name = "%s";' % sb.name.replace('"', ""))
+            w("%s_create(mySignalStart+%d,%d+ctx_index+1,ctx,new_cmp_name,myId);" % (_header(sb.tmpl), soff, coff))
+            w("mySubcomponents[%d] = %d+ctx_index+1;" % (i, coff))
+            w("}")
+            soff += sb.tmpl.total_signals
+            coff += sb.tmpl.total_components
+
+        def val(r, t=t):
+            k = r[0]
+            if k == K_OWN:
+                return "signalValues[mySignalStart + %d]" % r[2]
+            if k == K_SUB:
+                st = t.subs[r[1]].tmpl
+                if st.id in getattr(t.desc, "io_map_templates", ()):
+                    code, idx, is_array = _io_code(st, r[2])
+                    d0 = "ctx->templateInsId2IOSignalInfo[ctx->componentMemory[mySubcomponents[%d]].templateId].defs[%d]" % (r[1], code)
+                    acc = "%s.offset" % d0
+                    if is_array:
+                        acc = "%s+(%d)*%s.size" % (acc, idx, d0)
+                    return "ctx->signalValues[ctx->componentMemory[mySubcomponents[%d]].signalStart + %s]" % (r[1], acc)
+                return "ctx->signalValues[ctx->componentMemory[mySubcomponents[%d]].signalStart + %d]" % (r[1], r[2])
+            if k == K_CONST:
+                return "%dull" % t.desc.consts[r[2]]
+            if k == K_TMP:
+                return "expaux[%d]" % r[2]
+            if k == K_ONE:
+                return "signalValues[0]"
+            raise ValueError(r)
+        for op, d, a, b, c in t.ops:
+            if op == 27:
+                w('if (!Fr_isTrue(Fr_eq(%s,%s))) std::cout << "Failed assert in template/function " << myTemplateName << std::endl;' % (val(a), val(b)))
+                w("assert(Fr_isTrue(Fr_eq(%s,%s)));" % (val(a), val(b)))
+                continue
+            if op == 26:
+                w("assert(Fr_isTrue(%s));" % val(a))
+                continue
+            if op == 48:
+                w("%s = signalValues[mySignalStart + (%d + Fr_toInt(%s))];" % (val(d), a[2], val(b)))
+                continue
+            w("{")
+            if op == 24:
+                w("%s = %s;" % (val(d), val(a)))
+            elif op == 25:
+                w("if (Fr_isTrue(%s)) { %s = %s; } else { %s = %s; }" % (val(c), val(d), val(a), val(d), val(b)))
+            elif op in _FN:
+                w("%s = Fr_%s(%s,%s);" % (val(d), _FN[op], val(a), val(b)))
+            elif op in _FN1:
+                w("%s = Fr_%s(%s);" % (val(d), _FN1[op], val(a)))
+            else:
+                raise ValueError("cannot emit op %d" % op)
+            if d[0] == K_SUB:
+                st = t.subs[d[1]].tmpl
+                if st.n_out <= d[2] < st.n_out + st.n_in:
+                    w("if(!(ctx->componentMemory[mySubcomponents[%d]].inputCounter -= 1)){" % d[1])
+                    w("%s_run(mySubcomponents[%d],ctx);" % (_header(st), d[1]))
+                    w("}")
+            w("}")
+        w("for (uint i = 0; i < %d; i++){" % len(t.subs))
+        w("uint index_subc = ctx->componentMemory[ctx_index].subcomponents[i];")
+        w("if (index_subc != 0){")
+        w("assert(!(ctx->componentMemory[index_subc].inputCounter));")
+        w("release_memory_component(ctx,index_subc);")
+        w("}")
+        w("}")
+        w("}\n")
+    w("void run(Circom_CalcWit* ctx){")
+    w('%s_create(1,0,ctx,"main",0);' % _header(main))
+    if main.n_in > 0:
+        w("%s_run(0,ctx);" % _header(main))
+    w("}\n")
+    return "\n".join(out)
 
 
 def build_reference_calculator(desc, out_dir: str, name: str | None = None, opt: str = "-O3") -> str:

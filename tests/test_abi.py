@@ -150,7 +150,7 @@ def test_packed_record_layout_and_host_expansion():
     assert native.lib.cw_host_expand_isa() in (b"avx512", b"avx2", b"sse2")
 
 
-@pytest.mark.parametrize("prime", ["bn128", "bls12381"])
+@pytest.mark.parametrize("prime", ["bn128", "bls12381", "goldilocks"])
 def test_dat_equals_the_file_the_reference_runtime_loads(prime, tmp_path):
     """cw_circuit_write_dat (--O0 witness list) == the .dat the reference calculators of oracle/_ref are linked with
     (oracle/emit_ref_cpp.dat_bytes, consumed by the reference's loadCircuit, main.cpp:22-124): hash map, witness list

@@ -19,10 +19,13 @@ from circom_b200.circuit import CircuitDesc
 
 
 def wtns_frame(q: int, wit: np.ndarray) -> bytes:
+    """writeBinWitness: 32-byte elements (common/main.cpp:288-334), 8-byte ones for goldilocks (common64/main.cpp:312-353)"""
     n = wit.shape[0]
+    n8 = ((q.bit_length() + 63) // 64) * 8
+    body = wit.tobytes() if n8 == 32 else np.ascontiguousarray(wit.reshape(n, 4)[:, :n8 // 8]).tobytes()
     return (b"wtns" + (2).to_bytes(4, "little") + (2).to_bytes(4, "little") + (1).to_bytes(4, "little") +
-            (40).to_bytes(8, "little") + (32).to_bytes(4, "little") + q.to_bytes(32, "little") +
-            n.to_bytes(4, "little") + (2).to_bytes(4, "little") + (32 * n).to_bytes(8, "little") + wit.tobytes())
+            (8 + n8).to_bytes(8, "little") + n8.to_bytes(4, "little") + q.to_bytes(n8, "little") +
+            n.to_bytes(4, "little") + (2).to_bytes(4, "little") + (n8 * n).to_bytes(8, "little") + body)
 
 
 def input_json(desc, arr_row) -> dict:
@@ -66,7 +69,9 @@ def test_c_oracle_circuits_vs_python_evaluator(name):
 
 
 REF_NAMES = ["multiplier2", "all_ops", "all_ops_bls", "less_than8", "poseidon2", "int_div32", "ecdsa_scale_2x5",
-             "ecdsa_scale_8x132", "mixed_array", "table_lookup8"]
+             "ecdsa_scale_8x132", "mixed_array", "table_lookup8",
+             # the reference's goldilocks runtime (common64 + goldilocks/fr.hpp)
+             "all_ops_gl", "less_than8_gl", "mixed_array_gl"]
 
 
 @pytest.mark.parametrize("name", REF_NAMES)
@@ -95,6 +100,9 @@ def test_reference_runtime_wtns_equals_oracle(name, tmp_path):
         arr[:, :, 3] &= np.uint64(0x0FFFFFFFFFFFFFFF)
         if name.startswith("all_ops"):
             arr[:, 1, 1:] = 0   # keep b small enough that `a ** (b & 15)` etc. stay cheap
+        if d.prime == "goldilocks":   # values below q = 2^64 - 2^32 + 1
+            arr[:, :, 1:] = 0
+            arr[:, :, 0] &= np.uint64(0x7FFFFFFFFFFFFFFF)
     o = c_oracle.COracle(d.to_bytes())
     wit, st = o.run(arr)
     assert not st.any()

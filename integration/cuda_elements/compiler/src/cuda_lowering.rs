@@ -271,10 +271,10 @@ impl WriteCuda for StoreBucket {   // store_bucket.rs:607-834
             AddressType::SubcmpSignal { cmp_address, input_information, .. } => {
                 // the trigger (inputCounter, StatusInput::Last / NoLast, store_bucket.rs:660-734) is re-derived by the
                 // lowering from the order of the stores; a trigger that depends on run-time values is not expressible
-                if let InputInformation::Input { status: StatusInput::Unknown, .. } = input_information {
-                    // still fine when all stores of this component are compile-time ordered (the common case);
-                    // the lowering reports "never received all its inputs" otherwise
-                }
+                // StatusInput::Last / NoLast / Unknown (store_bucket.rs:663-734) need no distinction here: the lowering counts
+                // the stores into a component's inputs in execution order and runs it at the last one - the run-time rule of
+                // `Unknown`, of which `Last` / `NoLast` are the compiler's pre-computed cases
+                let _ = input_information;
                 let cmp = cx.address(cmp_address)?;
                 let a = cx.as_ref(&v);
                 cx.rec.ops.push(OpRec { op: Op::COPY, d: Ref::Sub { sub: cx.sub_of_cmp[cmp], idx: idx as u32 }, a, b: Ref::None, c: Ref::None });

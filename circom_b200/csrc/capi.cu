@@ -685,7 +685,9 @@ int cw_batch_run(cw_batch *b) {
     tp.n_inputs = (u32)t.n_inputs;
     tp.n_bitwords = t.n_bitwords;
     tp.prime = (u32)t.F.prime_id;
-    tp.vm_wide = env_int("CW_VM_WIDE", 0) ? 1u : 0u;
+    // the 128-bit register machine computes over the integers and gives up when a value leaves 128 bits: right only for a
+    // prime above 2^128 (every 256-bit one); goldilocks calls run on the full-width machine
+    tp.vm_wide = (env_int("CW_VM_WIDE", 0) || t.F.qbits <= 128) ? 1u : 0u;
     CU(cudaMemsetAsync(b->first_assert_d, 0xFF, (size_t)b->batch * 4, b->stream));
     CU(cudaMemsetAsync(b->err_d, 0, (size_t)b->batch * 4, b->stream));
     CU(cudaEventRecord(b->ev[0], b->stream));

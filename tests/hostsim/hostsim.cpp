@@ -260,7 +260,8 @@ int hs_run(const uint8_t *cb2c, size_t len, uint32_t flags, const uint64_t *inpu
                     int e = 0;
                     u32 ret_base, ret_cnt;
                     // as kernels.cuh exec_call: the 128-bit machine first, the full-width one when it gives up
-                    static const bool vm_wide = getenv("CW_VM_WIDE") && atoi(getenv("CW_VM_WIDE"));
+                    static const bool vm_wide_env = getenv("CW_VM_WIDE") && atoi(getenv("CW_VM_WIDE"));
+                    const bool vm_wide = vm_wide_env || t.F.qbits <= 128;   // (as capi.cu: the 128-bit machine needs a prime above 2^128)
                     const bool narrow = !vm_wide && vm_run_narrow(t.fn_code.data(), t.fn_info.data(), ct[0], regs.data(),
                                                                   (const u32 *)t.consts.data(), r, e, ret_base, ret_cnt);
                     g_narrow_calls += narrow;

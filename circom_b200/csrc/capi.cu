@@ -1444,6 +1444,46 @@ int cw_r1cs_check_batch(cw_r1cs *r, cw_batch *b, int64_t *first_bad, float *kern
     return rc;
 }
 
+int cw_circuit_assert_info(const cw_circuit *c, uint32_t assert_no, char *buf, size_t cap, size_t *len) {
+    if (!c) return fail(CW_EINVAL, "null argument");
+    const Tape &t = c->tape;
+    if (assert_no >= t.assert_tid.size()) return fail(CW_EINVAL, "no such assert (or a circuit without its description: broadcast)");
+    std::string msg = "Failed assert in template/function " + t.tmpl_names[t.assert_tid[assert_no]];
+    if (!t.sym.empty()) {
+        // the component whose signals start at assert_start: walk down from main by signal ranges (own signals first, then
+        // the sub-components in creation order - the numbering of the whole description)
+        std::string trace = "main";
+        uint32_t tid = t.sym_main;
+        uint64_t start = 1;   // (signal 0 is the constant one)
+        const uint64_t want = t.assert_start[assert_no];
+        while (start != want) {
+            const Tape::SymTemplate &st = t.sym[tid];
+            uint64_t off = start + st.n_own;
+            bool down = false;
+            for (size_t i = 0; i < st.subs.size(); ++i) {
+                const uint64_t n = t.sym[st.subs[i]].total_signals;
+                if (want >= off && want < off + n) {
+                    trace += "." + st.sub[i];
+                    tid = st.subs[i];
+                    start = off;
+                    down = true;
+                    break;
+                }
+                off += n;
+            }
+            if (!down) return fail(CW_EINVAL, "assert site outside the component tree");
+        }
+        msg += ". Followed trace of components: " + trace;
+    }
+    if (len) *len = msg.size();
+    if (buf && cap) {
+        const size_t n = std::min(msg.size(), cap - 1);
+        memcpy(buf, msg.data(), n);
+        buf[n] = 0;
+    }
+    return CW_OK;
+}
+
 int cw_r1cs_compiled_info(cw_r1cs *r, cw_batch *b, int device, uint64_t info[4]) {
     if (!r || !info) return fail(CW_EINVAL, "null argument");
     int rc = b ? CW_OK : ensure_device(device);

@@ -233,7 +233,9 @@ int main(int argc, char **argv) {
         CK(cw_batch_status(b, status.data()));
         for (size_t i = 0; i < instances.size(); ++i) {
             if (status[i] != 0) {
-                fprintf(stderr, "Failed assert (instance %zu, status %d)\n", i, status[i]);
+                char where[1024] = "";
+                if (status[i] > 0) cw_circuit_assert_info(c, (uint32_t)status[i] - 1, where, sizeof(where), nullptr);   // the reference's line
+                fprintf(stderr, "%s%sFailed assert (instance %zu, status %d)\n", where, where[0] ? "\n" : "", i, status[i]);
                 return 1;
             }
             std::string out = argv[3];

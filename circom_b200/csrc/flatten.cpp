@@ -808,6 +808,8 @@ struct Lowerer {
             }
             if (o.op == CW_OP_ASSERT_EQ || o.op == CW_OP_ASSERT) {
                 uint32_t id = (uint32_t)n_asserts++;
+                T.assert_tid.push_back(c.tid);
+                T.assert_start.push_back(c.start);
                 if (flags & CW_FLAG_NO_ASSERTS) continue;
                 if (o.op == CW_OP_ASSERT_EQ) {
                     int32_t a = load(o.a), b = load(o.b);
@@ -1869,6 +1871,7 @@ struct Lowerer {
         T.n_conv_ops = n_conv;
         T.n_asserts = n_asserts;
         T.flags = flags;
+        for (const Tmpl &t : tm) T.tmpl_names.push_back(t.name);
 
         // input hash map, laid out as the reference's .dat (c_code_generator.rs:575-603)
         uint64_t hs = 256;

@@ -87,6 +87,12 @@ struct Tape {
         std::vector<uint32_t> subs;          // template of each sub-component
         std::vector<std::string> own, sub;   // names of the own signals / of the sub-components
     };
+    // where each `===` / assert() of the description sits, in the numbering cw_batch_status reports: template instance and
+    // first signal of the component that executes it (the reference prints the template name and the component trace,
+    // c_code_generator.rs:461-468).  Not part of the lowered-circuit blob.
+    std::vector<uint32_t> assert_tid;
+    std::vector<uint64_t> assert_start;
+    std::vector<std::string> tmpl_names;
     std::vector<SymTemplate> sym;            // empty: no symbols
     // the compiler's io map (docs/CB2C.md, IOMP section), written into the `.dat` where the reference runtime looks for it
     // (c_code_generator.rs:681-735, main.cpp:57-93).  Not part of the lowered-circuit blob.

@@ -255,6 +255,15 @@ class Circuit:
         return [{"n_instr": int(info[4 * i + 1]), "n_regs": int(info[4 * i + 2]), "n_params": int(info[4 * i + 3])}
                 for i in range(n.value)]
 
+    def assert_info(self, assert_no: int) -> str:
+        """the reference's message for failed assert number `assert_no` (Batch.status() - 1): template name and, with the
+        symbols section, the trace of components (c_code_generator.rs:461-468)"""
+        n = ctypes.c_size_t()
+        check(lib.cw_circuit_assert_info(self._h, assert_no, None, 0, ctypes.byref(n)))
+        buf = ctypes.create_string_buffer(n.value + 1)
+        check(lib.cw_circuit_assert_info(self._h, assert_no, buf, n.value + 1, ctypes.byref(n)))
+        return buf.value.decode()
+
     def write_sym(self, path: str) -> None:
         """the compiler's `.sym` (`signal id,witness index or -1,node id,main.path.name` per signal); the description must
         carry the symbols section (Circuit(desc, symbols=True) / a producer that writes it)"""
@@ -493,7 +502,11 @@ class WitnessCalculator:
             i = int(bad[0])
             if st[i] < 0:
                 raise RuntimeError("Error: division by zero in instance %d" % i)
-            raise RuntimeError("Error: Assert Failed. (assert #%d, instance %d)" % (int(st[i]) - 1, i))
+            try:
+                where = " " + c.assert_info(int(st[i]) - 1)
+            except Exception:
+                where = ""
+            raise RuntimeError("Error: Assert Failed. (assert #%d, instance %d)%s" % (int(st[i]) - 1, i, where))
         return b
 
     # --- the reference surface (single input) ------------------------------------------------------

@@ -165,6 +165,12 @@ int cw_batch_set_inputs(cw_batch *b, const uint64_t *inputs, int is_device_ptr);
 /* run(ctx) (calcwit.cpp:6, generated Main_run) for the whole batch; asynchronous on the batch stream */
 int cw_batch_run(cw_batch *b);
 int cw_batch_sync(cw_batch *b);
+/* The text the reference prints for failed assert number `assert_no` (the k - 1 of cw_batch_status below):
+ * "Failed assert in template/function <template>. Followed trace of components: main.<component path>"
+ * (build_failed_assert_message, c_code_generator.rs:461-468; the description carries no line numbers, the trace needs
+ * its symbols section - without it the message ends after the template name).  Writes at most cap bytes incl. the
+ * terminator; *len = length of the whole message.  Not available on a circuit received through cw_circuit_broadcast. */
+int cw_circuit_assert_info(const cw_circuit *c, uint32_t assert_no, char *buf, size_t cap, size_t *len);
 /* per instance: 0 = ok, k>0 = first failed assert is IR assert number k-1, <0 = runtime error */
 int cw_batch_status(cw_batch *b, int32_t *status);
 /* getWitness(i) for all i and all instances, after Fr_toLongNormal (main.cpp:328-332):

@@ -317,3 +317,39 @@ def test_goldilocks_files_carry_8_byte_elements(tmp_path):
 
 def limbs_of(a):
     return [int.from_bytes(r.tobytes(), "little") for r in np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)]
+
+
+def test_failed_assert_message_names_template_and_component_trace():
+    """cw_circuit_assert_info: the reference's "Failed assert in template/function <T> ... Followed trace of components: <path>"
+    (c_code_generator.rs:461-468) for the assert number the status reports - checked against where the evaluator raises,
+    with asserts inside nested sub-components (LessThan -> Num2Bits), with and without the symbols section"""
+    from tests.util import hostsim_run
+    from oracle.ir_eval import AssertFailed
+    d = CircuitDesc("bn128")
+    lt = C.less_than(d, 4)
+
+    def build(t):
+        a = t.input("a", 2)
+        out = t.output("out")
+        c0 = t.component("lo", lt)
+        c1 = t.component("hi[1]", lt)
+        t.assign_constrained(c0["in", 0], a[0])
+        t.assign_constrained(c0["in", 1], 5)
+        t.assign_constrained(c1["in", 0], a[1])
+        t.assign_constrained(c1["in", 1], 9)
+        t.assign_constrained(out, c0["out"] + c1["out"])
+    d.set_main(d.template("Two", (), build))
+    c = Circuit(d, host_only=True, symbols=True)
+    plain = Circuit(d, host_only=True)
+    # a[1] = 100 overflows the 5-bit range check inside hi[1]'s Num2Bits: (100 + 16 - 9) needs 7 bits
+    _, st, _, _ = hostsim_run(d, [{"a": [3, 100]}, {"a": [100, 3]}, {"a": [3, 4]}])
+    assert st[2] == 0 and st[0] > 0 and st[1] > 0
+    m0, m1 = c.assert_info(int(st[0]) - 1), c.assert_info(int(st[1]) - 1)
+    assert m0 == "Failed assert in template/function Num2Bits_5. Followed trace of components: main.hi[1].n2b"
+    assert m1 == "Failed assert in template/function Num2Bits_5. Followed trace of components: main.lo.n2b"
+    assert plain.assert_info(int(st[0]) - 1) == "Failed assert in template/function Num2Bits_5"
+    for inp, name in (({"a": [3, 100]}, "Num2Bits_5"), ({"a": [100, 3]}, "Num2Bits_5")):
+        with pytest.raises(AssertFailed, match=name):
+            evaluate(d, inp)
+    with pytest.raises(Exception):
+        c.assert_info(10**6)

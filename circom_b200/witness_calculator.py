@@ -472,6 +472,11 @@ class WitnessCalculator:
     def __init__(self, circuit: Union[Circuit, CircuitDesc, bytes, str], sanity_check: bool = True, device: int = 0,
                  compact: Optional[bool] = None):
         self.circuit = circuit if isinstance(circuit, Circuit) else Circuit(circuit, sanity_check=sanity_check, compact=compact)
+        # witness_calculator.js:108-131: `init((this.sanityCheck || sanityCheck) ? 1 : 0)` - a calculator built without the
+        # `===` asserts still runs them for a call that asks for them (a second lowering of the same description, made on demand)
+        self._sanity = sanity_check
+        self._src = None if isinstance(circuit, Circuit) else (circuit, compact)
+        self._strict: Optional[Circuit] = None
         self.device = device
         self.prime = self.circuit.prime
         self.witnessSize = self.circuit.n_witness
@@ -488,12 +493,16 @@ class WitnessCalculator:
             self._batches = {n: b}  # keep one
         return b
 
-    def _run(self, inputs: Sequence[dict]) -> Batch:
+    def _run(self, inputs: Sequence[dict], sanityCheck: bool = False) -> Batch:
         c = self.circuit
+        if sanityCheck and not self._sanity and self._src is not None:
+            if self._strict is None:
+                self._strict = Circuit(self._src[0], sanity_check=True, compact=self._src[1])
+            c = self._strict
         flat: List[int] = []
         for inp in inputs:
             flat.extend(c.flatten_inputs(inp))
-        b = self._batch(len(inputs))
+        b = self._batch(len(inputs)) if c is self.circuit else Batch(c, len(inputs), self.device)
         b.set_inputs(ints_to_limbs(flat).reshape(len(inputs), c.n_inputs, 4))
         b.run()
         st = b.status()
@@ -510,16 +519,16 @@ class WitnessCalculator:
         return b
 
     # --- the reference surface (single input) ------------------------------------------------------
-    def calculateWitness(self, input: dict, sanityCheck: bool = True) -> List[int]:
-        return limbs_to_ints(self._run([input]).witness()[0])
+    def calculateWitness(self, input: dict, sanityCheck: bool = False) -> List[int]:
+        return limbs_to_ints(self._run([input], sanityCheck).witness()[0])
 
-    def calculateBinWitness(self, input: dict, sanityCheck: bool = True) -> bytes:
+    def calculateBinWitness(self, input: dict, sanityCheck: bool = False) -> bytes:
         """witnessSize x n32 32-bit words (witness_calculator.js:194-210)"""
-        w = self._run([input]).witness()[0]
+        w = self._run([input], sanityCheck).witness()[0]
         return np.ascontiguousarray(w[:, :self.n32 // 2]).tobytes()
 
-    def calculateWTNSBin(self, input: dict, sanityCheck: bool = True) -> bytes:
-        return self._run([input]).wtns_bytes(0)
+    def calculateWTNSBin(self, input: dict, sanityCheck: bool = False) -> bytes:
+        return self._run([input], sanityCheck).wtns_bytes(0)
 
     # --- batch variants -----------------------------------------------------------------------------
     def calculate_witness_batch(self, inputs: Sequence[dict]) -> np.ndarray:

@@ -43,6 +43,9 @@ OPS = {
     "SHL": 8, "SHR": 9, "LEQ": 10, "GEQ": 11, "LT": 12, "GT": 13, "EQ": 14, "NEQ": 15,
     "LOR": 16, "LAND": 17, "LNOT": 18, "BOR": 19, "BAND": 20, "BXOR": 21, "BNOT": 22,
     "NEG": 23, "COPY": 24, "SELECT": 25, "ASSERT": 26, "ASSERT_EQ": 27,
+    # one argument of a log() call (LogBucket, log_bucket.rs:104-162): a = the value (a signal, a constant) or NONE for a
+    # string, b = (NONE, string id), c = (NONE, 1) on the last argument of the call
+    "LOG": 29,
     # producer-level only (never in a .cb2c): d <- own signal array element a[toInt(b)], c = (NONE, extent) - Template.load_indexed
     "LOADSIG": 48,
     # function bodies (FunctionCodeInfo, compiler/src/circuit_design/function.rs) and their call sites
@@ -318,6 +321,22 @@ class Template:
         a = a if isinstance(a, Expr) else self.const(a)
         b = b if isinstance(b, Expr) else self.const(b)
         return Expr(self, self._emit("SELECT", a, b, cond))
+
+    def log(self, *args) -> None:
+        """`log(a, "text", b, ...)`: the reference prints the arguments separated by blanks, values as canonical decimals, and a
+        newline (log_bucket.rs:104-162).  Arguments: strings, constants, signals (own or of a sub-component); the value of a
+        logged signal is read from the witness after the run (cw_batch_log), so expressions have to be logged through the
+        signal that holds them."""
+        assert args, "log() needs an argument"
+        for k, a in enumerate(args):
+            last = (K_NONE, 0, 1 if k == len(args) - 1 else 0)
+            if isinstance(a, str):
+                assert a and all(0x20 <= ord(ch) < 0x7F and ch not in '%\\"' for ch in a), "log string: printable ASCII without % \\ \""
+                self.ops.append((OPS["LOG"], NONE_REF, NONE_REF, (K_NONE, 0, self.desc.string_id(a)), last))
+            else:
+                e = a if isinstance(a, Expr) else self.const(a)
+                assert e._ref is not None and e._ref[0] in (K_OWN, K_SUB, K_CONST, K_ONE), "log: a signal or a constant"
+                self.ops.append((OPS["LOG"], NONE_REF, e.ref, NONE_REF, last))
 
     def load_indexed(self, arr: Sequence[Expr], idx: Expr) -> Expr:
         """`arr[idx]` in a `<--` expression with a SIGNAL-dependent index - the reference compiler prints a load whose address
@@ -673,6 +692,12 @@ class CircuitDesc:
         self.main: Optional[Template] = None
         self.name = "circuit"
         self.io_map_templates: set = set()   # template ids that sit in component arrays of mixed templates (mark_mixed_array)
+        self.strings: List[str] = []          # the string table of log() (CProducer::get_string_table)
+
+    def string_id(self, text: str) -> int:
+        if text not in self.strings:
+            self.strings.append(text)
+        return self.strings.index(text)
 
     def const_id(self, v: int) -> int:
         v %= self.q
@@ -833,6 +858,12 @@ class CircuitDesc:
             for t in self.templates:
                 own, subs = self.symbol_names(t)
                 syms += b"".join(pstr(x) for x in own) + b"".join(pstr(x) for x in subs)
+        logs = b""
+        if self.strings:      # optional string table of log(): "LOGS", u32 count, count x str
+            logs = b"LOGS" + struct.pack("<I", len(self.strings))
+            for x in self.strings:
+                nb = x.encode()
+                logs += struct.pack("<I", len(nb)) + nb + b"\0" * ((-len(nb)) % 4)
         iomp = b""
         if self.io_map_templates:
             # the compiler's TemplateInstanceIOMap for the template instances that sit in component arrays of mixed
@@ -844,7 +875,7 @@ class CircuitDesc:
                 for off, lengths, size, bus in defs:
                     iomp += struct.pack("<II", off, len(lengths)) + b"".join(struct.pack("<I", x) for x in lengths)
                     iomp += struct.pack("<II", size, bus)
-        return head + consts + b"".join(blobs) + names + funcs + iomp + syms
+        return head + consts + b"".join(blobs) + names + funcs + logs + iomp + syms
 
     @staticmethod
     def io_defs(t: "Template"):

@@ -191,3 +191,31 @@ def table_lookup(d: CircuitDesc, n: int = 8) -> Template:
         t.constrain(picked, acc_p)
         t.assign_constrained(out, picked * picked)
     return d.template("TableLookup", (n,), build)
+
+
+def logging(d: CircuitDesc) -> Template:
+    """log() calls in a component tree: strings, constants, signals of the component and of a sub-component, a signal that
+    the signal merging eliminates (its value is printed through the entry it was merged into), calls in execution order
+    (the sub-component logs when its last input arrives)."""
+    def inner(t: Template):
+        x = t.input("x")
+        y = t.input("y")
+        out = t.output("out")
+        t.assign_constrained(out, x * y)
+        t.log("inner", x, y, "->", out)
+    it = d.template("Inner", (), inner)
+
+    def build(t: Template):
+        a = t.input("a")
+        b = t.input("b")
+        out = t.output("out")
+        t.log("start", a, 42)
+        c = t.component("c", it)
+        t.assign_constrained(c.sig("x"), a)
+        t.log("between the inputs of c")
+        t.assign_constrained(c.sig("y"), b + 1)
+        m = t.signal("m")
+        t.assign_constrained(m, c.sig("out"))          # m = c.out: merged away by the signal elimination
+        t.assign_constrained(out, m + a)
+        t.log(m, c.sig("out"), out, -1)
+    return d.template("Logging", (), build)

@@ -1444,6 +1444,41 @@ int cw_r1cs_check_batch(cw_r1cs *r, cw_batch *b, int64_t *first_bad, float *kern
     return rc;
 }
 
+static int copy_text(const std::string &msg, char *buf, size_t cap, size_t *len) {
+    if (len) *len = msg.size();
+    if (buf && cap) {
+        const size_t n = std::min(msg.size(), cap - 1);
+        memcpy(buf, msg.data(), n);
+        buf[n] = 0;
+    }
+    return CW_OK;
+}
+
+int cw_circuit_format_log(const cw_circuit *c, const uint64_t *witness, char *buf, size_t cap, size_t *len) {
+    if (!c || !witness) return fail(CW_EINVAL, "null argument");
+    return copy_text(format_log(c->tape, witness), buf, cap, len);
+}
+
+int cw_batch_log(cw_batch *b, uint32_t inst, char *buf, size_t cap, size_t *len) {
+    if (!b || inst >= b->batch) return fail(CW_EINVAL, "bad instance");
+    if (!b->ran) return fail(CW_ESTATE, "batch has not been run");
+    const Tape &t = b->c->tape;
+    if (t.log_args.empty()) return copy_text(std::string(), buf, cap, len);
+    CU(cudaSetDevice(b->device));
+    std::vector<uint64_t> w((size_t)t.n_witness * 4);
+    uint4 *row = nullptr;
+    CU(cudaMalloc((void **)&row, (size_t)t.n_witness * 32));
+    int rc = expand_rows(b, inst, 1, row);       // (the dense row of one instance, as the .wtns writer fetches it)
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(w.data(), row, (size_t)t.n_witness * 32, cudaMemcpyDeviceToHost, b->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(b->stream);
+        if (e != cudaSuccess) rc = fail(CW_ECUDA, cudaGetErrorString(e));
+    }
+    cudaFree(row);
+    if (rc) return rc;
+    return copy_text(format_log(t, w.data()), buf, cap, len);
+}
+
 int cw_circuit_assert_info(const cw_circuit *c, uint32_t assert_no, char *buf, size_t cap, size_t *len) {
     if (!c) return fail(CW_EINVAL, "null argument");
     const Tape &t = c->tape;

@@ -381,6 +381,9 @@ struct Lowerer {
     std::unordered_map<std::string, uint32_t> const_index;
     uint32_t n_pre = 0;
     uint64_t n_ir_ops = 0, n_conv = 0, n_asserts = 0, n_static_asserts = 0;
+    int64_t max_log_string = -1;
+    struct PendingLog { uint8_t kind; bool last; uint64_t idx; };   // kind 1: idx = global signal id until the witness exists
+    std::vector<PendingLog> pending_logs;
     int32_t vid_one = -1;
 
     Lowerer(Tape &t, uint32_t fl) : T(t), F(t.F), flags(fl) {}
@@ -806,6 +809,19 @@ struct Lowerer {
                 }
                 continue;
             }
+            if (o.op == 29 /* LOG: nothing to execute - the argument is looked up in the witness afterwards */) {
+                PendingLog pl;
+                pl.last = ridx(o.c) != 0;
+                switch (rk(o.a)) {
+                    case K_NONE: pl.kind = 0; pl.idx = ridx(o.b); break;
+                    case K_OWN: pl.kind = 1; pl.idx = c.start + ridx(o.a); break;
+                    case K_SUB: pl.kind = 1; pl.idx = subs[rsub(o.a)].start + ridx(o.a); break;
+                    case K_ONE: pl.kind = 1; pl.idx = 0; break;
+                    default: pl.kind = 2; pl.idx = ridx(o.a); break;   // K_CONST
+                }
+                pending_logs.push_back(pl);
+                continue;
+            }
             if (o.op == CW_OP_ASSERT_EQ || o.op == CW_OP_ASSERT) {
                 uint32_t id = (uint32_t)n_asserts++;
                 T.assert_tid.push_back(c.tid);
@@ -1062,6 +1078,12 @@ struct Lowerer {
                     check_ref(o.d, false, true);
                     if (rk(o.c) == K_NONE && ridx(o.c) > 1 && (ridx(o.c) > 64 || (uint64_t)ridx(o.d) + ridx(o.c) > t.n_tmp))
                         throw std::runtime_error("cb2c: bad result count of a call in template " + t.name);
+                } else if (o.op == 29 /* LOG */) {
+                    const int k = rk(o.a);
+                    if (k == K_TMP || rk(o.d) != K_NONE || rk(o.b) != K_NONE || rk(o.c) != K_NONE || ridx(o.c) > 1)
+                        throw std::runtime_error("cb2c: bad log argument in template " + t.name + " (a signal, a constant or a string)");
+                    check_ref(o.a, true, false);
+                    if (k == K_NONE) max_log_string = std::max<int64_t>(max_log_string, (int64_t)ridx(o.b));
                 } else {
                     if (o.op < CW_OP_MUL || o.op > CW_OP_INV) throw std::runtime_error("cb2c: unknown opcode in template " + t.name);
                     const bool is_assert = o.op == CW_OP_ASSERT || o.op == CW_OP_ASSERT_EQ;
@@ -1255,6 +1277,21 @@ struct Lowerer {
         // signals with offset, dimensions, element size, bus id).  The reference's generated code resolves `Mapped`
         // locations through it at run time (load_bucket.rs:264-322); here a producer has resolved them already, the map is
         // carried for the `.dat` only (c_code_generator.rs:681-735).
+        // optional string table of log(): "LOGS", u32 count, count x str (printable ASCII without % \ ": the reference pastes the
+        // text into a printf format, log_bucket.rs:128-137)
+        if (r.left() >= 4 && !memcmp(r.p, "LOGS", 4)) {
+            r.bytes(4);
+            const uint32_t n_s = r.get<uint32_t>();
+            r.expect(n_s, 4);
+            for (uint32_t i = 0; i < n_s; ++i) {
+                std::string x = r.str();
+                if (x.empty() || x.size() > 4096) throw std::runtime_error("cb2c: bad log string");
+                for (unsigned char ch : x)
+                    if (ch < 0x20 || ch >= 0x7F || ch == '%' || ch == '\\' || ch == '"') throw std::runtime_error("cb2c: bad character in a log string");
+                T.log_strings.push_back(std::move(x));
+            }
+        }
+        if (max_log_string >= (int64_t)T.log_strings.size()) throw std::runtime_error("cb2c: log() names a string the file does not carry");
         if (r.left() >= 4 && !memcmp(r.p, "IOMP", 4)) {
             r.bytes(4);
             const uint32_t n_e = r.get<uint32_t>();
@@ -1364,6 +1401,33 @@ struct Lowerer {
         // value, or a value only held in another representation, costs one move / conversion op.
         for (uint64_t i = 0; i < S; ++i)
             if (sig_vid[i] < 0) throw std::runtime_error("lowering: signal " + std::to_string(i) + " is never assigned");
+        if (!pending_logs.empty()) {   // logged signals -> the witness entries that hold their values
+            std::unordered_map<int32_t, uint32_t> entry_of_value;
+            for (uint64_t i = 0; i < W; ++i) entry_of_value.emplace(sig_vid[T.witness2signal[i]], (uint32_t)i);
+            std::unordered_map<std::string, uint32_t> const_at;
+            auto log_const = [&](const U256 &v) {
+                std::string key((const char *)v.v, 32);
+                auto it = const_at.find(key);
+                if (it != const_at.end()) return it->second;
+                T.log_consts.push_back(v);
+                return const_at.emplace(std::move(key), (uint32_t)T.log_consts.size() - 1).first->second;
+            };
+            for (const PendingLog &pl : pending_logs) {
+                Tape::LogArg a;
+                a.kind = pl.kind;
+                a.last = pl.last ? 1 : 0;
+                a.idx = (uint32_t)pl.idx;
+                if (pl.kind == 2) a.idx = log_const(ir_consts[pl.idx]);
+                if (pl.kind == 1) {
+                    const int32_t v = sig_vid[pl.idx];
+                    auto it = entry_of_value.find(v);
+                    if (it != entry_of_value.end()) a.idx = it->second;
+                    else if (vals[v].cid >= 0) { a.kind = 2; a.idx = log_const(ir_consts[vals[v].cid]); }
+                    else throw std::runtime_error("lowering: log() of a signal whose value is not part of the witness");
+                }
+                T.log_args.push_back(a);
+            }
+        }
         std::vector<int64_t> claimed;  // provisional slot -> witness index
         std::vector<uint32_t> wsrc(W);
         auto grow = [&]() { claimed.resize(n_pre + pops.size() / 4, -1); };

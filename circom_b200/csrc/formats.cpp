@@ -420,3 +420,39 @@ void write_sym(const Tape &t, const std::string &path) {
 }
 
 }  // namespace cw
+
+namespace cw {
+// decimal of a canonical 256-bit value, as Fr_element2str prints it (generic/fr.cpp:2836-2856: mpz_get_str base 10)
+static std::string u256_decimal(const uint64_t *v) {
+    uint32_t limb[8];
+    for (int i = 0; i < 4; ++i) { limb[2 * i] = (uint32_t)v[i]; limb[2 * i + 1] = (uint32_t)(v[i] >> 32); }
+    std::string out;
+    for (;;) {
+        uint64_t rem = 0;
+        bool any = false;
+        for (int i = 7; i >= 0; --i) {
+            uint64_t cur = (rem << 32) | limb[i];
+            limb[i] = (uint32_t)(cur / 1000000000u);
+            rem = cur % 1000000000u;
+            any |= limb[i] != 0;
+        }
+        char buf[16];
+        snprintf(buf, sizeof(buf), any ? "%09u" : "%u", (unsigned)rem);
+        out.insert(0, buf);
+        if (!any) break;
+    }
+    return out;
+}
+
+// LogBucket (log_bucket.rs:104-162): the arguments of a call separated by one blank, values as decimals, a newline after the last
+std::string format_log(const Tape &t, const uint64_t *witness) {
+    std::string out;
+    for (const Tape::LogArg &a : t.log_args) {
+        if (a.kind == 0) out += t.log_strings[a.idx];
+        else if (a.kind == 1) out += u256_decimal(witness + 4 * (size_t)a.idx);
+        else out += u256_decimal(t.log_consts[a.idx].v);
+        out += a.last ? "\n" : " ";
+    }
+    return out;
+}
+}  // namespace cw

@@ -90,6 +90,16 @@ struct Tape {
     // where each `===` / assert() of the description sits, in the numbering cw_batch_status reports: template instance and
     // first signal of the component that executes it (the reference prints the template name and the component trace,
     // c_code_generator.rs:461-468).  Not part of the lowered-circuit blob.
+    // log() calls in execution order (LogBucket, log_bucket.rs:104-162): one record per argument - a string, a constant, or the
+    // witness entry that holds the logged signal's value (an eliminated signal is read through the entry it was merged into)
+    struct LogArg {
+        uint8_t kind = 0;     // 0 string (idx into log_strings), 1 witness entry idx, 2 constant (idx into log_consts)
+        uint8_t last = 0;     // last argument of its log() call: a newline follows
+        uint32_t idx = 0;
+    };
+    std::vector<LogArg> log_args;
+    std::vector<std::string> log_strings;
+    std::vector<U256> log_consts;
     std::vector<uint32_t> assert_tid;
     std::vector<uint64_t> assert_start;
     std::vector<std::string> tmpl_names;
@@ -153,5 +163,7 @@ void read_wtns(const std::string &path, int &prime_id, std::vector<uint64_t> &wi
 // .sym (constraint_writers/src/sym_writer.rs:4-38, dag/src/sym_porting.rs:16-33): one line per signal,
 // `signal id,witness index or -1,node id,qualified name`.  Throws when the circuit carries no symbols.
 void write_sym(const Tape &t, const std::string &path);
+// the text the log() calls of the circuit print for one witness (n_witness x 4 u64), as the reference calculator prints it
+std::string format_log(const Tape &t, const uint64_t *witness);
 
 }  // namespace cw

@@ -112,6 +112,8 @@ def _load() -> ctypes.CDLL:
         "cw_r1cs_info": (c_int, [P, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint64), POINTER(c_int)]),
         "cw_r1cs_compiled_info": (c_int, [P, P, c_int, POINTER(c_uint64)]),
         "cw_circuit_assert_info": (c_int, [P, c_uint32, c_char_p, c_size_t, POINTER(c_size_t)]),
+        "cw_circuit_format_log": (c_int, [P, c_void_p, c_char_p, c_size_t, POINTER(c_size_t)]),
+        "cw_batch_log": (c_int, [P, c_uint32, c_char_p, c_size_t, POINTER(c_size_t)]),
         "cw_r1cs_destroy": (None, [P]),
         "cw_r1cs_check": (c_int, [P, c_void_p, c_int, c_uint32, c_int, c_void_p, POINTER(c_float)]),
         "cw_r1cs_check_strided": (c_int, [P, c_void_p, c_uint64, c_int, c_uint32, c_int, c_void_p, POINTER(c_float)]),

@@ -255,6 +255,16 @@ class Circuit:
         return [{"n_instr": int(info[4 * i + 1]), "n_regs": int(info[4 * i + 2]), "n_params": int(info[4 * i + 3])}
                 for i in range(n.value)]
 
+    def format_log(self, witness) -> str:
+        """what the circuit's log() calls print for one witness ([n_witness][4] uint64), as the reference calculator prints it"""
+        w = np.ascontiguousarray(witness, dtype=np.uint64)
+        assert w.size == self.n_witness * 4
+        n = ctypes.c_size_t()
+        check(lib.cw_circuit_format_log(self._h, w.ctypes.data, None, 0, ctypes.byref(n)))
+        buf = ctypes.create_string_buffer(n.value + 1)
+        check(lib.cw_circuit_format_log(self._h, w.ctypes.data, buf, n.value + 1, ctypes.byref(n)))
+        return buf.value.decode()
+
     def assert_info(self, assert_no: int) -> str:
         """the reference's message for failed assert number `assert_no` (Batch.status() - 1): template name and, with the
         symbols section, the trace of components (c_code_generator.rs:461-468)"""
@@ -402,6 +412,14 @@ class Batch:
         buf = (ctypes.c_uint8 * n.value)()
         check(lib.cw_batch_wtns_bytes(self._h, instance, buf, n.value, ctypes.byref(n)))
         return bytes(buf)
+
+    def log(self, instance: int) -> str:
+        """what the circuit's log() calls print for this instance (cw_batch_log)"""
+        n = ctypes.c_size_t()
+        check(lib.cw_batch_log(self._h, instance, None, 0, ctypes.byref(n)))
+        buf = ctypes.create_string_buffer(n.value + 1)
+        check(lib.cw_batch_log(self._h, instance, buf, n.value + 1, ctypes.byref(n)))
+        return buf.value.decode()
 
     def write_wtns(self, instance: int, path: str) -> None:
         check(lib.cw_batch_write_wtns(self._h, instance, path.encode()))

@@ -171,6 +171,13 @@ int cw_batch_sync(cw_batch *b);
  * its symbols section - without it the message ends after the template name).  Writes at most cap bytes incl. the
  * terminator; *len = length of the whole message.  Not available on a circuit received through cw_circuit_broadcast. */
 int cw_circuit_assert_info(const cw_circuit *c, uint32_t assert_no, char *buf, size_t cap, size_t *len);
+/* What the log() calls of the circuit print for one witness (LogBucket, log_bucket.rs:104-162: the arguments of a call
+ * separated by blanks, values as canonical decimals, a newline per call; calls in the reference's execution order).
+ * witness = n_witness x 4 u64 in host memory.  Writes at most cap bytes incl. the terminator; *len = length of the whole text.
+ * Arguments are strings, constants and signals (a producer logs an expression through the signal that holds it). */
+int cw_circuit_format_log(const cw_circuit *c, const uint64_t *witness, char *buf, size_t cap, size_t *len);
+/* the same for instance `inst` of a batch that has run (its witness row is fetched from the device) */
+int cw_batch_log(cw_batch *b, uint32_t inst, char *buf, size_t cap, size_t *len);
 /* per instance: 0 = ok, k>0 = first failed assert is IR assert number k-1, <0 = runtime error */
 int cw_batch_status(cw_batch *b, int32_t *status);
 /* getWitness(i) for all i and all instances, after Fr_toLongNormal (main.cpp:328-332):

@@ -25,6 +25,7 @@ pub struct CUDAProducer {
     pub function_ids: HashMap<String, u32>, // function header -> index in Cb2cFile::functions (Circuit::functions order)
     pub io_map: TemplateInstanceIOMap,      // as CProducer::io_map (c_elements/mod.rs:24): resolves LocationRule::Mapped now, travels to the .dat
     pub busid_field_info: FieldMap,         // as CProducer::busid_field_info: the fields of each bus (flattened by the producer)
+    pub string_table: Vec<String>,          // as CProducer::get_string_table(): the literals of log()
 }
 
 impl CUDAProducer {
@@ -75,7 +76,7 @@ impl Ref {
 #[repr(u64)]
 pub enum Op {
     MUL = 1, DIV, ADD, SUB, POW, IDIV, MOD, SHL, SHR, LEQ, GEQ, LT, GT, EQ, NEQ, LOR, LAND, LNOT, BOR, BAND, BXOR, BNOT,
-    NEG = 23, COPY = 24, SELECT = 25, ASSERT = 26, ASSERT_EQ = 27, INV = 28,
+    NEG = 23, COPY = 24, SELECT = 25, ASSERT = 26, ASSERT_EQ = 27, INV = 28, LOG = 29,
     JMP = 40, JZ = 41, RET = 42, LOADX = 43, STOREX = 44, CALL = 45, ARG = 46,
 }
 
@@ -108,9 +109,15 @@ pub struct Cb2cFile {
     pub names: Vec<(String, u32, u32)>,                   // (qualified name, global signal id, size)
     pub functions: Vec<FunctionRecord>,
     pub io_map: TemplateInstanceIOMap,                    // copied from the producer by produce_cb2c: the IOMP section
+    pub strings: Vec<String>,                             // the strings log() uses: the LOGS section
 }
 
 impl Cb2cFile {
+    pub fn string_id(&mut self, text: &str) -> u32 {
+        if let Some(p) = self.strings.iter().position(|s| s == text) { return p as u32; }
+        self.strings.push(text.to_string());
+        (self.strings.len() - 1) as u32
+    }
     pub fn const_id(&mut self, v: &BigInt, q: &BigInt) -> u32 {
         let mut n = v % q;
         if n < BigInt::from(0) { n += q; }
@@ -167,6 +174,11 @@ impl Cb2cFile {
             Self::w_str(w, &f.name)?;
             for v in [f.n_params, f.n_regs, f.code.len() as u32] { Self::w_u32(w, v)?; }
             Self::w_ops(w, &f.code)?;
+        }
+        if !self.strings.is_empty() {                              // optional string table of log()
+            w.write_all(b"LOGS").map_err(|_| {})?;
+            Self::w_u32(w, self.strings.len() as u32)?;
+            for s in &self.strings { Self::w_str(w, s)?; }
         }
         // optional io-map section (docs/CB2C.md): what generate_dat_io_signals_info puts into the .dat, handed to the library
         if !self.io_map.is_empty() {

@@ -195,7 +195,7 @@ impl WriteCuda for Instruction {
             Value(v) => v.produce_cuda(cx), Load(v) => v.produce_cuda(cx), Store(v) => v.produce_cuda(cx),
             Compute(v) => v.produce_cuda(cx), Call(v) => v.produce_cuda(cx), Branch(v) => v.produce_cuda(cx),
             Return(_) => Err(()),                 // only inside functions (FunctionCtx below)
-            Assert(v) => v.produce_cuda(cx), Log(_) => Ok(None), // log(): no effect on the witness (log_bucket.rs:105-135)
+            Assert(v) => v.produce_cuda(cx), Log(v) => v.produce_cuda(cx),
             Loop(v) => v.produce_cuda(cx), CreateCmp(v) => v.produce_cuda(cx),
         }
     }
@@ -278,6 +278,32 @@ impl WriteCuda for StoreBucket {   // store_bucket.rs:607-834
                 let cmp = cx.address(cmp_address)?;
                 let a = cx.as_ref(&v);
                 cx.rec.ops.push(OpRec { op: Op::COPY, d: Ref::Sub { sub: cx.sub_of_cmp[cmp], idx: idx as u32 }, a, b: Ref::None, c: Ref::None });
+            }
+        }
+        Ok(None)
+    }
+}
+
+impl WriteCuda for LogBucket {     // log_bucket.rs:104-162: one LOG op per argument; the library prints from the witness afterwards
+    fn produce_cuda(&self, cx: &mut TemplateCtx) -> Result<Option<Val>, ()> {
+        let n = self.argsprint.len();
+        for (k, arg) in self.argsprint.iter().enumerate() {
+            let last = Ref::Imm(if k + 1 == n { 1 } else { 0 });
+            match arg {
+                LogBucketArg::LogStr(id) => {
+                    let text = cx.producer.string_table[*id].clone();
+                    if text.is_empty() || text.bytes().any(|b| b < 0x20 || b >= 0x7f || b == b'%' || b == b'\\' || b == b'"') { return Err(()); }
+                    let sid = cx.file.string_id(&text);
+                    cx.rec.ops.push(OpRec { op: Op::LOG, d: Ref::None, a: Ref::None, b: Ref::Imm(sid), c: last });
+                }
+                LogBucketArg::LogExp(e) => {
+                    let a = match e.produce_cuda(cx)?.ok_or(())? {
+                        Val::Known(k) => { let q = cx.q.clone(); Ref::Const(cx.file.const_id(&k, &q)) }
+                        Val::Dynamic(r @ (Ref::Own(_) | Ref::Sub { .. } | Ref::One)) => r,
+                        Val::Dynamic(_) => return Err(()),   // an expression no signal holds: not printable from the witness
+                    };
+                    cx.rec.ops.push(OpRec { op: Op::LOG, d: Ref::None, a, b: Ref::None, c: last });
+                }
             }
         }
         Ok(None)

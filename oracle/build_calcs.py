@@ -30,6 +30,8 @@ def circuits():
         "mixed_array": ("bn128", lambda d: C.mixed_array(d)),
         # `out <-- table[sel]`: the calculator loads at a run-time address, the description carries the expansion
         "table_lookup8": ("bn128", lambda d: C.table_lookup(d, 8)),
+        # log() calls: the calculator prints them (stdout is part of the comparison)
+        "logging": ("bn128", lambda d: C.logging(d)),
         "poseidon2": ("bn128", lambda d: C.poseidon(d, 2)),
         "int_div32": ("bn128", lambda d: C.int_div(d, 32)),
         "int_div_arr32": ("bn128", lambda d: C.int_div_array(d, 32, "all")),     # `var qr[3] = f(a, b);`: one call, three results

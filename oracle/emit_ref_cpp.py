@@ -245,6 +245,13 @@ def _emit_template(w, t) -> None:
         if op == 26:  # ASSERT
             w("assert(Fr_isTrue(%s));" % addr(a))
             continue
+        if op == 29:  # LOG: LogBucket::produce_c (log_bucket.rs:104-162)
+            if a[0] == 0:
+                w('{ printf("%s"); }' % t.desc.strings[b[2]])
+            else:
+                w("{ char* temp = Fr_element2str(%s); printf(\"%%s\",temp); delete [] temp; }" % addr(a))
+            w('{ printf("%s"); }' % ("\\n" if c[2] else " "))
+            continue
         if op == 48:  # LOADSIG: a load whose Indexed location is computed at run time (load_bucket.rs:325-447 with
             #           ComputeBucket ToAddress = Fr_toInt, compute_bucket.rs:361-363)
             w("{")

@@ -21,6 +21,9 @@ from .field_model import Field, OPS
 K_NONE, K_OWN, K_SUB, K_CONST, K_TMP, K_ONE = 0, 1, 2, 3, 4, 5
 
 
+LOG_SINK: list = []   # what the log() calls of the last evaluate() printed (cleared by the caller)
+
+
 class AssertFailed(Exception):
     pass
 
@@ -150,6 +153,13 @@ def evaluate(desc, inputs: Dict[str, Sequence[int]], check_asserts: bool = True)
             if op == OPS["ASSERT"]:
                 if check_asserts and load(a) == 0:
                     raise AssertFailed(t.name)
+                continue
+            if op == 29:   # LOG: one argument of a log() call (log_bucket.rs:104-162)
+                if a[0] == 0:
+                    text = desc.strings[b[2]]
+                else:
+                    text = str(load(a))
+                LOG_SINK.append(text + ("\n" if cc[2] else " "))
                 continue
             if op == 48:   # LOADSIG (producer level, circuit.py: Template.load_indexed): own signal array a[toInt(b)], extent cc
                 iv = load(b)

@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 from oracle import build_calcs  # noqa: E402
 
 NAMES = ["multiplier2", "all_ops", "all_ops_bls", "less_than8", "poseidon2", "int_div32", "int_div_arr32", "ecdsa_scale_2x5",
-         "ecdsa_calls_2x5", "gcd32", "mixed_array", "table_lookup8",
+         "ecdsa_calls_2x5", "gcd32", "mixed_array", "table_lookup8", "logging",
          "all_ops_gl", "less_than8_gl", "mixed_array_gl",   # goldilocks: the reference's common64 runtime, 8-byte elements
          "sha256compression", "sha256_64_bls",   # the two SHA calculators take ~11 min of g++ each
          "ecdsa_scale_8x132"]                    # the bench circuit (1.2 M constraints): one case, 38 MB -> 1 MB
@@ -57,6 +57,8 @@ def gen_inputs(name: str, d, rng: random.Random):
     if name == "mixed_array":   # the reference calculator reads these sub-component signals through the io map of its .dat
         return [{"a": ["3", "4", "5"], "b": "7"}, {"a": ["0", "0", "0"], "b": str(q - 1)}] + \
                [{"a": [str(rng.randrange(q)) for _ in range(3)], "b": str(rng.randrange(q))} for _ in range(3)]
+    if name == "logging":
+        return [{"a": "3", "b": "5"}, {"a": str(q - 1), "b": str(q - 2)}, {"a": str(rng.randrange(q)), "b": str(rng.randrange(q))}]
     if name == "table_lookup8":   # `<-- table[sel]`: every position, small and field-sized entries
         return [{"table": [str(rng.randrange(q)) for _ in range(8)], "sel": str(k)} for k in range(8)] + \
                [{"table": [str(i) for i in range(8)], "sel": "5"}]

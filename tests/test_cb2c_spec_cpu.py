@@ -154,7 +154,7 @@ def test_rust_producer_numbers_match_the_format():
     kinds = re.search(r"let \(k, s, i\).*?match self \{(.*?)\};", src, re.S).group(1)
     for variant, k in (("None", 0), ("Own", 1), ("Sub", 2), ("Const", 3), ("Tmp", 4), ("One", 5)):
         assert re.search(r"Ref::%s\b[^=]*=> \(%d," % (variant, k), kinds), variant
-    assert src.index('b"CB2C"') < src.index('b"IOMP"') < src.index('b"SYMS"')
+    assert src.index('b"CB2C"') < src.index('b"LOGS"') < src.index('b"IOMP"') < src.index('b"SYMS"') and ops["LOG"] == 29
     head = re.search(r"for v in \[1u32, self\.prime, (.*?)\]", src, re.S).group(1)
     assert [w.strip().split(".")[1].split(" ")[0] for w in head.split(",")][:3] == ["consts", "templates", "main"]
     low = open(os.path.join(root, "compiler", "src", "cuda_lowering.rs")).read()

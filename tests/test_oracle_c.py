@@ -69,7 +69,7 @@ def test_c_oracle_circuits_vs_python_evaluator(name):
 
 
 REF_NAMES = ["multiplier2", "all_ops", "all_ops_bls", "less_than8", "poseidon2", "int_div32", "ecdsa_scale_2x5",
-             "ecdsa_scale_8x132", "mixed_array", "table_lookup8",
+             "ecdsa_scale_8x132", "mixed_array", "table_lookup8", "logging",
              # the reference's goldilocks runtime (common64 + goldilocks/fr.hpp)
              "all_ops_gl", "less_than8_gl", "mixed_array_gl"]
 
@@ -113,3 +113,13 @@ def test_reference_runtime_wtns_equals_oracle(name, tmp_path):
         r = subprocess.run([calc, jp, wp], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[-400:]
         assert open(wp, "rb").read() == wtns_frame(d.q, wit[i])
+        if d.strings:   # log() calls: what the calculator printed = cw_circuit_format_log of the witness, = the evaluator's text
+            from circom_b200.witness_calculator import Circuit
+            from oracle import ir_eval
+            for o0 in (True, False):
+                c = Circuit(d, host_only=True, o0=o0)
+                w2s = c.witness2signal().astype(np.int64)
+                assert c.format_log(wit[i][w2s]) == r.stdout
+            ir_eval.LOG_SINK.clear()
+            evaluate(d, {k: (int(v) if not isinstance(v, list) else [int(x) for x in v]) for k, v in input_json(d, arr[i]).items()})
+            assert "".join(ir_eval.LOG_SINK) == r.stdout and r.stdout.count("\n") == 4

@@ -341,6 +341,33 @@ def test_hostile_io_map_section():
         assert try_load(plain + bad) == native.CW_EFORMAT, bad[:24]
 
 
+def test_hostile_log_ops_and_string_table():
+    """log(): the strings are pasted into a printf format by the reference and printed verbatim here - no control characters,
+    %, backslash or quote; a LOG op names a string of the table, a signal or a constant, never a temporary"""
+    d = CircuitDesc("bn128")
+    d.set_main(C.logging(d))
+    good = d.to_bytes()
+    at = good.index(b"LOGS")
+    plain, sec = good[:at], good[at:]
+    assert try_load(good) == 0
+    assert try_load(plain) == native.CW_EFORMAT                                   # LOG ops without their strings
+    n = struct.unpack_from("<I", sec, 4)[0]
+    first = struct.unpack_from("<I", sec, 8)[0]
+    assert sec[12:12 + first] == b"inner"
+    for bad in (b"in%er", b"in\\er", b'in"er', b"in\ner", b"in\x7fer"):
+        assert try_load(plain + sec[:12] + bad + sec[17:]) == native.CW_EFORMAT, bad
+    assert try_load(plain + b"LOGS" + struct.pack("<I", n - 1) + sec[8:]) == native.CW_EFORMAT      # one string short (and bytes left over)
+    assert try_load(plain + b"LOGS" + struct.pack("<I", 0xFFFFFFFF)) == native.CW_EFORMAT
+    assert try_load(plain + b"LOGS" + struct.pack("<II", 1, 0)) == native.CW_EFORMAT                # empty string
+    # a LOG op on a temporary: patch the kind of the first LOG argument that names a signal
+    blob = bytearray(good)
+    op = struct.pack("<Q", 29)
+    pos = [i for i in range(0, len(blob) - 40, 4) if blob[i:i + 8] == op and blob[i + 8:i + 16] == bytes(8) and blob[i + 23] in (1, 2)]
+    assert pos
+    blob[pos[0] + 23] = 4                                                                            # K_TMP
+    assert try_load(bytes(blob)) == native.CW_EFORMAT
+
+
 def test_set_input_outside_main_inputs_is_refused():
     """cw_batch_set_input indexes host arrays with (signal id - first input): a hash-map entry pointing elsewhere must
     not be followed (defence in depth behind the parser's check) - exercised through the Python twin of the lookup"""

@@ -238,6 +238,13 @@ int main(int argc, char **argv) {
                 fprintf(stderr, "%s%sFailed assert (instance %zu, status %d)\n", where, where[0] ? "\n" : "", i, status[i]);
                 return 1;
             }
+            {   // what the circuit's log() calls print goes to stdout, as the reference binary prints it (log_bucket.rs:104-162)
+                size_t n = 0;
+                if (cw_batch_log(b, (uint32_t)i, nullptr, 0, &n) == 0 && n) {
+                    std::string text(n + 1, '\0');
+                    if (cw_batch_log(b, (uint32_t)i, &text[0], n + 1, &n) == 0) fwrite(text.data(), 1, n, stdout);
+                }
+            }
             std::string out = argv[3];
             if (is_batch) out += "." + std::to_string(i) + ".wtns";
             CK(cw_batch_write_wtns(b, (uint32_t)i, out.c_str()));

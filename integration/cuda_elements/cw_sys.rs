@@ -30,6 +30,9 @@ extern "C" {
     pub fn cw_batch_get_witness_async(b: *mut cw_batch, out: *mut u64) -> c_int;
     pub fn cw_batch_get_witness_wait(b: *mut cw_batch) -> c_int;
     pub fn cw_batch_write_wtns(b: *mut cw_batch, instance: u32, path: *const c_char) -> c_int;
+    /// what the circuit's log() calls print for an instance (LogBucket), and the reference's failed-assert message
+    pub fn cw_batch_log(b: *mut cw_batch, instance: u32, buf: *mut c_char, cap: usize, len: *mut usize) -> c_int;
+    pub fn cw_circuit_assert_info(c: *const cw_circuit, assert_no: u32, buf: *mut c_char, cap: usize, len: *mut usize) -> c_int;
     pub fn cw_batch_stream(b: *mut cw_batch) -> *mut c_void;   // cudaStream_t
     pub fn cw_r1cs_from_circuit(c: *const cw_circuit, out: *mut *mut cw_r1cs) -> c_int;
     pub fn cw_r1cs_check_batch(r: *mut cw_r1cs, b: *mut cw_batch, first_bad: *mut i64, kernel_ms: *mut c_float) -> c_int;
@@ -59,7 +62,7 @@ pub fn calculate_witness_batch(cb2c: &std::ffi::CStr, inputs: &[u64], batch: u32
         cw_batch_destroy(b);
         cw_circuit_destroy(c);
         if rc != 0 { return Err(err()); }
-        if let Some(i) = st.iter().position(|s| *s != 0) { return Err(format!("instance {}: status {}", i, st[i])); }
+        if let Some(i) = st.iter().position(|s| *s != 0) { return Err(format!("instance {}: status {}", i, st[i])); }   // (cw_circuit_assert_info(c, st[i] - 1, ..) before the destroy calls gives the reference's message)
         Ok(out)
     }
 }

@@ -7,7 +7,7 @@
  *         component m = Multiplier2(); m.a <== x; m.b <== y; p <== m.c + 1; }
  *
  * tests/test_cb2c_spec_cpu.py checks that the bytes equal what the DSL writes for the same circuit and that the file
- * loads, lowers and computes the expected witness.   usage: cb2c_conf out.cb2c [sym|iomap|iomap+sym]   (sym: with the symbols
+ * loads, lowers and computes the expected witness.   usage: cb2c_conf out.cb2c [sym|iomap|iomap+sym|log|log+iomap+sym]   (sym: with the symbols
  * section; iomap: with the io-map section, as if both templates sat in a component array of mixed templates) */
 #include <stdint.h>
 #include <stdio.h>
@@ -52,7 +52,8 @@ int main(int argc, char **argv) {
 
     /* ---- template 1: Conf (signals: bits[0]=0 bits[1]=1 p=2 | x=3 y=4; sub 0 = Multiplier2) ---- */
     str("Conf");
-    u32(3); u32(2); u32(0); u32(1); u32(12); u32(20); u32(6); u32(16);
+    const int with_log = argc > 2 && strstr(argv[2], "log") != NULL;   /* ... and `log("p =", p);` at the end of Conf */
+    u32(3); u32(2); u32(0); u32(1); u32(12); u32(with_log ? 22 : 20); u32(6); u32(16);
     u32(0); /* subs */
     for (int k = 0; k < 2; ++k) {
         uint32_t t0 = k ? 5 : 0, t1 = k ? 6 : 1, t2 = k ? 7 : 2, t3 = k ? 8 : 3, t4 = k ? 9 : 4;
@@ -70,6 +71,10 @@ int main(int argc, char **argv) {
     op(COPY, ref(SUB, 0, 2), ref(OWN, 0, 4), 0, 0);   /* m.b <== y : the last input, Multiplier2 runs here */
     op(ADD, ref(TMP, 0, 11), ref(SUB, 0, 0), ref(CONST, 0, C1), 0);
     op(COPY, ref(OWN, 0, 2), ref(TMP, 0, 11), 0, 0);
+    if (with_log) {   /* one LOG op per argument: a string (b = string id), then the signal p with c = 1: last argument */
+        op(29, 0, 0, ref(NONE, 0, 0), ref(NONE, 0, 0));
+        op(29, 0, ref(OWN, 0, 2), 0, ref(NONE, 0, 1));
+    }
     /* constraints; terms in ascending reference order */
     for (int k = 0; k < 2; ++k) { /* bits[k] * (bits[k] - 1) = 0 */
         u64(1); term(ref(OWN, 0, k), C1);
@@ -85,6 +90,11 @@ int main(int argc, char **argv) {
     str("x"); u32(4); u32(1);
     str("y"); u32(5); u32(1);
     /* ---- no functions; optional symbols section: per template the own signals in numbering order, then the sub-components ---- */
+    if (with_log) {   /* optional string table of log(): before the io map and the symbols */
+        fwrite("LOGS", 1, 4, f);
+        u32(1);
+        str("p =");
+    }
     if (argc > 2 && strstr(argv[2], "iomap")) {
         /* optional io-map section: entries in ascending template order; per signal {offset, #dims, dims.., element size, bus id} */
         fwrite("IOMP", 1, 4, f);

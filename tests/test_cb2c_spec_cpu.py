@@ -13,7 +13,7 @@ from circom_b200.witness_calculator import Circuit
 from tests.util import ROOT, hostsim, limbs_to_ints
 
 
-def dsl_conf():
+def dsl_conf(log=False):
     d = CircuitDesc("bn128")
     m2 = C.multiplier2(d)
 
@@ -31,6 +31,8 @@ def dsl_conf():
         t.assign_constrained(c["a"], x)
         t.assign_constrained(c["b"], y)
         t.assign_constrained(p, c["c"] + 1)
+        if log:
+            t.log("p =", p)
     d.set_main(d.template("Conf", (), build), "conf")
     return d
 
@@ -130,6 +132,26 @@ def test_io_map_section_from_the_spec(tmp_path):
     # template ids, then per template: #signals, {offset, #dims - 1, dims but the first, size, bus}
     assert io_map_bytes(d) == np.array([0, 1, 3, 0, 0, 1, 0, 1, 0, 1, 0, 2, 0, 1, 0,
                                         4, 0, 0, 1, 0, 2, 0, 1, 0, 3, 0, 1, 0, 4, 0, 1, 0], dtype="<u4").tobytes()
+
+
+def test_log_ops_and_string_table_from_the_spec(tmp_path):
+    """LOG ops and the LOGS section written from the spec by the C writer equal the DSL's (alone and with the two other
+    optional sections behind them); the text comes out as the reference prints it"""
+    exe = str(tmp_path / "cb2c_conf")
+    subprocess.check_call(["gcc", "-O1", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "cb2c_writer", "cb2c_conf.c")])
+    d = dsl_conf(log=True)
+    out = str(tmp_path / "conf_log.cb2c")
+    subprocess.check_call([exe, out, "log"])
+    blob = open(out, "rb").read()
+    assert blob == d.to_bytes() and b"LOGS" in blob
+    d.mark_mixed_array(*d.templates)
+    subprocess.check_call([exe, out, "log+iomap+sym"])
+    assert open(out, "rb").read() == d.to_bytes(symbols=True)
+    c = Circuit(blob, host_only=True)
+    from oracle.ir_eval import evaluate
+    sig = evaluate(d, {"x": 3, "y": 11})
+    from tests.util import ints_to_limbs
+    assert c.format_log(ints_to_limbs([sig[k] for k in c.witness2signal().astype(np.int64)])) == "p = 34\n"
 
 
 def test_rust_producer_numbers_match_the_format():

@@ -6,7 +6,10 @@
 // <output>.0.wtns, <output>.1.wtns, ...).  Input handling follows loadJson / qualify_input /
 // json2FrElements (main.cpp:126-286): nested objects and arrays of objects give qualified names
 // `a.b[i].c`, values are decimal / 0x / 0b / 0o strings or JSON integers, reduced modulo the prime.
+#include <algorithm>
 #include <cstdio>
+#include <dirent.h>
+#include <sys/stat.h>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -182,7 +185,7 @@ void qualify(const std::string &prefix, const JValue &in, std::vector<std::pair<
 
 int main(int argc, char **argv) {
     if (argc != 4) {
-        fprintf(stderr, "Usage: %s <circuit.cb2c> <input.json> <output.wtns>\n", argv[0]);
+        fprintf(stderr, "Usage: %s <circuit.cb2c> <input.json | directory of *.json> <output.wtns | output directory>\n", argv[0]);
         return 1;
     }
     try {
@@ -195,16 +198,44 @@ int main(int argc, char **argv) {
         int prime_id = 0;
         CK(cw_circuit_prime(c, &prime_id, nullptr));
         cw::FieldParams F = cw::make_field(prime_id);
-        std::ifstream f(argv[2]);
-        if (!f) throw std::runtime_error(std::string("cannot open ") + argv[2]);
-        std::stringstream ss;
-        ss << f.rdbuf();
-        std::string text = ss.str();
-        JValue root = JParser(text).parse();
+        auto slurp = [](const std::string &path) {
+            std::ifstream f(path);
+            if (!f) throw std::runtime_error("cannot open " + path);
+            std::stringstream ss;
+            ss << f.rdbuf();
+            return ss.str();
+        };
+        // <input.json>: one input object, or an array of them (a batch: outputs <output.wtns>.<i>.wtns); or a DIRECTORY of
+        // *.json files, one input each, taken in name order (outputs <output dir>/<name>.wtns)
+        std::vector<JValue> roots;
+        std::vector<std::string> out_names;
         std::vector<const JValue *> instances;
-        bool is_batch = root.kind == JValue::Array;
-        if (is_batch) for (const JValue &e : root.arr) instances.push_back(&e);
-        else instances.push_back(&root);
+        bool is_batch = false;
+        struct stat sb;
+        const bool is_dir = stat(argv[2], &sb) == 0 && S_ISDIR(sb.st_mode);
+        if (is_dir) {
+            std::vector<std::string> names;
+            if (DIR *dp = opendir(argv[2])) {
+                while (struct dirent *e = readdir(dp)) {
+                    const std::string n = e->d_name;
+                    if (n.size() > 5 && n.compare(n.size() - 5, 5, ".json") == 0) names.push_back(n);
+                }
+                closedir(dp);
+            }
+            std::sort(names.begin(), names.end());
+            roots.reserve(names.size());
+            for (const std::string &n : names) {
+                roots.push_back(JParser(slurp(std::string(argv[2]) + "/" + n)).parse());
+                out_names.push_back(std::string(argv[3]) + "/" + n.substr(0, n.size() - 5) + ".wtns");
+            }
+            for (const JValue &r : roots) instances.push_back(&r);
+            mkdir(argv[3], 0777);
+        } else {
+            roots.push_back(JParser(slurp(argv[2])).parse());
+            is_batch = roots[0].kind == JValue::Array;
+            if (is_batch) for (const JValue &e : roots[0].arr) instances.push_back(&e);
+            else instances.push_back(&roots[0]);
+        }
         if (instances.empty()) throw std::runtime_error("no inputs");
         cw_batch *b = nullptr;
         CK(cw_batch_create(c, (uint32_t)instances.size(), 0, &b));
@@ -246,7 +277,8 @@ int main(int argc, char **argv) {
                 }
             }
             std::string out = argv[3];
-            if (is_batch) out += "." + std::to_string(i) + ".wtns";
+            if (is_dir) out = out_names[i];
+            else if (is_batch) out += "." + std::to_string(i) + ".wtns";
             CK(cw_batch_write_wtns(b, (uint32_t)i, out.c_str()));
         }
         cw_batch_destroy(b);

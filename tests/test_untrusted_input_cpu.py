@@ -147,6 +147,39 @@ def test_cli_rejects_pathological_json(tmp_path):
         assert r.returncode == 1 and needle in r.stderr, (text[:20], r.returncode, r.stderr[-200:])
 
 
+def test_cli_directory_of_inputs(tmp_path):
+    """`circom_cuda_witness circuit.cb2c <directory of *.json> <output directory>`: one input per file, taken in name order,
+    other files ignored; an empty directory is an error; a malformed file is reported.  (Without a GPU the run stops where
+    the batch is created - after every file has been read and parsed; on a B200 it writes <name>.wtns per input.)"""
+    import json
+    import os
+    import subprocess
+    from circom_b200 import build
+    cli = os.path.join(os.path.dirname(build.LIB), "circom_cuda_witness")
+    if not os.path.exists(cli):
+        pytest.skip("CLI not built")
+    d = CircuitDesc("bn128")
+    d.set_main(C.multiplier2(d))
+    cb = d.save(str(tmp_path / "m.cb2c"))
+    ind, outd = str(tmp_path / "ins"), str(tmp_path / "out")
+    os.mkdir(ind)
+    r = subprocess.run([cli, cb, ind, outd], capture_output=True)
+    assert r.returncode == 1 and b"no inputs" in r.stderr
+    for k in range(3):
+        json.dump({"a": str(k + 2), "b": "5"}, open(os.path.join(ind, "in%d.json" % k), "w"))
+    open(os.path.join(ind, "notes.txt"), "w").write("not an input")
+    r = subprocess.run([cli, cb, ind, outd], capture_output=True)
+    if r.returncode == 0:     # a GPU is present
+        for k in range(3):
+            raw = open(os.path.join(outd, "in%d.wtns" % k), "rb").read()
+            assert int.from_bytes(raw[76 + 32:76 + 64], "little") == (k + 2) * 5
+    else:
+        assert b"no CUDA device" in r.stderr
+    open(os.path.join(ind, "zz.json"), "w").write('{"a": [1,')
+    r = subprocess.run([cli, cb, ind, outd], capture_output=True)
+    assert r.returncode == 1 and b"JSON" in r.stderr
+
+
 def test_hostile_input_name_table_and_function_bodies():
     """(signal id, size) of a main-input name and every register / array base / jump target / opcode of a function
     body come from the file: out-of-range values used to reach host and device memory unchecked"""

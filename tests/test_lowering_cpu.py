@@ -40,6 +40,7 @@ CIRCUITS = {
                             "b": r.choice([0, 1, r.randrange(1, 2**32), 2 * 3 * 5 * 7 * r.randrange(1, 100000)])}),
     # a component array of mixed templates (io map in the description) and a load at a run-time address (expanded by the producer)
     "mixed_array": (lambda d: C.mixed_array(d), lambda r, q: {"a": [r.randrange(q) for _ in range(3)], "b": r.choice([0, 1, r.randrange(q)])}),
+    "logging": (lambda d: C.logging(d), lambda r, q: {"a": r.choice([0, 1, q - 1, r.randrange(q)]), "b": r.randrange(q)}),   # log() calls: no tape ops
     "table_lookup8": (lambda d: C.table_lookup(d, 8), lambda r, q: {"table": [r.choice([0, 1, q - 1, r.randrange(q)]) for _ in range(8)],
                                                                      "sel": r.randrange(8)}),
     # the bench circuit's BigMultModP with its quotient / remainder hints computed by a long_div-style function
